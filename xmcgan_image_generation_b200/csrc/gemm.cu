@@ -1,0 +1,637 @@
+// tcgen05 implicit-GEMM kernels (sm_100a): forward/dgrad convolution + dense + batched GEMM (K-major operands),
+// and weight-gradient / A^T B GEMM (pixel-major operands, split-K).
+//
+// Structure of both kernels: one CTA per SM, 6 warps:
+//   warp 0      : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
+//   warp 1      : MMA issuer    (one elected lane issues tcgen05.mma, tcgen05.commit releases smem / signals epilogue)
+//   warps 2..5  : epilogue      (tcgen05.ld TMEM -> registers -> fused bias/mask/residual/relu -> global)
+// SAME padding, image borders, ragged M/N/K edges and channel counts that are not a multiple of 64 are all handled
+// by TMA out-of-bounds zero fill; nothing is ever im2col'ed in memory.
+#include <cudaTypedefs.h>
+#include <string.h>
+#include "common.h"
+#include "ptx.cuh"
+
+namespace xmc {
+
+constexpr int kStages = 4;
+constexpr int kABytes = 16384;  // 128 rows x 64 bf16
+constexpr int kBBytes = 32768;  // up to 256 rows x 64 bf16
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kBarBytes = 256;
+constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // + slack for 1024B alignment
+constexpr int kThreads = 192;
+constexpr int kTmemCols = 512;
+
+struct FwdParams {
+  int tiles_w, tiles_h, tiles_n;
+  int tw, th, tn;
+  int n_tiles, BN;
+  int KH, KW, pad_h, pad_w, C, cchunks;
+  int N, H, W, Cout;
+  int batched;
+  uint32_t stage_tx_bytes;
+  uint32_t idesc;
+  void* out;
+  int out_dtype, ldOut;
+  const float* bias;
+  const bf16* residual;
+  const bf16* mask;
+  int ldRes, ldMask, res_shift, relu;
+  float alpha;
+  int vec_ok;
+};
+
+struct WgradParams {
+  int chunks_w, chunks_h, chunks_n;  // pixel-chunk grid (K dimension)
+  int tw, th, tn;
+  int total_chunks, chunks_per_split, ksplit;
+  int n_tiles, BN, nslabs;
+  int KW, pad_h, pad_w;
+  int Ca, Cb;
+  int batched;
+  uint32_t slab_bytes;  // bytes one TMA box writes
+  uint32_t idesc;
+  void* out;
+  int out_mode, ldOut;
+  long long out_tap_stride, out_batch_stride;
+  float alpha;
+  int vec_ok;
+};
+
+__device__ __forceinline__ uint8_t* align_1024(uint8_t* p) {
+  return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~static_cast<uintptr_t>(1023));
+}
+
+__device__ __forceinline__ float bf16_bits_to_float(uint32_t h) { return __uint_as_float(h << 16); }
+
+__device__ __forceinline__ void load16_bf16(const bf16* p, bool vec, int nvalid, float* f) {
+  if (vec) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = __ldg(q), b = __ldg(q + 1);
+    uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      f[2 * i] = bf16_bits_to_float(w[i] & 0xFFFFu);
+      f[2 * i + 1] = bf16_bits_to_float(w[i] >> 16);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = (i < nvalid) ? __bfloat162float(p[i]) : 0.f;
+  }
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// =====================================================================================================================
+// Forward / dgrad / dense / batched GEMM:  D[pixels, Cout] = sum_taps A_tap[pixels, C] * B[Cout, tap*C + c]
+// =====================================================================================================================
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_1024(smem_raw);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar_base = sbase + kStages * kStageBytes;
+  // barrier layout: full[kStages], empty[kStages], tfull[2], tempty[2], then tmem pointer
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + kStages * kStageBytes + 8 * (2 * kStages + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_ptr_smem), kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int total_tiles = m_tiles * p.n_tiles;
+  const int taps = p.KH * p.KW;
+  const int kiters = taps * p.cchunks;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+        const int iw = mt % p.tiles_w;
+        const int ih = (mt / p.tiles_w) % p.tiles_h;
+        const int in = mt / (p.tiles_w * p.tiles_h);
+        const int w0 = iw * p.tw, h0 = ih * p.th, n0 = in * p.tn;
+        for (int tap = 0; tap < taps; ++tap) {
+          const int kh = tap / p.KW, kw = tap - kh * p.KW;
+          for (int c = 0; c < p.cchunks; ++c) {
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            mbar_arrive_expect_tx(full_bar(stage), p.stage_tx_bytes);
+            const uint32_t sa = sbase + stage * kStageBytes;
+            tma_load_4d(sa, &tmA, full_bar(stage), c * 64, w0 + kw - p.pad_w, h0 + kh - p.pad_h, n0);
+            tma_load_3d(sa + kABytes, &tmB, full_bar(stage), tap * p.C + c * 64, nt * p.BN, p.batched ? n0 : 0);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * 256;
+      for (int k = 0; k < kiters; ++k) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = sbase + stage * kStageBytes;
+          const uint64_t adesc = make_smem_desc(sa, 16, 1024);
+          const uint64_t bdesc = make_smem_desc(sa + kABytes, 16, 1024);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            // advance 16 K-elements = 32 bytes inside the 128B swizzle row: +2 in the (addr>>4) field
+            umma_bf16(d_tmem, adesc + 2 * j, bdesc + 2 * j, p.idesc, (k > 0 || j > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));
+          if (k == kiters - 1) umma_commit(tfull_bar(acc));
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else {
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+      const int iw = mt % p.tiles_w;
+      const int ih = (mt / p.tiles_w) % p.tiles_h;
+      const int in = mt / (p.tiles_w * p.tiles_h);
+      const int r = q * 32 + lane;
+      const int rw = r % p.tw, rh = (r / p.tw) % p.th, rn = r / (p.tw * p.th);
+      const int w = iw * p.tw + rw, h = ih * p.th + rh, n = in * p.tn + rn;
+      const bool row_ok = (rn < p.tn) && (n < p.N) && (h < p.H) && (w < p.W);
+      const long long pix = ((long long)n * p.H + h) * p.W + w;
+      long long rpix = 0;
+      if (p.residual) {
+        const int Hs = p.H >> p.res_shift, Ws = p.W >> p.res_shift;
+        rpix = ((long long)n * Hs + (h >> p.res_shift)) * Ws + (w >> p.res_shift);
+      }
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
+      for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_addr + c0, v);
+        tmem_ld_wait();
+        const int col = nt * p.BN + c0;
+        if (row_ok && col < p.Cout) {
+          const int nvalid = min(16, p.Cout - col);
+          const bool vec = p.vec_ok && nvalid == 16;
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
+          if (p.bias) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (i < nvalid) f[i] += __ldg(p.bias + col + i);
+          }
+          if (p.mask) {
+            float m[16];
+            load16_bf16(p.mask + pix * p.ldMask + col, vec, nvalid, m);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = (m[i] > 0.f) ? f[i] : 0.f;
+          }
+          if (p.residual) {
+            float m[16];
+            load16_bf16(p.residual + rpix * p.ldRes + col, vec, nvalid, m);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] += m[i];
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+          }
+          if (p.out_dtype == 0) {
+            bf16* o = reinterpret_cast<bf16*>(p.out) + pix * p.ldOut + col;
+            if (vec) {
+              uint4 a, b;
+              a.x = pack_bf16x2(f[0], f[1]);   a.y = pack_bf16x2(f[2], f[3]);
+              a.z = pack_bf16x2(f[4], f[5]);   a.w = pack_bf16x2(f[6], f[7]);
+              b.x = pack_bf16x2(f[8], f[9]);   b.y = pack_bf16x2(f[10], f[11]);
+              b.z = pack_bf16x2(f[12], f[13]); b.w = pack_bf16x2(f[14], f[15]);
+              reinterpret_cast<uint4*>(o)[0] = a;
+              reinterpret_cast<uint4*>(o)[1] = b;
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (i < nvalid) o[i] = __float2bfloat16(f[i]);
+            }
+          } else {
+            float* o = reinterpret_cast<float*>(p.out) + pix * p.ldOut + col;
+            if (vec) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                reinterpret_cast<float4*>(o)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (i < nvalid) o[i] = f[i];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// =====================================================================================================================
+// Weight gradient:  D[Ca-tile(128), Cb-tile(BN)] = sum_{pixel chunks} A[pixels(+tap shift), ca]^T * B[pixels, cb]
+// Both operands arrive pixel-major (64-channel slabs of [pixels][128B] rows) and are consumed as MN-major UMMA tiles.
+// grid = (m_tiles*n_tiles, taps, batch*ksplit); one output tile per CTA.
+// =====================================================================================================================
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_1024(smem_raw);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar_base = sbase + kStages * kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  const uint32_t tfull_bar = bar_base + 8u * (2 * kStages);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + kStages * kStageBytes + 8 * (2 * kStages + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // A pixel chunk can hold fewer than 64 pixels (tiny tensors); rows the TMA never writes must read as zero
+  // because they are part of the reduction dimension.
+  if (p.slab_bytes < 8192) {
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    for (int i = threadIdx.x; i < kStages * kStageBytes / 16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_ptr_smem), 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int mt = blockIdx.x / p.n_tiles, nt = blockIdx.x - mt * p.n_tiles;
+  const int tap = blockIdx.y;
+  const int kh = tap / p.KW, kw = tap - kh * p.KW;
+  const int bz = blockIdx.z / p.ksplit, split = blockIdx.z - bz * p.ksplit;
+  const int j0 = split * p.chunks_per_split;
+  const int j1 = min(p.total_chunks, j0 + p.chunks_per_split);
+  const int m0 = mt * 128, n_off = nt * p.BN;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx = (2 + p.nslabs) * p.slab_bytes;
+      for (int j = j0; j < j1; ++j) {
+        const int iw = j % p.chunks_w;
+        const int ih = (j / p.chunks_w) % p.chunks_h;
+        const int in = p.batched ? bz : j / (p.chunks_w * p.chunks_h);
+        const int w0 = iw * p.tw, h0 = ih * p.th, n0 = p.batched ? bz : in * p.tn;
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        mbar_arrive_expect_tx(full_bar(stage), tx);
+        const uint32_t sa = sbase + stage * kStageBytes;
+        tma_load_4d(sa, &tmA, full_bar(stage), m0, w0 + kw - p.pad_w, h0 + kh - p.pad_h, n0);
+        tma_load_4d(sa + 8192, &tmA, full_bar(stage), m0 + 64, w0 + kw - p.pad_w, h0 + kh - p.pad_h, n0);
+        for (int s = 0; s < p.nslabs; ++s)
+          tma_load_4d(sa + kABytes + s * 8192, &tmB, full_bar(stage), n_off + s * 64, w0, h0, n0);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int j = j0; j < j1; ++j) {
+      mbar_wait(full_bar(stage), phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = sbase + stage * kStageBytes;
+        // MN-major SW128: LBO = byte distance between 64-channel slabs, SBO = distance between 8-pixel groups.
+        const uint64_t adesc = make_smem_desc(sa, 8192, 1024);
+        const uint64_t bdesc = make_smem_desc(sa + kABytes, 8192, 1024);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          // 16 pixels (K) per MMA = two 8-pixel groups = 2048 bytes: +128 in the (addr>>4) field
+          umma_bf16(tmem_base, adesc + 128 * s, bdesc + 128 * s, p.idesc, (j > j0 || s > 0) ? 1u : 0u);
+        }
+        umma_commit(empty_bar(stage));
+        if (j == j1 - 1) umma_commit(tfull_bar);
+      }
+      __syncwarp();
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = m0 + q * 32 + lane;
+    const bool row_ok = m < p.Ca;
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const long long obase = (long long)bz * p.out_batch_stride + (long long)tap * p.out_tap_stride +
+                            (long long)m * p.ldOut;
+    for (int c0 = 0; c0 < p.BN; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(t_addr + c0, v);
+      tmem_ld_wait();
+      const int col = n_off + c0;
+      if (row_ok && col < p.Cb) {
+        const int nvalid = min(16, p.Cb - col);
+        const bool vec = p.vec_ok && nvalid == 16;
+        float f[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
+        if (p.out_mode == 2) {
+          bf16* o = reinterpret_cast<bf16*>(p.out) + obase + col;
+          if (vec) {
+            uint4 a, b;
+            a.x = pack_bf16x2(f[0], f[1]);   a.y = pack_bf16x2(f[2], f[3]);
+            a.z = pack_bf16x2(f[4], f[5]);   a.w = pack_bf16x2(f[6], f[7]);
+            b.x = pack_bf16x2(f[8], f[9]);   b.y = pack_bf16x2(f[10], f[11]);
+            b.z = pack_bf16x2(f[12], f[13]); b.w = pack_bf16x2(f[14], f[15]);
+            reinterpret_cast<uint4*>(o)[0] = a;
+            reinterpret_cast<uint4*>(o)[1] = b;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (i < nvalid) o[i] = __float2bfloat16(f[i]);
+          }
+        } else {
+          float* o = reinterpret_cast<float*>(p.out) + obase + col;
+          if (p.out_mode == 1) {
+            if (vec) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                reinterpret_cast<float4*>(o)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (i < nvalid) o[i] = f[i];
+            }
+          } else {
+            if (vec) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4 * i), "f"(f[4 * i]),
+                             "f"(f[4 * i + 1]), "f"(f[4 * i + 2]), "f"(f[4 * i + 3])
+                             : "memory");
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (i < nvalid) atomicAdd(o + i, f[i]);
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
+// =====================================================================================================================
+// Host side
+// =====================================================================================================================
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess) {
+      set_cuda_error(e != cudaSuccess ? e : cudaErrorUnknown);
+      return nullptr;
+    }
+    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  }
+  return fn;
+}
+
+// bf16 tensor map, SWIZZLE_128B, zero OOB fill. dims/box innermost first; strides in bytes for dims 1..rank-1.
+static int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                     const uint32_t* box) {
+  PFN_cuTensorMapEncodeTiled_v12000 fn = get_encode_fn();
+  if (!fn) return XMC_ECUDA;
+  cuuint64_t gdim[5], gstr[5];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+  }
+  for (int i = 0; i < rank - 1; ++i) gstr[i] = strides[i];
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_cuda_error(cudaErrorInvalidValue);
+    return XMC_ECUDA;
+  }
+  return XMC_OK;
+}
+
+// N-tile width: multiple of 16 in [16,256] minimising the padded width, ties -> wider tile.
+static int pick_bn(int n) {
+  if (n <= 256) return ceil_div(n, 16) * 16;
+  int best = 256, best_pad = ceil_div(n, 256) * 256;
+  for (int bn = 240; bn >= 128; bn -= 16) {
+    int pad = ceil_div(n, bn) * bn;
+    if (pad < best_pad) { best_pad = pad; best = bn; }
+  }
+  return best;
+}
+
+static bool g_attr_set_fwd = false, g_attr_set_wgrad = false;
+
+}  // namespace xmc
+
+using namespace xmc;
+
+extern "C" int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* wk, const float* bias,
+                              const void* residual, const void* mask, void* y, void* stream) {
+  if (!d || !x || !wk || !y) return XMC_EINVAL;
+  if (d->N < 1 || d->H < 1 || d->W < 1 || d->C < 1 || d->Cout < 1 || d->KH < 1 || d->KW < 1) return XMC_EINVAL;
+  if ((d->ldA % 8) || (d->ldB % 8) || d->ldA < d->C || d->ldB < d->KH * d->KW * d->C) return XMC_EINVAL;
+  if (d->C % 8) return XMC_EINVAL;
+  if (!aligned16(x) || !aligned16(wk)) return XMC_EALIGN;
+  if (d->batched && (d->strideB_batch % 8)) return XMC_EINVAL;
+
+  FwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = d->N; p.H = d->H; p.W = d->W; p.C = d->C; p.Cout = d->Cout;
+  p.KH = d->KH; p.KW = d->KW; p.pad_h = d->pad_h; p.pad_w = d->pad_w;
+  p.cchunks = ceil_div(d->C, 64);
+  p.batched = d->batched;
+  p.tw = d->W < 128 ? d->W : 128;
+  p.th = 128 / p.tw; if (p.th > d->H) p.th = d->H;
+  p.tn = d->batched ? 1 : 128 / (p.tw * p.th); if (p.tn > d->N) p.tn = d->N; if (p.tn < 1) p.tn = 1;
+  p.tiles_w = ceil_div(d->W, p.tw);
+  p.tiles_h = ceil_div(d->H, p.th);
+  p.tiles_n = ceil_div(d->N, p.tn);
+  p.BN = pick_bn(d->Cout);
+  p.n_tiles = ceil_div(d->Cout, p.BN);
+  p.idesc = make_idesc_bf16(128, p.BN, 0, 0);
+  p.stage_tx_bytes = (uint32_t)(64 * p.tw * p.th * p.tn * 2 + 64 * p.BN * 2);
+  p.out = y; p.out_dtype = d->out_dtype; p.ldOut = d->ldOut;
+  p.bias = bias; p.residual = (const bf16*)residual; p.mask = (const bf16*)mask;
+  p.ldRes = d->ldRes; p.ldMask = d->ldMask; p.res_shift = d->res_shift; p.relu = d->relu;
+  p.alpha = d->alpha;
+  bool vec = aligned16(y) && (d->out_dtype == 0 ? (d->ldOut % 8 == 0) : (d->ldOut % 4 == 0));
+  if (residual) vec = vec && aligned16(residual) && (d->ldRes % 8 == 0);
+  if (mask) vec = vec && aligned16(mask) && (d->ldMask % 8 == 0);
+  p.vec_ok = vec ? 1 : 0;
+
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[4] = {(uint64_t)d->C, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
+    uint64_t str[3] = {(uint64_t)d->ldA * 2, (uint64_t)d->ldA * 2 * d->W, (uint64_t)d->ldA * 2 * d->W * d->H};
+    uint32_t box[4] = {64, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.tn};
+    int r = make_tmap(&tmA, x, 4, dims, str, box);
+    if (r) return r;
+  }
+  {
+    const int nb = d->batched ? d->N : 1;
+    uint64_t dims[3] = {(uint64_t)d->KH * d->KW * d->C, (uint64_t)d->Cout, (uint64_t)nb};
+    uint64_t sb = d->batched ? (uint64_t)d->strideB_batch * 2 : (uint64_t)d->ldB * 2 * d->Cout;
+    uint64_t str[2] = {(uint64_t)d->ldB * 2, sb};
+    uint32_t box[3] = {64, (uint32_t)p.BN, 1};
+    int r = make_tmap(&tmB, wk, 3, dims, str, box);
+    if (r) return r;
+  }
+  if (!g_attr_set_fwd) {
+    XMC_CUDA_CHECK(cudaFuncSetAttribute(gemm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    g_attr_set_fwd = true;
+  }
+  const int total = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
+  const int grid = total < num_sms() ? total : num_sms();
+  gemm_fwd_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(tmA, tmB, p);
+  XMC_LAUNCH_CHECK();
+  return XMC_OK;
+}
+
+extern "C" int xmc_conv2d_wgrad(const XmcWgradDesc* d, const void* xa, const void* xb, void* dw, void* stream) {
+  if (!d || !xa || !xb || !dw) return XMC_EINVAL;
+  if (d->N < 1 || d->H < 1 || d->W < 1 || d->Ca < 1 || d->Cb < 1 || d->KH < 1 || d->KW < 1) return XMC_EINVAL;
+  if ((d->ldA % 8) || (d->ldB % 8) || d->ldA < d->Ca || d->ldB < d->Cb) return XMC_EINVAL;
+  if ((d->Ca % 8) || (d->Cb % 8)) return XMC_EINVAL;
+  if (!aligned16(xa) || !aligned16(xb)) return XMC_EALIGN;
+
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.tw = d->W < 64 ? d->W : 64;
+  p.th = 64 / p.tw; if (p.th > d->H) p.th = d->H;
+  p.tn = d->batched ? 1 : 64 / (p.tw * p.th); if (p.tn > d->N) p.tn = d->N; if (p.tn < 1) p.tn = 1;
+  p.chunks_w = ceil_div(d->W, p.tw);
+  p.chunks_h = ceil_div(d->H, p.th);
+  p.chunks_n = d->batched ? 1 : ceil_div(d->N, p.tn);
+  p.total_chunks = p.chunks_w * p.chunks_h * p.chunks_n;
+  p.BN = pick_bn(d->Cb);
+  p.n_tiles = ceil_div(d->Cb, p.BN);
+  p.nslabs = ceil_div(p.BN, 64);
+  const int m_tiles = ceil_div(d->Ca, 128);
+  const int taps = d->KH * d->KW;
+  const int nbatch = d->batched ? d->N : 1;
+  const int base_ctas = m_tiles * p.n_tiles * taps * nbatch;
+  int ksplit = 1;
+  if (d->out_mode == 0) {
+    // enough CTAs for ~2 waves, but keep at least 8 chunks (512 pixels) per CTA
+    ksplit = ceil_div(2 * num_sms(), base_ctas);
+    const int max_split = p.total_chunks / 8 > 0 ? p.total_chunks / 8 : 1;
+    if (ksplit > max_split) ksplit = max_split;
+    if (ksplit < 1) ksplit = 1;
+  }
+  p.chunks_per_split = ceil_div(p.total_chunks, ksplit);
+  p.ksplit = ceil_div(p.total_chunks, p.chunks_per_split);
+  p.KW = d->KW; p.pad_h = d->pad_h; p.pad_w = d->pad_w;
+  p.Ca = d->Ca; p.Cb = d->Cb; p.batched = d->batched;
+  p.slab_bytes = (uint32_t)(64 * p.tw * p.th * p.tn * 2);
+  p.idesc = make_idesc_bf16(128, p.BN, 1, 1);
+  p.out = dw; p.out_mode = d->out_mode; p.ldOut = d->ldOut;
+  p.out_tap_stride = d->out_tap_stride; p.out_batch_stride = d->out_batch_stride;
+  p.alpha = d->alpha;
+  const int unit = d->out_mode == 2 ? 8 : 4;
+  p.vec_ok = (aligned16(dw) && d->ldOut % unit == 0 && d->out_tap_stride % unit == 0 &&
+              d->out_batch_stride % unit == 0) ? 1 : 0;
+
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[4] = {(uint64_t)d->Ca, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
+    uint64_t str[3] = {(uint64_t)d->ldA * 2, (uint64_t)d->ldA * 2 * d->W, (uint64_t)d->ldA * 2 * d->W * d->H};
+    uint32_t box[4] = {64, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.tn};
+    int r = make_tmap(&tmA, xa, 4, dims, str, box);
+    if (r) return r;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)d->Cb, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
+    uint64_t str[3] = {(uint64_t)d->ldB * 2, (uint64_t)d->ldB * 2 * d->W, (uint64_t)d->ldB * 2 * d->W * d->H};
+    uint32_t box[4] = {64, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.tn};
+    int r = make_tmap(&tmB, xb, 4, dims, str, box);
+    if (r) return r;
+  }
+  if (!g_attr_set_wgrad) {
+    XMC_CUDA_CHECK(cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    g_attr_set_wgrad = true;
+  }
+  dim3 grid(m_tiles * p.n_tiles, taps, nbatch * p.ksplit);
+  gemm_wgrad_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(tmA, tmB, p);
+  XMC_LAUNCH_CHECK();
+  return XMC_OK;
+}

@@ -1,0 +1,41 @@
+// Library-level plumbing of libxmc.so: error strings, device queries.
+#include <stdio.h>
+#include <string.h>
+#include "common.h"
+
+namespace xmc {
+
+static thread_local char g_err[256] = "";
+
+void set_cuda_error(cudaError_t e) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", cudaGetErrorName(e), cudaGetErrorString(e));
+  (void)cudaGetLastError();  // clear the sticky-less error state
+}
+
+int num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
+    sms = v;
+  }
+  return sms;
+}
+
+}  // namespace xmc
+
+extern "C" const char* xmc_strerror(int code) {
+  switch (code) {
+    case XMC_OK: return "ok";
+    case XMC_EINVAL: return "invalid descriptor or unsupported shape";
+    case XMC_ECUDA: return "CUDA call failed (see xmc_last_cuda_error)";
+    case XMC_EALIGN: return "pointer or pitch not 16-byte aligned";
+    default: return "unknown error";
+  }
+}
+
+extern "C" const char* xmc_last_cuda_error(void) { return xmc::g_err; }
+extern "C" int xmc_version(void) { return 100; }
+extern "C" int xmc_num_sms(void) { return xmc::num_sms(); }
