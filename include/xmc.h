@@ -79,6 +79,176 @@ typedef struct {
 
 int xmc_conv2d_wgrad(const XmcWgradDesc* d, const void* xa, const void* xb, void* dw, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Conditional batch normalisation (train mode), fused with relu and nearest 2x upsampling.
+ * Replaces flax nn.BatchNorm(use_scale=False,use_bias=False) + `x*(gamma+1)+beta` + relu + common.upsample
+ * (xmcgan/libml/layers.py:256-257,271-272; xmcgan/nets/common.py:48-51,148-151,175-178).
+ * gamma/beta for pixel (n,h,w) are read from row (n*Hc + h/(H/Hc))*Hc + w/(W/Hc) of the bf16 matrix gb at column
+ * offsets goff / boff: Hc=1 is ConditionalBatchNorm, Hc=cond_size(16) is LocalConditionalBatchNorm with its 1x1
+ * convolutions evaluated once at 16x16 (a 1x1 conv commutes with nearest upsampling).
+ */
+typedef struct {
+  int N, H, W, C;  /* dims of x (before upsampling); H == W, H = Hc * 2^s */
+  int Hc;
+  int ldG, goff, boff;
+  int relu, upsample;
+} XmcBnDesc;
+
+int xmc_bn_stats(const void* x, long long P, int C, int ld, float* sums /*[2C], zeroed by caller*/, void* stream);
+int xmc_bn_finalize(const float* sums, long long P, int C, float eps, float momentum, const float* ra_mean,
+                    const float* ra_var, float* new_ra_mean, float* new_ra_var, float* mean_rstd /*[2C]*/,
+                    void* stream);
+int xmc_bn_eval_stats(const float* ra_mean, const float* ra_var, int C, float eps, float* mean_rstd, void* stream);
+int xmc_bn_apply(const XmcBnDesc* d, const void* x, const float* mean_rstd, const void* gb, void* y, void* stream);
+/* backward, pass 1: dgb (fp32, same row/column layout as gb) = d(gamma), d(beta); sums[2C] (zeroed by caller) +=
+ * per-channel sum(dxhat), sum(dxhat*xhat). dy has the upsampled shape when d->upsample. */
+int xmc_bn_bwd_reduce(const XmcBnDesc* d, const void* dy, const void* x, const float* mean_rstd, const void* gb,
+                      float* dgb, float* sums, void* stream);
+/* backward, pass 2: dx = rstd*(dxhat - mean(dxhat) - xhat*mean(dxhat*xhat)) */
+int xmc_bn_bwd_apply(const XmcBnDesc* d, const void* dy, const void* x, const float* mean_rstd, const void* gb,
+                     const float* sums, void* dx, void* stream);
+
+/* 2x2/2 pooling: out = scale * sum_{2x2}(a (+ b)) (+ low); optional out_relu = relu(out). scale=0.25 is
+ * common.dsample (xmcgan/nets/common.py:23-45,54-55); scale=1 is the transpose of common.upsample.
+ * a, b: [N,2*Hout,2*Wout,C]; low: [N,Hout,Wout,C]. */
+int xmc_pool2(const void* a, const void* b, const void* low, int N, int Hout, int Wout, int C, float scale, void* out,
+              void* out_relu, void* stream);
+/* transpose of pool2: g[n,2h+i,2w+j,c] = scale * dout[n,h,w,c] */
+int xmc_unpool2(const void* dout, int N, int Hin, int Win, int C, float scale, void* g, void* stream);
+/* out[c] += sum_p x[p][c] (bias gradients) */
+int xmc_colsum(const void* x, long long P, int C, int ld, float* out, void* stream);
+/* x_pool[n][c] = sum_hw relu(x[n,hw,c]) (xmcgan/nets/xmc_net.py:97-98) and its backward */
+int xmc_relu_sumhw(const void* x, int N, int HW, int C, float* out, void* stream);
+int xmc_relu_sumhw_bwd(const void* x, const float* dout, int N, int HW, int C, void* dx, void* stream);
+int xmc_cast_f32_to_bf16(const float* src, long long rows, int cols, long long ld_src, void* dst, long long ld_dst,
+                         void* stream);
+int xmc_cast_bf16_to_f32(const void* src, long long rows, int cols, long long ld_src, float* dst, long long ld_dst,
+                         int accumulate, void* stream);
+/* dst[b*reps + r][c] = src[b][c]  (jnp.tile of global_cond, xmc_net.py:233-234) and its transpose */
+int xmc_bcast_rows(const void* src, int B, int reps, int cols, int ld_src, void* dst, int ld_dst, void* stream);
+int xmc_sum_rows(const void* src, int B, int reps, int cols, int ld_src, float* dst, int ld_dst, int accumulate,
+                 void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Parameter-side multi-tensor kernels. Tables live in device memory; offsets index flat fp32 buffers.
+ */
+typedef struct {
+  long long w_off;        /* kernel [taps][cin][cout] (HWIO / [in,out]) inside the flat fp32 parameter buffer */
+  long long wk_fwd_off;   /* bf16 arena offset of the [cout][taps*cin] forward copy, or -1 */
+  long long wk_dg_off;    /* bf16 arena offset of the [cin][flip(tap)*cout+co] dgrad copy, or -1 */
+  long long bias_off;     /* bias inside the parameter buffer, or -1 */
+  long long bias_dst_off; /* destination inside the fp32 bias arena, or -1 */
+  int taps, cin, cout;
+  int ld_fwd, ld_dg;
+  int sn;                 /* spectral-norm slot, or -1 */
+  int tile_begin;         /* prefix sum of ceil(taps*cin/32)*ceil(cout/32) */
+  int reserved;
+} XmcPrepEntry;
+
+typedef struct {
+  long long w_off;        /* kernel viewed as [rows][cols] = [taps*cin][cout] */
+  long long t_off;        /* row-vector workspace offset (t = W u0^T) */
+  long long s_off;        /* column-vector workspace offset (s = t W) */
+  long long u_off;        /* offset of u0 inside the spectral_norm_stats buffers */
+  int rows, cols;
+  int row_block_begin;    /* prefix sum of ceil(rows/8) */
+  int col_tile_begin;     /* prefix sum of ceil(rows/256)*ceil(cols/32) */
+  int elem_block_begin;   /* prefix sum of ceil(rows*cols/2048) */
+  int reserved;
+} XmcSnEntry;
+
+/* One power-iteration step for every layer of the table (layers.py:94-101 / :211-221). scalars: float[4*n] =
+ * sum_t2 | norm_t | 1/(sigma+eps) | <dW,W>. Writes the new u0 to u0_new (old state is left untouched). */
+int xmc_sn_forward(const XmcSnEntry* table_dev, int n, float eps, const float* params, const float* u0, float* u0_new,
+                   float* t_ws, float* s_ws, long long s_ws_floats, float* scalars, int total_row_blocks,
+                   int total_col_tiles, void* stream);
+/* grads (holding d/dW~) -> d/dW in place: dW = dW~/s' - <dW~,W>/s'^2 * v0^T u1 (u1, v0 stop-gradient). */
+int xmc_sn_backward(const XmcSnEntry* table_dev, int n, const float* params, float* grads, const float* t_ws,
+                    const float* u0_new, float* scalars, int total_elem_blocks, void* stream);
+int xmc_prep_weights(const XmcPrepEntry* table_dev, int n, int total_tiles, const float* params,
+                     const float* sn_scalars, int n_sn, void* arena, float* bias_arena, void* stream);
+/* flax.optim.Adam.apply_gradient (weight_decay 0) in place on flat buffers, gradient pre-scaled by grad_scale
+ * (1/world after a sum all-reduce == lax.pmean); optional polyak EMA of the updated parameters
+ * (xmcgan/xmc_gan.py:172-177,252). bias_corr = 1 - beta^t. n must be a multiple of 4. */
+int xmc_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+             float bias_corr1, float bias_corr2, float grad_scale, float* ema, float ema_decay, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Row l2-normalisation xhat = x*rsqrt(max(sum x^2, eps)) (attention_lib.l2_normalize, attention_lib.py:30-33), one
+ * warp per row, and its backward dx = (dxhat - xhat<dxhat,xhat>)*invnorm. *_f32 flags select fp32 (1) or bf16 (0).
+ */
+int xmc_l2norm_rows(const void* x, int in_f32, long long rows, int D, long long ld_in, void* y, int out_f32,
+                    long long ld_out, float* invnorm, float eps, void* stream);
+int xmc_l2norm_rows_bwd(const void* dxhat, int g_f32, long long ld_g, const void* xhat, int x_f32, long long ld_x,
+                        const float* invnorm, long long rows, int D, void* dx, int out_f32, long long ld_o,
+                        int accumulate, void* stream);
+
+/* attention_lib.attention_for_g (attention_lib.py:194-219), fused QK^T - masked softmax over words - V, one warp per
+ * region: q bf16 [B*R][ld_q] (un-normalised regions), what fp32 [B][L][D] (l2-normalised words), max_len fp32 [B].
+ * Writes ctx bf16 [B*R][ld_ctx] and the attention weights attn fp32 [B*R][L]. bwd returns dq (words are data). */
+int xmc_attention_g_fwd(const void* q, int ld_q, const float* what, const float* max_len, int B, int R, int L, int D,
+                        float gamma, void* ctx, int ld_ctx, float* attn, void* stream);
+int xmc_attention_g_bwd(const void* dctx, int ld_dctx, const void* q, int ld_q, const float* what, const float* attn,
+                        int B, int R, int L, int D, float gamma, void* dq, int ld_dq, void* stream);
+
+/* Elementwise / reduction stages of attention_lib.word_loss (attention_lib.py:105-191); i image, j sentence, w word,
+ * r region, jw = j*L+w, BL = B*L, ldS = BL rounded up to 8. The three GEMM stages use xmc_conv2d_fwd/_wgrad.
+ *   wl_softmax : alpha[i][r][jw] = softmax_r(gamma1*S[i*R+r][jw]) (+ alphaT[i][jw][r]), both bf16
+ *   wl_cos     : cos[i][jw] = <W_jw, ctx[i][jw]>/(|W_jw||ctx|), cnorm = |ctx|     (winv = 1/|W_jw|)
+ *   wl_sim     : sim[j][i] = gamma3*LSE_{w<max_len[j]}(gamma2*cos)/gamma2, pw = the softmax weights of that LSE
+ *   wl_cos_bwd : dctx (bf16) from dsim[j][i];  wl_softmax_bwd: dS (bf16) from dalpha (fp32)
+ */
+int xmc_wl_softmax(const float* S, int B, int R, int BL, int ldS, float gamma1, void* alpha, void* alphaT,
+                   void* stream);
+int xmc_wl_softmax_bwd(const void* alpha, const float* dalpha, int B, int R, int BL, int ldS, float gamma1, void* dS,
+                       void* stream);
+int xmc_wl_cos(const float* ctx, long long ctx_batch_stride, const float* words, const float* winv, int B, int L,
+               int D, float* cosv, float* cnorm, void* stream);
+int xmc_wl_sim(const float* cosv, const float* max_len, int B, int L, float gamma2, float gamma3, float* sim, float* pw,
+               void* stream);
+int xmc_wl_cos_bwd(const float* dsim, const float* pw, const float* cosv, const float* cnorm, const float* ctx,
+                   long long ctx_batch_stride, const float* words, const float* winv, int B, int L, int D,
+                   float gamma3, void* dctx, long long dctx_batch_stride, void* stream);
+/* dst[c][r] = src[r][c] for r<rows, zero for rows <= r < ld_dst */
+int xmc_transpose_bf16(const void* src, int rows, int cols, int ld_src, void* dst, int ld_dst, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Loss heads. InfoNCE = l2norm_rows + small_gemm_nt (logits = scale*A B^T) + ce_sym, local-batch negatives only
+ * (attention_lib.contrastive_loss, attention_lib.py:46-79).
+ */
+int xmc_small_gemm_nt(const float* A, const float* B, int n, int m, int D, float scale, float* C, void* stream);
+/* out[i][f] (+)= scale * sum_j G(i,j) X[j][f], G(i,j) = transposed ? G[j][i] : G[i][j];  G is [n][m] ([m][n] if transposed) */
+int xmc_small_gemm_nn(const float* G, int transposed, const float* X, int n, int m, int D, float scale, float* out,
+                      int accumulate, void* stream);
+/* *loss_out = mean_i CE(row i) + mean_j CE(col j) with identity labels (losses.py:47-51); dlogits = weight*dloss/dlogits */
+int xmc_ce_sym(const float* logits, int n, float weight, float* loss_out, float* dlogits, void* stream);
+/* losses.hinge_loss (losses.py:30-35) on logit = [real(B); fake(B)] and the two cotangents */
+int xmc_hinge(const float* logit, int B, float* d_loss, float* g_loss, float* dlogit_d, float* dlogit_g, void* stream);
+/* projection-discriminator logit (xmc_net.py:97-104): out[n] = <xpool[n], w1*inv_sigma + emb[n%B]> + b1 */
+int xmc_proj_logit(const float* xpool, const float* w1, const float* inv_sigma, const float* b1, const float* emb,
+                   int N2, int B, int C, float* out, void* stream);
+int xmc_proj_logit_bwd(const float* dlogit, const float* xpool, const float* w1, const float* inv_sigma,
+                       const float* emb, int n0, int cnt, int B, int C, float* dxpool, int accumulate_x, float* dw1,
+                       float* db1, float* demb, void* stream);
+int xmc_colsum_f32(const float* x, int rows, int cols, int ld, float* out, void* stream);
+int xmc_axpy_f32(float* y, const float* x, float a, long long n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * 3-channel (image-side) convolutions: first discriminator block (common.py:125-133) and generator head
+ * (xmc_net.py:245-247). w is a bf16 [rows][ldw] K-major matrix from xmc_prep_weights.
+ */
+int xmc_conv_c3_in(const void* x, const void* w, int ldw, const float* bias, int N, int H, int W, int Cout, int KH,
+                   int KW, int relu, void* y, void* stream);
+/* mode 0: y fp32 (+= if accumulate); mode 1: y = (tanh(v)+1)/2 fp32 plus bf16 copy y_bf16 */
+int xmc_conv_c3_out(const void* x, const void* w, int ldw, const float* bias, int N, int H, int W, int Cin, int KH,
+                    int KW, int mode, int accumulate, float* y, void* y_bf16, void* stream);
+/* out[tap_o*s_tap + c3*s_c3 + c*s_c] += sum_p x3[p+shift(tap)][c3]*y[p][c], tap_o = flip ? taps-1-tap : tap */
+int xmc_wgrad_c3(const void* x3, const void* y, int N, int H, int W, int C, int KH, int KW, int flip, long long s_tap,
+                 int s_c3, int s_c, float* out, void* stream);
+int xmc_pool2_small(const void* a, int N, int Hout, int Wout, int C, float scale, void* out, void* stream);
+int xmc_unpool2_add_f32(const float* d, int N, int Hin, int Win, int C, float scale, float* g, void* stream);
+int xmc_tanh01_bwd(const float* dimg, const float* img, long long n, void* dpre, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,7 +14,9 @@ Every function cites the reference file:line it follows (paths relative to /root
 Precision policies: `Policy("float32")` computes everything in fp32 (the reference's `config.dtype="float32"` path).
 `Policy("bfloat16")` rounds activations and GEMM/conv weights to bf16 at the points where the reference's
 `config.dtype="bfloat16"` path stores bf16 tensors (conv/dense outputs, BatchNorm outputs), keeping fp32
-accumulation, fp32 statistics and fp32 losses; rounding uses a straight-through gradient.
+accumulation, fp32 statistics and fp32 losses; rounding uses a straight-through gradient. Where the B200 pipeline
+keeps MORE precision than the reference's bf16 graph (fp32 logit head, fp32 pre-tanh accumulator) the bf16 policy
+follows the pipeline; those spots are marked "B200 path" below.
 """
 import math
 from typing import Any, Dict, Tuple
@@ -165,22 +167,22 @@ def attention_for_g(region_feat, word_feat, gamma, mask=None):
 # ----------------------------------------------------------------------------------------------------------------------
 # flax.linen primitives (flax==0.3.3, not vendored) restated
 # ----------------------------------------------------------------------------------------------------------------------
-def conv2d(x, kernel, bias, policy=FP32):
+def conv2d(x, kernel, bias, policy=FP32, round_out=True):
   """flax nn.Conv, stride 1, padding SAME: x NHWC, kernel HWIO, both cast to dtype; output stored in dtype."""
   kh, kw = kernel.shape[0], kernel.shape[1]
   w = policy.q(kernel).permute(3, 2, 0, 1)
   y = F.conv2d(policy.q(x).permute(0, 3, 1, 2), w, padding=(kh // 2, kw // 2)).permute(0, 2, 3, 1)
   if bias is not None:
     y = y + bias
-  return policy.q(y)
+  return policy.q(y) if round_out else y
 
 
-def dense(x, kernel, bias, policy=FP32):
+def dense(x, kernel, bias, policy=FP32, round_out=True):
   """flax nn.Dense: kernel [in,out]."""
   y = policy.q(x) @ policy.q(kernel)
   if bias is not None:
     y = y + bias
-  return policy.q(y)
+  return policy.q(y) if round_out else y
 
 
 def batch_norm(x, stats, train, momentum=0.9, epsilon=1e-5, policy=FP32):
@@ -221,17 +223,17 @@ def spectral_normalize(kernel, u0, eps=1e-10):
   return (w / (sigma + eps)).reshape(shape), u1
 
 
-def spectral_conv(x, p, st, train, policy=FP32):
+def spectral_conv(x, p, st, train, policy=FP32, round_out=True):
   """layers.SpectralConv (layers.py:125-241). p = {kernel,bias}, st = {u0}. Returns (y, new_st)."""
   k, u1 = spectral_normalize(p["kernel"], st["u0"])
-  y = conv2d(x, k, p.get("bias"), policy)
+  y = conv2d(x, k, p.get("bias"), policy, round_out)
   return y, ({"u0": u1} if train else st)
 
 
-def spectral_dense(x, p, st, train, policy=FP32):
+def spectral_dense(x, p, st, train, policy=FP32, round_out=True):
   """layers.SpectralDense (layers.py:49-113)."""
   k, u1 = spectral_normalize(p["kernel"], st["u0"])
-  y = dense(x, k, p.get("bias"), policy)
+  y = dense(x, k, p.get("bias"), policy, round_out)
   return y, ({"u0": u1} if train else st)
 
 
@@ -261,25 +263,25 @@ class _Scope:
     node[self.path[-1]] = value
 
 
-def _conv_fn(scope, name, x, spectral, train, policy):
+def _conv_fn(scope, name, x, spectral, train, policy, round_out=True):
   """conv_fn(...)(x) of xmc_net.py:66-80 / 176-191: SpectralConv or nn.Conv under Flax auto-name `name`."""
   s = scope.child(name)
   p = s.get("params")
   if spectral:
-    y, st = spectral_conv(x, p, s.get("spectral_norm_stats"), train, policy)
+    y, st = spectral_conv(x, p, s.get("spectral_norm_stats"), train, policy, round_out)
     s.put("spectral_norm_stats", st)
     return y
-  return conv2d(x, p["kernel"], p.get("bias"), policy)
+  return conv2d(x, p["kernel"], p.get("bias"), policy, round_out)
 
 
-def _dense_fn(scope, name, x, spectral, train, policy):
+def _dense_fn(scope, name, x, spectral, train, policy, round_out=True):
   s = scope.child(name)
   p = s.get("params")
   if spectral:
-    y, st = spectral_dense(x, p, s.get("spectral_norm_stats"), train, policy)
+    y, st = spectral_dense(x, p, s.get("spectral_norm_stats"), train, policy, round_out)
     s.put("spectral_norm_stats", st)
     return y
-  return dense(x, p["kernel"], p.get("bias"), policy)
+  return dense(x, p["kernel"], p.get("bias"), policy, round_out)
 
 
 def _bn(scope, x, train, policy):
@@ -444,7 +446,7 @@ def generator_apply(variables, inputs, config, train, policy=FP32):
     spatial_cond = spatial_cond_upsample
   x = local_conditional_batch_norm(scope.child("LocalConditionalBatchNorm_0"), x, spatial_cond, sn, train, policy)
   x = F.relu(x)
-  x = _conv_fn(scope, cpre + "_1", x, sn, train, policy)
+  x = _conv_fn(scope, cpre + "_1", x, sn, train, policy, round_out=False)  # B200 path: fp32 accumulator -> tanh
   x = torch.tanh(x)
   x = (x + 1.0) / 2.0
   return x, scope.updates
@@ -476,8 +478,9 @@ def discriminator_apply(variables, inputs, config, train, policy=FP32):
       x_cond = x
   x = F.relu(x)
   x_pool = torch.sum(x.float(), dim=(1, 2))
-  out = _dense_fn(scope, dpre + "_0", x_pool, sn, train, policy)
-  embedding = _dense_fn(scope, dpre + "_1", cond, sn, train, policy)
+  # B200 path: the logit head stays in fp32 (more accurate than the reference's bf16 dense, never less)
+  out = _dense_fn(scope, dpre + "_0", x_pool, sn, train, FP32)
+  embedding = _dense_fn(scope, dpre + "_1", cond, sn, train, policy, round_out=False)
   sent_cond = embedding
   tile_num = x_pool.shape[0] // embedding.shape[0]
   embedding = embedding.repeat(tile_num, 1)

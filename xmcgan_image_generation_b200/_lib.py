@@ -1,13 +1,15 @@
-"""ctypes binding of libxmc.so (declared in include/xmc.h). The product path has no CPU fallback: if the library is
-missing or a call fails, an exception is raised."""
+"""ctypes binding of libxmc.so. Prototypes are taken from include/xmc.h (the single source of truth of the C ABI).
+The product path has no CPU fallback: if the library is missing or a call fails, an exception is raised."""
 import ctypes
 import os
+import re
 
 import torch
 
 from . import build as _build
 
 _LIB = None
+HEADER = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "include", "xmc.h")
 
 
 class XmcError(RuntimeError):
@@ -46,8 +48,61 @@ class WgradDesc(ctypes.Structure):
   ]
 
 
+class BnDesc(ctypes.Structure):
+  _fields_ = [
+      ("N", ctypes.c_int), ("H", ctypes.c_int), ("W", ctypes.c_int), ("C", ctypes.c_int),
+      ("Hc", ctypes.c_int),
+      ("ldG", ctypes.c_int), ("goff", ctypes.c_int), ("boff", ctypes.c_int),
+      ("relu", ctypes.c_int), ("upsample", ctypes.c_int),
+  ]
+
+
+class PrepEntry(ctypes.Structure):
+  _fields_ = [
+      ("w_off", ctypes.c_longlong), ("wk_fwd_off", ctypes.c_longlong), ("wk_dg_off", ctypes.c_longlong),
+      ("bias_off", ctypes.c_longlong), ("bias_dst_off", ctypes.c_longlong),
+      ("taps", ctypes.c_int), ("cin", ctypes.c_int), ("cout", ctypes.c_int),
+      ("ld_fwd", ctypes.c_int), ("ld_dg", ctypes.c_int),
+      ("sn", ctypes.c_int), ("tile_begin", ctypes.c_int), ("reserved", ctypes.c_int),
+  ]
+
+
+class SnEntry(ctypes.Structure):
+  _fields_ = [
+      ("w_off", ctypes.c_longlong), ("t_off", ctypes.c_longlong), ("s_off", ctypes.c_longlong),
+      ("u_off", ctypes.c_longlong),
+      ("rows", ctypes.c_int), ("cols", ctypes.c_int),
+      ("row_block_begin", ctypes.c_int), ("col_tile_begin", ctypes.c_int), ("elem_block_begin", ctypes.c_int),
+      ("reserved", ctypes.c_int),
+  ]
+
+
+_CTYPE = {"int": ctypes.c_int, "long long": ctypes.c_longlong, "float": ctypes.c_float}
+
+
+def declared_functions(header=HEADER):
+  """Parses include/xmc.h and returns {name: (restype, [argtypes])}."""
+  src = open(header).read()
+  src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
+  out = {}
+  for m in re.finditer(r"\b(int|const char\*)\s+(xmc_\w+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+    ret, name, args = m.group(1), m.group(2), m.group(3)
+    argtypes = []
+    args = args.strip()
+    if args and args != "void":
+      for a in args.split(","):
+        a = a.strip()
+        if "*" in a:
+          argtypes.append(ctypes.c_void_p)
+        else:
+          t = re.sub(r"\b\w+$", "", a).strip()  # drop the parameter name
+          argtypes.append(_CTYPE[t])
+    out[name] = (ctypes.c_char_p if "char" in ret else ctypes.c_int, argtypes)
+  return out
+
+
 def lib():
-  """Loads (building first if the in-tree .so is stale and nvcc is available) and returns the ctypes handle."""
+  """Loads (building first if the in-tree .so is missing) and returns the ctypes handle."""
   global _LIB
   if _LIB is not None:
     return _LIB
@@ -55,8 +110,10 @@ def lib():
   if not os.path.exists(path):
     path = _build.build()
   L = ctypes.CDLL(path)
-  L.xmc_strerror.restype = ctypes.c_char_p
-  L.xmc_last_cuda_error.restype = ctypes.c_char_p
+  for name, (res, args) in declared_functions().items():
+    fn = getattr(L, name)  # AttributeError here means the .so does not export a declared symbol
+    fn.restype = res
+    fn.argtypes = args
   _LIB = L
   return L
 
@@ -69,9 +126,9 @@ def check(code):
 
 def ptr(t):
   if t is None:
-    return ctypes.c_void_p(0)
-  return ctypes.c_void_p(t.data_ptr())
+    return None
+  return t.data_ptr()
 
 
 def stream():
-  return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+  return torch.cuda.current_stream().cuda_stream

@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libxmc.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "--use_fast_math", "-shared",
+    "-Xcompiler", "-fPIC", "-shared",
 ]
 
 

@@ -1,0 +1,627 @@
+// HBM-bound kernels of the XMC-GAN hot path: batch-norm statistics / conditional modulation (+relu, +nearest
+// upsample) and their backward, 2x2 pooling, bias-gradient column sums, casts and broadcasts.
+// All activation accesses are 16-byte vectors (8 bf16) with the channel index fastest -> fully coalesced.
+#include "common.h"
+#include "devutil.cuh"
+
+namespace xmc {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// BatchNorm statistics: sums[c] += sum_p x[p][c], sums[C+c] += sum_p x[p][c]^2   (flax nn.BatchNorm, fp32 stats)
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void bn_stats_kernel(const bf16* __restrict__ x, long long P, int C, int ld, float* __restrict__ sums) {
+  extern __shared__ float sm[];  // [lanes][cv*16]
+  const int cv = C >> 3;
+  const int cvb = min(cv - blockIdx.y * 256, 256);  // channel vectors handled by this blockIdx.y
+  const int lanes = blockDim.x / cvb;
+  const int v = threadIdx.x % cvb, pl = threadIdx.x / cvb;
+  const int cvec = blockIdx.y * 256 + v;
+  float s[8], s2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = s2[i] = 0.f;
+  if (pl < lanes) {
+    for (long long p = (long long)blockIdx.x * lanes + pl; p < P; p += (long long)gridDim.x * lanes) {
+      float f[8];
+      load8(x + p * ld + cvec * 8, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i] += f[i]; s2[i] += f[i] * f[i]; }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      sm[(pl * cvb + v) * 16 + i] = s[i];
+      sm[(pl * cvb + v) * 16 + 8 + i] = s2[i];
+    }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < cvb * 16; t += blockDim.x) {
+    float a = 0.f;
+    for (int l = 0; l < lanes; ++l) a += sm[l * cvb * 16 + t];
+    const int vv = t >> 4, i = t & 15;
+    const int c = (blockIdx.y * 256 + vv) * 8 + (i & 7);
+    atomicAdd(sums + (i >> 3) * C + c, a);
+  }
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ sums, float invP, int C, float eps, float momentum,
+                                   const float* ra_mean, const float* ra_var, float* new_ra_mean, float* new_ra_var,
+                                   float* mean_rstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float mean = sums[c] * invP;
+  const float var = sums[C + c] * invP - mean * mean;
+  mean_rstd[c] = mean;
+  mean_rstd[C + c] = rsqrtf(var + eps);
+  if (new_ra_mean) {
+    new_ra_mean[c] = momentum * ra_mean[c] + (1.f - momentum) * mean;
+    new_ra_var[c] = momentum * ra_var[c] + (1.f - momentum) * var;
+  }
+}
+
+// eval-mode: mean_rstd from running statistics
+__global__ void bn_eval_kernel(const float* ra_mean, const float* ra_var, int C, float eps, float* mean_rstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  mean_rstd[c] = ra_mean[c];
+  mean_rstd[C + c] = rsqrtf(ra_var[c] + eps);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// y = relu?( (x-mean)*rstd*(gamma+1)+beta ), optionally written to the 2x2 nearest-upsampled positions.
+// gamma/beta come from row (n*Hc + (h>>s))*Hc + (w>>s) of gb: Hc=1 -> ConditionalBatchNorm (layers.py:244-258),
+// Hc=16 -> LocalConditionalBatchNorm (layers.py:261-273) with the 1x1 convs evaluated once at 16x16.
+// ---------------------------------------------------------------------------------------------------------------------
+struct BnP {
+  int N, H, W, C, Hc, s, ldG, goff, boff, relu, upsample;
+};
+
+__device__ __forceinline__ long long cond_row(const BnP& p, int n, int h, int w) {
+  return ((long long)n * p.Hc + (h >> p.s)) * p.Hc + (w >> p.s);
+}
+
+__global__ void bn_apply_kernel(BnP p, const bf16* __restrict__ x, const float* __restrict__ mr,
+                                const bf16* __restrict__ gb, bf16* __restrict__ y) {
+  const int cv = p.C >> 3;
+  const long long total = (long long)p.N * p.H * p.W * cv;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int v = idx % cv;
+    long long pix = idx / cv;
+    const int w = pix % p.W;
+    const int h = (pix / p.W) % p.H;
+    const int n = pix / ((long long)p.W * p.H);
+    const int c = v * 8;
+    float f[8], g[8], b[8], o[8];
+    load8(x + pix * p.C + c, f);
+    const long long row = cond_row(p, n, h, w);
+    load8(gb + row * p.ldG + p.goff + c, g);
+    load8(gb + row * p.ldG + p.boff + c, b);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float xh = (f[i] - mr[c + i]) * mr[p.C + c + i];
+      float t = xh * (g[i] + 1.f) + b[i];
+      o[i] = p.relu ? fmaxf(t, 0.f) : t;
+    }
+    if (p.upsample) {
+      const int W2 = p.W * 2;
+      const long long base = (((long long)n * p.H * 2 + 2 * h) * W2 + 2 * w) * p.C + c;
+      store8(y + base, o);
+      store8(y + base + p.C, o);
+      store8(y + base + (long long)W2 * p.C, o);
+      store8(y + base + (long long)W2 * p.C + p.C, o);
+    } else {
+      store8(y + pix * p.C + c, o);
+    }
+  }
+}
+
+// gradient wrt the modulated/normalised tensor for one (pixel, 8 channels): returns g (post relu-mask, upsample-summed)
+__device__ __forceinline__ void bn_load_grad(const BnP& p, const bf16* dy, int n, int h, int w, int c, float* g) {
+  if (p.upsample) {
+    const int W2 = p.W * 2;
+    const long long base = (((long long)n * p.H * 2 + 2 * h) * W2 + 2 * w) * p.C + c;
+    float a[8], b[8], cc[8], d[8];
+    load8(dy + base, a);
+    load8(dy + base + p.C, b);
+    load8(dy + base + (long long)W2 * p.C, cc);
+    load8(dy + base + (long long)W2 * p.C + p.C, d);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = (a[i] + b[i]) + (cc[i] + d[i]);
+  } else {
+    load8(dy + (((long long)n * p.H + h) * p.W + w) * p.C + c, g);
+  }
+}
+
+// One block per (cond row, 256-channel-vector chunk): dgamma/dbeta are block-local sums (plain stores, no atomics);
+// the per-channel BN reduction terms S1 = sum dxhat, S2 = sum dxhat*xhat go to global atomics.
+__global__ void bn_bwd_reduce_kernel(BnP p, const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                     const float* __restrict__ mr, const bf16* __restrict__ gb,
+                                     float* __restrict__ dgb, float* __restrict__ sums) {
+  extern __shared__ float sm[];  // [lanes][cvb*32]
+  const int cv = p.C >> 3;
+  const int cvb = min(cv - blockIdx.y * 256, 256);
+  const int lanes = blockDim.x / cvb;
+  const int v = threadIdx.x % cvb, pl = threadIdx.x / cvb;
+  const int c = (blockIdx.y * 256 + v) * 8;
+  const long long row = blockIdx.x;
+  const int wc = row % p.Hc, hc = (row / p.Hc) % p.Hc, n = row / (p.Hc * p.Hc);
+  const int side = 1 << p.s;
+  const int npix = side * side;
+  float dg[8], db[8], s1[8], s2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) dg[i] = db[i] = s1[i] = s2[i] = 0.f;
+  if (pl < lanes) {
+    float gm[8], bt[8];
+    load8(gb + row * p.ldG + p.goff + c, gm);
+    load8(gb + row * p.ldG + p.boff + c, bt);
+    for (int q = pl; q < npix; q += lanes) {
+      const int h = hc * side + q / side, w = wc * side + q % side;
+      float f[8], g[8];
+      load8(x + (((long long)n * p.H + h) * p.W + w) * p.C + c, f);
+      bn_load_grad(p, dy, n, h, w, c, g);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float xh = (f[i] - mr[c + i]) * mr[p.C + c + i];
+        float gi = g[i];
+        if (p.relu && (xh * (gm[i] + 1.f) + bt[i]) <= 0.f) gi = 0.f;
+        dg[i] += gi * xh;
+        db[i] += gi;
+        const float dxh = gi * (gm[i] + 1.f);
+        s1[i] += dxh;
+        s2[i] += dxh * xh;
+      }
+    }
+    float* o = sm + (pl * cvb + v) * 32;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { o[i] = dg[i]; o[8 + i] = db[i]; o[16 + i] = s1[i]; o[24 + i] = s2[i]; }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < cvb * 32; t += blockDim.x) {
+    float a = 0.f;
+    for (int l = 0; l < lanes; ++l) a += sm[l * cvb * 32 + t];
+    const int vv = t >> 5, k = (t >> 3) & 3, i = t & 7;
+    const int cc = (blockIdx.y * 256 + vv) * 8 + i;
+    if (k == 0) dgb[row * p.ldG + p.goff + cc] = a;
+    else if (k == 1) dgb[row * p.ldG + p.boff + cc] = a;
+    else atomicAdd(sums + (k - 2) * p.C + cc, a);
+  }
+}
+
+__global__ void bn_bwd_apply_kernel(BnP p, const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                    const float* __restrict__ mr, const bf16* __restrict__ gb,
+                                    const float* __restrict__ sums, float invP, bf16* __restrict__ dx) {
+  const int cv = p.C >> 3;
+  const long long total = (long long)p.N * p.H * p.W * cv;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int v = idx % cv;
+    long long pix = idx / cv;
+    const int w = pix % p.W;
+    const int h = (pix / p.W) % p.H;
+    const int n = pix / ((long long)p.W * p.H);
+    const int c = v * 8;
+    float f[8], g[8], gm[8], bt[8], o[8];
+    load8(x + pix * p.C + c, f);
+    bn_load_grad(p, dy, n, h, w, c, g);
+    const long long row = cond_row(p, n, h, w);
+    load8(gb + row * p.ldG + p.goff + c, gm);
+    load8(gb + row * p.ldG + p.boff + c, bt);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float rstd = mr[p.C + c + i];
+      const float xh = (f[i] - mr[c + i]) * rstd;
+      float gi = g[i];
+      if (p.relu && (xh * (gm[i] + 1.f) + bt[i]) <= 0.f) gi = 0.f;
+      const float dxh = gi * (gm[i] + 1.f);
+      o[i] = rstd * (dxh - sums[c + i] * invP - xh * sums[p.C + c + i] * invP);
+    }
+    store8(dx + pix * p.C + c, o);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// 2x2 pooling (dsample, common.py:54-55 — scale 0.25; scale 1 gives the transpose of nearest upsample) and its
+// transpose.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void pool2_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, const bf16* __restrict__ low,
+                             int N, int H, int W, int C, float scale, bf16* __restrict__ out,
+                             bf16* __restrict__ out_relu) {
+  const int cv = C >> 3;
+  const long long total = (long long)N * H * W * cv;  // H,W are OUTPUT dims
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int v = idx % cv;
+    long long pix = idx / cv;
+    const int w = pix % W;
+    const int h = (pix / W) % H;
+    const int n = pix / ((long long)W * H);
+    const int c = v * 8;
+    const int W2 = 2 * W;
+    const long long base = (((long long)n * H * 2 + 2 * h) * W2 + 2 * w) * C + c;
+    const long long offs[4] = {0, C, (long long)W2 * C, (long long)W2 * C + C};
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float f[8];
+      load8(a + base + offs[k], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += f[i];
+      if (b) {
+        load8(b + base + offs[k], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += f[i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] *= scale;
+    if (low) {
+      float f[8];
+      load8(low + pix * C + c, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += f[i];
+    }
+    store8(out + pix * C + c, acc);
+    if (out_relu) {
+      // relu of the value as stored (bf16-rounded), so mask and activation agree bit-for-bit
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaxf(acc[i], 0.f);
+      store8(out_relu + pix * C + c, acc);
+    }
+  }
+}
+
+__global__ void unpool2_kernel(const bf16* __restrict__ dout, int N, int H, int W, int C, float scale,
+                               bf16* __restrict__ g) {
+  const int cv = C >> 3;
+  const long long total = (long long)N * H * W * cv;  // H,W are the LOW-res dims of dout
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int v = idx % cv;
+    long long pix = idx / cv;
+    const int w = pix % W;
+    const int h = (pix / W) % H;
+    const int n = pix / ((long long)W * H);
+    const int c = v * 8;
+    float f[8];
+    load8(dout + pix * C + c, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] *= scale;
+    const int W2 = 2 * W;
+    const long long base = (((long long)n * H * 2 + 2 * h) * W2 + 2 * w) * C + c;
+    store8(g + base, f);
+    store8(g + base + C, f);
+    store8(g + base + (long long)W2 * C, f);
+    store8(g + base + (long long)W2 * C + C, f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// out[c] += sum_p x[p][c]  (bias gradients)
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void colsum_kernel(const bf16* __restrict__ x, long long P, int C, int ld, float* __restrict__ out) {
+  extern __shared__ float sm[];
+  const int cv = C >> 3;
+  const int cvb = min(cv - blockIdx.y * 256, 256);
+  const int lanes = blockDim.x / cvb;
+  const int v = threadIdx.x % cvb, pl = threadIdx.x / cvb;
+  const int cvec = blockIdx.y * 256 + v;
+  float s[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = 0.f;
+  if (pl < lanes) {
+    for (long long p = (long long)blockIdx.x * lanes + pl; p < P; p += (long long)gridDim.x * lanes) {
+      float f[8];
+      load8(x + p * ld + cvec * 8, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[i] += f[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sm[(pl * cvb + v) * 8 + i] = s[i];
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < cvb * 8; t += blockDim.x) {
+    float a = 0.f;
+    for (int l = 0; l < lanes; ++l) a += sm[l * cvb * 8 + t];
+    atomicAdd(out + (blockIdx.y * 256 + (t >> 3)) * 8 + (t & 7), a);
+  }
+}
+
+// scalar fallback for channel counts that are not a multiple of 8 (the 3-channel image gradient)
+__global__ void colsum_scalar_kernel(const bf16* __restrict__ x, long long P, int C, int ld, float* __restrict__ out) {
+  __shared__ float sm[256];
+  const int c = blockIdx.y;
+  float s = 0.f;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x)
+    s += __bfloat162float(x[p * ld + c]);
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) atomicAdd(out + c, sm[0]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// x_pool[n][c] = sum_hw relu(x[n][hw][c])   (xmc_net.py:97-98) and its backward
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void relu_sumhw_kernel(const bf16* __restrict__ x, int HW, int C, float* __restrict__ out) {
+  const int n = blockIdx.y;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (c >= C) return;
+  float s[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = 0.f;
+  for (int q = 0; q < HW; ++q) {
+    float f[8];
+    load8(x + ((long long)n * HW + q) * C + c, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] += fmaxf(f[i], 0.f);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) out[(long long)n * C + c + i] = s[i];
+}
+
+__global__ void relu_sumhw_bwd_kernel(const bf16* __restrict__ x, const float* __restrict__ dout, int HW, int C,
+                                      bf16* __restrict__ dx) {
+  const int n = blockIdx.y;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (c >= C) return;
+  float d[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) d[i] = dout[(long long)n * C + c + i];
+  for (int q = 0; q < HW; ++q) {
+    float f[8], o[8];
+    load8(x + ((long long)n * HW + q) * C + c, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = f[i] > 0.f ? d[i] : 0.f;
+    store8(dx + ((long long)n * HW + q) * C + c, o);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// casts / broadcasts / grouped row sums (2-D, pitched)
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, long long rows, int cols, long long ld_src,
+                                     bf16* __restrict__ dst, long long ld_dst) {
+  const long long total = rows * cols;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / cols;
+    const int c = idx % cols;
+    dst[r * ld_dst + c] = __float2bfloat16(src[r * ld_src + c]);
+  }
+}
+
+__global__ void cast_bf16_f32_kernel(const bf16* __restrict__ src, long long rows, int cols, long long ld_src,
+                                     float* __restrict__ dst, long long ld_dst, int accumulate) {
+  const long long total = rows * cols;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / cols;
+    const int c = idx % cols;
+    const float v = __bfloat162float(src[r * ld_src + c]);
+    if (accumulate) dst[r * ld_dst + c] += v; else dst[r * ld_dst + c] = v;
+  }
+}
+
+// dst[(b*reps + r)][c] = src[b][c]
+__global__ void bcast_rows_kernel(const bf16* __restrict__ src, int B, int reps, int cols, int ld_src,
+                                  bf16* __restrict__ dst, int ld_dst) {
+  const long long total = (long long)B * reps * cols;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = idx % cols;
+    const long long br = idx / cols;
+    const int b = br / reps;
+    dst[br * ld_dst + c] = src[(long long)b * ld_src + c];
+  }
+}
+
+// dst[b][c] (+)= sum_r src[(b*reps + r)][c]
+__global__ void sum_rows_kernel(const bf16* __restrict__ src, int B, int reps, int cols, int ld_src,
+                                float* __restrict__ dst, int ld_dst, int accumulate) {
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float s = 0.f;
+  for (int r = 0; r < reps; ++r) s += __bfloat162float(src[((long long)b * reps + r) * ld_src + c]);
+  if (accumulate) dst[(long long)b * ld_dst + c] += s; else dst[(long long)b * ld_dst + c] = s;
+}
+
+static int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = (long long)num_sms() * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+static int fill_bnp(const XmcBnDesc* d, BnP* p) {
+  if (!d || d->N < 1 || d->H < 1 || d->W < 1 || d->C < 8 || (d->C % 8) || d->Hc < 1) return XMC_EINVAL;
+  if (d->H != d->W || d->H % d->Hc) return XMC_EINVAL;
+  int s = 0;
+  while ((d->Hc << s) < d->H) ++s;
+  if ((d->Hc << s) != d->H) return XMC_EINVAL;
+  if ((d->ldG % 8) || (d->goff % 8) || (d->boff % 8)) return XMC_EINVAL;
+  p->N = d->N; p->H = d->H; p->W = d->W; p->C = d->C; p->Hc = d->Hc; p->s = s;
+  p->ldG = d->ldG; p->goff = d->goff; p->boff = d->boff; p->relu = d->relu; p->upsample = d->upsample;
+  return XMC_OK;
+}
+
+}  // namespace xmc
+
+using namespace xmc;
+
+extern "C" int xmc_bn_stats(const void* x, long long P, int C, int ld, float* sums, void* stream) {
+  if (!x || !sums || P < 1 || C < 8 || (C % 8) || (ld % 8)) return XMC_EINVAL;
+  const int cv = C / 8;
+  const int ny = ceil_div(cv, 256);
+  const int cvb = cv < 256 ? cv : 256;
+  const int lanes = 256 / cvb;
+  long long gx = ceil_div_ll(P, (long long)lanes * 8);
+  const long long cap = (long long)num_sms() * 4;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  const size_t smem = (size_t)lanes * cvb * 16 * sizeof(float);
+  bn_stats_kernel<<<dim3((unsigned)gx, ny), 256, smem, (cudaStream_t)stream>>>((const bf16*)x, P, C, ld, sums);
+  XMC_LAUNCH_CHECK();
+  return XMC_OK;
+}
+
+extern "C" int xmc_bn_finalize(const float* sums, long long P, int C, float eps, float momentum, const float* ra_mean,
+                               const float* ra_var, float* new_ra_mean, float* new_ra_var, float* mean_rstd,
+                               void* stream) {
+  if (!sums || !mean_rstd || P < 1 || C < 1) return XMC_EINVAL;
+  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(sums, 1.f / (float)P, C, eps, momentum,
+                                                                        ra_mean, ra_var, new_ra_mean, new_ra_var,
+                                                                        mean_rstd);
+  XMC_LAUNCH_CHECK();
+  return XMC_OK;
+}
+
+extern "C" int xmc_bn_eval_stats(const float* ra_mean, const float* ra_var, int C, float eps, float* mean_rstd,
+                                 void* stream) {
+  if (!ra_mean || !ra_var || !mean_rstd || C < 1) return XMC_EINVAL;
+  bn_eval_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(ra_mean, ra_var, C, eps, mean_rstd);
+  XMC_LAUNCH_CHECK();
+  return XMC_OK;
+}
+
+extern "C" int xmc_bn_apply(const XmcBnDesc* d, const void* x, const float* mean_rstd, const void* gb, void* y,
+                            void* stream) {
+  BnP p;
+  int r = fill_bnp(d, &p);
+  if (r) return r;
+  if (!x || !mean_rstd || !gb || !y) return XMC_EINVAL;
+  const long long total = (long long)p.N * p.H * p.W * (p.C / 8);
+  bn_apply_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(p, (const bf16*)x, mean_rstd,
+                                                                         (const bf16*)gb, (bf16*)y);
+  XMC_LAUNCH_CHECK();
+  return XMC_OK;
+}
+
+extern "C" int xmc_bn_bwd_reduce(const XmcBnDesc* d, const void* dy, const void* x, const float* mean_rstd,
+                                 const void* gb, float* dgb, float* sums, void* stream) {
+  BnP p;
+  int r = fill_bnp(d, &p);
+  if (r) return r;
+  if (!dy || !x || !mean_rstd || !gb || !dgb || !sums) return XMC_EINVAL;
+  const int cv = p.C / 8;
+  const int ny = ceil_div(cv, 256);
+  const int cvb = cv < 256 ? cv : 256;
+  const int lanes = 256 / cvb;
+  const size_t smem = (size_t)lanes * cvb * 32 * sizeof(float);
+  const long long rows = (long long)p.N * p.Hc * p.Hc;
+  bn_bwd_reduce_kernel<<<dim3((unsigned)rows, ny), 256, smem, (cudaStream_t)stream>>>(
+      p, (const bf16*)dy, (const bf16*)x, mean_rstd, (const bf16*)gb, dgb, sums);
+  XMC_LAUNCH_CHECK();
+  return XMC_OK;
+}
+
+extern "C" int xmc_bn_bwd_apply(const XmcBnDesc* d, const void* dy, const void* x, const float* mean_rstd,
+                                const void* gb, const float* sums, void* dx, void* stream) {
+  BnP p;
+  int r = fill_bnp(d, &p);
+  if (r) return r;
+  if (!dy || !x || !mean_rstd || !gb || !sums || !dx) return XMC_EINVAL;
+  const long long total = (long long)p.N * p.H * p.W * (p.C / 8);
+  const float invP = 1.f / (float)((long long)p.N * p.H * p.W);
+  bn_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      p, (const bf16*)dy, (const bf16*)x, mean_rstd, (const bf16*)gb, sums, invP, (bf16*)dx);
+  XMC_LAUNCH_CHECK();
+  return XMC_OK;
+}
+
+extern "C" int xmc_pool2(const void* a, const void* b, const void* low, int N, int Hout, int Wout, int C, float scale,
+                         void* out, void* out_relu, void* stream) {
+  if (!a || !out || N < 1 || Hout < 1 || Wout < 1 || C < 8 || (C % 8)) return XMC_EINVAL;
+  const long long total = (long long)N * Hout * Wout * (C / 8);
+  pool2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)a, (const bf16*)b, (const bf16*)low, N, Hout, Wout, C, scale, (bf16*)out, (bf16*)out_relu);
+  XMC_LAUNCH_CHECK();
+  return XMC_OK;
+}
+
+extern "C" int xmc_unpool2(const void* dout, int N, int Hin, int Win, int C, float scale, void* g, void* stream) {
+  if (!dout || !g || N < 1 || Hin < 1 || Win < 1 || C < 8 || (C % 8)) return XMC_EINVAL;
+  const long long total = (long long)N * Hin * Win * (C / 8);
+  unpool2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)dout, N, Hin, Win, C, scale,
+                                                                        (bf16*)g);
+  XMC_LAUNCH_CHECK();
+  return XMC_OK;
+}
+
+extern "C" int xmc_colsum(const void* x, long long P, int C, int ld, float* out, void* stream) {
+  if (!x || !out || P < 1 || C < 1) return XMC_EINVAL;
+  if (C % 8 || ld % 8) {
+    long long gx = ceil_div_ll(P, 256 * 16);
+    if (gx > 512) gx = 512;
+    if (gx < 1) gx = 1;
+    colsum_scalar_kernel<<<dim3((unsigned)gx, C), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, P, C, ld, out);
+    XMC_LAUNCH_CHECK();
+    return XMC_OK;
+  }
+  const int cv = C / 8;
+  const int ny = ceil_div(cv, 256);
+  const int cvb = cv < 256 ? cv : 256;
+  const int lanes = 256 / cvb;
+  long long gx = ceil_div_ll(P, (long long)lanes * 8);
+  const long long cap = (long long)num_sms() * 4;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  const size_t smem = (size_t)lanes * cvb * 8 * sizeof(float);
+  colsum_kernel<<<dim3((unsigned)gx, ny), 256, smem, (cudaStream_t)stream>>>((const bf16*)x, P, C, ld, out);
+  XMC_LAUNCH_CHECK();
+  return XMC_OK;
+}
+
+extern "C" int xmc_relu_sumhw(const void* x, int N, int HW, int C, float* out, void* stream) {
+  if (!x || !out || N < 1 || HW < 1 || C < 8 || (C % 8)) return XMC_EINVAL;
+  relu_sumhw_kernel<<<dim3(ceil_div(C / 8, 64), N), 64, 0, (cudaStream_t)stream>>>((const bf16*)x, HW, C, out);
+  XMC_LAUNCH_CHECK();
+  return XMC_OK;
+}
+
+extern "C" int xmc_relu_sumhw_bwd(const void* x, const float* dout, int N, int HW, int C, void* dx, void* stream) {
+  if (!x || !dout || !dx || N < 1 || HW < 1 || C < 8 || (C % 8)) return XMC_EINVAL;
+  relu_sumhw_bwd_kernel<<<dim3(ceil_div(C / 8, 64), N), 64, 0, (cudaStream_t)stream>>>((const bf16*)x, dout, HW, C,
+                                                                                      (bf16*)dx);
+  XMC_LAUNCH_CHECK();
+  return XMC_OK;
+}
+
+extern "C" int xmc_cast_f32_to_bf16(const float* src, long long rows, int cols, long long ld_src, void* dst,
+                                    long long ld_dst, void* stream) {
+  if (!src || !dst || rows < 1 || cols < 1) return XMC_EINVAL;
+  cast_f32_bf16_kernel<<<grid_for(rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(src, rows, cols, ld_src,
+                                                                                    (bf16*)dst, ld_dst);
+  XMC_LAUNCH_CHECK();
+  return XMC_OK;
+}
+
+extern "C" int xmc_cast_bf16_to_f32(const void* src, long long rows, int cols, long long ld_src, float* dst,
+                                    long long ld_dst, int accumulate, void* stream) {
+  if (!src || !dst || rows < 1 || cols < 1) return XMC_EINVAL;
+  cast_bf16_f32_kernel<<<grid_for(rows * cols, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)src, rows, cols,
+                                                                                    ld_src, dst, ld_dst, accumulate);
+  XMC_LAUNCH_CHECK();
+  return XMC_OK;
+}
+
+extern "C" int xmc_bcast_rows(const void* src, int B, int reps, int cols, int ld_src, void* dst, int ld_dst,
+                              void* stream) {
+  if (!src || !dst || B < 1 || reps < 1 || cols < 1) return XMC_EINVAL;
+  bcast_rows_kernel<<<grid_for((long long)B * reps * cols, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)src, B, reps, cols, ld_src, (bf16*)dst, ld_dst);
+  XMC_LAUNCH_CHECK();
+  return XMC_OK;
+}
+
+extern "C" int xmc_sum_rows(const void* src, int B, int reps, int cols, int ld_src, float* dst, int ld_dst,
+                            int accumulate, void* stream) {
+  if (!src || !dst || B < 1 || reps < 1 || cols < 1) return XMC_EINVAL;
+  sum_rows_kernel<<<dim3(ceil_div(cols, 128), B), 128, 0, (cudaStream_t)stream>>>((const bf16*)src, B, reps, cols,
+                                                                                 ld_src, dst, ld_dst, accumulate);
+  XMC_LAUNCH_CHECK();
+  return XMC_OK;
+}

@@ -1,0 +1,262 @@
+// Parameter-side kernels (all multi-tensor: one launch walks a device table of layers):
+//   * spectral normalisation: one power-iteration step, sigma, and the sigma term of its backward
+//     (xmcgan/libml/layers.py:94-101 and :211-221);
+//   * weight preparation: fp32 HWIO kernel -> bf16 K-major copies for the forward ([Cout][tap*Cin+ci]) and dgrad
+//     ([Cin][flip(tap)*Cout+co]) tcgen05 GEMMs, scaled by 1/(sigma+eps) when spectrally normalised;
+//   * Adam (+ polyak EMA) on flat fp32 buffers (flax.optim.Adam as applied at xmcgan/xmc_gan.py:172-177,252).
+#include "common.h"
+#include "devutil.cuh"
+
+namespace xmc {
+
+template <typename E>
+__device__ __forceinline__ int find_entry(const E* tab, int n, int block, int E::*field) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (tab[mid].*field <= block) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+// ------------------------------------------------------------------------------------------------- spectral norm
+// scalars layout (SoA, n = number of SN layers): [0,n) sum_t2 | [n,2n) norm_t | [2n,3n) inv_sigma | [3n,4n) dot
+__global__ void sn_rowdot_kernel(const XmcSnEntry* __restrict__ tab, int n, const float* __restrict__ params,
+                                 const float* __restrict__ u0, float* __restrict__ t_ws, float* __restrict__ scalars) {
+  const int e = find_entry(tab, n, (int)blockIdx.x, &XmcSnEntry::row_block_begin);
+  const XmcSnEntry en = tab[e];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k = ((int)blockIdx.x - en.row_block_begin) * 8 + warp;
+  float t = 0.f;
+  if (k < en.rows) {
+    const float* w = params + en.w_off + (long long)k * en.cols;
+    const float* u = u0 + en.u_off;
+    for (int c = lane; c < en.cols; c += 32) t += w[c] * u[c];
+    t = warp_sum(t);
+    if (lane == 0) t_ws[en.t_off + k] = t;
+  }
+  __shared__ float sm[8];
+  if (lane == 0) sm[warp] = (k < en.rows) ? t * t : 0.f;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f;
+    for (int i = 0; i < 8; ++i) a += sm[i];
+    atomicAdd(scalars + e, a);
+  }
+}
+
+__global__ void sn_colsum_kernel(const XmcSnEntry* __restrict__ tab, int n, const float* __restrict__ params,
+                                 const float* __restrict__ t_ws, float* __restrict__ s_ws) {
+  const int e = find_entry(tab, n, (int)blockIdx.x, &XmcSnEntry::col_tile_begin);
+  const XmcSnEntry en = tab[e];
+  const int local = (int)blockIdx.x - en.col_tile_begin;
+  const int ctiles = (en.cols + 31) / 32;
+  const int rt = local / ctiles, ct = local - rt * ctiles;
+  const int c = ct * 32 + threadIdx.x;
+  const int k0 = rt * 256;
+  float acc = 0.f;
+  if (c < en.cols) {
+    const int k1 = min(en.rows, k0 + 256);
+    for (int k = k0 + threadIdx.y; k < k1; k += 8)
+      acc += t_ws[en.t_off + k] * params[en.w_off + (long long)k * en.cols + c];
+  }
+  __shared__ float sm[8][33];
+  sm[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < en.cols) {
+    float a = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a += sm[i][threadIdx.x];
+    atomicAdd(s_ws + en.s_off + c, a);
+  }
+}
+
+__global__ void sn_finalize_kernel(const XmcSnEntry* __restrict__ tab, int n, float eps, const float* __restrict__ s_ws,
+                                   float* __restrict__ u_new, float* __restrict__ scalars) {
+  __shared__ float sm[32];
+  const int e = blockIdx.x;
+  const XmcSnEntry en = tab[e];
+  const float norm_t = rsqrtf(scalars[e] + eps);  // v0 = t * norm_t   (layers.py:213 / :96)
+  float ss = 0.f;
+  for (int c = threadIdx.x; c < en.cols; c += blockDim.x) {
+    const float s = s_ws[en.s_off + c] * norm_t;  // (v0 W)[c]
+    ss += s * s;
+  }
+  ss = block_sum(ss, sm);
+  const float norm_s = rsqrtf(ss + eps);          // u1 = (v0 W) * norm_s  (layers.py:214 / :97)
+  for (int c = threadIdx.x; c < en.cols; c += blockDim.x)
+    u_new[en.u_off + c] = s_ws[en.s_off + c] * norm_t * norm_s;
+  if (threadIdx.x == 0) {
+    const float sigma = ss * norm_s;              // v0 W u1^T
+    scalars[n + e] = norm_t;
+    scalars[2 * n + e] = 1.f / (sigma + eps);     // kernel / (sigma + eps)  (layers.py:101 / :221)
+  }
+}
+
+// dot[e] = <dWtilde, W>
+__global__ void sn_bwd_dot_kernel(const XmcSnEntry* __restrict__ tab, int n, const float* __restrict__ params,
+                                  const float* __restrict__ grads, float* __restrict__ scalars) {
+  __shared__ float sm[32];
+  const int e = find_entry(tab, n, (int)blockIdx.x, &XmcSnEntry::elem_block_begin);
+  const XmcSnEntry en = tab[e];
+  const long long total = (long long)en.rows * en.cols;
+  const long long base = (long long)((int)blockIdx.x - en.elem_block_begin) * 2048;
+  float a = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const long long idx = base + i * 256 + threadIdx.x;
+    if (idx < total) a += grads[en.w_off + idx] * params[en.w_off + idx];
+  }
+  a = block_sum(a, sm);
+  if (threadIdx.x == 0) atomicAdd(scalars + 3 * n + e, a);
+}
+
+// dW = dWtilde/sigma' - <dWtilde,W>/sigma'^2 * v0^T u1     (sigma' = sigma + eps; u1, v0 are stop-gradient)
+__global__ void sn_bwd_apply_kernel(const XmcSnEntry* __restrict__ tab, int n, float* __restrict__ grads,
+                                    const float* __restrict__ t_ws, const float* __restrict__ u_new,
+                                    const float* __restrict__ scalars) {
+  const int e = find_entry(tab, n, (int)blockIdx.x, &XmcSnEntry::elem_block_begin);
+  const XmcSnEntry en = tab[e];
+  const long long total = (long long)en.rows * en.cols;
+  const long long base = (long long)((int)blockIdx.x - en.elem_block_begin) * 2048;
+  const float norm_t = scalars[n + e], inv = scalars[2 * n + e], dot = scalars[3 * n + e];
+  const float coef = dot * inv * inv * norm_t;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const long long idx = base + i * 256 + threadIdx.x;
+    if (idx < total) {
+      const int k = idx / en.cols, c = idx - (long long)k * en.cols;
+      grads[en.w_off + idx] = grads[en.w_off + idx] * inv - coef * t_ws[en.t_off + k] * u_new[en.u_off + c];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- weight prep
+__global__ void prep_weights_kernel(const XmcPrepEntry* __restrict__ tab, int n, const float* __restrict__ params,
+                                    const float* __restrict__ sn_scalars, int n_sn, bf16* __restrict__ arena,
+                                    float* __restrict__ bias_arena) {
+  __shared__ float tile[32][33];
+  const int e = find_entry(tab, n, (int)blockIdx.x, &XmcPrepEntry::tile_begin);
+  const XmcPrepEntry en = tab[e];
+  const int local = (int)blockIdx.x - en.tile_begin;
+  const int K = en.taps * en.cin;
+  const int ctiles = (en.cout + 31) / 32;
+  const int kt = local / ctiles, ct = local - kt * ctiles;
+  const float scale = (en.sn >= 0) ? sn_scalars[2 * n_sn + en.sn] : 1.f;
+  const int c = ct * 32 + threadIdx.x;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int k = kt * 32 + r;
+    float v = 0.f;
+    if (k < K && c < en.cout) {
+      v = params[en.w_off + (long long)k * en.cout + c] * scale;
+      if (en.wk_dg_off >= 0) {
+        const int tap = k / en.cin, ci = k - tap * en.cin;
+        arena[en.wk_dg_off + (long long)ci * en.ld_dg + (long long)(en.taps - 1 - tap) * en.cout + c] =
+            __float2bfloat16(v);
+      }
+    }
+    tile[r][threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (en.wk_fwd_off >= 0) {
+    const int k = kt * 32 + threadIdx.x;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+      const int cc = ct * 32 + r;
+      if (k < K && cc < en.cout) arena[en.wk_fwd_off + (long long)cc * en.ld_fwd + k] = __float2bfloat16(tile[threadIdx.x][r]);
+    }
+  }
+  if (local == 0 && en.bias_off >= 0 && en.bias_dst_off >= 0) {
+    for (int i = threadIdx.y * 32 + threadIdx.x; i < en.cout; i += 256)
+      bias_arena[en.bias_dst_off + i] = params[en.bias_off + i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- Adam (+EMA)
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float inv_c1,
+                            float inv_c2, float gscale, float* __restrict__ ema, float decay) {
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    float* pa = &pp.x; float* ga = &gg.x; float* ma = &mm.x; float* va = &vv.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gk = ga[k] * gscale;
+      ma[k] = b1 * ma[k] + (1.f - b1) * gk;
+      va[k] = b2 * va[k] + (1.f - b2) * gk * gk;
+      pa[k] = pa[k] - lr * (ma[k] * inv_c1) / (sqrtf(va[k] * inv_c2) + eps);
+    }
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    if (ema) {
+      float4 ee = reinterpret_cast<float4*>(ema)[i];
+      ee.x = ee.x * decay + (1.f - decay) * pp.x;
+      ee.y = ee.y * decay + (1.f - decay) * pp.y;
+      ee.z = ee.z * decay + (1.f - decay) * pp.z;
+      ee.w = ee.w * decay + (1.f - decay) * pp.w;
+      reinterpret_cast<float4*>(ema)[i] = ee;
+    }
+  }
+}
+
+}  // namespace xmc
+
+using namespace xmc;
+
+extern "C" int xmc_sn_forward(const XmcSnEntry* table_dev, int n, float eps, const float* params, const float* u0,
+                              float* u0_new, float* t_ws, float* s_ws, long long s_ws_floats, float* scalars,
+                              int total_row_blocks, int total_col_tiles, void* stream) {
+  if (!table_dev || n < 1 || !params || !u0 || !u0_new || !t_ws || !s_ws || !scalars) return XMC_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  XMC_CUDA_CHECK(cudaMemsetAsync(scalars, 0, sizeof(float) * 4 * n, st));
+  XMC_CUDA_CHECK(cudaMemsetAsync(s_ws, 0, sizeof(float) * s_ws_floats, st));
+  sn_rowdot_kernel<<<total_row_blocks, 256, 0, st>>>(table_dev, n, params, u0, t_ws, scalars);
+  XMC_LAUNCH_CHECK();
+  sn_colsum_kernel<<<total_col_tiles, dim3(32, 8), 0, st>>>(table_dev, n, params, t_ws, s_ws);
+  XMC_LAUNCH_CHECK();
+  sn_finalize_kernel<<<n, 256, 0, st>>>(table_dev, n, eps, s_ws, u0_new, scalars);
+  XMC_LAUNCH_CHECK();
+  return XMC_OK;
+}
+
+extern "C" int xmc_sn_backward(const XmcSnEntry* table_dev, int n, const float* params, float* grads,
+                               const float* t_ws, const float* u0_new, float* scalars, int total_elem_blocks,
+                               void* stream) {
+  if (!table_dev || n < 1 || !params || !grads || !t_ws || !u0_new || !scalars) return XMC_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  XMC_CUDA_CHECK(cudaMemsetAsync(scalars + 3 * n, 0, sizeof(float) * n, st));
+  sn_bwd_dot_kernel<<<total_elem_blocks, 256, 0, st>>>(table_dev, n, params, grads, scalars);
+  XMC_LAUNCH_CHECK();
+  sn_bwd_apply_kernel<<<total_elem_blocks, 256, 0, st>>>(table_dev, n, grads, t_ws, u0_new, scalars);
+  XMC_LAUNCH_CHECK();
+  return XMC_OK;
+}
+
+extern "C" int xmc_prep_weights(const XmcPrepEntry* table_dev, int n, int total_tiles, const float* params,
+                                const float* sn_scalars, int n_sn, void* arena, float* bias_arena, void* stream) {
+  if (!table_dev || n < 1 || total_tiles < 1 || !params || !arena) return XMC_EINVAL;
+  prep_weights_kernel<<<total_tiles, dim3(32, 8), 0, (cudaStream_t)stream>>>(table_dev, n, params, sn_scalars, n_sn,
+                                                                            (bf16*)arena, bias_arena);
+  XMC_LAUNCH_CHECK();
+  return XMC_OK;
+}
+
+extern "C" int xmc_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                        float eps, float bias_corr1, float bias_corr2, float grad_scale, float* ema, float ema_decay,
+                        void* stream) {
+  if (!p || !g || !m || !v || n < 4 || (n & 3)) return XMC_EINVAL;
+  if (!aligned16(p) || !aligned16(g) || !aligned16(m) || !aligned16(v) || (ema && !aligned16(ema))) return XMC_EALIGN;
+  long long blocks = ceil_div_ll(n / 4, 256);
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps,
+                                                                  1.f / bias_corr1, 1.f / bias_corr2, grad_scale, ema,
+                                                                  ema_decay);
+  XMC_LAUNCH_CHECK();
+  return XMC_OK;
+}

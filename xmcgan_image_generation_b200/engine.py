@@ -1,0 +1,873 @@
+"""Execution engines for the XMC-GAN generator and discriminator: parameter layout, weight preparation, and explicit
+forward / backward programs made of libxmc.so kernel launches (no autograd, no torch arithmetic).
+
+Reference semantics: xmcgan/nets/xmc_net.py:28-248, xmcgan/nets/common.py:58-186, xmcgan/libml/layers.py:49-273,
+xmcgan/libml/attention_lib.py:46-219. Differences that are exact in real arithmetic and deliberate:
+  * LocalConditionalBatchNorm's 1x1 gamma/beta convolutions run once at 16x16 as ONE concatenated GEMM and are read
+    through (h>>s, w>>s) indexing (a 1x1 conv commutes with nearest upsampling);
+  * generator shortcuts run conv1x1 before the upsample (same reason) and are added in the main conv's epilogue;
+  * the generator-side pull-back through the discriminator only touches the fake half of the batch (the
+    discriminator has no cross-example op, so the real half cannot reach the generator).
+"""
+import collections
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import ops
+from .ops import BF16, F32
+
+ConvRec = collections.namedtuple(
+    "ConvRec", "path kh cin cout w_off b_off fwd_off ld_fwd dg_off ld_dg sn")
+
+LOSS_SLOTS = dict(hinge_d=0, hinge_g=1, real_word=2, fake_word=3, real_sent=4, fake_sent=5, image=6, pretrained=7)
+
+
+def _r4(n):
+  return (n + 3) // 4 * 4
+
+
+def _r8(n):
+  return (n + 7) // 8 * 8
+
+
+def as4(t2d):
+  """[rows, C] (pitched) -> [1,1,rows,C] so that the GEMM sees `rows` pixels along W."""
+  return t2d[None, None]
+
+
+class Layout:
+  """Flat fp32 buffer layout: path tuple -> (offset, shape)."""
+
+  def __init__(self):
+    self.entries = collections.OrderedDict()
+    self.total = 0
+
+  def add(self, path, shape):
+    size = int(np.prod(shape))
+    self.entries[path] = (self.total, tuple(shape))
+    self.total += _r4(size)
+    return self.entries[path][0]
+
+  def off(self, path):
+    return self.entries[path][0]
+
+  def view(self, buf, path):
+    off, shape = self.entries[path]
+    return buf[off:off + int(np.prod(shape))].view(shape)
+
+  def tree(self, buf):
+    root = {}
+    for path in self.entries:
+      node = root
+      for k in path[:-1]:
+        node = node.setdefault(k, {})
+      node[path[-1]] = self.view(buf, path)
+    return root
+
+  def load_tree(self, buf, tree):
+    for path in self.entries:
+      node = tree
+      for k in path:
+        node = node[k]
+      self.view(buf, path).copy_(torch.as_tensor(node).to(buf.device, buf.dtype).reshape(self.entries[path][1]))
+
+
+def _glorot_std(shape):
+  rf = int(np.prod(shape[:-2])) if len(shape) > 2 else 1
+  fan_in, fan_out = shape[-2] * rf, shape[-1] * rf
+  return math.sqrt(2.0 / (fan_in + fan_out))
+
+
+def init_flat(layout, seed, kind_of):
+  """Random initialisation matching the reference's initialisers in distribution: glorot-normal kernels
+  (xmc_net.py:70-80,181-191), zero biases, u0 ~ N(0, 0.01^2) (layers.py:86-91), BN stats (0, 1)."""
+  g = torch.Generator(device="cpu").manual_seed(seed)
+  buf = torch.zeros(layout.total, dtype=torch.float32)
+  for path, (off, shape) in layout.entries.items():
+    n = int(np.prod(shape))
+    kind = kind_of(path)
+    if kind == "kernel":
+      buf[off:off + n] = torch.randn(n, generator=g) * _glorot_std(shape)
+    elif kind == "u0":
+      buf[off:off + n] = torch.randn(n, generator=g) * 0.01
+    elif kind == "var":
+      buf[off:off + n] = 1.0
+  return buf
+
+
+def _kind(path):
+  leaf = path[-1]
+  return leaf if leaf in ("kernel", "bias", "u0", "mean", "var") else "other"
+
+
+class _PrepTable:
+  """Device table for xmc_prep_weights (fp32 HWIO -> bf16 K-major forward / dgrad copies)."""
+
+  def __init__(self):
+    self.entries = []
+    self.tiles = 0
+
+  def add(self, w_off, taps, cin, cout, fwd_off, ld_fwd, dg_off, ld_dg, sn):
+    e = _lib.PrepEntry()
+    e.w_off, e.wk_fwd_off, e.wk_dg_off = w_off, fwd_off, dg_off
+    e.bias_off = e.bias_dst_off = -1
+    e.taps, e.cin, e.cout = taps, cin, cout
+    e.ld_fwd, e.ld_dg, e.sn = ld_fwd, ld_dg, sn
+    e.tile_begin = self.tiles
+    self.tiles += ((taps * cin + 31) // 32) * ((cout + 31) // 32)
+    self.entries.append(e)
+
+  def upload(self):
+    arr = (_lib.PrepEntry * len(self.entries))(*self.entries)
+    raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone()
+    self.dev = raw.cuda()
+    self.n = len(self.entries)
+
+
+# ======================================================================================================================
+# Generator
+# ======================================================================================================================
+class GeneratorEngine:
+  """xmc_net.Generator (xmc_net.py:145-248)."""
+
+  def __init__(self, config, embedding_dim=768):
+    if config.g_spectral_norm:
+      raise NotImplementedError("g_spectral_norm=True is not built yet (reference default is False, coco_xmc.py:58)")
+    if config.batch_norm_group_size > 0:
+      raise NotImplementedError("grouped cross-replica BatchNorm is not built yet (default -1, coco_xmc.py:44)")
+    if config.image_size == 256:
+      channel_dims = [16, 8, 8, 4, 2, 1]
+    elif config.image_size == 128:
+      channel_dims = [16, 8, 4, 2, 1]
+    else:
+      raise ValueError(f"image_size {config.image_size} is not supported (reference: xmc_net.py:202-205)")
+    self.config = config
+    self.E = E = embedding_dim
+    self.zd = zd = config.z_dim
+    self.cd = cd = 2 * zd
+    self.scd = scd = E + cd
+    gf = config.gf_dim
+    self.ch = ch = [gf * c for c in channel_dims]
+    self.c0 = c0 = gf * 16
+    self.n_spatial = len(channel_dims) - 2
+    self.gamma = float(config.gamma_for_g)
+    if any(c % 8 for c in ch + [c0, E, zd]):
+      raise ValueError("channel counts must be multiples of 8")
+
+    # ---- block descriptions -----------------------------------------------------------------------------------
+    blocks = []  # (name, kind, cin, cout)
+    cin = c0
+    for i in range(2):
+      blocks.append((f"GenBlock_{i}", "cbn", cin, ch[i]))
+      cin = ch[i]
+    for k in range(self.n_spatial):
+      blocks.append((f"GenSpatialBlock_{k}", "lcbn", cin, ch[k + 2]))
+      cin = ch[k + 2]
+    self.blocks = blocks
+    self.c_last = cin
+
+    # ---- concatenated gamma/beta groups ----------------------------------------------------------------------
+    self.cbn = []   # (path_prefix, C, goff, boff)
+    self.lcbn = []
+    off = 0
+    for name, kind, bcin, bcout in blocks:
+      if kind == "cbn":
+        for j, C in enumerate((bcin, bcout)):
+          self.cbn.append(((name, f"ConditionalBatchNorm_{j}"), C, off, off + C))
+          off += 2 * C
+    self.NC = off
+    off = 0
+    for name, kind, bcin, bcout in blocks:
+      if kind == "lcbn":
+        for j, C in enumerate((bcin, bcout)):
+          self.lcbn.append(((name, f"LocalConditionalBatchNorm_{j}"), C, off, off + C))
+          off += 2 * C
+    self.lcbn.append((("LocalConditionalBatchNorm_0",), self.c_last, off, off + self.c_last))
+    off += 2 * self.c_last
+    self.NL = off
+
+    # ---- parameter layout: concatenated biases first (so one bias vector / one colsum serves the whole group) --
+    L = self.layout = Layout()
+    self.lcbn_bias_off = L.total
+    for prefix, C, goff, boff in self.lcbn:
+      assert L.add(prefix + ("Conv_0", "bias"), (C,)) == self.lcbn_bias_off + goff
+      assert L.add(prefix + ("Conv_1", "bias"), (C,)) == self.lcbn_bias_off + boff
+    self.cbn_bias_off = L.total
+    for prefix, C, goff, boff in self.cbn:
+      assert L.add(prefix + ("Dense_0", "bias"), (C,)) == self.cbn_bias_off + goff
+      assert L.add(prefix + ("Dense_1", "bias"), (C,)) == self.cbn_bias_off + boff
+    for prefix, C, goff, boff in self.lcbn:
+      L.add(prefix + ("Conv_0", "kernel"), (1, 1, scd, C))
+      L.add(prefix + ("Conv_1", "kernel"), (1, 1, scd, C))
+    for prefix, C, goff, boff in self.cbn:
+      L.add(prefix + ("Dense_0", "kernel"), (cd, C))
+      L.add(prefix + ("Dense_1", "kernel"), (cd, C))
+
+    self.arena_size = 0
+    self.prep = _PrepTable()
+    self.convs = {}
+
+    def add_conv(path, kh, cin_, cout_, dense=False):
+      shape = (cin_, cout_) if dense else (kh, kh, cin_, cout_)
+      w_off = L.add(path + ("kernel",), shape)
+      b_off = L.add(path + ("bias",), (cout_,))
+      taps = kh * kh
+      ld_fwd, ld_dg = _r8(taps * cin_), _r8(taps * cout_)
+      fwd_off = self.arena_size
+      self.arena_size += _r8(cout_) * ld_fwd
+      dg_off = self.arena_size
+      self.arena_size += _r8(cin_) * ld_dg
+      self.prep.add(w_off, taps, cin_, cout_, fwd_off, ld_fwd, dg_off, ld_dg, -1)
+      self.convs[path] = ConvRec(path, kh, cin_, cout_, w_off, b_off, fwd_off, ld_fwd, dg_off, ld_dg, -1)
+
+    add_conv(("Dense_0",), 1, E, zd, dense=True)
+    add_conv(("Dense_1",), 1, zd, c0 * 16, dense=True)
+    for name, kind, bcin, bcout in blocks:
+      add_conv((name, "Conv_0"), 3, bcin, bcout)
+      add_conv((name, "Conv_1"), 3, bcout, bcout)
+      add_conv((name, "Conv_2"), 1, bcin, bcout)
+    add_conv(("Conv_0",), 1, ch[1], E)
+    add_conv(("Conv_1",), 3, self.c_last, 3)
+
+    # concatenated matrices: forward [N*][K] rows per layer, dgrad [K][N*] column slices
+    self.cbn_fwd_off = self.arena_size
+    self.arena_size += self.NC * cd
+    self.cbn_dg_off = self.arena_size
+    self.arena_size += cd * self.NC
+    self.lcbn_fwd_off = self.arena_size
+    self.arena_size += self.NL * scd
+    self.lcbn_dg_off = self.arena_size
+    self.arena_size += scd * self.NL
+    for prefix, C, goff, boff in self.cbn:
+      for leaf, o in (("Dense_0", goff), ("Dense_1", boff)):
+        self.prep.add(L.off(prefix + (leaf, "kernel")), 1, cd, C, self.cbn_fwd_off + o * cd, cd,
+                      self.cbn_dg_off + o, self.NC, -1)
+    for prefix, C, goff, boff in self.lcbn:
+      for leaf, o in (("Conv_0", goff), ("Conv_1", boff)):
+        self.prep.add(L.off(prefix + (leaf, "kernel")), 1, scd, C, self.lcbn_fwd_off + o * scd, scd,
+                      self.lcbn_dg_off + o, self.NL, -1)
+
+    # ---- batch_stats layout ------------------------------------------------------------------------------------
+    S = self.stats_layout = Layout()
+    for prefix, C, _, _ in self.cbn + self.lcbn:
+      S.add(prefix + ("BatchNorm_0", "mean"), (C,))
+      S.add(prefix + ("BatchNorm_0", "var"), (C,))
+    self.bn_index = {prefix: (C, goff, boff) for prefix, C, goff, boff in self.cbn + self.lcbn}
+    self.arena = None
+
+  # ------------------------------------------------------------------------------------------------------------
+  def init_params(self, seed):
+    return init_flat(self.layout, seed, _kind).cuda(), init_flat(self.stats_layout, seed + 1, _kind).cuda()
+
+  def _ensure(self):
+    if self.arena is None:
+      self.arena = torch.zeros(self.arena_size, device="cuda", dtype=BF16)
+      self.prep.upload()
+
+  def prep_weights(self, params):
+    self._ensure()
+    ops._call("xmc_prep_weights", self.prep.dev.data_ptr(), self.prep.n, self.prep.tiles, params.data_ptr(), None, 0,
+              self.arena.data_ptr(), None, _lib.stream())
+
+  def _wk(self, rec):
+    return self.arena[rec.fwd_off:]
+
+  def _wd(self, rec):
+    return self.arena[rec.dg_off:]
+
+  def _bn(self, x, prefix, stats, new_stats, train):
+    C = x.shape[-1]
+    SL = self.stats_layout
+    mean = SL.view(stats, prefix + ("BatchNorm_0", "mean"))
+    var = SL.view(stats, prefix + ("BatchNorm_0", "var"))
+    if train:
+      sums, P = ops.bn_stats(x)
+      nm = SL.view(new_stats, prefix + ("BatchNorm_0", "mean")) if new_stats is not None else None
+      nv = SL.view(new_stats, prefix + ("BatchNorm_0", "var")) if new_stats is not None else None
+      return ops.bn_finalize(sums, P, C, mean, var, nm, nv)
+    return ops.bn_eval_stats(mean, var, C)
+
+  def forward(self, params, stats, batch, z, train=True, new_stats=None, fake_bf16=None):
+    """Returns (image fp32 [B,S,S,3] in [0,1], ctx). `fake_bf16`: optional bf16 [B,S,S,3] view that also receives
+    the image (the second half of the discriminator input). Weights must have been prepared (prep_weights)."""
+    P = params
+    E, zd, cd, scd = self.E, self.zd, self.cd, self.scd
+    B = z.shape[0]
+    cond = batch["sentence_embedding"].reshape(B, E)
+    words = batch["embedding"]
+    Lw = words.shape[1]
+    max_len = batch["max_len"].reshape(B).contiguous()
+    ctx = {"B": B, "Lw": Lw, "train": train}
+
+    cond_bf = ops.cast_to_bf16(cond)
+    gc = ops.empty((B, cd))
+    r = self.convs[("Dense_0",)]
+    ops.conv_fwd(as4(cond_bf), self._wk(r), 1, zd, bias=P[r.b_off:], out=as4(gc[:, :zd]), ldb=r.ld_fwd)
+    ops.cast_to_bf16(z.reshape(B, zd), gc[:, zd:])
+    r = self.convs[("Dense_1",)]
+    x = ops.conv_fwd(as4(gc[:, zd:]), self._wk(r), 1, r.cout, bias=P[r.b_off:], ldb=r.ld_fwd)
+    x = x.view(B, 4, 4, self.c0)
+    gbC = ops.conv_fwd(as4(gc), self.arena[self.cbn_fwd_off:], 1, self.NC, bias=P[self.cbn_bias_off:],
+                       ldb=cd).view(B, self.NC)
+    ctx.update(cond_bf=cond_bf, gc=gc, gbC=gbC, blocks=[])
+
+    gb, Hc = gbC, 1
+    for name, kind, bcin, bcout in self.blocks:
+      if kind == "lcbn" and Hc == 1:
+        # ---- word-region attention at 16x16 and the spatial condition (xmc_net.py:220-235) ---------------------
+        r = self.convs[("Conv_0",)]
+        xq = ops.conv_fwd(x, self._wk(r), 1, E, bias=P[r.b_off:], ldb=r.ld_fwd)
+        R = xq.shape[1] * xq.shape[2]
+        what, _ = ops.l2norm_rows(words.reshape(B * Lw, E))
+        spatial = ops.empty((B * R, scd))
+        attn = ops.attention_g_fwd(xq.view(B, R, E), what.view(B, Lw, E), max_len, self.gamma, spatial)
+        ops.bcast_rows(gc, R, spatial[:, E:])
+        gbL = ops.conv_fwd(as4(spatial), self.arena[self.lcbn_fwd_off:], 1, self.NL, bias=P[self.lcbn_bias_off:],
+                           ldb=scd).view(B * R, self.NL)
+        ctx.update(x16=x, xq=xq, what=what, attn=attn, spatial=spatial, gbL=gbL, R=R, Hc=xq.shape[1])
+        gb, Hc = gbL, xq.shape[1]
+      bn0 = (name, ("ConditionalBatchNorm_0" if kind == "cbn" else "LocalConditionalBatchNorm_0"))
+      bn1 = (name, ("ConditionalBatchNorm_1" if kind == "cbn" else "LocalConditionalBatchNorm_1"))
+      _, g0, b0 = self.bn_index[bn0]
+      _, g1, b1 = self.bn_index[bn1]
+      r0, r1, r2 = (self.convs[(name, f"Conv_{i}")] for i in range(3))
+      mr0 = self._bn(x, bn0, stats, new_stats, train)
+      u = ops.bn_apply(x, mr0, gb, Hc, g0, b0, True, True)
+      c1 = ops.conv_fwd(u, self._wk(r0), 3, bcout, bias=P[r0.b_off:], ldb=r0.ld_fwd)
+      mr1 = self._bn(c1, bn1, stats, new_stats, train)
+      h2 = ops.bn_apply(c1, mr1, gb, Hc, g1, b1, True, False)
+      sc = ops.conv_fwd(x, self._wk(r2), 1, bcout, bias=P[r2.b_off:], ldb=r2.ld_fwd)
+      out = ops.conv_fwd(h2, self._wk(r1), 3, bcout, bias=P[r1.b_off:], residual=sc, res_shift=1, ldb=r1.ld_fwd)
+      ctx["blocks"].append(dict(x=x, mr0=mr0, u=u, c1=c1, mr1=mr1, h2=h2, Hc=Hc))
+      x = out
+    bnf = ("LocalConditionalBatchNorm_0",)
+    _, gf_, bf_ = self.bn_index[bnf]
+    mrf = self._bn(x, bnf, stats, new_stats, train)
+    hf = ops.bn_apply(x, mrf, gbL, Hc, gf_, bf_, True, False)
+    r = self.convs[("Conv_1",)]
+    S = x.shape[1]
+    img = ops.empty((B, S, S, 3), F32)
+    ops._call("xmc_conv_c3_out", hf.data_ptr(), self._wk(r).data_ptr(), r.ld_fwd, P[r.b_off:].data_ptr(), B, S, S,
+              self.c_last, 3, 3, 1, 0, img.data_ptr(), fake_bf16.data_ptr() if fake_bf16 is not None else None,
+              _lib.stream())
+    ctx.update(x_last=x, mrf=mrf, hf=hf, img=img)
+    return img, ctx
+
+  # ------------------------------------------------------------------------------------------------------------
+  def _conv_wgrad(self, rec, x_in, dy, grads):
+    ops.wgrad(x_in, dy, rec.kh, grads[rec.w_off:], out_mode=0, ld_out=rec.cout, tap_stride=rec.cin * rec.cout)
+    ops.colsum(dy, grads[rec.b_off:])
+
+  def backward(self, ctx, d_img, params, grads):
+    """Accumulates d(loss)/d(params) into the flat fp32 buffer `grads` given d(loss)/d(image) (fp32)."""
+    B, E, zd, cd, scd = ctx["B"], self.E, self.zd, self.cd, self.scd
+    S = d_img.shape[1]
+    gbC, gbL, R, Hc16 = ctx["gbC"], ctx["gbL"], ctx["R"], ctx["Hc"]
+    dgbC = ops.empty((B, self.NC), F32)
+    dgbL = ops.empty((B * R, self.NL), F32)
+
+    # output head: tanh, conv3x3 (C -> 3)
+    dpre = ops.empty((B, S, S, 3))
+    ops._call("xmc_tanh01_bwd", d_img.data_ptr(), ctx["img"].data_ptr(), d_img.numel(), dpre.data_ptr(), _lib.stream())
+    r = self.convs[("Conv_1",)]
+    C = self.c_last
+    ops._call("xmc_wgrad_c3", dpre.data_ptr(), ctx["hf"].data_ptr(), B, S, S, C, 3, 3, 1, C * 3, 1, 3,
+              grads[r.w_off:].data_ptr(), _lib.stream())
+    ops.colsum(dpre, grads[r.b_off:])
+    dhf = ops.empty((B, S, S, C))
+    ops._call("xmc_conv_c3_in", dpre.data_ptr(), self._wd(r).data_ptr(), r.ld_dg, None, B, S, S, C, 3, 3, 0,
+              dhf.data_ptr(), _lib.stream())
+    _, gf_, bf_ = self.bn_index[("LocalConditionalBatchNorm_0",)]
+    dout = ops.bn_bwd(dhf, ctx["x_last"], ctx["mrf"], gbL, dgbL, Hc16, gf_, bf_, True, False)
+
+    dx16_extra = None
+    for (name, kind, bcin, bcout), sv in zip(reversed(self.blocks), reversed(ctx["blocks"])):
+      gb, dgb = (gbC, dgbC) if kind == "cbn" else (gbL, dgbL)
+      bn0 = (name, ("ConditionalBatchNorm_0" if kind == "cbn" else "LocalConditionalBatchNorm_0"))
+      bn1 = (name, ("ConditionalBatchNorm_1" if kind == "cbn" else "LocalConditionalBatchNorm_1"))
+      _, g0, b0 = self.bn_index[bn0]
+      _, g1, b1 = self.bn_index[bn1]
+      r0, r1, r2 = (self.convs[(name, f"Conv_{i}")] for i in range(3))
+      if kind == "cbn" and dx16_extra is None:
+        # leaving the spatial part: finish everything that hangs off the 16x16 tensor (attention, spatial cond)
+        dx16_extra = True
+        dout = self._backward_cond16(ctx, dgbL, dout, params, grads)
+      # conv2 (Conv_1)
+      self._conv_wgrad(r1, sv["h2"], dout, grads)
+      dh2 = ops.conv_fwd(dout, self._wd(r1), 3, bcout, ldb=r1.ld_dg)
+      dc1 = ops.bn_bwd(dh2, sv["c1"], sv["mr1"], gb, dgb, sv["Hc"], g1, b1, True, False)
+      # conv1 (Conv_0)
+      self._conv_wgrad(r0, sv["u"], dc1, grads)
+      du = ops.conv_fwd(dc1, self._wd(r0), 3, bcin, ldb=r0.ld_dg)
+      dxa = ops.bn_bwd(du, sv["x"], sv["mr0"], gb, dgb, sv["Hc"], g0, b0, True, True)
+      # shortcut (Conv_2 at low resolution)
+      dsc = ops.pool2(dout, scale=1.0)
+      self._conv_wgrad(r2, sv["x"], dsc, grads)
+      dout = ops.conv_fwd(dsc, self._wd(r2), 1, bcin, residual=dxa, ldb=r2.ld_dg)
+
+    # ---- ConditionalBatchNorm gamma/beta dense layers + global condition ----------------------------------------
+    gc = ctx["gc"]
+    dgbC_bf = ops.cast_to_bf16(dgbC)
+    L = self.layout
+    for prefix, Cc, goff, boff in self.cbn:
+      for leaf, o in (("Dense_0", goff), ("Dense_1", boff)):
+        ops.wgrad(as4(gc), as4(dgbC_bf[:, o:o + Cc]), 1, grads[L.off(prefix + (leaf, "kernel")):], out_mode=0,
+                  ld_out=Cc, tap_stride=cd * Cc)
+    ops.colsum(dgbC_bf, grads[self.cbn_bias_off:])
+    dgc = ops.conv_fwd(as4(dgbC_bf), self.arena[self.cbn_dg_off:], 1, cd, ldb=self.NC, out_dtype=F32).view(B, cd)
+    ops.sum_rows(ctx["dspatial"][:, E:], B, R, dgc, accumulate=True)
+    dgc_bf = ops.cast_to_bf16(dgc)
+    r = self.convs[("Dense_0",)]
+    ops.wgrad(as4(ctx["cond_bf"]), as4(dgc_bf[:, :zd]), 1, grads[r.w_off:], out_mode=0, ld_out=zd, tap_stride=E * zd)
+    ops.colsum(dgc_bf[:, :zd], grads[r.b_off:])
+    # Dense_1 (z -> 4x4xC0); d(out) = input gradient of GenBlock_0
+    r = self.convs[("Dense_1",)]
+    dx0 = dout.view(B, r.cout)
+    ops.wgrad(as4(gc[:, zd:]), as4(dx0), 1, grads[r.w_off:], out_mode=0, ld_out=r.cout, tap_stride=zd * r.cout)
+    ops.colsum(dx0, grads[r.b_off:])
+
+  def _backward_cond16(self, ctx, dgbL, dx16, params, grads):
+    """Backward of everything attached to the 16x16 tensor: LCBN gamma/beta 1x1 convs (concatenated), spatial
+    condition, word-region attention, Conv_0. Returns the total gradient wrt the GenBlock_1 output."""
+    B, E, scd, R = ctx["B"], self.E, self.scd, ctx["R"]
+    L = self.layout
+    spatial = ctx["spatial"]
+    dgbL_bf = ops.cast_to_bf16(dgbL)
+    for prefix, Cc, goff, boff in self.lcbn:
+      for leaf, o in (("Conv_0", goff), ("Conv_1", boff)):
+        ops.wgrad(as4(spatial), as4(dgbL_bf[:, o:o + Cc]), 1, grads[L.off(prefix + (leaf, "kernel")):], out_mode=0,
+                  ld_out=Cc, tap_stride=scd * Cc)
+    ops.colsum(dgbL_bf, grads[self.lcbn_bias_off:])
+    dspatial = ops.conv_fwd(as4(dgbL_bf), self.arena[self.lcbn_dg_off:], 1, scd, ldb=self.NL).view(B * R, scd)
+    ctx["dspatial"] = dspatial
+    xq = ctx["xq"]
+    dq = ops.attention_g_bwd(dspatial, xq.view(B, R, E), ctx["what"].view(B, ctx["Lw"], E), ctx["attn"], self.gamma)
+    r = self.convs[("Conv_0",)]
+    dq4 = dq.view(xq.shape)
+    self._conv_wgrad(r, ctx["x16"], dq4, grads)
+    return ops.conv_fwd(dq4, self._wd(r), 1, r.cin, residual=dx16, ldb=r.ld_dg)
+
+
+# ======================================================================================================================
+# Loss heads
+# ======================================================================================================================
+class Contrastive:
+  """attention_lib.contrastive_loss (attention_lib.py:46-79) on fp32 features a (image_feat), b (cond_feat)."""
+
+  def __init__(self, a, b, slot, temperature=0.1):
+    self.inv_t = 1.0 / temperature
+    self.ah, self.ainv = ops.l2norm_rows(a)
+    self.bh, self.binv = ops.l2norm_rows(b)
+    logits = ops.small_gemm_nt(self.ah, self.bh, self.inv_t)
+    self.dlogits = ops.ce_sym(logits, slot)
+
+  def bwd_a(self, out, accumulate=True):
+    dah = ops.small_gemm_nn(self.dlogits, False, self.bh, self.inv_t)
+    ops.l2norm_rows_bwd(dah, self.ah, self.ainv, out=out, accumulate=accumulate)
+
+  def bwd_b(self, out, accumulate=True):
+    dbh = ops.small_gemm_nn(self.dlogits, True, self.ah, self.inv_t)
+    ops.l2norm_rows_bwd(dbh, self.bh, self.binv, out=out, accumulate=accumulate)
+
+
+class WordShared:
+  """Per-batch word tensors shared by the real and fake word_loss calls."""
+
+  def __init__(self, words, max_len):
+    B, Lw, E = words.shape
+    self.B, self.Lw, self.E = B, Lw, E
+    self.BL = B * Lw
+    self.ldS = _r8(self.BL)
+    self.words = words.reshape(self.BL, E).contiguous()
+    self.what_bf, self.winv = ops.l2norm_rows(self.words, out_dtype=BF16)
+    self.max_len = max_len.reshape(B).contiguous()
+    self._whatT = None
+
+  def whatT(self):
+    if self._whatT is None:
+      self._whatT = ops.transpose_bf16(self.what_bf, self.ldS)
+    return self._whatT
+
+
+class WordLoss:
+  """attention_lib.word_loss (attention_lib.py:130-191) with gamma1=gamma2=5, gamma3=50. R: [B, regions, E] bf16."""
+  G1, G2, G3 = 5.0, 5.0, 50.0
+
+  def __init__(self, R, ws, slot):
+    B, Rn, E = R.shape
+    self.ws, self.B, self.Rn, self.E = ws, B, Rn, E
+    BL, ldS = ws.BL, ws.ldS
+    padded = ldS != BL
+    self.Rh, self.rinv = ops.l2norm_rows(R.reshape(B * Rn, E), out_dtype=BF16)
+    S = ops.empty((B * Rn, ldS), F32)
+    ops.conv_fwd(as4(self.Rh), ws.what_bf, 1, BL, ldb=E, out=as4(S[:, :BL]))
+    self.alpha = ops.empty((B * Rn, ldS))
+    self.alphaT = ops.zeros((B, ldS, Rn), BF16) if padded else ops.empty((B, ldS, Rn))
+    ops._call("xmc_wl_softmax", S.data_ptr(), B, Rn, BL, ldS, self.G1, self.alpha.data_ptr(), self.alphaT.data_ptr(),
+              _lib.stream())
+    self.ctx = ops.empty((B, ldS, E), F32)
+    ops.wgrad(self.alpha.view(B, 1, Rn, ldS), self.Rh.view(B, 1, Rn, E), 1, self.ctx, out_mode=1, batched=True,
+              ld_out=E, tap_stride=0, batch_stride=ldS * E)
+    self.cos = ops.empty((B, BL), F32)
+    self.cnorm = ops.empty((B, BL), F32)
+    ops._call("xmc_wl_cos", self.ctx.data_ptr(), ldS * E, ws.words.data_ptr(), ws.winv.data_ptr(), B, ws.Lw, E,
+              self.cos.data_ptr(), self.cnorm.data_ptr(), _lib.stream())
+    self.sim = ops.empty((B, B), F32)
+    self.pw = ops.empty((B, BL), F32)
+    ops._call("xmc_wl_sim", self.cos.data_ptr(), ws.max_len.data_ptr(), B, ws.Lw, self.G2, self.G3,
+              self.sim.data_ptr(), self.pw.data_ptr(), _lib.stream())
+    self.dsim = ops.ce_sym(self.sim, slot)
+
+  def bwd(self):
+    """Returns d(loss)/dR as bf16 [B*regions, E]."""
+    ws, B, Rn, E = self.ws, self.B, self.Rn, self.E
+    BL, ldS = ws.BL, ws.ldS
+    padded = ldS != BL
+    dctx = ops.zeros((B, ldS, E), BF16) if padded else ops.empty((B, ldS, E))
+    ops._call("xmc_wl_cos_bwd", self.dsim.data_ptr(), self.pw.data_ptr(), self.cos.data_ptr(), self.cnorm.data_ptr(),
+              self.ctx.data_ptr(), ldS * E, ws.words.data_ptr(), ws.winv.data_ptr(), B, ws.Lw, E, self.G3,
+              dctx.data_ptr(), ldS * E, _lib.stream())
+    dalpha = ops.empty((B * Rn, ldS), F32)
+    ops.conv_fwd(self.Rh.view(B, 1, Rn, E), dctx, 1, BL, ldb=E, batched=True, stride_b=ldS * E,
+                 out=dalpha.view(B, 1, Rn, ldS)[..., :BL])
+    dS = ops.empty((B * Rn, ldS))
+    ops._call("xmc_wl_softmax_bwd", self.alpha.data_ptr(), dalpha.data_ptr(), B, Rn, BL, ldS, self.G1, dS.data_ptr(),
+              _lib.stream())
+    tmp = ops.empty((B * Rn, E))
+    ops.wgrad(self.alphaT.view(B, 1, ldS, Rn), dctx.view(B, 1, ldS, E), 1, tmp, out_mode=2, batched=True, ld_out=E,
+              tap_stride=0, batch_stride=Rn * E)
+    dRh = ops.conv_fwd(as4(dS), ws.whatT(), 1, E, ldb=ldS, residual=as4(tmp))
+    return ops.l2norm_rows_bwd(dRh.view(B * Rn, E), self.Rh, self.rinv)
+
+
+# ======================================================================================================================
+# Discriminator
+# ======================================================================================================================
+class DiscriminatorEngine:
+  """xmc_net.Discriminator (xmc_net.py:28-142)."""
+
+  def __init__(self, config, embedding_dim=768):
+    if config.image_size == 128:
+      channel_dims, downs = [2, 4, 8, 16, 16], [True, True, True, True, False]
+    elif config.image_size == 256:
+      channel_dims, downs = [2, 4, 8, 8, 16, 16], [True, True, True, True, True, False]
+    else:
+      raise ValueError(f"image_size {config.image_size} is not supported (reference: xmc_net.py:81-86)")
+    self.config = config
+    self.E = E = embedding_dim
+    df = config.df_dim
+    self.sn = bool(config.d_spectral_norm)
+    self.cpre = "SpectralConv" if self.sn else "Conv"
+    self.dpre = "SpectralDense" if self.sn else "Dense"
+    self.cond_size = config.cond_size
+    if df % 8:
+      raise ValueError("df_dim must be a multiple of 8")
+    L = self.layout = Layout()
+    U = self.u_layout = Layout()
+    self.arena_size = 0
+    self.prep = _PrepTable()
+    self.convs = {}
+    self.sn_entries = []
+    self._rb = self._ct = self._eb = 0
+    self._t = self._s = 0
+
+    def add_conv(path, kh, cin_, cout_, dense=False, prep=True):
+      shape = (cin_, cout_) if dense else (kh, kh, cin_, cout_)
+      w_off = L.add(path + ("kernel",), shape)
+      b_off = L.add(path + ("bias",), (cout_,))
+      taps = kh * kh
+      slot = -1
+      if self.sn:
+        slot = len(self.sn_entries)
+        u_off = U.add(path + ("u0",), (1, cout_))
+        e = _lib.SnEntry()
+        rows = taps * cin_
+        e.w_off, e.t_off, e.s_off, e.u_off = w_off, self._t, self._s, u_off
+        e.rows, e.cols = rows, cout_
+        e.row_block_begin, e.col_tile_begin, e.elem_block_begin = self._rb, self._ct, self._eb
+        self._t += _r4(rows)
+        self._s += _r4(cout_)
+        self._rb += (rows + 7) // 8
+        self._ct += ((rows + 255) // 256) * ((cout_ + 31) // 32)
+        self._eb += (rows * cout_ + 2047) // 2048
+        self.sn_entries.append(e)
+      ld_fwd, ld_dg = _r8(taps * cin_), _r8(taps * cout_)
+      fwd_off = dg_off = -1
+      if prep:
+        fwd_off = self.arena_size
+        self.arena_size += _r8(cout_) * ld_fwd
+        dg_off = self.arena_size
+        self.arena_size += _r8(cin_) * ld_dg
+        self.prep.add(w_off, taps, cin_, cout_, fwd_off, ld_fwd, dg_off, ld_dg, slot)
+      self.convs[path] = ConvRec(path, kh, cin_, cout_, w_off, b_off, fwd_off, ld_fwd, dg_off, ld_dg, slot)
+
+    cp = self.cpre
+    add_conv(("DiscOptimizedBlock_0", cp + "_0"), 3, 3, df)
+    add_conv(("DiscOptimizedBlock_0", cp + "_1"), 3, df, df)
+    add_conv(("DiscOptimizedBlock_0", cp + "_2"), 1, 3, df)
+    self.blocks = []
+    cin = df
+    size = config.image_size // 2
+    self.cond_channels = None
+    for i, (cr, down) in enumerate(zip(channel_dims, downs)):
+      cout = df * cr
+      proj = down or cin != cout
+      name = f"DiscBlock_{i}"
+      add_conv((name, cp + "_0"), 3, cin, cout)
+      add_conv((name, cp + "_1"), 3, cout, cout)
+      if proj:
+        add_conv((name, cp + "_2"), 1, cin, cout)
+      if not down and i != len(channel_dims) - 1:
+        raise NotImplementedError("a non-final DiscBlock without downsampling is not built")
+      size = size // 2 if down else size
+      is_cond = size == self.cond_size
+      self.blocks.append((name, cin, cout, down, proj, is_cond))
+      if is_cond:
+        self.cond_channels = cout
+      cin = cout
+    self.c_last = cin
+    add_conv((self.dpre + "_0",), 1, cin, 1, dense=True, prep=False)
+    add_conv((self.dpre + "_1",), 1, E, cin, dense=True)
+    if config.word_contrastive:
+      if self.cond_channels is None:
+        raise ValueError("no discriminator feature map of size cond_size")
+      add_conv((cp + "_0",), 1, self.cond_channels, E)
+    self.n_sn = len(self.sn_entries)
+    self.arena = None
+
+  def init_params(self, seed):
+    return init_flat(self.layout, seed, _kind).cuda(), init_flat(self.u_layout, seed + 1, _kind).cuda()
+
+  def _ensure(self):
+    if self.arena is None:
+      self.arena = torch.zeros(self.arena_size, device="cuda", dtype=BF16)
+      self.prep.upload()
+      if self.sn:
+        arr = (_lib.SnEntry * self.n_sn)(*self.sn_entries)
+        self.sn_dev = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone().cuda()
+        self.t_ws = torch.zeros(self._t, device="cuda")
+        self.s_ws = torch.zeros(self._s, device="cuda")
+        self.scalars = torch.zeros(4 * self.n_sn, device="cuda")
+
+  def prep_weights(self, params, u0, u0_new):
+    """Spectral normalisation (one power-iteration step, new u0 written to u0_new) + bf16 weight copies."""
+    self._ensure()
+    if self.sn:
+      ops._call("xmc_sn_forward", self.sn_dev.data_ptr(), self.n_sn, 1e-10, params.data_ptr(), u0.data_ptr(),
+                u0_new.data_ptr(), self.t_ws.data_ptr(), self.s_ws.data_ptr(), self._s, self.scalars.data_ptr(),
+                self._rb, self._ct, _lib.stream(), launches=5)
+    ops._call("xmc_prep_weights", self.prep.dev.data_ptr(), self.prep.n, self.prep.tiles, params.data_ptr(),
+              self.scalars.data_ptr() if self.sn else None, self.n_sn, self.arena.data_ptr(), None, _lib.stream())
+
+  def sn_backward(self, params, grads, u0_new):
+    if self.sn:
+      ops._call("xmc_sn_backward", self.sn_dev.data_ptr(), self.n_sn, params.data_ptr(), grads.data_ptr(),
+                self.t_ws.data_ptr(), u0_new.data_ptr(), self.scalars.data_ptr(), self._eb, _lib.stream(),
+                launches=3)
+
+  def _wk(self, rec):
+    return self.arena[rec.fwd_off:]
+
+  def _wd(self, rec):
+    return self.arena[rec.dg_off:]
+
+  def _inv_sigma(self, rec):
+    return self.scalars[2 * self.n_sn + rec.sn:] if self.sn else None
+
+  # ------------------------------------------------------------------------------------------------------------
+  def forward(self, params, images, batch, losses, need_g=True):
+    """images: bf16 [2B,S,S,3] (real first). Fills `losses` (fp32[16]) slots, returns (logit fp32 [2B], ctx)."""
+    P = params
+    cfg = self.config
+    cp = self.cpre
+    N2, S = images.shape[0], images.shape[1]
+    B = N2 // 2
+    E = self.E
+    df = cfg.df_dim
+    ctx = {"B": B, "need_g": need_g, "images": images}
+    r0, r1, r2 = (self.convs[("DiscOptimizedBlock_0", cp + f"_{i}")] for i in range(3))
+    xp = ops.empty((N2, S // 2, S // 2, 3))
+    ops._call("xmc_pool2_small", images.data_ptr(), N2, S // 2, S // 2, 3, 0.25, xp.data_ptr(), _lib.stream())
+    sc = ops.empty((N2, S // 2, S // 2, df))
+    ops._call("xmc_conv_c3_in", xp.data_ptr(), self._wk(r2).data_ptr(), r2.ld_fwd, P[r2.b_off:].data_ptr(), N2, S // 2,
+              S // 2, df, 1, 1, 0, sc.data_ptr(), _lib.stream())
+    c1r = ops.empty((N2, S, S, df))
+    ops._call("xmc_conv_c3_in", images.data_ptr(), self._wk(r0).data_ptr(), r0.ld_fwd, P[r0.b_off:].data_ptr(), N2, S, S,
+              df, 3, 3, 1, c1r.data_ptr(), _lib.stream())
+    c2 = ops.conv_fwd(c1r, self._wk(r1), 3, df, bias=P[r1.b_off:], ldb=r1.ld_fwd)
+    x, xr = ops.pool2(c2, low=sc, want_relu=True)
+    del c2, sc
+    ctx["b0"] = dict(xp=xp, c1r=c1r)
+    ctx["blocks"] = []
+    x_cond = None
+    for name, cin, cout, down, proj, is_cond in self.blocks:
+      q0, q1 = self.convs[(name, cp + "_0")], self.convs[(name, cp + "_1")]
+      c1r = ops.conv_fwd(xr, self._wk(q0), 3, cout, bias=P[q0.b_off:], relu=True, ldb=q0.ld_fwd)
+      if proj:
+        q2 = self.convs[(name, cp + "_2")]
+        scf = ops.conv_fwd(x, self._wk(q2), 1, cout, bias=P[q2.b_off:], ldb=q2.ld_fwd)
+      else:
+        scf = x
+      c2s = ops.conv_fwd(c1r, self._wk(q1), 3, cout, bias=P[q1.b_off:], residual=scf, ldb=q1.ld_fwd)
+      ctx["blocks"].append(dict(x=x, xr=xr, c1r=c1r))
+      if down:
+        x, xr = ops.pool2(c2s, want_relu=True)
+      else:
+        x, xr = c2s, None
+      if is_cond:
+        x_cond = x
+    ctx["x_last"] = x
+    xpool = ops.relu_sumhw(x)
+    C = self.c_last
+    cond_bf = ops.cast_to_bf16(batch["sentence_embedding"].reshape(B, E))
+    rd0, rd1 = self.convs[(self.dpre + "_0",)], self.convs[(self.dpre + "_1",)]
+    sent = ops.conv_fwd(as4(cond_bf), self._wk(rd1), 1, C, bias=P[rd1.b_off:], ldb=rd1.ld_fwd,
+                        out_dtype=F32).view(B, C)
+    logit = ops.empty(N2, F32)
+    inv0 = self._inv_sigma(rd0)
+    ops._call("xmc_proj_logit", xpool.data_ptr(), P[rd0.w_off:].data_ptr(), inv0.data_ptr() if inv0 is not None else None,
+              P[rd0.b_off:].data_ptr(), sent.data_ptr(), N2, B, C, logit.data_ptr(), _lib.stream())
+    dl_d, dl_g = ops.hinge(logit, B, losses[LOSS_SLOTS["hinge_d"]:], losses[LOSS_SLOTS["hinge_g"]:])
+    ctx.update(xpool=xpool, cond_bf=cond_bf, sent=sent, logit=logit, dl_d=dl_d, dl_g=dl_g)
+    real_feat, fake_feat = xpool[:B], xpool[B:]
+    if cfg.sentence_contrastive:
+      ctx["real_sent"] = Contrastive(real_feat, sent, losses[LOSS_SLOTS["real_sent"]:])
+      if need_g:
+        ctx["fake_sent"] = Contrastive(fake_feat, sent, losses[LOSS_SLOTS["fake_sent"]:])
+    if cfg.word_contrastive:
+      rw = self.convs[(cp + "_0",)]
+      xw = ops.conv_fwd(x_cond, self._wk(rw), 1, E, bias=P[rw.b_off:], ldb=rw.ld_fwd)
+      Rn = xw.shape[1] * xw.shape[2]
+      ws = WordShared(batch["embedding"], batch["max_len"])
+      ctx["x_cond"] = x_cond
+      ctx["xw_shape"] = xw.shape
+      ctx["real_word"] = WordLoss(xw[:B].view(B, Rn, E), ws, losses[LOSS_SLOTS["real_word"]:])
+      if need_g:
+        ctx["fake_word"] = WordLoss(xw[B:].view(B, Rn, E), ws, losses[LOSS_SLOTS["fake_word"]:])
+    if cfg.image_contrastive and need_g:
+      ctx["image"] = Contrastive(fake_feat, real_feat, losses[LOSS_SLOTS["image"]:])
+    return logit, ctx
+
+  # ------------------------------------------------------------------------------------------------------------
+  def _wgrad(self, rec, x_in, dy, grads, dy_low=None):
+    ops.wgrad(x_in, dy, rec.kh, grads[rec.w_off:], out_mode=0, ld_out=rec.cout, tap_stride=rec.cin * rec.cout)
+    # the bias gradient of a conv whose output is average-pooled equals the column sum of the pooled gradient
+    ops.colsum(dy if dy_low is None else dy_low, grads[rec.b_off:])
+
+  def _backward_trunk(self, ctx, dout, sl, grads, d_xw, xw_sub, want_image_grad):
+    """Backward through the residual trunk for images `sl` (a slice of the 2B batch). dout: gradient wrt the last
+    block output. d_xw: gradient wrt the word-feature map (bf16 [n,16,16,E]) of the images `xw_sub` (a slice relative
+    to `sl`), or None. grads None -> dgrad only."""
+    P = None
+    cp = self.cpre
+    wg = grads is not None
+    for (name, cin, cout, down, proj, is_cond), sv in zip(reversed(self.blocks), reversed(ctx["blocks"])):
+      x, xr, c1r = sv["x"][sl], sv["xr"][sl], sv["c1r"][sl]
+      q0, q1 = self.convs[(name, cp + "_0")], self.convs[(name, cp + "_1")]
+      if is_cond and d_xw is not None:
+        rw = self.convs[(cp + "_0",)]
+        if wg:
+          self._wgrad(rw, ctx["x_cond"][sl][xw_sub], d_xw, grads)
+        # in place on the sub-batch that has a word-loss gradient (elementwise read-then-write of the same address)
+        ops.conv_fwd(d_xw, self._wd(rw), 1, rw.cin, residual=dout[xw_sub], out=dout[xw_sub], ldb=rw.ld_dg)
+      if down:
+        g = ops.unpool2(dout, 0.25)
+        dlow = dout
+      else:
+        g, dlow = dout, None
+      if wg:
+        self._wgrad(q1, c1r, g, grads, dlow)
+      dc1 = ops.conv_fwd(g, self._wd(q1), 3, cout, mask=c1r, ldb=q1.ld_dg)
+      if proj:
+        q2 = self.convs[(name, cp + "_2")]
+        if wg:
+          self._wgrad(q2, x, g, grads, dlow)
+        dxb = ops.conv_fwd(g, self._wd(q2), 1, cin, ldb=q2.ld_dg)
+      else:
+        dxb = g
+      if wg:
+        self._wgrad(q0, xr, dc1, grads)
+      dout = ops.conv_fwd(dc1, self._wd(q0), 3, cin, mask=xr, residual=dxb, ldb=q0.ld_dg)
+    # ---- DiscOptimizedBlock_0 ------------------------------------------------------------------------------------
+    r0, r1, r2 = (self.convs[("DiscOptimizedBlock_0", cp + f"_{i}")] for i in range(3))
+    b0 = ctx["b0"]
+    images = ctx["images"][sl]
+    xp, c1r = b0["xp"][sl], b0["c1r"][sl]
+    n, S = images.shape[0], images.shape[1]
+    df = r1.cout
+    g = ops.unpool2(dout, 0.25)
+    if wg:
+      self._wgrad(r1, c1r, g, grads, dout)
+    dc1 = ops.conv_fwd(g, self._wd(r1), 3, df, mask=c1r, ldb=r1.ld_dg)
+    if wg:
+      ops._call("xmc_wgrad_c3", images.data_ptr(), dc1.data_ptr(), n, S, S, df, 3, 3, 0, 3 * df, df, 1,
+                grads[r0.w_off:].data_ptr(), _lib.stream())
+      ops.colsum(dc1, grads[r0.b_off:])
+      ops._call("xmc_wgrad_c3", xp.data_ptr(), dout.data_ptr(), n, S // 2, S // 2, df, 1, 1, 0, 3 * df, df, 1,
+                grads[r2.w_off:].data_ptr(), _lib.stream())
+      ops.colsum(dout, grads[r2.b_off:])
+    if not want_image_grad:
+      return None
+    dimg = ops.empty((n, S, S, 3), F32)
+    ops._call("xmc_conv_c3_out", dc1.data_ptr(), self._wd(r0).data_ptr(), r0.ld_dg, None, n, S, S, df, 3, 3, 0, 0,
+              dimg.data_ptr(), None, _lib.stream())
+    dxp = ops.empty((n, S // 2, S // 2, 3), F32)
+    ops._call("xmc_conv_c3_out", dout.data_ptr(), self._wd(r2).data_ptr(), r2.ld_dg, None, n, S // 2, S // 2, df, 1, 1,
+              0, 0, dxp.data_ptr(), None, _lib.stream())
+    ops._call("xmc_unpool2_add_f32", dxp.data_ptr(), n, S // 2, S // 2, 3, 0.25, dimg.data_ptr(), _lib.stream())
+    return dimg
+
+  def backward_d(self, ctx, params, grads):
+    """d(d_loss)/d(params_d) accumulated into `grads` (holds d/dW~ for spectrally normalised kernels until
+    sn_backward runs). d_loss = hinge_d + real_word + real_sentence (xmc_gan.py:146-153,237-241)."""
+    P = params
+    B, C, E = ctx["B"], self.c_last, self.E
+    N2 = 2 * B
+    rd0, rd1 = self.convs[(self.dpre + "_0",)], self.convs[(self.dpre + "_1",)]
+    dxpool = ops.empty((N2, C), F32)
+    dsent = ops.zeros((B, C), F32)
+    inv0 = self._inv_sigma(rd0)
+    ops._call("xmc_proj_logit_bwd", ctx["dl_d"].data_ptr(), ctx["xpool"].data_ptr(), P[rd0.w_off:].data_ptr(),
+              inv0.data_ptr() if inv0 is not None else None, ctx["sent"].data_ptr(), 0, N2, B, C, dxpool.data_ptr(), 0,
+              grads[rd0.w_off:].data_ptr(), grads[rd0.b_off:].data_ptr(), dsent.data_ptr(), _lib.stream())
+    if "real_sent" in ctx:
+      ctx["real_sent"].bwd_a(dxpool[:B])
+      ctx["real_sent"].bwd_b(dsent)
+    dsent_bf = ops.cast_to_bf16(dsent)
+    ops.wgrad(as4(ctx["cond_bf"]), as4(dsent_bf), 1, grads[rd1.w_off:], out_mode=0, ld_out=C, tap_stride=E * C)
+    ops.colsum_f32(dsent, grads[rd1.b_off:])
+    dout = ops.relu_sumhw_bwd(ctx["x_last"], dxpool)
+    d_xw = None
+    if "real_word" in ctx:
+      # only the real half has a word-loss gradient for d_loss
+      shp = ctx["xw_shape"]
+      d_xw = ctx["real_word"].bwd().view(B, shp[1], shp[2], E)
+    self._backward_trunk(ctx, dout, slice(0, N2), grads, d_xw, slice(0, B), False)
+
+  def backward_g(self, ctx, params):
+    """d(g_loss)/d(fake images): fp32 [B,S,S,3]. g_loss's discriminator part = hinge_g + fake_word + fake_sentence +
+    image_contrastive (xmc_gan.py:146-154). Only the fake half is pulled back, dgrad only."""
+    P = params
+    B, C, E = ctx["B"], self.c_last, self.E
+    rd0 = self.convs[(self.dpre + "_0",)]
+    dxpool = ops.empty((2 * B, C), F32)
+    inv0 = self._inv_sigma(rd0)
+    ops._call("xmc_proj_logit_bwd", ctx["dl_g"].data_ptr(), ctx["xpool"].data_ptr(), P[rd0.w_off:].data_ptr(),
+              inv0.data_ptr() if inv0 is not None else None, ctx["sent"].data_ptr(), B, B, B, C, dxpool.data_ptr(), 0,
+              None, None, None, _lib.stream())
+    dfake = dxpool[B:]
+    if "fake_sent" in ctx:
+      ctx["fake_sent"].bwd_a(dfake)
+    if "image" in ctx:
+      ctx["image"].bwd_a(dfake)
+    sl = slice(B, 2 * B)
+    dout = ops.relu_sumhw_bwd(ctx["x_last"][sl], dfake)
+    d_xw = None
+    if "fake_word" in ctx:
+      shp = ctx["xw_shape"]
+      d_xw = ctx["fake_word"].bwd().view(B, shp[1], shp[2], E)
+    return self._backward_trunk(ctx, dout, sl, None, d_xw, slice(0, B), True)

@@ -1,0 +1,303 @@
+"""Thin tensor-level wrappers over the libxmc.so C ABI. torch tensors are only device-memory containers here; every
+arithmetic operation below is a hand-written sm_100a kernel. Each wrapper counts its kernel launches in LAUNCHES."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import BnDesc, ConvDesc, WgradDesc, ptr, stream
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+LAUNCHES = [0]
+
+
+def _call(name, *args, launches=1):
+  fn = getattr(_lib.lib(), name)
+  _lib.check(fn(*args))
+  LAUNCHES[0] += launches
+
+
+def _pix_ld(t):
+  """Pitch (elements) between consecutive pixels/rows of a tensor whose last dim is contiguous."""
+  assert t.stride(-1) == 1
+  return t.stride(-2)
+
+
+def _check_dense_rows(t):
+  """All leading dims must collapse into one row index with pitch stride(-2)."""
+  ld = t.stride(-2)
+  exp = ld
+  for d in range(t.dim() - 2, -1, -1):
+    assert t.stride(d) == exp or t.shape[d] == 1, f"non-collapsible layout {t.shape} {t.stride()}"
+    exp *= t.shape[d]
+
+
+def empty(shape, dtype=BF16):
+  return torch.empty(shape, device="cuda", dtype=dtype)
+
+
+def zeros(shape, dtype=F32):
+  return torch.zeros(shape, device="cuda", dtype=dtype)
+
+
+# ------------------------------------------------------------------------------------------------------------- GEMMs
+def conv_fwd(x, wk, kh, cout, *, bias=None, residual=None, res_shift=0, mask=None, relu=False, out=None,
+             out_dtype=BF16, alpha=1.0, ldb=None, batched=False, stride_b=0, c=None):
+  """x: [N,H,W,>=C] bf16 view (channel-contiguous); wk: bf16 tensor whose data pointer is the [cout][kh*kh*C] K-major
+  matrix (row pitch ldb). Returns y [N,H,W,cout] (or writes into the `out` view)."""
+  N, H, W = x.shape[0], x.shape[1], x.shape[2]
+  C = x.shape[3] if c is None else c
+  _check_dense_rows(x)
+  d = ConvDesc()
+  d.N, d.H, d.W, d.C, d.ldA = N, H, W, C, _pix_ld(x)
+  d.KH = d.KW = kh
+  d.pad_h = d.pad_w = kh // 2
+  d.Cout = cout
+  d.ldB = ldb if ldb is not None else kh * kh * C
+  d.batched = 1 if batched else 0
+  d.strideB_batch = stride_b
+  if out is None:
+    out = empty((N, H, W, cout), out_dtype)
+  else:
+    _check_dense_rows(out)
+  d.out_dtype = 0 if out.dtype == BF16 else 1
+  d.ldOut = _pix_ld(out)
+  d.alpha = alpha
+  d.relu = 1 if relu else 0
+  d.res_shift = res_shift
+  d.ldRes = _pix_ld(residual) if residual is not None else 0
+  d.ldMask = _pix_ld(mask) if mask is not None else 0
+  _call("xmc_conv2d_fwd", ctypes.byref(d), ptr(x), ptr(wk), ptr(bias), ptr(residual), ptr(mask), ptr(out), stream())
+  return out
+
+
+def wgrad(xa, xb, kh, out, *, out_mode=0, batched=False, ld_out=None, tap_stride=None, batch_stride=0, alpha=1.0,
+          ca=None, cb=None):
+  """out[b][tap][ca][cb] (+)= sum_pixels xa[p+shift][ca] * xb[p][cb]. xa, xb: [N,H,W,C*] bf16 views."""
+  N, H, W = xa.shape[0], xa.shape[1], xa.shape[2]
+  _check_dense_rows(xa)
+  _check_dense_rows(xb)
+  d = WgradDesc()
+  d.N, d.H, d.W = N, H, W
+  d.Ca = xa.shape[3] if ca is None else ca
+  d.Cb = xb.shape[3] if cb is None else cb
+  d.ldA, d.ldB = _pix_ld(xa), _pix_ld(xb)
+  d.KH = d.KW = kh
+  d.pad_h = d.pad_w = kh // 2
+  d.batched = 1 if batched else 0
+  d.out_mode = out_mode
+  d.ldOut = d.Cb if ld_out is None else ld_out
+  d.out_tap_stride = d.Ca * d.Cb if tap_stride is None else tap_stride
+  d.out_batch_stride = batch_stride
+  d.alpha = alpha
+  _call("xmc_conv2d_wgrad", ctypes.byref(d), ptr(xa), ptr(xb), ptr(out), stream())
+  return out
+
+
+# --------------------------------------------------------------------------------------------------------- batch norm
+def _bn_desc(N, H, W, C, Hc, ldG, goff, boff, relu, upsample):
+  d = BnDesc()
+  d.N, d.H, d.W, d.C, d.Hc = N, H, W, C, Hc
+  d.ldG, d.goff, d.boff = ldG, goff, boff
+  d.relu, d.upsample = int(relu), int(upsample)
+  return d
+
+
+def bn_stats(x):
+  C = x.shape[-1]
+  P = x.numel() // C
+  sums = zeros(2 * C)
+  LAUNCHES[0] += 1  # the zero fill
+  _call("xmc_bn_stats", ptr(x), P, C, C, ptr(sums), stream())
+  return sums, P
+
+
+def bn_finalize(sums, P, C, ra_mean, ra_var, new_ra_mean, new_ra_var, eps=1e-5, momentum=0.9):
+  mr = empty(2 * C, F32)
+  _call("xmc_bn_finalize", ptr(sums), P, C, eps, momentum, ptr(ra_mean), ptr(ra_var), ptr(new_ra_mean),
+        ptr(new_ra_var), ptr(mr), stream())
+  return mr
+
+
+def bn_eval_stats(ra_mean, ra_var, C, eps=1e-5):
+  mr = empty(2 * C, F32)
+  _call("xmc_bn_eval_stats", ptr(ra_mean), ptr(ra_var), C, eps, ptr(mr), stream())
+  return mr
+
+
+def bn_apply(x, mr, gb, Hc, goff, boff, relu, upsample):
+  N, H, W, C = x.shape
+  d = _bn_desc(N, H, W, C, Hc, gb.stride(0), goff, boff, relu, upsample)
+  y = empty((N, 2 * H, 2 * W, C) if upsample else (N, H, W, C))
+  _call("xmc_bn_apply", ctypes.byref(d), ptr(x), ptr(mr), ptr(gb), ptr(y), stream())
+  return y
+
+
+def bn_bwd(dy, x, mr, gb, dgb, Hc, goff, boff, relu, upsample):
+  """Returns dx (bf16, shape of x); writes d(gamma), d(beta) into the fp32 matrix dgb (same layout as gb)."""
+  N, H, W, C = x.shape
+  assert gb.stride(0) == dgb.stride(0)
+  d = _bn_desc(N, H, W, C, Hc, gb.stride(0), goff, boff, relu, upsample)
+  sums = zeros(2 * C)
+  LAUNCHES[0] += 1
+  _call("xmc_bn_bwd_reduce", ctypes.byref(d), ptr(dy), ptr(x), ptr(mr), ptr(gb), ptr(dgb), ptr(sums), stream())
+  dx = empty((N, H, W, C))
+  _call("xmc_bn_bwd_apply", ctypes.byref(d), ptr(dy), ptr(x), ptr(mr), ptr(gb), ptr(sums), ptr(dx), stream())
+  return dx
+
+
+# ------------------------------------------------------------------------------------------------- pooling and misc
+def pool2(a, b=None, low=None, scale=0.25, want_relu=False):
+  N, H2, W2, C = a.shape
+  out = empty((N, H2 // 2, W2 // 2, C))
+  out_relu = empty((N, H2 // 2, W2 // 2, C)) if want_relu else None
+  _call("xmc_pool2", ptr(a), ptr(b), ptr(low), N, H2 // 2, W2 // 2, C, scale, ptr(out), ptr(out_relu), stream())
+  return (out, out_relu) if want_relu else out
+
+
+def unpool2(dout, scale=0.25):
+  N, H, W, C = dout.shape
+  g = empty((N, 2 * H, 2 * W, C))
+  _call("xmc_unpool2", ptr(dout), N, H, W, C, scale, ptr(g), stream())
+  return g
+
+
+def colsum(x, out, c=None):
+  """out[c] += sum over all leading dims of x[..., c] (x bf16)."""
+  C = x.shape[-1] if c is None else c
+  _check_dense_rows(x)
+  P = x.numel() // x.shape[-1]
+  _call("xmc_colsum", ptr(x), P, C, _pix_ld(x), ptr(out), stream())
+
+
+def relu_sumhw(x):
+  N, H, W, C = x.shape
+  out = empty((N, C), F32)
+  _call("xmc_relu_sumhw", ptr(x), N, H * W, C, ptr(out), stream())
+  return out
+
+
+def relu_sumhw_bwd(x, dout):
+  N, H, W, C = x.shape
+  dx = empty((N, H, W, C))
+  _call("xmc_relu_sumhw_bwd", ptr(x), ptr(dout), N, H * W, C, ptr(dx), stream())
+  return dx
+
+
+def cast_to_bf16(src, dst=None):
+  """2-D (rows, cols) fp32 -> bf16, pitched views allowed."""
+  rows, cols = src.shape
+  if dst is None:
+    dst = empty((rows, cols))
+  _call("xmc_cast_f32_to_bf16", ptr(src), rows, cols, src.stride(0), ptr(dst), dst.stride(0), stream())
+  return dst
+
+
+def cast_to_f32(src, dst=None, accumulate=False):
+  rows, cols = src.shape
+  if dst is None:
+    dst = empty((rows, cols), F32)
+  _call("xmc_cast_bf16_to_f32", ptr(src), rows, cols, src.stride(0), ptr(dst), dst.stride(0), int(accumulate),
+        stream())
+  return dst
+
+
+def bcast_rows(src, reps, dst):
+  """dst[b*reps + r, :] = src[b, :]; dst is a [B*reps, cols] pitched bf16 view."""
+  B, cols = src.shape
+  _call("xmc_bcast_rows", ptr(src), B, reps, cols, src.stride(0), ptr(dst), dst.stride(0), stream())
+
+
+def sum_rows(src, B, reps, dst, accumulate=False):
+  cols = src.shape[-1]
+  _call("xmc_sum_rows", ptr(src), B, reps, cols, src.stride(0), ptr(dst), dst.stride(0), int(accumulate), stream())
+
+
+def axpy(y, x, a=1.0):
+  _call("xmc_axpy_f32", ptr(y), ptr(x), a, y.numel(), stream())
+
+
+def colsum_f32(x, out):
+  rows, cols = x.shape
+  _call("xmc_colsum_f32", ptr(x), rows, cols, x.stride(0), ptr(out), stream())
+
+
+# -------------------------------------------------------------------------------------------- attention / word loss
+def l2norm_rows(x, out_dtype=F32, want_out=True, eps=1e-12):
+  """x: [rows, D] (fp32 or bf16, pitched). Returns (xhat or None, invnorm)."""
+  rows, D = x.shape
+  y = empty((rows, D), out_dtype) if want_out else None
+  inv = empty(rows, F32)
+  _call("xmc_l2norm_rows", ptr(x), int(x.dtype == F32), rows, D, x.stride(0), ptr(y), int(out_dtype == F32),
+        D, ptr(inv), eps, stream())
+  return y, inv
+
+
+def l2norm_rows_bwd(dxhat, xhat, inv, out=None, accumulate=False):
+  rows, D = xhat.shape
+  if out is None:
+    out = empty((rows, D), dxhat.dtype)
+  _call("xmc_l2norm_rows_bwd", ptr(dxhat), int(dxhat.dtype == F32), dxhat.stride(0), ptr(xhat),
+        int(xhat.dtype == F32), xhat.stride(0), ptr(inv), rows, D, ptr(out), int(out.dtype == F32), out.stride(0),
+        int(accumulate), stream())
+  return out
+
+
+def attention_g_fwd(q, what, max_len, gamma, ctx_out):
+  """q: [B,R,D] bf16; what: [B,L,D] fp32 normalised words; ctx_out: [B*R, >=D] bf16 pitched view."""
+  B, R, D = q.shape
+  L = what.shape[1]
+  attn = empty((B * R, L), F32)
+  _call("xmc_attention_g_fwd", ptr(q), q.stride(1), ptr(what), ptr(max_len), B, R, L, D, float(gamma), ptr(ctx_out),
+        ctx_out.stride(0), ptr(attn), stream())
+  return attn
+
+
+def attention_g_bwd(dctx, q, what, attn, gamma):
+  B, R, D = q.shape
+  L = what.shape[1]
+  dq = empty((B, R, D))
+  _call("xmc_attention_g_bwd", ptr(dctx), dctx.stride(0), ptr(q), q.stride(1), ptr(what), ptr(attn), B, R, L, D,
+        float(gamma), ptr(dq), D, stream())
+  return dq
+
+
+def transpose_bf16(src, ld_dst):
+  rows, cols = src.shape
+  dst = empty((cols, ld_dst))
+  _call("xmc_transpose_bf16", ptr(src), rows, cols, src.stride(0), ptr(dst), ld_dst, stream())
+  return dst
+
+
+# ----------------------------------------------------------------------------------------------------------- losses
+def small_gemm_nt(A, B, scale):
+  n, D = A.shape
+  m = B.shape[0]
+  C = empty((n, m), F32)
+  _call("xmc_small_gemm_nt", ptr(A), ptr(B), n, m, D, scale, ptr(C), stream())
+  return C
+
+
+def small_gemm_nn(G, transposed, X, scale, out=None, accumulate=False):
+  n = G.shape[1] if transposed else G.shape[0]
+  m = G.shape[0] if transposed else G.shape[1]
+  D = X.shape[1]
+  if out is None:
+    out = empty((n, D), F32)
+  _call("xmc_small_gemm_nn", ptr(G), int(transposed), ptr(X), n, m, D, scale, ptr(out), int(accumulate), stream())
+  return out
+
+
+def ce_sym(logits, loss_slot, weight=1.0, want_grad=True):
+  n = logits.shape[0]
+  dl = empty((n, n), F32) if want_grad else None
+  _call("xmc_ce_sym", ptr(logits), n, weight, ptr(loss_slot), ptr(dl), stream())
+  return dl
+
+
+def hinge(logit, B, d_slot, g_slot):
+  dd = empty(2 * B, F32)
+  dg = empty(2 * B, F32)
+  _call("xmc_hinge", ptr(logit), B, ptr(d_slot), ptr(g_slot), ptr(dd), ptr(dg), stream())
+  return dd, dg

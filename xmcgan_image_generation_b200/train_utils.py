@@ -1,0 +1,76 @@
+"""Counterparts of the hot-path symbols of xmcgan/train_utils.py: TrainState (:42-50), split_input_dict (:69-88),
+train_step (:91-130), create_train_state (:133-193). The outer loop (train/test, checkpoints, summaries) is out of
+scope."""
+import dataclasses
+import functools
+from typing import Any, Optional
+
+import torch
+
+from .nets import xmc_net
+
+
+class Optimizer:
+  """flax.optim.Optimizer(Adam) stand-in: `target` (the parameters), Adam moments and step count."""
+
+  def __init__(self, target, learning_rate, beta1, beta2, eps=1e-8):
+    self.target = target  # FlatTree
+    self.m = torch.zeros_like(target.buf)
+    self.v = torch.zeros_like(target.buf)
+    self.step = 0
+    self.learning_rate, self.beta1, self.beta2, self.eps = learning_rate, beta1, beta2, eps
+
+
+@dataclasses.dataclass
+class TrainState:
+  """train_utils.TrainState (train_utils.py:42-50)."""
+  step: int
+  g_optimizer: Optimizer
+  d_optimizer: Optimizer
+  generator_state: Optional[Any]
+  discriminator_state: Optional[Any]
+  ema_params: Any
+
+  def replace(self, **kw):
+    return dataclasses.replace(self, **kw)
+
+
+def split_input_dict(input_dict, splits, axis=0):
+  """train_utils.split_input_dict (train_utils.py:69-88): equal splits of every leaf along `axis` (views)."""
+  output = [dict() for _ in range(splits)]
+  for key, value in input_dict.items():
+    n = value.shape[axis]
+    if n % splits:
+      raise ValueError(f"cannot split axis of size {n} into {splits} equal parts")  # jnp.split raises as well
+    for i, part in enumerate(torch.split(torch.as_tensor(value), n // splits, dim=axis)):
+      output[i][key] = part
+  return output
+
+
+def train_step(rng, state, batch, gan_model, generator, discriminator, config, additional_data):
+  """train_utils.train_step (train_utils.py:91-130): d_step_per_g_step-1 discriminator steps, then one joint step."""
+  batch = xmc_net.batch_to_device(batch)
+  batches = split_input_dict(batch, config.d_step_per_g_step)
+  for i in range(config.d_step_per_g_step - 1):
+    state = gan_model.train_d(None, state, batches[i], generator, discriminator, config)
+  return gan_model.train_g_d(None, state, batches[-1], generator, discriminator, config, additional_data)
+
+
+def create_train_state(config, rng, init_batch):
+  """train_utils.create_train_state (train_utils.py:133-193)."""
+  dtype = torch.bfloat16 if config.dtype == "bfloat16" else torch.float32
+  if config.architecture == "xmc_net":
+    generator_cls, discriminator_cls = xmc_net.Generator, xmc_net.Discriminator
+  else:
+    raise ValueError(f"Architecture {config.architecture} is not supported.")
+  generator = functools.partial(generator_cls, config=config, dtype=dtype)
+  discriminator = functools.partial(discriminator_cls, config=config, dtype=dtype)
+  seed = xmc_net._seed_of(rng)
+  g_vars = dict(generator(train=False).init(seed * 3 + 1, (init_batch, None)))
+  g_params = g_vars.pop("params")
+  d_vars = dict(discriminator(train=False).init(seed * 3 + 2, (None, init_batch)))
+  d_params = d_vars.pop("params")
+  g_opt = Optimizer(g_params, config.g_lr, config.beta1, config.beta2)
+  d_opt = Optimizer(d_params, config.d_lr, config.beta1, config.beta2)
+  return generator, discriminator, TrainState(step=0, g_optimizer=g_opt, d_optimizer=d_opt, generator_state=g_vars,
+                                              discriminator_state=d_vars, ema_params=g_params.clone())

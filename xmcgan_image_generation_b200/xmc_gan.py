@@ -1,0 +1,178 @@
+"""Counterparts of xmcgan/xmc_gan.py: train_d (:194-256), train_g_d (:93-191), calculate_contrastive_loss (:58-71),
+create_additional_data (:43-55), TrainMetrics (:33-40).
+
+State handling: the returned TrainState reuses (and overwrites) the parameter / moment / statistics buffers of the
+state passed in — the argument is donated, as `state = p_train_step(state, ...)` in the reference loop
+(train_utils.py:424) discards the old state anyway."""
+import torch
+
+from . import engine as _engine
+from . import ops
+from . import parallel
+from .nets import xmc_net
+
+_S = _engine.LOSS_SLOTS
+
+
+class TrainMetrics:
+  """Cross-replica mean of the five loss scalars (clu.metrics.Average of xmc_gan.py:33-40, gathered at :185-190)."""
+  names = ("d_loss", "g_loss", "c_loss_d", "c_loss_g", "c_loss_g_pretrained")
+
+  def __init__(self, values):
+    self._values = values  # device fp32 [5], already averaged over replicas
+
+  @classmethod
+  def gather_from_model_output(cls, losses):
+    l = losses
+    d_c = l[_S["real_word"]] + l[_S["real_sent"]]
+    g_c = l[_S["fake_word"]] + l[_S["fake_sent"]] + l[_S["image"]]
+    vals = torch.stack([l[_S["hinge_d"]] + d_c, l[_S["hinge_g"]] + g_c + l[_S["pretrained"]], d_c, g_c,
+                        l[_S["pretrained"]]])
+    if parallel.world_size() > 1:
+      parallel.all_reduce_sum_(vals)
+      vals = vals / parallel.world_size()
+    return cls(vals)
+
+  def compute(self):
+    host = self._values.detach().float().cpu().tolist()  # device -> host read of the step's result
+    return dict(zip(self.names, host))
+
+
+def calculate_contrastive_loss(result_dict):
+  """xmc_gan.calculate_contrastive_loss (xmc_gan.py:58-71)."""
+  real_loss = result_dict["real_word_loss"] + result_dict["real_sentence_loss"]
+  fake_loss = result_dict["fake_word_loss"] + result_dict["fake_sentence_loss"]
+  return real_loss, fake_loss + result_dict["image_contrastive_loss"]
+
+
+def create_additional_data(config):
+  """xmc_gan.create_additional_data (xmc_gan.py:43-55). The frozen ResNet-50 branch is not built in this round."""
+  if config.pretrained_image_contrastive:
+    raise NotImplementedError(
+        "pretrained_image_contrastive=True (frozen ResNet-50 image-image InfoNCE, xmc_gan.py:74-90,148-152) is not "
+        "built yet; set config.pretrained_image_contrastive=False")
+  return {}
+
+
+class _Workspace:
+  """Persistent per-state device buffers (gradients, double-buffered statistics, loss slots)."""
+
+  def __init__(self, state, g_eng, d_eng):
+    self.g_grads = torch.zeros_like(state.g_optimizer.target.buf)
+    self.d_grads = torch.zeros_like(state.d_optimizer.target.buf)
+    self.g_stats_alt = torch.empty_like(state.generator_state["batch_stats"].buf)
+    self.u0_alt = torch.empty_like(state.discriminator_state["spectral_norm_stats"].buf) if d_eng.sn else None
+    self.g_prepped = False
+
+
+def _workspace(state, g_eng, d_eng):
+  ws = getattr(state, "_ws", None)
+  if ws is None:
+    ws = _Workspace(state, g_eng, d_eng)
+    object.__setattr__(state, "_ws", ws)
+  return ws
+
+
+def _engines(config, batch):
+  e = int(batch["embedding"].shape[-1])
+  return xmc_net.get_engine(config, "g", e), xmc_net.get_engine(config, "d", e)
+
+
+def _adam(opt, grads, ema=None, decay=0.0):
+  opt.step += 1
+  t = opt.step
+  ops._call("xmc_adam", opt.target.buf.data_ptr(), grads.data_ptr(), opt.m.data_ptr(), opt.v.data_ptr(),
+            opt.target.buf.numel(), opt.learning_rate, opt.beta1, opt.beta2, opt.eps, 1.0 - opt.beta1 ** t,
+            1.0 - opt.beta2 ** t, 1.0 / parallel.world_size(), ema.data_ptr() if ema is not None else None, decay,
+            ops._lib.stream())
+
+
+def _forward_both(state, batch, config, ws, g_eng, d_eng, losses, keep_g_state, need_g):
+  B = batch["z"].shape[0]
+  S = config.image_size
+  g_params = state.g_optimizer.target.buf
+  d_params = state.d_optimizer.target.buf
+  if not ws.g_prepped:
+    g_eng.prep_weights(g_params)
+    ws.g_prepped = True
+  u0 = state.discriminator_state["spectral_norm_stats"].buf if d_eng.sn else None
+  d_eng.prep_weights(d_params, u0, ws.u0_alt)
+  all_images = ops.empty((2 * B, S, S, 3))
+  ops.cast_to_bf16(batch["image"].reshape(B * S * S, 3), all_images[:B].view(B * S * S, 3))
+  fake, gctx = g_eng.forward(g_params, state.generator_state["batch_stats"].buf, batch, batch["z"], train=True,
+                             new_stats=ws.g_stats_alt if keep_g_state else None, fake_bf16=all_images[B:])
+  _, dctx = d_eng.forward(d_params, all_images, batch, losses, need_g=need_g)
+  return gctx, dctx
+
+
+def _swap_d_state(state, ws, d_eng):
+  if not d_eng.sn:
+    return state.discriminator_state
+  old = state.discriminator_state["spectral_norm_stats"]
+  new = xmc_net.FlatTree(d_eng.u_layout, ws.u0_alt)
+  ws.u0_alt = old.buf
+  return {"spectral_norm_stats": new}
+
+
+def train_d(rng, state, batch, generator, discriminator, config):
+  """xmc_gan.train_d (xmc_gan.py:194-256): d_loss = hinge_d + real_word + real_sentence; gradient wrt params_d only;
+  pmean; Adam on D; the generator's new batch statistics are discarded, the discriminator's new u0 is kept."""
+  batch = xmc_net.batch_to_device(batch)
+  g_eng, d_eng = _engines(config, batch)
+  ws = _workspace(state, g_eng, d_eng)
+  losses = torch.zeros(16, device="cuda")
+  gctx, dctx = _forward_both(state, batch, config, ws, g_eng, d_eng, losses, keep_g_state=False, need_g=False)
+  del gctx
+  d_params = state.d_optimizer.target.buf
+  ws.d_grads.zero_()
+  ops.LAUNCHES[0] += 1
+  d_eng.backward_d(dctx, d_params, ws.d_grads)
+  d_eng.sn_backward(d_params, ws.d_grads, ws.u0_alt)
+  parallel.all_reduce_sum_(ws.d_grads)
+  _adam(state.d_optimizer, ws.d_grads)
+  new_d_state = _swap_d_state(state, ws, d_eng)
+  new_state = state.replace(discriminator_state=new_d_state)
+  object.__setattr__(new_state, "_ws", ws)
+  return new_state
+
+
+def train_g_d(rng, state, batch, generator, discriminator, config, additional_data):
+  """xmc_gan.train_g_d (xmc_gan.py:93-191): one forward, two pull-backs at the old parameters (:162-167), pmean of
+  both gradients (:170-171), Adam on D and G (:172-173), polyak EMA (:174-177), metrics (:185-190)."""
+  if config.pretrained_image_contrastive:
+    raise NotImplementedError("pretrained_image_contrastive=True is not built yet (see create_additional_data)")
+  batch = xmc_net.batch_to_device(batch)
+  g_eng, d_eng = _engines(config, batch)
+  ws = _workspace(state, g_eng, d_eng)
+  losses = torch.zeros(16, device="cuda")
+  gctx, dctx = _forward_both(state, batch, config, ws, g_eng, d_eng, losses, keep_g_state=True, need_g=True)
+  g_params = state.g_optimizer.target.buf
+  d_params = state.d_optimizer.target.buf
+  # pull-back #1: d_loss -> params_d
+  ws.d_grads.zero_()
+  ops.LAUNCHES[0] += 1
+  d_eng.backward_d(dctx, d_params, ws.d_grads)
+  d_eng.sn_backward(d_params, ws.d_grads, ws.u0_alt)
+  h_d = parallel.all_reduce_sum_(ws.d_grads, async_op=True)
+  # pull-back #2: g_loss -> fake images -> params_g
+  d_fake = d_eng.backward_g(dctx, d_params)
+  del dctx
+  ws.g_grads.zero_()
+  ops.LAUNCHES[0] += 1
+  g_eng.backward(gctx, d_fake, g_params, ws.g_grads)
+  del gctx
+  h_g = parallel.all_reduce_sum_(ws.g_grads, async_op=True)
+  if h_d is not None:
+    h_d.wait()
+    h_g.wait()
+  _adam(state.d_optimizer, ws.d_grads)
+  _adam(state.g_optimizer, ws.g_grads, ema=state.ema_params.buf, decay=config.polyak_decay)
+  ws.g_prepped = False
+  old_stats = state.generator_state["batch_stats"]
+  new_g_state = {"batch_stats": xmc_net.FlatTree(g_eng.stats_layout, ws.g_stats_alt)}
+  ws.g_stats_alt = old_stats.buf
+  new_d_state = _swap_d_state(state, ws, d_eng)
+  new_state = state.replace(step=state.step + 1, generator_state=new_g_state, discriminator_state=new_d_state)
+  object.__setattr__(new_state, "_ws", ws)
+  metrics = TrainMetrics.gather_from_model_output(losses)
+  return new_state, metrics
