@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""Benchmark of XMC-GAN's train_step hot path (BASELINE.json metric: images/sec, G+D step, 128 px, bs=56 per GPU).
+
+  python bench.py --gpus N --steps K --warmup W              # B200 arm (this repo's CUDA path)
+  python bench.py --impl reference --gpus N --steps K ...    # the reference algorithm on the host CPU cores
+
+One *step* = one train_step = train_d on B examples + train_g_d on B examples (train_utils.py:91-130), i.e. 2B real
+images consumed per device; images/sec = world * 2B / t_step. Data: synthetic COCO-shaped batches (BERT-sized
+embeddings + noise), random-init weights. Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch
+import torch.distributed as dist
+
+E_DIM, N_WORDS = 768, 17
+PER_GPU_B = 56  # per-device sub-batch of train_d and of train_g_d (coco_xmc.py:49 with one device)
+
+
+def make_config(image_size=128):
+  from xmcgan_image_generation_b200.configs import coco_xmc
+  c = coco_xmc.get_config()
+  # the frozen ResNet-50 image-image InfoNCE branch (xmc_gan.py:148-152) is not built yet: stated in `config`
+  c.update(dict(image_size=image_size, pretrained_image_contrastive=False))
+  return c
+
+
+def synth_batch(n, config, seed):
+  """image U[0,1), embedding N(0,0.5^2), max_len U{3..17}, sentence = sum/len, z N(0,1)."""
+  g = torch.Generator().manual_seed(seed)
+  S = config.image_size
+  emb = torch.randn(n, N_WORDS, E_DIM, generator=g) * 0.5
+  max_len = torch.randint(3, N_WORDS + 1, (n, 1), generator=g).float()
+  return {"image": torch.rand(n, S, S, 3, generator=g), "embedding": emb, "max_len": max_len,
+          "sentence_embedding": emb.sum(1) / max_len, "z": torch.randn(n, config.z_dim, generator=g)}
+
+
+class ClockSampler:
+  """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+  Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+       "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+  def __init__(self, index):
+    self.rows, self.proc, self.index = [], None, index
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                    "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+      self.thread = threading.Thread(target=self._read, daemon=True)
+      self.thread.start()
+    except OSError:
+      self.proc = None
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.rows.append([x.strip() for x in line.split(",")])
+
+  def stop(self):
+    if self.proc is None:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    self.proc.terminate()
+    self.thread.join(timeout=2)
+    sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+    mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+    return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+            "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def algorithmic_tflop_per_step(B):
+  """BASELINE.md §3 / SURVEY.md §8(d), 128 px, ResNet branch off: 25.55 TFLOP at B=56 (scaled by its B and B^2 parts)."""
+  wl = 0.01337e-3 * B * B              # TFLOP per word_loss forward call
+  g, d = 43.40e-3, 21.23e-3            # TFLOP per image forward (algorithmic G, D)
+  train_d = g * B + d * 2 * B * 3 + 3 * wl
+  train_g_d = 3 * g * B + d * 2 * B * 3 + d * B + 6 * wl
+  return train_d + train_g_d
+
+
+class GemmTimer:
+  """CUDA-event timing of every tcgen05 GEMM launch (on the launching stream) + its algorithmic FLOPs."""
+
+  def __init__(self):
+    self.records = []  # (kernel, flops, start_event, end_event)
+
+  def install(self, ops):
+    self.ops = ops
+    self._fwd, self._wgrad = ops.conv_fwd, ops.wgrad
+    timer = self
+
+    def conv_fwd(x, wk, kh, cout, **kw):
+      c = kw.get("c") or x.shape[3]
+      flops = 2.0 * x.shape[0] * x.shape[1] * x.shape[2] * kh * kh * c * cout
+      s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      s.record()
+      out = timer._fwd(x, wk, kh, cout, **kw)
+      e.record()
+      timer.records.append(("gemm_fwd_kernel", flops, s, e))
+      return out
+
+    def wgrad(xa, xb, kh, out, **kw):
+      ca = kw.get("ca") or xa.shape[3]
+      cb = kw.get("cb") or xb.shape[3]
+      flops = 2.0 * xa.shape[0] * xa.shape[1] * xa.shape[2] * kh * kh * ca * cb
+      s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      s.record()
+      r = timer._wgrad(xa, xb, kh, out, **kw)
+      e.record()
+      timer.records.append(("gemm_wgrad_kernel", flops, s, e))
+      return r
+
+    ops.conv_fwd, ops.wgrad = conv_fwd, wgrad
+
+  def uninstall(self):
+    self.ops.conv_fwd, self.ops.wgrad = self._fwd, self._wgrad
+
+  def summary(self):
+    agg = {}
+    for k, fl, s, e in self.records:
+      a = agg.setdefault(k, [0, 0.0, 0.0])
+      a[0] += 1
+      a[1] += fl
+      a[2] += s.elapsed_time(e)
+    return {k: {"launches": v[0], "tflop": v[1] / 1e12, "ms": v[2]} for k, v in agg.items()}
+
+
+def run_b200(args):
+  from xmcgan_image_generation_b200 import ops, train_utils, xmc_gan
+  rank = int(os.environ.get("RANK", "0"))
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  local = int(os.environ.get("LOCAL_RANK", "0"))
+  torch.cuda.set_device(local)
+  if world > 1:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+  config = make_config(args.image_size)
+  B = args.batch
+  config.batch_size = B * world
+  host = synth_batch(2 * B, config, 42 + rank)
+  pinned = {k: v.pin_memory() for k, v in host.items()}
+  dev = {k: v.cuda() for k, v in host.items()}
+  generator, discriminator, state = train_utils.create_train_state(config, 42, host)
+  additional = {}
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  def max_over_ranks(ms):
+    if world == 1:
+      return ms
+    t = torch.tensor([ms], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.item()
+
+  # ---- warm-up ------------------------------------------------------------------------------------------------------
+  metrics = None
+  for _ in range(args.warmup):
+    state, metrics = train_utils.train_step(None, state, dev, xmc_gan, generator, discriminator, config, additional)
+  barrier()
+
+  # ---- timed: inputs resident in HBM -----------------------------------------------------------------------------------
+  sampler = ClockSampler(local)
+  if rank == 0:
+    sampler.start()
+  timer = GemmTimer()
+  timer.install(ops)
+  launches0 = ops.LAUNCHES[0]
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  barrier()
+  e0.record()
+  for _ in range(args.steps):
+    state, metrics = train_utils.train_step(None, state, dev, xmc_gan, generator, discriminator, config, additional)
+  e1.record()
+  barrier()
+  ms_dev = max_over_ranks(e0.elapsed_time(e1))
+  launches = ops.LAUNCHES[0] - launches0
+  gemm = timer.summary()
+  timer.uninstall()
+  clocks = sampler.stop() if rank == 0 else None
+  last = metrics.compute()
+
+  # ---- timed: end to end through the public API with host buffers ------------------------------------------------------
+  h2d = sum(v.numel() * v.element_size() for v in pinned.values())
+  barrier()
+  e0.record()
+  for _ in range(args.steps):
+    step_in = {k: v.cuda(non_blocking=True) for k, v in pinned.items()}
+    state, metrics = train_utils.train_step(None, state, step_in, xmc_gan, generator, discriminator, config, additional)
+    last = metrics.compute()  # device -> host read of the step's result
+  e1.record()
+  barrier()
+  ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+
+  if rank != 0:
+    if world > 1:
+      dist.destroy_process_group()
+    return
+  peaks = {}
+  ppath = os.path.join(ROOT, "MEASURED_PEAKS.json")
+  if os.path.exists(ppath):
+    peaks = json.load(open(ppath))
+  peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+  peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained"
+  dom = max(gemm, key=lambda k: gemm[k]["ms"]) if gemm else None
+  roofline = None
+  if dom:
+    ach = gemm[dom]["tflop"] / (gemm[dom]["ms"] / 1e3)
+    roofline = {"bound": "tensor", "kernel": dom, "achieved": round(ach, 1), "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": round(ach / peak_tf, 4), "traffic": None, "peak_source": peak_src,
+                "launches_timed": gemm[dom]["launches"],
+                "share_of_step": round(gemm[dom]["ms"] / ms_dev, 3),
+                "all_gemm": {k: {"tflops": round(v["tflop"] / (v["ms"] / 1e3), 1), "ms_per_step":
+                                 round(v["ms"] / args.steps, 2)} for k, v in gemm.items()}}
+  imgs = world * 2 * B * args.steps
+  out = {
+      "metric": "images/sec (G+D train_step, 128px, bs=56 per GPU)", "value": round(imgs / (ms_dev / 1e3), 2),
+      "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+      "ms_per_step": round(ms_dev / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+      "dtype": "bf16", "data": "synthetic",
+      "config": {"workload": f"coco_xmc.py {config.image_size}px, per-GPU sub-batch B={B} (2B real images per step), "
+                             "train_d + train_g_d, Adam, EMA, grad all-reduce",
+                 "global_batch": B * world, "parallelism": f"dp{world}",
+                 "pretrained_image_contrastive": False,
+                 "l2": "per-step working set (several GB of activations) >> 126 MB L2; no explicit flush",
+                 "algorithmic_tflop_per_step_per_gpu": round(algorithmic_tflop_per_step(B), 2),
+                 "model_tflops_per_gpu": round(algorithmic_tflop_per_step(B) / (ms_dev / args.steps / 1e3), 1)},
+      "e2e": {"value": round(imgs / (ms_e2e / 1e3), 2), "unit": "images/sec", "h2d_bytes_per_step": h2d,
+              "d2h_bytes_per_step": 20},
+      "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "losses": last,
+  }
+  if world == 1 and not args.no_cpu_baseline:
+    out["cpu_baseline"] = cpu_baseline(args, quick=True)
+  print(json.dumps(out), flush=True)
+  if world > 1:
+    dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def _oracle_state(config, seed=1):
+  from oracle import xmc_oracle as orc
+  from xmcgan_image_generation_b200 import engine
+  g = engine.GeneratorEngine(config, E_DIM)
+  d = engine.DiscriminatorEngine(config, E_DIM)
+  gp = engine.init_flat(g.layout, seed, engine._kind)
+  gs = engine.init_flat(g.stats_layout, seed + 1, engine._kind)
+  dp = engine.init_flat(d.layout, seed + 2, engine._kind)
+  du = engine.init_flat(d.u_layout, seed + 3, engine._kind)
+  return orc.make_state({"params": g.layout.tree(gp), "batch_stats": g.stats_layout.tree(gs)},
+                        {"params": d.layout.tree(dp), "spectral_norm_stats": d.u_layout.tree(du)})
+
+
+def cpu_baseline(args, quick):
+  """The reference algorithm (oracle restatement, torch-CPU fp32 ops, all host threads) on a bounded sample."""
+  from oracle import xmc_oracle as orc
+  cores = os.cpu_count() or 1
+  torch.set_num_threads(cores)
+  config = make_config(args.image_size)
+  Bc = 2
+  state = _oracle_state(config)
+  batch = synth_batch(2 * Bc, config, 42)
+  n = 1 if quick else max(1, args.steps)
+  if not quick:
+    for _ in range(min(1, args.warmup)):
+      state, _ = orc.train_step(state, batch, config, orc.FP32)
+  t0 = time.time()
+  for _ in range(n):
+    state, _ = orc.train_step(state, batch, config, orc.FP32)
+  dt = (time.time() - t0) / n
+  return {"value": round(2 * Bc / dt, 4), "unit": "images/sec", "cores": cores, "kind": "port",
+          "sample": f"{n} train_step(s) of the torch-CPU fp32 restatement at per-device sub-batch B={Bc} "
+                    f"({2 * Bc} real images per step), 128px, full-width networks",
+          "sec_per_step": round(dt, 2)}
+
+
+def run_reference(args):
+  rank = int(os.environ.get("RANK", "0"))
+  if rank != 0:
+    return
+  cb = cpu_baseline(args, quick=False)
+  out = {"impl": "reference", "metric": "images/sec (G+D train_step, 128px, bs=56 per GPU)", "value": cb["value"],
+         "unit": "images/sec", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+         "ms_per_step": round(cb["sec_per_step"] * 1e3, 1), "higher_is_better": True, "scaling": "weak",
+         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+         "config": {"workload": "coco_xmc.py 128px train_step, reference algorithm (CPU restatement: JAX/Flax are not "
+                                "installable here), bounded sample", "pretrained_image_contrastive": False},
+         "cpu_baseline": cb,
+         "e2e": {"value": cb["value"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+  print(json.dumps(out), flush=True)
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=10)
+  ap.add_argument("--warmup", type=int, default=3)
+  ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+  ap.add_argument("--batch", type=int, default=PER_GPU_B, help="per-GPU sub-batch B")
+  ap.add_argument("--image-size", type=int, default=128)
+  ap.add_argument("--no-cpu-baseline", action="store_true")
+  args = ap.parse_args()
+  if args.warmup < 3 and args.impl == "b200":
+    args.warmup = 3
+  if args.impl == "reference":
+    run_reference(args)
+  else:
+    run_b200(args)
+
+
+if __name__ == "__main__":
+  main()
