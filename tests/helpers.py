@@ -1,0 +1,44 @@
+"""Shared builders for the parity tests: small configs, synthetic COCO-shaped batches, oracle <-> product state."""
+import torch
+
+from xmcgan_image_generation_b200.configs import coco_xmc
+
+
+def small_config(**kw):
+  c = coco_xmc.get_config()
+  c.update(dict(gf_dim=16, df_dim=16, z_dim=8, batch_size=8, pretrained_image_contrastive=False))
+  c.update(kw)
+  return c
+
+
+def make_batch(n, config, E=64, L=17, seed=0, min_len=3):
+  g = torch.Generator().manual_seed(seed)
+  S = config.image_size
+  emb = torch.randn(n, L, E, generator=g) * 0.5
+  max_len = torch.randint(min_len, L + 1, (n, 1), generator=g).float()
+  return {"image": torch.rand(n, S, S, 3, generator=g), "embedding": emb, "max_len": max_len,
+          "sentence_embedding": emb.sum(1) / max_len, "z": torch.randn(n, config.z_dim, generator=g)}
+
+
+def cpu_variables(config, E=64, seed=1, bias_scale=0.1):
+  """Random G/D variable trees on the CPU (same layouts/names as the product, no GPU needed)."""
+  from xmcgan_image_generation_b200 import engine
+  g = engine.GeneratorEngine(config, E)
+  d = engine.DiscriminatorEngine(config, E)
+  bufs = [engine.init_flat(g.layout, seed, engine._kind), engine.init_flat(g.stats_layout, seed + 1, engine._kind),
+          engine.init_flat(d.layout, seed + 2, engine._kind), engine.init_flat(d.u_layout, seed + 3, engine._kind)]
+  gen = torch.Generator().manual_seed(seed + 4)
+  for lay, buf in ((g.layout, bufs[0]), (d.layout, bufs[2])):
+    for path, (off, shape) in lay.entries.items():
+      if path[-1] == "bias":
+        n = int(torch.tensor(shape).prod())
+        buf[off:off + n] = torch.randn(n, generator=gen) * bias_scale
+  g_vars = {"params": g.layout.tree(bufs[0]), "batch_stats": g.stats_layout.tree(bufs[1])}
+  d_vars = {"params": d.layout.tree(bufs[2]), "spectral_norm_stats": d.u_layout.tree(bufs[3])}
+  return g, d, g_vars, d_vars
+
+
+def rel(a, b):
+  a = a.detach().float().cpu()
+  b = b.detach().float().cpu()
+  return ((a - b).norm() / (b.norm() + 1e-12)).item()

@@ -1,0 +1,132 @@
+"""CPU-side tests: the C-ABI library loads and exports every declared symbol, parameter layouts reproduce the
+reference's variable trees, host logic (config surface, splitting, device groups, error conventions)."""
+import ctypes
+
+import pytest
+import torch
+
+from tests import helpers
+from xmcgan_image_generation_b200 import _lib, engine, parallel, train_utils
+from xmcgan_image_generation_b200.configs import coco_xmc
+
+
+def test_library_exports_every_declared_symbol():
+  decl = _lib.declared_functions()
+  assert len(decl) >= 45
+  L = _lib.lib()
+  for name in decl:
+    assert hasattr(L, name), name
+  assert L.xmc_version() >= 100
+  assert L.xmc_strerror(-1).decode().startswith("invalid")
+
+
+def test_abi_rejects_bad_descriptors_without_touching_the_gpu():
+  L = _lib.lib()
+  d = _lib.ConvDesc()
+  assert L.xmc_conv2d_fwd(ctypes.byref(d), None, None, None, None, None, None, None) == -1
+  w = _lib.WgradDesc()
+  assert L.xmc_conv2d_wgrad(ctypes.byref(w), None, None, None, None) == -1
+  assert L.xmc_adam(None, None, None, None, 16, 0.1, 0.5, 0.9, 1e-8, 0.5, 0.1, 1.0, None, 0.0, None) == -1
+
+
+def test_parameter_counts_match_reference():
+  """G 78 507 779 / D 87 911 713 (128 px); 92 865 539 / 99 415 585 (256 px)."""
+  import numpy as np
+  for size, ng, nd in ((128, 78507779, 87911713), (256, 92865539, 99415585)):
+    c = coco_xmc.get_config()
+    c.image_size = size
+    g, d = engine.GeneratorEngine(c), engine.DiscriminatorEngine(c)
+    assert sum(int(np.prod(s)) for _, s in g.layout.entries.values()) == ng
+    assert sum(int(np.prod(s)) for _, s in d.layout.entries.values()) == nd
+
+
+def test_variable_tree_names_follow_flax_auto_naming():
+  c = coco_xmc.get_config()
+  g, d = engine.GeneratorEngine(c), engine.DiscriminatorEngine(c)
+  gp = g.layout.entries
+  assert gp[("Dense_0", "kernel")][1] == (768, 128)
+  assert gp[("Dense_1", "kernel")][1] == (128, 24576)
+  assert gp[("GenBlock_0", "ConditionalBatchNorm_0", "Dense_1", "kernel")][1] == (256, 1536)
+  assert gp[("GenBlock_1", "Conv_0", "kernel")][1] == (3, 3, 1536, 768)
+  assert gp[("GenBlock_1", "Conv_2", "kernel")][1] == (1, 1, 1536, 768)
+  assert gp[("Conv_0", "kernel")][1] == (1, 1, 768, 768)
+  assert gp[("GenSpatialBlock_2", "LocalConditionalBatchNorm_1", "Conv_0", "kernel")][1] == (1, 1, 1024, 96)
+  assert gp[("LocalConditionalBatchNorm_0", "Conv_1", "bias")][1] == (96,)
+  assert gp[("Conv_1", "kernel")][1] == (3, 3, 96, 3)
+  assert len(g.stats_layout.entries) == 22  # 11 BatchNorm layers x (mean, var)
+  dp = d.layout.entries
+  assert dp[("DiscOptimizedBlock_0", "SpectralConv_0", "kernel")][1] == (3, 3, 3, 96)
+  assert dp[("DiscBlock_3", "SpectralConv_2", "kernel")][1] == (1, 1, 768, 1536)
+  assert ("DiscBlock_4", "SpectralConv_2", "kernel") not in dp
+  assert dp[("SpectralDense_0", "kernel")][1] == (1536, 1)
+  assert dp[("SpectralDense_1", "kernel")][1] == (768, 1536)
+  assert dp[("SpectralConv_0", "kernel")][1] == (1, 1, 384, 768)
+  assert d.u_layout.entries[("SpectralConv_0", "u0")][1] == (1, 768)
+  assert d.n_sn == 20
+
+
+def test_layout_tree_roundtrip_and_alignment():
+  c = helpers.small_config()
+  g = engine.GeneratorEngine(c, 64)
+  buf = engine.init_flat(g.layout, 3, engine._kind)
+  tree = g.layout.tree(buf)
+  buf2 = torch.zeros_like(buf)
+  g.layout.load_tree(buf2, tree)
+  assert torch.equal(buf, buf2)
+  assert all(off % 4 == 0 for off, _ in g.layout.entries.values())
+  # concatenated-bias blocks are contiguous (one bias vector / one column sum per group)
+  assert g.layout.off(g.lcbn[0][0] + ("Conv_0", "bias")) == g.lcbn_bias_off
+  assert g.cbn_bias_off == g.lcbn_bias_off + g.NL
+
+
+def test_config_surface():
+  c = coco_xmc.get_config()
+  for k in ("dtype", "z_dim", "d_step_per_g_step", "polyak_decay", "pretrained_image_contrastive", "image_size",
+            "gf_dim", "df_dim", "g_spectral_norm", "d_spectral_norm", "batch_norm_group_size", "gamma_for_g",
+            "word_contrastive", "sentence_contrastive", "image_contrastive", "cond_size", "g_lr", "d_lr", "beta1",
+            "beta2", "architecture", "model_name"):
+    assert hasattr(c, k), k
+  assert (c.batch_size, c.image_size, c.gf_dim, c.df_dim, c.z_dim) == (56, 128, 96, 96, 128)
+  assert (c.g_lr, c.d_lr, c.beta1, c.beta2, c.polyak_decay) == (1e-4, 4e-4, 0.5, 0.999, 0.999)
+  t = coco_xmc.get_test_config()
+  assert (t.batch_size, t.gf_dim, t.df_dim, t.z_dim) == (2, 16, 16, 8)
+  c.batch_size = 8
+  assert c["batch_size"] == 8
+
+
+def test_split_input_dict_is_an_exact_index_op():
+  batch = {"a": torch.arange(24).reshape(6, 4), "b": torch.arange(6)}
+  parts = train_utils.split_input_dict(batch, 2)
+  assert torch.equal(parts[0]["a"], batch["a"][:3]) and torch.equal(parts[1]["a"], batch["a"][3:])
+  assert torch.equal(parts[1]["b"], torch.tensor([3, 4, 5]))
+  with pytest.raises(ValueError):
+    train_utils.split_input_dict({"a": torch.zeros(5, 2)}, 2)
+
+
+def test_error_conventions():
+  c = helpers.small_config(image_size=64)
+  with pytest.raises(ValueError):
+    engine.GeneratorEngine(c, 64)
+  with pytest.raises(ValueError):
+    engine.DiscriminatorEngine(c, 64)
+  c = helpers.small_config(architecture="resnet")
+  with pytest.raises(ValueError):
+    train_utils.create_train_state(c, 0, helpers.make_batch(2, c))
+  from xmcgan_image_generation_b200.libml import attention_lib
+  with pytest.raises(NotImplementedError):
+    attention_lib.contrastive_loss(torch.ones(2, 4), torch.ones(2, 4), sync_match=True)
+
+
+def test_device_groups():
+  assert parallel.get_device_groups(16, 8, device_count=8) == [[0, 1], [2, 3], [4, 5], [6, 7]]
+  assert parallel.get_device_groups(8, 8, device_count=2) == [[0], [1]]
+  with pytest.raises(AssertionError):
+    parallel.get_device_groups(12, 8, device_count=8)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_product_path_has_no_cpu_fallback():
+  """Without a CUDA device the product must fail loudly, never compute on the CPU."""
+  c = helpers.small_config()
+  with pytest.raises(Exception):
+    train_utils.create_train_state(c, 0, helpers.make_batch(2, c))

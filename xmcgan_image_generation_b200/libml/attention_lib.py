@@ -1,0 +1,61 @@
+"""Counterparts of xmcgan/libml/attention_lib.py with the same signatures, on CUDA tensors. Forward values only;
+train_step uses the same kernels plus their backward through engine.py. accuracy / entropy are dead on the train path
+(attention_lib.py:75-78,183-190, removed by XLA DCE) and are returned as None."""
+import torch
+
+from .. import engine as _engine
+from .. import ops
+
+LARGE_NUM = 1e9
+
+
+def _dev(x):
+  return torch.as_tensor(x).to("cuda", torch.float32).contiguous()
+
+
+def l2_normalize(x, axis=-1, epsilon=1e-12):
+  """attention_lib.l2_normalize (attention_lib.py:30-33); only the last axis is supported."""
+  x = _dev(x)
+  if axis not in (-1, x.dim() - 1):
+    raise NotImplementedError("l2_normalize is built for the last axis only (the only use on the hot path)")
+  y, _ = ops.l2norm_rows(x.reshape(-1, x.shape[-1]), eps=epsilon)
+  return y.view(x.shape)
+
+
+def contrastive_loss(image_feat, cond_feat, l2_norm=True, temperature=0.1, sync_match=False):
+  """attention_lib.contrastive_loss (attention_lib.py:46-79): InfoNCE over the LOCAL batch."""
+  if sync_match:
+    raise NotImplementedError  # same as the reference (attention_lib.py:58-59)
+  if not l2_norm:
+    raise NotImplementedError("l2_norm=False is not used on the hot path and is not built")
+  slot = ops.empty(1, ops.F32)
+  _engine.Contrastive(_dev(image_feat), _dev(cond_feat), slot, temperature)
+  return slot[0], None, None
+
+
+def word_loss(image_feat, word_feat, max_len, gamma1=5, gamma2=5, gamma3=50):
+  """attention_lib.word_loss (attention_lib.py:130-191)."""
+  if (gamma1, gamma2, gamma3) != (5, 5, 50):
+    raise NotImplementedError("only the reference defaults gamma1=gamma2=5, gamma3=50 are built")
+  img = _dev(image_feat).to(torch.bfloat16)  # plumbing cast of the caller's tensor; the kernels consume bf16 regions
+  ws = _engine.WordShared(_dev(word_feat), _dev(max_len))
+  slot = ops.empty(1, ops.F32)
+  _engine.WordLoss(img, ws, slot)
+  return slot[0], None, None
+
+
+def attention_for_g(region_feat, word_feat, gamma, mask=None):
+  """attention_lib.attention_for_g (attention_lib.py:194-219). `mask` must be the reference's word-padding mask
+  (1 for w >= max_len, constant over regions) or None."""
+  q = _dev(region_feat).to(torch.bfloat16)
+  w = _dev(word_feat)
+  B, R, D = q.shape
+  L = w.shape[1]
+  if mask is None:
+    max_len = torch.full((B,), float(L), device="cuda")
+  else:
+    max_len = (L - _dev(mask)[:, 0, :].sum(-1)).contiguous()  # index glue: the mask is [arange(L) >= max_len]
+  what, _ = ops.l2norm_rows(w.reshape(B * L, D))
+  ctx = ops.empty((B * R, D))
+  attn = ops.attention_g_fwd(q, what.view(B, L, D), max_len, gamma, ctx)
+  return ctx.view(B, R, D), attn.view(B, R, L)
