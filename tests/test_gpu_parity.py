@@ -1,0 +1,276 @@
+"""Parity of the B200 CUDA path (through the C ABI / the reference-shaped Python API) against the CPU oracle.
+Tolerances (stated per test): the kernels use bf16 operands / bf16 activation storage with fp32 accumulation, the
+oracle's bf16 policy rounds at the same storage points; index / mask / split semantics are exact."""
+import pytest
+import torch
+
+from oracle import xmc_oracle as orc
+from tests import helpers
+
+gpu = pytest.mark.gpu
+
+
+def _mods():
+  from xmcgan_image_generation_b200 import _lib, engine, ops, train_utils, xmc_gan
+  from xmcgan_image_generation_b200.nets import xmc_net
+  return _lib, engine, ops, train_utils, xmc_gan, xmc_net
+
+
+def _q(t):
+  return t.to(torch.bfloat16).float()
+
+
+@gpu
+def test_native_library_is_loaded():
+  _lib, *_ = _mods()
+  L = _lib.lib()
+  assert L.xmc_num_sms() > 0
+  assert _lib._LIB is not None
+
+
+@gpu
+@pytest.mark.parametrize("N,H,W,C,Cout,k", [(2, 16, 16, 64, 64, 3), (3, 32, 32, 96, 192, 3), (16, 4, 4, 192, 64, 3),
+                                             (1, 128, 128, 96, 96, 3), (5, 8, 8, 64, 32, 1), (2, 4, 4, 16, 16, 3)])
+def test_conv_forward_and_wgrad_match_oracle(N, H, W, C, Cout, k):
+  """tcgen05 implicit-GEMM conv vs the oracle's conv2d on bf16-rounded operands: fp32 results within 1e-4 rel."""
+  _, _, ops, *_ = _mods()
+  torch.manual_seed(N * 100 + C)
+  x = _q(torch.randn(N, H, W, C))
+  kern = _q(torch.randn(k, k, C, Cout) * 0.05)
+  bias = torch.randn(Cout)
+  want = orc.conv2d(x, kern, bias)
+  wk = kern.permute(3, 0, 1, 2).reshape(Cout, k * k * C).contiguous().cuda().to(torch.bfloat16)
+  got = ops.conv_fwd(x.cuda().to(torch.bfloat16), wk, k, Cout, bias=bias.cuda(), out_dtype=torch.float32)
+  assert helpers.rel(got, want) < 1e-4
+  # weight gradient for a given output cotangent
+  dy = _q(torch.randn(N, H, W, Cout) * 0.1)
+  kp = kern.clone().requires_grad_(True)
+  (orc.conv2d(x, kp, None) * dy).sum().backward()
+  out = torch.zeros(k * k * C * Cout, device="cuda")
+  ops.wgrad(x.cuda().to(torch.bfloat16), dy.cuda().to(torch.bfloat16), k, out, out_mode=0, ld_out=Cout,
+            tap_stride=C * Cout)
+  assert helpers.rel(out.view(k, k, C, Cout), kp.grad) < 1e-4
+
+
+@gpu
+def test_wgrad_is_the_adjoint_of_conv_at_full_size():
+  """Size-independent property at BASELINE's largest layer (56x128x128, 96->96): <conv(x,W), dy> == <W, wgrad(x,dy)>."""
+  _, _, ops, *_ = _mods()
+  torch.manual_seed(0)
+  N, S, C = 56, 128, 96
+  x = (torch.randn(N, S, S, C, device="cuda") * 0.5).to(torch.bfloat16)
+  dy = (torch.randn(N, S, S, C, device="cuda") * 0.1).to(torch.bfloat16)
+  w = (torch.randn(C, 9 * C, device="cuda") * 0.05).to(torch.bfloat16)
+  y = ops.conv_fwd(x, w, 3, C, out_dtype=torch.float32)
+  lhs = (y.double() * dy.double()).sum().item()
+  dw = torch.zeros(9 * C * C, device="cuda")
+  ops.wgrad(x, dy, 3, dw, out_mode=0, ld_out=C, tap_stride=C * C)
+  w_hwio = w.float().view(C, 9, C).permute(1, 2, 0).reshape(-1)  # [co][tap][ci] -> [tap][ci][co]
+  rhs = (dw.double() * w_hwio.double()).sum().item()
+  assert abs(lhs - rhs) < 2e-3 * abs(lhs)
+
+
+@gpu
+def test_attention_for_g_matches_oracle_and_single_word_kat():
+  from xmcgan_image_generation_b200.libml import attention_lib
+  torch.manual_seed(1)
+  B, R, L, D = 3, 256, 17, 64
+  q = _q(torch.randn(B, R, D))
+  w = torch.randn(B, L, D) * 0.5
+  max_len = torch.tensor([[3.0], [17.0], [9.0]])
+  mask = (torch.arange(L)[None, :] >= max_len).float()[:, None, :].repeat(1, R, 1)
+  want, want_attn = orc.attention_for_g(q, w, 15.0, mask)
+  got, attn = attention_lib.attention_for_g(q, w, 15.0, mask)
+  assert helpers.rel(got, want) < 5e-3  # bf16 output rounding
+  assert helpers.rel(attn, want_attn) < 1e-4
+  assert (attn.cpu()[0, :, 3:] == 0).all()  # padded words get exactly zero weight
+  one = torch.ones(B, R, L)
+  one[:, :, 0] = 0
+  got1, _ = attention_lib.attention_for_g(q, w, 15.0, one)
+  assert helpers.rel(got1, orc.l2_normalize(w)[:, :1].expand(B, R, D)) < 5e-3
+
+
+@gpu
+@pytest.mark.parametrize("B", [3, 8])
+def test_word_loss_and_contrastive_match_oracle(B):
+  """B=3 exercises the padded (B*L not a multiple of 8) layout. bf16 region/word operands: 3e-3 rel on the loss."""
+  from xmcgan_image_generation_b200.libml import attention_lib
+  torch.manual_seed(2)
+  R, L, D = 256, 17, 64
+  img = _q(torch.randn(B, R, D))
+  words = torch.randn(B, L, D) * 0.5
+  max_len = torch.randint(1, L + 1, (B, 1)).float()
+  want, _, _ = orc.word_loss(img, words, max_len)
+  got, _, _ = attention_lib.word_loss(img, words, max_len)
+  assert abs(got.item() - want.item()) < 3e-3 * abs(want.item())
+  a, b = torch.randn(B, 96), torch.randn(B, 96)
+  want, _, _ = orc.contrastive_loss(a, b)
+  got, _, _ = attention_lib.contrastive_loss(a, b)
+  assert abs(got.item() - want.item()) < 1e-4 * abs(want.item())
+  eye = torch.eye(B, 96)
+  got, _, _ = attention_lib.contrastive_loss(eye, eye)
+  import math
+  assert abs(got.item() - 2 * math.log(1 + (B - 1) * math.exp(-10.0))) < 1e-5
+
+
+@gpu
+def test_hinge_and_resampling_known_answers():
+  from xmcgan_image_generation_b200.libml import losses
+  from xmcgan_image_generation_b200.nets import common
+  d, g = losses.hinge_loss(torch.zeros(5, 1), torch.zeros(5, 1))
+  assert d.item() == 2.0 and g.item() == 0.0
+  r, f = torch.randn(7, 1), torch.randn(7, 1)
+  wd, wg = orc.hinge_loss(r, f)
+  d, g = losses.hinge_loss(r, f)
+  assert abs(d.item() - wd.item()) < 1e-6 and abs(g.item() - wg.item()) < 1e-6
+  x = _q(torch.randn(2, 8, 8, 16))
+  assert torch.equal(common.upsample(x).float().cpu(), orc.upsample(x))            # index op: exact
+  assert helpers.rel(common.dsample(x), orc.dsample(x)) < 4e-3
+  img = _q(torch.rand(2, 8, 8, 3))
+  assert helpers.rel(common.dsample(img), orc.dsample(img)) < 4e-3
+
+
+def _build(config, E=64, seed=1):
+  _, engine, ops, train_utils, xmc_gan, xmc_net = _mods()
+  g_eng, d_eng, g_vars, d_vars = helpers.cpu_variables(config, E, seed)
+  to_flat = lambda lay, tree: xmc_net.FlatTree(lay, xmc_net.as_flat(lay, tree))
+  g_params = to_flat(xmc_net.get_engine(config, "g", E).layout, g_vars["params"])
+  g_stats = to_flat(xmc_net.get_engine(config, "g", E).stats_layout, g_vars["batch_stats"])
+  d_params = to_flat(xmc_net.get_engine(config, "d", E).layout, d_vars["params"])
+  d_u = to_flat(xmc_net.get_engine(config, "d", E).u_layout, d_vars["spectral_norm_stats"])
+  return g_vars, d_vars, g_params, g_stats, d_params, d_u
+
+
+@gpu
+def test_generator_and_discriminator_apply_match_oracle():
+  """Through the Flax-shaped module API. Image: 2e-2 rel-L2 (bf16 activations through 11 BN layers); logits 3e-2;
+  contrastive losses 5e-3; new batch_stats / u0 1e-2 / 1e-4."""
+  *_, xmc_net = _mods()
+  import functools
+  cfg = helpers.small_config()
+  B = 4
+  g_vars, d_vars, g_params, g_stats, d_params, d_u = _build(cfg)
+  batch = helpers.make_batch(B, cfg)
+  gen = functools.partial(xmc_net.Generator, config=cfg)
+  img, new = gen(train=True).apply({"params": g_params, "batch_stats": g_stats}, (batch, batch["z"]),
+                                   mutable=["batch_stats"])
+  want, upd = orc.generator_apply(g_vars, (batch, batch["z"]), cfg, True, orc.Policy("bfloat16"))
+  assert img.shape == (B, 128, 128, 3) and img.min() >= 0 and img.max() <= 1
+  assert helpers.rel(img, want) < 2e-2
+  for (p, a), (_, b) in zip(orc.tree_leaves(new["batch_stats"].to_cpu_tree()), orc.tree_leaves(upd["batch_stats"])):
+    assert helpers.rel(a, b) < 1e-2, p
+  # eval mode uses the running statistics and leaves them untouched
+  img_eval = gen(train=False).apply({"params": g_params, "batch_stats": g_stats}, (batch, batch["z"]), mutable=False)
+  want_eval, _ = orc.generator_apply(g_vars, (batch, batch["z"]), cfg, False, orc.Policy("bfloat16"))
+  assert helpers.rel(img_eval, want_eval) < 2e-2
+
+  disc = functools.partial(xmc_net.Discriminator, config=cfg)
+  all_images = torch.cat([batch["image"], want.detach()])
+  (logit, stat), new_d = disc(train=True).apply({"params": d_params, "spectral_norm_stats": d_u},
+                                                (all_images, batch), mutable=["spectral_norm_stats"])
+  (wlogit, wstat), wupd = orc.discriminator_apply(d_vars, (all_images, batch), cfg, True, orc.Policy("bfloat16"))
+  assert logit.shape == (2 * B, 1)
+  assert helpers.rel(logit, wlogit) < 3e-2
+  for k in ("real_word_loss", "fake_word_loss", "real_sentence_loss", "fake_sentence_loss", "image_contrastive_loss"):
+    assert abs(stat[k].item() - wstat[k].item()) < 5e-3 * abs(wstat[k].item()), k
+  for (p, a), (_, b) in zip(orc.tree_leaves(new_d["spectral_norm_stats"].to_cpu_tree()),
+                            orc.tree_leaves(wupd["spectral_norm_stats"])):
+    assert helpers.rel(a, b) < 1e-4, p
+
+
+def _assert_grad_tree(got_tree, ref_tree, tol):
+  """Per-leaf rel-L2 for leaves that carry gradient; leaves whose true gradient is (numerically) zero — biases in
+  front of a BatchNorm — are compared in absolute terms against the largest leaf norm."""
+  ref = orc.tree_leaves(ref_tree)
+  scale = max(r.norm().item() for _, r in ref)
+  for (path, g), (_, r) in zip(orc.tree_leaves(got_tree), ref):
+    if r.norm().item() > 1e-4 * scale:
+      assert helpers.rel(g, r) < tol, (path, helpers.rel(g, r))
+    else:
+      assert (g.float().cpu() - r).norm().item() < 1e-3 * scale, path
+
+
+@gpu
+@pytest.mark.parametrize("variant", ["default", "no_sn", "no_word", "ragged"])
+def test_both_pullbacks_match_oracle(variant):
+  """d(d_loss)/d(params_d) and d(g_loss)/d(params_g) from ONE forward (xmc_gan.py:162-167) vs oracle autograd.
+  Tolerance 6e-2 rel-L2 per leaf vs the bf16-policy oracle (bf16 storage of activation gradients), losses 2e-3."""
+  _, engine, ops, _, _, xmc_net = _mods()
+  kw = {"no_sn": dict(d_spectral_norm=False), "no_word": dict(word_contrastive=False)}.get(variant, {})
+  cfg = helpers.small_config(**kw)
+  B = 3 if variant == "ragged" else 4
+  g_vars, d_vars, g_params, g_stats, d_params, d_u = _build(cfg, seed=4)
+  batch = helpers.make_batch(B, cfg, seed=2, min_len=1 if variant == "ragged" else 3)
+  dev = xmc_net.batch_to_device(batch)
+  g_eng, d_eng = xmc_net.get_engine(cfg, "g", 64), xmc_net.get_engine(cfg, "d", 64)
+  S = cfg.image_size
+  g_eng.prep_weights(g_params.buf)
+  u_new = torch.empty_like(d_u.buf)
+  d_eng.prep_weights(d_params.buf, d_u.buf if d_eng.sn else None, u_new if d_eng.sn else None)
+  all_images = ops.empty((2 * B, S, S, 3))
+  ops.cast_to_bf16(dev["image"].reshape(-1, 3), all_images[:B].view(-1, 3))
+  img, gctx = g_eng.forward(g_params.buf, g_stats.buf, dev, dev["z"], train=True, fake_bf16=all_images[B:])
+  losses = torch.zeros(16, device="cuda")
+  _, dctx = d_eng.forward(d_params.buf, all_images, dev, losses, need_g=True)
+  d_grads = torch.zeros_like(d_params.buf)
+  d_eng.backward_d(dctx, d_params.buf, d_grads)
+  d_eng.sn_backward(d_params.buf, d_grads, u_new)
+  d_fake = d_eng.backward_g(dctx, d_params.buf)
+  g_grads = torch.zeros_like(g_params.buf)
+  g_eng.backward(gctx, d_fake, g_params.buf, g_grads)
+  torch.cuda.synchronize()
+  state = orc.make_state(g_vars, d_vars if d_eng.sn else {"params": d_vars["params"]})
+  r = orc.d_losses_and_grads(state, batch, cfg, orc.Policy("bfloat16"), want_g=True)
+  l = losses.cpu()
+  assert abs((l[0] + l[2] + l[4]).item() - r["d_loss"].item()) < 2e-3 * abs(r["d_loss"].item())
+  assert abs((l[1] + l[3] + l[5] + l[6]).item() - r["g_loss"].item()) < 2e-3 * abs(r["g_loss"].item())
+  _assert_grad_tree(xmc_net.FlatTree(d_eng.layout, d_grads).to_cpu_tree(), r["d_grad"], 6e-2)
+  _assert_grad_tree(xmc_net.FlatTree(g_eng.layout, g_grads).to_cpu_tree(), r["g_grad"], 6e-2)
+
+
+@gpu
+def test_train_step_matches_oracle_for_two_steps():
+  """Public API: train_utils.train_step == oracle train_step (bf16 policy): metrics 5e-3 rel, parameters 5e-3,
+  EMA 1e-4, batch_stats 1e-2, u0 1e-2; step counters exact (D's Adam advances twice per step)."""
+  _, engine, ops, train_utils, xmc_gan, xmc_net = _mods()
+  cfg = helpers.small_config()
+  B = 4
+  g_vars, d_vars, g_params, g_stats, d_params, d_u = _build(cfg, seed=6)
+  batch = helpers.make_batch(2 * B, cfg, seed=7)
+  ostate = orc.make_state(g_vars, d_vars)
+  state = train_utils.TrainState(0, train_utils.Optimizer(g_params, cfg.g_lr, cfg.beta1, cfg.beta2),
+                                 train_utils.Optimizer(d_params, cfg.d_lr, cfg.beta1, cfg.beta2),
+                                 {"batch_stats": g_stats}, {"spectral_norm_stats": d_u}, g_params.clone())
+  for _ in range(2):
+    state, metrics = train_utils.train_step(None, state, batch, xmc_gan, None, None, cfg, {})
+    got = metrics.compute()
+    ostate, want = orc.train_step(ostate, batch, cfg, orc.Policy("bfloat16"))
+    for k in ("d_loss", "g_loss", "c_loss_d", "c_loss_g"):
+      assert abs(got[k] - want[k]) < 5e-3 * abs(want[k]), (k, got[k], want[k])
+    assert got["c_loss_g_pretrained"] == 0.0
+  assert (state.step, state.d_optimizer.step, state.g_optimizer.step) == (2, 4, 2)
+  pairs = [(state.g_optimizer.target, ostate["g_params"], 5e-3), (state.d_optimizer.target, ostate["d_params"], 5e-3),
+           (state.ema_params, ostate["ema_params"], 1e-4),
+           (state.generator_state["batch_stats"], ostate["generator_state"]["batch_stats"], 1e-2),
+           (state.discriminator_state["spectral_norm_stats"], ostate["discriminator_state"]["spectral_norm_stats"],
+            1e-2)]
+  for got_t, want_t, tol in pairs:
+    for (p, a), (_, b) in zip(orc.tree_leaves(got_t.to_cpu_tree()), orc.tree_leaves(want_t)):
+      assert helpers.rel(a, b) < tol, (p, helpers.rel(a, b))
+
+
+@gpu
+def test_train_step_runs_at_baseline_width_and_decreases_nothing_to_nan():
+  """Full-width networks (gf=df=96, E=768) at a small batch: losses finite, EMA moves, D sees 2B images."""
+  _, engine, ops, train_utils, xmc_gan, xmc_net = _mods()
+  from xmcgan_image_generation_b200.configs import coco_xmc
+  cfg = coco_xmc.get_config()
+  cfg.update(dict(batch_size=8, pretrained_image_contrastive=False))
+  batch = helpers.make_batch(16, cfg, E=768)
+  gen, disc, state = train_utils.create_train_state(cfg, 42, batch)
+  ema0 = state.ema_params.buf.clone()
+  state, metrics = train_utils.train_step(None, state, batch, xmc_gan, gen, disc, cfg, {})
+  m = metrics.compute()
+  assert all(torch.isfinite(torch.tensor(v)) for v in m.values())
+  assert not torch.equal(ema0, state.ema_params.buf)
+  assert torch.isfinite(state.g_optimizer.target.buf).all() and torch.isfinite(state.d_optimizer.target.buf).all()
