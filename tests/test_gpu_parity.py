@@ -178,16 +178,24 @@ def test_generator_and_discriminator_apply_match_oracle():
     assert helpers.rel(a, b) < 1e-4, p
 
 
-def _assert_grad_tree(got_tree, ref_tree, tol):
-  """Per-leaf rel-L2 for leaves that carry gradient; leaves whose true gradient is (numerically) zero — biases in
-  front of a BatchNorm — are compared in absolute terms against the largest leaf norm."""
+def _assert_grad_tree(got_tree, ref_tree, ref32_tree, tol):
+  """Per-leaf rel-L2 against the bf16-policy oracle. The oracle does not model the bf16 storage of activation
+  GRADIENTS, so the per-leaf tolerance is max(tol, 3 x the distance between the bf16-policy and the fp32 oracle
+  gradients of that leaf) — the oracle's own measure of how sensitive that leaf is to bf16 rounding. Leaves whose
+  true gradient is (numerically) zero — biases in front of a BatchNorm — are compared in absolute terms."""
   ref = orc.tree_leaves(ref_tree)
+  ref32 = orc.tree_leaves(ref32_tree)
   scale = max(r.norm().item() for _, r in ref)
-  for (path, g), (_, r) in zip(orc.tree_leaves(got_tree), ref):
+  bad = []
+  for (path, g), (_, r), (_, r32) in zip(orc.tree_leaves(got_tree), ref, ref32):
     if r.norm().item() > 1e-4 * scale:
-      assert helpers.rel(g, r) < tol, (path, helpers.rel(g, r))
-    else:
-      assert (g.float().cpu() - r).norm().item() < 1e-3 * scale, path
+      e, noise = helpers.rel(g, r), helpers.rel(r, r32)
+      cos = torch.nn.functional.cosine_similarity(g.float().cpu().reshape(-1), r.reshape(-1), dim=0).item()
+      if not (e < max(tol, 3 * noise) and cos > 0.99):
+        bad.append((path, round(e, 4), round(noise, 4), round(cos, 5)))
+    elif (g.float().cpu() - r).norm().item() > 1e-3 * scale:
+      bad.append((path, "abs", (g.float().cpu() - r).norm().item(), scale))
+  assert not bad, bad
 
 
 @gpu
@@ -221,11 +229,15 @@ def test_both_pullbacks_match_oracle(variant):
   torch.cuda.synchronize()
   state = orc.make_state(g_vars, d_vars if d_eng.sn else {"params": d_vars["params"]})
   r = orc.d_losses_and_grads(state, batch, cfg, orc.Policy("bfloat16"), want_g=True)
+  r32 = orc.d_losses_and_grads(state, batch, cfg, orc.FP32, want_g=True)
   l = losses.cpu()
-  assert abs((l[0] + l[2] + l[4]).item() - r["d_loss"].item()) < 2e-3 * abs(r["d_loss"].item())
-  assert abs((l[1] + l[3] + l[5] + l[6]).item() - r["g_loss"].item()) < 2e-3 * abs(r["g_loss"].item())
-  _assert_grad_tree(xmc_net.FlatTree(d_eng.layout, d_grads).to_cpu_tree(), r["d_grad"], 6e-2)
-  _assert_grad_tree(xmc_net.FlatTree(g_eng.layout, g_grads).to_cpu_tree(), r["g_grad"], 6e-2)
+  # the totals are sums of terms of mixed sign (hinge_g = -mean(fake logit)): tolerance relative to the term sizes
+  d_scale = (l[0].abs() + l[2].abs() + l[4].abs()).item()
+  g_scale = (l[1].abs() + l[3].abs() + l[5].abs() + l[6].abs()).item()
+  assert abs((l[0] + l[2] + l[4]).item() - r["d_loss"].item()) < 2e-3 * d_scale
+  assert abs((l[1] + l[3] + l[5] + l[6]).item() - r["g_loss"].item()) < 2e-3 * g_scale
+  _assert_grad_tree(xmc_net.FlatTree(d_eng.layout, d_grads).to_cpu_tree(), r["d_grad"], r32["d_grad"], 6e-2)
+  _assert_grad_tree(xmc_net.FlatTree(g_eng.layout, g_grads).to_cpu_tree(), r["g_grad"], r32["g_grad"], 6e-2)
 
 
 @gpu
@@ -245,8 +257,9 @@ def test_train_step_matches_oracle_for_two_steps():
     state, metrics = train_utils.train_step(None, state, batch, xmc_gan, None, None, cfg, {})
     got = metrics.compute()
     ostate, want = orc.train_step(ostate, batch, cfg, orc.Policy("bfloat16"))
+    scale = max(abs(v) for v in want.values())
     for k in ("d_loss", "g_loss", "c_loss_d", "c_loss_g"):
-      assert abs(got[k] - want[k]) < 5e-3 * abs(want[k]), (k, got[k], want[k])
+      assert abs(got[k] - want[k]) < 5e-3 * scale, (k, got[k], want[k])
     assert got["c_loss_g_pretrained"] == 0.0
   assert (state.step, state.d_optimizer.step, state.g_optimizer.step) == (2, 4, 2)
   pairs = [(state.g_optimizer.target, ostate["g_params"], 5e-3), (state.d_optimizer.target, ostate["d_params"], 5e-3),
