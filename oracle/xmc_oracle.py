@@ -31,15 +31,32 @@ LARGE_NUM = 1e9  # xmcgan/libml/attention_lib.py:20
 # ----------------------------------------------------------------------------------------------------------------------
 # precision policy
 # ----------------------------------------------------------------------------------------------------------------------
+class _RoundBoth(torch.autograd.Function):
+  """bf16 rounding of the value in forward AND of the cotangent in backward (models bf16 storage of activation
+  gradients, which both the reference's bf16 graph and the B200 pipeline do)."""
+
+  @staticmethod
+  def forward(ctx, x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+  @staticmethod
+  def backward(ctx, g):
+    return g.to(torch.bfloat16).to(torch.float32)
+
+
 class Policy:
-  def __init__(self, dtype="float32"):
+  def __init__(self, dtype="float32", round_grads=False):
     assert dtype in ("float32", "bfloat16")
     self.dtype = dtype
+    self.round_grads = round_grads
 
   def q(self, x):
-    """Storage rounding of an activation / cast of a weight to the compute dtype (straight-through gradient)."""
+    """Storage rounding of an activation / cast of a weight to the compute dtype (straight-through gradient).
+    With round_grads=True the cotangent is rounded to bf16 at the same points (noise model of bf16 gradient storage)."""
     if self.dtype == "float32":
       return x
+    if self.round_grads and x.requires_grad:
+      return _RoundBoth.apply(x)
     return x + (x.detach().to(torch.bfloat16).to(torch.float32) - x.detach())
 
 

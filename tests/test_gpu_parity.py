@@ -130,6 +130,83 @@ def test_hinge_and_resampling_known_answers():
   assert helpers.rel(common.dsample(img), orc.dsample(img)) < 4e-3
 
 
+@gpu
+@pytest.mark.parametrize("Hc,H,up", [(1, 4, True), (1, 8, False), (16, 16, True), (16, 64, False), (16, 32, True)])
+def test_conditional_batch_norm_forward_backward_single_op(Hc, H, up):
+  """(Local)ConditionalBatchNorm + relu (+ nearest upsample) and its full backward (dx, dgamma, dbeta) on identical
+  bf16 inputs vs oracle autograd: 1e-2 rel-L2 (outputs are bf16). No cross-layer error amplification here, so this is
+  the sharp check of the backward formulas."""
+  _, _, ops, *_ = _mods()
+  torch.manual_seed(H * 10 + Hc)
+  N, C = 3, 32
+  x = _q(torch.randn(N, H, H, C) * 2 + 0.5).requires_grad_(True)
+  rows = N * Hc * Hc
+  gb = _q(torch.randn(rows, 2 * C + 16) * 0.5).requires_grad_(True)   # gamma at col 8, beta at col 8+C
+  goff, boff = 8, 8 + C
+  s = H // Hc
+  idx = torch.arange(H) // s
+  g4 = gb[:, goff:goff + C].reshape(N, Hc, Hc, C)[:, idx][:, :, idx]
+  b4 = gb[:, boff:boff + C].reshape(N, Hc, Hc, C)[:, idx][:, :, idx]
+  xh, _ = orc.batch_norm(x, {"mean": torch.zeros(C), "var": torch.ones(C)}, True)
+  y = torch.relu(xh * (g4 + 1.0) + b4)
+  if up:
+    y = orc.upsample(y)
+  dy = _q(torch.randn_like(y) * 0.1)
+  (y * dy).sum().backward()
+  xd, gbd = x.detach().cuda().to(torch.bfloat16), gb.detach().cuda().to(torch.bfloat16)
+  sums, P = ops.bn_stats(xd)
+  mr = ops.bn_finalize(sums, P, C, torch.zeros(C, device="cuda"), torch.ones(C, device="cuda"), None, None)
+  got = ops.bn_apply(xd, mr, gbd, Hc, goff, boff, True, up)
+  assert helpers.rel(got, y) < 1e-2
+  dgb = torch.zeros(rows, 2 * C + 16, device="cuda")
+  dx = ops.bn_bwd(dy.cuda().to(torch.bfloat16), xd, mr, gbd, dgb, Hc, goff, boff, True, up)
+  assert helpers.rel(dx, x.grad) < 1e-2
+  assert helpers.rel(dgb[:, goff:goff + C], gb.grad[:, goff:goff + C]) < 1e-2
+  assert helpers.rel(dgb[:, boff:boff + C], gb.grad[:, boff:boff + C]) < 1e-2
+
+
+@gpu
+def test_attention_and_loss_heads_backward_single_op():
+  """Backward of attention_for_g, word_loss and contrastive_loss on identical inputs vs oracle autograd."""
+  _, engine, ops, *_ = _mods()
+  torch.manual_seed(5)
+  B, R, L, D = 4, 256, 17, 64
+  max_len = torch.tensor([[5.0], [17.0], [1.0], [9.0]])
+  words = torch.randn(B, L, D) * 0.5
+  # attention_for_g: d(ctx)/dq
+  q = _q(torch.randn(B, R, D)).requires_grad_(True)
+  mask = (torch.arange(L)[None, :] >= max_len).float()[:, None, :].repeat(1, R, 1)
+  ctx, _ = orc.attention_for_g(q, words, 15.0, mask)
+  dctx = _q(torch.randn(B, R, D) * 0.1)
+  (ctx * dctx).sum().backward()
+  what, _ = ops.l2norm_rows(words.cuda().reshape(B * L, D))
+  qd = q.detach().cuda().to(torch.bfloat16)
+  out = ops.empty((B * R, D))
+  attn = ops.attention_g_fwd(qd, what.view(B, L, D), max_len.cuda().reshape(B), 15.0, out)
+  dq = ops.attention_g_bwd(dctx.cuda().to(torch.bfloat16).view(B * R, D), qd, what.view(B, L, D), attn, 15.0)
+  assert helpers.rel(dq, q.grad) < 1e-2
+  # word_loss: d(loss)/d(image regions)
+  img = _q(torch.randn(B, R, D)).requires_grad_(True)
+  loss, _, _ = orc.word_loss(img, words, max_len)
+  loss.backward()
+  ws = engine.WordShared(words.cuda(), max_len.cuda())
+  slot = ops.empty(1, torch.float32)
+  wl = engine.WordLoss(img.detach().cuda().to(torch.bfloat16), ws, slot)
+  dR = wl.bwd()
+  assert abs(slot.item() - loss.item()) < 3e-3 * abs(loss.item())
+  assert helpers.rel(dR.view(B, R, D), img.grad) < 3e-2   # bf16 alpha / dS / dctx operands
+  # contrastive_loss: both cotangents
+  a = torch.randn(B, 96).requires_grad_(True)
+  b = torch.randn(B, 96).requires_grad_(True)
+  loss, _, _ = orc.contrastive_loss(a, b)
+  loss.backward()
+  c = engine.Contrastive(a.detach().cuda(), b.detach().cuda(), slot)
+  da, db = torch.zeros(B, 96, device="cuda"), torch.zeros(B, 96, device="cuda")
+  c.bwd_a(da)
+  c.bwd_b(db)
+  assert helpers.rel(da, a.grad) < 1e-4 and helpers.rel(db, b.grad) < 1e-4
+
+
 def _build(config, E=64, seed=1):
   _, engine, ops, train_utils, xmc_gan, xmc_net = _mods()
   g_eng, d_eng, g_vars, d_vars = helpers.cpu_variables(config, E, seed)
@@ -199,14 +276,16 @@ def _assert_grad_tree(got_tree, ref_tree, ref32_tree, tol):
 
 
 @gpu
-@pytest.mark.parametrize("variant", ["default", "no_sn", "no_word", "ragged"])
+@pytest.mark.parametrize("variant", ["default", "no_sn", "no_word", "ragged", "px256"])
 def test_both_pullbacks_match_oracle(variant):
   """d(d_loss)/d(params_d) and d(g_loss)/d(params_g) from ONE forward (xmc_gan.py:162-167) vs oracle autograd.
   Tolerance 6e-2 rel-L2 per leaf vs the bf16-policy oracle (bf16 storage of activation gradients), losses 2e-3."""
   _, engine, ops, _, _, xmc_net = _mods()
-  kw = {"no_sn": dict(d_spectral_norm=False), "no_word": dict(word_contrastive=False)}.get(variant, {})
+  kw = {"no_sn": dict(d_spectral_norm=False), "no_word": dict(word_contrastive=False),
+        "px256": dict(image_size=256, gf_dim=8, df_dim=8)}.get(variant, {})
   cfg = helpers.small_config(**kw)
-  B = 3 if variant == "ragged" else 4
+  B = {"ragged": 3, "px256": 2}.get(variant, 4)
+  tol = 1e-1 if variant == "px256" else 6e-2  # one more block, batch 2, width 8: the noisiest configuration
   g_vars, d_vars, g_params, g_stats, d_params, d_u = _build(cfg, seed=4)
   batch = helpers.make_batch(B, cfg, seed=2, min_len=1 if variant == "ragged" else 3)
   dev = xmc_net.batch_to_device(batch)
@@ -236,8 +315,8 @@ def test_both_pullbacks_match_oracle(variant):
   g_scale = (l[1].abs() + l[3].abs() + l[5].abs() + l[6].abs()).item()
   assert abs((l[0] + l[2] + l[4]).item() - r["d_loss"].item()) < 2e-3 * d_scale
   assert abs((l[1] + l[3] + l[5] + l[6]).item() - r["g_loss"].item()) < 2e-3 * g_scale
-  _assert_grad_tree(xmc_net.FlatTree(d_eng.layout, d_grads).to_cpu_tree(), r["d_grad"], r32["d_grad"], 6e-2)
-  _assert_grad_tree(xmc_net.FlatTree(g_eng.layout, g_grads).to_cpu_tree(), r["g_grad"], r32["g_grad"], 6e-2)
+  _assert_grad_tree(xmc_net.FlatTree(d_eng.layout, d_grads).to_cpu_tree(), r["d_grad"], r32["d_grad"], tol)
+  _assert_grad_tree(xmc_net.FlatTree(g_eng.layout, g_grads).to_cpu_tree(), r["g_grad"], r32["g_grad"], tol)
 
 
 @gpu

@@ -58,7 +58,7 @@ def cmp(name, got, ref, tol):
         f"ref_norm={ref.detach().float().norm().item():.3e}", flush=True)
 
 
-def tree_cmp(name, got_tree, ref_tree, tol, top=12):
+def tree_cmp(name, got_tree, ref_tree, tol, top=int(os.environ.get("TOP", "12"))):
   rows = []
   for (path, g), (_, r) in zip(orc.tree_leaves(got_tree), orc.tree_leaves(ref_tree)):
     rows.append((rel(g, r), path, r.float().norm().item(), g.detach().float().cpu().norm().item()))
@@ -194,8 +194,10 @@ STAGES = dict(g=stage_g, d=stage_d, grads=stage_grads, step=stage_step)
 
 if __name__ == "__main__":
   torch.manual_seed(0)
-  names = sys.argv[1:] or list(STAGES)
-  cfg = small_config()
+  names = [a for a in sys.argv[1:] if "=" not in a] or list(STAGES)
+  kw = {k: int(v) for k, v in (a.split("=") for a in sys.argv[1:] if "=" in a)}
+  B = kw.pop("B", 4)
+  cfg = small_config(**kw)
   for n in names:
-    print(f"== {n}", flush=True)
-    STAGES[n](cfg, 4)
+    print(f"== {n} {kw} B={B}", flush=True)
+    STAGES[n](cfg, B)
