@@ -106,7 +106,8 @@ class GemmTimer:
       s.record()
       out = timer._fwd(x, wk, kh, cout, **kw)
       e.record()
-      timer.records.append(("gemm_fwd_kernel", flops, s, e))
+      timer.records.append(("gemm_fwd_kernel", flops, s, e,
+                            (x.shape[0], x.shape[1], x.shape[2], c, kh, cout, int(kw.get("batched", False)))))
       return out
 
     def wgrad(xa, xb, kh, out, **kw):
@@ -117,7 +118,8 @@ class GemmTimer:
       s.record()
       r = timer._wgrad(xa, xb, kh, out, **kw)
       e.record()
-      timer.records.append(("gemm_wgrad_kernel", flops, s, e))
+      timer.records.append(("gemm_wgrad_kernel", flops, s, e,
+                            (xa.shape[0], xa.shape[1], xa.shape[2], ca, kh, cb, int(kw.get("batched", False)))))
       return r
 
     ops.conv_fwd, ops.wgrad = conv_fwd, wgrad
@@ -127,12 +129,24 @@ class GemmTimer:
 
   def summary(self):
     agg = {}
-    for k, fl, s, e in self.records:
+    for k, fl, s, e, _ in self.records:
       a = agg.setdefault(k, [0, 0.0, 0.0])
       a[0] += 1
       a[1] += fl
       a[2] += s.elapsed_time(e)
     return {k: {"launches": v[0], "tflop": v[1] / 1e12, "ms": v[2]} for k, v in agg.items()}
+
+  def per_shape(self):
+    agg = {}
+    for k, fl, s, e, shp in self.records:
+      a = agg.setdefault((k,) + shp, [0, 0.0, 0.0])
+      a[0] += 1
+      a[1] += fl
+      a[2] += s.elapsed_time(e)
+    rows = [{"kernel": k[0], "N": k[1], "H": k[2], "W": k[3], "C": k[4], "k": k[5], "Cout": k[6], "batched": k[7],
+             "launches": v[0], "ms": round(v[2], 3), "tflops": round(v[1] / 1e12 / (v[2] / 1e3), 1)}
+            for k, v in agg.items()]
+    return sorted(rows, key=lambda r: -r["ms"])
 
 
 def run_b200(args):
@@ -187,6 +201,9 @@ def run_b200(args):
   ms_dev = max_over_ranks(e0.elapsed_time(e1))
   launches = ops.LAUNCHES[0] - launches0
   gemm = timer.summary()
+  if args.dump_gemm and rank == 0:
+    with open(args.dump_gemm, "w") as f:
+      json.dump({"steps": args.steps, "rows": timer.per_shape()}, f, indent=0)
   timer.uninstall()
   clocks = sampler.stop() if rank == 0 else None
   last = metrics.compute()
@@ -309,6 +326,7 @@ def main():
   ap.add_argument("--batch", type=int, default=PER_GPU_B, help="per-GPU sub-batch B")
   ap.add_argument("--image-size", type=int, default=128)
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--dump-gemm", default=None, help="write per-shape GEMM timings (JSON) to this file")
   args = ap.parse_args()
   if args.warmup < 3 and args.impl == "b200":
     args.warmup = 3

@@ -4,7 +4,7 @@
 // Structure of both kernels: one CTA per SM, 6 warps:
 //   warp 0      : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
 //   warp 1      : MMA issuer    (one elected lane issues tcgen05.mma, tcgen05.commit releases smem / signals epilogue)
-//   warps 2..5  : epilogue      (tcgen05.ld TMEM -> registers -> fused bias/mask/residual/relu -> global)
+//   warps 2..   : epilogue      (tcgen05.ld TMEM -> registers -> fused bias/mask/residual/relu -> global)
 // SAME padding, image borders, ragged M/N/K edges and channel counts that are not a multiple of 64 are all handled
 // by TMA out-of-bounds zero fill; nothing is ever im2col'ed in memory.
 #include <cudaTypedefs.h>
@@ -20,7 +20,8 @@ constexpr int kBBytes = 32768;  // up to 256 rows x 64 bf16
 constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kBarBytes = 256;
 constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // + slack for 1024B alignment
-constexpr int kThreads = 192;
+constexpr int kThreads = 192;     // wgrad kernel: TMA, MMA, 4 epilogue warps
+constexpr int kThreadsFwd = 320;  // forward kernel: TMA, MMA, 8 epilogue warps
 constexpr int kTmemCols = 512;
 
 struct FwdParams {
@@ -65,22 +66,6 @@ __device__ __forceinline__ uint8_t* align_1024(uint8_t* p) {
 
 __device__ __forceinline__ float bf16_bits_to_float(uint32_t h) { return __uint_as_float(h << 16); }
 
-__device__ __forceinline__ void load16_bf16(const bf16* p, bool vec, int nvalid, float* f) {
-  if (vec) {
-    const uint4* q = reinterpret_cast<const uint4*>(p);
-    uint4 a = __ldg(q), b = __ldg(q + 1);
-    uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      f[2 * i] = bf16_bits_to_float(w[i] & 0xFFFFu);
-      f[2 * i + 1] = bf16_bits_to_float(w[i] >> 16);
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) f[i] = (i < nvalid) ? __bfloat162float(p[i]) : 0.f;
-  }
-}
-
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -89,7 +74,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 // =====================================================================================================================
 // Forward / dgrad / dense / batched GEMM:  D[pixels, Cout] = sum_taps A_tap[pixels, C] * B[Cout, tap*C + c]
 // =====================================================================================================================
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreadsFwd, 1)
 gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_1024(smem_raw);
@@ -112,7 +97,7 @@ gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
+      mbar_init(tempty_bar(a), 8);
     }
     fence_barrier_init();
   }
@@ -186,7 +171,10 @@ gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (acc == 0) acc_phase ^= 1;
     }
   } else {
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // 8 epilogue warps: warp w may only touch TMEM lanes 32*(w%4)..+31; the two warps that share a lane quarter
+    // split the 16-column chunks of the tile between them (even / odd chunks).
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -207,33 +195,62 @@ gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
-      for (int c0 = 0; c0 < p.BN; c0 += 16) {
+      for (int c0 = half * 16; c0 < p.BN; c0 += 32) {
         uint32_t v[16];
-        tmem_ld16(t_addr + c0, v);
-        tmem_ld_wait();
+        tmem_ld16(t_addr + c0, v);  // asynchronous until tmem_ld_wait
         const int col = nt * p.BN + c0;
-        if (row_ok && col < p.Cout) {
-          const int nvalid = min(16, p.Cout - col);
-          const bool vec = p.vec_ok && nvalid == 16;
+        const bool active = row_ok && col < p.Cout;
+        const int nvalid = min(16, p.Cout - col);
+        const bool vec = p.vec_ok && nvalid == 16;
+        const bool fast = active && vec;
+        float4 bz[4];
+        uint4 mk[2], rs[2];
+        if (fast) {
+          // fast path: all operand loads are 16-byte vectors issued while the TMEM load is in flight
+          if (p.bias) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) bz[i] = __ldg(b4 + i);
+          }
+          if (p.mask) {
+            const uint4* m4 = reinterpret_cast<const uint4*>(p.mask + pix * p.ldMask + col);
+            mk[0] = __ldg(m4);
+            mk[1] = __ldg(m4 + 1);
+          }
+          if (p.residual) {
+            const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + rpix * p.ldRes + col);
+            rs[0] = __ldg(r4);
+            rs[1] = __ldg(r4 + 1);
+          }
+        }
+        tmem_ld_wait();  // .sync.aligned: executed by the whole warp at a convergent point
+        if (fast) {
           float f[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
           if (p.bias) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (i < nvalid) f[i] += __ldg(p.bias + col + i);
+            for (int i = 0; i < 4; ++i) {
+              f[4 * i] += bz[i].x; f[4 * i + 1] += bz[i].y; f[4 * i + 2] += bz[i].z; f[4 * i + 3] += bz[i].w;
+            }
           }
           if (p.mask) {
-            float m[16];
-            load16_bf16(p.mask + pix * p.ldMask + col, vec, nvalid, m);
+            const uint32_t mw[8] = {mk[0].x, mk[0].y, mk[0].z, mk[0].w, mk[1].x, mk[1].y, mk[1].z, mk[1].w};
 #pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = (m[i] > 0.f) ? f[i] : 0.f;
+            for (int i = 0; i < 8; ++i) {
+              // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+              const uint32_t lo = mw[i] & 0xFFFFu, hi = mw[i] >> 16;
+              if (!(lo != 0 && lo < 0x8000u)) f[2 * i] = 0.f;
+              if (!(hi != 0 && hi < 0x8000u)) f[2 * i + 1] = 0.f;
+            }
           }
           if (p.residual) {
-            float m[16];
-            load16_bf16(p.residual + rpix * p.ldRes + col, vec, nvalid, m);
+            const uint32_t rw_[8] = {rs[0].x, rs[0].y, rs[0].z, rs[0].w, rs[1].x, rs[1].y, rs[1].z, rs[1].w};
 #pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] += m[i];
+            for (int i = 0; i < 8; ++i) {
+              f[2 * i] += bf16_bits_to_float(rw_[i] & 0xFFFFu);
+              f[2 * i + 1] += bf16_bits_to_float(rw_[i] >> 16);
+            }
           }
           if (p.relu) {
 #pragma unroll
@@ -241,29 +258,35 @@ gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
           if (p.out_dtype == 0) {
             bf16* o = reinterpret_cast<bf16*>(p.out) + pix * p.ldOut + col;
-            if (vec) {
-              uint4 a, b;
-              a.x = pack_bf16x2(f[0], f[1]);   a.y = pack_bf16x2(f[2], f[3]);
-              a.z = pack_bf16x2(f[4], f[5]);   a.w = pack_bf16x2(f[6], f[7]);
-              b.x = pack_bf16x2(f[8], f[9]);   b.y = pack_bf16x2(f[10], f[11]);
-              b.z = pack_bf16x2(f[12], f[13]); b.w = pack_bf16x2(f[14], f[15]);
-              reinterpret_cast<uint4*>(o)[0] = a;
-              reinterpret_cast<uint4*>(o)[1] = b;
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (i < nvalid) o[i] = __float2bfloat16(f[i]);
-            }
+            uint4 a, b;
+            a.x = pack_bf16x2(f[0], f[1]);   a.y = pack_bf16x2(f[2], f[3]);
+            a.z = pack_bf16x2(f[4], f[5]);   a.w = pack_bf16x2(f[6], f[7]);
+            b.x = pack_bf16x2(f[8], f[9]);   b.y = pack_bf16x2(f[10], f[11]);
+            b.z = pack_bf16x2(f[12], f[13]); b.w = pack_bf16x2(f[14], f[15]);
+            reinterpret_cast<uint4*>(o)[0] = a;
+            reinterpret_cast<uint4*>(o)[1] = b;
           } else {
             float* o = reinterpret_cast<float*>(p.out) + pix * p.ldOut + col;
-            if (vec) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
-                reinterpret_cast<float4*>(o)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-            } else {
+            for (int i = 0; i < 4; ++i)
+              reinterpret_cast<float4*>(o)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+          }
+        } else {
+          if (active) {
+            // generic path (ragged N edge or unaligned pitches): scalar accesses
+            float f[16];
 #pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (i < nvalid) o[i] = f[i];
+            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              if (i < nvalid) {
+                if (p.bias) f[i] += p.bias[col + i];
+                if (p.mask && !(__bfloat162float(p.mask[pix * p.ldMask + col + i]) > 0.f)) f[i] = 0.f;
+                if (p.residual) f[i] += __bfloat162float(p.residual[rpix * p.ldRes + col + i]);
+                if (p.relu) f[i] = fmaxf(f[i], 0.f);
+                if (p.out_dtype == 0) reinterpret_cast<bf16*>(p.out)[pix * p.ldOut + col + i] = __float2bfloat16(f[i]);
+                else reinterpret_cast<float*>(p.out)[pix * p.ldOut + col + i] = f[i];
+              }
             }
           }
         }
@@ -562,7 +585,7 @@ extern "C" int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* w
   }
   const int total = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
-  gemm_fwd_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(tmA, tmB, p);
+  gemm_fwd_kernel<<<grid, kThreadsFwd, kSmemBytes, (cudaStream_t)stream>>>(tmA, tmB, p);
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }
@@ -592,11 +615,21 @@ extern "C" int xmc_conv2d_wgrad(const XmcWgradDesc* d, const void* xa, const voi
   const int base_ctas = m_tiles * p.n_tiles * taps * nbatch;
   int ksplit = 1;
   if (d->out_mode == 0) {
-    // enough CTAs for ~2 waves, but keep at least 8 chunks (512 pixels) per CTA
-    ksplit = ceil_div(2 * num_sms(), base_ctas);
+    // Split K (pixels) across CTAs so that the grid fills whole waves of SMs: pick the split with the best
+    // last-wave utilisation (ties -> fewer splits = fewer atomics), keeping >= 8 chunks (512 pixels) per CTA.
+    const int sms = num_sms();
     const int max_split = p.total_chunks / 8 > 0 ? p.total_chunks / 8 : 1;
-    if (ksplit > max_split) ksplit = max_split;
-    if (ksplit < 1) ksplit = 1;
+    double best_score = -1.0;
+    for (int ks = 1; ks <= max_split && ks <= 1024; ++ks) {
+      const int cps = ceil_div(p.total_chunks, ks);
+      const int ks_eff = ceil_div(p.total_chunks, cps);
+      const long long ctas = (long long)base_ctas * ks_eff;
+      const long long waves = (ctas + sms - 1) / sms;
+      const double eff = (double)ctas / (double)(waves * sms);
+      const double score = eff - 1e-4 * ks_eff;
+      if (score > best_score) { best_score = score; ksplit = ks_eff; }
+      if (ctas > 16LL * sms) break;
+    }
   }
   p.chunks_per_split = ceil_div(p.total_chunks, ksplit);
   p.ksplit = ceil_div(p.total_chunks, p.chunks_per_split);

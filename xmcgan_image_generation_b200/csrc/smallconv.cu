@@ -9,104 +9,175 @@ namespace xmc {
 constexpr int kImgC = 3;
 
 // y[p][co] = relu?( sum_{tap,c3} x[p+d(tap)][c3] * w[co][tap*3+c3] + bias[co] ),  x: bf16 [N,H,W,3], y: bf16 [.,Cout]
-__global__ void conv_c3_in_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, int ldw,
-                                  const float* __restrict__ bias, int N, int H, int W, int Cout, int KH, int KW,
-                                  int relu, bf16* __restrict__ y) {
-  extern __shared__ float ws[];  // [Cout][K] + bias[Cout]
-  const int K = KH * KW * kImgC;
-  for (int t = threadIdx.x; t < Cout * K; t += blockDim.x) ws[t] = __bfloat162float(w[(t / K) * ldw + (t % K)]);
+// Each thread computes 4 horizontally adjacent pixels x 8 channels at a time: the 3x6x3 input window lives in
+// registers, every weight read from shared memory (one LDS.128 broadcast per 4 weights) feeds 4 FMAs.
+constexpr int kPx = 4;
+template <int KS>
+__global__ void __launch_bounds__(128)
+conv_c3_in_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, int ldw, const float* __restrict__ bias,
+                  int N, int H, int W, int Cout, int relu, bf16* __restrict__ y) {
+  extern __shared__ float ws[];  // [K][Cout] (transposed for vector reads) + bias[Cout]
+  constexpr int KH = KS, KW = KS;
+  constexpr int K = KH * KW * kImgC;
+  for (int t = threadIdx.x; t < Cout * K; t += blockDim.x) {
+    const int co = t / K, k = t - co * K;
+    ws[k * Cout + co] = __bfloat162float(w[co * ldw + k]);
+  }
   float* bs = ws + Cout * K;
   for (int t = threadIdx.x; t < Cout; t += blockDim.x) bs[t] = bias ? bias[t] : 0.f;
   __syncthreads();
-  const long long P = (long long)N * H * W;
-  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P) return;
-  const int wq = p % W, hq = (p / W) % H;
-  const long long nbase = p - (long long)hq * W - wq;
-  float in[27];
-  const int ph = KH / 2, pw = KW / 2;
-  for (int kh = 0; kh < KH; ++kh)
-    for (int kw = 0; kw < KW; ++kw) {
-      const int hh = hq + kh - ph, ww = wq + kw - pw;
+  const int wq4 = (W + kPx - 1) / kPx;
+  const long long groups = (long long)N * H * wq4;
+  const long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gidx >= groups) return;
+  const int wg = gidx % wq4;
+  const int hq = (gidx / wq4) % H;
+  const long long n = gidx / ((long long)wq4 * H);
+  const int w0 = wg * kPx;
+  constexpr int ph = KH / 2, pw = KW / 2;
+  constexpr int cols = kPx + KW - 1;
+  float win[KH * cols * kImgC];  // [kh][col][c]
+#pragma unroll
+  for (int kh = 0; kh < KH; ++kh) {
+    const int hh = hq + kh - ph;
+#pragma unroll
+    for (int cc = 0; cc < cols; ++cc) {
+      const int ww = w0 + cc - pw;
       const bool ok = hh >= 0 && hh < H && ww >= 0 && ww < W;
-      const bf16* src = x + (nbase + (long long)hh * W + ww) * kImgC;
+      const bf16* src = x + ((n * H + hh) * W + ww) * kImgC;
 #pragma unroll
-      for (int c = 0; c < kImgC; ++c) in[(kh * KW + kw) * kImgC + c] = ok ? __bfloat162float(src[c]) : 0.f;
+      for (int c = 0; c < kImgC; ++c) win[(kh * cols + cc) * kImgC + c] = ok ? __bfloat162float(src[c]) : 0.f;
     }
-  bf16* yo = y + p * Cout;
+  }
+  const long long pbase = (n * H + hq) * W + w0;
   for (int c0 = 0; c0 < Cout; c0 += 8) {
-    float acc[8];
+    float acc[kPx][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = bs[c0 + i];
-    for (int k = 0; k < K; ++k) {
-      const float v = in[k];
+    for (int px = 0; px < kPx; ++px)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += v * ws[(c0 + i) * K + k];
+      for (int i = 0; i < 8; ++i) acc[px][i] = bs[c0 + i];
+#pragma unroll
+    for (int kh = 0; kh < KH; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < KW; ++kw)
+#pragma unroll
+        for (int c = 0; c < kImgC; ++c) {
+          const float* wp = ws + ((kh * KW + kw) * kImgC + c) * Cout + c0;
+          const float4 wa = *reinterpret_cast<const float4*>(wp);
+          const float4 wb = *reinterpret_cast<const float4*>(wp + 4);
+#pragma unroll
+          for (int px = 0; px < kPx; ++px) {
+            const float v = win[(kh * cols + px + kw) * kImgC + c];
+            acc[px][0] += v * wa.x; acc[px][1] += v * wa.y; acc[px][2] += v * wa.z; acc[px][3] += v * wa.w;
+            acc[px][4] += v * wb.x; acc[px][5] += v * wb.y; acc[px][6] += v * wb.z; acc[px][7] += v * wb.w;
+          }
+        }
+#pragma unroll
+    for (int px = 0; px < kPx; ++px) {
+      if (w0 + px < W) {
+        if (relu) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[px][i] = fmaxf(acc[px][i], 0.f);
+        }
+        store8(y + (pbase + px) * Cout + c0, acc[px]);
+      }
     }
-    if (relu) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = fmaxf(acc[i], 0.f);
-    }
-    store8(yo + c0, acc);
   }
 }
 
 // y[p][c3] = sum_{tap,ci} x[p+d(tap)][ci] * w[c3][tap*Cin+ci] + bias[c3];  x: bf16 [N,H,W,Cin] (Cin % 8 == 0)
 // mode 0: fp32 out (accumulate optional); mode 1: img = (tanh(v)+1)/2 -> fp32 out + bf16 copy (xmc_net.py:245-247)
-__global__ void conv_c3_out_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, int ldw,
-                                   const float* __restrict__ bias, int N, int H, int W, int Cin, int KH, int KW,
-                                   int mode, int accumulate, float* __restrict__ y, bf16* __restrict__ y_bf16) {
+// Each thread computes 4 horizontally adjacent pixels: per (kh, 8-channel vector) it loads the 6 input vectors once
+// and reads each weight vector from shared memory once for all 4 pixels.
+template <int KS>
+__global__ void __launch_bounds__(128)
+conv_c3_out_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, int ldw, const float* __restrict__ bias,
+                   int N, int H, int W, int Cin, int mode, int accumulate, float* __restrict__ y,
+                   bf16* __restrict__ y_bf16) {
   extern __shared__ float ws[];  // [3][K]
+  constexpr int KH = KS, KW = KS;
   const int K = KH * KW * Cin;
   for (int t = threadIdx.x; t < kImgC * K; t += blockDim.x) ws[t] = __bfloat162float(w[(t / K) * ldw + (t % K)]);
   __syncthreads();
-  const long long P = (long long)N * H * W;
-  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P) return;
-  const int wq = p % W, hq = (p / W) % H;
-  const long long nbase = p - (long long)hq * W - wq;
-  const int ph = KH / 2, pw = KW / 2;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-  for (int kh = 0; kh < KH; ++kh)
-    for (int kw = 0; kw < KW; ++kw) {
-      const int hh = hq + kh - ph, ww = wq + kw - pw;
-      if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
-      const bf16* src = x + (nbase + (long long)hh * W + ww) * Cin;
-      const float* wk = ws + (kh * KW + kw) * Cin;
-      for (int c = 0; c < Cin; c += 8) {
-        float f[8];
-        load8(src + c, f);
+  const int wq4 = (W + kPx - 1) / kPx;
+  const long long groups = (long long)N * H * wq4;
+  const long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gidx >= groups) return;
+  const int wg = gidx % wq4;
+  const int hq = (gidx / wq4) % H;
+  const long long n = gidx / ((long long)wq4 * H);
+  const int w0 = wg * kPx;
+  constexpr int ph = KH / 2, pw = KW / 2;
+  float acc[kPx][kImgC];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          a0 += f[i] * wk[c + i];
-          a1 += f[i] * wk[K + c + i];
-          a2 += f[i] * wk[2 * K + c + i];
+  for (int px = 0; px < kPx; ++px)
+#pragma unroll
+    for (int c = 0; c < kImgC; ++c) acc[px][c] = 0.f;
+  for (int kh = 0; kh < KH; ++kh) {
+    const int hh = hq + kh - ph;
+    if (hh < 0 || hh >= H) continue;
+    const bf16* row = x + (n * H + hh) * (long long)W * Cin;
+    for (int c = 0; c < Cin; c += 8) {
+      float in[kPx + KW - 1][8];
+#pragma unroll
+      for (int cc = 0; cc < kPx + KW - 1; ++cc) {
+        const int ww = w0 + cc - pw;
+        if (ww >= 0 && ww < W) {
+          load8(row + (long long)ww * Cin + c, in[cc]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) in[cc][i] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int kw = 0; kw < KW; ++kw) {
+#pragma unroll
+        for (int c3 = 0; c3 < kImgC; ++c3) {
+          const float* wp = ws + c3 * K + (kh * KW + kw) * Cin + c;
+          const float4 wa = *reinterpret_cast<const float4*>(wp);
+          const float4 wb = *reinterpret_cast<const float4*>(wp + 4);
+#pragma unroll
+          for (int px = 0; px < kPx; ++px) {
+            const float* v = in[px + kw];
+            acc[px][c3] += v[0] * wa.x + v[1] * wa.y + v[2] * wa.z + v[3] * wa.w + v[4] * wb.x + v[5] * wb.y +
+                           v[6] * wb.z + v[7] * wb.w;
+          }
         }
       }
     }
-  if (bias) { a0 += bias[0]; a1 += bias[1]; a2 += bias[2]; }
-  float* yo = y + p * kImgC;
-  if (mode == 1) {
-    a0 = (tanhf(a0) + 1.f) * 0.5f; a1 = (tanhf(a1) + 1.f) * 0.5f; a2 = (tanhf(a2) + 1.f) * 0.5f;
-    yo[0] = a0; yo[1] = a1; yo[2] = a2;
-    if (y_bf16) {
-      bf16* yb = y_bf16 + p * kImgC;
-      yb[0] = __float2bfloat16(a0); yb[1] = __float2bfloat16(a1); yb[2] = __float2bfloat16(a2);
+  }
+  const long long pbase = (n * H + hq) * W + w0;
+#pragma unroll
+  for (int px = 0; px < kPx; ++px) {
+    if (w0 + px >= W) continue;
+    float a0 = acc[px][0], a1 = acc[px][1], a2 = acc[px][2];
+    if (bias) { a0 += bias[0]; a1 += bias[1]; a2 += bias[2]; }
+    float* yo = y + (pbase + px) * kImgC;
+    if (mode == 1) {
+      a0 = (tanhf(a0) + 1.f) * 0.5f; a1 = (tanhf(a1) + 1.f) * 0.5f; a2 = (tanhf(a2) + 1.f) * 0.5f;
+      yo[0] = a0; yo[1] = a1; yo[2] = a2;
+      if (y_bf16) {
+        bf16* yb = y_bf16 + (pbase + px) * kImgC;
+        yb[0] = __float2bfloat16(a0); yb[1] = __float2bfloat16(a1); yb[2] = __float2bfloat16(a2);
+      }
+    } else if (accumulate) {
+      yo[0] += a0; yo[1] += a1; yo[2] += a2;
+    } else {
+      yo[0] = a0; yo[1] = a1; yo[2] = a2;
     }
-  } else if (accumulate) {
-    yo[0] += a0; yo[1] += a1; yo[2] += a2;
-  } else {
-    yo[0] = a0; yo[1] = a1; yo[2] = a2;
   }
 }
 
 // out[tap_o][..] += sum_p x3[p + d(tap)][c3] * y[p][c];  x3: bf16 [N,H,W,3], y: bf16 [N,H,W,C]
-// out index = tap_o*s_tap + c3*s_c3 + c*s_c with tap_o = flip ? taps-1-tap : tap. One block = 8 image rows x 64 px.
+// out index = tap_o*s_tap + c3*s_c3 + c*s_c with tap_o = flip ? taps-1-tap : tap. One block = 8 image rows x 64 px;
+// one thread = 2 adjacent channels; the 3x3x3 input window slides along the row in registers (9 shared-memory reads
+// per pixel feed 54 FMAs).
+template <int KS>
 __global__ void wgrad_c3_kernel(const bf16* __restrict__ x3, const bf16* __restrict__ y, int N, int H, int W, int C,
-                                int KH, int KW, int flip, long long s_tap, int s_c3, int s_c,
-                                float* __restrict__ out) {
+                                int flip, long long s_tap, int s_c3, int s_c, float* __restrict__ out) {
   extern __shared__ float xs[];  // [(rows+2ph)][64+2pw][3]
-  const int ph = KH / 2, pw = KW / 2;
+  constexpr int KH = KS, KW = KS;
+  constexpr int ph = KH / 2, pw = KW / 2;
   const int rows = 8, seg = 64;
   const int wsegs = (W + seg - 1) / seg;
   const int hblocks = (H + rows - 1) / rows;
@@ -124,39 +195,72 @@ __global__ void wgrad_c3_kernel(const bf16* __restrict__ x3, const bf16* __restr
     xs[t] = v;
   }
   __syncthreads();
-  const int c = threadIdx.x;
+  const int c = threadIdx.x * 2;
   if (c >= C) return;
-  float acc[27];
+  constexpr int taps = KH * KW;
+  float acc[2][taps * 3];
 #pragma unroll
-  for (int i = 0; i < 27; ++i) acc[i] = 0.f;
-  const int taps = KH * KW;
+  for (int i = 0; i < taps * 3; ++i) acc[0][i] = acc[1][i] = 0.f;
   for (int r = 0; r < rows; ++r) {
     const int gh = h0 + r;
     if (gh >= H) break;
-    for (int q = 0; q < seg; ++q) {
-      const int gw = w0 + q;
-      if (gw >= W) break;
-      const float yv = __bfloat162float(y[(((long long)n * H + gh) * W + gw) * C + c]);
-      if (taps == 9) {
+    const bf16* yrow = y + (((long long)n * H + gh) * W + w0) * C + c;
+    const int qn = min(seg, W - w0);
+    if constexpr (taps == 9) {
+      // win[slot][kh][c3]: slot (col % 3) holds input column `col` of the halo tile
+      float win[3][3][3];
+#pragma unroll
+      for (int col = 0; col < 2; ++col)
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-          for (int kw = 0; kw < 3; ++kw) {
-            const float* xp = xs + ((r + kh) * xw + (q + kw)) * kImgC;
+          for (int c3 = 0; c3 < 3; ++c3) win[col][kh][c3] = xs[((r + kh) * xw + col) * kImgC + c3];
+      for (int q0 = 0; q0 < qn; q0 += 3) {
 #pragma unroll
-            for (int c3 = 0; c3 < 3; ++c3) acc[(kh * 3 + kw) * 3 + c3] += xp[c3] * yv;
+        for (int j = 0; j < 3; ++j) {
+          const int q = q0 + j;
+          if (q < qn) {
+            // bring in column q+2 into slot (j+2)%3
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+              for (int c3 = 0; c3 < 3; ++c3) win[(j + 2) % 3][kh][c3] = xs[((r + kh) * xw + q + 2) * kImgC + c3];
+            const __nv_bfloat162 yv2 = *reinterpret_cast<const __nv_bfloat162*>(yrow + (long long)q * C);
+            const float y0 = __low2float(yv2), y1 = __high2float(yv2);
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+              for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+                for (int c3 = 0; c3 < 3; ++c3) {
+                  const float xv = win[(j + kw) % 3][kh][c3];
+                  acc[0][(kh * 3 + kw) * 3 + c3] += xv * y0;
+                  acc[1][(kh * 3 + kw) * 3 + c3] += xv * y1;
+                }
           }
-      } else {
+        }
+      }
+    } else {
+      for (int q = 0; q < qn; ++q) {
+        const __nv_bfloat162 yv2 = *reinterpret_cast<const __nv_bfloat162*>(yrow + (long long)q * C);
+        const float y0 = __low2float(yv2), y1 = __high2float(yv2);
         const float* xp = xs + (r * xw + q) * kImgC;
 #pragma unroll
-        for (int c3 = 0; c3 < 3; ++c3) acc[c3] += xp[c3] * yv;
+        for (int c3 = 0; c3 < 3; ++c3) {
+          acc[0][c3] += xp[c3] * y0;
+          acc[1][c3] += xp[c3] * y1;
+        }
       }
     }
   }
+#pragma unroll
   for (int tap = 0; tap < taps; ++tap) {
     const int tap_o = flip ? taps - 1 - tap : tap;
 #pragma unroll
-    for (int c3 = 0; c3 < 3; ++c3) atomicAdd(out + tap_o * s_tap + c3 * s_c3 + (long long)c * s_c, acc[tap * 3 + c3]);
+    for (int c3 = 0; c3 < 3; ++c3) {
+      atomicAdd(out + tap_o * s_tap + c3 * s_c3 + (long long)c * s_c, acc[0][tap * 3 + c3]);
+      if (c + 1 < C) atomicAdd(out + tap_o * s_tap + c3 * s_c3 + (long long)(c + 1) * s_c, acc[1][tap * 3 + c3]);
+    }
   }
 }
 
@@ -218,9 +322,14 @@ extern "C" int xmc_conv_c3_in(const void* x, const void* w, int ldw, const float
   const int K = KH * KW * kImgC;
   const size_t smem = (size_t)(Cout * K + Cout) * sizeof(float);
   if (smem > 48 * 1024) return XMC_EINVAL;
-  const long long P = (long long)N * H * W;
-  conv_c3_in_kernel<<<(unsigned)ceil_div_ll(P, 128), 128, smem, (cudaStream_t)stream>>>(
-      (const bf16*)x, (const bf16*)w, ldw, bias, N, H, W, Cout, KH, KW, relu, (bf16*)y);
+  const long long P = (long long)N * H * ceil_div(W, kPx);
+  if (KH != KW || (KH != 1 && KH != 3)) return XMC_EINVAL;
+  if (KH == 3)
+    conv_c3_in_kernel<3><<<(unsigned)ceil_div_ll(P, 128), 128, smem, (cudaStream_t)stream>>>(
+        (const bf16*)x, (const bf16*)w, ldw, bias, N, H, W, Cout, relu, (bf16*)y);
+  else
+    conv_c3_in_kernel<1><<<(unsigned)ceil_div_ll(P, 128), 128, smem, (cudaStream_t)stream>>>(
+        (const bf16*)x, (const bf16*)w, ldw, bias, N, H, W, Cout, relu, (bf16*)y);
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }
@@ -230,22 +339,32 @@ extern "C" int xmc_conv_c3_out(const void* x, const void* w, int ldw, const floa
   if (!x || !w || !y || Cin < 8 || (Cin % 8)) return XMC_EINVAL;
   const size_t smem = (size_t)kImgC * KH * KW * Cin * sizeof(float);
   if (smem > 48 * 1024) return XMC_EINVAL;
-  const long long P = (long long)N * H * W;
-  conv_c3_out_kernel<<<(unsigned)ceil_div_ll(P, 128), 128, smem, (cudaStream_t)stream>>>(
-      (const bf16*)x, (const bf16*)w, ldw, bias, N, H, W, Cin, KH, KW, mode, accumulate, y, (bf16*)y_bf16);
+  const long long P = (long long)N * H * ceil_div(W, kPx);
+  if (KH != KW || (KH != 1 && KH != 3)) return XMC_EINVAL;
+  if (KH == 3)
+    conv_c3_out_kernel<3><<<(unsigned)ceil_div_ll(P, 128), 128, smem, (cudaStream_t)stream>>>(
+        (const bf16*)x, (const bf16*)w, ldw, bias, N, H, W, Cin, mode, accumulate, y, (bf16*)y_bf16);
+  else
+    conv_c3_out_kernel<1><<<(unsigned)ceil_div_ll(P, 128), 128, smem, (cudaStream_t)stream>>>(
+        (const bf16*)x, (const bf16*)w, ldw, bias, N, H, W, Cin, mode, accumulate, y, (bf16*)y_bf16);
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }
 
 extern "C" int xmc_wgrad_c3(const void* x3, const void* y, int N, int H, int W, int C, int KH, int KW, int flip,
                             long long s_tap, int s_c3, int s_c, float* out, void* stream) {
-  if (!x3 || !y || !out || C < 1 || C > 1024 || KH * KW > 9) return XMC_EINVAL;
+  if (!x3 || !y || !out || C < 2 || (C % 2) || C > 2048 || KH * KW > 9) return XMC_EINVAL;
   const int ph = KH / 2, pw = KW / 2;
   const size_t smem = (size_t)(8 + 2 * ph) * (64 + 2 * pw) * kImgC * sizeof(float);
   const int blocks = N * ceil_div(H, 8) * ceil_div(W, 64);
-  const int threads = ceil_div(C, 32) * 32;
-  wgrad_c3_kernel<<<blocks, threads, smem, (cudaStream_t)stream>>>((const bf16*)x3, (const bf16*)y, N, H, W, C, KH, KW,
-                                                                  flip, s_tap, s_c3, s_c, out);
+  const int threads = ceil_div(C / 2, 32) * 32;
+  if (KH != KW || (KH != 1 && KH != 3)) return XMC_EINVAL;
+  if (KH == 3)
+    wgrad_c3_kernel<3><<<blocks, threads, smem, (cudaStream_t)stream>>>((const bf16*)x3, (const bf16*)y, N, H, W, C,
+                                                                       flip, s_tap, s_c3, s_c, out);
+  else
+    wgrad_c3_kernel<1><<<blocks, threads, smem, (cudaStream_t)stream>>>((const bf16*)x3, (const bf16*)y, N, H, W, C,
+                                                                       flip, s_tap, s_c3, s_c, out);
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }
