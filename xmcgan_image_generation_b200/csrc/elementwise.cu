@@ -131,58 +131,93 @@ __device__ __forceinline__ void bn_load_grad(const BnP& p, const bf16* dy, int n
   }
 }
 
-// One block per (cond row, 256-channel-vector chunk): dgamma/dbeta are block-local sums (plain stores, no atomics);
-// the per-channel BN reduction terms S1 = sum dxhat, S2 = sum dxhat*xhat go to global atomics.
+// Each block walks `rows_per_block` consecutive cond rows (and one 256-channel-vector chunk). Within a block the
+// 256 threads are (channel vector) x (lane); lanes are split into `rows_par` rows processed at once x `lpr` lanes per
+// row. dgamma/dbeta are block-local sums (plain stores, no atomics); the per-channel BN reduction terms
+// S1 = sum dxhat, S2 = sum dxhat*xhat are accumulated in registers over all rows of the block and leave through ONE
+// atomic per channel per block.
 __global__ void bn_bwd_reduce_kernel(BnP p, const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                      const float* __restrict__ mr, const bf16* __restrict__ gb,
-                                     float* __restrict__ dgb, float* __restrict__ sums) {
-  extern __shared__ float sm[];  // [lanes][cvb*32]
+                                     float* __restrict__ dgb, float* __restrict__ sums, int rows_per_block,
+                                     long long total_rows) {
+  extern __shared__ float sm[];  // [lanes][cvb*16]
   const int cv = p.C >> 3;
   const int cvb = min(cv - blockIdx.y * 256, 256);
   const int lanes = blockDim.x / cvb;
   const int v = threadIdx.x % cvb, pl = threadIdx.x / cvb;
   const int c = (blockIdx.y * 256 + v) * 8;
-  const long long row = blockIdx.x;
-  const int wc = row % p.Hc, hc = (row / p.Hc) % p.Hc, n = row / (p.Hc * p.Hc);
   const int side = 1 << p.s;
   const int npix = side * side;
-  float dg[8], db[8], s1[8], s2[8];
+  const int lpr = min(lanes, npix);      // lanes per cond row
+  const int rows_par = lanes / lpr;      // cond rows processed concurrently
+  const int row_local = pl / lpr, sub = pl % lpr;
+  const bool lane_ok = pl < rows_par * lpr;
+  const long long row0 = (long long)blockIdx.x * rows_per_block;
+  const long long row_end = min(total_rows, row0 + rows_per_block);
+  float s1[8], s2[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) dg[i] = db[i] = s1[i] = s2[i] = 0.f;
-  if (pl < lanes) {
-    float gm[8], bt[8];
-    load8(gb + row * p.ldG + p.goff + c, gm);
-    load8(gb + row * p.ldG + p.boff + c, bt);
-    for (int q = pl; q < npix; q += lanes) {
-      const int h = hc * side + q / side, w = wc * side + q % side;
-      float f[8], g[8];
-      load8(x + (((long long)n * p.H + h) * p.W + w) * p.C + c, f);
-      bn_load_grad(p, dy, n, h, w, c, g);
+  for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
+  float mean[8], rstd[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float xh = (f[i] - mr[c + i]) * mr[p.C + c + i];
-        float gi = g[i];
-        if (p.relu && (xh * (gm[i] + 1.f) + bt[i]) <= 0.f) gi = 0.f;
-        dg[i] += gi * xh;
-        db[i] += gi;
-        const float dxh = gi * (gm[i] + 1.f);
-        s1[i] += dxh;
-        s2[i] += dxh * xh;
+  for (int i = 0; i < 8; ++i) { mean[i] = mr[c + i]; rstd[i] = mr[p.C + c + i]; }
+  for (long long rbase = row0; rbase < row_end; rbase += rows_par) {
+    const long long row = rbase + row_local;
+    float dg[8], db[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dg[i] = db[i] = 0.f;
+    if (lane_ok && row < row_end) {
+      const int wc = row % p.Hc, hc = (row / p.Hc) % p.Hc, n = row / (p.Hc * p.Hc);
+      float gm[8], bt[8];
+      load8(gb + row * p.ldG + p.goff + c, gm);
+      load8(gb + row * p.ldG + p.boff + c, bt);
+      for (int q = sub; q < npix; q += lpr) {
+        const int h = hc * side + q / side, w = wc * side + q % side;
+        float f[8], g[8];
+        load8(x + (((long long)n * p.H + h) * p.W + w) * p.C + c, f);
+        bn_load_grad(p, dy, n, h, w, c, g);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xh = (f[i] - mean[i]) * rstd[i];
+          float gi = g[i];
+          if (p.relu && (xh * (gm[i] + 1.f) + bt[i]) <= 0.f) gi = 0.f;
+          dg[i] += gi * xh;
+          db[i] += gi;
+          const float dxh = gi * (gm[i] + 1.f);
+          s1[i] += dxh;
+          s2[i] += dxh * xh;
+        }
       }
     }
-    float* o = sm + (pl * cvb + v) * 32;
+    if (lane_ok) {
+      float* o = sm + (pl * cvb + v) * 16;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { o[i] = dg[i]; o[8 + i] = db[i]; o[16 + i] = s1[i]; o[24 + i] = s2[i]; }
+      for (int i = 0; i < 8; ++i) { o[i] = dg[i]; o[8 + i] = db[i]; }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < rows_par * cvb * 16; t += blockDim.x) {
+      const int rl = t / (cvb * 16), rem = t - rl * cvb * 16;
+      const long long orow = rbase + rl;
+      if (orow < row_end) {
+        float a = 0.f;
+        for (int l = 0; l < lpr; ++l) a += sm[((rl * lpr + l) * cvb) * 16 + rem];
+        const int vv = rem >> 4, k = (rem >> 3) & 1, i = rem & 7;
+        const int cc = (blockIdx.y * 256 + vv) * 8 + i;
+        dgb[orow * p.ldG + (k == 0 ? p.goff : p.boff) + cc] = a;
+      }
+    }
+    __syncthreads();
+  }
+  if (lane_ok) {
+    float* o = sm + (pl * cvb + v) * 16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { o[i] = s1[i]; o[8 + i] = s2[i]; }
   }
   __syncthreads();
-  for (int t = threadIdx.x; t < cvb * 32; t += blockDim.x) {
+  for (int t = threadIdx.x; t < cvb * 16; t += blockDim.x) {
     float a = 0.f;
-    for (int l = 0; l < lanes; ++l) a += sm[l * cvb * 32 + t];
-    const int vv = t >> 5, k = (t >> 3) & 3, i = t & 7;
-    const int cc = (blockIdx.y * 256 + vv) * 8 + i;
-    if (k == 0) dgb[row * p.ldG + p.goff + cc] = a;
-    else if (k == 1) dgb[row * p.ldG + p.boff + cc] = a;
-    else atomicAdd(sums + (k - 2) * p.C + cc, a);
+    for (int l = 0; l < rows_par * lpr; ++l) a += sm[l * cvb * 16 + t];
+    const int vv = t >> 4, k = (t >> 3) & 1, i = t & 7;
+    atomicAdd(sums + k * p.C + (blockIdx.y * 256 + vv) * 8 + i, a);
   }
 }
 
@@ -510,10 +545,18 @@ extern "C" int xmc_bn_bwd_reduce(const XmcBnDesc* d, const void* dy, const void*
   const int ny = ceil_div(cv, 256);
   const int cvb = cv < 256 ? cv : 256;
   const int lanes = 256 / cvb;
-  const size_t smem = (size_t)lanes * cvb * 32 * sizeof(float);
+  const size_t smem = (size_t)lanes * cvb * 16 * sizeof(float);
   const long long rows = (long long)p.N * p.Hc * p.Hc;
-  bn_bwd_reduce_kernel<<<dim3((unsigned)rows, ny), 256, smem, (cudaStream_t)stream>>>(
-      p, (const bf16*)dy, (const bf16*)x, mean_rstd, (const bf16*)gb, dgb, sums);
+  // enough blocks for ~8 per SM, each walking several cond rows so the S1/S2 atomics stay rare
+  int rpb = (int)ceil_div_ll(rows, (long long)num_sms() * 8);
+  const int npix = (1 << p.s) * (1 << p.s);
+  const int lpr = lanes < npix ? lanes : npix;
+  const int rows_par = lanes / lpr;
+  rpb = ceil_div(rpb, rows_par) * rows_par;
+  if (rpb < rows_par) rpb = rows_par;
+  const long long gx = ceil_div_ll(rows, rpb);
+  bn_bwd_reduce_kernel<<<dim3((unsigned)gx, ny), 256, smem, (cudaStream_t)stream>>>(
+      p, (const bf16*)dy, (const bf16*)x, mean_rstd, (const bf16*)gb, dgb, sums, rpb, rows);
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }

@@ -215,9 +215,15 @@ __global__ void wgrad_c3_kernel(const bf16* __restrict__ x3, const bf16* __restr
         for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
           for (int c3 = 0; c3 < 3; ++c3) win[col][kh][c3] = xs[((r + kh) * xw + col) * kImgC + c3];
-      for (int q0 = 0; q0 < qn; q0 += 3) {
+      // 12 pixels per outer iteration: all 12 y loads are issued first (the loop is latency-bound otherwise)
+      for (int q0 = 0; q0 < qn; q0 += 12) {
+        __nv_bfloat162 yv[12];
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
+        for (int j = 0; j < 12; ++j)
+          yv[j] = (q0 + j < qn) ? *reinterpret_cast<const __nv_bfloat162*>(yrow + (long long)(q0 + j) * C)
+                                : __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 12; ++j) {
           const int q = q0 + j;
           if (q < qn) {
             // bring in column q+2 into slot (j+2)%3
@@ -225,8 +231,7 @@ __global__ void wgrad_c3_kernel(const bf16* __restrict__ x3, const bf16* __restr
             for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
               for (int c3 = 0; c3 < 3; ++c3) win[(j + 2) % 3][kh][c3] = xs[((r + kh) * xw + q + 2) * kImgC + c3];
-            const __nv_bfloat162 yv2 = *reinterpret_cast<const __nv_bfloat162*>(yrow + (long long)q * C);
-            const float y0 = __low2float(yv2), y1 = __high2float(yv2);
+            const float y0 = __low2float(yv[j]), y1 = __high2float(yv[j]);
 #pragma unroll
             for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
