@@ -101,7 +101,8 @@ int xmc_bn_finalize(const float* sums, long long P, int C, float eps, float mome
 int xmc_bn_eval_stats(const float* ra_mean, const float* ra_var, int C, float eps, float* mean_rstd, void* stream);
 int xmc_bn_apply(const XmcBnDesc* d, const void* x, const float* mean_rstd, const void* gb, void* y, void* stream);
 /* backward, pass 1: dgb (fp32, same row/column layout as gb) = d(gamma), d(beta); sums[2C] (zeroed by caller) +=
- * per-channel sum(dxhat), sum(dxhat*xhat). dy has the upsampled shape when d->upsample. */
+ * per-channel sum(dxhat), sum(dxhat*xhat). dy has the upsampled shape when d->upsample. For Hc == 1 the gamma/beta
+ * columns of dgb are accumulated atomically and must be zero-filled by the caller; for Hc > 1 they are overwritten. */
 int xmc_bn_bwd_reduce(const XmcBnDesc* d, const void* dy, const void* x, const float* mean_rstd, const void* gb,
                       float* dgb, float* sums, void* stream);
 /* backward, pass 2: dx = rstd*(dxhat - mean(dxhat) - xhat*mean(dxhat*xhat)) */

@@ -78,18 +78,21 @@ __device__ __forceinline__ long long cond_row(const BnP& p, int n, int h, int w)
   return ((long long)n * p.Hc + (h >> p.s)) * p.Hc + (w >> p.s);
 }
 
+// blockDim = (C/8 channel vectors, pixels per block): a thread keeps its channel vector for the whole loop, so
+// mean / rstd stay in registers and consecutive threads touch consecutive 16-byte vectors of the same pixel.
 __global__ void bn_apply_kernel(BnP p, const bf16* __restrict__ x, const float* __restrict__ mr,
                                 const bf16* __restrict__ gb, bf16* __restrict__ y) {
-  const int cv = p.C >> 3;
-  const long long total = (long long)p.N * p.H * p.W * cv;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int v = idx % cv;
-    long long pix = idx / cv;
-    const int w = pix % p.W;
-    const int h = (pix / p.W) % p.H;
-    const int n = pix / ((long long)p.W * p.H);
-    const int c = v * 8;
+  const int c = threadIdx.x * 8;
+  float mean[8], rstd[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { mean[i] = mr[c + i]; rstd[i] = mr[p.C + c + i]; }
+  const int HW = p.H * p.W;
+  const long long P = (long long)p.N * HW;
+  for (long long pix = (long long)blockIdx.x * blockDim.y + threadIdx.y; pix < P;
+       pix += (long long)gridDim.x * blockDim.y) {
+    const int n = (int)(pix / HW);
+    const int hw = (int)(pix - (long long)n * HW);
+    const int h = hw / p.W, w = hw - h * p.W;
     float f[8], g[8], b[8], o[8];
     load8(x + pix * p.C + c, f);
     const long long row = cond_row(p, n, h, w);
@@ -97,8 +100,7 @@ __global__ void bn_apply_kernel(BnP p, const bf16* __restrict__ x, const float* 
     load8(gb + row * p.ldG + p.boff + c, b);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float xh = (f[i] - mr[c + i]) * mr[p.C + c + i];
-      float t = xh * (g[i] + 1.f) + b[i];
+      const float t = (f[i] - mean[i]) * rstd[i] * (g[i] + 1.f) + b[i];
       o[i] = p.relu ? fmaxf(t, 0.f) : t;
     }
     if (p.upsample) {
@@ -131,47 +133,38 @@ __device__ __forceinline__ void bn_load_grad(const BnP& p, const bf16* dy, int n
   }
 }
 
-// Each block walks `rows_per_block` consecutive cond rows (and one 256-channel-vector chunk). Within a block the
-// 256 threads are (channel vector) x (lane); lanes are split into `rows_par` rows processed at once x `lpr` lanes per
-// row. dgamma/dbeta are block-local sums (plain stores, no atomics); the per-channel BN reduction terms
-// S1 = sum dxhat, S2 = sum dxhat*xhat are accumulated in registers over all rows of the block and leave through ONE
-// atomic per channel per block.
+// One thread owns one (cond row, 8-channel vector): it walks the (H/Hc)^2 pixels of that cond cell, so dgamma/dbeta
+// need no cross-thread reduction at all (plain stores). The per-channel BN terms S1 = sum dxhat, S2 = sum dxhat*xhat
+// are combined per block in shared memory and leave through one global atomic per channel per block.
 __global__ void bn_bwd_reduce_kernel(BnP p, const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                      const float* __restrict__ mr, const bf16* __restrict__ gb,
-                                     float* __restrict__ dgb, float* __restrict__ sums, int rows_per_block,
-                                     long long total_rows) {
-  extern __shared__ float sm[];  // [lanes][cvb*16]
+                                     float* __restrict__ dgb, float* __restrict__ sums, long long total_rows,
+                                     int psplit) {
+  extern __shared__ float sm[];  // [cv][16]
   const int cv = p.C >> 3;
-  const int cvb = min(cv - blockIdx.y * 256, 256);
-  const int lanes = blockDim.x / cvb;
-  const int v = threadIdx.x % cvb, pl = threadIdx.x / cvb;
-  const int c = (blockIdx.y * 256 + v) * 8;
-  const int side = 1 << p.s;
-  const int npix = side * side;
-  const int lpr = min(lanes, npix);      // lanes per cond row
-  const int rows_par = lanes / lpr;      // cond rows processed concurrently
-  const int row_local = pl / lpr, sub = pl % lpr;
-  const bool lane_ok = pl < rows_par * lpr;
-  const long long row0 = (long long)blockIdx.x * rows_per_block;
-  const long long row_end = min(total_rows, row0 + rows_per_block);
-  float s1[8], s2[8];
+  for (int t = threadIdx.x; t < cv * 16; t += blockDim.x) sm[t] = 0.f;
+  __syncthreads();
+  const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item < total_rows * cv * psplit) {
+    const int v = item % cv;
+    const int sp = (item / cv) % psplit;   // pixel-split index (psplit > 1 only for per-image cells, Hc == 1)
+    const long long row = item / ((long long)cv * psplit);
+    const int c = v * 8;
+    const int wc = row % p.Hc, hc = (row / p.Hc) % p.Hc, n = row / (p.Hc * p.Hc);
+    const int side = 1 << p.s;
+    float gm[8], bt[8], mean[8], rstd[8], dg[8], db[8], s1[8], s2[8];
+    load8(gb + row * p.ldG + p.goff + c, gm);
+    load8(gb + row * p.ldG + p.boff + c, bt);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
-  float mean[8], rstd[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { mean[i] = mr[c + i]; rstd[i] = mr[p.C + c + i]; }
-  for (long long rbase = row0; rbase < row_end; rbase += rows_par) {
-    const long long row = rbase + row_local;
-    float dg[8], db[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) dg[i] = db[i] = 0.f;
-    if (lane_ok && row < row_end) {
-      const int wc = row % p.Hc, hc = (row / p.Hc) % p.Hc, n = row / (p.Hc * p.Hc);
-      float gm[8], bt[8];
-      load8(gb + row * p.ldG + p.goff + c, gm);
-      load8(gb + row * p.ldG + p.boff + c, bt);
-      for (int q = sub; q < npix; q += lpr) {
-        const int h = hc * side + q / side, w = wc * side + q % side;
+    for (int i = 0; i < 8; ++i) {
+      mean[i] = mr[c + i];
+      rstd[i] = mr[p.C + c + i];
+      dg[i] = db[i] = s1[i] = s2[i] = 0.f;
+    }
+    for (int a = sp; a < side; a += psplit) {
+      const int h = hc * side + a;
+      for (int b = 0; b < side; ++b) {
+        const int w = wc * side + b;
         float f[8], g[8];
         load8(x + (((long long)n * p.H + h) * p.W + w) * p.C + c, f);
         bn_load_grad(p, dy, n, h, w, c, g);
@@ -188,52 +181,47 @@ __global__ void bn_bwd_reduce_kernel(BnP p, const bf16* __restrict__ dy, const b
         }
       }
     }
-    if (lane_ok) {
-      float* o = sm + (pl * cvb + v) * 16;
+    float* og = dgb + row * p.ldG + p.goff + c;
+    float* ob = dgb + row * p.ldG + p.boff + c;
+    if (psplit == 1) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { o[i] = dg[i]; o[8 + i] = db[i]; }
-    }
-    __syncthreads();
-    for (int t = threadIdx.x; t < rows_par * cvb * 16; t += blockDim.x) {
-      const int rl = t / (cvb * 16), rem = t - rl * cvb * 16;
-      const long long orow = rbase + rl;
-      if (orow < row_end) {
-        float a = 0.f;
-        for (int l = 0; l < lpr; ++l) a += sm[((rl * lpr + l) * cvb) * 16 + rem];
-        const int vv = rem >> 4, k = (rem >> 3) & 1, i = rem & 7;
-        const int cc = (blockIdx.y * 256 + vv) * 8 + i;
-        dgb[orow * p.ldG + (k == 0 ? p.goff : p.boff) + cc] = a;
-      }
-    }
-    __syncthreads();
-  }
-  if (lane_ok) {
-    float* o = sm + (pl * cvb + v) * 16;
+      for (int i = 0; i < 8; ++i) { og[i] = dg[i]; ob[i] = db[i]; }
+    } else {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { o[i] = s1[i]; o[8 + i] = s2[i]; }
+      for (int i = 0; i < 8; ++i) { atomicAdd(og + i, dg[i]); atomicAdd(ob + i, db[i]); }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(sm + v * 16 + i, s1[i]);
+      atomicAdd(sm + v * 16 + 8 + i, s2[i]);
+    }
   }
   __syncthreads();
-  for (int t = threadIdx.x; t < cvb * 16; t += blockDim.x) {
-    float a = 0.f;
-    for (int l = 0; l < rows_par * lpr; ++l) a += sm[l * cvb * 16 + t];
+  for (int t = threadIdx.x; t < cv * 16; t += blockDim.x) {
     const int vv = t >> 4, k = (t >> 3) & 1, i = t & 7;
-    atomicAdd(sums + k * p.C + (blockIdx.y * 256 + vv) * 8 + i, a);
+    atomicAdd(sums + k * p.C + vv * 8 + i, sm[t]);
   }
 }
 
 __global__ void bn_bwd_apply_kernel(BnP p, const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                     const float* __restrict__ mr, const bf16* __restrict__ gb,
                                     const float* __restrict__ sums, float invP, bf16* __restrict__ dx) {
-  const int cv = p.C >> 3;
-  const long long total = (long long)p.N * p.H * p.W * cv;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int v = idx % cv;
-    long long pix = idx / cv;
-    const int w = pix % p.W;
-    const int h = (pix / p.W) % p.H;
-    const int n = pix / ((long long)p.W * p.H);
-    const int c = v * 8;
+  const int c = threadIdx.x * 8;
+  float mean[8], rstd[8], m1[8], m2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    mean[i] = mr[c + i];
+    rstd[i] = mr[p.C + c + i];
+    m1[i] = sums[c + i] * invP;
+    m2[i] = sums[p.C + c + i] * invP;
+  }
+  const int HW = p.H * p.W;
+  const long long P = (long long)p.N * HW;
+  for (long long pix = (long long)blockIdx.x * blockDim.y + threadIdx.y; pix < P;
+       pix += (long long)gridDim.x * blockDim.y) {
+    const int n = (int)(pix / HW);
+    const int hw = (int)(pix - (long long)n * HW);
+    const int h = hw / p.W, w = hw - h * p.W;
     float f[8], g[8], gm[8], bt[8], o[8];
     load8(x + pix * p.C + c, f);
     bn_load_grad(p, dy, n, h, w, c, g);
@@ -242,12 +230,11 @@ __global__ void bn_bwd_apply_kernel(BnP p, const bf16* __restrict__ dy, const bf
     load8(gb + row * p.ldG + p.boff + c, bt);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float rstd = mr[p.C + c + i];
-      const float xh = (f[i] - mr[c + i]) * rstd;
+      const float xh = (f[i] - mean[i]) * rstd[i];
       float gi = g[i];
       if (p.relu && (xh * (gm[i] + 1.f) + bt[i]) <= 0.f) gi = 0.f;
       const float dxh = gi * (gm[i] + 1.f);
-      o[i] = rstd * (dxh - sums[c + i] * invP - xh * sums[p.C + c + i] * invP);
+      o[i] = rstd[i] * (dxh - m1[i] - xh * m2[i]);
     }
     store8(dx + pix * p.C + c, o);
   }
@@ -471,6 +458,19 @@ static int grid_for(long long total, int block) {
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
+// (C/8, pixels-per-block) thread block and a grid capped at 16 blocks per SM
+static void bn_launch_dims(const BnP& p, dim3* grid, dim3* block) {
+  const int cv = p.C / 8;
+  const int py = 256 / cv > 0 ? 256 / cv : 1;
+  const long long P = (long long)p.N * p.H * p.W;
+  long long g = (P + py - 1) / py;
+  const long long cap = (long long)num_sms() * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  *grid = dim3((unsigned)g);
+  *block = dim3(cv, py);
+}
+
 static int fill_bnp(const XmcBnDesc* d, BnP* p) {
   if (!d || d->N < 1 || d->H < 1 || d->W < 1 || d->C < 8 || (d->C % 8) || d->Hc < 1) return XMC_EINVAL;
   if (d->H != d->W || d->H % d->Hc) return XMC_EINVAL;
@@ -528,9 +528,10 @@ extern "C" int xmc_bn_apply(const XmcBnDesc* d, const void* x, const float* mean
   int r = fill_bnp(d, &p);
   if (r) return r;
   if (!x || !mean_rstd || !gb || !y) return XMC_EINVAL;
-  const long long total = (long long)p.N * p.H * p.W * (p.C / 8);
-  bn_apply_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(p, (const bf16*)x, mean_rstd,
-                                                                         (const bf16*)gb, (bf16*)y);
+  if (p.C / 8 > 1024) return XMC_EINVAL;
+  dim3 grid, block;
+  bn_launch_dims(p, &grid, &block);
+  bn_apply_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(p, (const bf16*)x, mean_rstd, (const bf16*)gb, (bf16*)y);
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }
@@ -542,21 +543,21 @@ extern "C" int xmc_bn_bwd_reduce(const XmcBnDesc* d, const void* dy, const void*
   if (r) return r;
   if (!dy || !x || !mean_rstd || !gb || !dgb || !sums) return XMC_EINVAL;
   const int cv = p.C / 8;
-  const int ny = ceil_div(cv, 256);
-  const int cvb = cv < 256 ? cv : 256;
-  const int lanes = 256 / cvb;
-  const size_t smem = (size_t)lanes * cvb * 16 * sizeof(float);
+  const size_t smem = (size_t)cv * 16 * sizeof(float);
+  if (smem > 48 * 1024) return XMC_EINVAL;
   const long long rows = (long long)p.N * p.Hc * p.Hc;
-  // enough blocks for ~8 per SM, each walking several cond rows so the S1/S2 atomics stay rare
-  int rpb = (int)ceil_div_ll(rows, (long long)num_sms() * 8);
-  const int npix = (1 << p.s) * (1 << p.s);
-  const int lpr = lanes < npix ? lanes : npix;
-  const int rows_par = lanes / lpr;
-  rpb = ceil_div(rpb, rows_par) * rows_par;
-  if (rpb < rows_par) rpb = rows_par;
-  const long long gx = ceil_div_ll(rows, rpb);
-  bn_bwd_reduce_kernel<<<dim3((unsigned)gx, ny), 256, smem, (cudaStream_t)stream>>>(
-      p, (const bf16*)dy, (const bf16*)x, mean_rstd, (const bf16*)gb, dgb, sums, rpb, rows);
+  // small cells (few pixels per thread) -> larger blocks amortise the shared/global atomics; big cells -> 128 threads
+  const int threads = p.s >= 2 ? 128 : 256;
+  // per-image cells (ConditionalBatchNorm) have few rows and many pixels: split the pixel rows over several threads,
+  // which then accumulate dgamma/dbeta atomically (the caller zero-fills dgb for Hc == 1)
+  int psplit = 1;
+  if (p.Hc == 1) {
+    const int side = 1 << p.s;
+    psplit = side < 8 ? side : 8;
+  }
+  const long long gx = ceil_div_ll(rows * cv * psplit, threads);
+  bn_bwd_reduce_kernel<<<(unsigned)gx, threads, smem, (cudaStream_t)stream>>>(
+      p, (const bf16*)dy, (const bf16*)x, mean_rstd, (const bf16*)gb, dgb, sums, rows, psplit);
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }
@@ -567,9 +568,11 @@ extern "C" int xmc_bn_bwd_apply(const XmcBnDesc* d, const void* dy, const void* 
   int r = fill_bnp(d, &p);
   if (r) return r;
   if (!dy || !x || !mean_rstd || !gb || !sums || !dx) return XMC_EINVAL;
-  const long long total = (long long)p.N * p.H * p.W * (p.C / 8);
+  if (p.C / 8 > 1024) return XMC_EINVAL;
   const float invP = 1.f / (float)((long long)p.N * p.H * p.W);
-  bn_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+  dim3 grid, block;
+  bn_launch_dims(p, &grid, &block);
+  bn_bwd_apply_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(
       p, (const bf16*)dy, (const bf16*)x, mean_rstd, (const bf16*)gb, sums, invP, (bf16*)dx);
   XMC_LAUNCH_CHECK();
   return XMC_OK;

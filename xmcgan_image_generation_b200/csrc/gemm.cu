@@ -47,10 +47,11 @@ struct WgradParams {
   int chunks_w, chunks_h, chunks_n;  // pixel-chunk grid (K dimension)
   int tw, th, tn;
   int total_chunks, chunks_per_split, ksplit;
-  int n_tiles, BN, nslabs;
-  int KW, pad_h, pad_w;
+  int m_tiles, n_tiles, BN, nslabs;
+  int taps, KW, pad_h, pad_w;
   int Ca, Cb;
   int batched;
+  int items_per_split, total_items;
   uint32_t slab_bytes;  // bytes one TMA box writes
   uint32_t idesc;
   void* out;
@@ -307,7 +308,9 @@ gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // =====================================================================================================================
 // Weight gradient:  D[Ca-tile(128), Cb-tile(BN)] = sum_{pixel chunks} A[pixels(+tap shift), ca]^T * B[pixels, cb]
 // Both operands arrive pixel-major (64-channel slabs of [pixels][128B] rows) and are consumed as MN-major UMMA tiles.
-// grid = (m_tiles*n_tiles, taps, batch*ksplit); one output tile per CTA.
+// Persistent: work item = (K split, batch, tap, output tile); items that run concurrently share the same pixel range
+// (HBM reads it once, L2 serves the rest). Two TMEM accumulators: the epilogue (vector reductions to global) of one
+// item overlaps the MMAs of the next.
 // =====================================================================================================================
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -318,7 +321,8 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t bar_base = sbase + kStages * kStageBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
-  const uint32_t tfull_bar = bar_base + 8u * (2 * kStages);
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + kStages * kStageBytes + 8 * (2 * kStages + 4));
 
   const int warp = threadIdx.x >> 5;
@@ -336,11 +340,14 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(tfull_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(tmem_ptr_smem), 256);
+    tmem_alloc(smem_u32(tmem_ptr_smem), kTmemCols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -348,13 +355,18 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  const int mt = blockIdx.x / p.n_tiles, nt = blockIdx.x - mt * p.n_tiles;
-  const int tap = blockIdx.y;
-  const int kh = tap / p.KW, kw = tap - kh * p.KW;
-  const int bz = blockIdx.z / p.ksplit, split = blockIdx.z - bz * p.ksplit;
-  const int j0 = split * p.chunks_per_split;
-  const int j1 = min(p.total_chunks, j0 + p.chunks_per_split);
-  const int m0 = mt * 128, n_off = nt * p.BN;
+  // item -> (split, batch, tap, m tile, n tile)
+  auto decode = [&](int item, int& split, int& bz, int& tap, int& mt, int& nt) {
+    split = item / p.items_per_split;
+    int rem = item - split * p.items_per_split;
+    const int tiles = p.m_tiles * p.n_tiles;
+    bz = rem / (p.taps * tiles);
+    rem -= bz * p.taps * tiles;
+    tap = rem / tiles;
+    rem -= tap * tiles;
+    mt = rem / p.n_tiles;
+    nt = rem - mt * p.n_tiles;
+  };
 
   if (warp == 0) {
     if (elect_one()) {
@@ -363,111 +375,143 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx = (2 + p.nslabs) * p.slab_bytes;
-      for (int j = j0; j < j1; ++j) {
-        const int iw = j % p.chunks_w;
-        const int ih = (j / p.chunks_w) % p.chunks_h;
-        const int in = p.batched ? bz : j / (p.chunks_w * p.chunks_h);
-        const int w0 = iw * p.tw, h0 = ih * p.th, n0 = p.batched ? bz : in * p.tn;
-        mbar_wait(empty_bar(stage), phase ^ 1);
-        mbar_arrive_expect_tx(full_bar(stage), tx);
-        const uint32_t sa = sbase + stage * kStageBytes;
-        tma_load_4d(sa, &tmA, full_bar(stage), m0, w0 + kw - p.pad_w, h0 + kh - p.pad_h, n0);
-        tma_load_4d(sa + 8192, &tmA, full_bar(stage), m0 + 64, w0 + kw - p.pad_w, h0 + kh - p.pad_h, n0);
-        for (int s = 0; s < p.nslabs; ++s)
-          tma_load_4d(sa + kABytes + s * 8192, &tmB, full_bar(stage), n_off + s * 64, w0, h0, n0);
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        int split, bz, tap, mt, nt;
+        decode(item, split, bz, tap, mt, nt);
+        const int kh = tap / p.KW, kw = tap - kh * p.KW;
+        const int j0 = split * p.chunks_per_split;
+        const int j1 = min(p.total_chunks, j0 + p.chunks_per_split);
+        const int m0 = mt * 128, n_off = nt * p.BN;
+        for (int j = j0; j < j1; ++j) {
+          const int iw = j % p.chunks_w;
+          const int ih = (j / p.chunks_w) % p.chunks_h;
+          const int in = j / (p.chunks_w * p.chunks_h);
+          const int w0 = iw * p.tw, h0 = ih * p.th, n0 = p.batched ? bz : in * p.tn;
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          mbar_arrive_expect_tx(full_bar(stage), tx);
+          const uint32_t sa = sbase + stage * kStageBytes;
+          tma_load_4d(sa, &tmA, full_bar(stage), m0, w0 + kw - p.pad_w, h0 + kh - p.pad_h, n0);
+          tma_load_4d(sa + 8192, &tmA, full_bar(stage), m0 + 64, w0 + kw - p.pad_w, h0 + kh - p.pad_h, n0);
+          for (int s = 0; s < p.nslabs; ++s)
+            tma_load_4d(sa + kABytes + s * 8192, &tmB, full_bar(stage), n_off + s * 64, w0, h0, n0);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
     int stage = 0;
     uint32_t phase = 0;
-    for (int j = j0; j < j1; ++j) {
-      mbar_wait(full_bar(stage), phase);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      const int split = item / p.items_per_split;
+      const int j0 = split * p.chunks_per_split;
+      const int j1 = min(p.total_chunks, j0 + p.chunks_per_split);
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1);
       tc_fence_after();
-      if (elect_one()) {
-        const uint32_t sa = sbase + stage * kStageBytes;
-        // MN-major SW128: LBO = byte distance between 64-channel slabs, SBO = distance between 8-pixel groups.
-        const uint64_t adesc = make_smem_desc(sa, 8192, 1024);
-        const uint64_t bdesc = make_smem_desc(sa + kABytes, 8192, 1024);
+      const uint32_t d_tmem = tmem_base + acc * 256;
+      for (int j = j0; j < j1; ++j) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = sbase + stage * kStageBytes;
+          // MN-major SW128: LBO = byte distance between 64-channel slabs, SBO = distance between 8-pixel groups.
+          const uint64_t adesc = make_smem_desc(sa, 8192, 1024);
+          const uint64_t bdesc = make_smem_desc(sa + kABytes, 8192, 1024);
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
-          // 16 pixels (K) per MMA = two 8-pixel groups = 2048 bytes: +128 in the (addr>>4) field
-          umma_bf16(tmem_base, adesc + 128 * s, bdesc + 128 * s, p.idesc, (j > j0 || s > 0) ? 1u : 0u);
+          for (int s = 0; s < 4; ++s) {
+            // 16 pixels (K) per MMA = two 8-pixel groups = 2048 bytes: +128 in the (addr>>4) field
+            umma_bf16(d_tmem, adesc + 128 * s, bdesc + 128 * s, p.idesc, (j > j0 || s > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));
+          if (j == j1 - 1) umma_commit(tfull_bar(acc));
         }
-        umma_commit(empty_bar(stage));
-        if (j == j1 - 1) umma_commit(tfull_bar);
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
-      __syncwarp();
-      if (++stage == kStages) { stage = 0; phase ^= 1; }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   } else {
     const int q = warp & 3;
-    const int m = m0 + q * 32 + lane;
-    const bool row_ok = m < p.Ca;
-    mbar_wait(tfull_bar, 0);
-    tc_fence_after();
-    const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const long long obase = (long long)bz * p.out_batch_stride + (long long)tap * p.out_tap_stride +
-                            (long long)m * p.ldOut;
-    for (int c0 = 0; c0 < p.BN; c0 += 16) {
-      uint32_t v[16];
-      tmem_ld16(t_addr + c0, v);
-      tmem_ld_wait();
-      const int col = n_off + c0;
-      if (row_ok && col < p.Cb) {
-        const int nvalid = min(16, p.Cb - col);
-        const bool vec = p.vec_ok && nvalid == 16;
-        float f[16];
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      int split, bz, tap, mt, nt;
+      decode(item, split, bz, tap, mt, nt);
+      const int m = mt * 128 + q * 32 + lane;
+      const int n_off = nt * p.BN;
+      const bool row_ok = m < p.Ca;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
+      const long long obase = (long long)bz * p.out_batch_stride + (long long)tap * p.out_tap_stride +
+                              (long long)m * p.ldOut;
+      for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_addr + c0, v);
+        tmem_ld_wait();
+        const int col = n_off + c0;
+        if (row_ok && col < p.Cb) {
+          const int nvalid = min(16, p.Cb - col);
+          const bool vec = p.vec_ok && nvalid == 16;
+          float f[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
-        if (p.out_mode == 2) {
-          bf16* o = reinterpret_cast<bf16*>(p.out) + obase + col;
-          if (vec) {
-            uint4 a, b;
-            a.x = pack_bf16x2(f[0], f[1]);   a.y = pack_bf16x2(f[2], f[3]);
-            a.z = pack_bf16x2(f[4], f[5]);   a.w = pack_bf16x2(f[6], f[7]);
-            b.x = pack_bf16x2(f[8], f[9]);   b.y = pack_bf16x2(f[10], f[11]);
-            b.z = pack_bf16x2(f[12], f[13]); b.w = pack_bf16x2(f[14], f[15]);
-            reinterpret_cast<uint4*>(o)[0] = a;
-            reinterpret_cast<uint4*>(o)[1] = b;
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (i < nvalid) o[i] = __float2bfloat16(f[i]);
-          }
-        } else {
-          float* o = reinterpret_cast<float*>(p.out) + obase + col;
-          if (p.out_mode == 1) {
+          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
+          if (p.out_mode == 2) {
+            bf16* o = reinterpret_cast<bf16*>(p.out) + obase + col;
             if (vec) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                reinterpret_cast<float4*>(o)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+              uint4 a, b;
+              a.x = pack_bf16x2(f[0], f[1]);   a.y = pack_bf16x2(f[2], f[3]);
+              a.z = pack_bf16x2(f[4], f[5]);   a.w = pack_bf16x2(f[6], f[7]);
+              b.x = pack_bf16x2(f[8], f[9]);   b.y = pack_bf16x2(f[10], f[11]);
+              b.z = pack_bf16x2(f[12], f[13]); b.w = pack_bf16x2(f[14], f[15]);
+              reinterpret_cast<uint4*>(o)[0] = a;
+              reinterpret_cast<uint4*>(o)[1] = b;
             } else {
 #pragma unroll
               for (int i = 0; i < 16; ++i)
-                if (i < nvalid) o[i] = f[i];
+                if (i < nvalid) o[i] = __float2bfloat16(f[i]);
             }
           } else {
-            if (vec) {
+            float* o = reinterpret_cast<float*>(p.out) + obase + col;
+            if (p.out_mode == 1) {
+              if (vec) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4 * i), "f"(f[4 * i]),
-                             "f"(f[4 * i + 1]), "f"(f[4 * i + 2]), "f"(f[4 * i + 3])
-                             : "memory");
+                for (int i = 0; i < 4; ++i)
+                  reinterpret_cast<float4*>(o)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  if (i < nvalid) o[i] = f[i];
+              }
             } else {
+              if (vec) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (i < nvalid) atomicAdd(o + i, f[i]);
+                for (int i = 0; i < 4; ++i)
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4 * i), "f"(f[4 * i]),
+                               "f"(f[4 * i + 1]), "f"(f[4 * i + 2]), "f"(f[4 * i + 3])
+                               : "memory");
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  if (i < nvalid) atomicAdd(o + i, f[i]);
+              }
             }
           }
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 1) tmem_dealloc(tmem_base, 256);
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 // =====================================================================================================================
@@ -634,6 +678,9 @@ extern "C" int xmc_conv2d_wgrad(const XmcWgradDesc* d, const void* xa, const voi
   p.chunks_per_split = ceil_div(p.total_chunks, ksplit);
   p.ksplit = ceil_div(p.total_chunks, p.chunks_per_split);
   p.KW = d->KW; p.pad_h = d->pad_h; p.pad_w = d->pad_w;
+  p.taps = taps; p.m_tiles = m_tiles;
+  p.items_per_split = base_ctas;
+  p.total_items = base_ctas * p.ksplit;
   p.Ca = d->Ca; p.Cb = d->Cb; p.batched = d->batched;
   p.slab_bytes = (uint32_t)(64 * p.tw * p.th * p.tn * 2);
   p.idesc = make_idesc_bf16(128, p.BN, 1, 1);
@@ -663,7 +710,7 @@ extern "C" int xmc_conv2d_wgrad(const XmcWgradDesc* d, const void* xa, const voi
     XMC_CUDA_CHECK(cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     g_attr_set_wgrad = true;
   }
-  dim3 grid(m_tiles * p.n_tiles, taps, nbatch * p.ksplit);
+  const int grid = p.total_items < num_sms() ? p.total_items : num_sms();
   gemm_wgrad_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(tmA, tmB, p);
   XMC_LAUNCH_CHECK();
   return XMC_OK;

@@ -367,7 +367,7 @@ class GeneratorEngine:
     B, E, zd, cd, scd = ctx["B"], self.E, self.zd, self.cd, self.scd
     S = d_img.shape[1]
     gbC, gbL, R, Hc16 = ctx["gbC"], ctx["gbL"], ctx["R"], ctx["Hc"]
-    dgbC = ops.empty((B, self.NC), F32)
+    dgbC = ops.zeros((B, self.NC), F32)  # ConditionalBatchNorm d(gamma), d(beta) are accumulated atomically
     dgbL = ops.empty((B * R, self.NL), F32)
 
     # output head: tanh, conv3x3 (C -> 3)
