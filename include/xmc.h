@@ -55,6 +55,14 @@ typedef struct {
   int relu;
   int res_shift;           /* residual is an (N, H>>s, W>>s) tensor read at (n, h>>s, w>>s): fused nearest upsample */
   int ldRes, ldMask;
+  /* Optional strided / re-pitched input view (all 0 = dense stride-1 input of the output's size). The input is read
+   * through a tensor map of extents (C, Win, Hin, N) with element pitches (pitchW, pitchH, pitchN) and traversal
+   * strides (strideW, strideH): output pixel (h, w), tap (kh, kw) reads input position
+   * (h*strideH + kh - pad_h, w*strideW + kw - pad_w). Used for the stride-2 convolutions of the frozen ResNet-50
+   * (xmcgan/utils/resnet_v1.py:64,79,146-151; XLA SAME padding low=floor(p/2)). */
+  int strideH, strideW, Hin, Win;
+  long long pitchW, pitchH, pitchN;
+  int mask_last;           /* 1: apply the mask after the residual add: v = (alpha*acc + bias + residual) masked */
 } XmcConvDesc;
 
 int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* wk, const float* bias, const void* residual,
@@ -144,6 +152,7 @@ typedef struct {
   int sn;                 /* spectral-norm slot, or -1 */
   int tile_begin;         /* prefix sum of ceil(taps*cin/32)*ceil(cout/32) */
   int reserved;
+  long long cscale_off;   /* per-output-channel scale inside the fp32 `cscale` buffer (folded eval BatchNorm), or -1 */
 } XmcPrepEntry;
 
 typedef struct {
@@ -167,7 +176,8 @@ int xmc_sn_forward(const XmcSnEntry* table_dev, int n, float eps, const float* p
 int xmc_sn_backward(const XmcSnEntry* table_dev, int n, const float* params, float* grads, const float* t_ws,
                     const float* u0_new, float* scalars, int total_elem_blocks, void* stream);
 int xmc_prep_weights(const XmcPrepEntry* table_dev, int n, int total_tiles, const float* params,
-                     const float* sn_scalars, int n_sn, void* arena, float* bias_arena, void* stream);
+                     const float* sn_scalars, int n_sn, void* arena, float* bias_arena, const float* cscale,
+                     void* stream);
 /* flax.optim.Adam.apply_gradient (weight_decay 0) in place on flat buffers, gradient pre-scaled by grad_scale
  * (1/world after a sum all-reduce == lax.pmean); optional polyak EMA of the updated parameters
  * (xmcgan/xmc_gan.py:172-177,252). bias_corr = 1 - beta^t. n must be a multiple of 4. */
@@ -249,6 +259,23 @@ int xmc_wgrad_c3(const void* x3, const void* y, int N, int H, int W, int C, int 
 int xmc_pool2_small(const void* a, int N, int Hout, int Wout, int C, float scale, void* out, void* stream);
 int xmc_unpool2_add_f32(const float* d, int N, int Hin, int Win, int C, float scale, float* g, void* stream);
 int xmc_tanh01_bwd(const float* dimg, const float* img, long long n, void* dpre, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Frozen ResNet-50 feature branch (xmcgan/xmc_gan.py:74-90, xmcgan/utils/resnet_v1.py:129-172,
+ * xmcgan/utils/pretrained_model_utils.py:102-127). Its convolutions use xmc_conv2d_fwd (BatchNorm folded).
+ */
+/* jax.image.resize(img, (T,T), "bilinear") of fp32 [N,S,S,3] into a zero-bordered bf16 [N,Tp,Tp,8] buffer */
+int xmc_resize_bilinear_pad(const float* img, int N, int S, int T, int Tp, int pad_lo, void* out, void* stream);
+/* transpose of the resize: dimg[N,S,S,3] += R^T dout[N,T,T,3] */
+int xmc_resize_bilinear_bwd(const float* dout, int N, int S, int T, float* dimg, void* stream);
+/* input gradient of the 7x7/2 stem (resnet_v1.py:146-151): dy bf16 [N,Ho,Ho,Cout], wk bf16 [Cout][7*56] */
+int xmc_stem_dgrad(const void* dy, const void* wk, int N, int T, int Ho, int Cout, int pad_lo, float* dimg,
+                   void* stream);
+/* nn.max_pool 3x3/2 SAME (resnet_v1.py:154) on bf16 [N,H,H,C] and its transpose (first-max tie rule) */
+int xmc_maxpool3s2(const void* x, int N, int H, int C, void* y, void* stream);
+int xmc_maxpool3s2_bwd(const void* dy, const void* x, const void* y, int N, int H, int C, void* dx, void* stream);
+/* z[n,2h,2w,:] = dy[n,h,w,:], zero elsewhere (transpose of stride-2 sampling) */
+int xmc_zero_insert2(const void* dy, int N, int H, int W, int C, void* z, void* stream);
 
 #ifdef __cplusplus
 }

@@ -699,3 +699,150 @@ def make_state(g_vars, d_vars):
       "generator_state": g_vars, "discriminator_state": d_vars,
       "ema_params": tree_map(lambda t: t.clone(), g_params),
   }
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# frozen ResNet-50 feature branch: utils/resnet_v1.py, utils/pretrained_model_utils.py, xmc_gan.py:74-90
+# ----------------------------------------------------------------------------------------------------------------------
+RESNET50_STAGES = [3, 4, 6, 3]  # resnet_v1.py:179-180
+
+
+def _same_pads(n, k, s):
+  """XLA 'SAME': total = max((ceil(n/s)-1)*s + k - n, 0), low = total // 2, high = total - low."""
+  out = -(-n // s)
+  total = max((out - 1) * s + k - n, 0)
+  return total // 2, total - total // 2
+
+
+def _conv_same(x, kernel, stride, policy, scale=None):
+  """flax nn.Conv(use_bias=False, strides, padding='SAME') on NHWC / HWIO. `scale`: per-output-channel factor folded
+  into the kernel before the cast (B200 path: eval BatchNorm folded into the bf16 weights)."""
+  kh, kw = kernel.shape[0], kernel.shape[1]
+  w = kernel if scale is None else kernel * scale
+  pt, pb = _same_pads(x.shape[1], kh, stride)
+  pl, pr = _same_pads(x.shape[2], kw, stride)
+  xp = F.pad(policy.q(x).permute(0, 3, 1, 2), (pl, pr, pt, pb))
+  return F.conv2d(xp, policy.q(w).permute(3, 2, 0, 1), stride=stride).permute(0, 2, 3, 1)
+
+
+def _bn_eval_affine(p, st, eps=1e-5):
+  """flax nn.BatchNorm(use_running_average=True) as y = x*s + b."""
+  s = p["scale"] * torch.rsqrt(st["var"] + eps)
+  return s, p["bias"] - st["mean"] * s
+
+
+def _conv_bn(x, params, stats, conv, bn, stride, policy, relu, residual=None):
+  s, b = _bn_eval_affine(params[bn], stats[bn])
+  if policy.dtype == "float32":
+    y = _conv_same(x, params[conv]["kernel"], stride, policy) * s + b
+  else:
+    y = _conv_same(x, params[conv]["kernel"], stride, policy, scale=s) + b
+  if residual is not None:
+    y = y + residual
+  if relu:
+    y = F.relu(y)
+  return policy.q(y)
+
+
+def resnet50_apply(variables, x, policy=FP32):
+  """resnet_v1.ResNet.__call__ (resnet_v1.py:129-172), train=False, BottleneckResNetBlock (:60-86).
+  Note: no ReLU after init_bn (:146-154); the stride sits on the 3x3 conv (:79). Returns (pool, logits)."""
+  P, S = variables["params"], variables["batch_stats"]
+  x = _conv_bn(x, P, S, "init_conv", "init_bn", 2, policy, relu=False)
+  pt, pb = _same_pads(x.shape[1], 3, 2)
+  xp = F.pad(x.permute(0, 3, 1, 2), (pt, pb, pt, pb), value=float("-inf"))
+  x = F.max_pool2d(xp, 3, 2).permute(0, 2, 3, 1)
+  for si, nblocks in enumerate(RESNET50_STAGES):
+    for bi in range(nblocks):
+      p, s = P[f"stage{si + 1}"][f"block{bi + 1}"], S[f"stage{si + 1}"][f"block{bi + 1}"]
+      stride = 2 if (si > 0 and bi == 0) else 1
+      residual = x
+      y = _conv_bn(x, p, s, "conv1", "bn1", 1, policy, relu=True)
+      y = _conv_bn(y, p, s, "conv2", "bn2", stride, policy, relu=True)
+      if "proj_conv" in p:
+        residual = _conv_bn(x, p, s, "proj_conv", "proj_bn", stride, policy, relu=False)
+      x = _conv_bn(y, p, s, "conv3", "bn3", 1, policy, relu=True, residual=residual)
+  pool = x
+  feat = pool.float().mean(dim=(1, 2))
+  logits = policy.q(feat) @ policy.q(P["head"]["kernel"]) + P["head"]["bias"]
+  return pool, logits
+
+
+def get_pretrained_embs(variables, images, policy=FP32, size=224):
+  """pretrained_model_utils.get_pretrained_embs (pretrained_model_utils.py:102-127): bilinear resize to 224 (half-pixel
+  centres; identical to torch align_corners=False when up-sampling), then the frozen network."""
+  if images.dim() != 4 or images.shape[3] != 3:
+    raise ValueError("images should be of shape (H, W, 3).")
+  if images.shape[1] != size and images.shape[2] != size:
+    images = F.interpolate(images.permute(0, 3, 1, 2), size=(size, size), mode="bilinear",
+                           align_corners=False).permute(0, 2, 3, 1)
+  return resnet50_apply(variables, images, policy)
+
+
+def calculate_contrastive_loss_on_pretrained(variables, real_images, fake_images, policy=FP32):
+  """xmc_gan.calculate_contrastive_loss_on_pretrained (xmc_gan.py:74-90)."""
+  _, real_outputs = get_pretrained_embs(variables, real_images, policy)
+  _, fake_outputs = get_pretrained_embs(variables, fake_images, policy)
+  loss, _, _ = contrastive_loss(real_outputs, fake_outputs)
+  return loss
+
+
+def resnet50_param_shapes(num_classes=1000, width=64):
+  """Variable tree shapes of resnet_v1.ResNet50 (names as in resnet_v1.py); 25 557 032 parameters."""
+  params, stats = {}, {}
+
+  def bn(c):
+    return {"scale": (c,), "bias": (c,)}, {"mean": (c,), "var": (c,)}
+
+  params["init_conv"] = {"kernel": (7, 7, 3, width)}
+  params["init_bn"], stats["init_bn"] = bn(width)
+  cin = width
+  for si, nblocks in enumerate(RESNET50_STAGES):
+    f = width * 2 ** si
+    sp, ss = {}, {}
+    for bi in range(nblocks):
+      p, s = {}, {}
+      p["conv1"] = {"kernel": (1, 1, cin, f)}
+      p["bn1"], s["bn1"] = bn(f)
+      p["conv2"] = {"kernel": (3, 3, f, f)}
+      p["bn2"], s["bn2"] = bn(f)
+      p["conv3"] = {"kernel": (1, 1, f, 4 * f)}
+      p["bn3"], s["bn3"] = bn(4 * f)
+      if cin != 4 * f or (si > 0 and bi == 0):
+        p["proj_conv"] = {"kernel": (1, 1, cin, 4 * f)}
+        p["proj_bn"], s["proj_bn"] = bn(4 * f)
+      sp[f"block{bi + 1}"], ss[f"block{bi + 1}"] = p, s
+      cin = 4 * f
+    params[f"stage{si + 1}"], stats[f"stage{si + 1}"] = sp, ss
+  params["head"] = {"kernel": (cin, num_classes), "bias": (num_classes,)}
+  return params, stats
+
+
+def resnet50_random_variables(seed=0, head_scale=0.05):
+  """Synthetic frozen weights (the reference's data/resnet_pretrained.npy is not shipped, README.md:60-63): He-normal
+  kernels, BatchNorm scale ~ 1, small random bias / mean, var ~ 1, and a NON-zero head (the reference initialises the
+  head to zeros, resnet_v1.py:171, which would make the loss the constant 2 log B)."""
+  g = torch.Generator().manual_seed(seed)
+  pshapes, sshapes = resnet50_param_shapes()
+
+  def fill(tree, path=()):
+    out = {}
+    for k, v in tree.items():
+      if isinstance(v, dict):
+        out[k] = fill(v, path + (k,))
+      else:
+        shape = v
+        if k == "kernel" and len(shape) == 4:
+          fan_in = shape[0] * shape[1] * shape[2]
+          out[k] = torch.randn(shape, generator=g) * math.sqrt(2.0 / fan_in)
+        elif k == "kernel":
+          out[k] = torch.randn(shape, generator=g) * head_scale
+        elif k == "scale":
+          out[k] = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        elif k == "var":
+          out[k] = 1.0 + 0.2 * torch.rand(shape, generator=g)
+        else:  # bias, mean
+          out[k] = 0.1 * torch.randn(shape, generator=g)
+    return out
+
+  return {"params": fill(pshapes), "batch_stats": fill(sshapes)}

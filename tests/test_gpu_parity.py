@@ -368,3 +368,64 @@ def test_train_step_runs_at_baseline_width_and_decreases_nothing_to_nan():
   assert all(torch.isfinite(torch.tensor(v)) for v in m.values())
   assert not torch.equal(ema0, state.ema_params.buf)
   assert torch.isfinite(state.g_optimizer.target.buf).all() and torch.isfinite(state.d_optimizer.target.buf).all()
+
+
+@gpu
+def test_frozen_resnet50_branch_matches_oracle():
+  """calculate_contrastive_loss_on_pretrained (xmc_gan.py:74-90): logits of the frozen ResNet-50 on bilinearly
+  resized images vs the oracle (bf16 policy) 2e-2 rel-L2; loss 2e-3; gradient wrt the fake images vs oracle autograd
+  cosine > 0.98 / rel-L2 < 0.2 (bf16 activation gradients through 50 layers)."""
+  _, engine, ops, _, xmc_gan, _ = _mods()
+  torch.manual_seed(3)
+  variables = orc.resnet50_random_variables(1)
+  model = engine.ResNetEngine()
+  model.load(variables)
+  B, S = 3, 128
+  real = torch.rand(B, S, S, 3)
+  fake = torch.rand(B, S, S, 3)
+  both = torch.cat([real, fake]).cuda()
+  logits, rctx = model.forward(both)
+  pol = orc.Policy("bfloat16")
+  _, want = orc.get_pretrained_embs(variables, torch.cat([real, fake]), pol)
+  assert logits.shape == (2 * B, 1000)
+  assert helpers.rel(logits, want) < 2e-2
+  slot = ops.empty(1, torch.float32)
+  c = engine.Contrastive(logits[:B], logits[B:], slot)
+  fk = fake.clone().requires_grad_(True)
+  loss = orc.calculate_contrastive_loss_on_pretrained(variables, real, fk, pol)
+  loss.backward()
+  assert abs(slot.item() - loss.item()) < 2e-3 * abs(loss.item())
+  dl = ops.empty((B, 1000), torch.float32)
+  c.bwd_b(dl, accumulate=False)
+  d_fake = torch.zeros(B, S, S, 3, device="cuda")
+  model.backward(rctx, dl, B, d_fake)
+  g, r = d_fake.cpu().reshape(-1), fk.grad.reshape(-1)
+  cos = torch.nn.functional.cosine_similarity(g, r, dim=0).item()
+  assert cos > 0.98 and helpers.rel(g, r) < 0.2, (cos, helpers.rel(g, r))
+
+
+@gpu
+def test_train_step_with_pretrained_image_contrastive():
+  """The reference's default configuration (pretrained_image_contrastive=True) through train_step vs the oracle."""
+  _, engine, ops, train_utils, xmc_gan, xmc_net = _mods()
+  cfg = helpers.small_config(pretrained_image_contrastive=True)
+  B = 3
+  variables = orc.resnet50_random_variables(2)
+  g_vars, d_vars, g_params, g_stats, d_params, d_u = _build(cfg, seed=8)
+  batch = helpers.make_batch(2 * B, cfg, seed=9)
+  ostate = orc.make_state(g_vars, d_vars)
+  state = train_utils.TrainState(0, train_utils.Optimizer(g_params, cfg.g_lr, cfg.beta1, cfg.beta2),
+                                 train_utils.Optimizer(d_params, cfg.d_lr, cfg.beta1, cfg.beta2),
+                                 {"batch_stats": g_stats}, {"spectral_norm_stats": d_u}, g_params.clone())
+  additional = xmc_gan.create_additional_data(cfg, variables=variables)
+  pol = orc.Policy("bfloat16")
+  pre = lambda real, fake: orc.calculate_contrastive_loss_on_pretrained(variables, real, fake, pol)
+  state, metrics = train_utils.train_step(None, state, batch, xmc_gan, None, None, cfg, additional)
+  got = metrics.compute()
+  ostate, want = orc.train_step(ostate, batch, cfg, pol, pretrained_fn=pre)
+  scale = max(abs(v) for v in want.values())
+  for k in ("d_loss", "g_loss", "c_loss_d", "c_loss_g", "c_loss_g_pretrained"):
+    assert abs(got[k] - want[k]) < 5e-3 * scale, (k, got[k], want[k])
+  assert got["c_loss_g_pretrained"] > 0
+  for (p, a), (_, b) in zip(orc.tree_leaves(state.g_optimizer.target.to_cpu_tree()), orc.tree_leaves(ostate["g_params"])):
+    assert helpers.rel(a, b) < 5e-3, (p, helpers.rel(a, b))

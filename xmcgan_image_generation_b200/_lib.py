@@ -31,6 +31,9 @@ class ConvDesc(ctypes.Structure):
       ("relu", ctypes.c_int),
       ("res_shift", ctypes.c_int),
       ("ldRes", ctypes.c_int), ("ldMask", ctypes.c_int),
+      ("strideH", ctypes.c_int), ("strideW", ctypes.c_int), ("Hin", ctypes.c_int), ("Win", ctypes.c_int),
+      ("pitchW", ctypes.c_longlong), ("pitchH", ctypes.c_longlong), ("pitchN", ctypes.c_longlong),
+      ("mask_last", ctypes.c_int),
   ]
 
 
@@ -64,6 +67,7 @@ class PrepEntry(ctypes.Structure):
       ("taps", ctypes.c_int), ("cin", ctypes.c_int), ("cout", ctypes.c_int),
       ("ld_fwd", ctypes.c_int), ("ld_dg", ctypes.c_int),
       ("sn", ctypes.c_int), ("tile_begin", ctypes.c_int), ("reserved", ctypes.c_int),
+      ("cscale_off", ctypes.c_longlong),
   ]
 
 

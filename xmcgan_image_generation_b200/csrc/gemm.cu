@@ -31,6 +31,7 @@ struct FwdParams {
   int KH, KW, pad_h, pad_w, C, cchunks;
   int N, H, W, Cout;
   int batched;
+  int strideH, strideW;
   uint32_t stage_tx_bytes;
   uint32_t idesc;
   void* out;
@@ -38,7 +39,7 @@ struct FwdParams {
   const float* bias;
   const bf16* residual;
   const bf16* mask;
-  int ldRes, ldMask, res_shift, relu;
+  int ldRes, ldMask, res_shift, relu, mask_last;
   float alpha;
   int vec_ok;
 };
@@ -134,7 +135,8 @@ gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             mbar_wait(empty_bar(stage), phase ^ 1);
             mbar_arrive_expect_tx(full_bar(stage), p.stage_tx_bytes);
             const uint32_t sa = sbase + stage * kStageBytes;
-            tma_load_4d(sa, &tmA, full_bar(stage), c * 64, w0 + kw - p.pad_w, h0 + kh - p.pad_h, n0);
+            tma_load_4d(sa, &tmA, full_bar(stage), c * 64, w0 * p.strideW + kw - p.pad_w,
+                        h0 * p.strideH + kh - p.pad_h, n0);
             tma_load_3d(sa + kABytes, &tmB, full_bar(stage), tap * p.C + c * 64, nt * p.BN, p.batched ? n0 : 0);
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
@@ -235,6 +237,14 @@ gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               f[4 * i] += bz[i].x; f[4 * i + 1] += bz[i].y; f[4 * i + 2] += bz[i].z; f[4 * i + 3] += bz[i].w;
             }
           }
+          if (p.residual && p.mask_last) {
+            const uint32_t rw_[8] = {rs[0].x, rs[0].y, rs[0].z, rs[0].w, rs[1].x, rs[1].y, rs[1].z, rs[1].w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              f[2 * i] += bf16_bits_to_float(rw_[i] & 0xFFFFu);
+              f[2 * i + 1] += bf16_bits_to_float(rw_[i] >> 16);
+            }
+          }
           if (p.mask) {
             const uint32_t mw[8] = {mk[0].x, mk[0].y, mk[0].z, mk[0].w, mk[1].x, mk[1].y, mk[1].z, mk[1].w};
 #pragma unroll
@@ -245,7 +255,7 @@ gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               if (!(hi != 0 && hi < 0x8000u)) f[2 * i + 1] = 0.f;
             }
           }
-          if (p.residual) {
+          if (p.residual && !p.mask_last) {
             const uint32_t rw_[8] = {rs[0].x, rs[0].y, rs[0].z, rs[0].w, rs[1].x, rs[1].y, rs[1].z, rs[1].w};
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -282,8 +292,9 @@ gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int i = 0; i < 16; ++i) {
               if (i < nvalid) {
                 if (p.bias) f[i] += p.bias[col + i];
+                if (p.residual && p.mask_last) f[i] += __bfloat162float(p.residual[rpix * p.ldRes + col + i]);
                 if (p.mask && !(__bfloat162float(p.mask[pix * p.ldMask + col + i]) > 0.f)) f[i] = 0.f;
-                if (p.residual) f[i] += __bfloat162float(p.residual[rpix * p.ldRes + col + i]);
+                if (p.residual && !p.mask_last) f[i] += __bfloat162float(p.residual[rpix * p.ldRes + col + i]);
                 if (p.relu) f[i] = fmaxf(f[i], 0.f);
                 if (p.out_dtype == 0) reinterpret_cast<bf16*>(p.out)[pix * p.ldOut + col + i] = __float2bfloat16(f[i]);
                 else reinterpret_cast<float*>(p.out)[pix * p.ldOut + col + i] = f[i];
@@ -534,7 +545,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 
 // bf16 tensor map, SWIZZLE_128B, zero OOB fill. dims/box innermost first; strides in bytes for dims 1..rank-1.
 static int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
-                     const uint32_t* box) {
+                     const uint32_t* box, const uint32_t* estrides = nullptr) {
   PFN_cuTensorMapEncodeTiled_v12000 fn = get_encode_fn();
   if (!fn) return XMC_ECUDA;
   cuuint64_t gdim[5], gstr[5];
@@ -542,7 +553,7 @@ static int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bx[i] = box[i];
-    es[i] = 1;
+    es[i] = estrides ? estrides[i] : 1;
   }
   for (int i = 0; i < rank - 1; ++i) gstr[i] = strides[i];
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, es,
@@ -576,7 +587,8 @@ extern "C" int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* w
                               const void* residual, const void* mask, void* y, void* stream) {
   if (!d || !x || !wk || !y) return XMC_EINVAL;
   if (d->N < 1 || d->H < 1 || d->W < 1 || d->C < 1 || d->Cout < 1 || d->KH < 1 || d->KW < 1) return XMC_EINVAL;
-  if ((d->ldA % 8) || (d->ldB % 8) || d->ldA < d->C || d->ldB < d->KH * d->KW * d->C) return XMC_EINVAL;
+  if ((d->ldA % 8) || (d->ldB % 8) || d->ldB < d->KH * d->KW * d->C) return XMC_EINVAL;
+  if (d->pitchW <= 0 && d->ldA < d->C) return XMC_EINVAL;
   if (d->C % 8) return XMC_EINVAL;
   if (!aligned16(x) || !aligned16(wk)) return XMC_EALIGN;
   if (d->batched && (d->strideB_batch % 8)) return XMC_EINVAL;
@@ -587,6 +599,9 @@ extern "C" int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* w
   p.KH = d->KH; p.KW = d->KW; p.pad_h = d->pad_h; p.pad_w = d->pad_w;
   p.cchunks = ceil_div(d->C, 64);
   p.batched = d->batched;
+  p.strideH = d->strideH > 0 ? d->strideH : 1;
+  p.strideW = d->strideW > 0 ? d->strideW : 1;
+  if (p.strideH > 8 || p.strideW > 8) return XMC_EINVAL;
   p.tw = d->W < 128 ? d->W : 128;
   p.th = 128 / p.tw; if (p.th > d->H) p.th = d->H;
   p.tn = d->batched ? 1 : 128 / (p.tw * p.th); if (p.tn > d->N) p.tn = d->N; if (p.tn < 1) p.tn = 1;
@@ -600,6 +615,7 @@ extern "C" int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* w
   p.out = y; p.out_dtype = d->out_dtype; p.ldOut = d->ldOut;
   p.bias = bias; p.residual = (const bf16*)residual; p.mask = (const bf16*)mask;
   p.ldRes = d->ldRes; p.ldMask = d->ldMask; p.res_shift = d->res_shift; p.relu = d->relu;
+  p.mask_last = d->mask_last;
   p.alpha = d->alpha;
   bool vec = aligned16(y) && (d->out_dtype == 0 ? (d->ldOut % 8 == 0) : (d->ldOut % 4 == 0));
   if (residual) vec = vec && aligned16(residual) && (d->ldRes % 8 == 0);
@@ -608,10 +624,18 @@ extern "C" int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* w
 
   CUtensorMap tmA, tmB;
   {
-    uint64_t dims[4] = {(uint64_t)d->C, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
-    uint64_t str[3] = {(uint64_t)d->ldA * 2, (uint64_t)d->ldA * 2 * d->W, (uint64_t)d->ldA * 2 * d->W * d->H};
-    uint32_t box[4] = {64, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.tn};
-    int r = make_tmap(&tmA, x, 4, dims, str, box);
+    const int Hin = d->Hin > 0 ? d->Hin : d->H * p.strideH;
+    const int Win = d->Win > 0 ? d->Win : d->W * p.strideW;
+    const uint64_t pW = d->pitchW > 0 ? (uint64_t)d->pitchW : (uint64_t)d->ldA;
+    const uint64_t pH = d->pitchH > 0 ? (uint64_t)d->pitchH : pW * Win;
+    const uint64_t pN = d->pitchN > 0 ? (uint64_t)d->pitchN : pH * Hin;
+    if ((pW % 8) || (pH % 8) || (pN % 8)) return XMC_EINVAL;
+    if (p.tw * p.strideW > 256 || p.th * p.strideH > 256) return XMC_EINVAL;
+    uint64_t dims[4] = {(uint64_t)d->C, (uint64_t)Win, (uint64_t)Hin, (uint64_t)d->N};
+    uint64_t str[3] = {pW * 2, pH * 2, pN * 2};
+    uint32_t box[4] = {64, (uint32_t)(p.tw * p.strideW), (uint32_t)(p.th * p.strideH), (uint32_t)p.tn};
+    uint32_t est[4] = {1, (uint32_t)p.strideW, (uint32_t)p.strideH, 1};
+    int r = make_tmap(&tmA, x, 4, dims, str, box, est);
     if (r) return r;
   }
   {

@@ -1,0 +1,268 @@
+// Kernels that only the frozen ResNet-50 feature branch needs (xmcgan/xmc_gan.py:74-90, xmcgan/utils/resnet_v1.py,
+// xmcgan/utils/pretrained_model_utils.py:102-127): bilinear resize 128->224 (+ transpose), the 7x7/2 stem's input
+// gradient, 3x3/2 max-pool (+ transpose) and zero insertion (transpose of a stride-2 sampling). All convolutions of
+// the network itself run on the tcgen05 implicit-GEMM kernel (gemm.cu) with eval-mode BatchNorm folded into weights.
+#include "common.h"
+#include "devutil.cuh"
+
+namespace xmc {
+
+// jax.image.resize(..., "bilinear") when up-sampling: half-pixel centres, 2-tap triangle weights, renormalised at the
+// borders (== index clamping). Writes a zero-bordered, 8-channel bf16 buffer [N, Tp, Tp, 8] (image at offset pad_lo)
+// so that the stride-2 7x7 stem can read (kw, c) as one contiguous 56-element run per output pixel.
+__global__ void resize_bilinear_pad_kernel(const float* __restrict__ img, int N, int S, int T, int Tp, int pad_lo,
+                                           bf16* __restrict__ out) {
+  const long long total = (long long)N * Tp * Tp;
+  const float scale = (float)S / (float)T;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int xp = idx % Tp, yp = (idx / Tp) % Tp;
+    const long long n = idx / ((long long)Tp * Tp);
+    const int x = xp - pad_lo, y = yp - pad_lo;
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = 0.f;
+    if (x >= 0 && x < T && y >= 0 && y < T) {
+      const float sx = (x + 0.5f) * scale - 0.5f, sy = (y + 0.5f) * scale - 0.5f;
+      const float fx0 = floorf(sx), fy0 = floorf(sy);
+      const float wx = sx - fx0, wy = sy - fy0;
+      const int x0 = max(0, min(S - 1, (int)fx0)), x1 = max(0, min(S - 1, (int)fx0 + 1));
+      const int y0 = max(0, min(S - 1, (int)fy0)), y1 = max(0, min(S - 1, (int)fy0 + 1));
+      const float* b = img + n * S * S * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float v00 = b[(y0 * S + x0) * 3 + c], v01 = b[(y0 * S + x1) * 3 + c];
+        const float v10 = b[(y1 * S + x0) * 3 + c], v11 = b[(y1 * S + x1) * 3 + c];
+        o[c] = (1.f - wy) * ((1.f - wx) * v00 + wx * v01) + wy * ((1.f - wx) * v10 + wx * v11);
+      }
+    }
+    store8(out + idx * 8, o);
+  }
+}
+
+// transpose of the resize: dimg[n, src] += w * dout[n, dst]
+__global__ void resize_bilinear_bwd_kernel(const float* __restrict__ dout, int N, int S, int T,
+                                           float* __restrict__ dimg) {
+  const long long total = (long long)N * T * T;
+  const float scale = (float)S / (float)T;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int x = idx % T, y = (idx / T) % T;
+    const long long n = idx / ((long long)T * T);
+    const float sx = (x + 0.5f) * scale - 0.5f, sy = (y + 0.5f) * scale - 0.5f;
+    const float fx0 = floorf(sx), fy0 = floorf(sy);
+    const float wx = sx - fx0, wy = sy - fy0;
+    const int x0 = max(0, min(S - 1, (int)fx0)), x1 = max(0, min(S - 1, (int)fx0 + 1));
+    const int y0 = max(0, min(S - 1, (int)fy0)), y1 = max(0, min(S - 1, (int)fy0 + 1));
+    float* b = dimg + n * S * S * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float g = dout[idx * 3 + c];
+      atomicAdd(b + (y0 * S + x0) * 3 + c, (1.f - wy) * (1.f - wx) * g);
+      atomicAdd(b + (y0 * S + x1) * 3 + c, (1.f - wy) * wx * g);
+      atomicAdd(b + (y1 * S + x0) * 3 + c, wy * (1.f - wx) * g);
+      atomicAdd(b + (y1 * S + x1) * 3 + c, wy * wx * g);
+    }
+  }
+}
+
+// Input gradient of the 7x7 stride-2 stem (SAME padding low=2): one thread per input pixel.
+// wk: bf16 [Cout][7*56] with k = kh*56 + kw*8 + c (the packed forward weights), dy: bf16 [N,Ho,Wo,Cout].
+__global__ void stem_dgrad_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ wk, int N, int T, int Ho,
+                                  int Cout, int pad_lo, float* __restrict__ dimg) {
+  extern __shared__ float ws[];  // [7][7][3][Cout]
+  for (int t = threadIdx.x; t < 49 * 3 * Cout; t += blockDim.x) {
+    const int co = t % Cout, c = (t / Cout) % 3, kw = (t / (Cout * 3)) % 7, kh = t / (Cout * 21);
+    ws[t] = __bfloat162float(wk[(long long)co * 392 + kh * 56 + kw * 8 + c]);
+  }
+  __syncthreads();
+  const long long total = (long long)N * T * T;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int x = idx % T, y = (idx / T) % T;
+  const long long n = idx / ((long long)T * T);
+  const int yp = y + pad_lo, xp = x + pad_lo;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (int ho = max(0, (yp - 5) >> 1); ho <= min(Ho - 1, yp >> 1); ++ho) {
+    const int kh = yp - 2 * ho;
+    if (kh < 0 || kh > 6) continue;
+    for (int wo = max(0, (xp - 5) >> 1); wo <= min(Ho - 1, xp >> 1); ++wo) {
+      const int kw = xp - 2 * wo;
+      if (kw < 0 || kw > 6) continue;
+      const bf16* g = dy + ((n * Ho + ho) * Ho + wo) * Cout;
+      const float* w = ws + ((kh * 7 + kw) * 3) * Cout;
+      for (int co = 0; co < Cout; co += 8) {
+        float f[8];
+        load8(g + co, f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          a0 += f[i] * w[co + i];
+          a1 += f[i] * w[Cout + co + i];
+          a2 += f[i] * w[2 * Cout + co + i];
+        }
+      }
+    }
+  }
+  float* o = dimg + idx * 3;
+  o[0] = a0; o[1] = a1; o[2] = a2;
+}
+
+// flax nn.max_pool(x, (3,3), strides=(2,2), padding="SAME") on an even-sized map: window rows 2ho..2ho+2 (pad high)
+__global__ void maxpool3s2_kernel(const bf16* __restrict__ x, int N, int H, int C, bf16* __restrict__ y) {
+  const int Ho = H / 2, cv = C >> 3;
+  const long long total = (long long)N * Ho * Ho * cv;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int v = idx % cv;
+    long long pix = idx / cv;
+    const int wo = pix % Ho, ho = (pix / Ho) % Ho;
+    const long long n = pix / ((long long)Ho * Ho);
+    float m[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] = -3.0e38f;
+    for (int kh = 0; kh < 3; ++kh) {
+      const int h = 2 * ho + kh;
+      if (h >= H) continue;
+      for (int kw = 0; kw < 3; ++kw) {
+        const int w = 2 * wo + kw;
+        if (w >= H) continue;
+        float f[8];
+        load8(x + ((n * H + h) * H + w) * C + v * 8, f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], f[i]);
+      }
+    }
+    store8(y + pix * C + v * 8, m);
+  }
+}
+
+// transpose: the gradient of a window goes to its FIRST maximal element in row-major window order
+// (XLA select_and_scatter with a >= selector)
+__global__ void maxpool3s2_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                      const bf16* __restrict__ y, int N, int H, int C, bf16* __restrict__ dx) {
+  const int Ho = H / 2, cv = C >> 3;
+  const long long total = (long long)N * H * H * cv;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int v = idx % cv;
+    long long pix = idx / cv;
+    const int w = pix % H, h = (pix / H) % H;
+    const long long n = pix / ((long long)H * H);
+    const int c = v * 8;
+    float xv[8], acc[8];
+    load8(x + pix * C + c, xv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int ho = max(0, (h - 1) >> 1); ho <= min(Ho - 1, h >> 1); ++ho) {
+      for (int wo = max(0, (w - 1) >> 1); wo <= min(Ho - 1, w >> 1); ++wo) {
+        if (2 * ho > h || 2 * ho + 2 < h || 2 * wo > w || 2 * wo + 2 < w) continue;
+        float yv[8], g[8];
+        load8(y + ((n * Ho + ho) * Ho + wo) * C + c, yv);
+        load8(dy + ((n * Ho + ho) * Ho + wo) * C + c, g);
+        bool first[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) first[i] = (xv[i] == yv[i]);
+        // an earlier window element with the same (maximal) value takes the gradient instead
+        for (int kh = 0; kh < 3; ++kh)
+          for (int kw = 0; kw < 3; ++kw) {
+            const int hh = 2 * ho + kh, ww = 2 * wo + kw;
+            if (hh >= H || ww >= H) continue;
+            if (hh > h || (hh == h && ww >= w)) continue;
+            float e[8];
+            load8(x + ((n * H + hh) * H + ww) * C + c, e);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (e[i] == yv[i]) first[i] = false;
+          }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (first[i]) acc[i] += g[i];
+      }
+    }
+    store8(dx + pix * C + c, acc);
+  }
+}
+
+// z[n,2h,2w,:] = dy[n,h,w,:], zero elsewhere (transpose of stride-2 sampling)
+__global__ void zero_insert2_kernel(const bf16* __restrict__ dy, int N, int H, int W, int C, bf16* __restrict__ z) {
+  const int cv = C >> 3;
+  const long long total = (long long)N * H * W * cv;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int v = idx % cv;
+    long long pix = idx / cv;
+    const int w = pix % W, h = (pix / W) % H;
+    const long long n = pix / ((long long)W * H);
+    const uint4 val = *reinterpret_cast<const uint4*>(dy + pix * C + v * 8);
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    const int W2 = 2 * W;
+    const long long base = ((n * 2 * H + 2 * h) * W2 + 2 * w) * C + v * 8;
+    *reinterpret_cast<uint4*>(z + base) = val;
+    *reinterpret_cast<uint4*>(z + base + C) = zero;
+    *reinterpret_cast<uint4*>(z + base + (long long)W2 * C) = zero;
+    *reinterpret_cast<uint4*>(z + base + (long long)W2 * C + C) = zero;
+  }
+}
+
+static int grid1(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = (long long)num_sms() * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace xmc
+
+using namespace xmc;
+
+extern "C" int xmc_resize_bilinear_pad(const float* img, int N, int S, int T, int Tp, int pad_lo, void* out,
+                                       void* stream) {
+  if (!img || !out || N < 1 || S < 1 || T < S || Tp < T + pad_lo) return XMC_EINVAL;
+  resize_bilinear_pad_kernel<<<grid1((long long)N * Tp * Tp, 256), 256, 0, (cudaStream_t)stream>>>(img, N, S, T, Tp,
+                                                                                                   pad_lo, (bf16*)out);
+  XMC_LAUNCH_CHECK();
+  return XMC_OK;
+}
+
+extern "C" int xmc_resize_bilinear_bwd(const float* dout, int N, int S, int T, float* dimg, void* stream) {
+  if (!dout || !dimg || N < 1 || S < 1 || T < S) return XMC_EINVAL;
+  resize_bilinear_bwd_kernel<<<grid1((long long)N * T * T, 256), 256, 0, (cudaStream_t)stream>>>(dout, N, S, T, dimg);
+  XMC_LAUNCH_CHECK();
+  return XMC_OK;
+}
+
+extern "C" int xmc_stem_dgrad(const void* dy, const void* wk, int N, int T, int Ho, int Cout, int pad_lo, float* dimg,
+                              void* stream) {
+  if (!dy || !wk || !dimg || N < 1 || Cout < 8 || (Cout % 8)) return XMC_EINVAL;
+  const size_t smem = (size_t)49 * 3 * Cout * sizeof(float);
+  if (smem > 48 * 1024) return XMC_EINVAL;
+  const long long total = (long long)N * T * T;
+  stem_dgrad_kernel<<<(unsigned)ceil_div_ll(total, 128), 128, smem, (cudaStream_t)stream>>>(
+      (const bf16*)dy, (const bf16*)wk, N, T, Ho, Cout, pad_lo, dimg);
+  XMC_LAUNCH_CHECK();
+  return XMC_OK;
+}
+
+extern "C" int xmc_maxpool3s2(const void* x, int N, int H, int C, void* y, void* stream) {
+  if (!x || !y || N < 1 || H < 2 || (H % 2) || C < 8 || (C % 8)) return XMC_EINVAL;
+  maxpool3s2_kernel<<<grid1((long long)N * (H / 2) * (H / 2) * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, N, H, C, (bf16*)y);
+  XMC_LAUNCH_CHECK();
+  return XMC_OK;
+}
+
+extern "C" int xmc_maxpool3s2_bwd(const void* dy, const void* x, const void* y, int N, int H, int C, void* dx,
+                                  void* stream) {
+  if (!dy || !x || !y || !dx || N < 1 || H < 2 || (H % 2) || C < 8 || (C % 8)) return XMC_EINVAL;
+  maxpool3s2_bwd_kernel<<<grid1((long long)N * H * H * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)dy, (const bf16*)x, (const bf16*)y, N, H, C, (bf16*)dx);
+  XMC_LAUNCH_CHECK();
+  return XMC_OK;
+}
+
+extern "C" int xmc_zero_insert2(const void* dy, int N, int H, int W, int C, void* z, void* stream) {
+  if (!dy || !z || N < 1 || H < 1 || W < 1 || C < 8 || (C % 8)) return XMC_EINVAL;
+  zero_insert2_kernel<<<grid1((long long)N * H * W * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)dy, N,
+                                                                                                   H, W, C, (bf16*)z);
+  XMC_LAUNCH_CHECK();
+  return XMC_OK;
+}

@@ -134,7 +134,7 @@ __global__ void sn_bwd_apply_kernel(const XmcSnEntry* __restrict__ tab, int n, f
 // ------------------------------------------------------------------------------------------------- weight prep
 __global__ void prep_weights_kernel(const XmcPrepEntry* __restrict__ tab, int n, const float* __restrict__ params,
                                     const float* __restrict__ sn_scalars, int n_sn, bf16* __restrict__ arena,
-                                    float* __restrict__ bias_arena) {
+                                    float* __restrict__ bias_arena, const float* __restrict__ cscale) {
   __shared__ float tile[32][33];
   const int e = find_entry(tab, n, (int)blockIdx.x, &XmcPrepEntry::tile_begin);
   const XmcPrepEntry en = tab[e];
@@ -149,6 +149,7 @@ __global__ void prep_weights_kernel(const XmcPrepEntry* __restrict__ tab, int n,
     float v = 0.f;
     if (k < K && c < en.cout) {
       v = params[en.w_off + (long long)k * en.cout + c] * scale;
+      if (en.cscale_off >= 0) v *= cscale[en.cscale_off + c];
       if (en.wk_dg_off >= 0) {
         const int tap = k / en.cin, ci = k - tap * en.cin;
         arena[en.wk_dg_off + (long long)ci * en.ld_dg + (long long)(en.taps - 1 - tap) * en.cout + c] =
@@ -238,10 +239,11 @@ extern "C" int xmc_sn_backward(const XmcSnEntry* table_dev, int n, const float* 
 }
 
 extern "C" int xmc_prep_weights(const XmcPrepEntry* table_dev, int n, int total_tiles, const float* params,
-                                const float* sn_scalars, int n_sn, void* arena, float* bias_arena, void* stream) {
+                                const float* sn_scalars, int n_sn, void* arena, float* bias_arena,
+                                const float* cscale, void* stream) {
   if (!table_dev || n < 1 || total_tiles < 1 || !params || !arena) return XMC_EINVAL;
   prep_weights_kernel<<<total_tiles, dim3(32, 8), 0, (cudaStream_t)stream>>>(table_dev, n, params, sn_scalars, n_sn,
-                                                                            (bf16*)arena, bias_arena);
+                                                                            (bf16*)arena, bias_arena, cscale);
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }

@@ -111,10 +111,11 @@ class _PrepTable:
     self.entries = []
     self.tiles = 0
 
-  def add(self, w_off, taps, cin, cout, fwd_off, ld_fwd, dg_off, ld_dg, sn):
+  def add(self, w_off, taps, cin, cout, fwd_off, ld_fwd, dg_off, ld_dg, sn, cscale_off=-1):
     e = _lib.PrepEntry()
     e.w_off, e.wk_fwd_off, e.wk_dg_off = w_off, fwd_off, dg_off
     e.bias_off = e.bias_dst_off = -1
+    e.cscale_off = cscale_off
     e.taps, e.cin, e.cout = taps, cin, cout
     e.ld_fwd, e.ld_dg, e.sn = ld_fwd, ld_dg, sn
     e.tile_begin = self.tiles
@@ -271,7 +272,7 @@ class GeneratorEngine:
   def prep_weights(self, params):
     self._ensure()
     ops._call("xmc_prep_weights", self.prep.dev.data_ptr(), self.prep.n, self.prep.tiles, params.data_ptr(), None, 0,
-              self.arena.data_ptr(), None, _lib.stream())
+              self.arena.data_ptr(), None, None, _lib.stream())
 
   def _wk(self, rec):
     return self.arena[rec.fwd_off:]
@@ -661,7 +662,8 @@ class DiscriminatorEngine:
                 u0_new.data_ptr(), self.t_ws.data_ptr(), self.s_ws.data_ptr(), self._s, self.scalars.data_ptr(),
                 self._rb, self._ct, _lib.stream(), launches=5)
     ops._call("xmc_prep_weights", self.prep.dev.data_ptr(), self.prep.n, self.prep.tiles, params.data_ptr(),
-              self.scalars.data_ptr() if self.sn else None, self.n_sn, self.arena.data_ptr(), None, _lib.stream())
+              self.scalars.data_ptr() if self.sn else None, self.n_sn, self.arena.data_ptr(), None, None,
+              _lib.stream())
 
   def sn_backward(self, params, grads, u0_new):
     if self.sn:
@@ -871,3 +873,194 @@ class DiscriminatorEngine:
       shp = ctx["xw_shape"]
       d_xw = ctx["fake_word"].bwd().view(B, shp[1], shp[2], E)
     return self._backward_trunk(ctx, dout, sl, None, d_xw, slice(0, B), True)
+
+
+# ======================================================================================================================
+# Frozen ResNet-50 feature branch (pretrained_image_contrastive)
+# ======================================================================================================================
+RESNET50_STAGES = [3, 4, 6, 3]
+
+
+class ResNetEngine:
+  """resnet_v1.ResNet50 in eval mode (xmcgan/utils/resnet_v1.py:129-180) behind get_pretrained_embs
+  (pretrained_model_utils.py:102-127): forward on [real; fake] images, input gradient for the fake half.
+  Eval BatchNorm is folded into the bf16 weights / an fp32 bias once at construction; operands are bf16 with fp32
+  accumulation (the reference runs this network in fp32)."""
+  T, PAD_LO, TP = 224, 2, 229  # 7x7/2 SAME on 224: pad (2,3)
+
+  def __init__(self, num_classes=1000, width=64):
+    self.width, self.num_classes = width, num_classes
+    L = self.layout = Layout()
+    S = self.stats_layout = Layout()
+    self.convs = collections.OrderedDict()  # path -> dict(kh, cin, cout, stride, bn)
+    self.arena_size = 0
+    self.prep = _PrepTable()
+    self.cscale_size = 0
+
+    def add_bn(path, c):
+      L.add(path + ("scale",), (c,))
+      L.add(path + ("bias",), (c,))
+      S.add(path + ("mean",), (c,))
+      S.add(path + ("var",), (c,))
+
+    def add_conv(path, bn_path, kh, cin, cout, stride):
+      w_off = L.add(path + ("kernel",), (kh, kh, cin, cout))
+      add_bn(bn_path, cout)
+      taps = kh * kh
+      rec = dict(kh=kh, cin=cin, cout=cout, stride=stride, bn=bn_path, w_off=w_off, cs_off=self.cscale_size)
+      self.cscale_size += _r4(cout)
+      if cin >= 8:
+        rec["ld_fwd"], rec["ld_dg"] = _r8(taps * cin), _r8(taps * cout)
+        rec["fwd_off"] = self.arena_size
+        self.arena_size += _r8(cout) * rec["ld_fwd"]
+        rec["dg_off"] = self.arena_size
+        self.arena_size += _r8(cin) * rec["ld_dg"]
+        self.prep.add(w_off, taps, cin, cout, rec["fwd_off"], rec["ld_fwd"], rec["dg_off"], rec["ld_dg"], -1,
+                      cscale_off=rec["cs_off"])
+      self.convs[path] = rec
+
+    add_conv(("init_conv",), ("init_bn",), 7, 3, width, 2)
+    self.blocks = []
+    cin = width
+    for si, nb in enumerate(RESNET50_STAGES):
+      f = width * 2 ** si
+      for bi in range(nb):
+        pre = (f"stage{si + 1}", f"block{bi + 1}")
+        stride = 2 if (si > 0 and bi == 0) else 1
+        add_conv(pre + ("conv1",), pre + ("bn1",), 1, cin, f, 1)
+        add_conv(pre + ("conv2",), pre + ("bn2",), 3, f, f, stride)
+        add_conv(pre + ("conv3",), pre + ("bn3",), 1, f, 4 * f, 1)
+        proj = cin != 4 * f or stride == 2
+        if proj:
+          add_conv(pre + ("proj_conv",), pre + ("proj_bn",), 1, cin, 4 * f, stride)
+        self.blocks.append((pre, cin, f, stride, proj))
+        cin = 4 * f
+    self.c_last = cin
+    self.head_w = L.add(("head", "kernel"), (cin, num_classes))
+    self.head_b = L.add(("head", "bias"), (num_classes,))
+    self.head_fwd = self.arena_size
+    self.arena_size += _r8(num_classes) * cin
+    self.head_dg = self.arena_size
+    self.arena_size += cin * _r8(num_classes)
+    self.prep.add(self.head_w, 1, cin, num_classes, self.head_fwd, cin, self.head_dg, _r8(num_classes), -1)
+    self.stem_off = self.arena_size          # packed stem weights [width][7*56]: k = kh*56 + kw*8 + c
+    self.arena_size += width * 392
+
+  def load(self, variables):
+    """variables: {"params": tree, "batch_stats": tree} (Flax names). One-time set-up: folds BatchNorm, writes the
+    bf16 weight arena. (Set-up only — torch is used here for the tiny per-channel fold, never on the step path.)"""
+    self.params = torch.zeros(self.layout.total, device="cuda")
+    self.stats = torch.zeros(self.stats_layout.total, device="cuda")
+    self.layout.load_tree(self.params, variables["params"])
+    self.stats_layout.load_tree(self.stats, variables["batch_stats"])
+    self.arena = torch.zeros(self.arena_size, device="cuda", dtype=BF16)
+    self.cscale = torch.ones(self.cscale_size, device="cuda")
+    self.fbias = torch.zeros(self.cscale_size, device="cuda")
+    L, S = self.layout, self.stats_layout
+    for path, rec in self.convs.items():
+      bn = rec["bn"]
+      s = L.view(self.params, bn + ("scale",)) * torch.rsqrt(S.view(self.stats, bn + ("var",)) + 1e-5)
+      b = L.view(self.params, bn + ("bias",)) - S.view(self.stats, bn + ("mean",)) * s
+      self.cscale[rec["cs_off"]:rec["cs_off"] + rec["cout"]] = s
+      self.fbias[rec["cs_off"]:rec["cs_off"] + rec["cout"]] = b
+    self.prep.upload()
+    ops._call("xmc_prep_weights", self.prep.dev.data_ptr(), self.prep.n, self.prep.tiles, self.params.data_ptr(), None,
+              0, self.arena.data_ptr(), None, self.cscale.data_ptr(), _lib.stream())
+    # stem: [co][kh*56 + kw*8 + c] = W[kh,kw,c,co] * s[co]  (zeros for c >= 3): per output pixel and kh the 7 kw taps
+    # x 8 padded channels are ONE contiguous 56-element run of the zero-bordered 8-channel image
+    rec = self.convs[("init_conv",)]
+    w = L.view(self.params, ("init_conv", "kernel")) * self.cscale[rec["cs_off"]:rec["cs_off"] + self.width]
+    packed = torch.zeros(self.width, 7, 7, 8, device="cuda")
+    packed[:, :, :, :3] = w.permute(3, 0, 1, 2)
+    self.arena[self.stem_off:self.stem_off + self.width * 392] = packed.reshape(self.width, 392).to(BF16).reshape(-1)
+    torch.cuda.synchronize()
+
+  def _bias(self, rec):
+    return self.fbias[rec["cs_off"]:]
+
+  def forward(self, images_f32):
+    """images_f32: fp32 [N,S,S,3] in [0,1]. Returns (logits fp32 [N,num_classes], ctx)."""
+    N, S = images_f32.shape[0], images_f32.shape[1]
+    T, TP, W0 = self.T, self.TP, self.width
+    xpad = ops.empty((N, TP, TP, 8))
+    ops._call("xmc_resize_bilinear_pad", images_f32.data_ptr(), N, S, T, TP, self.PAD_LO, xpad.data_ptr(),
+              _lib.stream())
+    rec = self.convs[("init_conv",)]
+    view = dict(Hout=T // 2, Wout=T // 2, KH=7, KW=1, strideH=2, strideW=1, Hin=TP, Win=T // 2, pitchW=16,
+                pitchH=TP * 8, pitchN=TP * TP * 8)
+    stem = ops.conv_fwd(xpad, self.arena[self.stem_off:], 7, W0, bias=self._bias(rec), ldb=392, c=56, view=view)
+    x = ops.empty((N, T // 4, T // 4, W0))
+    ops._call("xmc_maxpool3s2", stem.data_ptr(), N, T // 2, W0, x.data_ptr(), _lib.stream())
+    ctx = {"N": N, "S": S, "stem": stem, "pool0": x, "blocks": []}
+    for pre, cin, f, stride, proj in self.blocks:
+      r1c, r2c, r3c = (self.convs[pre + (f"conv{i}",)] for i in (1, 2, 3))
+      r1 = ops.conv_fwd(x, self.arena[r1c["fwd_off"]:], 1, f, bias=self._bias(r1c), relu=True, ldb=r1c["ld_fwd"])
+      r2 = ops.conv_fwd(r1, self.arena[r2c["fwd_off"]:], 3, f, bias=self._bias(r2c), relu=True, ldb=r2c["ld_fwd"],
+                        stride=stride)
+      if proj:
+        pc = self.convs[pre + ("proj_conv",)]
+        sc = ops.conv_fwd(x, self.arena[pc["fwd_off"]:], 1, 4 * f, bias=self._bias(pc), ldb=pc["ld_fwd"],
+                          stride=stride)
+      else:
+        sc = x
+      out = ops.conv_fwd(r2, self.arena[r3c["fwd_off"]:], 1, 4 * f, bias=self._bias(r3c), residual=sc, relu=True,
+                         ldb=r3c["ld_fwd"])
+      ctx["blocks"].append(dict(x=x, r1=r1, r2=r2))
+      x = out
+    ctx["x_last"] = x
+    feat = ops.relu_sumhw(x)  # the block output is already >= 0: this is the plain spatial sum
+    feat_bf = ops.cast_to_bf16(feat)
+    hw = x.shape[1] * x.shape[2]
+    logits = ops.conv_fwd(as4(feat_bf), self.arena[self.head_fwd:], 1, self.num_classes,
+                          bias=self.params[self.head_b:], ldb=self.c_last, alpha=1.0 / hw,
+                          out_dtype=F32).view(N, self.num_classes)
+    ctx["hw"] = hw
+    return logits, ctx
+
+  def backward(self, ctx, dlogits, n0, d_images):
+    """dlogits: fp32 [n, num_classes] for images [n0, n0+n). Accumulates d(loss)/d(images) into d_images fp32
+    [n,S,S,3] (the 128-px images, i.e. through the bilinear resize as well)."""
+    n = dlogits.shape[0]
+    sl = slice(n0, n0 + n)
+    T, W0 = self.T, self.width
+    ncp = _r8(self.num_classes)
+    dl_bf = ops.zeros((n, ncp), BF16) if ncp != self.num_classes else ops.empty((n, ncp))
+    ops.cast_to_bf16(dlogits, dl_bf[:, :self.num_classes])
+    dfeat = ops.conv_fwd(as4(dl_bf), self.arena[self.head_dg:], 1, self.c_last, ldb=ncp, alpha=1.0 / ctx["hw"],
+                         out_dtype=F32).view(n, self.c_last)
+    dout = ops.relu_sumhw_bwd(ctx["x_last"][sl], dfeat)   # includes the relu mask of the last block output
+    masked = True
+    for (pre, cin, f, stride, proj), sv in zip(reversed(self.blocks), reversed(ctx["blocks"])):
+      x, r1, r2 = sv["x"][sl], sv["r1"][sl], sv["r2"][sl]
+      r1c, r2c, r3c = (self.convs[pre + (f"conv{i}",)] for i in (1, 2, 3))
+      g = dout  # already multiplied by [block output > 0]
+      dr2 = ops.conv_fwd(g, self.arena[r3c["dg_off"]:], 1, f, mask=r2, ldb=r3c["ld_dg"])
+      if stride == 2:
+        z = ops.empty((n, 2 * dr2.shape[1], 2 * dr2.shape[2], f))
+        ops._call("xmc_zero_insert2", dr2.data_ptr(), n, dr2.shape[1], dr2.shape[2], f, z.data_ptr(), _lib.stream())
+        dr1 = ops.conv_fwd(z, self.arena[r2c["dg_off"]:], 3, f, mask=r1, ldb=r2c["ld_dg"], pad=2)
+      else:
+        dr1 = ops.conv_fwd(dr2, self.arena[r2c["dg_off"]:], 3, f, mask=r1, ldb=r2c["ld_dg"])
+      if proj:
+        pc = self.convs[pre + ("proj_conv",)]
+        if stride == 2:
+          zg = ops.empty((n, 2 * g.shape[1], 2 * g.shape[2], 4 * f))
+          ops._call("xmc_zero_insert2", g.data_ptr(), n, g.shape[1], g.shape[2], 4 * f, zg.data_ptr(), _lib.stream())
+          g_in = zg
+        else:
+          g_in = g
+        sg = ops.conv_fwd(g_in, self.arena[pc["dg_off"]:], 1, cin, ldb=pc["ld_dg"])
+      else:
+        sg = g
+      first = pre == self.blocks[0][0]
+      # d(block input) = (conv1 dgrad + shortcut gradient) * [input > 0]; the first block's input (max-pool output)
+      # is not a relu output (no ReLU after init_bn, resnet_v1.py:146-154)
+      dout = ops.conv_fwd(dr1, self.arena[r1c["dg_off"]:], 1, cin, residual=sg, ldb=r1c["ld_dg"],
+                          mask=None if first else x, mask_last=True)
+    dstem = ops.empty((n, T // 2, T // 2, W0))
+    ops._call("xmc_maxpool3s2_bwd", dout.data_ptr(), ctx["stem"][sl].data_ptr(), ctx["pool0"][sl].data_ptr(), n, T // 2,
+              W0, dstem.data_ptr(), _lib.stream())
+    d224 = ops.empty((n, T, T, 3), F32)
+    ops._call("xmc_stem_dgrad", dstem.data_ptr(), self.arena[self.stem_off:].data_ptr(), n, T, T // 2, W0, self.PAD_LO,
+              d224.data_ptr(), _lib.stream())
+    ops._call("xmc_resize_bilinear_bwd", d224.data_ptr(), n, ctx["S"], T, d_images.data_ptr(), _lib.stream())

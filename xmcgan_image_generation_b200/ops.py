@@ -43,18 +43,31 @@ def zeros(shape, dtype=F32):
 
 # ------------------------------------------------------------------------------------------------------------- GEMMs
 def conv_fwd(x, wk, kh, cout, *, bias=None, residual=None, res_shift=0, mask=None, relu=False, out=None,
-             out_dtype=BF16, alpha=1.0, ldb=None, batched=False, stride_b=0, c=None):
+             out_dtype=BF16, alpha=1.0, ldb=None, batched=False, stride_b=0, c=None, stride=1, pad=None,
+             mask_last=False, view=None):
   """x: [N,H,W,>=C] bf16 view (channel-contiguous); wk: bf16 tensor whose data pointer is the [cout][kh*kh*C] K-major
-  matrix (row pitch ldb). Returns y [N,H,W,cout] (or writes into the `out` view)."""
+  matrix (row pitch ldb). Returns y [N,H/stride,W/stride,cout] (or writes into the `out` view).
+  stride=2 reads the input at (h*2+kh-pad, w*2+kw-pad) (XLA SAME: pad low = 0 for a 3x3 or 1x1 kernel on an even
+  input). `view`: dict overriding the input view (Hout, Wout, KH, KW, pitches, strides) for the ResNet stem."""
   N, H, W = x.shape[0], x.shape[1], x.shape[2]
   C = x.shape[3] if c is None else c
   _check_dense_rows(x)
   d = ConvDesc()
-  d.N, d.H, d.W, d.C, d.ldA = N, H, W, C, _pix_ld(x)
+  d.N, d.H, d.W, d.C, d.ldA = N, H // stride, W // stride, C, _pix_ld(x)
   d.KH = d.KW = kh
-  d.pad_h = d.pad_w = kh // 2
+  d.pad_h = d.pad_w = (kh // 2 if stride == 1 else 0) if pad is None else pad
+  if stride != 1:
+    d.strideH = d.strideW = stride
+    d.Hin, d.Win = H, W
+  if view is not None:
+    d.H, d.W, d.KH, d.KW = view["Hout"], view["Wout"], view["KH"], view["KW"]
+    d.pad_h = d.pad_w = 0
+    d.strideH, d.strideW, d.Hin, d.Win = view["strideH"], view["strideW"], view["Hin"], view["Win"]
+    d.pitchW, d.pitchH, d.pitchN = view["pitchW"], view["pitchH"], view["pitchN"]
+  H, W = d.H, d.W
+  d.mask_last = 1 if mask_last else 0
   d.Cout = cout
-  d.ldB = ldb if ldb is not None else kh * kh * C
+  d.ldB = ldb if ldb is not None else d.KH * d.KW * C
   d.batched = 1 if batched else 0
   d.strideB_batch = stride_b
   if out is None:

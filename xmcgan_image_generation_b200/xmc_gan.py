@@ -45,13 +45,30 @@ def calculate_contrastive_loss(result_dict):
   return real_loss, fake_loss + result_dict["image_contrastive_loss"]
 
 
-def create_additional_data(config):
-  """xmc_gan.create_additional_data (xmc_gan.py:43-55). The frozen ResNet-50 branch is not built in this round."""
-  if config.pretrained_image_contrastive:
-    raise NotImplementedError(
-        "pretrained_image_contrastive=True (frozen ResNet-50 image-image InfoNCE, xmc_gan.py:74-90,148-152) is not "
-        "built yet; set config.pretrained_image_contrastive=False")
-  return {}
+def create_additional_data(config, variables=None, checkpoint_path="data/resnet_pretrained.npy"):
+  """xmc_gan.create_additional_data (xmc_gan.py:43-55) + pretrained_model_utils.get_pretrained_model (:65-99): returns
+  {"image_model", "image_model_state"} for the frozen ResNet-50. `variables` ({"params","batch_stats"} with the
+  names of resnet_v1.py) takes precedence; otherwise the reference's .npy checkpoint is loaded from `checkpoint_path`
+  (not shipped with the reference, README.md:60-63)."""
+  if not config.pretrained_image_contrastive:
+    return {}
+  if variables is None:
+    import numpy as np
+    data = np.load(checkpoint_path, allow_pickle=True).item()  # same format as pretrained_model_utils.py:95-98
+    variables = {"params": data["params"], "batch_stats": data["batch_stats"]}
+  model = _engine.ResNetEngine()
+  model.load(variables)
+  return {"image_model": model, "image_model_state": variables}
+
+
+def calculate_contrastive_loss_on_pretrained(model, state, real_images, fake_images):
+  """xmc_gan.calculate_contrastive_loss_on_pretrained (xmc_gan.py:74-90), forward value only."""
+  b = real_images.shape[0]
+  both = torch.cat([xmc_net._to_dev(real_images), xmc_net._to_dev(fake_images)])  # plumbing: one batched forward
+  logits, _ = model.forward(both)
+  slot = ops.empty(1, ops.F32)
+  _engine.Contrastive(logits[:b], logits[b:], slot)
+  return slot[0]
 
 
 class _Workspace:
@@ -102,6 +119,7 @@ def _forward_both(state, batch, config, ws, g_eng, d_eng, losses, keep_g_state, 
   fake, gctx = g_eng.forward(g_params, state.generator_state["batch_stats"].buf, batch, batch["z"], train=True,
                              new_stats=ws.g_stats_alt if keep_g_state else None, fake_bf16=all_images[B:])
   _, dctx = d_eng.forward(d_params, all_images, batch, losses, need_g=need_g)
+  gctx["fake"] = fake
   return gctx, dctx
 
 
@@ -139,8 +157,6 @@ def train_d(rng, state, batch, generator, discriminator, config):
 def train_g_d(rng, state, batch, generator, discriminator, config, additional_data):
   """xmc_gan.train_g_d (xmc_gan.py:93-191): one forward, two pull-backs at the old parameters (:162-167), pmean of
   both gradients (:170-171), Adam on D and G (:172-173), polyak EMA (:174-177), metrics (:185-190)."""
-  if config.pretrained_image_contrastive:
-    raise NotImplementedError("pretrained_image_contrastive=True is not built yet (see create_additional_data)")
   batch = xmc_net.batch_to_device(batch)
   g_eng, d_eng = _engines(config, batch)
   ws = _workspace(state, g_eng, d_eng)
@@ -157,6 +173,21 @@ def train_g_d(rng, state, batch, generator, discriminator, config, additional_da
   # pull-back #2: g_loss -> fake images -> params_g
   d_fake = d_eng.backward_g(dctx, d_params)
   del dctx
+  if config.pretrained_image_contrastive:
+    # frozen ResNet-50 image-image InfoNCE between real and generated images (xmc_gan.py:148-152); its gradient
+    # reaches the generator only through the fake images
+    model = additional_data["image_model"]
+    B = batch["z"].shape[0]
+    S = config.image_size
+    both = ops.empty((2 * B, S, S, 3), ops.F32)
+    both[:B].copy_(batch["image"])     # device-to-device copies (plumbing)
+    both[B:].copy_(gctx["fake"])
+    logits, rctx = model.forward(both)
+    c = _engine.Contrastive(logits[:B], logits[B:], losses[_S["pretrained"]:])
+    dl_fake = ops.empty((B, logits.shape[1]), ops.F32)
+    c.bwd_b(dl_fake, accumulate=False)
+    model.backward(rctx, dl_fake, B, d_fake)
+    del rctx
   ws.g_grads.zero_()
   ops.LAUNCHES[0] += 1
   g_eng.backward(gctx, d_fake, g_params, ws.g_grads)
