@@ -26,11 +26,10 @@ E_DIM, N_WORDS = 768, 17
 PER_GPU_B = 56  # per-device sub-batch of train_d and of train_g_d (coco_xmc.py:49 with one device)
 
 
-def make_config(image_size=128):
+def make_config(image_size=128, pretrained=True):
   from xmcgan_image_generation_b200.configs import coco_xmc
-  c = coco_xmc.get_config()
-  # the frozen ResNet-50 image-image InfoNCE branch (xmc_gan.py:148-152) is not built yet: stated in `config`
-  c.update(dict(image_size=image_size, pretrained_image_contrastive=False))
+  c = coco_xmc.get_config()  # reference defaults, incl. pretrained_image_contrastive=True (coco_xmc.py:65)
+  c.update(dict(image_size=image_size, pretrained_image_contrastive=bool(pretrained)))
   return c
 
 
@@ -79,12 +78,12 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-def algorithmic_tflop_per_step(B):
-  """BASELINE.md §3 / SURVEY.md §8(d), 128 px, ResNet branch off: 25.55 TFLOP at B=56 (scaled by its B and B^2 parts)."""
+def algorithmic_tflop_per_step(B, pretrained=True):
+  """BASELINE.md §3 / SURVEY.md §8(d), 128 px: 26.93 TFLOP at B=56 (25.55 with the ResNet branch off)."""
   wl = 0.01337e-3 * B * B              # TFLOP per word_loss forward call
-  g, d = 43.40e-3, 21.23e-3            # TFLOP per image forward (algorithmic G, D)
+  g, d, r = 43.40e-3, 21.23e-3, 8.18e-3  # TFLOP per image forward (algorithmic G, D, ResNet-50 @224)
   train_d = g * B + d * 2 * B * 3 + 3 * wl
-  train_g_d = 3 * g * B + d * 2 * B * 3 + d * B + 6 * wl
+  train_g_d = 3 * g * B + d * 2 * B * 3 + d * B + 6 * wl + (r * 3 * B if pretrained else 0.0)
   return train_d + train_g_d
 
 
@@ -157,14 +156,18 @@ def run_b200(args):
   torch.cuda.set_device(local)
   if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-  config = make_config(args.image_size)
+  from xmcgan_image_generation_b200 import engine
+  pretrained = not args.no_pretrained
+  config = make_config(args.image_size, pretrained)
   B = args.batch
   config.batch_size = B * world
   host = synth_batch(2 * B, config, 42 + rank)
   pinned = {k: v.pin_memory() for k, v in host.items()}
   dev = {k: v.cuda() for k, v in host.items()}
   generator, discriminator, state = train_utils.create_train_state(config, 42, host)
-  additional = {}
+  # frozen ResNet-50 with synthetic weights (the reference's checkpoint is not shipped): same seed on every rank
+  additional = xmc_gan.create_additional_data(
+      config, variables=engine.ResNetEngine().random_variables(7) if pretrained else None)
 
   def barrier():
     if world > 1:
@@ -249,10 +252,11 @@ def run_b200(args):
       "config": {"workload": f"coco_xmc.py {config.image_size}px, per-GPU sub-batch B={B} (2B real images per step), "
                              "train_d + train_g_d, Adam, EMA, grad all-reduce",
                  "global_batch": B * world, "parallelism": f"dp{world}",
-                 "pretrained_image_contrastive": False,
+                 "pretrained_image_contrastive": pretrained,
                  "l2": "per-step working set (several GB of activations) >> 126 MB L2; no explicit flush",
-                 "algorithmic_tflop_per_step_per_gpu": round(algorithmic_tflop_per_step(B), 2),
-                 "model_tflops_per_gpu": round(algorithmic_tflop_per_step(B) / (ms_dev / args.steps / 1e3), 1)},
+                 "algorithmic_tflop_per_step_per_gpu": round(algorithmic_tflop_per_step(B, pretrained), 2),
+                 "model_tflops_per_gpu": round(algorithmic_tflop_per_step(B, pretrained) /
+                                               (ms_dev / args.steps / 1e3), 1)},
       "e2e": {"value": round(imgs / (ms_e2e / 1e3), 2), "unit": "images/sec", "h2d_bytes_per_step": h2d,
               "d2h_bytes_per_step": 20},
       "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "losses": last,
@@ -283,17 +287,22 @@ def cpu_baseline(args, quick):
   from oracle import xmc_oracle as orc
   cores = os.cpu_count() or 1
   torch.set_num_threads(cores)
-  config = make_config(args.image_size)
+  pretrained = not args.no_pretrained
+  config = make_config(args.image_size, pretrained)
   Bc = 2
   state = _oracle_state(config)
   batch = synth_batch(2 * Bc, config, 42)
+  pre = None
+  if pretrained:
+    rvars = orc.resnet50_random_variables(7)
+    pre = lambda real, fake: orc.calculate_contrastive_loss_on_pretrained(rvars, real, fake, orc.FP32)
   n = 1 if quick else max(1, args.steps)
   if not quick:
     for _ in range(min(1, args.warmup)):
-      state, _ = orc.train_step(state, batch, config, orc.FP32)
+      state, _ = orc.train_step(state, batch, config, orc.FP32, pretrained_fn=pre)
   t0 = time.time()
   for _ in range(n):
-    state, _ = orc.train_step(state, batch, config, orc.FP32)
+    state, _ = orc.train_step(state, batch, config, orc.FP32, pretrained_fn=pre)
   dt = (time.time() - t0) / n
   return {"value": round(2 * Bc / dt, 4), "unit": "images/sec", "cores": cores, "kind": "port",
           "sample": f"{n} train_step(s) of the torch-CPU fp32 restatement at per-device sub-batch B={Bc} "
@@ -311,7 +320,8 @@ def run_reference(args):
          "ms_per_step": round(cb["sec_per_step"] * 1e3, 1), "higher_is_better": True, "scaling": "weak",
          "vs_baseline": None, "dtype": "f32", "data": "synthetic",
          "config": {"workload": "coco_xmc.py 128px train_step, reference algorithm (CPU restatement: JAX/Flax are not "
-                                "installable here), bounded sample", "pretrained_image_contrastive": False},
+                                "installable here), bounded sample",
+                    "pretrained_image_contrastive": not args.no_pretrained},
          "cpu_baseline": cb,
          "e2e": {"value": cb["value"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
   print(json.dumps(out), flush=True)
@@ -326,6 +336,8 @@ def main():
   ap.add_argument("--batch", type=int, default=PER_GPU_B, help="per-GPU sub-batch B")
   ap.add_argument("--image-size", type=int, default=128)
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--no-pretrained", action="store_true",
+                  help="switch the frozen ResNet-50 image-image InfoNCE branch off (reference default: on)")
   ap.add_argument("--dump-gemm", default=None, help="write per-shape GEMM timings (JSON) to this file")
   args = ap.parse_args()
   if args.warmup < 3 and args.impl == "b200":

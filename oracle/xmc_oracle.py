@@ -744,24 +744,35 @@ def _conv_bn(x, params, stats, conv, bn, stride, policy, relu, residual=None):
   return policy.q(y)
 
 
+def bottleneck_block(x, p, s, stride, policy=FP32):
+  """resnet_v1.BottleneckResNetBlock (resnet_v1.py:60-86): 1x1 -> 3x3 (strided) -> 1x1, projection shortcut when the
+  shape changes, relu(residual + x)."""
+  residual = x
+  y = _conv_bn(x, p, s, "conv1", "bn1", 1, policy, relu=True)
+  y = _conv_bn(y, p, s, "conv2", "bn2", stride, policy, relu=True)
+  if "proj_conv" in p:
+    residual = _conv_bn(x, p, s, "proj_conv", "proj_bn", stride, policy, relu=False)
+  return _conv_bn(y, p, s, "conv3", "bn3", 1, policy, relu=True, residual=residual)
+
+
+def resnet_stem(variables, x, policy=FP32):
+  """init_conv 7x7/2 + init_bn (no ReLU) + max_pool 3x3/2 SAME (resnet_v1.py:146-154). Returns (stem, pooled)."""
+  P, S = variables["params"], variables["batch_stats"]
+  stem = _conv_bn(x, P, S, "init_conv", "init_bn", 2, policy, relu=False)
+  pt, pb = _same_pads(stem.shape[1], 3, 2)
+  xp = F.pad(stem.permute(0, 3, 1, 2), (pt, pb, pt, pb), value=float("-inf"))
+  return stem, F.max_pool2d(xp, 3, 2).permute(0, 2, 3, 1)
+
+
 def resnet50_apply(variables, x, policy=FP32):
   """resnet_v1.ResNet.__call__ (resnet_v1.py:129-172), train=False, BottleneckResNetBlock (:60-86).
   Note: no ReLU after init_bn (:146-154); the stride sits on the 3x3 conv (:79). Returns (pool, logits)."""
   P, S = variables["params"], variables["batch_stats"]
-  x = _conv_bn(x, P, S, "init_conv", "init_bn", 2, policy, relu=False)
-  pt, pb = _same_pads(x.shape[1], 3, 2)
-  xp = F.pad(x.permute(0, 3, 1, 2), (pt, pb, pt, pb), value=float("-inf"))
-  x = F.max_pool2d(xp, 3, 2).permute(0, 2, 3, 1)
+  _, x = resnet_stem(variables, x, policy)
   for si, nblocks in enumerate(RESNET50_STAGES):
     for bi in range(nblocks):
       p, s = P[f"stage{si + 1}"][f"block{bi + 1}"], S[f"stage{si + 1}"][f"block{bi + 1}"]
-      stride = 2 if (si > 0 and bi == 0) else 1
-      residual = x
-      y = _conv_bn(x, p, s, "conv1", "bn1", 1, policy, relu=True)
-      y = _conv_bn(y, p, s, "conv2", "bn2", stride, policy, relu=True)
-      if "proj_conv" in p:
-        residual = _conv_bn(x, p, s, "proj_conv", "proj_bn", stride, policy, relu=False)
-      x = _conv_bn(y, p, s, "conv3", "bn3", 1, policy, relu=True, residual=residual)
+      x = bottleneck_block(x, p, s, 2 if (si > 0 and bi == 0) else 1, policy)
   pool = x
   feat = pool.float().mean(dim=(1, 2))
   logits = policy.q(feat) @ policy.q(P["head"]["kernel"]) + P["head"]["bias"]
@@ -818,7 +829,7 @@ def resnet50_param_shapes(num_classes=1000, width=64):
   return params, stats
 
 
-def resnet50_random_variables(seed=0, head_scale=0.05):
+def resnet50_random_variables(seed=0, head_scale=0.05, residual_scale=0.3):
   """Synthetic frozen weights (the reference's data/resnet_pretrained.npy is not shipped, README.md:60-63): He-normal
   kernels, BatchNorm scale ~ 1, small random bias / mean, var ~ 1, and a NON-zero head (the reference initialises the
   head to zeros, resnet_v1.py:171, which would make the loss the constant 2 log B)."""
@@ -839,6 +850,8 @@ def resnet50_random_variables(seed=0, head_scale=0.05):
           out[k] = torch.randn(shape, generator=g) * head_scale
         elif k == "scale":
           out[k] = 1.0 + 0.1 * torch.randn(shape, generator=g)
+          if path and path[-1] == "bn3":
+            out[k] = out[k] * residual_scale  # keeps the residual stream O(1) so that features stay image-dependent
         elif k == "var":
           out[k] = 1.0 + 0.2 * torch.rand(shape, generator=g)
         else:  # bias, mean

@@ -372,9 +372,10 @@ def test_train_step_runs_at_baseline_width_and_decreases_nothing_to_nan():
 
 @gpu
 def test_frozen_resnet50_branch_matches_oracle():
-  """calculate_contrastive_loss_on_pretrained (xmc_gan.py:74-90): logits of the frozen ResNet-50 on bilinearly
-  resized images vs the oracle (bf16 policy) 2e-2 rel-L2; loss 2e-3; gradient wrt the fake images vs oracle autograd
-  cosine > 0.98 / rel-L2 < 0.2 (bf16 activation gradients through 50 layers)."""
+  """calculate_contrastive_loss_on_pretrained (xmc_gan.py:74-90). Forward: logits of the frozen ResNet-50 on
+  bilinearly resized images vs the oracle (bf16 policy) 2e-2 rel-L2, loss 2e-3. The end-to-end input gradient of a
+  50-layer relu/max-pool network is chaotic under bf16 perturbations (the oracle's own bf16-vs-fp32 gradients differ
+  by 20-40 %), so it is bounded by 1.5x that distance here and checked sharply piece by piece in the next test."""
   _, engine, ops, _, xmc_gan, _ = _mods()
   torch.manual_seed(3)
   variables = orc.resnet50_random_variables(1)
@@ -391,17 +392,60 @@ def test_frozen_resnet50_branch_matches_oracle():
   assert helpers.rel(logits, want) < 2e-2
   slot = ops.empty(1, torch.float32)
   c = engine.Contrastive(logits[:B], logits[B:], slot)
-  fk = fake.clone().requires_grad_(True)
-  loss = orc.calculate_contrastive_loss_on_pretrained(variables, real, fk, pol)
-  loss.backward()
-  assert abs(slot.item() - loss.item()) < 2e-3 * abs(loss.item())
+  grads = {}
+  for name, p in (("bf16", pol), ("fp32", orc.FP32)):
+    fk = fake.clone().requires_grad_(True)
+    loss = orc.calculate_contrastive_loss_on_pretrained(variables, real, fk, p)
+    loss.backward()
+    grads[name] = fk.grad.reshape(-1)
+    if name == "bf16":
+      assert abs(slot.item() - loss.item()) < 2e-3 * abs(loss.item())
   dl = ops.empty((B, 1000), torch.float32)
   c.bwd_b(dl, accumulate=False)
   d_fake = torch.zeros(B, S, S, 3, device="cuda")
   model.backward(rctx, dl, B, d_fake)
-  g, r = d_fake.cpu().reshape(-1), fk.grad.reshape(-1)
-  cos = torch.nn.functional.cosine_similarity(g, r, dim=0).item()
-  assert cos > 0.98 and helpers.rel(g, r) < 0.2, (cos, helpers.rel(g, r))
+  g = d_fake.cpu().reshape(-1)
+  noise = helpers.rel(grads["bf16"], grads["fp32"])
+  assert helpers.rel(g, grads["bf16"]) < max(0.1, 1.5 * noise), (helpers.rel(g, grads["bf16"]), noise)
+  assert torch.nn.functional.cosine_similarity(g, grads["bf16"], dim=0).item() > 0.9
+
+
+@gpu
+def test_resnet_pieces_forward_and_backward_sharp():
+  """Sharp checks of every new piece of the ResNet branch on identical inputs: stem (resize + 7x7/2 conv + folded BN
+  + 3x3/2 max-pool) forward 1e-2 and its (linear) input gradient 2e-2; bottleneck blocks with stride 1 / stride 2 +
+  projection: forward 1e-2, input gradient 3e-2 (single block, so relu-mask disagreement is negligible)."""
+  _, engine, ops, *_ = _mods()
+  torch.manual_seed(5)
+  variables = orc.resnet50_random_variables(4)
+  model = engine.ResNetEngine()
+  model.load(variables)
+  pol = orc.Policy("bfloat16")
+  n, S = 2, 128
+  img = torch.rand(n, S, S, 3).requires_grad_(True)
+  x224 = torch.nn.functional.interpolate(img.permute(0, 3, 1, 2), size=(224, 224), mode="bilinear",
+                                         align_corners=False).permute(0, 2, 3, 1)
+  stem_o, pool_o = orc.resnet_stem(variables, x224, pol)
+  stem, pooled = model.stem_forward(img.detach().cuda())
+  assert helpers.rel(stem, stem_o) < 1e-2 and helpers.rel(pooled, pool_o) < 1e-2
+  dpool = _q(torch.randn_like(pool_o) * 0.1)
+  (pool_o * dpool).sum().backward()
+  d_img = torch.zeros(n, S, S, 3, device="cuda")
+  model.stem_backward(dpool.cuda().to(torch.bfloat16), stem, pooled, S, d_img)
+  assert helpers.rel(d_img, img.grad) < 2e-2
+  for idx in (1, 3, 7):  # stage1/block2 (identity), stage2/block1 (stride 2 + projection), stage3/block1
+    spec = model.blocks[idx]
+    pre, cin, f, stride, proj = spec
+    Hin = {0: 56, 1: 56, 2: 28, 3: 14}[int(pre[0][-1]) - 1 if stride == 1 else int(pre[0][-1]) - 2]
+    x = _q(torch.relu(torch.randn(n, Hin, Hin, cin))).requires_grad_(True)
+    p, s_ = variables["params"][pre[0]][pre[1]], variables["batch_stats"][pre[0]][pre[1]]
+    out_o = orc.bottleneck_block(x, p, s_, stride, pol)
+    out, sv = model.block_forward(x.detach().cuda().to(torch.bfloat16), spec)
+    assert helpers.rel(out, out_o) < 1e-2, pre
+    dout = _q(torch.randn_like(out_o) * 0.1) * (out_o.detach() > 0)
+    (out_o * dout).sum().backward()
+    dx = model.block_backward(dout.cuda().to(torch.bfloat16), sv["x"], sv["r1"], sv["r2"], spec, mask_input=False)
+    assert helpers.rel(dx, x.grad) < 3e-2, (pre, helpers.rel(dx, x.grad))
 
 
 @gpu

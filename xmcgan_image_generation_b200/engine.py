@@ -946,6 +946,37 @@ class ResNetEngine:
     self.stem_off = self.arena_size          # packed stem weights [width][7*56]: k = kh*56 + kw*8 + c
     self.arena_size += width * 392
 
+  def random_variables(self, seed=0, head_scale=0.05, residual_scale=0.3):
+    """Synthetic frozen weights for benchmarking (the reference's data/resnet_pretrained.npy is not shipped,
+    README.md:60-63): He-normal kernels, BatchNorm scale ~ 1 (bn3 scaled down so the residual stream stays O(1)),
+    small random bias / mean, var ~ 1 and a non-zero head (the reference's zero-initialised head, resnet_v1.py:171,
+    would make the loss the constant 2 log B). Returns {"params","batch_stats"} nested dicts of CPU tensors."""
+    g = torch.Generator().manual_seed(seed)
+
+    def leaf(path, shape):
+      k = path[-1]
+      if k == "kernel" and len(shape) == 4:
+        return torch.randn(shape, generator=g) * math.sqrt(2.0 / (shape[0] * shape[1] * shape[2]))
+      if k == "kernel":
+        return torch.randn(shape, generator=g) * head_scale
+      if k == "scale":
+        t = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        return t * residual_scale if path[-2] == "bn3" else t
+      if k == "var":
+        return 1.0 + 0.2 * torch.rand(shape, generator=g)
+      return 0.1 * torch.randn(shape, generator=g)
+
+    out = {}
+    for name, layout in (("params", self.layout), ("batch_stats", self.stats_layout)):
+      root = {}
+      for path, (_, shape) in layout.entries.items():
+        node = root
+        for k in path[:-1]:
+          node = node.setdefault(k, {})
+        node[path[-1]] = leaf(path, shape)
+      out[name] = root
+    return out
+
   def load(self, variables):
     """variables: {"params": tree, "batch_stats": tree} (Flax names). One-time set-up: folds BatchNorm, writes the
     bf16 weight arena. (Set-up only — torch is used here for the tiny per-channel fold, never on the step path.)"""
@@ -978,8 +1009,8 @@ class ResNetEngine:
   def _bias(self, rec):
     return self.fbias[rec["cs_off"]:]
 
-  def forward(self, images_f32):
-    """images_f32: fp32 [N,S,S,3] in [0,1]. Returns (logits fp32 [N,num_classes], ctx)."""
+  def stem_forward(self, images_f32):
+    """bilinear resize to 224 -> 7x7/2 conv (+ folded init_bn, no ReLU) -> 3x3/2 max-pool. Returns (stem, pooled)."""
     N, S = images_f32.shape[0], images_f32.shape[1]
     T, TP, W0 = self.T, self.TP, self.width
     xpad = ops.empty((N, TP, TP, 8))
@@ -991,22 +1022,68 @@ class ResNetEngine:
     stem = ops.conv_fwd(xpad, self.arena[self.stem_off:], 7, W0, bias=self._bias(rec), ldb=392, c=56, view=view)
     x = ops.empty((N, T // 4, T // 4, W0))
     ops._call("xmc_maxpool3s2", stem.data_ptr(), N, T // 2, W0, x.data_ptr(), _lib.stream())
+    return stem, x
+
+  def stem_backward(self, dpool, stem, pooled, S, d_images):
+    """d(loss)/d(pooled) bf16 -> accumulates d(loss)/d(images) (fp32 [n,S,S,3]) through max-pool, stem and resize."""
+    n = dpool.shape[0]
+    T, W0 = self.T, self.width
+    dstem = ops.empty((n, T // 2, T // 2, W0))
+    ops._call("xmc_maxpool3s2_bwd", dpool.data_ptr(), stem.data_ptr(), pooled.data_ptr(), n, T // 2, W0,
+              dstem.data_ptr(), _lib.stream())
+    d224 = ops.empty((n, T, T, 3), F32)
+    ops._call("xmc_stem_dgrad", dstem.data_ptr(), self.arena[self.stem_off:].data_ptr(), n, T, T // 2, W0, self.PAD_LO,
+              d224.data_ptr(), _lib.stream())
+    ops._call("xmc_resize_bilinear_bwd", d224.data_ptr(), n, S, T, d_images.data_ptr(), _lib.stream())
+
+  def block_forward(self, x, spec):
+    pre, cin, f, stride, proj = spec
+    r1c, r2c, r3c = (self.convs[pre + (f"conv{i}",)] for i in (1, 2, 3))
+    r1 = ops.conv_fwd(x, self.arena[r1c["fwd_off"]:], 1, f, bias=self._bias(r1c), relu=True, ldb=r1c["ld_fwd"])
+    r2 = ops.conv_fwd(r1, self.arena[r2c["fwd_off"]:], 3, f, bias=self._bias(r2c), relu=True, ldb=r2c["ld_fwd"],
+                      stride=stride)
+    if proj:
+      pc = self.convs[pre + ("proj_conv",)]
+      sc = ops.conv_fwd(x, self.arena[pc["fwd_off"]:], 1, 4 * f, bias=self._bias(pc), ldb=pc["ld_fwd"], stride=stride)
+    else:
+      sc = x
+    out = ops.conv_fwd(r2, self.arena[r3c["fwd_off"]:], 1, 4 * f, bias=self._bias(r3c), residual=sc, relu=True,
+                       ldb=r3c["ld_fwd"])
+    return out, dict(x=x, r1=r1, r2=r2)
+
+  def block_backward(self, g, x, r1, r2, spec, mask_input):
+    """g: gradient wrt the block output, already multiplied by [output > 0]. Returns the gradient wrt the block input
+    (multiplied by [input > 0] when mask_input: the input is the previous block's relu output)."""
+    pre, cin, f, stride, proj = spec
+    n = g.shape[0]
+    r1c, r2c, r3c = (self.convs[pre + (f"conv{i}",)] for i in (1, 2, 3))
+    dr2 = ops.conv_fwd(g, self.arena[r3c["dg_off"]:], 1, f, mask=r2, ldb=r3c["ld_dg"])
+    if stride == 2:
+      z = ops.empty((n, 2 * dr2.shape[1], 2 * dr2.shape[2], f))
+      ops._call("xmc_zero_insert2", dr2.data_ptr(), n, dr2.shape[1], dr2.shape[2], f, z.data_ptr(), _lib.stream())
+      dr1 = ops.conv_fwd(z, self.arena[r2c["dg_off"]:], 3, f, mask=r1, ldb=r2c["ld_dg"], pad=2)
+    else:
+      dr1 = ops.conv_fwd(dr2, self.arena[r2c["dg_off"]:], 3, f, mask=r1, ldb=r2c["ld_dg"])
+    if proj:
+      pc = self.convs[pre + ("proj_conv",)]
+      g_in = g
+      if stride == 2:
+        g_in = ops.empty((n, 2 * g.shape[1], 2 * g.shape[2], 4 * f))
+        ops._call("xmc_zero_insert2", g.data_ptr(), n, g.shape[1], g.shape[2], 4 * f, g_in.data_ptr(), _lib.stream())
+      sg = ops.conv_fwd(g_in, self.arena[pc["dg_off"]:], 1, cin, ldb=pc["ld_dg"])
+    else:
+      sg = g
+    return ops.conv_fwd(dr1, self.arena[r1c["dg_off"]:], 1, cin, residual=sg, ldb=r1c["ld_dg"],
+                        mask=x if mask_input else None, mask_last=True)
+
+  def forward(self, images_f32):
+    """images_f32: fp32 [N,S,S,3] in [0,1]. Returns (logits fp32 [N,num_classes], ctx)."""
+    N, S = images_f32.shape[0], images_f32.shape[1]
+    stem, x = self.stem_forward(images_f32)
     ctx = {"N": N, "S": S, "stem": stem, "pool0": x, "blocks": []}
-    for pre, cin, f, stride, proj in self.blocks:
-      r1c, r2c, r3c = (self.convs[pre + (f"conv{i}",)] for i in (1, 2, 3))
-      r1 = ops.conv_fwd(x, self.arena[r1c["fwd_off"]:], 1, f, bias=self._bias(r1c), relu=True, ldb=r1c["ld_fwd"])
-      r2 = ops.conv_fwd(r1, self.arena[r2c["fwd_off"]:], 3, f, bias=self._bias(r2c), relu=True, ldb=r2c["ld_fwd"],
-                        stride=stride)
-      if proj:
-        pc = self.convs[pre + ("proj_conv",)]
-        sc = ops.conv_fwd(x, self.arena[pc["fwd_off"]:], 1, 4 * f, bias=self._bias(pc), ldb=pc["ld_fwd"],
-                          stride=stride)
-      else:
-        sc = x
-      out = ops.conv_fwd(r2, self.arena[r3c["fwd_off"]:], 1, 4 * f, bias=self._bias(r3c), residual=sc, relu=True,
-                         ldb=r3c["ld_fwd"])
-      ctx["blocks"].append(dict(x=x, r1=r1, r2=r2))
-      x = out
+    for spec in self.blocks:
+      x, sv = self.block_forward(x, spec)
+      ctx["blocks"].append(sv)
     ctx["x_last"] = x
     feat = ops.relu_sumhw(x)  # the block output is already >= 0: this is the plain spatial sum
     feat_bf = ops.cast_to_bf16(feat)
@@ -1022,45 +1099,14 @@ class ResNetEngine:
     [n,S,S,3] (the 128-px images, i.e. through the bilinear resize as well)."""
     n = dlogits.shape[0]
     sl = slice(n0, n0 + n)
-    T, W0 = self.T, self.width
     ncp = _r8(self.num_classes)
     dl_bf = ops.zeros((n, ncp), BF16) if ncp != self.num_classes else ops.empty((n, ncp))
     ops.cast_to_bf16(dlogits, dl_bf[:, :self.num_classes])
     dfeat = ops.conv_fwd(as4(dl_bf), self.arena[self.head_dg:], 1, self.c_last, ldb=ncp, alpha=1.0 / ctx["hw"],
                          out_dtype=F32).view(n, self.c_last)
     dout = ops.relu_sumhw_bwd(ctx["x_last"][sl], dfeat)   # includes the relu mask of the last block output
-    masked = True
-    for (pre, cin, f, stride, proj), sv in zip(reversed(self.blocks), reversed(ctx["blocks"])):
-      x, r1, r2 = sv["x"][sl], sv["r1"][sl], sv["r2"][sl]
-      r1c, r2c, r3c = (self.convs[pre + (f"conv{i}",)] for i in (1, 2, 3))
-      g = dout  # already multiplied by [block output > 0]
-      dr2 = ops.conv_fwd(g, self.arena[r3c["dg_off"]:], 1, f, mask=r2, ldb=r3c["ld_dg"])
-      if stride == 2:
-        z = ops.empty((n, 2 * dr2.shape[1], 2 * dr2.shape[2], f))
-        ops._call("xmc_zero_insert2", dr2.data_ptr(), n, dr2.shape[1], dr2.shape[2], f, z.data_ptr(), _lib.stream())
-        dr1 = ops.conv_fwd(z, self.arena[r2c["dg_off"]:], 3, f, mask=r1, ldb=r2c["ld_dg"], pad=2)
-      else:
-        dr1 = ops.conv_fwd(dr2, self.arena[r2c["dg_off"]:], 3, f, mask=r1, ldb=r2c["ld_dg"])
-      if proj:
-        pc = self.convs[pre + ("proj_conv",)]
-        if stride == 2:
-          zg = ops.empty((n, 2 * g.shape[1], 2 * g.shape[2], 4 * f))
-          ops._call("xmc_zero_insert2", g.data_ptr(), n, g.shape[1], g.shape[2], 4 * f, zg.data_ptr(), _lib.stream())
-          g_in = zg
-        else:
-          g_in = g
-        sg = ops.conv_fwd(g_in, self.arena[pc["dg_off"]:], 1, cin, ldb=pc["ld_dg"])
-      else:
-        sg = g
-      first = pre == self.blocks[0][0]
-      # d(block input) = (conv1 dgrad + shortcut gradient) * [input > 0]; the first block's input (max-pool output)
-      # is not a relu output (no ReLU after init_bn, resnet_v1.py:146-154)
-      dout = ops.conv_fwd(dr1, self.arena[r1c["dg_off"]:], 1, cin, residual=sg, ldb=r1c["ld_dg"],
-                          mask=None if first else x, mask_last=True)
-    dstem = ops.empty((n, T // 2, T // 2, W0))
-    ops._call("xmc_maxpool3s2_bwd", dout.data_ptr(), ctx["stem"][sl].data_ptr(), ctx["pool0"][sl].data_ptr(), n, T // 2,
-              W0, dstem.data_ptr(), _lib.stream())
-    d224 = ops.empty((n, T, T, 3), F32)
-    ops._call("xmc_stem_dgrad", dstem.data_ptr(), self.arena[self.stem_off:].data_ptr(), n, T, T // 2, W0, self.PAD_LO,
-              d224.data_ptr(), _lib.stream())
-    ops._call("xmc_resize_bilinear_bwd", d224.data_ptr(), n, ctx["S"], T, d_images.data_ptr(), _lib.stream())
+    for i in range(len(self.blocks) - 1, -1, -1):
+      sv = ctx["blocks"][i]
+      # the first block's input (max-pool output) is not a relu output (no ReLU after init_bn, resnet_v1.py:146-154)
+      dout = self.block_backward(dout, sv["x"][sl], sv["r1"][sl], sv["r2"][sl], self.blocks[i], mask_input=i > 0)
+    self.stem_backward(dout, ctx["stem"][sl], ctx["pool0"][sl], ctx["S"], d_images)
