@@ -100,7 +100,12 @@ class GemmTimer:
 
     def conv_fwd(x, wk, kh, cout, **kw):
       c = kw.get("c") or x.shape[3]
-      flops = 2.0 * x.shape[0] * x.shape[1] * x.shape[2] * kh * kh * c * cout
+      st = kw.get("stride", 1)
+      ho, wo, taps = x.shape[1] // st, x.shape[2] // st, kh * kh
+      view = kw.get("view")
+      if view is not None:  # ResNet stem: 7x7x3 taps per output pixel (the packed window has 8-channel padding)
+        ho, wo, taps, c = view["Hout"], view["Wout"], 49, 3
+      flops = 2.0 * x.shape[0] * ho * wo * taps * c * cout
       s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
       s.record()
       out = timer._fwd(x, wk, kh, cout, **kw)

@@ -68,6 +68,18 @@ __device__ __forceinline__ uint8_t* align_1024(uint8_t* p) {
 
 __device__ __forceinline__ float bf16_bits_to_float(uint32_t h) { return __uint_as_float(h << 16); }
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256); addresses must be 32-byte aligned
+__device__ __forceinline__ void ldg256(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+               "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -216,14 +228,22 @@ gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int i = 0; i < 4; ++i) bz[i] = __ldg(b4 + i);
           }
           if (p.mask) {
-            const uint4* m4 = reinterpret_cast<const uint4*>(p.mask + pix * p.ldMask + col);
-            mk[0] = __ldg(m4);
-            mk[1] = __ldg(m4 + 1);
+            const bf16* mp = p.mask + pix * p.ldMask + col;
+            if (p.vec_ok == 2) {
+              ldg256(mp, mk[0], mk[1]);
+            } else {
+              mk[0] = __ldg(reinterpret_cast<const uint4*>(mp));
+              mk[1] = __ldg(reinterpret_cast<const uint4*>(mp) + 1);
+            }
           }
           if (p.residual) {
-            const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + rpix * p.ldRes + col);
-            rs[0] = __ldg(r4);
-            rs[1] = __ldg(r4 + 1);
+            const bf16* rp = p.residual + rpix * p.ldRes + col;
+            if (p.vec_ok == 2) {
+              ldg256(rp, rs[0], rs[1]);
+            } else {
+              rs[0] = __ldg(reinterpret_cast<const uint4*>(rp));
+              rs[1] = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
+            }
           }
         }
         tmem_ld_wait();  // .sync.aligned: executed by the whole warp at a convergent point
@@ -274,13 +294,23 @@ gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             a.z = pack_bf16x2(f[4], f[5]);   a.w = pack_bf16x2(f[6], f[7]);
             b.x = pack_bf16x2(f[8], f[9]);   b.y = pack_bf16x2(f[10], f[11]);
             b.z = pack_bf16x2(f[12], f[13]); b.w = pack_bf16x2(f[14], f[15]);
-            reinterpret_cast<uint4*>(o)[0] = a;
-            reinterpret_cast<uint4*>(o)[1] = b;
+            if (p.vec_ok == 2) {
+              stg256(o, a, b);
+            } else {
+              reinterpret_cast<uint4*>(o)[0] = a;
+              reinterpret_cast<uint4*>(o)[1] = b;
+            }
           } else {
             float* o = reinterpret_cast<float*>(p.out) + pix * p.ldOut + col;
+            if (p.vec_ok == 2) {
+              const uint4* fv = reinterpret_cast<const uint4*>(f);
+              stg256(o, fv[0], fv[1]);
+              stg256(o + 8, fv[2], fv[3]);
+            } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              reinterpret_cast<float4*>(o)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+              for (int i = 0; i < 4; ++i)
+                reinterpret_cast<float4*>(o)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+            }
           }
         } else {
           if (active) {
@@ -620,7 +650,12 @@ extern "C" int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* w
   bool vec = aligned16(y) && (d->out_dtype == 0 ? (d->ldOut % 8 == 0) : (d->ldOut % 4 == 0));
   if (residual) vec = vec && aligned16(residual) && (d->ldRes % 8 == 0);
   if (mask) vec = vec && aligned16(mask) && (d->ldMask % 8 == 0);
-  p.vec_ok = vec ? 1 : 0;
+  // 32-byte accesses when every pointer and pitch allows it (16 bf16 / 8 fp32 columns per access)
+  auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
+  bool vec32 = vec && al32(y) && (d->out_dtype == 0 ? (d->ldOut % 16 == 0) : (d->ldOut % 8 == 0));
+  if (residual) vec32 = vec32 && al32(residual) && (d->ldRes % 16 == 0);
+  if (mask) vec32 = vec32 && al32(mask) && (d->ldMask % 16 == 0);
+  p.vec_ok = vec32 ? 2 : (vec ? 1 : 0);
 
   CUtensorMap tmA, tmB;
   {

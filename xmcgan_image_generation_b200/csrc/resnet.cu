@@ -66,45 +66,71 @@ __global__ void resize_bilinear_bwd_kernel(const float* __restrict__ dout, int N
   }
 }
 
-// Input gradient of the 7x7 stride-2 stem (SAME padding low=2): one thread per input pixel.
-// wk: bf16 [Cout][7*56] with k = kh*56 + kw*8 + c (the packed forward weights), dy: bf16 [N,Ho,Wo,Cout].
-__global__ void stem_dgrad_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ wk, int N, int T, int Ho,
-                                  int Cout, int pad_lo, float* __restrict__ dimg) {
+// Input gradient of the 7x7 stride-2 stem (SAME padding low=2). One thread computes 4 input pixels of the same column
+// parity in one row (x, x+2, x+4, x+6): they use the same filter taps, so every weight vector read from shared memory
+// feeds 4 pixels. wk: bf16 [Cout][7*56] with k = kh*56 + kw*8 + c (the packed forward weights), dy: [N,Ho,Ho,Cout].
+__global__ void __launch_bounds__(128)
+stem_dgrad_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ wk, int N, int T, int Ho, int Cout, int pad_lo,
+                  float* __restrict__ dimg) {
   extern __shared__ float ws[];  // [7][7][3][Cout]
   for (int t = threadIdx.x; t < 49 * 3 * Cout; t += blockDim.x) {
     const int co = t % Cout, c = (t / Cout) % 3, kw = (t / (Cout * 3)) % 7, kh = t / (Cout * 21);
     ws[t] = __bfloat162float(wk[(long long)co * 392 + kh * 56 + kw * 8 + c]);
   }
   __syncthreads();
-  const long long total = (long long)N * T * T;
+  const int groups_x = (T + 7) / 8;             // 8 consecutive pixels = 2 parities x 4 pixels
+  const long long total = (long long)N * T * groups_x * 2;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int x = idx % T, y = (idx / T) % T;
-  const long long n = idx / ((long long)T * T);
-  const int yp = y + pad_lo, xp = x + pad_lo;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  const int par = idx & 1;
+  const int gx = (idx >> 1) % groups_x;
+  const int y = (idx / (2 * groups_x)) % T;
+  const long long n = idx / ((long long)2 * groups_x * T);
+  const int x0 = gx * 8 + par;                  // pixels x0, x0+2, x0+4, x0+6
+  const int yp = y + pad_lo;
+  const int xp0 = x0 + pad_lo;
+  float acc[4][3];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = 0.f;
   for (int ho = max(0, (yp - 5) >> 1); ho <= min(Ho - 1, yp >> 1); ++ho) {
     const int kh = yp - 2 * ho;
     if (kh < 0 || kh > 6) continue;
-    for (int wo = max(0, (xp - 5) >> 1); wo <= min(Ho - 1, xp >> 1); ++wo) {
-      const int kw = xp - 2 * wo;
-      if (kw < 0 || kw > 6) continue;
-      const bf16* g = dy + ((n * Ho + ho) * Ho + wo) * Cout;
+    // taps for this column parity: kw = (xp0 & 1) + 2j, output column of pixel i: wo = (xp0 >> 1) + i - j
+    for (int j = 0; j < 4; ++j) {
+      const int kw = (xp0 & 1) + 2 * j;
+      if (kw > 6) continue;
       const float* w = ws + ((kh * 7 + kw) * 3) * Cout;
+      const bf16* grow = dy + (n * Ho + ho) * (long long)Ho * Cout;
       for (int co = 0; co < Cout; co += 8) {
-        float f[8];
-        load8(g + co, f);
+        const float4 wa0 = *reinterpret_cast<const float4*>(w + co), wb0 = *reinterpret_cast<const float4*>(w + co + 4);
+        const float4 wa1 = *reinterpret_cast<const float4*>(w + Cout + co);
+        const float4 wb1 = *reinterpret_cast<const float4*>(w + Cout + co + 4);
+        const float4 wa2 = *reinterpret_cast<const float4*>(w + 2 * Cout + co);
+        const float4 wb2 = *reinterpret_cast<const float4*>(w + 2 * Cout + co + 4);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          a0 += f[i] * w[co + i];
-          a1 += f[i] * w[Cout + co + i];
-          a2 += f[i] * w[2 * Cout + co + i];
+        for (int i = 0; i < 4; ++i) {
+          const int wo = (xp0 >> 1) + i - j;
+          if (wo < 0 || wo >= Ho) continue;
+          float f[8];
+          load8(grow + (long long)wo * Cout + co, f);
+          acc[i][0] += f[0] * wa0.x + f[1] * wa0.y + f[2] * wa0.z + f[3] * wa0.w + f[4] * wb0.x + f[5] * wb0.y +
+                       f[6] * wb0.z + f[7] * wb0.w;
+          acc[i][1] += f[0] * wa1.x + f[1] * wa1.y + f[2] * wa1.z + f[3] * wa1.w + f[4] * wb1.x + f[5] * wb1.y +
+                       f[6] * wb1.z + f[7] * wb1.w;
+          acc[i][2] += f[0] * wa2.x + f[1] * wa2.y + f[2] * wa2.z + f[3] * wa2.w + f[4] * wb2.x + f[5] * wb2.y +
+                       f[6] * wb2.z + f[7] * wb2.w;
         }
       }
     }
   }
-  float* o = dimg + idx * 3;
-  o[0] = a0; o[1] = a1; o[2] = a2;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int x = x0 + 2 * i;
+    if (x < T) {
+      float* o = dimg + ((n * T + y) * T + x) * 3;
+      o[0] = acc[i][0]; o[1] = acc[i][1]; o[2] = acc[i][2];
+    }
+  }
 }
 
 // flax nn.max_pool(x, (3,3), strides=(2,2), padding="SAME") on an even-sized map: window rows 2ho..2ho+2 (pad high)
@@ -235,7 +261,7 @@ extern "C" int xmc_stem_dgrad(const void* dy, const void* wk, int N, int T, int 
   if (!dy || !wk || !dimg || N < 1 || Cout < 8 || (Cout % 8)) return XMC_EINVAL;
   const size_t smem = (size_t)49 * 3 * Cout * sizeof(float);
   if (smem > 48 * 1024) return XMC_EINVAL;
-  const long long total = (long long)N * T * T;
+  const long long total = (long long)N * T * ((T + 7) / 8) * 2;
   stem_dgrad_kernel<<<(unsigned)ceil_div_ll(total, 128), 128, smem, (cudaStream_t)stream>>>(
       (const bf16*)dy, (const bf16*)wk, N, T, Ho, Cout, pad_lo, dimg);
   XMC_LAUNCH_CHECK();
