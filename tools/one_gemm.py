@@ -1,0 +1,28 @@
+"""GPU debugging aid: runs one conv_fwd shape in a loop (for ncu). python tools/one_gemm.py N H W C k Cout [res] [relu]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from xmcgan_image_generation_b200 import ops
+
+N, H, W, C, k, Cout = (int(a) for a in sys.argv[1:7])
+flags = sys.argv[7:]
+x = (torch.randn(N, H, W, C, device="cuda") * 0.5).to(torch.bfloat16)
+wk = (torch.randn(Cout, k * k * C, device="cuda") * 0.05).to(torch.bfloat16)
+bias = torch.randn(Cout, device="cuda")
+res = (torch.randn(N, H, W, Cout, device="cuda")).to(torch.bfloat16) if "res" in flags else None
+for _ in range(3):
+  y = ops.conv_fwd(x, wk, k, Cout, bias=bias, residual=res, relu="relu" in flags)
+torch.cuda.synchronize()
+s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+s.record()
+for _ in range(10):
+  y = ops.conv_fwd(x, wk, k, Cout, bias=bias, residual=res, relu="relu" in flags)
+e.record()
+torch.cuda.synchronize()
+ms = s.elapsed_time(e) / 10
+fl = 2.0 * N * H * W * k * k * C * Cout
+by = (x.numel() + y.numel() + (res.numel() if res is not None else 0)) * 2
+print(f"{ms*1e3:.1f} us  {fl/ms/1e9:.1f} TFLOP/s  {by/ms/1e6:.1f} GB/s (algorithmic bytes)")
