@@ -105,6 +105,8 @@ class GemmTimer:
       view = kw.get("view")
       if view is not None:  # ResNet stem: 7x7x3 taps per output pixel (the packed window has 8-channel padding)
         ho, wo, taps, c = view["Hout"], view["Wout"], 49, 3
+      if kw.get("subpixel"):  # four parities x 2x2 taps per input pixel
+        taps = 16
       flops = 2.0 * x.shape[0] * ho * wo * taps * c * cout
       s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
       s.record()
@@ -117,7 +119,7 @@ class GemmTimer:
     def wgrad(xa, xb, kh, out, **kw):
       ca = kw.get("ca") or xa.shape[3]
       cb = kw.get("cb") or xb.shape[3]
-      flops = 2.0 * xa.shape[0] * xa.shape[1] * xa.shape[2] * kh * kh * ca * cb
+      flops = 2.0 * xa.shape[0] * xa.shape[1] * xa.shape[2] * (16 if kw.get("subpixel") else kh * kh) * ca * cb
       s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
       s.record()
       r = timer._wgrad(xa, xb, kh, out, **kw)

@@ -63,6 +63,11 @@ typedef struct {
   int strideH, strideW, Hin, Win;
   long long pitchW, pitchH, pitchN;
   int mask_last;           /* 1: apply the mask after the residual add: v = (alpha*acc + bias + residual) masked */
+  /* 1: sub-pixel mode = conv3x3(nearest_upsample2x(x)) computed as four 2x2 convolutions on x (one per output
+   * parity) with pre-summed weights: KH=KW=2, pad=1, wk = [4*Cout][4*C] from xmc_subpixel_prep, y is the
+   * [N,2H,2W,Cout] tensor and output pixel (2h+a, 2w+b) belongs to parity a*2+b. 2.25x fewer FLOPs than the
+   * reference's upsample-then-conv (xmcgan/nets/common.py:151-153,178-179), identical in exact arithmetic. */
+  int subpixel;
 } XmcConvDesc;
 
 int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* wk, const float* bias, const void* residual,
@@ -83,6 +88,10 @@ typedef struct {
   int ldOut;
   long long out_tap_stride, out_batch_stride;
   float alpha;
+  /* 1: weight gradient of conv3x3(nearest_upsample2x(xa)): xa is the low-resolution [N,H,W,Ca] input, xb the
+   * [N,2H,2W,Cb] output gradient (read with stride 2, one parity per tap); the 16 parity/tap products are added to
+   * the 9 taps of dw ([3][3][Ca][Cb]) they belong to. KH=KW=3, out_mode 0. */
+  int subpixel;
 } XmcWgradDesc;
 
 int xmc_conv2d_wgrad(const XmcWgradDesc* d, const void* xa, const void* xb, void* dw, void* stream);
@@ -178,6 +187,10 @@ int xmc_sn_backward(const XmcSnEntry* table_dev, int n, const float* params, flo
 int xmc_prep_weights(const XmcPrepEntry* table_dev, int n, int total_tiles, const float* params,
                      const float* sn_scalars, int n_sn, void* arena, float* bias_arena, const float* cscale,
                      void* stream);
+/* Weights of the sub-pixel form of conv3x3(nearest_upsample2x(x)) (xmcgan/nets/common.py:151-153,178-179) from the
+ * fp32 HWIO kernel w [3][3][Cin][Cout]: wf bf16 [4*Cout][4*Cin] for XmcConvDesc.subpixel, vd bf16 [Cin][16*Cout] for
+ * the input gradient (= xmc_conv2d_fwd with KH=KW=4, stride 2, pad 1 over the [N,2H,2W,Cout] output gradient). */
+int xmc_subpixel_prep(const float* w, int Cin, int Cout, void* wf, void* vd, void* stream);
 /* flax.optim.Adam.apply_gradient (weight_decay 0) in place on flat buffers, gradient pre-scaled by grad_scale
  * (1/world after a sum all-reduce == lax.pmean); optional polyak EMA of the updated parameters
  * (xmcgan/xmc_gan.py:172-177,252). bias_corr = 1 - beta^t. n must be a multiple of 4. */

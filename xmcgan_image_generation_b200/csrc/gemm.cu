@@ -32,6 +32,7 @@ struct FwdParams {
   int N, H, W, Cout;
   int batched;
   int strideH, strideW;
+  int parities;  // 1, or 4: sub-pixel mode (nearest-2x-upsample fused into a 3x3 conv as four 2x2 convs)
   uint32_t stage_tx_bytes;
   uint32_t idesc;
   void* out;
@@ -53,6 +54,7 @@ struct WgradParams {
   int Ca, Cb;
   int batched;
   int items_per_split, total_items;
+  int subpixel;         // 1: 16 parity taps (a,dh,b,dw); B is the 2x up-sampled gradient read with stride 2
   uint32_t slab_bytes;  // bytes one TMA box writes
   uint32_t idesc;
   void* out;
@@ -125,7 +127,7 @@ gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-  const int total_tiles = m_tiles * p.n_tiles;
+  const int total_tiles = m_tiles * p.n_tiles * p.parities;
   const int taps = p.KH * p.KW;
   const int kiters = taps * p.cchunks;
 
@@ -136,20 +138,26 @@ gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+        // tile -> (m tile, parity, n tile); parity (a,b) of sub-pixel mode: output pixel (2h+a, 2w+b) reads the 2x2
+        // input window starting at (h-(1-a), w-(1-b)) and the parity's own summed weights (rows par*Cout.. of B)
+        const int nt = tile % p.n_tiles;
+        const int t2 = tile / p.n_tiles;
+        const int par = t2 % p.parities, mt = t2 / p.parities;
         const int iw = mt % p.tiles_w;
         const int ih = (mt / p.tiles_w) % p.tiles_h;
         const int in = mt / (p.tiles_w * p.tiles_h);
         const int w0 = iw * p.tw, h0 = ih * p.th, n0 = in * p.tn;
+        const int pad_h = p.pad_h - (par >> 1), pad_w = p.pad_w - (par & 1);
         for (int tap = 0; tap < taps; ++tap) {
           const int kh = tap / p.KW, kw = tap - kh * p.KW;
           for (int c = 0; c < p.cchunks; ++c) {
             mbar_wait(empty_bar(stage), phase ^ 1);
             mbar_arrive_expect_tx(full_bar(stage), p.stage_tx_bytes);
             const uint32_t sa = sbase + stage * kStageBytes;
-            tma_load_4d(sa, &tmA, full_bar(stage), c * 64, w0 * p.strideW + kw - p.pad_w,
-                        h0 * p.strideH + kh - p.pad_h, n0);
-            tma_load_3d(sa + kABytes, &tmB, full_bar(stage), tap * p.C + c * 64, nt * p.BN, p.batched ? n0 : 0);
+            tma_load_4d(sa, &tmA, full_bar(stage), c * 64, w0 * p.strideW + kw - pad_w,
+                        h0 * p.strideH + kh - pad_h, n0);
+            tma_load_3d(sa + kABytes, &tmB, full_bar(stage), tap * p.C + c * 64, par * p.Cout + nt * p.BN,
+                        p.batched ? n0 : 0);
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -193,7 +201,9 @@ gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+      const int nt = tile % p.n_tiles;
+      const int t2 = tile / p.n_tiles;
+      const int par = t2 % p.parities, mt = t2 / p.parities;
       const int iw = mt % p.tiles_w;
       const int ih = (mt / p.tiles_w) % p.tiles_h;
       const int in = mt / (p.tiles_w * p.tiles_h);
@@ -201,7 +211,10 @@ gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int rw = r % p.tw, rh = (r / p.tw) % p.th, rn = r / (p.tw * p.th);
       const int w = iw * p.tw + rw, h = ih * p.th + rh, n = in * p.tn + rn;
       const bool row_ok = (rn < p.tn) && (n < p.N) && (h < p.H) && (w < p.W);
-      const long long pix = ((long long)n * p.H + h) * p.W + w;
+      // sub-pixel mode scatters the tile into the 2x up-sampled output at (2h+a, 2w+b)
+      const long long pix = p.parities == 1
+                                ? ((long long)n * p.H + h) * p.W + w
+                                : ((long long)n * 2 * p.H + 2 * h + (par >> 1)) * (2 * p.W) + 2 * w + (par & 1);
       long long rpix = 0;
       if (p.residual) {
         const int Hs = p.H >> p.res_shift, Ws = p.W >> p.res_shift;
@@ -419,7 +432,16 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
         int split, bz, tap, mt, nt;
         decode(item, split, bz, tap, mt, nt);
-        const int kh = tap / p.KW, kw = tap - kh * p.KW;
+        // A shift (ah, aw) and B start (bh + bs*h0, bw + bs*w0) of this tap
+        int ah, aw, bh = 0, bw = 0, bs = 1;
+        if (p.subpixel) {
+          // tap = a<<3 | dh<<2 | b<<1 | dw : x[i+dh-(1-a), j+dw-(1-b)] * dy[2i+a, 2j+b]
+          const int a = (tap >> 3) & 1, dh = (tap >> 2) & 1, b = (tap >> 1) & 1, dw = tap & 1;
+          ah = dh - (1 - a); aw = dw - (1 - b); bh = a; bw = b; bs = 2;
+        } else {
+          const int kh = tap / p.KW, kw = tap - kh * p.KW;
+          ah = kh - p.pad_h; aw = kw - p.pad_w;
+        }
         const int j0 = split * p.chunks_per_split;
         const int j1 = min(p.total_chunks, j0 + p.chunks_per_split);
         const int m0 = mt * 128, n_off = nt * p.BN;
@@ -431,10 +453,11 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_wait(empty_bar(stage), phase ^ 1);
           mbar_arrive_expect_tx(full_bar(stage), tx);
           const uint32_t sa = sbase + stage * kStageBytes;
-          tma_load_4d(sa, &tmA, full_bar(stage), m0, w0 + kw - p.pad_w, h0 + kh - p.pad_h, n0);
-          tma_load_4d(sa + 8192, &tmA, full_bar(stage), m0 + 64, w0 + kw - p.pad_w, h0 + kh - p.pad_h, n0);
+          tma_load_4d(sa, &tmA, full_bar(stage), m0, w0 + aw, h0 + ah, n0);
+          tma_load_4d(sa + 8192, &tmA, full_bar(stage), m0 + 64, w0 + aw, h0 + ah, n0);
           for (int s = 0; s < p.nslabs; ++s)
-            tma_load_4d(sa + kABytes + s * 8192, &tmB, full_bar(stage), n_off + s * 64, w0, h0, n0);
+            tma_load_4d(sa + kABytes + s * 8192, &tmB, full_bar(stage), n_off + s * 64, bs * w0 + bw, bs * h0 + bh,
+                        n0);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -486,8 +509,20 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
-      const long long obase = (long long)bz * p.out_batch_stride + (long long)tap * p.out_tap_stride +
-                              (long long)m * p.ldOut;
+      // destinations: a plain tap writes its own [Ca][Cb] matrix; a sub-pixel parity tap (a,dh,b,dw) is the gradient of
+      // a SUM of 3x3 taps, W_a[dh] = sum_{kh in S(a,dh)} W[kh] with S(0,0)={0}, S(0,1)={1,2}, S(1,0)={0,1}, S(1,1)={2},
+      // so it is added to every (kh, kw) in S(a,dh) x S(b,dw)
+      int dest[4], ndest = 1;
+      dest[0] = tap;
+      if (p.subpixel) {
+        const int a = (tap >> 3) & 1, dh = (tap >> 2) & 1, b = (tap >> 1) & 1, dw = tap & 1;
+        const int kh0 = (a == 0) ? (dh == 0 ? 0 : 1) : (dh == 0 ? 0 : 2), nkh = (a != dh) ? 2 : 1;
+        const int kw0 = (b == 0) ? (dw == 0 ? 0 : 1) : (dw == 0 ? 0 : 2), nkw = (b != dw) ? 2 : 1;
+        ndest = 0;
+        for (int i = 0; i < nkh; ++i)
+          for (int j2 = 0; j2 < nkw; ++j2) dest[ndest++] = (kh0 + i) * 3 + kw0 + j2;
+      }
+      const long long obase0 = (long long)bz * p.out_batch_stride + (long long)m * p.ldOut;
       for (int c0 = 0; c0 < p.BN; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(t_addr + c0, v);
@@ -499,44 +534,47 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           float f[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
-          if (p.out_mode == 2) {
-            bf16* o = reinterpret_cast<bf16*>(p.out) + obase + col;
-            if (vec) {
-              uint4 a, b;
-              a.x = pack_bf16x2(f[0], f[1]);   a.y = pack_bf16x2(f[2], f[3]);
-              a.z = pack_bf16x2(f[4], f[5]);   a.w = pack_bf16x2(f[6], f[7]);
-              b.x = pack_bf16x2(f[8], f[9]);   b.y = pack_bf16x2(f[10], f[11]);
-              b.z = pack_bf16x2(f[12], f[13]); b.w = pack_bf16x2(f[14], f[15]);
-              reinterpret_cast<uint4*>(o)[0] = a;
-              reinterpret_cast<uint4*>(o)[1] = b;
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (i < nvalid) o[i] = __float2bfloat16(f[i]);
-            }
-          } else {
-            float* o = reinterpret_cast<float*>(p.out) + obase + col;
-            if (p.out_mode == 1) {
+          for (int di = 0; di < ndest; ++di) {
+            const long long obase = obase0 + (long long)dest[di] * p.out_tap_stride;
+            if (p.out_mode == 2) {
+              bf16* o = reinterpret_cast<bf16*>(p.out) + obase + col;
               if (vec) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                  reinterpret_cast<float4*>(o)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+                uint4 a, b;
+                a.x = pack_bf16x2(f[0], f[1]);   a.y = pack_bf16x2(f[2], f[3]);
+                a.z = pack_bf16x2(f[4], f[5]);   a.w = pack_bf16x2(f[6], f[7]);
+                b.x = pack_bf16x2(f[8], f[9]);   b.y = pack_bf16x2(f[10], f[11]);
+                b.z = pack_bf16x2(f[12], f[13]); b.w = pack_bf16x2(f[14], f[15]);
+                reinterpret_cast<uint4*>(o)[0] = a;
+                reinterpret_cast<uint4*>(o)[1] = b;
               } else {
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
-                  if (i < nvalid) o[i] = f[i];
+                  if (i < nvalid) o[i] = __float2bfloat16(f[i]);
               }
             } else {
-              if (vec) {
+              float* o = reinterpret_cast<float*>(p.out) + obase + col;
+              if (p.out_mode == 1) {
+                if (vec) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4 * i), "f"(f[4 * i]),
-                               "f"(f[4 * i + 1]), "f"(f[4 * i + 2]), "f"(f[4 * i + 3])
-                               : "memory");
+                  for (int i = 0; i < 4; ++i)
+                    reinterpret_cast<float4*>(o)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i)
+                    if (i < nvalid) o[i] = f[i];
+                }
               } else {
+                if (vec) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i)
-                  if (i < nvalid) atomicAdd(o + i, f[i]);
+                  for (int i = 0; i < 4; ++i)
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4 * i), "f"(f[4 * i]),
+                                 "f"(f[4 * i + 1]), "f"(f[4 * i + 2]), "f"(f[4 * i + 3])
+                                 : "memory");
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i)
+                    if (i < nvalid) atomicAdd(o + i, f[i]);
+                }
               }
             }
           }
@@ -631,6 +669,9 @@ extern "C" int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* w
   p.batched = d->batched;
   p.strideH = d->strideH > 0 ? d->strideH : 1;
   p.strideW = d->strideW > 0 ? d->strideW : 1;
+  p.parities = d->subpixel ? 4 : 1;
+  if (d->subpixel && (d->KH != 2 || d->KW != 2 || d->pad_h != 1 || d->pad_w != 1 || residual || mask || d->batched))
+    return XMC_EINVAL;
   if (p.strideH > 8 || p.strideW > 8) return XMC_EINVAL;
   p.tw = d->W < 128 ? d->W : 128;
   p.th = 128 / p.tw; if (p.th > d->H) p.th = d->H;
@@ -675,7 +716,7 @@ extern "C" int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* w
   }
   {
     const int nb = d->batched ? d->N : 1;
-    uint64_t dims[3] = {(uint64_t)d->KH * d->KW * d->C, (uint64_t)d->Cout, (uint64_t)nb};
+    uint64_t dims[3] = {(uint64_t)d->KH * d->KW * d->C, (uint64_t)d->Cout * p.parities, (uint64_t)nb};
     uint64_t sb = d->batched ? (uint64_t)d->strideB_batch * 2 : (uint64_t)d->ldB * 2 * d->Cout;
     uint64_t str[2] = {(uint64_t)d->ldB * 2, sb};
     uint32_t box[3] = {64, (uint32_t)p.BN, 1};
@@ -686,7 +727,7 @@ extern "C" int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* w
     XMC_CUDA_CHECK(cudaFuncSetAttribute(gemm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     g_attr_set_fwd = true;
   }
-  const int total = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
+  const int total = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles * p.parities;
   const int grid = total < num_sms() ? total : num_sms();
   gemm_fwd_kernel<<<grid, kThreadsFwd, kSmemBytes, (cudaStream_t)stream>>>(tmA, tmB, p);
   XMC_LAUNCH_CHECK();
@@ -713,7 +754,9 @@ extern "C" int xmc_conv2d_wgrad(const XmcWgradDesc* d, const void* xa, const voi
   p.n_tiles = ceil_div(d->Cb, p.BN);
   p.nslabs = ceil_div(p.BN, 64);
   const int m_tiles = ceil_div(d->Ca, 128);
-  const int taps = d->KH * d->KW;
+  if (d->subpixel && (d->KH != 3 || d->KW != 3 || d->out_mode != 0 || d->batched)) return XMC_EINVAL;
+  const int taps = d->subpixel ? 16 : d->KH * d->KW;
+  p.subpixel = d->subpixel ? 1 : 0;
   const int nbatch = d->batched ? d->N : 1;
   const int base_ctas = m_tiles * p.n_tiles * taps * nbatch;
   int ksplit = 1;
@@ -759,10 +802,15 @@ extern "C" int xmc_conv2d_wgrad(const XmcWgradDesc* d, const void* xa, const voi
     if (r) return r;
   }
   {
-    uint64_t dims[4] = {(uint64_t)d->Cb, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
-    uint64_t str[3] = {(uint64_t)d->ldB * 2, (uint64_t)d->ldB * 2 * d->W, (uint64_t)d->ldB * 2 * d->W * d->H};
-    uint32_t box[4] = {64, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.tn};
-    int r = make_tmap(&tmB, xb, 4, dims, str, box);
+    // sub-pixel mode: xb is the [N,2H,2W,Cb] gradient, traversed with stride 2 (one parity per tap)
+    const int bs = d->subpixel ? 2 : 1;
+    if (p.tw * bs > 256 || p.th * bs > 256) return XMC_EINVAL;
+    uint64_t dims[4] = {(uint64_t)d->Cb, (uint64_t)d->W * bs, (uint64_t)d->H * bs, (uint64_t)d->N};
+    uint64_t str[3] = {(uint64_t)d->ldB * 2, (uint64_t)d->ldB * 2 * d->W * bs,
+                       (uint64_t)d->ldB * 2 * d->W * bs * d->H * bs};
+    uint32_t box[4] = {64, (uint32_t)(p.tw * bs), (uint32_t)(p.th * bs), (uint32_t)p.tn};
+    uint32_t est[4] = {1, (uint32_t)bs, (uint32_t)bs, 1};
+    int r = make_tmap(&tmB, xb, 4, dims, str, box, est);
     if (r) return r;
   }
   if (!g_attr_set_wgrad) {

@@ -172,6 +172,48 @@ __global__ void prep_weights_kernel(const XmcPrepEntry* __restrict__ tab, int n,
   }
 }
 
+// ------------------------------------------------------------------------------------------------- sub-pixel prep
+// conv3x3(nearest_upsample2x(x)) == four 2x2 convolutions on x, one per output parity (a,b), whose weights are sums of
+// the 3x3 taps: W_a[dh] = sum_{kh in S(a,dh)} W[kh], S(0,0)={0}, S(0,1)={1,2}, S(1,0)={0,1}, S(1,1)={2} (same for
+// columns). Writes the forward matrix wf[(a*2+b)*Cout + co][(dh*2+dw)*Cin + ci] and the input-gradient matrix
+// vd[ci][(r*4+s)*Cout + co] of the equivalent 4x4 / stride-2 / pad-1 convolution over the output gradient, where
+// row offset r-1 in {-1,0,1,2} <-> (a,dh) = (1,1),(0,1),(1,0),(0,0).
+__global__ void subpixel_prep_kernel(const float* __restrict__ w, int Cin, int Cout, bf16* __restrict__ wf,
+                                     bf16* __restrict__ vd) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)Cin * Cout) return;
+  const int co = idx % Cout, ci = idx / Cout;
+  float k[3][3];
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) k[kh][kw] = w[((long long)(kh * 3 + kw) * Cin + ci) * Cout + co];
+  // row-combined: rc[a][dh][kw]
+  float rc[2][2][3];
+#pragma unroll
+  for (int kw = 0; kw < 3; ++kw) {
+    rc[0][0][kw] = k[0][kw];
+    rc[0][1][kw] = k[1][kw] + k[2][kw];
+    rc[1][0][kw] = k[0][kw] + k[1][kw];
+    rc[1][1][kw] = k[2][kw];
+  }
+  const int r_of[2][2] = {{3, 1}, {2, 0}};  // r_of[a][dh]
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int dw = 0; dw < 2; ++dw) {
+          const float* r = rc[a][dh];
+          const float v = (b == 0) ? (dw == 0 ? r[0] : r[1] + r[2]) : (dw == 0 ? r[0] + r[1] : r[2]);
+          const bf16 q = __float2bfloat16(v);
+          wf[((long long)((a * 2 + b) * Cout + co)) * (4 * Cin) + (dh * 2 + dw) * Cin + ci] = q;
+          vd[(long long)ci * (16 * Cout) + (r_of[a][dh] * 4 + r_of[b][dw]) * Cout + co] = q;
+        }
+}
+
 // ------------------------------------------------------------------------------------------------- Adam (+EMA)
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float inv_c1,
@@ -244,6 +286,15 @@ extern "C" int xmc_prep_weights(const XmcPrepEntry* table_dev, int n, int total_
   if (!table_dev || n < 1 || total_tiles < 1 || !params || !arena) return XMC_EINVAL;
   prep_weights_kernel<<<total_tiles, dim3(32, 8), 0, (cudaStream_t)stream>>>(table_dev, n, params, sn_scalars, n_sn,
                                                                             (bf16*)arena, bias_arena, cscale);
+  XMC_LAUNCH_CHECK();
+  return XMC_OK;
+}
+
+extern "C" int xmc_subpixel_prep(const float* w, int Cin, int Cout, void* wf, void* vd, void* stream) {
+  if (!w || !wf || !vd || Cin < 8 || Cout < 8 || (Cin % 8) || (Cout % 8)) return XMC_EINVAL;
+  const long long n = (long long)Cin * Cout;
+  subpixel_prep_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, (cudaStream_t)stream>>>(w, Cin, Cout, (bf16*)wf,
+                                                                                       (bf16*)vd);
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }

@@ -212,12 +212,23 @@ class GeneratorEngine:
     self.prep = _PrepTable()
     self.convs = {}
 
-    def add_conv(path, kh, cin_, cout_, dense=False):
+    self.subpixel = {}  # path -> (wf_off, vd_off): sub-pixel form of the convs that follow a nearest 2x upsample
+
+    def add_conv(path, kh, cin_, cout_, dense=False, subpixel=False):
       shape = (cin_, cout_) if dense else (kh, kh, cin_, cout_)
       w_off = L.add(path + ("kernel",), shape)
       b_off = L.add(path + ("bias",), (cout_,))
       taps = kh * kh
       ld_fwd, ld_dg = _r8(taps * cin_), _r8(taps * cout_)
+      if subpixel:
+        # conv3x3(upsample(x)) as four 2x2 convs on x: [4*Cout][4*Cin] forward and [Cin][16*Cout] dgrad matrices
+        wf_off = self.arena_size
+        self.arena_size += 4 * cout_ * 4 * cin_
+        vd_off = self.arena_size
+        self.arena_size += cin_ * 16 * cout_
+        self.subpixel[path] = (wf_off, vd_off)
+        self.convs[path] = ConvRec(path, kh, cin_, cout_, w_off, b_off, -1, ld_fwd, -1, ld_dg, -1)
+        return
       fwd_off = self.arena_size
       self.arena_size += _r8(cout_) * ld_fwd
       dg_off = self.arena_size
@@ -228,7 +239,7 @@ class GeneratorEngine:
     add_conv(("Dense_0",), 1, E, zd, dense=True)
     add_conv(("Dense_1",), 1, zd, c0 * 16, dense=True)
     for name, kind, bcin, bcout in blocks:
-      add_conv((name, "Conv_0"), 3, bcin, bcout)
+      add_conv((name, "Conv_0"), 3, bcin, bcout, subpixel=True)
       add_conv((name, "Conv_1"), 3, bcout, bcout)
       add_conv((name, "Conv_2"), 1, bcin, bcout)
     add_conv(("Conv_0",), 1, ch[1], E)
@@ -273,6 +284,10 @@ class GeneratorEngine:
     self._ensure()
     ops._call("xmc_prep_weights", self.prep.dev.data_ptr(), self.prep.n, self.prep.tiles, params.data_ptr(), None, 0,
               self.arena.data_ptr(), None, None, _lib.stream())
+    for path, (wf_off, vd_off) in self.subpixel.items():
+      rec = self.convs[path]
+      ops._call("xmc_subpixel_prep", params[rec.w_off:].data_ptr(), rec.cin, rec.cout,
+                self.arena[wf_off:].data_ptr(), self.arena[vd_off:].data_ptr(), _lib.stream())
 
   def _wk(self, rec):
     return self.arena[rec.fwd_off:]
@@ -337,8 +352,11 @@ class GeneratorEngine:
       _, g1, b1 = self.bn_index[bn1]
       r0, r1, r2 = (self.convs[(name, f"Conv_{i}")] for i in range(3))
       mr0 = self._bn(x, bn0, stats, new_stats, train)
-      u = ops.bn_apply(x, mr0, gb, Hc, g0, b0, True, True)
-      c1 = ops.conv_fwd(u, self._wk(r0), 3, bcout, bias=P[r0.b_off:], ldb=r0.ld_fwd)
+      # CBN -> relu at the block's input resolution; the nearest 2x upsample is folded into the next conv
+      # (sub-pixel form: four 2x2 convs, 2.25x fewer FLOPs, the up-sampled tensor is never materialised)
+      u = ops.bn_apply(x, mr0, gb, Hc, g0, b0, True, False)
+      wf_off, _ = self.subpixel[(name, "Conv_0")]
+      c1 = ops.conv_fwd(u, self.arena[wf_off:], 2, bcout, bias=P[r0.b_off:], ldb=4 * bcin, pad=1, subpixel=True)
       mr1 = self._bn(c1, bn1, stats, new_stats, train)
       h2 = ops.bn_apply(c1, mr1, gb, Hc, g1, b1, True, False)
       sc = ops.conv_fwd(x, self._wk(r2), 1, bcout, bias=P[r2.b_off:], ldb=r2.ld_fwd)
@@ -401,10 +419,13 @@ class GeneratorEngine:
       self._conv_wgrad(r1, sv["h2"], dout, grads)
       dh2 = ops.conv_fwd(dout, self._wd(r1), 3, bcout, ldb=r1.ld_dg)
       dc1 = ops.bn_bwd(dh2, sv["c1"], sv["mr1"], gb, dgb, sv["Hc"], g1, b1, True, False)
-      # conv1 (Conv_0)
-      self._conv_wgrad(r0, sv["u"], dc1, grads)
-      du = ops.conv_fwd(dc1, self._wd(r0), 3, bcin, ldb=r0.ld_dg)
-      dxa = ops.bn_bwd(du, sv["x"], sv["mr0"], gb, dgb, sv["Hc"], g0, b0, True, True)
+      # conv1 (Conv_0, sub-pixel form): weight gradient from the low-resolution input and the 2x gradient; input
+      # gradient = 4x4 / stride-2 / pad-1 convolution over the gradient, directly at the input resolution
+      ops.wgrad(sv["u"], dc1, 3, grads[r0.w_off:], out_mode=0, ld_out=bcout, tap_stride=bcin * bcout, subpixel=True)
+      ops.colsum(dc1, grads[r0.b_off:])
+      _, vd_off = self.subpixel[(name, "Conv_0")]
+      du = ops.conv_fwd(dc1, self.arena[vd_off:], 4, bcin, ldb=16 * bcout, stride=2, pad=1)
+      dxa = ops.bn_bwd(du, sv["x"], sv["mr0"], gb, dgb, sv["Hc"], g0, b0, True, False)
       # shortcut (Conv_2 at low resolution)
       dsc = ops.pool2(dout, scale=1.0)
       self._conv_wgrad(r2, sv["x"], dsc, grads)

@@ -44,7 +44,7 @@ def zeros(shape, dtype=F32):
 # ------------------------------------------------------------------------------------------------------------- GEMMs
 def conv_fwd(x, wk, kh, cout, *, bias=None, residual=None, res_shift=0, mask=None, relu=False, out=None,
              out_dtype=BF16, alpha=1.0, ldb=None, batched=False, stride_b=0, c=None, stride=1, pad=None,
-             mask_last=False, view=None):
+             mask_last=False, view=None, subpixel=False):
   """x: [N,H,W,>=C] bf16 view (channel-contiguous); wk: bf16 tensor whose data pointer is the [cout][kh*kh*C] K-major
   matrix (row pitch ldb). Returns y [N,H/stride,W/stride,cout] (or writes into the `out` view).
   stride=2 reads the input at (h*2+kh-pad, w*2+kw-pad) (XLA SAME: pad low = 0 for a 3x3 or 1x1 kernel on an even
@@ -66,6 +66,9 @@ def conv_fwd(x, wk, kh, cout, *, bias=None, residual=None, res_shift=0, mask=Non
     d.pitchW, d.pitchH, d.pitchN = view["pitchW"], view["pitchH"], view["pitchN"]
   H, W = d.H, d.W
   d.mask_last = 1 if mask_last else 0
+  if subpixel:  # four 2x2 convs writing the 2x up-sampled output (see XmcConvDesc.subpixel)
+    d.subpixel = 1
+    H, W = 2 * d.H, 2 * d.W
   d.Cout = cout
   d.ldB = ldb if ldb is not None else d.KH * d.KW * C
   d.batched = 1 if batched else 0
@@ -86,7 +89,7 @@ def conv_fwd(x, wk, kh, cout, *, bias=None, residual=None, res_shift=0, mask=Non
 
 
 def wgrad(xa, xb, kh, out, *, out_mode=0, batched=False, ld_out=None, tap_stride=None, batch_stride=0, alpha=1.0,
-          ca=None, cb=None):
+          ca=None, cb=None, subpixel=False):
   """out[b][tap][ca][cb] (+)= sum_pixels xa[p+shift][ca] * xb[p][cb]. xa, xb: [N,H,W,C*] bf16 views."""
   N, H, W = xa.shape[0], xa.shape[1], xa.shape[2]
   _check_dense_rows(xa)
@@ -104,6 +107,7 @@ def wgrad(xa, xb, kh, out, *, out_mode=0, batched=False, ld_out=None, tap_stride
   d.out_tap_stride = d.Ca * d.Cb if tap_stride is None else tap_stride
   d.out_batch_stride = batch_stride
   d.alpha = alpha
+  d.subpixel = 1 if subpixel else 0
   _call("xmc_conv2d_wgrad", ctypes.byref(d), ptr(xa), ptr(xb), ptr(out), stream())
   return out
 
