@@ -245,7 +245,10 @@ def run_b200(args):
   if dom:
     ach = gemm[dom]["tflop"] / (gemm[dom]["ms"] / 1e3)
     roofline = {"bound": "tensor", "kernel": dom, "achieved": round(ach, 1), "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": round(ach / peak_tf, 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(ach / peak_tf, 4), "traffic": None,
+                "traffic_note": "aggregate over launches of many shapes; per-shape ncu DRAM bytes (= algorithmic "
+                                "bytes, inputs read once) are in profiles/r01_gemm_shape_classes.md",
+                "peak_source": peak_src,
                 "launches_timed": gemm[dom]["launches"],
                 "share_of_step": round(gemm[dom]["ms"] / ms_dev, 3),
                 "all_gemm": {k: {"tflops": round(v["tflop"] / (v["ms"] / 1e3), 1), "ms_per_step":
