@@ -189,8 +189,9 @@ int xmc_prep_weights(const XmcPrepEntry* table_dev, int n, int total_tiles, cons
                      void* stream);
 /* Weights of the sub-pixel form of conv3x3(nearest_upsample2x(x)) (xmcgan/nets/common.py:151-153,178-179) from the
  * fp32 HWIO kernel w [3][3][Cin][Cout]: wf bf16 [4*Cout][4*Cin] for XmcConvDesc.subpixel, vd bf16 [Cin][16*Cout] for
- * the input gradient (= xmc_conv2d_fwd with KH=KW=4, stride 2, pad 1 over the [N,2H,2W,Cout] output gradient). */
-int xmc_subpixel_prep(const float* w, int Cin, int Cout, void* wf, void* vd, void* stream);
+ * the input gradient (= xmc_conv2d_fwd with KH=KW=4, stride 2, pad 1 over the [N,2H,2W,Cout] output gradient).
+ * scale: optional device scalar 1/(sigma+eps) of a spectrally normalised kernel (layers.py:221), NULL = 1. */
+int xmc_subpixel_prep(const float* w, const float* scale, int Cin, int Cout, void* wf, void* vd, void* stream);
 /* flax.optim.Adam.apply_gradient (weight_decay 0) in place on flat buffers, gradient pre-scaled by grad_scale
  * (1/world after a sum all-reduce == lax.pmean); optional polyak EMA of the updated parameters
  * (xmcgan/xmc_gan.py:172-177,252). bias_corr = 1 - beta^t. n must be a multiple of 4. */
@@ -246,6 +247,10 @@ int xmc_small_gemm_nn(const float* G, int transposed, const float* X, int n, int
                       int accumulate, void* stream);
 /* *loss_out = mean_i CE(row i) + mean_j CE(col j) with identity labels (losses.py:47-51); dlogits = weight*dloss/dlogits */
 int xmc_ce_sym(const float* logits, int n, float weight, float* loss_out, float* dlogits, void* stream);
+/* attention_lib.get_statistics (attention_lib.py:36-43) for both directions of an [n][n] logit matrix with identity
+ * labels: out[0] = accuracy (argmax == label, first maximum wins; bit-exact index op), out[1] = entropy. These side
+ * statistics are dead on the train path (XLA removes them); they exist for the functional API. */
+int xmc_ce_stats(const float* logits, int n, float* out, void* stream);
 /* losses.hinge_loss (losses.py:30-35) on logit = [real(B); fake(B)] and the two cotangents */
 int xmc_hinge(const float* logit, int B, float* d_loss, float* g_loss, float* dlogit_d, float* dlogit_g, void* stream);
 /* projection-discriminator logit (xmc_net.py:97-104): out[n] = <xpool[n], w1*inv_sigma + emb[n%B]> + b1 */

@@ -34,6 +34,8 @@ def cpu_variables(config, E=64, seed=1, bias_scale=0.1):
         n = int(torch.tensor(shape).prod())
         buf[off:off + n] = torch.randn(n, generator=gen) * bias_scale
   g_vars = {"params": g.layout.tree(bufs[0]), "batch_stats": g.stats_layout.tree(bufs[1])}
+  if g.sn:
+    g_vars["spectral_norm_stats"] = g.u_layout.tree(engine.init_flat(g.u_layout, seed + 5, engine._kind))
   d_vars = {"params": d.layout.tree(bufs[2]), "spectral_norm_stats": d.u_layout.tree(bufs[3])}
   return g, d, g_vars, d_vars
 

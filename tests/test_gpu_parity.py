@@ -218,6 +218,13 @@ def _build(config, E=64, seed=1):
   return g_vars, d_vars, g_params, g_stats, d_params, d_u
 
 
+def _g_u0(config, g_vars, E=64):
+  """The generator's spectral_norm_stats collection on the device (g_spectral_norm=True only)."""
+  *_, xmc_net = _mods()
+  lay = xmc_net.get_engine(config, "g", E).u_layout
+  return xmc_net.FlatTree(lay, xmc_net.as_flat(lay, g_vars["spectral_norm_stats"]))
+
+
 @gpu
 def test_generator_and_discriminator_apply_match_oracle():
   """Through the Flax-shaped module API. Image: 2e-2 rel-L2 (bf16 activations through 11 BN layers); logits 3e-2;
@@ -277,13 +284,13 @@ def _assert_grad_tree(got_tree, ref_tree, ref32_tree, tol):
 
 
 @gpu
-@pytest.mark.parametrize("variant", ["default", "no_sn", "no_word", "ragged", "px256"])
+@pytest.mark.parametrize("variant", ["default", "no_sn", "no_word", "ragged", "px256", "g_sn"])
 def test_both_pullbacks_match_oracle(variant):
   """d(d_loss)/d(params_d) and d(g_loss)/d(params_g) from ONE forward (xmc_gan.py:162-167) vs oracle autograd.
   Tolerance 6e-2 rel-L2 per leaf vs the bf16-policy oracle (bf16 storage of activation gradients), losses 2e-3."""
   _, engine, ops, _, _, xmc_net = _mods()
   kw = {"no_sn": dict(d_spectral_norm=False), "no_word": dict(word_contrastive=False),
-        "px256": dict(image_size=256, gf_dim=8, df_dim=8)}.get(variant, {})
+        "px256": dict(image_size=256, gf_dim=8, df_dim=8), "g_sn": dict(g_spectral_norm=True)}.get(variant, {})
   cfg = helpers.small_config(**kw)
   B = {"ragged": 3, "px256": 2}.get(variant, 4)
   # 256 px: one more block in G and D, batch 2, width 8 — the configuration most sensitive to bf16 perturbations
@@ -294,7 +301,9 @@ def test_both_pullbacks_match_oracle(variant):
   dev = xmc_net.batch_to_device(batch)
   g_eng, d_eng = xmc_net.get_engine(cfg, "g", 64), xmc_net.get_engine(cfg, "d", 64)
   S = cfg.image_size
-  g_eng.prep_weights(g_params.buf)
+  g_u = _g_u0(cfg, g_vars).buf if g_eng.sn else None
+  g_u_new = torch.empty_like(g_u) if g_eng.sn else None
+  g_eng.prep_weights(g_params.buf, g_u, g_u_new)
   u_new = torch.empty_like(d_u.buf)
   d_eng.prep_weights(d_params.buf, d_u.buf if d_eng.sn else None, u_new if d_eng.sn else None)
   all_images = ops.empty((2 * B, S, S, 3))
@@ -308,6 +317,7 @@ def test_both_pullbacks_match_oracle(variant):
   d_fake = d_eng.backward_g(dctx, d_params.buf)
   g_grads = torch.zeros_like(g_params.buf)
   g_eng.backward(gctx, d_fake, g_params.buf, g_grads)
+  g_eng.sn_backward(g_params.buf, g_grads, g_u_new)
   torch.cuda.synchronize()
   state = orc.make_state(g_vars, d_vars if d_eng.sn else {"params": d_vars["params"]})
   r = orc.d_losses_and_grads(state, batch, cfg, orc.Policy("bfloat16"), want_g=True)
@@ -494,7 +504,7 @@ def test_subpixel_conv_equals_upsample_then_conv(N, H, C, Cout):
   wf = ops.empty((4 * Cout, 4 * C))
   vd = ops.empty((C, 16 * Cout))
   kd = kern.detach().cuda().contiguous()
-  ops._call("xmc_subpixel_prep", kd.data_ptr(), C, Cout, wf.data_ptr(), vd.data_ptr(), _lib.stream())
+  ops._call("xmc_subpixel_prep", kd.data_ptr(), None, C, Cout, wf.data_ptr(), vd.data_ptr(), _lib.stream())
   xd = x.detach().cuda().to(torch.bfloat16)
   got = ops.conv_fwd(xd, wf, 2, Cout, bias=bias.cuda(), ldb=4 * C, pad=1, subpixel=True, out_dtype=torch.float32)
   assert got.shape == (N, 2 * H, 2 * H, Cout)
@@ -505,3 +515,63 @@ def test_subpixel_conv_equals_upsample_then_conv(N, H, C, Cout):
   dw = torch.zeros(9 * C * Cout, device="cuda")
   ops.wgrad(xd, dyd, 3, dw, out_mode=0, ld_out=Cout, tap_stride=C * Cout, subpixel=True)
   assert helpers.rel(dw.view(3, 3, C, Cout), kern.grad) < 1e-2
+
+
+@gpu
+def test_train_step_with_generator_spectral_norm():
+  """config.g_spectral_norm=True (xmc_net.py:176-191): every generator conv / dense is spectrally normalised, its u0
+  collection advances in train_g_d only (train_d discards the generator's new state, xmc_gan.py:225). One train_step vs
+  the oracle: metrics 5e-3, parameters 5e-3, generator u0 1e-3."""
+  _, engine, ops, train_utils, xmc_gan, xmc_net = _mods()
+  cfg = helpers.small_config(g_spectral_norm=True)
+  B = 3
+  g_vars, d_vars, g_params, g_stats, d_params, d_u = _build(cfg, seed=11)
+  g_u = _g_u0(cfg, g_vars)
+  batch = helpers.make_batch(2 * B, cfg, seed=12)
+  ostate = orc.make_state(g_vars, d_vars)
+  state = train_utils.TrainState(0, train_utils.Optimizer(g_params, cfg.g_lr, cfg.beta1, cfg.beta2),
+                                 train_utils.Optimizer(d_params, cfg.d_lr, cfg.beta1, cfg.beta2),
+                                 {"batch_stats": g_stats, "spectral_norm_stats": g_u}, {"spectral_norm_stats": d_u},
+                                 g_params.clone())
+  state, metrics = train_utils.train_step(None, state, batch, xmc_gan, None, None, cfg, {})
+  got = metrics.compute()
+  ostate, want = orc.train_step(ostate, batch, cfg, orc.Policy("bfloat16"))
+  scale = max(abs(v) for v in want.values())
+  for k in ("d_loss", "g_loss", "c_loss_d", "c_loss_g"):
+    assert abs(got[k] - want[k]) < 5e-3 * scale, (k, got[k], want[k])
+  pairs = [(state.g_optimizer.target, ostate["g_params"], 5e-3),
+           (state.generator_state["spectral_norm_stats"], ostate["generator_state"]["spectral_norm_stats"], 1e-3),
+           (state.generator_state["batch_stats"], ostate["generator_state"]["batch_stats"], 1e-2)]
+  for got_t, want_t, tol in pairs:
+    for (p, a), (_, b) in zip(orc.tree_leaves(got_t.to_cpu_tree()), orc.tree_leaves(want_t)):
+      assert helpers.rel(a, b) < tol, (p, helpers.rel(a, b))
+  # the module API carries the collection as well
+  import functools
+  gen = functools.partial(xmc_net.Generator, config=cfg)
+  v = gen(train=False).init(0, (batch, batch["z"]))
+  assert set(v) == {"params", "batch_stats", "spectral_norm_stats"}
+  img, new = gen(train=True).apply(v, (batch, batch["z"]), mutable=["batch_stats", "spectral_norm_stats"])
+  assert img.shape[0] == 2 * B and not torch.equal(new["spectral_norm_stats"].buf, v["spectral_norm_stats"].buf)
+
+
+@gpu
+@pytest.mark.parametrize("B", [3, 8])
+def test_accuracy_and_entropy_side_statistics(B):
+  """get_statistics (attention_lib.py:36-43) through contrastive_loss / word_loss: accuracy is an index op (argmax ==
+  label) and must be exact; entropy 1e-4 (InfoNCE, fp32 logits) / 2e-2 (word_loss, bf16 region operands)."""
+  from xmcgan_image_generation_b200.libml import attention_lib
+  torch.manual_seed(20 + B)
+  a, b = torch.randn(B, 96), torch.randn(B, 96)
+  a[: B // 2] = b[: B // 2] + 0.1 * torch.randn(B // 2, 96)   # some matched pairs, some not
+  _, wacc, went = orc.contrastive_loss(a, b)
+  _, acc, ent = attention_lib.contrastive_loss(a, b)
+  assert acc.item() == wacc.item()
+  assert abs(ent.item() - went.item()) < 1e-4 * max(1.0, abs(went.item()))
+  R, L, D = 256, 17, 64
+  img = _q(torch.randn(B, R, D))
+  words = torch.randn(B, L, D) * 0.5
+  max_len = torch.randint(1, L + 1, (B, 1)).float()
+  _, wacc, went = orc.word_loss(img, words, max_len)
+  _, acc, ent = attention_lib.word_loss(img, words, max_len)
+  assert abs(acc.item() - wacc.item()) <= 0.5 / B + 1e-6      # at most one near-tie flipped by bf16 operands
+  assert abs(ent.item() - went.item()) < 2e-2 * max(1.0, abs(went.item()))

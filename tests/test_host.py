@@ -62,7 +62,21 @@ def test_variable_tree_names_follow_flax_auto_naming():
   assert dp[("SpectralDense_1", "kernel")][1] == (768, 1536)
   assert dp[("SpectralConv_0", "kernel")][1] == (1, 1, 384, 768)
   assert d.u_layout.entries[("SpectralConv_0", "u0")][1] == (1, 768)
-  assert d.n_sn == 20
+  assert d.sntab.n == 20
+  # g_spectral_norm=True renames every conv / dense of the generator (also inside the conditional BatchNorms) and adds
+  # a spectral_norm_stats collection with one u0 per kernel (xmc_net.py:176-191, layers.py:86-91,203-208)
+  c.g_spectral_norm = True
+  gs = engine.GeneratorEngine(c)
+  sp = gs.layout.entries
+  assert sp[("SpectralDense_0", "kernel")][1] == (768, 128)
+  assert sp[("GenBlock_0", "ConditionalBatchNorm_0", "SpectralDense_1", "kernel")][1] == (256, 1536)
+  assert sp[("GenSpatialBlock_2", "LocalConditionalBatchNorm_1", "SpectralConv_0", "kernel")][1] == (1, 1, 1024, 96)
+  assert sp[("SpectralConv_1", "kernel")][1] == (3, 3, 96, 3)
+  assert not any(k.startswith(("Conv_", "Dense_")) for path in sp for k in path)
+  assert gs.layout.total == g.layout.total
+  assert gs.u_layout.entries[("GenBlock_1", "SpectralConv_2", "u0")][1] == (1, 768)
+  assert gs.u_layout.entries[("LocalConditionalBatchNorm_0", "SpectralConv_0", "u0")][1] == (1, 96)
+  assert gs.sntab.n == 2 + 15 + 2 + 8 + 14  # dense, block convs, attention / output conv, CBN dense, LCBN conv
 
 
 def test_layout_tree_roundtrip_and_alignment():

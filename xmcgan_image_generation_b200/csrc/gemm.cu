@@ -29,6 +29,7 @@ struct FwdParams {
   int tw, th, tn;
   int n_tiles, BN;
   int KH, KW, pad_h, pad_w, C, cchunks;
+  int last_mmas;  // K=16 MMA slices of the last 64-channel chunk that hold real channels
   int N, H, W, Cout;
   int batched;
   int strideH, strideW;
@@ -172,7 +173,12 @@ gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_wait(tempty_bar(acc), acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * 256;
+      int c = 0;
       for (int k = 0; k < kiters; ++k) {
+        // the last 64-channel chunk of a tap may be ragged (C = 96: 64 + 32): only the K=16 slices that hold real
+        // channels are issued, the TMA zero fill beyond C is never multiplied
+        const int nmma = (c == p.cchunks - 1) ? p.last_mmas : 4;
+        if (++c == p.cchunks) c = 0;
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         if (elect_one()) {
@@ -182,7 +188,7 @@ gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             // advance 16 K-elements = 32 bytes inside the 128B swizzle row: +2 in the (addr>>4) field
-            umma_bf16(d_tmem, adesc + 2 * j, bdesc + 2 * j, p.idesc, (k > 0 || j > 0) ? 1u : 0u);
+            if (j < nmma) umma_bf16(d_tmem, adesc + 2 * j, bdesc + 2 * j, p.idesc, (k > 0 || j > 0) ? 1u : 0u);
           }
           umma_commit(empty_bar(stage));
           if (k == kiters - 1) umma_commit(tfull_bar(acc));
@@ -666,6 +672,7 @@ extern "C" int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* w
   p.N = d->N; p.H = d->H; p.W = d->W; p.C = d->C; p.Cout = d->Cout;
   p.KH = d->KH; p.KW = d->KW; p.pad_h = d->pad_h; p.pad_w = d->pad_w;
   p.cchunks = ceil_div(d->C, 64);
+  p.last_mmas = ceil_div(d->C - (p.cchunks - 1) * 64, 16);
   p.batched = d->batched;
   p.strideH = d->strideH > 0 ? d->strideH : 1;
   p.strideW = d->strideW > 0 ? d->strideW : 1;

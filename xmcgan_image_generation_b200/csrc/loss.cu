@@ -70,6 +70,40 @@ __global__ void ce_sym_kernel(const float* __restrict__ logits, int n, float wei
   }
 }
 
+// get_statistics (attention_lib.py:36-43) of a square logit matrix with identity labels, both directions at once:
+// out[0] = accuracy = 0.5 * (mean_i [argmax_j logits[i][j] == i] + mean_j [argmax_i logits[i][j] == j])  (first maximum
+// wins, as jnp.argmax), out[1] = entropy = 0.5 * (mean row entropy + mean column entropy) with -sum p log(p + 1e-8).
+__global__ void ce_stats_kernel(const float* __restrict__ logits, int n, float* __restrict__ out) {
+  __shared__ float red[32];
+  float hits = 0.f, ent = 0.f;
+  for (int t = threadIdx.x; t < 2 * n; t += blockDim.x) {
+    const bool is_col = t >= n;
+    const int k = is_col ? t - n : t;
+    float mx = -3.0e38f;
+    int am = 0;
+    for (int q = 0; q < n; ++q) {
+      const float l = is_col ? logits[(long long)q * n + k] : logits[(long long)k * n + q];
+      if (l > mx) { mx = l; am = q; }
+    }
+    float s = 0.f;
+    for (int q = 0; q < n; ++q) s += expf((is_col ? logits[(long long)q * n + k] : logits[(long long)k * n + q]) - mx);
+    const float inv = 1.f / s;
+    float e = 0.f;
+    for (int q = 0; q < n; ++q) {
+      const float pr = expf((is_col ? logits[(long long)q * n + k] : logits[(long long)k * n + q]) - mx) * inv;
+      e -= pr * logf(pr + 1e-8f);
+    }
+    hits += (am == k) ? 1.f : 0.f;
+    ent += e;
+  }
+  hits = block_sum(hits, red);
+  ent = block_sum(ent, red);
+  if (threadIdx.x == 0) {
+    out[0] = 0.5f * hits / (float)n;
+    out[1] = 0.5f * ent / (float)n;
+  }
+}
+
 // hinge (losses.py:30-35): d = mean(relu(1-real) + relu(1+fake)), g = -mean(fake). logit = [real(B); fake(B)].
 __global__ void hinge_kernel(const float* __restrict__ logit, int B, float* __restrict__ d_loss,
                              float* __restrict__ g_loss, float* __restrict__ dlogit_d, float* __restrict__ dlogit_g) {
@@ -179,6 +213,13 @@ extern "C" int xmc_ce_sym(const float* logits, int n, float weight, float* loss_
   if (!logits || !loss_out || n < 1 || n > 2048) return XMC_EINVAL;
   const size_t smem = (size_t)(2 * n + 32) * sizeof(float);
   ce_sym_kernel<<<1, 512, smem, (cudaStream_t)stream>>>(logits, n, weight, loss_out, dlogits);
+  XMC_LAUNCH_CHECK();
+  return XMC_OK;
+}
+
+extern "C" int xmc_ce_stats(const float* logits, int n, float* out, void* stream) {
+  if (!logits || !out || n < 1) return XMC_EINVAL;
+  ce_stats_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(logits, n, out);
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }

@@ -178,16 +178,17 @@ __global__ void prep_weights_kernel(const XmcPrepEntry* __restrict__ tab, int n,
 // columns). Writes the forward matrix wf[(a*2+b)*Cout + co][(dh*2+dw)*Cin + ci] and the input-gradient matrix
 // vd[ci][(r*4+s)*Cout + co] of the equivalent 4x4 / stride-2 / pad-1 convolution over the output gradient, where
 // row offset r-1 in {-1,0,1,2} <-> (a,dh) = (1,1),(0,1),(1,0),(0,0).
-__global__ void subpixel_prep_kernel(const float* __restrict__ w, int Cin, int Cout, bf16* __restrict__ wf,
-                                     bf16* __restrict__ vd) {
+__global__ void subpixel_prep_kernel(const float* __restrict__ w, const float* __restrict__ scale, int Cin, int Cout,
+                                     bf16* __restrict__ wf, bf16* __restrict__ vd) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)Cin * Cout) return;
   const int co = idx % Cout, ci = idx / Cout;
+  const float sc = scale ? *scale : 1.f;
   float k[3][3];
 #pragma unroll
   for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-    for (int kw = 0; kw < 3; ++kw) k[kh][kw] = w[((long long)(kh * 3 + kw) * Cin + ci) * Cout + co];
+    for (int kw = 0; kw < 3; ++kw) k[kh][kw] = w[((long long)(kh * 3 + kw) * Cin + ci) * Cout + co] * sc;
   // row-combined: rc[a][dh][kw]
   float rc[2][2][3];
 #pragma unroll
@@ -290,11 +291,12 @@ extern "C" int xmc_prep_weights(const XmcPrepEntry* table_dev, int n, int total_
   return XMC_OK;
 }
 
-extern "C" int xmc_subpixel_prep(const float* w, int Cin, int Cout, void* wf, void* vd, void* stream) {
+extern "C" int xmc_subpixel_prep(const float* w, const float* scale, int Cin, int Cout, void* wf, void* vd,
+                                 void* stream) {
   if (!w || !wf || !vd || Cin < 8 || Cout < 8 || (Cin % 8) || (Cout % 8)) return XMC_EINVAL;
   const long long n = (long long)Cin * Cout;
-  subpixel_prep_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, (cudaStream_t)stream>>>(w, Cin, Cout, (bf16*)wf,
-                                                                                       (bf16*)vd);
+  subpixel_prep_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, (cudaStream_t)stream>>>(w, scale, Cin, Cout,
+                                                                                       (bf16*)wf, (bf16*)vd);
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }

@@ -129,6 +129,57 @@ class _PrepTable:
     self.n = len(self.entries)
 
 
+class _SnTable:
+  """Device table + workspaces for the multi-tensor spectral-norm kernels (xmc_sn_forward / xmc_sn_backward): one
+  entry per SpectralConv / SpectralDense (layers.py:49-113,125-241), u0 of every layer in one flat `u_layout`."""
+
+  def __init__(self):
+    self.entries = []
+    self.u_layout = Layout()
+    self._t = self._s = self._rb = self._ct = self._eb = 0
+    self.dev = None
+
+  def add(self, path, w_off, rows, cols):
+    """Registers a [rows, cols] kernel at params[w_off:]; returns its slot."""
+    slot = len(self.entries)
+    e = _lib.SnEntry()
+    e.w_off, e.t_off, e.s_off, e.u_off = w_off, self._t, self._s, self.u_layout.add(path + ("u0",), (1, cols))
+    e.rows, e.cols = rows, cols
+    e.row_block_begin, e.col_tile_begin, e.elem_block_begin = self._rb, self._ct, self._eb
+    self._t += _r4(rows)
+    self._s += _r4(cols)
+    self._rb += (rows + 7) // 8
+    self._ct += ((rows + 255) // 256) * ((cols + 31) // 32)
+    self._eb += (rows * cols + 2047) // 2048
+    self.entries.append(e)
+    return slot
+
+  @property
+  def n(self):
+    return len(self.entries)
+
+  def upload(self):
+    arr = (_lib.SnEntry * self.n)(*self.entries)
+    self.dev = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone().cuda()
+    self.t_ws = torch.zeros(self._t, device="cuda")
+    self.s_ws = torch.zeros(self._s, device="cuda")
+    self.scalars = torch.zeros(4 * self.n, device="cuda")
+
+  def forward(self, params, u0, u0_new):
+    """One power-iteration step for every layer: u0_new, and 1/(sigma+eps) into scalars[2n + slot]."""
+    ops._call("xmc_sn_forward", self.dev.data_ptr(), self.n, 1e-10, params.data_ptr(), u0.data_ptr(),
+              u0_new.data_ptr(), self.t_ws.data_ptr(), self.s_ws.data_ptr(), self._s, self.scalars.data_ptr(),
+              self._rb, self._ct, _lib.stream(), launches=5)
+
+  def backward(self, params, grads, u0_new):
+    """grads holds d/dW~ for every registered kernel -> d/dW in place (sigma is differentiable, u/v are not)."""
+    ops._call("xmc_sn_backward", self.dev.data_ptr(), self.n, params.data_ptr(), grads.data_ptr(),
+              self.t_ws.data_ptr(), u0_new.data_ptr(), self.scalars.data_ptr(), self._eb, _lib.stream(), launches=3)
+
+  def inv_sigma(self, slot):
+    return self.scalars[2 * self.n + slot:]
+
+
 # ======================================================================================================================
 # Generator
 # ======================================================================================================================
@@ -136,8 +187,6 @@ class GeneratorEngine:
   """xmc_net.Generator (xmc_net.py:145-248)."""
 
   def __init__(self, config, embedding_dim=768):
-    if config.g_spectral_norm:
-      raise NotImplementedError("g_spectral_norm=True is not built yet (reference default is False, coco_xmc.py:58)")
     if config.batch_norm_group_size > 0:
       raise NotImplementedError("grouped cross-replica BatchNorm is not built yet (default -1, coco_xmc.py:44)")
     if config.image_size == 256:
@@ -147,6 +196,12 @@ class GeneratorEngine:
     else:
       raise ValueError(f"image_size {config.image_size} is not supported (reference: xmc_net.py:202-205)")
     self.config = config
+    # g_spectral_norm switches EVERY conv / dense of the generator, including the gamma / beta layers inside
+    # (Local)ConditionalBatchNorm, to the spectral variants (xmc_net.py:176-191, layers.py:244-273)
+    self.sn = bool(config.g_spectral_norm)
+    self.cpre = cp = "SpectralConv" if self.sn else "Conv"
+    self.dpre = dp = "SpectralDense" if self.sn else "Dense"
+    self.sntab = _SnTable() if self.sn else None
     self.E = E = embedding_dim
     self.zd = zd = config.z_dim
     self.cd = cd = 2 * zd
@@ -195,18 +250,18 @@ class GeneratorEngine:
     L = self.layout = Layout()
     self.lcbn_bias_off = L.total
     for prefix, C, goff, boff in self.lcbn:
-      assert L.add(prefix + ("Conv_0", "bias"), (C,)) == self.lcbn_bias_off + goff
-      assert L.add(prefix + ("Conv_1", "bias"), (C,)) == self.lcbn_bias_off + boff
+      assert L.add(prefix + (cp + "_0", "bias"), (C,)) == self.lcbn_bias_off + goff
+      assert L.add(prefix + (cp + "_1", "bias"), (C,)) == self.lcbn_bias_off + boff
     self.cbn_bias_off = L.total
     for prefix, C, goff, boff in self.cbn:
-      assert L.add(prefix + ("Dense_0", "bias"), (C,)) == self.cbn_bias_off + goff
-      assert L.add(prefix + ("Dense_1", "bias"), (C,)) == self.cbn_bias_off + boff
+      assert L.add(prefix + (dp + "_0", "bias"), (C,)) == self.cbn_bias_off + goff
+      assert L.add(prefix + (dp + "_1", "bias"), (C,)) == self.cbn_bias_off + boff
     for prefix, C, goff, boff in self.lcbn:
-      L.add(prefix + ("Conv_0", "kernel"), (1, 1, scd, C))
-      L.add(prefix + ("Conv_1", "kernel"), (1, 1, scd, C))
+      L.add(prefix + (cp + "_0", "kernel"), (1, 1, scd, C))
+      L.add(prefix + (cp + "_1", "kernel"), (1, 1, scd, C))
     for prefix, C, goff, boff in self.cbn:
-      L.add(prefix + ("Dense_0", "kernel"), (cd, C))
-      L.add(prefix + ("Dense_1", "kernel"), (cd, C))
+      L.add(prefix + (dp + "_0", "kernel"), (cd, C))
+      L.add(prefix + (dp + "_1", "kernel"), (cd, C))
 
     self.arena_size = 0
     self.prep = _PrepTable()
@@ -219,6 +274,7 @@ class GeneratorEngine:
       w_off = L.add(path + ("kernel",), shape)
       b_off = L.add(path + ("bias",), (cout_,))
       taps = kh * kh
+      slot = self.sntab.add(path, w_off, taps * cin_, cout_) if self.sn else -1
       ld_fwd, ld_dg = _r8(taps * cin_), _r8(taps * cout_)
       if subpixel:
         # conv3x3(upsample(x)) as four 2x2 convs on x: [4*Cout][4*Cin] forward and [Cin][16*Cout] dgrad matrices
@@ -227,23 +283,24 @@ class GeneratorEngine:
         vd_off = self.arena_size
         self.arena_size += cin_ * 16 * cout_
         self.subpixel[path] = (wf_off, vd_off)
-        self.convs[path] = ConvRec(path, kh, cin_, cout_, w_off, b_off, -1, ld_fwd, -1, ld_dg, -1)
+        self.convs[path] = ConvRec(path, kh, cin_, cout_, w_off, b_off, -1, ld_fwd, -1, ld_dg, slot)
         return
       fwd_off = self.arena_size
       self.arena_size += _r8(cout_) * ld_fwd
       dg_off = self.arena_size
       self.arena_size += _r8(cin_) * ld_dg
-      self.prep.add(w_off, taps, cin_, cout_, fwd_off, ld_fwd, dg_off, ld_dg, -1)
-      self.convs[path] = ConvRec(path, kh, cin_, cout_, w_off, b_off, fwd_off, ld_fwd, dg_off, ld_dg, -1)
+      self.prep.add(w_off, taps, cin_, cout_, fwd_off, ld_fwd, dg_off, ld_dg, slot)
+      self.convs[path] = ConvRec(path, kh, cin_, cout_, w_off, b_off, fwd_off, ld_fwd, dg_off, ld_dg, slot)
 
-    add_conv(("Dense_0",), 1, E, zd, dense=True)
-    add_conv(("Dense_1",), 1, zd, c0 * 16, dense=True)
+    # registration order = the reference's call order (xmc_net.py:209-246): Flax auto-numbers modules per class
+    add_conv((dp + "_0",), 1, E, zd, dense=True)
+    add_conv((dp + "_1",), 1, zd, c0 * 16, dense=True)
     for name, kind, bcin, bcout in blocks:
-      add_conv((name, "Conv_0"), 3, bcin, bcout, subpixel=True)
-      add_conv((name, "Conv_1"), 3, bcout, bcout)
-      add_conv((name, "Conv_2"), 1, bcin, bcout)
-    add_conv(("Conv_0",), 1, ch[1], E)
-    add_conv(("Conv_1",), 3, self.c_last, 3)
+      add_conv((name, cp + "_0"), 3, bcin, bcout, subpixel=True)
+      add_conv((name, cp + "_1"), 3, bcout, bcout)
+      add_conv((name, cp + "_2"), 1, bcin, bcout)
+    add_conv((cp + "_0",), 1, ch[1], E)
+    add_conv((cp + "_1",), 3, self.c_last, 3)
 
     # concatenated matrices: forward [N*][K] rows per layer, dgrad [K][N*] column slices
     self.cbn_fwd_off = self.arena_size
@@ -255,13 +312,16 @@ class GeneratorEngine:
     self.lcbn_dg_off = self.arena_size
     self.arena_size += scd * self.NL
     for prefix, C, goff, boff in self.cbn:
-      for leaf, o in (("Dense_0", goff), ("Dense_1", boff)):
-        self.prep.add(L.off(prefix + (leaf, "kernel")), 1, cd, C, self.cbn_fwd_off + o * cd, cd,
-                      self.cbn_dg_off + o, self.NC, -1)
+      for leaf, o in ((dp + "_0", goff), (dp + "_1", boff)):
+        w_off = L.off(prefix + (leaf, "kernel"))
+        slot = self.sntab.add(prefix + (leaf,), w_off, cd, C) if self.sn else -1
+        self.prep.add(w_off, 1, cd, C, self.cbn_fwd_off + o * cd, cd, self.cbn_dg_off + o, self.NC, slot)
     for prefix, C, goff, boff in self.lcbn:
-      for leaf, o in (("Conv_0", goff), ("Conv_1", boff)):
-        self.prep.add(L.off(prefix + (leaf, "kernel")), 1, scd, C, self.lcbn_fwd_off + o * scd, scd,
-                      self.lcbn_dg_off + o, self.NL, -1)
+      for leaf, o in ((cp + "_0", goff), (cp + "_1", boff)):
+        w_off = L.off(prefix + (leaf, "kernel"))
+        slot = self.sntab.add(prefix + (leaf,), w_off, scd, C) if self.sn else -1
+        self.prep.add(w_off, 1, scd, C, self.lcbn_fwd_off + o * scd, scd, self.lcbn_dg_off + o, self.NL, slot)
+    self.u_layout = self.sntab.u_layout if self.sn else Layout()
 
     # ---- batch_stats layout ------------------------------------------------------------------------------------
     S = self.stats_layout = Layout()
@@ -270,24 +330,47 @@ class GeneratorEngine:
       S.add(prefix + ("BatchNorm_0", "var"), (C,))
     self.bn_index = {prefix: (C, goff, boff) for prefix, C, goff, boff in self.cbn + self.lcbn}
     self.arena = None
+    self.prepped_for = None  # (data_ptr, version) of the parameter buffer the bf16 arena currently mirrors
 
   # ------------------------------------------------------------------------------------------------------------
   def init_params(self, seed):
     return init_flat(self.layout, seed, _kind).cuda(), init_flat(self.stats_layout, seed + 1, _kind).cuda()
 
+  def init_u0(self, seed):
+    return init_flat(self.u_layout, seed, _kind).cuda()
+
   def _ensure(self):
     if self.arena is None:
       self.arena = torch.zeros(self.arena_size, device="cuda", dtype=BF16)
       self.prep.upload()
+      if self.sn:
+        self.sntab.upload()
 
-  def prep_weights(self, params):
+  def prep_weights(self, params, u0=None, u0_new=None):
+    """bf16 weight copies of `params`; with g_spectral_norm one power-iteration step first (u0 -> u0_new)."""
     self._ensure()
-    ops._call("xmc_prep_weights", self.prep.dev.data_ptr(), self.prep.n, self.prep.tiles, params.data_ptr(), None, 0,
+    if self.sn:
+      if u0 is None or u0_new is None:
+        raise ValueError("g_spectral_norm=True: the spectral_norm_stats collection (u0) is required")
+      self.sntab.forward(params, u0, u0_new)
+    ops._call("xmc_prep_weights", self.prep.dev.data_ptr(), self.prep.n, self.prep.tiles, params.data_ptr(),
+              self.sntab.scalars.data_ptr() if self.sn else None, self.sntab.n if self.sn else 0,
               self.arena.data_ptr(), None, None, _lib.stream())
     for path, (wf_off, vd_off) in self.subpixel.items():
       rec = self.convs[path]
-      ops._call("xmc_subpixel_prep", params[rec.w_off:].data_ptr(), rec.cin, rec.cout,
+      scale = self.sntab.inv_sigma(rec.sn).data_ptr() if self.sn else None
+      ops._call("xmc_subpixel_prep", params[rec.w_off:].data_ptr(), scale, rec.cin, rec.cout,
                 self.arena[wf_off:].data_ptr(), self.arena[vd_off:].data_ptr(), _lib.stream())
+    self.prepped_for = self.prep_key(params, u0_new)
+
+  def prep_key(self, params, u0_new=None):
+    """Identity of what the bf16 arena mirrors: parameter buffer + its torch version (+ where the new u0 went).
+    Kernels that update the parameters through raw pointers (xmc_adam) must reset `prepped_for` themselves."""
+    return (params.data_ptr(), params._version, u0_new.data_ptr() if (self.sn and u0_new is not None) else 0)
+
+  def sn_backward(self, params, grads, u0_new):
+    if self.sn:
+      self.sntab.backward(params, grads, u0_new)
 
   def _wk(self, rec):
     return self.arena[rec.fwd_off:]
@@ -321,10 +404,10 @@ class GeneratorEngine:
 
     cond_bf = ops.cast_to_bf16(cond)
     gc = ops.empty((B, cd))
-    r = self.convs[("Dense_0",)]
+    r = self.convs[(self.dpre + "_0",)]
     ops.conv_fwd(as4(cond_bf), self._wk(r), 1, zd, bias=P[r.b_off:], out=as4(gc[:, :zd]), ldb=r.ld_fwd)
     ops.cast_to_bf16(z.reshape(B, zd), gc[:, zd:])
-    r = self.convs[("Dense_1",)]
+    r = self.convs[(self.dpre + "_1",)]
     x = ops.conv_fwd(as4(gc[:, zd:]), self._wk(r), 1, r.cout, bias=P[r.b_off:], ldb=r.ld_fwd)
     x = x.view(B, 4, 4, self.c0)
     gbC = ops.conv_fwd(as4(gc), self.arena[self.cbn_fwd_off:], 1, self.NC, bias=P[self.cbn_bias_off:],
@@ -335,7 +418,7 @@ class GeneratorEngine:
     for name, kind, bcin, bcout in self.blocks:
       if kind == "lcbn" and Hc == 1:
         # ---- word-region attention at 16x16 and the spatial condition (xmc_net.py:220-235) ---------------------
-        r = self.convs[("Conv_0",)]
+        r = self.convs[(self.cpre + "_0",)]
         xq = ops.conv_fwd(x, self._wk(r), 1, E, bias=P[r.b_off:], ldb=r.ld_fwd)
         R = xq.shape[1] * xq.shape[2]
         what, _ = ops.l2norm_rows(words.reshape(B * Lw, E))
@@ -350,12 +433,12 @@ class GeneratorEngine:
       bn1 = (name, ("ConditionalBatchNorm_1" if kind == "cbn" else "LocalConditionalBatchNorm_1"))
       _, g0, b0 = self.bn_index[bn0]
       _, g1, b1 = self.bn_index[bn1]
-      r0, r1, r2 = (self.convs[(name, f"Conv_{i}")] for i in range(3))
+      r0, r1, r2 = (self.convs[(name, f"{self.cpre}_{i}")] for i in range(3))
       mr0 = self._bn(x, bn0, stats, new_stats, train)
       # CBN -> relu at the block's input resolution; the nearest 2x upsample is folded into the next conv
       # (sub-pixel form: four 2x2 convs, 2.25x fewer FLOPs, the up-sampled tensor is never materialised)
       u = ops.bn_apply(x, mr0, gb, Hc, g0, b0, True, False)
-      wf_off, _ = self.subpixel[(name, "Conv_0")]
+      wf_off, _ = self.subpixel[(name, self.cpre + "_0")]
       c1 = ops.conv_fwd(u, self.arena[wf_off:], 2, bcout, bias=P[r0.b_off:], ldb=4 * bcin, pad=1, subpixel=True)
       mr1 = self._bn(c1, bn1, stats, new_stats, train)
       h2 = ops.bn_apply(c1, mr1, gb, Hc, g1, b1, True, False)
@@ -367,7 +450,7 @@ class GeneratorEngine:
     _, gf_, bf_ = self.bn_index[bnf]
     mrf = self._bn(x, bnf, stats, new_stats, train)
     hf = ops.bn_apply(x, mrf, gbL, Hc, gf_, bf_, True, False)
-    r = self.convs[("Conv_1",)]
+    r = self.convs[(self.cpre + "_1",)]
     S = x.shape[1]
     img = ops.empty((B, S, S, 3), F32)
     ops._call("xmc_conv_c3_out", hf.data_ptr(), self._wk(r).data_ptr(), r.ld_fwd, P[r.b_off:].data_ptr(), B, S, S,
@@ -392,7 +475,7 @@ class GeneratorEngine:
     # output head: tanh, conv3x3 (C -> 3)
     dpre = ops.empty((B, S, S, 3))
     ops._call("xmc_tanh01_bwd", d_img.data_ptr(), ctx["img"].data_ptr(), d_img.numel(), dpre.data_ptr(), _lib.stream())
-    r = self.convs[("Conv_1",)]
+    r = self.convs[(self.cpre + "_1",)]
     C = self.c_last
     ops._call("xmc_wgrad_c3", dpre.data_ptr(), ctx["hf"].data_ptr(), B, S, S, C, 3, 3, 1, C * 3, 1, 3,
               grads[r.w_off:].data_ptr(), _lib.stream())
@@ -410,7 +493,7 @@ class GeneratorEngine:
       bn1 = (name, ("ConditionalBatchNorm_1" if kind == "cbn" else "LocalConditionalBatchNorm_1"))
       _, g0, b0 = self.bn_index[bn0]
       _, g1, b1 = self.bn_index[bn1]
-      r0, r1, r2 = (self.convs[(name, f"Conv_{i}")] for i in range(3))
+      r0, r1, r2 = (self.convs[(name, f"{self.cpre}_{i}")] for i in range(3))
       if kind == "cbn" and dx16_extra is None:
         # leaving the spatial part: finish everything that hangs off the 16x16 tensor (attention, spatial cond)
         dx16_extra = True
@@ -423,7 +506,7 @@ class GeneratorEngine:
       # gradient = 4x4 / stride-2 / pad-1 convolution over the gradient, directly at the input resolution
       ops.wgrad(sv["u"], dc1, 3, grads[r0.w_off:], out_mode=0, ld_out=bcout, tap_stride=bcin * bcout, subpixel=True)
       ops.colsum(dc1, grads[r0.b_off:])
-      _, vd_off = self.subpixel[(name, "Conv_0")]
+      _, vd_off = self.subpixel[(name, self.cpre + "_0")]
       du = ops.conv_fwd(dc1, self.arena[vd_off:], 4, bcin, ldb=16 * bcout, stride=2, pad=1)
       dxa = ops.bn_bwd(du, sv["x"], sv["mr0"], gb, dgb, sv["Hc"], g0, b0, True, False)
       # shortcut (Conv_2 at low resolution)
@@ -436,18 +519,18 @@ class GeneratorEngine:
     dgbC_bf = ops.cast_to_bf16(dgbC)
     L = self.layout
     for prefix, Cc, goff, boff in self.cbn:
-      for leaf, o in (("Dense_0", goff), ("Dense_1", boff)):
+      for leaf, o in ((self.dpre + "_0", goff), (self.dpre + "_1", boff)):
         ops.wgrad(as4(gc), as4(dgbC_bf[:, o:o + Cc]), 1, grads[L.off(prefix + (leaf, "kernel")):], out_mode=0,
                   ld_out=Cc, tap_stride=cd * Cc)
     ops.colsum(dgbC_bf, grads[self.cbn_bias_off:])
     dgc = ops.conv_fwd(as4(dgbC_bf), self.arena[self.cbn_dg_off:], 1, cd, ldb=self.NC, out_dtype=F32).view(B, cd)
     ops.sum_rows(ctx["dspatial"][:, E:], B, R, dgc, accumulate=True)
     dgc_bf = ops.cast_to_bf16(dgc)
-    r = self.convs[("Dense_0",)]
+    r = self.convs[(self.dpre + "_0",)]
     ops.wgrad(as4(ctx["cond_bf"]), as4(dgc_bf[:, :zd]), 1, grads[r.w_off:], out_mode=0, ld_out=zd, tap_stride=E * zd)
     ops.colsum(dgc_bf[:, :zd], grads[r.b_off:])
     # Dense_1 (z -> 4x4xC0); d(out) = input gradient of GenBlock_0
-    r = self.convs[("Dense_1",)]
+    r = self.convs[(self.dpre + "_1",)]
     dx0 = dout.view(B, r.cout)
     ops.wgrad(as4(gc[:, zd:]), as4(dx0), 1, grads[r.w_off:], out_mode=0, ld_out=r.cout, tap_stride=zd * r.cout)
     ops.colsum(dx0, grads[r.b_off:])
@@ -460,7 +543,7 @@ class GeneratorEngine:
     spatial = ctx["spatial"]
     dgbL_bf = ops.cast_to_bf16(dgbL)
     for prefix, Cc, goff, boff in self.lcbn:
-      for leaf, o in (("Conv_0", goff), ("Conv_1", boff)):
+      for leaf, o in ((self.cpre + "_0", goff), (self.cpre + "_1", boff)):
         ops.wgrad(as4(spatial), as4(dgbL_bf[:, o:o + Cc]), 1, grads[L.off(prefix + (leaf, "kernel")):], out_mode=0,
                   ld_out=Cc, tap_stride=scd * Cc)
     ops.colsum(dgbL_bf, grads[self.lcbn_bias_off:])
@@ -468,7 +551,7 @@ class GeneratorEngine:
     ctx["dspatial"] = dspatial
     xq = ctx["xq"]
     dq = ops.attention_g_bwd(dspatial, xq.view(B, R, E), ctx["what"].view(B, ctx["Lw"], E), ctx["attn"], self.gamma)
-    r = self.convs[("Conv_0",)]
+    r = self.convs[(self.cpre + "_0",)]
     dq4 = dq.view(xq.shape)
     self._conv_wgrad(r, ctx["x16"], dq4, grads)
     return ops.conv_fwd(dq4, self._wd(r), 1, r.cin, residual=dx16, ldb=r.ld_dg)
@@ -480,12 +563,15 @@ class GeneratorEngine:
 class Contrastive:
   """attention_lib.contrastive_loss (attention_lib.py:46-79) on fp32 features a (image_feat), b (cond_feat)."""
 
-  def __init__(self, a, b, slot, temperature=0.1):
+  def __init__(self, a, b, slot, temperature=0.1, stats=None):
+    """stats: optional fp32[2] device view receiving (accuracy, entropy) of attention_lib.py:75-78."""
     self.inv_t = 1.0 / temperature
     self.ah, self.ainv = ops.l2norm_rows(a)
     self.bh, self.binv = ops.l2norm_rows(b)
     logits = ops.small_gemm_nt(self.ah, self.bh, self.inv_t)
     self.dlogits = ops.ce_sym(logits, slot)
+    if stats is not None:
+      ops.ce_stats(logits, stats)
 
   def bwd_a(self, out, accumulate=True):
     dah = ops.small_gemm_nn(self.dlogits, False, self.bh, self.inv_t)
@@ -519,7 +605,8 @@ class WordLoss:
   """attention_lib.word_loss (attention_lib.py:130-191) with gamma1=gamma2=5, gamma3=50. R: [B, regions, E] bf16."""
   G1, G2, G3 = 5.0, 5.0, 50.0
 
-  def __init__(self, R, ws, slot):
+  def __init__(self, R, ws, slot, stats=None):
+    """stats: optional fp32[2] device view receiving (accuracy, entropy) of attention_lib.py:183-190."""
     B, Rn, E = R.shape
     self.ws, self.B, self.Rn, self.E = ws, B, Rn, E
     BL, ldS = ws.BL, ws.ldS
@@ -543,6 +630,8 @@ class WordLoss:
     ops._call("xmc_wl_sim", self.cos.data_ptr(), ws.max_len.data_ptr(), B, ws.Lw, self.G2, self.G3,
               self.sim.data_ptr(), self.pw.data_ptr(), _lib.stream())
     self.dsim = ops.ce_sym(self.sim, slot)
+    if stats is not None:
+      ops.ce_stats(self.sim, stats)
 
   def bwd(self):
     """Returns d(loss)/dR as bf16 [B*regions, E]."""
@@ -589,34 +678,18 @@ class DiscriminatorEngine:
     if df % 8:
       raise ValueError("df_dim must be a multiple of 8")
     L = self.layout = Layout()
-    U = self.u_layout = Layout()
+    self.sntab = _SnTable() if self.sn else None
+    self.u_layout = self.sntab.u_layout if self.sn else Layout()
     self.arena_size = 0
     self.prep = _PrepTable()
     self.convs = {}
-    self.sn_entries = []
-    self._rb = self._ct = self._eb = 0
-    self._t = self._s = 0
 
     def add_conv(path, kh, cin_, cout_, dense=False, prep=True):
       shape = (cin_, cout_) if dense else (kh, kh, cin_, cout_)
       w_off = L.add(path + ("kernel",), shape)
       b_off = L.add(path + ("bias",), (cout_,))
       taps = kh * kh
-      slot = -1
-      if self.sn:
-        slot = len(self.sn_entries)
-        u_off = U.add(path + ("u0",), (1, cout_))
-        e = _lib.SnEntry()
-        rows = taps * cin_
-        e.w_off, e.t_off, e.s_off, e.u_off = w_off, self._t, self._s, u_off
-        e.rows, e.cols = rows, cout_
-        e.row_block_begin, e.col_tile_begin, e.elem_block_begin = self._rb, self._ct, self._eb
-        self._t += _r4(rows)
-        self._s += _r4(cout_)
-        self._rb += (rows + 7) // 8
-        self._ct += ((rows + 255) // 256) * ((cout_ + 31) // 32)
-        self._eb += (rows * cout_ + 2047) // 2048
-        self.sn_entries.append(e)
+      slot = self.sntab.add(path, w_off, taps * cin_, cout_) if self.sn else -1
       ld_fwd, ld_dg = _r8(taps * cin_), _r8(taps * cout_)
       fwd_off = dg_off = -1
       if prep:
@@ -658,7 +731,6 @@ class DiscriminatorEngine:
       if self.cond_channels is None:
         raise ValueError("no discriminator feature map of size cond_size")
       add_conv((cp + "_0",), 1, self.cond_channels, E)
-    self.n_sn = len(self.sn_entries)
     self.arena = None
 
   def init_params(self, seed):
@@ -669,28 +741,20 @@ class DiscriminatorEngine:
       self.arena = torch.zeros(self.arena_size, device="cuda", dtype=BF16)
       self.prep.upload()
       if self.sn:
-        arr = (_lib.SnEntry * self.n_sn)(*self.sn_entries)
-        self.sn_dev = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone().cuda()
-        self.t_ws = torch.zeros(self._t, device="cuda")
-        self.s_ws = torch.zeros(self._s, device="cuda")
-        self.scalars = torch.zeros(4 * self.n_sn, device="cuda")
+        self.sntab.upload()
 
   def prep_weights(self, params, u0, u0_new):
     """Spectral normalisation (one power-iteration step, new u0 written to u0_new) + bf16 weight copies."""
     self._ensure()
     if self.sn:
-      ops._call("xmc_sn_forward", self.sn_dev.data_ptr(), self.n_sn, 1e-10, params.data_ptr(), u0.data_ptr(),
-                u0_new.data_ptr(), self.t_ws.data_ptr(), self.s_ws.data_ptr(), self._s, self.scalars.data_ptr(),
-                self._rb, self._ct, _lib.stream(), launches=5)
+      self.sntab.forward(params, u0, u0_new)
     ops._call("xmc_prep_weights", self.prep.dev.data_ptr(), self.prep.n, self.prep.tiles, params.data_ptr(),
-              self.scalars.data_ptr() if self.sn else None, self.n_sn, self.arena.data_ptr(), None, None,
-              _lib.stream())
+              self.sntab.scalars.data_ptr() if self.sn else None, self.sntab.n if self.sn else 0,
+              self.arena.data_ptr(), None, None, _lib.stream())
 
   def sn_backward(self, params, grads, u0_new):
     if self.sn:
-      ops._call("xmc_sn_backward", self.sn_dev.data_ptr(), self.n_sn, params.data_ptr(), grads.data_ptr(),
-                self.t_ws.data_ptr(), u0_new.data_ptr(), self.scalars.data_ptr(), self._eb, _lib.stream(),
-                launches=3)
+      self.sntab.backward(params, grads, u0_new)
 
   def _wk(self, rec):
     return self.arena[rec.fwd_off:]
@@ -699,11 +763,14 @@ class DiscriminatorEngine:
     return self.arena[rec.dg_off:]
 
   def _inv_sigma(self, rec):
-    return self.scalars[2 * self.n_sn + rec.sn:] if self.sn else None
+    return self.sntab.inv_sigma(rec.sn) if self.sn else None
 
   # ------------------------------------------------------------------------------------------------------------
-  def forward(self, params, images, batch, losses, need_g=True):
-    """images: bf16 [2B,S,S,3] (real first). Fills `losses` (fp32[16]) slots, returns (logit fp32 [2B], ctx)."""
+  def forward(self, params, images, batch, losses, need_g=True, stats=None):
+    """images: bf16 [2B,S,S,3] (real first). Fills `losses` (fp32[16]) slots, returns (logit fp32 [2B], ctx).
+    stats: optional fp32 [16,2] receiving (accuracy, entropy) per loss slot — the side statistics of
+    attention_lib.get_statistics, dead on the train path and therefore off by default."""
+    st = (lambda name: stats[LOSS_SLOTS[name]]) if stats is not None else (lambda name: None)
     P = params
     cfg = self.config
     cp = self.cpre
@@ -758,9 +825,9 @@ class DiscriminatorEngine:
     ctx.update(xpool=xpool, cond_bf=cond_bf, sent=sent, logit=logit, dl_d=dl_d, dl_g=dl_g)
     real_feat, fake_feat = xpool[:B], xpool[B:]
     if cfg.sentence_contrastive:
-      ctx["real_sent"] = Contrastive(real_feat, sent, losses[LOSS_SLOTS["real_sent"]:])
+      ctx["real_sent"] = Contrastive(real_feat, sent, losses[LOSS_SLOTS["real_sent"]:], stats=st("real_sent"))
       if need_g:
-        ctx["fake_sent"] = Contrastive(fake_feat, sent, losses[LOSS_SLOTS["fake_sent"]:])
+        ctx["fake_sent"] = Contrastive(fake_feat, sent, losses[LOSS_SLOTS["fake_sent"]:], stats=st("fake_sent"))
     if cfg.word_contrastive:
       rw = self.convs[(cp + "_0",)]
       xw = ops.conv_fwd(x_cond, self._wk(rw), 1, E, bias=P[rw.b_off:], ldb=rw.ld_fwd)
@@ -768,11 +835,12 @@ class DiscriminatorEngine:
       ws = WordShared(batch["embedding"], batch["max_len"])
       ctx["x_cond"] = x_cond
       ctx["xw_shape"] = xw.shape
-      ctx["real_word"] = WordLoss(xw[:B].view(B, Rn, E), ws, losses[LOSS_SLOTS["real_word"]:])
+      ctx["real_word"] = WordLoss(xw[:B].view(B, Rn, E), ws, losses[LOSS_SLOTS["real_word"]:], stats=st("real_word"))
       if need_g:
-        ctx["fake_word"] = WordLoss(xw[B:].view(B, Rn, E), ws, losses[LOSS_SLOTS["fake_word"]:])
+        ctx["fake_word"] = WordLoss(xw[B:].view(B, Rn, E), ws, losses[LOSS_SLOTS["fake_word"]:],
+                                    stats=st("fake_word"))
     if cfg.image_contrastive and need_g:
-      ctx["image"] = Contrastive(fake_feat, real_feat, losses[LOSS_SLOTS["image"]:])
+      ctx["image"] = Contrastive(fake_feat, real_feat, losses[LOSS_SLOTS["image"]:], stats=st("image"))
     return logit, ctx
 
   # ------------------------------------------------------------------------------------------------------------

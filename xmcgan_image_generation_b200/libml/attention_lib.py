@@ -1,6 +1,7 @@
 """Counterparts of xmcgan/libml/attention_lib.py with the same signatures, on CUDA tensors. Forward values only;
-train_step uses the same kernels plus their backward through engine.py. accuracy / entropy are dead on the train path
-(attention_lib.py:75-78,183-190, removed by XLA DCE) and are returned as None."""
+train_step uses the same kernels plus their backward through engine.py. Every loss returns the reference's
+(loss, accuracy, entropy) triple (attention_lib.py:75-78,183-190); train_step itself never reads accuracy / entropy
+(XLA removes them there) and skips them."""
 import torch
 
 from .. import engine as _engine
@@ -29,8 +30,9 @@ def contrastive_loss(image_feat, cond_feat, l2_norm=True, temperature=0.1, sync_
   if not l2_norm:
     raise NotImplementedError("l2_norm=False is not used on the hot path and is not built")
   slot = ops.empty(1, ops.F32)
-  _engine.Contrastive(_dev(image_feat), _dev(cond_feat), slot, temperature)
-  return slot[0], None, None
+  stats = ops.empty(2, ops.F32)
+  _engine.Contrastive(_dev(image_feat), _dev(cond_feat), slot, temperature, stats=stats)
+  return slot[0], stats[0], stats[1]
 
 
 def word_loss(image_feat, word_feat, max_len, gamma1=5, gamma2=5, gamma3=50):
@@ -40,8 +42,9 @@ def word_loss(image_feat, word_feat, max_len, gamma1=5, gamma2=5, gamma3=50):
   img = _dev(image_feat).to(torch.bfloat16)  # plumbing cast of the caller's tensor; the kernels consume bf16 regions
   ws = _engine.WordShared(_dev(word_feat), _dev(max_len))
   slot = ops.empty(1, ops.F32)
-  _engine.WordLoss(img, ws, slot)
-  return slot[0], None, None
+  stats = ops.empty(2, ops.F32)
+  _engine.WordLoss(img, ws, slot, stats=stats)
+  return slot[0], stats[0], stats[1]
 
 
 def attention_for_g(region_feat, word_feat, gamma, mask=None):

@@ -97,7 +97,10 @@ class Generator:
   def init(self, rng, inputs):
     eng = self._engine(inputs)
     p, s = eng.init_params(_seed_of(rng))
-    return {"params": FlatTree(eng.layout, p), "batch_stats": FlatTree(eng.stats_layout, s)}
+    out = {"params": FlatTree(eng.layout, p), "batch_stats": FlatTree(eng.stats_layout, s)}
+    if eng.sn:
+      out["spectral_norm_stats"] = FlatTree(eng.u_layout, eng.init_u0(_seed_of(rng) + 2))
+    return out
 
   def apply(self, variables, inputs, mutable=False, rngs=None):
     eng = self._engine(inputs)
@@ -106,13 +109,17 @@ class Generator:
     z = _to_dev(z)
     params = as_flat(eng.layout, variables["params"])
     stats = as_flat(eng.stats_layout, variables["batch_stats"])
-    eng.prep_weights(params)
+    u0 = as_flat(eng.u_layout, variables["spectral_norm_stats"]) if eng.sn else None
+    u0_new = torch.empty_like(u0) if eng.sn else None
+    eng.prep_weights(params, u0, u0_new)
     want_state = bool(mutable) and self.train
     new_stats = torch.empty_like(stats) if want_state else None
     img, _ = eng.forward(params, stats, batch, z, train=self.train, new_stats=new_stats)
     if mutable is False:
       return img
     out_state = {"batch_stats": FlatTree(eng.stats_layout, new_stats if want_state else stats)}
+    if eng.sn:  # u0 advances only in train mode (layers.py:98-99,215-216)
+      out_state["spectral_norm_stats"] = FlatTree(eng.u_layout, u0_new if self.train else u0)
     return img, out_state
 
 
@@ -146,16 +153,17 @@ class Discriminator:
     u0_new = torch.empty_like(u0) if eng.sn else None
     eng.prep_weights(params, u0, u0_new)
     losses = torch.zeros(16, device="cuda")
-    logit, _ = eng.forward(params, images, batch, losses, need_g=True)
+    # the module API returns the reference's full statistic dict (xmc_net.py:106-141), including the accuracy /
+    # entropy side statistics that train_step never reads (XLA removes them there; the engine skips them there too)
+    stats = torch.zeros(16, 2, device="cuda")
+    logit, _ = eng.forward(params, images, batch, losses, need_g=True, stats=stats)
     S = _engine.LOSS_SLOTS
-    zero = torch.zeros((), device="cuda")
     stat = {}
     for name, slot in (("fake_word", "fake_word"), ("real_word", "real_word"), ("fake_sentence", "fake_sent"),
                        ("real_sentence", "real_sent"), ("image_contrastive", "image")):
       stat[name + "_loss"] = losses[S[slot]]
-      # accuracy / entropy are dead on the train path (attention_lib.py:75-78,183-190; DCE'd by XLA): not computed
-      stat[name + "_acc"] = zero
-      stat[name + "_entropy"] = zero
+      stat[name + "_acc"] = stats[S[slot], 0]
+      stat[name + "_entropy"] = stats[S[slot], 1]
     out = (logit.view(n2, 1), stat)
     if mutable is False:
       return out

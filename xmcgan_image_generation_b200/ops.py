@@ -313,6 +313,11 @@ def ce_sym(logits, loss_slot, weight=1.0, want_grad=True):
   return dl
 
 
+def ce_stats(logits, out):
+  """out[0] = accuracy, out[1] = entropy of get_statistics (attention_lib.py:36-43), both directions averaged."""
+  _call("xmc_ce_stats", ptr(logits), logits.shape[0], ptr(out), stream())
+
+
 def hinge(logit, B, d_slot, g_slot):
   dd = empty(2 * B, F32)
   dg = empty(2 * B, F32)

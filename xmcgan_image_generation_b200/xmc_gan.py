@@ -79,7 +79,7 @@ class _Workspace:
     self.d_grads = torch.zeros_like(state.d_optimizer.target.buf)
     self.g_stats_alt = torch.empty_like(state.generator_state["batch_stats"].buf)
     self.u0_alt = torch.empty_like(state.discriminator_state["spectral_norm_stats"].buf) if d_eng.sn else None
-    self.g_prepped = False
+    self.g_u0_alt = torch.empty_like(state.generator_state["spectral_norm_stats"].buf) if g_eng.sn else None
 
 
 def _workspace(state, g_eng, d_eng):
@@ -109,9 +109,11 @@ def _forward_both(state, batch, config, ws, g_eng, d_eng, losses, keep_g_state, 
   S = config.image_size
   g_params = state.g_optimizer.target.buf
   d_params = state.d_optimizer.target.buf
-  if not ws.g_prepped:
-    g_eng.prep_weights(g_params)
-    ws.g_prepped = True
+  # the generator's bf16 weights (and, with g_spectral_norm, its power-iteration step) are shared by train_d and
+  # train_g_d of one train_step: same parameters, same u0 (train_d discards the generator's new state, xmc_gan.py:225)
+  g_u0 = state.generator_state["spectral_norm_stats"].buf if g_eng.sn else None
+  if g_eng.prepped_for != g_eng.prep_key(g_params, ws.g_u0_alt):
+    g_eng.prep_weights(g_params, g_u0, ws.g_u0_alt)
   u0 = state.discriminator_state["spectral_norm_stats"].buf if d_eng.sn else None
   d_eng.prep_weights(d_params, u0, ws.u0_alt)
   all_images = ops.empty((2 * B, S, S, 3))
@@ -191,6 +193,7 @@ def train_g_d(rng, state, batch, generator, discriminator, config, additional_da
   ws.g_grads.zero_()
   ops.LAUNCHES[0] += 1
   g_eng.backward(gctx, d_fake, g_params, ws.g_grads)
+  g_eng.sn_backward(g_params, ws.g_grads, ws.g_u0_alt)
   del gctx
   h_g = parallel.all_reduce_sum_(ws.g_grads, async_op=True)
   if h_d is not None:
@@ -198,10 +201,14 @@ def train_g_d(rng, state, batch, generator, discriminator, config, additional_da
     h_g.wait()
   _adam(state.d_optimizer, ws.d_grads)
   _adam(state.g_optimizer, ws.g_grads, ema=state.ema_params.buf, decay=config.polyak_decay)
-  ws.g_prepped = False
+  g_eng.prepped_for = None  # xmc_adam rewrote the parameters through raw pointers
   old_stats = state.generator_state["batch_stats"]
   new_g_state = {"batch_stats": xmc_net.FlatTree(g_eng.stats_layout, ws.g_stats_alt)}
   ws.g_stats_alt = old_stats.buf
+  if g_eng.sn:
+    old_u0 = state.generator_state["spectral_norm_stats"]
+    new_g_state["spectral_norm_stats"] = xmc_net.FlatTree(g_eng.u_layout, ws.g_u0_alt)
+    ws.g_u0_alt = old_u0.buf
   new_d_state = _swap_d_state(state, ws, d_eng)
   new_state = state.replace(step=state.step + 1, generator_state=new_g_state, discriminator_state=new_d_state)
   object.__setattr__(new_state, "_ws", ws)
