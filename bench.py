@@ -26,10 +26,11 @@ E_DIM, N_WORDS = 768, 17
 PER_GPU_B = 56  # per-device sub-batch of train_d and of train_g_d (coco_xmc.py:49 with one device)
 
 
-def make_config(image_size=128, pretrained=True):
+def make_config(image_size=128, pretrained=True, word_contrastive=True):
   from xmcgan_image_generation_b200.configs import coco_xmc
   c = coco_xmc.get_config()  # reference defaults, incl. pretrained_image_contrastive=True (coco_xmc.py:65)
-  c.update(dict(image_size=image_size, pretrained_image_contrastive=bool(pretrained)))
+  c.update(dict(image_size=image_size, pretrained_image_contrastive=bool(pretrained),
+                word_contrastive=bool(word_contrastive)))
   return c
 
 
@@ -78,10 +79,13 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-def algorithmic_tflop_per_step(B, pretrained=True):
-  """BASELINE.md §3 / SURVEY.md §8(d), 128 px: 26.93 TFLOP at B=56 (25.55 with the ResNet branch off)."""
-  wl = 0.01337e-3 * B * B              # TFLOP per word_loss forward call
+def algorithmic_tflop_per_step(B, pretrained=True, image_size=128, word_contrastive=True):
+  """BASELINE.md §3 / SURVEY.md §8(d): 26.93 TFLOP at 128 px, B=56 (25.55 with the ResNet branch off); 37.73 TFLOP
+  at 256 px, B=24. The word loss works on 16x16 regions at both resolutions."""
+  wl = 0.01337e-3 * B * B if word_contrastive else 0.0  # TFLOP per word_loss forward call
   g, d, r = 43.40e-3, 21.23e-3, 8.18e-3  # TFLOP per image forward (algorithmic G, D, ResNet-50 @224)
+  if image_size == 256:
+    g, d = 147.03e-3, 73.58e-3
   train_d = g * B + d * 2 * B * 3 + 3 * wl
   train_g_d = 3 * g * B + d * 2 * B * 3 + d * B + 6 * wl + (r * 3 * B if pretrained else 0.0)
   return train_d + train_g_d
@@ -165,7 +169,7 @@ def run_b200(args):
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
   from xmcgan_image_generation_b200 import engine
   pretrained = not args.no_pretrained
-  config = make_config(args.image_size, pretrained)
+  config = make_config(args.image_size, pretrained, not args.no_word_contrastive)
   B = args.batch
   config.batch_size = B * world
   host = synth_batch(2 * B, config, 42 + rank)
@@ -198,8 +202,6 @@ def run_b200(args):
   sampler = ClockSampler(local)
   if rank == 0:
     sampler.start()
-  timer = GemmTimer()
-  timer.install(ops)
   launches0 = ops.LAUNCHES[0]
   e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   barrier()
@@ -210,13 +212,25 @@ def run_b200(args):
   barrier()
   ms_dev = max_over_ranks(e0.elapsed_time(e1))
   launches = ops.LAUNCHES[0] - launches0
+  clocks = sampler.stop() if rank == 0 else None
+  last = metrics.compute()
+
+  # ---- the same K steps once more with every tcgen05 GEMM launch bracketed by CUDA events on its stream (roofline).
+  # Kept out of the pass above: ~500 event records per step cost a few per cent of step time.
+  timer = GemmTimer()
+  timer.install(ops)
+  barrier()
+  e0.record()
+  for _ in range(args.steps):
+    state, metrics = train_utils.train_step(None, state, dev, xmc_gan, generator, discriminator, config, additional)
+  e1.record()
+  barrier()
+  ms_instr = e0.elapsed_time(e1)
   gemm = timer.summary()
   if args.dump_gemm and rank == 0:
     with open(args.dump_gemm, "w") as f:
       json.dump({"steps": args.steps, "rows": timer.per_shape()}, f, indent=0)
   timer.uninstall()
-  clocks = sampler.stop() if rank == 0 else None
-  last = metrics.compute()
 
   # ---- timed: end to end through the public API with host buffers ------------------------------------------------------
   h2d = sum(v.numel() * v.element_size() for v in pinned.values())
@@ -250,23 +264,26 @@ def run_b200(args):
                                 "bytes, inputs read once) are in profiles/r01_gemm_shape_classes.md",
                 "peak_source": peak_src,
                 "launches_timed": gemm[dom]["launches"],
-                "share_of_step": round(gemm[dom]["ms"] / ms_dev, 3),
+                "share_of_step": round(gemm[dom]["ms"] / ms_instr, 3),
+                "timed_in": "second pass of the same K steps with per-launch CUDA events "
+                            f"({round(ms_instr / args.steps, 3)} ms/step incl. event overhead)",
                 "all_gemm": {k: {"tflops": round(v["tflop"] / (v["ms"] / 1e3), 1), "ms_per_step":
                                  round(v["ms"] / args.steps, 2)} for k, v in gemm.items()}}
   imgs = world * 2 * B * args.steps
+  alg_tf = algorithmic_tflop_per_step(B, pretrained, config.image_size, config.word_contrastive)
   out = {
-      "metric": "images/sec (G+D train_step, 128px, bs=56 per GPU)", "value": round(imgs / (ms_dev / 1e3), 2),
+      "metric": f"images/sec (G+D train_step, {config.image_size}px, bs={B} per GPU)",
+      "value": round(imgs / (ms_dev / 1e3), 2),
       "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
       "ms_per_step": round(ms_dev / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
       "dtype": "bf16", "data": "synthetic",
       "config": {"workload": f"coco_xmc.py {config.image_size}px, per-GPU sub-batch B={B} (2B real images per step), "
                              "train_d + train_g_d, Adam, EMA, grad all-reduce",
                  "global_batch": B * world, "parallelism": f"dp{world}",
-                 "pretrained_image_contrastive": pretrained,
+                 "pretrained_image_contrastive": pretrained, "word_contrastive": bool(config.word_contrastive),
                  "l2": "per-step working set (several GB of activations) >> 126 MB L2; no explicit flush",
-                 "algorithmic_tflop_per_step_per_gpu": round(algorithmic_tflop_per_step(B, pretrained), 2),
-                 "model_tflops_per_gpu": round(algorithmic_tflop_per_step(B, pretrained) /
-                                               (ms_dev / args.steps / 1e3), 1)},
+                 "algorithmic_tflop_per_step_per_gpu": round(alg_tf, 2),
+                 "model_tflops_per_gpu": round(alg_tf / (ms_dev / args.steps / 1e3), 1)},
       "e2e": {"value": round(imgs / (ms_e2e / 1e3), 2), "unit": "images/sec", "h2d_bytes_per_step": h2d,
               "d2h_bytes_per_step": 20},
       "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "losses": last,
@@ -348,6 +365,8 @@ def main():
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-pretrained", action="store_true",
                   help="switch the frozen ResNet-50 image-image InfoNCE branch off (reference default: on)")
+  ap.add_argument("--no-word-contrastive", action="store_true",
+                  help="BASELINE config 5 (attention ablation): discriminator-side word_loss off (xmc_net.py:112)")
   ap.add_argument("--dump-gemm", default=None, help="write per-shape GEMM timings (JSON) to this file")
   args = ap.parse_args()
   if args.warmup < 3 and args.impl == "b200":

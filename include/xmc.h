@@ -109,6 +109,10 @@ typedef struct {
   int Hc;
   int ldG, goff, boff;
   int relu, upsample;
+  /* cross-replica BatchNorm (nn.BatchNorm axis_name="batch" with axis_index_groups, xmc_net.py:192-201): number of
+   * replicas whose statistics were summed into `sums` by the caller's all-reduce; 0 or 1 = replica-local. Only
+   * xmc_bn_bwd_apply reads it (its means divide by N*H*W*replicas). */
+  int replicas;
 } XmcBnDesc;
 
 int xmc_bn_stats(const void* x, long long P, int C, int ld, float* sums /*[2C], zeroed by caller*/, void* stream);

@@ -56,7 +56,7 @@ class BnDesc(ctypes.Structure):
       ("N", ctypes.c_int), ("H", ctypes.c_int), ("W", ctypes.c_int), ("C", ctypes.c_int),
       ("Hc", ctypes.c_int),
       ("ldG", ctypes.c_int), ("goff", ctypes.c_int), ("boff", ctypes.c_int),
-      ("relu", ctypes.c_int), ("upsample", ctypes.c_int),
+      ("relu", ctypes.c_int), ("upsample", ctypes.c_int), ("replicas", ctypes.c_int),
   ]
 
 

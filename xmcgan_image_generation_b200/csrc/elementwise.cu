@@ -569,7 +569,7 @@ extern "C" int xmc_bn_bwd_apply(const XmcBnDesc* d, const void* dy, const void* 
   if (r) return r;
   if (!dy || !x || !mean_rstd || !gb || !sums || !dx) return XMC_EINVAL;
   if (p.C / 8 > 1024) return XMC_EINVAL;
-  const float invP = 1.f / (float)((long long)p.N * p.H * p.W);
+  const float invP = 1.f / (float)((long long)p.N * p.H * p.W * (d->replicas > 1 ? d->replicas : 1));
   dim3 grid, block;
   bn_launch_dims(p, &grid, &block);
   bn_bwd_apply_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(

@@ -187,8 +187,6 @@ class GeneratorEngine:
   """xmc_net.Generator (xmc_net.py:145-248)."""
 
   def __init__(self, config, embedding_dim=768):
-    if config.batch_norm_group_size > 0:
-      raise NotImplementedError("grouped cross-replica BatchNorm is not built yet (default -1, coco_xmc.py:44)")
     if config.image_size == 256:
       channel_dims = [16, 8, 8, 4, 2, 1]
     elif config.image_size == 128:
@@ -378,13 +376,27 @@ class GeneratorEngine:
   def _wd(self, rec):
     return self.arena[rec.dg_off:]
 
-  def _bn(self, x, prefix, stats, new_stats, train):
+  def _bn_group(self, B, train):
+    """Cross-replica BatchNorm group of this rank (train mode, batch_norm_group_size > 0, xmc_net.py:196-200)."""
+    gbs = self.config.batch_norm_group_size
+    if not train or gbs <= 0:
+      return None
+    from . import parallel
+    return parallel.bn_group(gbs, B)
+
+  def _bn(self, x, prefix, stats, new_stats, train, group=None):
     C = x.shape[-1]
     SL = self.stats_layout
     mean = SL.view(stats, prefix + ("BatchNorm_0", "mean"))
     var = SL.view(stats, prefix + ("BatchNorm_0", "var"))
     if train:
       sums, P = ops.bn_stats(x)
+      if group is not None:
+        # flax BatchNorm pmean's [mean, mean of squares] over the replica group; all replicas hold the same number of
+        # elements, so summing the raw sums and dividing by P * group_size is the same
+        from . import parallel
+        parallel.all_reduce_sum_(sums, group=group[0])
+        P *= group[1]
       nm = SL.view(new_stats, prefix + ("BatchNorm_0", "mean")) if new_stats is not None else None
       nv = SL.view(new_stats, prefix + ("BatchNorm_0", "var")) if new_stats is not None else None
       return ops.bn_finalize(sums, P, C, mean, var, nm, nv)
@@ -400,7 +412,8 @@ class GeneratorEngine:
     words = batch["embedding"]
     Lw = words.shape[1]
     max_len = batch["max_len"].reshape(B).contiguous()
-    ctx = {"B": B, "Lw": Lw, "train": train}
+    grp = self._bn_group(B, train)
+    ctx = {"B": B, "Lw": Lw, "train": train, "bn_group": grp}
 
     cond_bf = ops.cast_to_bf16(cond)
     gc = ops.empty((B, cd))
@@ -434,13 +447,13 @@ class GeneratorEngine:
       _, g0, b0 = self.bn_index[bn0]
       _, g1, b1 = self.bn_index[bn1]
       r0, r1, r2 = (self.convs[(name, f"{self.cpre}_{i}")] for i in range(3))
-      mr0 = self._bn(x, bn0, stats, new_stats, train)
+      mr0 = self._bn(x, bn0, stats, new_stats, train, grp)
       # CBN -> relu at the block's input resolution; the nearest 2x upsample is folded into the next conv
       # (sub-pixel form: four 2x2 convs, 2.25x fewer FLOPs, the up-sampled tensor is never materialised)
       u = ops.bn_apply(x, mr0, gb, Hc, g0, b0, True, False)
       wf_off, _ = self.subpixel[(name, self.cpre + "_0")]
       c1 = ops.conv_fwd(u, self.arena[wf_off:], 2, bcout, bias=P[r0.b_off:], ldb=4 * bcin, pad=1, subpixel=True)
-      mr1 = self._bn(c1, bn1, stats, new_stats, train)
+      mr1 = self._bn(c1, bn1, stats, new_stats, train, grp)
       h2 = ops.bn_apply(c1, mr1, gb, Hc, g1, b1, True, False)
       sc = ops.conv_fwd(x, self._wk(r2), 1, bcout, bias=P[r2.b_off:], ldb=r2.ld_fwd)
       out = ops.conv_fwd(h2, self._wk(r1), 3, bcout, bias=P[r1.b_off:], residual=sc, res_shift=1, ldb=r1.ld_fwd)
@@ -448,7 +461,7 @@ class GeneratorEngine:
       x = out
     bnf = ("LocalConditionalBatchNorm_0",)
     _, gf_, bf_ = self.bn_index[bnf]
-    mrf = self._bn(x, bnf, stats, new_stats, train)
+    mrf = self._bn(x, bnf, stats, new_stats, train, grp)
     hf = ops.bn_apply(x, mrf, gbL, Hc, gf_, bf_, True, False)
     r = self.convs[(self.cpre + "_1",)]
     S = x.shape[1]
@@ -469,6 +482,7 @@ class GeneratorEngine:
     B, E, zd, cd, scd = ctx["B"], self.E, self.zd, self.cd, self.scd
     S = d_img.shape[1]
     gbC, gbL, R, Hc16 = ctx["gbC"], ctx["gbL"], ctx["R"], ctx["Hc"]
+    grp = ctx["bn_group"]
     dgbC = ops.zeros((B, self.NC), F32)  # ConditionalBatchNorm d(gamma), d(beta) are accumulated atomically
     dgbL = ops.empty((B * R, self.NL), F32)
 
@@ -484,7 +498,7 @@ class GeneratorEngine:
     ops._call("xmc_conv_c3_in", dpre.data_ptr(), self._wd(r).data_ptr(), r.ld_dg, None, B, S, S, C, 3, 3, 0,
               dhf.data_ptr(), _lib.stream())
     _, gf_, bf_ = self.bn_index[("LocalConditionalBatchNorm_0",)]
-    dout = ops.bn_bwd(dhf, ctx["x_last"], ctx["mrf"], gbL, dgbL, Hc16, gf_, bf_, True, False)
+    dout = ops.bn_bwd(dhf, ctx["x_last"], ctx["mrf"], gbL, dgbL, Hc16, gf_, bf_, True, False, group=grp)
 
     dx16_extra = None
     for (name, kind, bcin, bcout), sv in zip(reversed(self.blocks), reversed(ctx["blocks"])):
@@ -501,14 +515,14 @@ class GeneratorEngine:
       # conv2 (Conv_1)
       self._conv_wgrad(r1, sv["h2"], dout, grads)
       dh2 = ops.conv_fwd(dout, self._wd(r1), 3, bcout, ldb=r1.ld_dg)
-      dc1 = ops.bn_bwd(dh2, sv["c1"], sv["mr1"], gb, dgb, sv["Hc"], g1, b1, True, False)
+      dc1 = ops.bn_bwd(dh2, sv["c1"], sv["mr1"], gb, dgb, sv["Hc"], g1, b1, True, False, group=grp)
       # conv1 (Conv_0, sub-pixel form): weight gradient from the low-resolution input and the 2x gradient; input
       # gradient = 4x4 / stride-2 / pad-1 convolution over the gradient, directly at the input resolution
       ops.wgrad(sv["u"], dc1, 3, grads[r0.w_off:], out_mode=0, ld_out=bcout, tap_stride=bcin * bcout, subpixel=True)
       ops.colsum(dc1, grads[r0.b_off:])
       _, vd_off = self.subpixel[(name, self.cpre + "_0")]
       du = ops.conv_fwd(dc1, self.arena[vd_off:], 4, bcin, ldb=16 * bcout, stride=2, pad=1)
-      dxa = ops.bn_bwd(du, sv["x"], sv["mr0"], gb, dgb, sv["Hc"], g0, b0, True, False)
+      dxa = ops.bn_bwd(du, sv["x"], sv["mr0"], gb, dgb, sv["Hc"], g0, b0, True, False, group=grp)
       # shortcut (Conv_2 at low resolution)
       dsc = ops.pool2(dout, scale=1.0)
       self._conv_wgrad(r2, sv["x"], dsc, grads)

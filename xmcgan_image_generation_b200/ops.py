@@ -151,14 +151,20 @@ def bn_apply(x, mr, gb, Hc, goff, boff, relu, upsample):
   return y
 
 
-def bn_bwd(dy, x, mr, gb, dgb, Hc, goff, boff, relu, upsample):
-  """Returns dx (bf16, shape of x); writes d(gamma), d(beta) into the fp32 matrix dgb (same layout as gb)."""
+def bn_bwd(dy, x, mr, gb, dgb, Hc, goff, boff, relu, upsample, group=None):
+  """Returns dx (bf16, shape of x); writes d(gamma), d(beta) into the fp32 matrix dgb (same layout as gb).
+  group: (process_group, size) of a cross-replica BatchNorm — the two per-channel sums of the backward are then
+  all-reduced over the group (the transpose of the forward's pmean), see parallel.bn_group."""
   N, H, W, C = x.shape
   assert gb.stride(0) == dgb.stride(0)
   d = _bn_desc(N, H, W, C, Hc, gb.stride(0), goff, boff, relu, upsample)
   sums = zeros(2 * C)
   LAUNCHES[0] += 1
   _call("xmc_bn_bwd_reduce", ctypes.byref(d), ptr(dy), ptr(x), ptr(mr), ptr(gb), ptr(dgb), ptr(sums), stream())
+  if group is not None:
+    from . import parallel
+    parallel.all_reduce_sum_(sums, group=group[0])
+    d.replicas = group[1]
   dx = empty((N, H, W, C))
   _call("xmc_bn_bwd_apply", ctypes.byref(d), ptr(dy), ptr(x), ptr(mr), ptr(gb), ptr(sums), ptr(dx), stream())
   return dx
