@@ -54,28 +54,61 @@ def _worker(rank, world, port, out):
     torch.cuda.synchronize()
     return img, new_stats, grads
 
+  # ---- single op: statistics + backward of one LocalConditionalBatchNorm over the group vs the joint batch ---------
+  torch.manual_seed(24)
+  C, H, Hc = 32, 16, 16
+  x_full = (torch.randn(world * B, H, H, C) * 2 + 0.5).cuda().to(torch.bfloat16)
+  gb_full = (torch.randn(world * B * Hc * Hc, 2 * C) * 0.5).cuda().to(torch.bfloat16)
+  dy_full = (torch.randn(world * B, H, H, C) * 0.1).cuda().to(torch.bfloat16)
+  grp = parallel.bn_group(world * B, B)
+  assert grp is not None and grp[1] == world
+
+  def bn_op(x, gb, dy, group):
+    sums, P = ops.bn_stats(x)
+    if group is not None:
+      parallel.all_reduce_sum_(sums, group=group[0])
+      P *= group[1]
+    zeros, ones = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    mr = ops.bn_finalize(sums, P, C, zeros, ones, None, None)
+    y = ops.bn_apply(x, mr, gb, Hc, 0, C, True, False)
+    dgb = torch.zeros(gb.shape, device="cuda")
+    dx = ops.bn_bwd(dy, x, mr, gb, dgb, Hc, 0, C, True, False, group=group)
+    torch.cuda.synchronize()
+    return y, dx, dgb
+
+  rows = slice(rank * B * Hc * Hc, (rank + 1) * B * Hc * Hc)
+  y_s, dx_s, dgb_s = bn_op(x_full[sl].contiguous(), gb_full[rows].contiguous(), dy_full[sl].contiguous(), grp)
+  y_f, dx_f, dgb_f = bn_op(x_full, gb_full, dy_full, None)
+  rel = lambda a, b: ((a.float() - b.float()).norm() / (b.float().norm() + 1e-12)).item()
+  op = {"y": rel(y_s, y_f[sl]), "dx": rel(dx_s, dx_f[sl]), "dgb": rel(dgb_s, dgb_f[rows])}
+
   img_s, stats_s, grads_s = run(g_sync, shard, d_img_full[sl])
   parallel.all_reduce_sum_(grads_s)                       # sum over replicas of the per-replica gradients
   img_f, stats_f, grads_f = run(g_local, full, d_img_full)
-  rel = lambda a, b: ((a.float() - b.float()).norm() / (b.float().norm() + 1e-12)).item()
-  res = {"img": rel(img_s, img_f[sl]), "stats": rel(stats_s, stats_f), "grads": rel(grads_s, grads_f)}
+  res = {"op": op, "img": rel(img_s, img_f[sl]), "stats": rel(stats_s, stats_f), "grads": rel(grads_s, grads_f)}
   # and the group really changes the result: replica-local statistics on the shard differ from the full batch
-  img_l, _, _ = run(g_local, shard, d_img_full[sl])
+  img_l, _, grads_l = run(g_local, shard, d_img_full[sl])
+  parallel.all_reduce_sum_(grads_l)
   res["local_differs"] = rel(img_l, img_f[sl])
+  res["local_grads_differ"] = rel(grads_l, grads_f)
   out[rank] = res
   dist.destroy_process_group()
 
 
 @gpu
 def test_grouped_batch_norm_over_two_replicas_equals_one_replica_on_the_joint_batch():
-  """Tolerances: images 1e-2 rel-L2 (bf16 activations; the statistics differ only in summation order), running
-  statistics 1e-4, summed parameter gradients 2e-2."""
+  """Tolerances: one BatchNorm op (forward, dx, dgamma/dbeta) 2e-3 — only the summation order of the statistics
+  differs; whole generator: images 1e-2 rel-L2, running statistics 1e-4, summed parameter gradients 6e-2 (the bar of
+  the other whole-network gradient tests: bf16 activation gradients through 11 normalisation layers) and at least 3x
+  closer than the same two replicas with replica-local statistics."""
   world = 2
   out = mp.Manager().dict()
   mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
   for r in range(world):
     res = out[r]
+    assert max(res["op"].values()) < 2e-3, res
     assert res["img"] < 1e-2, res
     assert res["stats"] < 1e-4, res
-    assert res["grads"] < 2e-2, res
+    assert res["grads"] < 6e-2, res
     assert res["local_differs"] > 5 * res["img"], res
+    assert res["local_grads_differ"] > 3 * res["grads"], res

@@ -21,7 +21,8 @@ constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kBarBytes = 256;
 constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // + slack for 1024B alignment
 constexpr int kThreads = 192;     // wgrad kernel: TMA, MMA, 4 epilogue warps
-constexpr int kThreadsFwd = 320;  // forward kernel: TMA, MMA, 8 epilogue warps
+constexpr int kEpiParts = 3;      // forward kernel: epilogue warps per TMEM lane quarter
+constexpr int kThreadsFwd = 64 + 128 * kEpiParts;  // TMA warp, MMA warp, 4 * kEpiParts epilogue warps
 constexpr int kTmemCols = 512;
 
 struct FwdParams {
@@ -114,7 +115,7 @@ gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 8);
+      mbar_init(tempty_bar(a), 4 * kEpiParts);
     }
     fence_barrier_init();
   }
@@ -200,8 +201,10 @@ gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (acc == 0) acc_phase ^= 1;
     }
   } else {
-    // 8 epilogue warps: warp w may only touch TMEM lanes 32*(w%4)..+31; the two warps that share a lane quarter
-    // split the 16-column chunks of the tile between them (even / odd chunks).
+    // 4 * kEpiParts epilogue warps: warp w may only touch TMEM lanes 32*(w%4)..+31; the kEpiParts warps that share a
+    // lane quarter take the 16-column chunks of the tile round-robin. A chunk is a dependent chain of ~200
+    // instructions, so short-K tiles (1x1 convolutions) are bound by the epilogue's latency: more warps, not wider
+    // accesses, is what shortens it (measured: grouping loads or staging through shared memory made it slower).
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     int acc = 0;
@@ -229,7 +232,7 @@ gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
-      for (int c0 = half * 16; c0 < p.BN; c0 += 32) {
+      for (int c0 = half * 16; c0 < p.BN; c0 += 16 * kEpiParts) {
         uint32_t v[16];
         tmem_ld16(t_addr + c0, v);  // asynchronous until tmem_ld_wait
         const int col = nt * p.BN + c0;
@@ -651,6 +654,26 @@ static int pick_bn(int n) {
   return best;
 }
 
+// N-tile width of the forward kernel from a small cost model (cycles): tensor time = waves * k-iterations * 2*BN
+// (four 128xBNx16 MMAs per 64-channel k-iteration), L2->SM time = all tiles' operand bytes / the chip-wide L2
+// throughput cap (~6300 B/clk), plus the exposed epilogue of the last tile. For layers with many waves this reduces to
+// "fewest padded columns, widest tile"; for the small-M layers (4x4 / 8x8 feature maps: fewer tiles than SMs at
+// BN=256) it trades tile width against occupied SMs.
+static int pick_bn_fwd(int cout, long long m_tiles, int kiters, int sms) {
+  const int cmax = ceil_div(cout, 16) * 16;
+  int best = cmax < 256 ? cmax : 256;
+  double best_cost = 1e300;
+  for (int bn = (cmax < 256 ? cmax : 256); bn >= 32; bn -= 16) {
+    const long long tiles = m_tiles * ceil_div(cout, bn);
+    const long long waves = (tiles + sms - 1) / sms;
+    const double mma = (double)waves * kiters * 2.0 * bn;
+    const double l2 = (double)tiles * kiters * (16384.0 + 128.0 * bn) / 6300.0;
+    const double cost = (mma > l2 ? mma : l2) + 1000.0 + 8.0 * bn;
+    if (cost < best_cost * 0.999) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
 static bool g_attr_set_fwd = false, g_attr_set_wgrad = false;
 
 }  // namespace xmc
@@ -686,7 +709,8 @@ extern "C" int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* w
   p.tiles_w = ceil_div(d->W, p.tw);
   p.tiles_h = ceil_div(d->H, p.th);
   p.tiles_n = ceil_div(d->N, p.tn);
-  p.BN = pick_bn(d->Cout);
+  p.BN = pick_bn_fwd(d->Cout, (long long)p.tiles_w * p.tiles_h * p.tiles_n * p.parities,
+                     d->KH * d->KW * p.cchunks, num_sms());
   p.n_tiles = ceil_div(d->Cout, p.BN);
   p.idesc = make_idesc_bf16(128, p.BN, 0, 0);
   p.stage_tx_bytes = (uint32_t)(64 * p.tw * p.th * p.tn * 2 + 64 * p.BN * 2);
