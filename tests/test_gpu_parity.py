@@ -578,3 +578,48 @@ def test_accuracy_and_entropy_side_statistics(B):
   _, acc, ent = attention_lib.word_loss(img, words, max_len)
   assert abs(acc.item() - wacc.item()) <= 0.5 / B + 1e-6      # at most one near-tie flipped by bf16 operands
   assert abs(ent.item() - went.item()) < 2e-2 * max(1.0, abs(went.item()))
+
+
+@gpu
+def test_generate_batch_and_checkpoint_round_trip(tmp_path):
+  """train_utils.generate_batch (train_utils.py:245-309): inference-mode samples with the current and the EMA
+  parameters vs the oracle's generator_apply(train=False) on the same z (2e-2 rel-L2, bf16 activations), grid layout
+  exact; then the state survives a ckpt-N.flax round trip bit for bit and keeps training."""
+  _, engine, ops, train_utils, xmc_gan, xmc_net = _mods()
+  import functools
+  from xmcgan_image_generation_b200 import checkpoint as ck
+  cfg = helpers.small_config(show_num=4)
+  B = 3
+  g_vars, d_vars, g_params, g_stats, d_params, d_u = _build(cfg, seed=13)
+  batch = helpers.make_batch(2 * B, cfg, seed=14)
+  state = train_utils.TrainState(0, train_utils.Optimizer(g_params, cfg.g_lr, cfg.beta1, cfg.beta2),
+                                 train_utils.Optimizer(d_params, cfg.d_lr, cfg.beta1, cfg.beta2),
+                                 {"batch_stats": g_stats}, {"spectral_norm_stats": d_u}, g_params.clone())
+  state, _ = train_utils.train_step(None, state, batch, xmc_gan, None, None, cfg, {})   # EMA != params afterwards
+  gen = functools.partial(xmc_net.Generator, config=cfg)
+  out = train_utils.generate_batch(0, state, batch, gen, cfg)
+  assert set(out) == {"generated_image_batch", "ema_generated_image_batch", "ori_image_batch"}
+  assert out["generated_image_batch"].shape == (1, 2 * 128, 2 * 128, 3)
+  pol = orc.Policy("bfloat16")
+  stats = state.generator_state["batch_stats"].to_cpu_tree()
+  for key, params in (("generated_image_batch", state.g_optimizer.target), ("ema_generated_image_batch", state.ema_params)):
+    want, _ = orc.generator_apply({"params": params.to_cpu_tree(), "batch_stats": stats}, (batch, batch["z"]), cfg,
+                                  False, pol)
+    assert helpers.rel(out[key][0], train_utils.make_grid(want.detach(), 4)) < 2e-2, key
+  assert torch.equal(out["ori_image_batch"][0].cpu(), train_utils.make_grid(batch["image"], 4))
+  assert not torch.equal(out["generated_image_batch"], out["ema_generated_image_batch"])
+  # checkpoint round trip through the reference's file format, then one more step on both copies
+  path = ck.save_checkpoint(str(tmp_path), state)
+  g2, d2, g_params2, g_stats2, d_params2, d_u2 = _build(cfg, seed=99)
+  other = train_utils.TrainState(0, train_utils.Optimizer(g_params2, cfg.g_lr, cfg.beta1, cfg.beta2),
+                                 train_utils.Optimizer(d_params2, cfg.d_lr, cfg.beta1, cfg.beta2),
+                                 {"batch_stats": g_stats2}, {"spectral_norm_stats": d_u2}, g_params2.clone())
+  ck.restore_checkpoint(other, path)
+  assert (other.step, other.d_optimizer.step, other.g_optimizer.step) == (1, 2, 1)
+  assert torch.equal(other.d_optimizer.target.buf, state.d_optimizer.target.buf)
+  assert torch.equal(other.ema_params.buf, state.ema_params.buf)
+  state, m1 = train_utils.train_step(None, state, batch, xmc_gan, None, None, cfg, {})
+  other, m2 = train_utils.train_step(None, other, batch, xmc_gan, None, None, cfg, {})
+  a, b = m1.compute(), m2.compute()
+  for k in a:
+    assert abs(a[k] - b[k]) <= 1e-3 * max(1.0, abs(a[k])), (k, a[k], b[k])   # atomics order only

@@ -1,12 +1,15 @@
 """Counterparts of the hot-path symbols of xmcgan/train_utils.py: TrainState (:42-50), split_input_dict (:69-88),
-train_step (:91-130), create_train_state (:133-193). The outer loop (train/test, checkpoints, summaries) is out of
-scope."""
+train_step (:91-130), create_train_state (:133-193), and the sampling path generate_batch (:245-309, SURVEY.md §8f
+rank 1). The outer loop (train/test, summaries) is out of scope; the checkpoint format is in
+checkpoint.py."""
 import dataclasses
 import functools
+import math
 from typing import Any, Optional
 
 import torch
 
+from . import parallel
 from .nets import xmc_net
 
 
@@ -54,6 +57,46 @@ def train_step(rng, state, batch, gan_model, generator, discriminator, config, a
   for i in range(config.d_step_per_g_step - 1):
     state = gan_model.train_d(None, state, batches[i], generator, discriminator, config)
   return gan_model.train_g_d(None, state, batches[-1], generator, discriminator, config, additional_data)
+
+
+def make_grid(samples, show_num=64):
+  """image_utils.make_grid (xmcgan/utils/image_utils.py:23-38): the first h*w images tiled into one [h*H, w*W, C]
+  image. A pure index permutation (views / one strided copy, no arithmetic): exact."""
+  batch_size, height, width, c = samples.shape
+  show_num = min(show_num, batch_size)
+  h_num = int(math.sqrt(show_num))
+  w_num = int(show_num / h_num)
+  grid = samples[:h_num * w_num].reshape(h_num, w_num, height, width, c).transpose(1, 2)
+  return grid.reshape(height * h_num, width * w_num, c)
+
+
+def generate_batch(rng, state, batch, generator, config, collect_all=False):
+  """train_utils.generate_batch (train_utils.py:245-309): samples with the current and with the EMA generator
+  parameters in inference mode (running BatchNorm statistics; with g_spectral_norm the power iteration still runs but
+  u0 is not advanced), tiled into grids next to the original images. `rng` seeds z ~ N(0,1) (a torch CUDA generator:
+  JAX's threefry stream cannot be reproduced, so z differs from the reference's for the same key; pass batch["z"] to
+  pin it). collect_all gathers over all replicas (jax.lax.all_gather over "batch")."""
+  batch = xmc_net.batch_to_device(batch)
+  n = batch["image"].shape[0]
+  if "z" in batch and batch["z"].shape[0] == n:
+    z = batch["z"]
+  else:
+    g = torch.Generator(device="cuda").manual_seed(xmc_net._seed_of(rng))
+    z = torch.randn(n, config.z_dim, device="cuda", generator=g)
+  g_variables = dict(state.generator_state, params=state.g_optimizer.target)
+  ema_g_variables = dict(state.generator_state, params=state.ema_params)
+  images = {"generated_image_batch": generator(train=False).apply(g_variables, (batch, z), mutable=False),
+            "ema_generated_image_batch": generator(train=False).apply(ema_g_variables, (batch, z), mutable=False),
+            "ori_image_batch": batch["image"]}
+  out = {}
+  for key, img in images.items():
+    img = img.float()
+    if collect_all and parallel.world_size() > 1:
+      parts = [torch.empty_like(img) for _ in range(parallel.world_size())]
+      torch.distributed.all_gather(parts, img.contiguous())
+      img = torch.cat(parts)
+    out[key] = make_grid(img, config.show_num)[None]  # the summary writer wants a 4-D tensor
+  return out
 
 
 def create_train_state(config, rng, init_batch):
