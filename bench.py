@@ -107,8 +107,8 @@ class GemmTimer:
       st = kw.get("stride", 1)
       ho, wo, taps = x.shape[1] // st, x.shape[2] // st, kh * kh
       view = kw.get("view")
-      if view is not None:  # ResNet stem: 7x7x3 taps per output pixel (the packed window has 8-channel padding)
-        ho, wo, taps, c = view["Hout"], view["Wout"], 49, 3
+      if view is not None:  # packed-window convs (ResNet stem 7x7x3, image convs 3x3x3): count the real taps/channels
+        ho, wo, taps, c = view["Hout"], view["Wout"], view.get("real_taps", 49), view.get("real_c", 3)
       if kw.get("subpixel"):  # four parities x 2x2 taps per input pixel
         taps = 16
       flops = 2.0 * x.shape[0] * ho * wo * taps * c * cout
@@ -123,13 +123,17 @@ class GemmTimer:
     def wgrad(xa, xb, kh, out, **kw):
       ca = kw.get("ca") or xa.shape[3]
       cb = kw.get("cb") or xb.shape[3]
-      flops = 2.0 * xa.shape[0] * xa.shape[1] * xa.shape[2] * (16 if kw.get("subpixel") else kh * kh) * ca * cb
+      taps = 16 if kw.get("subpixel") else kh * kh
+      if kw.get("view_a") is not None:  # packed-window 3-channel image wgrad: 9 taps x 3 real channels
+        taps, ca = 9, 3
+      g = xb if kw.get("view_a") is not None else xa  # pixel grid of the reduction
+      flops = 2.0 * g.shape[0] * g.shape[1] * g.shape[2] * taps * ca * cb
       s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
       s.record()
       r = timer._wgrad(xa, xb, kh, out, **kw)
       e.record()
       timer.records.append(("gemm_wgrad_kernel", flops, s, e,
-                            (xa.shape[0], xa.shape[1], xa.shape[2], ca, kh, cb, int(kw.get("batched", False)))))
+                            (g.shape[0], g.shape[1], g.shape[2], ca, kh, cb, int(kw.get("batched", False)))))
       return r
 
     ops.conv_fwd, ops.wgrad = conv_fwd, wgrad

@@ -92,6 +92,12 @@ typedef struct {
    * [N,2H,2W,Cb] output gradient (read with stride 2, one parity per tap); the 16 parity/tap products are added to
    * the 9 taps of dw ([3][3][Ca][Cb]) they belong to. KH=KW=3, out_mode 0. */
   int subpixel;
+  /* Optional re-pitched view of xa (all 0 = dense [N,H,W,ldA]): xa is read through a tensor map of extents
+   * (Ca, W, HinA, N) with element pitches (pitchWA, pitchHA, pitchNA); tap (kh, kw) reads position
+   * (h + kh - pad_h, w + kw - pad_w). Used for the packed-window form of the 3-channel image convolutions (an
+   * 8-channel zero-bordered image whose 3 kw taps x 8 channels are one contiguous 24-element run: Ca=24, KH=3, KW=1). */
+  int HinA;
+  long long pitchWA, pitchHA, pitchNA;
 } XmcWgradDesc;
 
 int xmc_conv2d_wgrad(const XmcWgradDesc* d, const void* xa, const void* xb, void* dw, void* stream);
@@ -270,6 +276,17 @@ int xmc_axpy_f32(float* y, const float* x, float a, long long n, void* stream);
  * 3-channel (image-side) convolutions: first discriminator block (common.py:125-133) and generator head
  * (xmc_net.py:245-247). w is a bf16 [rows][ldw] K-major matrix from xmc_prep_weights.
  */
+/* Packed-window form of the 3x3 convolutions with 3 image channels on the input side (first discriminator conv,
+ * xmc_net.py:88 / common.py:125-127; input gradient of the generator's output conv): they run on the tcgen05 GEMM
+ * kernels over an 8-channel zero-bordered copy of the image.
+ *   xmc_pad_c3_to_c8:   x bf16 [N,H,W,3] -> out bf16 [N,H+2,W+2,8] (border and channels 3..7 zero; writes all of out)
+ *   xmc_pack_c3_weights: w bf16 [Cout][ldw] with k = (kh*3+kw)*3+c -> out bf16 [Cout][72] with k = kh*24 + kw*8 + c
+ *   xmc_unpack_c3_wgrad: tmp fp32 [3 kh][24 = kw*8+c][C] (from xmc_conv2d_wgrad on the packed view) is ADDED to
+ *                        out[tap_o*s_tap + c3*s_c3 + c*s_c], tap_o = flip ? 8-tap : tap (as xmc_wgrad_c3) */
+int xmc_pad_c3_to_c8(const void* x, int N, int H, int W, void* out, void* stream);
+int xmc_pack_c3_weights(const void* w, int ldw, int Cout, void* out, void* stream);
+int xmc_unpack_c3_wgrad(const float* tmp, int C, int flip, long long s_tap, int s_c3, int s_c, float* out,
+                        void* stream);
 int xmc_conv_c3_in(const void* x, const void* w, int ldw, const float* bias, int N, int H, int W, int Cout, int KH,
                    int KW, int relu, void* y, void* stream);
 /* mode 0: y fp32 (+= if accumulate); mode 1: y = (tanh(v)+1)/2 fp32 plus bf16 copy y_bf16 */

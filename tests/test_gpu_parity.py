@@ -623,3 +623,42 @@ def test_generate_batch_and_checkpoint_round_trip(tmp_path):
   a, b = m1.compute(), m2.compute()
   for k in a:
     assert abs(a[k] - b[k]) <= 1e-3 * max(1.0, abs(a[k])), (k, a[k], b[k])   # atomics order only
+
+
+@gpu
+@pytest.mark.parametrize("N,S,C", [(2, 16, 16), (3, 32, 96), (1, 128, 96)])
+def test_packed_window_image_convs_match_oracle(N, S, C):
+  """The 3x3 convolutions with 3 image channels on the input side, run on the tcgen05 GEMM kernels over a
+  zero-bordered 8-channel copy of the image (K = 3 kh-taps x [3 kw x 8 channels]): forward (+bias, relu) 1e-3 rel-L2
+  (bf16 output), weight gradient 1e-4 (fp32 out) and the flipped / transposed indexing used for the generator's output
+  conv, all vs the oracle's conv2d / autograd on identical bf16 operands. The padded copy is an index op: exact."""
+  _, _, ops, *_ = _mods()
+  torch.manual_seed(S + C)
+  x = _q(torch.rand(N, S, S, 3))
+  kern = _q(torch.randn(3, 3, 3, C) * 0.2).requires_grad_(True)
+  bias = torch.randn(C)
+  want = torch.relu(orc.conv2d(x, kern, bias))
+  dy = _q(torch.randn(N, S, S, C) * 0.1)
+  orc.conv2d(x, kern, None).mul(dy).sum().backward()
+  xd = x.cuda().to(torch.bfloat16)
+  xpad = ops.c3_pad(xd)
+  ref_pad = torch.zeros(N, S + 2, S + 2, 8)
+  ref_pad[:, 1:-1, 1:-1, :3] = x
+  assert torch.equal(xpad.float().cpu(), ref_pad)
+  wk = kern.detach().permute(3, 0, 1, 2).reshape(C, 27)
+  wk32 = torch.zeros(C, 32)
+  wk32[:, :27] = wk
+  wp = ops.c3_pack_weights(wk32.cuda().to(torch.bfloat16), 32, C)
+  got = ops.c3_conv(xpad, wp, C, bias=bias.cuda(), relu=True)
+  assert got.shape == (N, S, S, C)
+  assert helpers.rel(got, want) < 4e-3
+  dw = torch.zeros(27 * C, device="cuda")
+  ops.c3_wgrad(xpad, dy.cuda().to(torch.bfloat16), 0, 3 * C, C, 1, dw)
+  assert helpers.rel(dw.view(3, 3, 3, C), kern.grad) < 1e-4
+  # generator output conv (C -> 3): dW[tap][ci][c3] = sum_p h[p + d(tap)][ci] * dpre[p][c3] in the flipped indexing
+  h = _q(torch.randn(N, S, S, C) * 0.5)
+  k2 = _q(torch.randn(3, 3, C, 3) * 0.1).requires_grad_(True)
+  orc.conv2d(h, k2, None).mul(x).sum().backward()      # x plays d(pre-tanh)
+  dw2 = torch.zeros(27 * C, device="cuda")
+  ops.c3_wgrad(xpad, h.cuda().to(torch.bfloat16), 1, C * 3, 1, 3, dw2)
+  assert helpers.rel(dw2.view(3, 3, C, 3), k2.grad) < 1e-4

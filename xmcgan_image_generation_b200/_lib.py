@@ -48,6 +48,8 @@ class WgradDesc(ctypes.Structure):
       ("ldOut", ctypes.c_int),
       ("out_tap_stride", ctypes.c_longlong), ("out_batch_stride", ctypes.c_longlong),
       ("alpha", ctypes.c_float), ("subpixel", ctypes.c_int),
+      ("HinA", ctypes.c_int),
+      ("pitchWA", ctypes.c_longlong), ("pitchHA", ctypes.c_longlong), ("pitchNA", ctypes.c_longlong),
   ]
 
 

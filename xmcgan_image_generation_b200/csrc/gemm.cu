@@ -768,7 +768,7 @@ extern "C" int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* w
 extern "C" int xmc_conv2d_wgrad(const XmcWgradDesc* d, const void* xa, const void* xb, void* dw, void* stream) {
   if (!d || !xa || !xb || !dw) return XMC_EINVAL;
   if (d->N < 1 || d->H < 1 || d->W < 1 || d->Ca < 1 || d->Cb < 1 || d->KH < 1 || d->KW < 1) return XMC_EINVAL;
-  if ((d->ldA % 8) || (d->ldB % 8) || d->ldA < d->Ca || d->ldB < d->Cb) return XMC_EINVAL;
+  if ((d->ldA % 8) || (d->ldB % 8) || (d->pitchWA <= 0 && d->ldA < d->Ca) || d->ldB < d->Cb) return XMC_EINVAL;
   if ((d->Ca % 8) || (d->Cb % 8)) return XMC_EINVAL;
   if (!aligned16(xa) || !aligned16(xb)) return XMC_EALIGN;
 
@@ -825,7 +825,16 @@ extern "C" int xmc_conv2d_wgrad(const XmcWgradDesc* d, const void* xa, const voi
               d->out_batch_stride % unit == 0) ? 1 : 0;
 
   CUtensorMap tmA, tmB;
-  {
+  if (d->pitchWA > 0) {
+    // re-pitched view of xa (packed-window convolutions): extents (Ca, W, HinA, N), caller-given pitches
+    if ((d->pitchWA % 8) || (d->pitchHA % 8) || (d->pitchNA % 8) || d->HinA < d->H || d->subpixel || d->batched)
+      return XMC_EINVAL;
+    uint64_t dims[4] = {(uint64_t)d->Ca, (uint64_t)d->W, (uint64_t)d->HinA, (uint64_t)d->N};
+    uint64_t str[3] = {(uint64_t)d->pitchWA * 2, (uint64_t)d->pitchHA * 2, (uint64_t)d->pitchNA * 2};
+    uint32_t box[4] = {64, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.tn};
+    int r = make_tmap(&tmA, xa, 4, dims, str, box);
+    if (r) return r;
+  } else {
     uint64_t dims[4] = {(uint64_t)d->Ca, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
     uint64_t str[3] = {(uint64_t)d->ldA * 2, (uint64_t)d->ldA * 2 * d->W, (uint64_t)d->ldA * 2 * d->W * d->H};
     uint32_t box[4] = {64, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.tn};

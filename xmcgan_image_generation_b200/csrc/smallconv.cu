@@ -311,6 +311,45 @@ __global__ void tanh01_bwd_kernel(const float* __restrict__ dimg, const float* _
   }
 }
 
+// ---- packed-window helpers: the 3-channel 3x3 convolutions on the tensor-core GEMM kernels ------------------------
+// out[n][h+1][w+1][0..2] = x[n][h][w][0..2]; everything else (1-pixel border, channels 3..7) zero. One thread per
+// output pixel writes one 16-byte vector.
+__global__ void pad_c3_to_c8_kernel(const bf16* __restrict__ x, int N, int H, int W, bf16* __restrict__ out) {
+  const int HP = H + 2, WP = W + 2;
+  const long long total = (long long)N * HP * WP;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int wp = idx % WP, hp = (idx / WP) % HP;
+    const long long n = idx / ((long long)WP * HP);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (hp >= 1 && hp <= H && wp >= 1 && wp <= W) {
+      const unsigned short* src =
+          reinterpret_cast<const unsigned short*>(x) + ((n * H + hp - 1) * W + wp - 1) * kImgC;
+      v.x = (uint32_t)src[0] | ((uint32_t)src[1] << 16);
+      v.y = (uint32_t)src[2];
+    }
+    reinterpret_cast<uint4*>(out)[idx] = v;
+  }
+}
+
+__global__ void pack_c3_weights_kernel(const bf16* __restrict__ w, int ldw, int Cout, bf16* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= Cout * 72) return;
+  const int co = t / 72, k = t - co * 72;
+  const int kh = k / 24, r = k - kh * 24, kw = r >> 3, c = r & 7;
+  out[t] = c < kImgC ? w[co * ldw + (kh * 3 + kw) * kImgC + c] : __float2bfloat16(0.f);
+}
+
+__global__ void unpack_c3_wgrad_kernel(const float* __restrict__ tmp, int C, int flip, long long s_tap, int s_c3,
+                                       int s_c, float* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 27 * C) return;
+  const int c = t % C, k = t / C;          // k = (kh*3+kw)*3 + c3
+  const int c3 = k % 3, tap = k / 3, kh = tap / 3, kw = tap - kh * 3;
+  const int tap_o = flip ? 8 - tap : tap;
+  out[tap_o * s_tap + c3 * s_c3 + (long long)c * s_c] += tmp[(kh * 24 + kw * 8 + c3) * C + c];
+}
+
 static int grid1d(long long total, int block) {
   long long g = (total + block - 1) / block;
   const long long cap = (long long)num_sms() * 16;
@@ -320,6 +359,30 @@ static int grid1d(long long total, int block) {
 }  // namespace xmc
 
 using namespace xmc;
+
+extern "C" int xmc_pad_c3_to_c8(const void* x, int N, int H, int W, void* out, void* stream) {
+  if (!x || !out || N < 1 || H < 1 || W < 1 || !aligned16(out)) return XMC_EINVAL;
+  pad_c3_to_c8_kernel<<<grid1d((long long)N * (H + 2) * (W + 2), 256), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, N, H, W, (bf16*)out);
+  XMC_LAUNCH_CHECK();
+  return XMC_OK;
+}
+
+extern "C" int xmc_pack_c3_weights(const void* w, int ldw, int Cout, void* out, void* stream) {
+  if (!w || !out || Cout < 1 || ldw < 27) return XMC_EINVAL;
+  pack_c3_weights_kernel<<<ceil_div(Cout * 72, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)w, ldw, Cout,
+                                                                                    (bf16*)out);
+  XMC_LAUNCH_CHECK();
+  return XMC_OK;
+}
+
+extern "C" int xmc_unpack_c3_wgrad(const float* tmp, int C, int flip, long long s_tap, int s_c3, int s_c, float* out,
+                                   void* stream) {
+  if (!tmp || !out || C < 1) return XMC_EINVAL;
+  unpack_c3_wgrad_kernel<<<ceil_div(27 * C, 256), 256, 0, (cudaStream_t)stream>>>(tmp, C, flip, s_tap, s_c3, s_c, out);
+  XMC_LAUNCH_CHECK();
+  return XMC_OK;
+}
 
 extern "C" int xmc_conv_c3_in(const void* x, const void* w, int ldw, const float* bias, int N, int H, int W, int Cout,
                               int KH, int KW, int relu, void* y, void* stream) {

@@ -89,9 +89,11 @@ def conv_fwd(x, wk, kh, cout, *, bias=None, residual=None, res_shift=0, mask=Non
 
 
 def wgrad(xa, xb, kh, out, *, out_mode=0, batched=False, ld_out=None, tap_stride=None, batch_stride=0, alpha=1.0,
-          ca=None, cb=None, subpixel=False):
-  """out[b][tap][ca][cb] (+)= sum_pixels xa[p+shift][ca] * xb[p][cb]. xa, xb: [N,H,W,C*] bf16 views."""
-  N, H, W = xa.shape[0], xa.shape[1], xa.shape[2]
+          ca=None, cb=None, subpixel=False, view_a=None):
+  """out[b][tap][ca][cb] (+)= sum_pixels xa[p+shift][ca] * xb[p][cb]. xa, xb: [N,H,W,C*] bf16 views.
+  view_a: dict re-pitching xa (packed-window form, see XmcWgradDesc.HinA): KH, KW, Hin, pitchW, pitchH, pitchN."""
+  # pixel grid of the reduction: xa's (the low-resolution input in sub-pixel mode), xb's for a re-pitched xa view
+  N, H, W = (xa if view_a is None else xb).shape[:3]
   _check_dense_rows(xa)
   _check_dense_rows(xb)
   d = WgradDesc()
@@ -101,6 +103,9 @@ def wgrad(xa, xb, kh, out, *, out_mode=0, batched=False, ld_out=None, tap_stride
   d.ldA, d.ldB = _pix_ld(xa), _pix_ld(xb)
   d.KH = d.KW = kh
   d.pad_h = d.pad_w = kh // 2
+  if view_a is not None:
+    d.KH, d.KW, d.pad_h, d.pad_w = view_a["KH"], view_a["KW"], 0, 0
+    d.HinA, d.pitchWA, d.pitchHA, d.pitchNA = view_a["Hin"], view_a["pitchW"], view_a["pitchH"], view_a["pitchN"]
   d.batched = 1 if batched else 0
   d.out_mode = out_mode
   d.ldOut = d.Cb if ld_out is None else ld_out
@@ -110,6 +115,47 @@ def wgrad(xa, xb, kh, out, *, out_mode=0, batched=False, ld_out=None, tap_stride
   d.subpixel = 1 if subpixel else 0
   _call("xmc_conv2d_wgrad", ctypes.byref(d), ptr(xa), ptr(xb), ptr(out), stream())
   return out
+
+
+# ------------------------------------------------------------------ 3-channel image convolutions (packed-window form)
+def c3_pad(x3):
+  """[N,H,W,3] bf16 -> zero-bordered 8-channel copy [N,H+2,W+2,8]: per output pixel and kh the 3 kw taps x 8 channels
+  are one contiguous 24-element run, which a tensor map with a 16-byte pixel pitch hands to the GEMM kernels."""
+  N, H, W, _ = x3.shape
+  out = empty((N, H + 2, W + 2, 8))
+  _call("xmc_pad_c3_to_c8", ptr(x3), N, H, W, ptr(out), stream())
+  return out
+
+
+def c3_pack_weights(w, ldw, cout):
+  """bf16 [cout][ldw] with k = tap*3+c (a forward or dgrad arena matrix) -> bf16 [cout][72] with k = kh*24+kw*8+c."""
+  out = empty((cout, 72))
+  _call("xmc_pack_c3_weights", ptr(w), ldw, cout, ptr(out), stream())
+  return out
+
+
+def _c3_view(xpad):
+  S = xpad.shape[1] - 2
+  WP = xpad.shape[2]
+  return dict(Hout=S, Wout=WP - 2, KH=3, KW=1, strideH=1, strideW=1, Hin=S + 2, Win=WP - 2, pitchW=8, pitchH=WP * 8,
+              pitchN=(S + 2) * WP * 8, real_taps=9, real_c=3)
+
+
+def c3_conv(xpad, wpacked, cout, **kw):
+  """conv3x3 (3 image channels -> cout) on the tcgen05 GEMM kernel: K = 3 kh-taps x 24 (two K=16 MMA slices each)."""
+  return conv_fwd(xpad, wpacked, 3, cout, ldb=72, c=24, view=_c3_view(xpad), **kw)
+
+
+def c3_wgrad(xpad, y, flip, s_tap, s_c3, s_c, out):
+  """out[tap_o*s_tap + c3*s_c3 + c*s_c] += sum_p x3[p + d(tap)][c3] * y[p][c] (the contract of xmc_wgrad_c3) on the
+  tcgen05 wgrad kernel: [3 kh][24][C] partial result, then a 27*C-element scatter-add."""
+  C = y.shape[3]
+  v = _c3_view(xpad)
+  tmp = zeros((3, 24, C))
+  LAUNCHES[0] += 1
+  wgrad(xpad, y, 3, tmp, out_mode=0, ld_out=C, tap_stride=24 * C, ca=24,
+        view_a=dict(KH=3, KW=1, Hin=v["Hin"], pitchW=8, pitchH=v["pitchH"], pitchN=v["pitchN"]))
+  _call("xmc_unpack_c3_wgrad", ptr(tmp), C, int(flip), s_tap, s_c3, s_c, ptr(out), stream())
 
 
 # --------------------------------------------------------------------------------------------------------- batch norm
