@@ -31,5 +31,17 @@ span = iv[-1][1] - iv[0][0]
 gaps = sorted(((iv[i + 1][0] - iv[i][1], iv[i][2][:50], iv[i + 1][2][:50]) for i in range(len(iv) - 1)), reverse=True)
 print(f"kernels {len(iv)}  busy {busy/1e3:.2f} ms  span {span/1e3:.2f} ms  idle {100*(span-busy)/span:.1f}%")
 print("gaps > 20us:", sum(1 for g in gaps if g[0] > 20), " total gap us:", sum(g[0] for g in gaps if g[0] > 0))
-for g in gaps[:12]:
+for g in gaps[:6]:
   print(f"  {g[0]:.1f} us between {g[1]} -> {g[2]}")
+import collections
+import re
+agg = collections.defaultdict(lambda: [0, 0.0])
+for a, b, name in iv:
+  k = re.sub(r"\(.*", "", name)[:70]
+  agg[k][0] += 1
+  agg[k][1] += (b - a) / 2e3   # ms per step (2 steps profiled)
+print("| ms/step | share | launches/step | kernel |")
+print("|---:|---:|---:|---|")
+tot = sum(v[1] for v in agg.values())
+for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
+  print(f"| {v[1]:.3f} | {100*v[1]/tot:.1f}% | {v[0]//2} | {k} |")

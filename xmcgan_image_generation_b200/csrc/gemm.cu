@@ -24,6 +24,8 @@ constexpr int kThreads = 192;     // wgrad kernel: TMA, MMA, 4 epilogue warps
 constexpr int kEpiParts = 3;      // forward kernel: epilogue warps per TMEM lane quarter
 constexpr int kThreadsFwd = 64 + 128 * kEpiParts;  // TMA warp, MMA warp, 4 * kEpiParts epilogue warps
 constexpr int kTmemCols = 512;
+constexpr int kBiasMax = 2048;    // forward kernel: floats of bias staged in shared memory
+constexpr int kSmemFwd = kSmemBytes + kBiasMax * 4;
 
 struct FwdParams {
   int tiles_w, tiles_h, tiles_n;
@@ -45,6 +47,7 @@ struct FwdParams {
   int ldRes, ldMask, res_shift, relu, mask_last;
   float alpha;
   int vec_ok;
+  int bias_smem;  // 1: the bias vector (Cout <= kBiasMax floats) is staged in shared memory by the epilogue warps
 };
 
 struct WgradParams {
@@ -128,6 +131,11 @@ gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
+  float* bias_s = reinterpret_cast<float*>(smem + kStages * kStageBytes + kBarBytes);
+  if (p.bias_smem && warp >= 2) {
+    for (int i = threadIdx.x - 64; i < p.Cout; i += kThreadsFwd - 64) bias_s[i] = p.bias[i];
+    asm volatile("bar.sync 1, %0;" ::"n"(kThreadsFwd - 64) : "memory");  // epilogue warps only
+  }
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   const int total_tiles = m_tiles * p.n_tiles * p.parities;
   const int taps = p.KH * p.KW;
@@ -232,23 +240,13 @@ gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
-      for (int c0 = half * 16; c0 < p.BN; c0 += 16 * kEpiParts) {
-        uint32_t v[16];
+      // One 16-column chunk = issue (TMEM load + the chunk's mask / residual vectors) ... finish (fused math, store).
+      // The chunks of a warp are software-pipelined over two register sets: chunk i+1 is issued before chunk i is
+      // finished, so its TMEM / global latency hides behind the math and the stores of chunk i.
+      auto issue = [&](int c0, uint32_t (&v)[16], uint4 (&mk)[2], uint4 (&rs)[2]) {
         tmem_ld16(t_addr + c0, v);  // asynchronous until tmem_ld_wait
         const int col = nt * p.BN + c0;
-        const bool active = row_ok && col < p.Cout;
-        const int nvalid = min(16, p.Cout - col);
-        const bool vec = p.vec_ok && nvalid == 16;
-        const bool fast = active && vec;
-        float4 bz[4];
-        uint4 mk[2], rs[2];
-        if (fast) {
-          // fast path: all operand loads are 16-byte vectors issued while the TMEM load is in flight
-          if (p.bias) {
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) bz[i] = __ldg(b4 + i);
-          }
+        if (row_ok && p.vec_ok && p.Cout - col >= 16) {
           if (p.mask) {
             const bf16* mp = p.mask + pix * p.ldMask + col;
             if (p.vec_ok == 2) {
@@ -268,19 +266,28 @@ gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
           }
         }
-        tmem_ld_wait();  // .sync.aligned: executed by the whole warp at a convergent point
-        if (fast) {
+      };
+      auto finish = [&](int c0, const uint32_t (&v)[16], const uint4 (&mk)[2], const uint4 (&rs)[2]) {
+        const int col = nt * p.BN + c0;
+        const bool active = row_ok && col < p.Cout;
+        const int nvalid = min(16, p.Cout - col);
+        if (active && p.vec_ok && nvalid == 16) {
           float f[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
           if (p.bias) {
+            // bias_s: the whole bias vector staged in shared memory once per CTA (an LDG per chunk was the single
+            // largest stall of the short-K epilogue); vectors too long for the staging area come from global memory
+            const float4* b4 = p.bias_smem ? reinterpret_cast<const float4*>(bias_s + col)
+                                           : reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              f[4 * i] += bz[i].x; f[4 * i + 1] += bz[i].y; f[4 * i + 2] += bz[i].z; f[4 * i + 3] += bz[i].w;
+              const float4 bz = b4[i];
+              f[4 * i] += bz.x; f[4 * i + 1] += bz.y; f[4 * i + 2] += bz.z; f[4 * i + 3] += bz.w;
             }
           }
+          const uint32_t rw_[8] = {rs[0].x, rs[0].y, rs[0].z, rs[0].w, rs[1].x, rs[1].y, rs[1].z, rs[1].w};
           if (p.residual && p.mask_last) {
-            const uint32_t rw_[8] = {rs[0].x, rs[0].y, rs[0].z, rs[0].w, rs[1].x, rs[1].y, rs[1].z, rs[1].w};
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               f[2 * i] += bf16_bits_to_float(rw_[i] & 0xFFFFu);
@@ -298,7 +305,6 @@ gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
           }
           if (p.residual && !p.mask_last) {
-            const uint32_t rw_[8] = {rs[0].x, rs[0].y, rs[0].z, rs[0].w, rs[1].x, rs[1].y, rs[1].z, rs[1].w};
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               f[2 * i] += bf16_bits_to_float(rw_[i] & 0xFFFFu);
@@ -334,26 +340,40 @@ gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 reinterpret_cast<float4*>(o)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
             }
           }
-        } else {
-          if (active) {
-            // generic path (ragged N edge or unaligned pitches): scalar accesses
-            float f[16];
+        } else if (active) {
+          // generic path (ragged N edge or unaligned pitches): scalar accesses
+          float f[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
+          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              if (i < nvalid) {
-                if (p.bias) f[i] += p.bias[col + i];
-                if (p.residual && p.mask_last) f[i] += __bfloat162float(p.residual[rpix * p.ldRes + col + i]);
-                if (p.mask && !(__bfloat162float(p.mask[pix * p.ldMask + col + i]) > 0.f)) f[i] = 0.f;
-                if (p.residual && !p.mask_last) f[i] += __bfloat162float(p.residual[rpix * p.ldRes + col + i]);
-                if (p.relu) f[i] = fmaxf(f[i], 0.f);
-                if (p.out_dtype == 0) reinterpret_cast<bf16*>(p.out)[pix * p.ldOut + col + i] = __float2bfloat16(f[i]);
-                else reinterpret_cast<float*>(p.out)[pix * p.ldOut + col + i] = f[i];
-              }
+          for (int i = 0; i < 16; ++i) {
+            if (i < nvalid) {
+              if (p.bias) f[i] += p.bias[col + i];
+              if (p.residual && p.mask_last) f[i] += __bfloat162float(p.residual[rpix * p.ldRes + col + i]);
+              if (p.mask && !(__bfloat162float(p.mask[pix * p.ldMask + col + i]) > 0.f)) f[i] = 0.f;
+              if (p.residual && !p.mask_last) f[i] += __bfloat162float(p.residual[rpix * p.ldRes + col + i]);
+              if (p.relu) f[i] = fmaxf(f[i], 0.f);
+              if (p.out_dtype == 0) reinterpret_cast<bf16*>(p.out)[pix * p.ldOut + col + i] = __float2bfloat16(f[i]);
+              else reinterpret_cast<float*>(p.out)[pix * p.ldOut + col + i] = f[i];
             }
           }
         }
+      };
+      constexpr int kStep = 16 * kEpiParts;
+      uint32_t va[16], vb[16];
+      uint4 mka[2], mkb[2], rsa[2], rsb[2];
+      int c0 = half * 16;
+      if (c0 < p.BN) issue(c0, va, mka, rsa);
+      while (c0 < p.BN) {  // all conditions are warp-uniform (tcgen05.ld / wait::ld are .sync.aligned)
+        tmem_ld_wait();
+        if (c0 + kStep < p.BN) issue(c0 + kStep, vb, mkb, rsb);
+        finish(c0, va, mka, rsa);
+        c0 += kStep;
+        if (c0 >= p.BN) break;
+        tmem_ld_wait();
+        if (c0 + kStep < p.BN) issue(c0 + kStep, va, mka, rsa);
+        finish(c0, vb, mkb, rsb);
+        c0 += kStep;
       }
       tc_fence_before();
       __syncwarp();
@@ -728,6 +748,7 @@ extern "C" int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* w
   if (residual) vec32 = vec32 && al32(residual) && (d->ldRes % 16 == 0);
   if (mask) vec32 = vec32 && al32(mask) && (d->ldMask % 16 == 0);
   p.vec_ok = vec32 ? 2 : (vec ? 1 : 0);
+  p.bias_smem = (bias && d->Cout <= kBiasMax && aligned16(bias)) ? 1 : 0;
 
   CUtensorMap tmA, tmB;
   {
@@ -755,12 +776,12 @@ extern "C" int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* w
     if (r) return r;
   }
   if (!g_attr_set_fwd) {
-    XMC_CUDA_CHECK(cudaFuncSetAttribute(gemm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    XMC_CUDA_CHECK(cudaFuncSetAttribute(gemm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFwd));
     g_attr_set_fwd = true;
   }
   const int total = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles * p.parities;
   const int grid = total < num_sms() ? total : num_sms();
-  gemm_fwd_kernel<<<grid, kThreadsFwd, kSmemBytes, (cudaStream_t)stream>>>(tmA, tmB, p);
+  gemm_fwd_kernel<<<grid, kThreadsFwd, kSmemFwd, (cudaStream_t)stream>>>(tmA, tmB, p);
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }

@@ -178,41 +178,58 @@ __global__ void prep_weights_kernel(const XmcPrepEntry* __restrict__ tab, int n,
 // columns). Writes the forward matrix wf[(a*2+b)*Cout + co][(dh*2+dw)*Cin + ci] and the input-gradient matrix
 // vd[ci][(r*4+s)*Cout + co] of the equivalent 4x4 / stride-2 / pad-1 convolution over the output gradient, where
 // row offset r-1 in {-1,0,1,2} <-> (a,dh) = (1,1),(0,1),(1,0),(0,0).
-__global__ void subpixel_prep_kernel(const float* __restrict__ w, const float* __restrict__ scale, int Cin, int Cout,
-                                     bf16* __restrict__ wf, bf16* __restrict__ vd) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)Cin * Cout) return;
-  const int co = idx % Cout, ci = idx / Cout;
+// One block = a 32(ci) x 32(co) tile. The 9 taps are read with co fastest (coalesced fp32 reads of the HWIO kernel), the
+// 16 parity/tap sums are staged in shared memory; vd (co contiguous) is written in the same orientation, wf (ci
+// contiguous) after a transpose through the staging tile, so both bf16 matrices are written in full 64-byte runs.
+__global__ void __launch_bounds__(256)
+subpixel_prep_kernel(const float* __restrict__ w, const float* __restrict__ scale, int Cin, int Cout,
+                     bf16* __restrict__ wf, bf16* __restrict__ vd) {
+  __shared__ bf16 tile[16][32][34];  // [a,dh,b,dw][ci][co], already rounded
+  const int ci0 = blockIdx.y * 32, co0 = blockIdx.x * 32;
   const float sc = scale ? *scale : 1.f;
-  float k[3][3];
-#pragma unroll
-  for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-    for (int kw = 0; kw < 3; ++kw) k[kh][kw] = w[((long long)(kh * 3 + kw) * Cin + ci) * Cout + co] * sc;
-  // row-combined: rc[a][dh][kw]
-  float rc[2][2][3];
-#pragma unroll
-  for (int kw = 0; kw < 3; ++kw) {
-    rc[0][0][kw] = k[0][kw];
-    rc[0][1][kw] = k[1][kw] + k[2][kw];
-    rc[1][0][kw] = k[0][kw] + k[1][kw];
-    rc[1][1][kw] = k[2][kw];
-  }
   const int r_of[2][2] = {{3, 1}, {2, 0}};  // r_of[a][dh]
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int ci = ci0 + r, co = co0 + threadIdx.x;
+    if (ci >= Cin || co >= Cout) continue;
+    float k[3][3];
 #pragma unroll
-  for (int a = 0; a < 2; ++a)
+    for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-    for (int dh = 0; dh < 2; ++dh)
+      for (int kw = 0; kw < 3; ++kw) k[kh][kw] = w[((long long)(kh * 3 + kw) * Cin + ci) * Cout + co] * sc;
+    float rc[2][2][3];  // row-combined: rc[a][dh][kw]
 #pragma unroll
-      for (int b = 0; b < 2; ++b)
+    for (int kw = 0; kw < 3; ++kw) {
+      rc[0][0][kw] = k[0][kw];
+      rc[0][1][kw] = k[1][kw] + k[2][kw];
+      rc[1][0][kw] = k[0][kw] + k[1][kw];
+      rc[1][1][kw] = k[2][kw];
+    }
 #pragma unroll
-        for (int dw = 0; dw < 2; ++dw) {
-          const float* r = rc[a][dh];
-          const float v = (b == 0) ? (dw == 0 ? r[0] : r[1] + r[2]) : (dw == 0 ? r[0] + r[1] : r[2]);
-          const bf16 q = __float2bfloat16(v);
-          wf[((long long)((a * 2 + b) * Cout + co)) * (4 * Cin) + (dh * 2 + dw) * Cin + ci] = q;
-          vd[(long long)ci * (16 * Cout) + (r_of[a][dh] * 4 + r_of[b][dw]) * Cout + co] = q;
-        }
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+          for (int dw = 0; dw < 2; ++dw) {
+            const float* q = rc[a][dh];
+            const float v = (b == 0) ? (dw == 0 ? q[0] : q[1] + q[2]) : (dw == 0 ? q[0] + q[1] : q[2]);
+            const bf16 qv = __float2bfloat16(v);
+            tile[((a * 2 + dh) * 2 + b) * 2 + dw][r][threadIdx.x] = qv;
+            vd[(long long)ci * (16 * Cout) + (r_of[a][dh] * 4 + r_of[b][dw]) * Cout + co] = qv;
+          }
+  }
+  __syncthreads();
+  // wf[(a*2+b)*Cout + co][(dh*2+dw)*Cin + ci]: ci fastest across the warp
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int co = co0 + r, ci = ci0 + threadIdx.x;
+    if (ci >= Cin || co >= Cout) continue;
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+      const int a = t >> 3, dh = (t >> 2) & 1, b = (t >> 1) & 1, dw = t & 1;
+      wf[((long long)((a * 2 + b) * Cout + co)) * (4 * Cin) + (dh * 2 + dw) * Cin + ci] = tile[t][threadIdx.x][r];
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------- Adam (+EMA)
@@ -294,9 +311,8 @@ extern "C" int xmc_prep_weights(const XmcPrepEntry* table_dev, int n, int total_
 extern "C" int xmc_subpixel_prep(const float* w, const float* scale, int Cin, int Cout, void* wf, void* vd,
                                  void* stream) {
   if (!w || !wf || !vd || Cin < 8 || Cout < 8 || (Cin % 8) || (Cout % 8)) return XMC_EINVAL;
-  const long long n = (long long)Cin * Cout;
-  subpixel_prep_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, (cudaStream_t)stream>>>(w, scale, Cin, Cout,
-                                                                                       (bf16*)wf, (bf16*)vd);
+  subpixel_prep_kernel<<<dim3(ceil_div(Cout, 32), ceil_div(Cin, 32)), dim3(32, 8), 0, (cudaStream_t)stream>>>(
+      w, scale, Cin, Cout, (bf16*)wf, (bf16*)vd);
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }

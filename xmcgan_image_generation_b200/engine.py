@@ -491,12 +491,16 @@ class GeneratorEngine:
     ops._call("xmc_tanh01_bwd", d_img.data_ptr(), ctx["img"].data_ptr(), d_img.numel(), dpre.data_ptr(), _lib.stream())
     r = self.convs[(self.cpre + "_1",)]
     C = self.c_last
-    # both gradients of the 3-channel output conv run on the tensor-core GEMMs over a zero-bordered 8-channel copy of
-    # d(pre-tanh) (packed-window form: K = 3 kh-taps x 24)
+    # the weight gradient of the 3-channel output conv runs on the tensor-core wgrad kernel over a zero-bordered
+    # 8-channel copy of d(pre-tanh) (packed-window form: M = 3 kw x 8 channels per kh tap)
     dpad = ops.c3_pad(dpre)
     ops.c3_wgrad(dpad, ctx["hf"], 1, C * 3, 1, 3, grads[r.w_off:])
     ops.colsum(dpre, grads[r.b_off:])
-    dhf = ops.c3_conv(dpad, ops.c3_pack_weights(self._wd(r), r.ld_dg, C), C)
+    # the input gradient stays on the CUDA-core kernel: as a GEMM it is a 3-k-iteration tile bound by the epilogue's
+    # latency (measured 0.42 ms vs 0.32 ms per 112-image launch); ops.c3_conv is the tensor-core form
+    dhf = ops.empty((B, S, S, C))
+    ops._call("xmc_conv_c3_in", dpre.data_ptr(), self._wd(r).data_ptr(), r.ld_dg, None, B, S, S, C, 3, 3, 0,
+              dhf.data_ptr(), _lib.stream())
     _, gf_, bf_ = self.bn_index[("LocalConditionalBatchNorm_0",)]
     dout = ops.bn_bwd(dhf, ctx["x_last"], ctx["mrf"], gbL, dgbL, Hc16, gf_, bf_, True, False, group=grp)
 
@@ -799,9 +803,12 @@ class DiscriminatorEngine:
     sc = ops.empty((N2, S // 2, S // 2, df))
     ops._call("xmc_conv_c3_in", xp.data_ptr(), self._wk(r2).data_ptr(), r2.ld_fwd, P[r2.b_off:].data_ptr(), N2, S // 2,
               S // 2, df, 1, 1, 0, sc.data_ptr(), _lib.stream())
-    # first conv (3 -> df, 3x3) in packed-window form on the tensor-core GEMM: zero-bordered 8-channel image copy
+    # first conv (3 -> df, 3x3): forward on the CUDA-core kernel (see GeneratorEngine.backward), its weight gradient
+    # on the tensor-core wgrad kernel over the zero-bordered 8-channel image copy made here
     xpad = ops.c3_pad(images)
-    c1r = ops.c3_conv(xpad, ops.c3_pack_weights(self._wk(r0), r0.ld_fwd, df), df, bias=P[r0.b_off:], relu=True)
+    c1r = ops.empty((N2, S, S, df))
+    ops._call("xmc_conv_c3_in", images.data_ptr(), self._wk(r0).data_ptr(), r0.ld_fwd, P[r0.b_off:].data_ptr(), N2, S, S,
+              df, 3, 3, 1, c1r.data_ptr(), _lib.stream())
     c2 = ops.conv_fwd(c1r, self._wk(r1), 3, df, bias=P[r1.b_off:], ldb=r1.ld_fwd)
     x, xr = ops.pool2(c2, low=sc, want_relu=True)
     del c2, sc
