@@ -8,6 +8,7 @@
 // SAME padding, image borders, ragged M/N/K edges and channel counts that are not a multiple of 64 are all handled
 // by TMA out-of-bounds zero fill; nothing is ever im2col'ed in memory.
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 #include <string.h>
 #include "common.h"
 #include "ptx.cuh"
@@ -26,6 +27,11 @@ constexpr int kThreadsFwd = 64 + 128 * kEpiParts;  // TMA warp, MMA warp, 4 * kE
 constexpr int kTmemCols = 512;
 constexpr int kBiasMax = 2048;    // forward kernel: floats of bias staged in shared memory
 constexpr int kSmemFwd = kSmemBytes + kBiasMax * 4;
+// resident-weights 3x3 kernel: all 9 taps of a [Cout <= 96][C <= 96] kernel + a 3-stage ring of 130-pixel halo rows
+constexpr int kResBBytes = 9 * (96 * 128 + 96 * 64);  // 165888
+constexpr int kResAStage = 17408;                     // 130 rows x 128 B, rounded up to the 1024 B swizzle repeat
+constexpr int kResStages = 3;
+constexpr int kSmemRes = kResBBytes + kResStages * kResAStage + kBarBytes + kBiasMax * 4 + 1024;
 
 struct FwdParams {
   int tiles_w, tiles_h, tiles_n;
@@ -47,6 +53,7 @@ struct FwdParams {
   int ldRes, ldMask, res_shift, relu, mask_last;
   float alpha;
   int vec_ok;
+  int halo;       // resident kernel: 1 = one 130-pixel halo row serves the three kw taps, 0 = one 128-pixel box per tap
   int bias_smem;  // 1: the bias vector (Cout <= kBiasMax floats) is staged in shared memory by the epilogue warps
 };
 
@@ -90,6 +97,148 @@ __device__ __forceinline__ void stg256(void* p, const uint4& a, const uint4& b) 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// Epilogue of one 128 x BN output tile for one warp: t_addr = TMEM address of the warp's 32 lanes in the tile's
+// accumulator, (row_ok, pix, rpix) = this lane's output row, `part` = which of the kEpiParts warps sharing the lane
+// quarter this is. Shared by the streaming and the resident-weights forward kernels.
+__device__ __forceinline__ void fwd_epilogue_tile(const FwdParams& p, uint32_t t_addr, int nt, bool row_ok,
+                                                  long long pix, long long rpix, const float* bias_s, int half) {
+  // One 16-column chunk = issue (TMEM load + the chunk's mask / residual vectors) ... finish (fused math, store).
+  // The chunks of a warp are software-pipelined over two register sets: chunk i+1 is issued before chunk i is
+  // finished, so its TMEM / global latency hides behind the math and the stores of chunk i.
+  auto issue = [&](int c0, uint32_t (&v)[16], uint4 (&mk)[2], uint4 (&rs)[2]) {
+    tmem_ld16(t_addr + c0, v);  // asynchronous until tmem_ld_wait
+    const int col = nt * p.BN + c0;
+    if (row_ok && p.vec_ok && p.Cout - col >= 16) {
+      if (p.mask) {
+        const bf16* mp = p.mask + pix * p.ldMask + col;
+        if (p.vec_ok == 2) {
+          ldg256(mp, mk[0], mk[1]);
+        } else {
+          mk[0] = __ldg(reinterpret_cast<const uint4*>(mp));
+          mk[1] = __ldg(reinterpret_cast<const uint4*>(mp) + 1);
+        }
+      }
+      if (p.residual) {
+        const bf16* rp = p.residual + rpix * p.ldRes + col;
+        if (p.vec_ok == 2) {
+          ldg256(rp, rs[0], rs[1]);
+        } else {
+          rs[0] = __ldg(reinterpret_cast<const uint4*>(rp));
+          rs[1] = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
+        }
+      }
+    }
+  };
+  auto finish = [&](int c0, const uint32_t (&v)[16], const uint4 (&mk)[2], const uint4 (&rs)[2]) {
+    const int col = nt * p.BN + c0;
+    const bool active = row_ok && col < p.Cout;
+    const int nvalid = min(16, p.Cout - col);
+    if (active && p.vec_ok && nvalid == 16) {
+      float f[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
+      if (p.bias) {
+        // bias_s: the whole bias vector staged in shared memory once per CTA (an LDG per chunk was the single
+        // largest stall of the short-K epilogue); vectors too long for the staging area come from global memory
+        const float4* b4 = p.bias_smem ? reinterpret_cast<const float4*>(bias_s + col)
+                                       : reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 bz = b4[i];
+          f[4 * i] += bz.x; f[4 * i + 1] += bz.y; f[4 * i + 2] += bz.z; f[4 * i + 3] += bz.w;
+        }
+      }
+      const uint32_t rw_[8] = {rs[0].x, rs[0].y, rs[0].z, rs[0].w, rs[1].x, rs[1].y, rs[1].z, rs[1].w};
+      if (p.residual && p.mask_last) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          f[2 * i] += bf16_bits_to_float(rw_[i] & 0xFFFFu);
+          f[2 * i + 1] += bf16_bits_to_float(rw_[i] >> 16);
+        }
+      }
+      if (p.mask) {
+        const uint32_t mw[8] = {mk[0].x, mk[0].y, mk[0].z, mk[0].w, mk[1].x, mk[1].y, mk[1].z, mk[1].w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+          const uint32_t lo = mw[i] & 0xFFFFu, hi = mw[i] >> 16;
+          if (!(lo != 0 && lo < 0x8000u)) f[2 * i] = 0.f;
+          if (!(hi != 0 && hi < 0x8000u)) f[2 * i + 1] = 0.f;
+        }
+      }
+      if (p.residual && !p.mask_last) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          f[2 * i] += bf16_bits_to_float(rw_[i] & 0xFFFFu);
+          f[2 * i + 1] += bf16_bits_to_float(rw_[i] >> 16);
+        }
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+      }
+      if (p.out_dtype == 0) {
+        bf16* o = reinterpret_cast<bf16*>(p.out) + pix * p.ldOut + col;
+        uint4 a, b;
+        a.x = pack_bf16x2(f[0], f[1]);   a.y = pack_bf16x2(f[2], f[3]);
+        a.z = pack_bf16x2(f[4], f[5]);   a.w = pack_bf16x2(f[6], f[7]);
+        b.x = pack_bf16x2(f[8], f[9]);   b.y = pack_bf16x2(f[10], f[11]);
+        b.z = pack_bf16x2(f[12], f[13]); b.w = pack_bf16x2(f[14], f[15]);
+        if (p.vec_ok == 2) {
+          stg256(o, a, b);
+        } else {
+          reinterpret_cast<uint4*>(o)[0] = a;
+          reinterpret_cast<uint4*>(o)[1] = b;
+        }
+      } else {
+        float* o = reinterpret_cast<float*>(p.out) + pix * p.ldOut + col;
+        if (p.vec_ok == 2) {
+          const uint4* fv = reinterpret_cast<const uint4*>(f);
+          stg256(o, fv[0], fv[1]);
+          stg256(o + 8, fv[2], fv[3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            reinterpret_cast<float4*>(o)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+        }
+      }
+    } else if (active) {
+      // generic path (ragged N edge or unaligned pitches): scalar accesses
+      float f[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        if (i < nvalid) {
+          if (p.bias) f[i] += p.bias[col + i];
+          if (p.residual && p.mask_last) f[i] += __bfloat162float(p.residual[rpix * p.ldRes + col + i]);
+          if (p.mask && !(__bfloat162float(p.mask[pix * p.ldMask + col + i]) > 0.f)) f[i] = 0.f;
+          if (p.residual && !p.mask_last) f[i] += __bfloat162float(p.residual[rpix * p.ldRes + col + i]);
+          if (p.relu) f[i] = fmaxf(f[i], 0.f);
+          if (p.out_dtype == 0) reinterpret_cast<bf16*>(p.out)[pix * p.ldOut + col + i] = __float2bfloat16(f[i]);
+          else reinterpret_cast<float*>(p.out)[pix * p.ldOut + col + i] = f[i];
+        }
+      }
+    }
+  };
+  constexpr int kStep = 16 * kEpiParts;
+  uint32_t va[16], vb[16];
+  uint4 mka[2], mkb[2], rsa[2], rsb[2];
+  int c0 = half * 16;
+  if (c0 < p.BN) issue(c0, va, mka, rsa);
+  while (c0 < p.BN) {  // all conditions are warp-uniform (tcgen05.ld / wait::ld are .sync.aligned)
+    tmem_ld_wait();
+    if (c0 + kStep < p.BN) issue(c0 + kStep, vb, mkb, rsb);
+    finish(c0, va, mka, rsa);
+    c0 += kStep;
+    if (c0 >= p.BN) break;
+    tmem_ld_wait();
+    if (c0 + kStep < p.BN) issue(c0 + kStep, va, mka, rsa);
+    finish(c0, vb, mkb, rsb);
+    c0 += kStep;
+  }
 }
 
 // =====================================================================================================================
@@ -240,141 +389,188 @@ gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
-      // One 16-column chunk = issue (TMEM load + the chunk's mask / residual vectors) ... finish (fused math, store).
-      // The chunks of a warp are software-pipelined over two register sets: chunk i+1 is issued before chunk i is
-      // finished, so its TMEM / global latency hides behind the math and the stores of chunk i.
-      auto issue = [&](int c0, uint32_t (&v)[16], uint4 (&mk)[2], uint4 (&rs)[2]) {
-        tmem_ld16(t_addr + c0, v);  // asynchronous until tmem_ld_wait
-        const int col = nt * p.BN + c0;
-        if (row_ok && p.vec_ok && p.Cout - col >= 16) {
-          if (p.mask) {
-            const bf16* mp = p.mask + pix * p.ldMask + col;
-            if (p.vec_ok == 2) {
-              ldg256(mp, mk[0], mk[1]);
-            } else {
-              mk[0] = __ldg(reinterpret_cast<const uint4*>(mp));
-              mk[1] = __ldg(reinterpret_cast<const uint4*>(mp) + 1);
-            }
-          }
-          if (p.residual) {
-            const bf16* rp = p.residual + rpix * p.ldRes + col;
-            if (p.vec_ok == 2) {
-              ldg256(rp, rs[0], rs[1]);
-            } else {
-              rs[0] = __ldg(reinterpret_cast<const uint4*>(rp));
-              rs[1] = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
-            }
-          }
-        }
-      };
-      auto finish = [&](int c0, const uint32_t (&v)[16], const uint4 (&mk)[2], const uint4 (&rs)[2]) {
-        const int col = nt * p.BN + c0;
-        const bool active = row_ok && col < p.Cout;
-        const int nvalid = min(16, p.Cout - col);
-        if (active && p.vec_ok && nvalid == 16) {
-          float f[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
-          if (p.bias) {
-            // bias_s: the whole bias vector staged in shared memory once per CTA (an LDG per chunk was the single
-            // largest stall of the short-K epilogue); vectors too long for the staging area come from global memory
-            const float4* b4 = p.bias_smem ? reinterpret_cast<const float4*>(bias_s + col)
-                                           : reinterpret_cast<const float4*>(p.bias + col);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 bz = b4[i];
-              f[4 * i] += bz.x; f[4 * i + 1] += bz.y; f[4 * i + 2] += bz.z; f[4 * i + 3] += bz.w;
-            }
-          }
-          const uint32_t rw_[8] = {rs[0].x, rs[0].y, rs[0].z, rs[0].w, rs[1].x, rs[1].y, rs[1].z, rs[1].w};
-          if (p.residual && p.mask_last) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              f[2 * i] += bf16_bits_to_float(rw_[i] & 0xFFFFu);
-              f[2 * i + 1] += bf16_bits_to_float(rw_[i] >> 16);
-            }
-          }
-          if (p.mask) {
-            const uint32_t mw[8] = {mk[0].x, mk[0].y, mk[0].z, mk[0].w, mk[1].x, mk[1].y, mk[1].z, mk[1].w};
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              // bf16 > 0  <=>  sign bit clear and magnitude non-zero
-              const uint32_t lo = mw[i] & 0xFFFFu, hi = mw[i] >> 16;
-              if (!(lo != 0 && lo < 0x8000u)) f[2 * i] = 0.f;
-              if (!(hi != 0 && hi < 0x8000u)) f[2 * i + 1] = 0.f;
-            }
-          }
-          if (p.residual && !p.mask_last) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              f[2 * i] += bf16_bits_to_float(rw_[i] & 0xFFFFu);
-              f[2 * i + 1] += bf16_bits_to_float(rw_[i] >> 16);
-            }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
-          }
-          if (p.out_dtype == 0) {
-            bf16* o = reinterpret_cast<bf16*>(p.out) + pix * p.ldOut + col;
-            uint4 a, b;
-            a.x = pack_bf16x2(f[0], f[1]);   a.y = pack_bf16x2(f[2], f[3]);
-            a.z = pack_bf16x2(f[4], f[5]);   a.w = pack_bf16x2(f[6], f[7]);
-            b.x = pack_bf16x2(f[8], f[9]);   b.y = pack_bf16x2(f[10], f[11]);
-            b.z = pack_bf16x2(f[12], f[13]); b.w = pack_bf16x2(f[14], f[15]);
-            if (p.vec_ok == 2) {
-              stg256(o, a, b);
-            } else {
-              reinterpret_cast<uint4*>(o)[0] = a;
-              reinterpret_cast<uint4*>(o)[1] = b;
-            }
-          } else {
-            float* o = reinterpret_cast<float*>(p.out) + pix * p.ldOut + col;
-            if (p.vec_ok == 2) {
-              const uint4* fv = reinterpret_cast<const uint4*>(f);
-              stg256(o, fv[0], fv[1]);
-              stg256(o + 8, fv[2], fv[3]);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                reinterpret_cast<float4*>(o)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-            }
-          }
-        } else if (active) {
-          // generic path (ragged N edge or unaligned pitches): scalar accesses
-          float f[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            if (i < nvalid) {
-              if (p.bias) f[i] += p.bias[col + i];
-              if (p.residual && p.mask_last) f[i] += __bfloat162float(p.residual[rpix * p.ldRes + col + i]);
-              if (p.mask && !(__bfloat162float(p.mask[pix * p.ldMask + col + i]) > 0.f)) f[i] = 0.f;
-              if (p.residual && !p.mask_last) f[i] += __bfloat162float(p.residual[rpix * p.ldRes + col + i]);
-              if (p.relu) f[i] = fmaxf(f[i], 0.f);
-              if (p.out_dtype == 0) reinterpret_cast<bf16*>(p.out)[pix * p.ldOut + col + i] = __float2bfloat16(f[i]);
-              else reinterpret_cast<float*>(p.out)[pix * p.ldOut + col + i] = f[i];
-            }
-          }
-        }
-      };
-      constexpr int kStep = 16 * kEpiParts;
-      uint32_t va[16], vb[16];
-      uint4 mka[2], mkb[2], rsa[2], rsb[2];
-      int c0 = half * 16;
-      if (c0 < p.BN) issue(c0, va, mka, rsa);
-      while (c0 < p.BN) {  // all conditions are warp-uniform (tcgen05.ld / wait::ld are .sync.aligned)
-        tmem_ld_wait();
-        if (c0 + kStep < p.BN) issue(c0 + kStep, vb, mkb, rsb);
-        finish(c0, va, mka, rsa);
-        c0 += kStep;
-        if (c0 >= p.BN) break;
-        tmem_ld_wait();
-        if (c0 + kStep < p.BN) issue(c0 + kStep, va, mka, rsa);
-        finish(c0, vb, mkb, rsb);
-        c0 += kStep;
+      fwd_epilogue_tile(p, t_addr, nt, row_ok, pix, rpix, bias_s, half);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// =====================================================================================================================
+// Resident-weights 3x3 convolution for the widest feature maps (C <= 96 channels, W a multiple of 128: the 96 -> 96
+// layers at 128x128 / 256x256). In the streaming kernel those layers are bound by L2 -> SM bandwidth, not by the
+// tensor pipe: every 128-pixel tile re-fetches all 9 weight taps (216 KB) and the same input row once per kw tap
+// (216 KB) for 2.6k cycles of MMA. Here
+//   * the whole weight tensor (9 taps x [Cout][64 + 32 channels], 162 KB at Cout = 96) is loaded ONCE per CTA and stays
+//     in shared memory; the ragged second channel chunk uses a 32-channel box in a SWIZZLE_64B layout so that it costs
+//     half the space (the A operand keeps its 128-byte rows: the two descriptors of an MMA are independent);
+//   * one 130-pixel halo row of the input per (kh, channel chunk) serves all three kw taps: the A descriptor of tap kw
+//     simply starts kw rows (kw * 128 bytes) into the tile.
+// L2 -> SM traffic per tile drops from 432 KB to 75 KB and the TMA request count from 36 to 6; the epilogue is the
+// streaming kernel's. Measured (112 x 128 x 128, 96 -> 96): 500 us -> 370 us. The halo rows are what pays: resident
+// weights alone (XMC_RESIDENT=2) are slower than streaming because only 3 ring stages fit beside them.
+// =====================================================================================================================
+__global__ void __launch_bounds__(kThreadsFwd, 1)
+conv3x3_resident_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                        const __grid_constant__ CUtensorMap tmB2, const FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_1024(smem_raw);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t sA = sbase + kResBBytes;
+  const uint32_t bar_base = sA + kResStages * kResAStage;
+  // barriers: full[kResStages], empty[kResStages], bfull, tfull[2], tempty[2], then the tmem pointer
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kResStages + s); };
+  const uint32_t bfull_bar = bar_base + 8u * (2 * kResStages);
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kResStages + 1 + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kResStages + 3 + a); };
+  uint8_t* bar_ptr = smem + kResBBytes + kResStages * kResAStage;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bar_ptr + 8 * (2 * kResStages + 5));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kResStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(bfull_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4 * kEpiParts);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_ptr_smem), kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  float* bias_s = reinterpret_cast<float*>(bar_ptr + kBarBytes);
+  if (p.bias_smem && warp >= 2) {
+    for (int i = threadIdx.x - 64; i < p.Cout; i += kThreadsFwd - 64) bias_s[i] = p.bias[i];
+    asm volatile("bar.sync 1, %0;" ::"n"(kThreadsFwd - 64) : "memory");
+  }
+
+  const int total_tiles = p.tiles_w * p.H * p.N;   // one tile = 128 pixels of one image row
+  const uint32_t bmain = (uint32_t)p.BN * 128u;    // bytes of one tap's [BN][64-channel] weight box
+  const uint32_t btail = (uint32_t)p.BN * 64u;     // bytes of one tap's [BN][32-channel] box (SWIZZLE_64B)
+  const uint32_t sBt = sbase + 9u * bmain;
+  const bool halo = p.halo != 0;
+  const uint32_t a_bytes = halo ? 130u * 128u : 128u * 128u;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+      // resident weights: all taps, both channel chunks, one barrier
+      mbar_arrive_expect_tx(bfull_bar, 9u * (bmain + (p.cchunks > 1 ? btail : 0u)));
+      for (int tap = 0; tap < 9; ++tap) {
+        tma_load_3d(sbase + tap * bmain, &tmB, bfull_bar, tap * p.C, 0, 0);
+        if (p.cchunks > 1) tma_load_3d(sBt + tap * btail, &tmB2, bfull_bar, tap * p.C + 64, 0, 0);
       }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int iw = tile % p.tiles_w;
+        const int h = (tile / p.tiles_w) % p.H;
+        const int n = tile / (p.tiles_w * p.H);
+        const int w0 = iw * 128;
+        for (int kh = 0; kh < 3; ++kh) {
+          for (int c = 0; c < p.cchunks; ++c) {
+            for (int kw = 0; kw < (halo ? 1 : 3); ++kw) {
+              mbar_wait(empty_bar(stage), phase ^ 1);
+              mbar_arrive_expect_tx(full_bar(stage), a_bytes);
+              tma_load_4d(sA + stage * kResAStage, &tmA, full_bar(stage), c * 64, w0 + kw - 1, h + kh - 1, n);
+              if (++stage == kResStages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    mbar_wait(bfull_bar, 0);
+    tc_fence_after();
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * 256;
+      uint32_t first = 1;
+      for (int kh = 0; kh < 3; ++kh) {
+        for (int c = 0; c < p.cchunks; ++c) {
+          const int nmma = (c == p.cchunks - 1) ? p.last_mmas : 4;
+          const bool last_kc = (kh == 2) && (c == p.cchunks - 1);
+          for (int ld = 0; ld < (halo ? 1 : 3); ++ld) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t sa = sA + stage * kResAStage;
+              for (int t = 0; t < (halo ? 3 : 1); ++t) {
+                const int kw = halo ? t : ld;
+                const int tap = kh * 3 + kw;
+                // halo tile: tap kw reads rows kw .. kw+127 of the 130-row tile (row = pixel, 128 B each)
+                const uint32_t shift = halo ? (uint32_t)kw : 0u;
+                // (measured on B200: the swizzle XOR is taken from the absolute shared-memory address, so a start address
+                // kw rows into the 1024-byte repeat needs NO base offset; setting it to kw gives wrong results)
+                const uint64_t adesc = make_smem_desc_ex(sa + shift * 128u, 16, 1024, 2, 0);
+                const uint64_t bdesc = (c == 0) ? make_smem_desc_ex(sbase + tap * bmain, 16, 1024, 2, 0)
+                                                : make_smem_desc_ex(sBt + tap * btail, 16, 512, 4, 0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  if (j < nmma) {
+                    umma_bf16(d_tmem, adesc + 2 * j, bdesc + 2 * j, p.idesc, first ? 0u : 1u);
+                    first = 0;
+                  }
+                }
+              }
+              umma_commit(empty_bar(stage));
+              if (last_kc && (halo || ld == 2)) umma_commit(tfull_bar(acc));
+            }
+            __syncwarp();
+            first = 0;
+            if (++stage == kResStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else {
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int iw = tile % p.tiles_w;
+      const int h = (tile / p.tiles_w) % p.H;
+      const int n = tile / (p.tiles_w * p.H);
+      const int w = iw * 128 + q * 32 + lane;
+      const bool row_ok = w < p.W;
+      const long long pix = ((long long)n * p.H + h) * p.W + w;
+      long long rpix = 0;
+      if (p.residual) {
+        const int Hs = p.H >> p.res_shift, Ws = p.W >> p.res_shift;
+        rpix = ((long long)n * Hs + (h >> p.res_shift)) * Ws + (w >> p.res_shift);
+      }
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
+      fwd_epilogue_tile(p, t_addr, 0, row_ok, pix, rpix, bias_s, half);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -642,7 +838,8 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 
 // bf16 tensor map, SWIZZLE_128B, zero OOB fill. dims/box innermost first; strides in bytes for dims 1..rank-1.
 static int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
-                     const uint32_t* box, const uint32_t* estrides = nullptr) {
+                     const uint32_t* box, const uint32_t* estrides = nullptr,
+                     CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   PFN_cuTensorMapEncodeTiled_v12000 fn = get_encode_fn();
   if (!fn) return XMC_ECUDA;
   cuuint64_t gdim[5], gstr[5];
@@ -654,7 +851,7 @@ static int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t
   }
   for (int i = 0; i < rank - 1; ++i) gstr[i] = strides[i];
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_cuda_error(cudaErrorInvalidValue);
@@ -749,6 +946,55 @@ extern "C" int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* w
   if (mask) vec32 = vec32 && al32(mask) && (d->ldMask % 16 == 0);
   p.vec_ok = vec32 ? 2 : (vec ? 1 : 0);
   p.bias_smem = (bias && d->Cout <= kBiasMax && aligned16(bias)) ? 1 : 0;
+
+  // ---- resident-weights path for the wide 3x3 layers (see conv3x3_resident_kernel) ------------------------------------
+  static int resident_mode = -1;  // XMC_RESIDENT: 0 = off, 1 = resident weights + halo rows (default), 2 = no halo
+  if (resident_mode < 0) {
+    const char* e = getenv("XMC_RESIDENT");
+    resident_mode = e ? atoi(e) : 1;
+  }
+  const int bn_res = ceil_div(d->Cout, 16) * 16;
+  const bool res_ok = resident_mode > 0 && d->KH == 3 && d->KW == 3 && d->pad_h == 1 && d->pad_w == 1 &&
+                      p.strideH == 1 && p.strideW == 1 && !d->batched && !d->subpixel && d->pitchW <= 0 &&
+                      d->Hin <= 0 && d->Win <= 0 && (d->W % 128) == 0 && d->C <= 96 && (d->C % 16) == 0 &&
+                      bn_res <= 256 && 9 * (bn_res * 128 + (d->C > 64 ? bn_res * 64 : 0)) <= kResBBytes;
+  if (res_ok) {
+    p.BN = bn_res;
+    p.n_tiles = 1;
+    p.tw = 128; p.th = 1; p.tn = 1;
+    p.tiles_w = d->W / 128; p.tiles_h = d->H; p.tiles_n = d->N;
+    p.idesc = make_idesc_bf16(128, p.BN, 0, 0);
+    p.halo = resident_mode == 1 ? 1 : 0;
+    CUtensorMap tmA, tmB, tmB2;
+    {
+      uint64_t dims[4] = {(uint64_t)d->C, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
+      uint64_t str[3] = {(uint64_t)d->ldA * 2, (uint64_t)d->ldA * 2 * d->W, (uint64_t)d->ldA * 2 * d->W * d->H};
+      uint32_t box[4] = {64, p.halo ? 130u : 128u, 1, 1};
+      int r = make_tmap(&tmA, x, 4, dims, str, box);
+      if (r) return r;
+    }
+    {
+      uint64_t dims[3] = {(uint64_t)9 * d->C, (uint64_t)d->Cout, 1};
+      uint64_t str[2] = {(uint64_t)d->ldB * 2, (uint64_t)d->ldB * 2 * d->Cout};
+      uint32_t box[3] = {64, (uint32_t)p.BN, 1};
+      int r = make_tmap(&tmB, wk, 3, dims, str, box);
+      if (r) return r;
+      uint32_t box2[3] = {32, (uint32_t)p.BN, 1};
+      r = make_tmap(&tmB2, wk, 3, dims, str, box2, nullptr, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (r) return r;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+      XMC_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          kSmemRes));
+      attr_set = true;
+    }
+    const int total = p.tiles_w * d->H * d->N;
+    const int grid = total < num_sms() ? total : num_sms();
+    conv3x3_resident_kernel<<<grid, kThreadsFwd, kSmemRes, (cudaStream_t)stream>>>(tmA, tmB, tmB2, p);
+    XMC_LAUNCH_CHECK();
+    return XMC_OK;
+  }
 
   CUtensorMap tmA, tmB;
   {

@@ -135,6 +135,20 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo,
   d |= (uint64_t)2 << 61;  // SWIZZLE_128B
   return d;
 }
+// General form: layout 2 = SWIZZLE_128B, 4 = SWIZZLE_64B. base_offset (bits 49-51) stays 0 in this code base even for
+// start addresses that are not aligned to the swizzle repeat: on B200 the swizzle XOR follows the absolute
+// shared-memory address (what TMA wrote), verified by the halo-row convolution kernel.
+__device__ __forceinline__ uint64_t make_smem_desc_ex(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout,
+                                                      uint32_t base_offset) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(base_offset & 7) << 49;
+  d |= (uint64_t)(layout & 7) << 61;
+  return d;
+}
 // Instruction descriptor: bf16 A/B, fp32 accumulate.
 __host__ __device__ inline uint32_t make_idesc_bf16(uint32_t M, uint32_t N, uint32_t a_mn_major, uint32_t b_mn_major) {
   uint32_t d = 0;
