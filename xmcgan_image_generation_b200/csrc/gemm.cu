@@ -53,7 +53,6 @@ struct FwdParams {
   int ldRes, ldMask, res_shift, relu, mask_last;
   float alpha;
   int vec_ok;
-  int halo;       // resident kernel: 1 = one 130-pixel halo row serves the three kw taps, 0 = one 128-pixel box per tap
   int bias_smem;  // 1: the bias vector (Cout <= kBiasMax floats) is staged in shared memory by the epilogue warps
 };
 
@@ -413,9 +412,9 @@ gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 //     half the space (the A operand keeps its 128-byte rows: the two descriptors of an MMA are independent);
 //   * one 130-pixel halo row of the input per (kh, channel chunk) serves all three kw taps: the A descriptor of tap kw
 //     simply starts kw rows (kw * 128 bytes) into the tile.
-// L2 -> SM traffic per tile drops from 432 KB to 75 KB and the TMA request count from 36 to 6; the epilogue is the
-// streaming kernel's. Measured (112 x 128 x 128, 96 -> 96): 500 us -> 370 us. The halo rows are what pays: resident
-// weights alone (XMC_RESIDENT=2) are slower than streaming because only 3 ring stages fit beside them.
+// L2 -> SM traffic per 128 output pixels drops from 432 KB to 50 KB and the TMA request count from 36 to 4; the
+// epilogue is the streaming kernel's. Measured (112 x 128 x 128, 96 -> 96): streaming 500 us, resident weights alone
+// 567 us (only 3 ring stages fit beside them), + halo rows 370 us, + two output rows per tile: see DESIGN.md.
 // =====================================================================================================================
 __global__ void __launch_bounds__(kThreadsFwd, 1)
 conv3x3_resident_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -463,12 +462,14 @@ conv3x3_resident_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     asm volatile("bar.sync 1, %0;" ::"n"(kThreadsFwd - 64) : "memory");
   }
 
-  const int total_tiles = p.tiles_w * p.H * p.N;   // one tile = 128 pixels of one image row
+  // one tile = 128 pixels of TWO consecutive image rows (h, h+1): the four input rows h-1 .. h+2 it needs are each
+  // loaded once and feed up to two accumulators (row h with kh = ir, row h+1 with kh = ir-1), which doubles the MMA
+  // work per TMA box and with it the latency the 3-stage ring can hide
+  const int hpairs = p.H >> 1;
+  const int total_tiles = p.tiles_w * hpairs * p.N;
   const uint32_t bmain = (uint32_t)p.BN * 128u;    // bytes of one tap's [BN][64-channel] weight box
   const uint32_t btail = (uint32_t)p.BN * 64u;     // bytes of one tap's [BN][32-channel] box (SWIZZLE_64B)
   const uint32_t sBt = sbase + 9u * bmain;
-  const bool halo = p.halo != 0;
-  const uint32_t a_bytes = halo ? 130u * 128u : 128u * 128u;
 
   if (warp == 0) {
     if (elect_one()) {
@@ -484,17 +485,16 @@ conv3x3_resident_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int iw = tile % p.tiles_w;
-        const int h = (tile / p.tiles_w) % p.H;
-        const int n = tile / (p.tiles_w * p.H);
+        const int h = 2 * ((tile / p.tiles_w) % hpairs);
+        const int n = tile / (p.tiles_w * hpairs);
         const int w0 = iw * 128;
-        for (int kh = 0; kh < 3; ++kh) {
+        for (int ir = 0; ir < 4; ++ir) {
           for (int c = 0; c < p.cchunks; ++c) {
-            for (int kw = 0; kw < (halo ? 1 : 3); ++kw) {
-              mbar_wait(empty_bar(stage), phase ^ 1);
-              mbar_arrive_expect_tx(full_bar(stage), a_bytes);
-              tma_load_4d(sA + stage * kResAStage, &tmA, full_bar(stage), c * 64, w0 + kw - 1, h + kh - 1, n);
-              if (++stage == kResStages) { stage = 0; phase ^= 1; }
-            }
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            mbar_arrive_expect_tx(full_bar(stage), 130u * 128u);
+            // 130-pixel halo row (w0-1 .. w0+128) of input row h-1+ir; image borders are TMA zero fill = SAME padding
+            tma_load_4d(sA + stage * kResAStage, &tmA, full_bar(stage), c * 64, w0 - 1, h - 1 + ir, n);
+            if (++stage == kResStages) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -509,42 +509,37 @@ conv3x3_resident_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       mbar_wait(tempty_bar(acc), acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * 256;
-      uint32_t first = 1;
-      for (int kh = 0; kh < 3; ++kh) {
+      for (int ir = 0; ir < 4; ++ir) {
         for (int c = 0; c < p.cchunks; ++c) {
           const int nmma = (c == p.cchunks - 1) ? p.last_mmas : 4;
-          const bool last_kc = (kh == 2) && (c == p.cchunks - 1);
-          for (int ld = 0; ld < (halo ? 1 : 3); ++ld) {
-            mbar_wait(full_bar(stage), phase);
-            tc_fence_after();
-            if (elect_one()) {
-              const uint32_t sa = sA + stage * kResAStage;
-              for (int t = 0; t < (halo ? 3 : 1); ++t) {
-                const int kw = halo ? t : ld;
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t sa = sA + stage * kResAStage;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {       // output row h + r uses this input row as filter row kh = ir - r
+              const int kh = ir - r;
+              if (kh < 0 || kh > 2) continue;
+              const uint32_t d_tmem = tmem_base + acc * 256 + r * 128;
+              for (int kw = 0; kw < 3; ++kw) {
                 const int tap = kh * 3 + kw;
-                // halo tile: tap kw reads rows kw .. kw+127 of the 130-row tile (row = pixel, 128 B each)
-                const uint32_t shift = halo ? (uint32_t)kw : 0u;
-                // (measured on B200: the swizzle XOR is taken from the absolute shared-memory address, so a start address
-                // kw rows into the 1024-byte repeat needs NO base offset; setting it to kw gives wrong results)
-                const uint64_t adesc = make_smem_desc_ex(sa + shift * 128u, 16, 1024, 2, 0);
+                // tap kw reads rows kw .. kw+127 of the 130-row tile (row = pixel, 128 B each). The swizzle XOR follows
+                // the absolute shared-memory address (what TMA wrote), so a start address kw rows into the 1024-byte
+                // repeat needs no base offset (measured on B200: setting it to kw gives wrong results).
+                const uint64_t adesc = make_smem_desc_ex(sa + kw * 128u, 16, 1024, 2, 0);
                 const uint64_t bdesc = (c == 0) ? make_smem_desc_ex(sbase + tap * bmain, 16, 1024, 2, 0)
                                                 : make_smem_desc_ex(sBt + tap * btail, 16, 512, 4, 0);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  if (j < nmma) {
-                    umma_bf16(d_tmem, adesc + 2 * j, bdesc + 2 * j, p.idesc, first ? 0u : 1u);
-                    first = 0;
-                  }
-                }
+                for (int j = 0; j < 4; ++j)
+                  if (j < nmma)
+                    umma_bf16(d_tmem, adesc + 2 * j, bdesc + 2 * j, p.idesc, (kh | c | kw | j) ? 1u : 0u);
               }
-              umma_commit(empty_bar(stage));
-              if (last_kc && (halo || ld == 2)) umma_commit(tfull_bar(acc));
             }
-            __syncwarp();
-            first = 0;
-            if (++stage == kResStages) { stage = 0; phase ^= 1; }
+            umma_commit(empty_bar(stage));
+            if (ir == 3 && c == p.cchunks - 1) umma_commit(tfull_bar(acc));
           }
+          __syncwarp();
+          if (++stage == kResStages) { stage = 0; phase ^= 1; }
         }
       }
       acc ^= 1;
@@ -557,20 +552,23 @@ conv3x3_resident_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int iw = tile % p.tiles_w;
-      const int h = (tile / p.tiles_w) % p.H;
-      const int n = tile / (p.tiles_w * p.H);
+      const int h0 = 2 * ((tile / p.tiles_w) % hpairs);
+      const int n = tile / (p.tiles_w * hpairs);
       const int w = iw * 128 + q * 32 + lane;
       const bool row_ok = w < p.W;
-      const long long pix = ((long long)n * p.H + h) * p.W + w;
-      long long rpix = 0;
-      if (p.residual) {
-        const int Hs = p.H >> p.res_shift, Ws = p.W >> p.res_shift;
-        rpix = ((long long)n * Hs + (h >> p.res_shift)) * Ws + (w >> p.res_shift);
-      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
-      fwd_epilogue_tile(p, t_addr, 0, row_ok, pix, rpix, bias_s, half);
+      for (int r = 0; r < 2; ++r) {
+        const int h = h0 + r;
+        const long long pix = ((long long)n * p.H + h) * p.W + w;
+        long long rpix = 0;
+        if (p.residual) {
+          const int Hs = p.H >> p.res_shift, Ws = p.W >> p.res_shift;
+          rpix = ((long long)n * Hs + (h >> p.res_shift)) * Ws + (w >> p.res_shift);
+        }
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + r * 128;
+        fwd_epilogue_tile(p, t_addr, 0, row_ok, pix, rpix, bias_s, half);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -948,7 +946,7 @@ extern "C" int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* w
   p.bias_smem = (bias && d->Cout <= kBiasMax && aligned16(bias)) ? 1 : 0;
 
   // ---- resident-weights path for the wide 3x3 layers (see conv3x3_resident_kernel) ------------------------------------
-  static int resident_mode = -1;  // XMC_RESIDENT: 0 = off, 1 = resident weights + halo rows (default), 2 = no halo
+  static int resident_mode = -1;  // XMC_RESIDENT=0 switches the path off (debugging aid)
   if (resident_mode < 0) {
     const char* e = getenv("XMC_RESIDENT");
     resident_mode = e ? atoi(e) : 1;
@@ -956,20 +954,19 @@ extern "C" int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* w
   const int bn_res = ceil_div(d->Cout, 16) * 16;
   const bool res_ok = resident_mode > 0 && d->KH == 3 && d->KW == 3 && d->pad_h == 1 && d->pad_w == 1 &&
                       p.strideH == 1 && p.strideW == 1 && !d->batched && !d->subpixel && d->pitchW <= 0 &&
-                      d->Hin <= 0 && d->Win <= 0 && (d->W % 128) == 0 && d->C <= 96 && (d->C % 16) == 0 &&
-                      bn_res <= 256 && 9 * (bn_res * 128 + (d->C > 64 ? bn_res * 64 : 0)) <= kResBBytes;
+                      d->Hin <= 0 && d->Win <= 0 && (d->W % 128) == 0 && (d->H % 2) == 0 && d->C <= 96 &&
+                      (d->C % 16) == 0 && bn_res <= 128 && 9 * (bn_res * 128 + (d->C > 64 ? bn_res * 64 : 0)) <= kResBBytes;
   if (res_ok) {
     p.BN = bn_res;
     p.n_tiles = 1;
     p.tw = 128; p.th = 1; p.tn = 1;
     p.tiles_w = d->W / 128; p.tiles_h = d->H; p.tiles_n = d->N;
     p.idesc = make_idesc_bf16(128, p.BN, 0, 0);
-    p.halo = resident_mode == 1 ? 1 : 0;
     CUtensorMap tmA, tmB, tmB2;
     {
       uint64_t dims[4] = {(uint64_t)d->C, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
       uint64_t str[3] = {(uint64_t)d->ldA * 2, (uint64_t)d->ldA * 2 * d->W, (uint64_t)d->ldA * 2 * d->W * d->H};
-      uint32_t box[4] = {64, p.halo ? 130u : 128u, 1, 1};
+      uint32_t box[4] = {64, 130, 1, 1};
       int r = make_tmap(&tmA, x, 4, dims, str, box);
       if (r) return r;
     }
@@ -989,7 +986,7 @@ extern "C" int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* w
                                           kSmemRes));
       attr_set = true;
     }
-    const int total = p.tiles_w * d->H * d->N;
+    const int total = p.tiles_w * (d->H / 2) * d->N;
     const int grid = total < num_sms() ? total : num_sms();
     conv3x3_resident_kernel<<<grid, kThreadsFwd, kSmemRes, (cudaStream_t)stream>>>(tmA, tmB, tmB2, p);
     XMC_LAUNCH_CHECK();
