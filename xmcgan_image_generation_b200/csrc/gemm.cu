@@ -66,6 +66,7 @@ struct WgradParams {
   int batched;
   int items_per_split, total_items;
   int subpixel;         // 1: 16 parity taps (a,dh,b,dw); B is the 2x up-sampled gradient read with stride 2
+  int tap3;             // 1: items are filter rows; the three kw taps share one 66-pixel halo chunk of A (3 accumulators)
   uint32_t slab_bytes;  // bytes one TMA box writes
   uint32_t idesc;
   void* out;
@@ -631,6 +632,9 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // A slab slot: 64 pixels x 128 B, or the 66-pixel halo chunk of tap3 mode rounded up to the 1024 B swizzle repeat
+  const uint32_t a_slab = p.tap3 ? 9216u : 8192u;
+  const uint32_t acc_cols = (uint32_t)((p.BN + 31) / 32) * 32u;  // tap3: column pitch of the three kw accumulators
 
   // item -> (split, batch, tap, m tile, n tile)
   auto decode = [&](int item, int& split, int& bz, int& tap, int& mt, int& nt) {
@@ -652,6 +656,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx = (2 + p.nslabs) * p.slab_bytes;
+      const uint32_t tx3 = 2u * 66u * 128u + p.nslabs * p.slab_bytes;
       for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
         int split, bz, tap, mt, nt;
         decode(item, split, bz, tap, mt, nt);
@@ -665,6 +670,9 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int kh = tap / p.KW, kw = tap - kh * p.KW;
           ah = kh - p.pad_h; aw = kw - p.pad_w;
         }
+        if (p.tap3) {  // item = filter ROW kh: one 66-pixel halo chunk of A serves the three kw taps
+          ah = tap - p.pad_h; aw = -p.pad_w;
+        }
         const int j0 = split * p.chunks_per_split;
         const int j1 = min(p.total_chunks, j0 + p.chunks_per_split);
         const int m0 = mt * 128, n_off = nt * p.BN;
@@ -674,12 +682,12 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int in = j / (p.chunks_w * p.chunks_h);
           const int w0 = iw * p.tw, h0 = ih * p.th, n0 = p.batched ? bz : in * p.tn;
           mbar_wait(empty_bar(stage), phase ^ 1);
-          mbar_arrive_expect_tx(full_bar(stage), tx);
+          mbar_arrive_expect_tx(full_bar(stage), p.tap3 ? tx3 : tx);
           const uint32_t sa = sbase + stage * kStageBytes;
           tma_load_4d(sa, &tmA, full_bar(stage), m0, w0 + aw, h0 + ah, n0);
-          tma_load_4d(sa + 8192, &tmA, full_bar(stage), m0 + 64, w0 + aw, h0 + ah, n0);
+          tma_load_4d(sa + a_slab, &tmA, full_bar(stage), m0 + 64, w0 + aw, h0 + ah, n0);
           for (int s = 0; s < p.nslabs; ++s)
-            tma_load_4d(sa + kABytes + s * 8192, &tmB, full_bar(stage), n_off + s * 64, bs * w0 + bw, bs * h0 + bh,
+            tma_load_4d(sa + 2 * a_slab + s * 8192, &tmB, full_bar(stage), n_off + s * 64, bs * w0 + bw, bs * h0 + bh,
                         n0);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -703,12 +711,25 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (elect_one()) {
           const uint32_t sa = sbase + stage * kStageBytes;
           // MN-major SW128: LBO = byte distance between 64-channel slabs, SBO = distance between 8-pixel groups.
-          const uint64_t adesc = make_smem_desc(sa, 8192, 1024);
-          const uint64_t bdesc = make_smem_desc(sa + kABytes, 8192, 1024);
+          const uint64_t adesc = make_smem_desc(sa, a_slab, 1024);
+          const uint64_t bdesc = make_smem_desc(sa + 2 * a_slab, 8192, 1024);
+          if (p.tap3) {
+            // tap kw multiplies pixels kw .. kw+63 of the 66-pixel halo chunk (one pixel = one 128 B row; the start
+            // address moves kw rows into the swizzle repeat, the XOR follows the absolute address) into its own
+            // accumulator: three taps per loaded chunk
 #pragma unroll
-          for (int s = 0; s < 4; ++s) {
-            // 16 pixels (K) per MMA = two 8-pixel groups = 2048 bytes: +128 in the (addr>>4) field
-            umma_bf16(d_tmem, adesc + 128 * s, bdesc + 128 * s, p.idesc, (j > j0 || s > 0) ? 1u : 0u);
+            for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+              for (int s = 0; s < 4; ++s)
+                umma_bf16(tmem_base + kw * acc_cols, adesc + 8 * kw + 128 * s, bdesc + 128 * s, p.idesc,
+                          (j > j0 || s > 0) ? 1u : 0u);
+            }
+          } else {
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+              // 16 pixels (K) per MMA = two 8-pixel groups = 2048 bytes: +128 in the (addr>>4) field
+              umma_bf16(d_tmem, adesc + 128 * s, bdesc + 128 * s, p.idesc, (j > j0 || s > 0) ? 1u : 0u);
+            }
           }
           umma_commit(empty_bar(stage));
           if (j == j1 - 1) umma_commit(tfull_bar(acc));
@@ -716,8 +737,12 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      if (p.tap3) {  // the three kw accumulators fill TMEM: single-buffered, the barrier pair just alternates phase
+        acc_phase ^= 1;
+      } else {
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
     }
   } else {
     const int q = warp & 3;
@@ -731,12 +756,13 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const bool row_ok = m < p.Ca;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
+      for (int kw3 = 0; kw3 < (p.tap3 ? 3 : 1); ++kw3) {
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (p.tap3 ? kw3 * acc_cols : acc * 256);
       // destinations: a plain tap writes its own [Ca][Cb] matrix; a sub-pixel parity tap (a,dh,b,dw) is the gradient of
       // a SUM of 3x3 taps, W_a[dh] = sum_{kh in S(a,dh)} W[kh] with S(0,0)={0}, S(0,1)={1,2}, S(1,0)={0,1}, S(1,1)={2},
       // so it is added to every (kh, kw) in S(a,dh) x S(b,dw)
       int dest[4], ndest = 1;
-      dest[0] = tap;
+      dest[0] = p.tap3 ? tap * 3 + kw3 : tap;  // tap3: item = filter row `tap`, accumulator = kw
       if (p.subpixel) {
         const int a = (tap >> 3) & 1, dh = (tap >> 2) & 1, b = (tap >> 1) & 1, dw = tap & 1;
         const int kh0 = (a == 0) ? (dh == 0 ? 0 : 1) : (dh == 0 ? 0 : 2), nkh = (a != dh) ? 2 : 1;
@@ -803,11 +829,16 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
       }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      if (p.tap3) {
+        acc_phase ^= 1;
+      } else {
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
     }
   }
   tc_fence_before();
@@ -1050,7 +1081,18 @@ extern "C" int xmc_conv2d_wgrad(const XmcWgradDesc* d, const void* xa, const voi
   p.nslabs = ceil_div(p.BN, 64);
   const int m_tiles = ceil_div(d->Ca, 128);
   if (d->subpixel && (d->KH != 3 || d->KW != 3 || d->out_mode != 0 || d->batched)) return XMC_EINVAL;
-  const int taps = d->subpixel ? 16 : d->KH * d->KW;
+  // tap3: for 3x3 kernels on rows of >= 64 pixels whose three kw accumulators fit TMEM (Cb <= 160), a work item is a
+  // filter ROW: one 66-pixel halo chunk of xa and one chunk of xb feed three taps (3x less operand traffic; these
+  // narrow-channel layers are L2 -> SM bandwidth bound). XMC_WGRAD_TAP3=0 switches it off (debugging aid).
+  static int tap3_mode = -1;
+  if (tap3_mode < 0) {
+    const char* e = getenv("XMC_WGRAD_TAP3");
+    tap3_mode = e ? atoi(e) : 1;
+  }
+  p.tap3 = (tap3_mode && d->KH == 3 && d->KW == 3 && d->pad_h == 1 && d->pad_w == 1 && !d->subpixel && !d->batched &&
+            d->pitchWA <= 0 && d->out_mode == 0 && d->W >= 64 && p.n_tiles == 1 && 3 * (((p.BN + 31) / 32) * 32) <= 512)
+               ? 1 : 0;
+  const int taps = d->subpixel ? 16 : (p.tap3 ? 3 : d->KH * d->KW);
   p.subpixel = d->subpixel ? 1 : 0;
   const int nbatch = d->batched ? d->N : 1;
   const int base_ctas = m_tiles * p.n_tiles * taps * nbatch;
@@ -1101,7 +1143,7 @@ extern "C" int xmc_conv2d_wgrad(const XmcWgradDesc* d, const void* xa, const voi
   } else {
     uint64_t dims[4] = {(uint64_t)d->Ca, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
     uint64_t str[3] = {(uint64_t)d->ldA * 2, (uint64_t)d->ldA * 2 * d->W, (uint64_t)d->ldA * 2 * d->W * d->H};
-    uint32_t box[4] = {64, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.tn};
+    uint32_t box[4] = {64, (uint32_t)(p.tap3 ? p.tw + 2 : p.tw), (uint32_t)p.th, (uint32_t)p.tn};
     int r = make_tmap(&tmA, xa, 4, dims, str, box);
     if (r) return r;
   }
