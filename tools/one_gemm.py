@@ -1,4 +1,5 @@
-"""GPU debugging aid: runs one conv_fwd shape in a loop (for ncu). python tools/one_gemm.py N H W C k Cout [res] [relu]"""
+"""GPU debugging aid: runs one conv_fwd (or, with the `wgrad` flag, one weight-gradient) shape in a loop (for ncu).
+python tools/one_gemm.py N H W C k Cout [res] [relu] [wgrad]"""
 import os
 import sys
 
@@ -13,6 +14,22 @@ x = (torch.randn(N, H, W, C, device="cuda") * 0.5).to(torch.bfloat16)
 wk = (torch.randn(Cout, k * k * C, device="cuda") * 0.05).to(torch.bfloat16)
 bias = torch.randn(Cout, device="cuda")
 res = (torch.randn(N, H, W, Cout, device="cuda")).to(torch.bfloat16) if "res" in flags else None
+if "wgrad" in flags:
+  dy = (torch.randn(N, H, W, Cout, device="cuda") * 0.1).to(torch.bfloat16)
+  dw = torch.zeros(k * k * C * Cout, device="cuda")
+  run = lambda: ops.wgrad(x, dy, k, dw, out_mode=0, ld_out=Cout, tap_stride=C * Cout)
+  for _ in range(3):
+    run()
+  torch.cuda.synchronize()
+  s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  s.record()
+  for _ in range(10):
+    run()
+  e.record()
+  torch.cuda.synchronize()
+  ms = s.elapsed_time(e) / 10
+  print(f"wgrad {ms*1e3:.1f} us  {2.0 * N * H * W * k * k * C * Cout / ms / 1e9:.1f} TFLOP/s")
+  sys.exit(0)
 for _ in range(3):
   y = ops.conv_fwd(x, wk, k, Cout, bias=bias, residual=res, relu="relu" in flags)
 torch.cuda.synchronize()
