@@ -224,47 +224,84 @@ __global__ void attn_g_bwd_kernel(const bf16* __restrict__ dctx, int ld_dctx, co
 // alpha[i][r][jw] = softmax_r(gamma1 * S[i*R+r][jw]) (softmax over REGIONS, attention_lib.py:125); also alpha^T.
 // The reference adds -1e9 to padded-word columns before the region softmax; those columns are dropped again by the
 // word mask of the LSE (attention_lib.py:164-165), so they are computed unmasked here.
-__global__ void wl_softmax_kernel(const float* __restrict__ S, int B, int R, int BL, int ldS, float gamma1,
-                                  bf16* __restrict__ alpha, bf16* __restrict__ alphaT) {
+// One block = image i x 32 columns jw, 256 threads as (32 columns) x (8 row groups): every global access is a run of 32
+// consecutive jw (S, alpha) or 32 consecutive r (alpha^T); the [R][32] tile lives in shared memory between the passes.
+constexpr int kWlMaxR = 256;
+__global__ void __launch_bounds__(256)
+wl_softmax_kernel(const float* __restrict__ S, int B, int R, int BL, int ldS, float gamma1,
+                  bf16* __restrict__ alpha, bf16* __restrict__ alphaT) {
+  __shared__ float tile[kWlMaxR][33];
+  __shared__ float red[8][33];
   const int i = blockIdx.y;
-  const int jw = blockIdx.x * blockDim.x + threadIdx.x;
-  if (jw >= ldS) return;
-  const float* s = S + (long long)i * R * ldS + jw;
-  bf16* a = alpha + (long long)i * R * ldS + jw;
-  if (jw >= BL) {
-    for (int r = 0; r < R; ++r) a[(long long)r * ldS] = __float2bfloat16(0.f);
-    return;
-  }
+  const int cx = threadIdx.x, ry = threadIdx.y;
+  const int jw = blockIdx.x * 32 + cx;
+  const bool live = jw < BL;
+  const long long base = (long long)i * R * ldS + jw;
   float mx = -3.0e38f;
-  for (int r = 0; r < R; ++r) mx = fmaxf(mx, s[(long long)r * ldS]);
+  for (int r = ry; r < R; r += 8) {
+    const float v = live ? S[base + (long long)r * ldS] : 0.f;
+    tile[r][cx] = v;
+    mx = fmaxf(mx, v);
+  }
+  red[ry][cx] = mx;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 8; ++k) mx = fmaxf(mx, red[k][cx]);
+  __syncthreads();
   float sum = 0.f;
-  for (int r = 0; r < R; ++r) sum += __expf(gamma1 * (s[(long long)r * ldS] - mx));
+  for (int r = ry; r < R; r += 8) {
+    const float e = __expf(gamma1 * (tile[r][cx] - mx));
+    tile[r][cx] = e;
+    sum += e;
+  }
+  red[ry][cx] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) sum += red[k][cx];
   const float rs = 1.f / sum;
-  bf16* at = alphaT + ((long long)i * ldS + jw) * R;
-  for (int r = 0; r < R; ++r) {
-    const bf16 v = __float2bfloat16(__expf(gamma1 * (s[(long long)r * ldS] - mx)) * rs);
-    a[(long long)r * ldS] = v;
-    at[r] = v;
+  for (int r = ry; r < R; r += 8) {
+    const bf16 v = __float2bfloat16(live ? tile[r][cx] * rs : 0.f);
+    tile[r][cx] = __bfloat162float(v);
+    if (jw < ldS) alpha[base + (long long)r * ldS] = v;   // padded columns [BL, ldS) are written as zeros
+  }
+  __syncthreads();
+  // alpha^T[i][jw][r]: one warp per column, lanes along r
+  for (int c = ry; c < 32; c += 8) {
+    const int jc = blockIdx.x * 32 + c;
+    if (jc >= BL) continue;
+    bf16* at = alphaT + ((long long)i * ldS + jc) * R;
+    for (int r = cx; r < R; r += 32) at[r] = __float2bfloat16(tile[r][c]);
   }
 }
 
-// dS = gamma1 * alpha * (dalpha - sum_r alpha*dalpha)
-__global__ void wl_softmax_bwd_kernel(const bf16* __restrict__ alpha, const float* __restrict__ dalpha, int B, int R,
-                                      int BL, int ldS, float gamma1, bf16* __restrict__ dS) {
+// dS = gamma1 * alpha * (dalpha - sum_r alpha*dalpha); same block shape as the forward kernel
+__global__ void __launch_bounds__(256)
+wl_softmax_bwd_kernel(const bf16* __restrict__ alpha, const float* __restrict__ dalpha, int B, int R,
+                      int BL, int ldS, float gamma1, bf16* __restrict__ dS) {
+  __shared__ float red[8][33];
   const int i = blockIdx.y;
-  const int jw = blockIdx.x * blockDim.x + threadIdx.x;
-  if (jw >= ldS) return;
+  const int cx = threadIdx.x, ry = threadIdx.y;
+  const int jw = blockIdx.x * 32 + cx;
+  const bool live = jw < BL;
   const long long base = (long long)i * R * ldS + jw;
-  if (jw >= BL) {
-    for (int r = 0; r < R; ++r) dS[base + (long long)r * ldS] = __float2bfloat16(0.f);
-    return;
-  }
   float t = 0.f;
-  for (int r = 0; r < R; ++r)
-    t += __bfloat162float(alpha[base + (long long)r * ldS]) * dalpha[base + (long long)r * ldS];
-  for (int r = 0; r < R; ++r) {
-    const float a = __bfloat162float(alpha[base + (long long)r * ldS]);
-    dS[base + (long long)r * ldS] = __float2bfloat16(gamma1 * a * (dalpha[base + (long long)r * ldS] - t));
+  if (live)
+    for (int r = ry; r < R; r += 8)
+      t += __bfloat162float(alpha[base + (long long)r * ldS]) * dalpha[base + (long long)r * ldS];
+  red[ry][cx] = t;
+  __syncthreads();
+  t = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) t += red[k][cx];
+  if (jw >= ldS) return;
+  for (int r = ry; r < R; r += 8) {
+    float v = 0.f;
+    if (live) {
+      const float a = __bfloat162float(alpha[base + (long long)r * ldS]);
+      v = gamma1 * a * (dalpha[base + (long long)r * ldS] - t);
+    }
+    dS[base + (long long)r * ldS] = __float2bfloat16(v);
   }
 }
 
@@ -417,9 +454,9 @@ extern "C" int xmc_attention_g_bwd(const void* dctx, int ld_dctx, const void* q,
 
 extern "C" int xmc_wl_softmax(const float* S, int B, int R, int BL, int ldS, float gamma1, void* alpha, void* alphaT,
                               void* stream) {
-  if (!S || !alpha || !alphaT || B < 1 || R < 1 || BL < 1 || ldS < BL) return XMC_EINVAL;
-  wl_softmax_kernel<<<dim3(ceil_div(ldS, 128), B), 128, 0, (cudaStream_t)stream>>>(S, B, R, BL, ldS, gamma1,
-                                                                                  (bf16*)alpha, (bf16*)alphaT);
+  if (!S || !alpha || !alphaT || B < 1 || R < 1 || R > kWlMaxR || BL < 1 || ldS < BL) return XMC_EINVAL;
+  wl_softmax_kernel<<<dim3(ceil_div(ldS, 32), B), dim3(32, 8), 0, (cudaStream_t)stream>>>(S, B, R, BL, ldS, gamma1,
+                                                                                         (bf16*)alpha, (bf16*)alphaT);
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }
@@ -427,8 +464,8 @@ extern "C" int xmc_wl_softmax(const float* S, int B, int R, int BL, int ldS, flo
 extern "C" int xmc_wl_softmax_bwd(const void* alpha, const float* dalpha, int B, int R, int BL, int ldS, float gamma1,
                                   void* dS, void* stream) {
   if (!alpha || !dalpha || !dS || B < 1 || R < 1 || BL < 1 || ldS < BL) return XMC_EINVAL;
-  wl_softmax_bwd_kernel<<<dim3(ceil_div(ldS, 128), B), 128, 0, (cudaStream_t)stream>>>((const bf16*)alpha, dalpha, B, R,
-                                                                                      BL, ldS, gamma1, (bf16*)dS);
+  wl_softmax_bwd_kernel<<<dim3(ceil_div(ldS, 32), B), dim3(32, 8), 0, (cudaStream_t)stream>>>(
+      (const bf16*)alpha, dalpha, B, R, BL, ldS, gamma1, (bf16*)dS);
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }

@@ -366,15 +366,21 @@ gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int half = (warp - 2) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
+    // this lane's row of every tile: (rw, rh, rn) inside the tw x th x tn pixel box. Hoisted out of the tile loop,
+    // and the tile decode skips the divisions of the common n_tiles == 1 / parities == 1 cases: on short-K tiles the
+    // epilogue is the critical path and a dozen emulated integer divisions per tile are a visible part of it.
+    const int r = q * 32 + lane;
+    const int rw = r % p.tw, rh = (r / p.tw) % p.th, rn = r / (p.tw * p.th);
+    const int tiles_wh = p.tiles_w * p.tiles_h;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int nt = tile % p.n_tiles;
-      const int t2 = tile / p.n_tiles;
-      const int par = t2 % p.parities, mt = t2 / p.parities;
-      const int iw = mt % p.tiles_w;
-      const int ih = (mt / p.tiles_w) % p.tiles_h;
-      const int in = mt / (p.tiles_w * p.tiles_h);
-      const int r = q * 32 + lane;
-      const int rw = r % p.tw, rh = (r / p.tw) % p.th, rn = r / (p.tw * p.th);
+      int nt = 0, t2 = tile;
+      if (p.n_tiles > 1) { nt = tile % p.n_tiles; t2 = tile / p.n_tiles; }
+      int par = 0, mt = t2;
+      if (p.parities > 1) { par = t2 & 3; mt = t2 >> 2; }
+      const int in = mt / tiles_wh;
+      const int rem = mt - in * tiles_wh;
+      const int ih = rem / p.tiles_w;
+      const int iw = rem - ih * p.tiles_w;
       const int w = iw * p.tw + rw, h = ih * p.th + rh, n = in * p.tn + rn;
       const bool row_ok = (rn < p.tn) && (n < p.N) && (h < p.H) && (w < p.W);
       // sub-pixel mode scatters the tile into the 2x up-sampled output at (2h+a, 2w+b)
