@@ -780,13 +780,15 @@ def resnet50_apply(variables, x, policy=FP32):
 
 
 def get_pretrained_embs(variables, images, policy=FP32, size=224):
-  """pretrained_model_utils.get_pretrained_embs (pretrained_model_utils.py:102-127): bilinear resize to 224 (half-pixel
-  centres; identical to torch align_corners=False when up-sampling), then the frozen network."""
+  """pretrained_model_utils.get_pretrained_embs (pretrained_model_utils.py:102-127): jax.image.resize "bilinear" to 224
+  (half-pixel centres; identical to torch align_corners=False when up-sampling; when down-sampling — the 256 px
+  configuration — jax widens the triangle kernel by the scale factor and renormalises, which is torch's
+  antialias=True), then the frozen network."""
   if images.dim() != 4 or images.shape[3] != 3:
     raise ValueError("images should be of shape (H, W, 3).")
   if images.shape[1] != size and images.shape[2] != size:
-    images = F.interpolate(images.permute(0, 3, 1, 2), size=(size, size), mode="bilinear",
-                           align_corners=False).permute(0, 2, 3, 1)
+    images = F.interpolate(images.permute(0, 3, 1, 2), size=(size, size), mode="bilinear", align_corners=False,
+                           antialias=images.shape[1] > size).permute(0, 2, 3, 1)
   return resnet50_apply(variables, images, policy)
 
 

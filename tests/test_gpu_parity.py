@@ -662,3 +662,28 @@ def test_packed_window_image_convs_match_oracle(N, S, C):
   dw2 = torch.zeros(27 * C, device="cuda")
   ops.c3_wgrad(xpad, h.cuda().to(torch.bfloat16), 1, C * 3, 1, 3, dw2)
   assert helpers.rel(dw2.view(3, 3, C, 3), k2.grad) < 1e-4
+
+
+@gpu
+@pytest.mark.parametrize("S", [128, 256])
+def test_bilinear_resize_to_224_matches_jax_semantics(S):
+  """jax.image.resize(..., "bilinear") of get_pretrained_embs (pretrained_model_utils.py:118-121): 128 -> 224 is plain
+  half-pixel bilinear; 256 -> 224 down-samples with the triangle kernel widened by 256/224 and renormalised (== torch
+  antialias=True, which the oracle uses). Forward 4e-3 (bf16 output), transpose (backward) 1e-5 vs autograd."""
+  _, _, ops, *_ = _mods()
+  from xmcgan_image_generation_b200 import _lib
+  torch.manual_seed(S)
+  n, T, TP, PAD = 2, 224, 229, 2
+  img = torch.rand(n, S, S, 3, requires_grad=True)
+  want = torch.nn.functional.interpolate(img.permute(0, 3, 1, 2), size=(T, T), mode="bilinear", align_corners=False,
+                                         antialias=S > T).permute(0, 2, 3, 1)
+  out = ops.empty((n, TP, TP, 8))
+  ops._call("xmc_resize_bilinear_pad", img.detach().cuda().data_ptr(), n, S, T, TP, PAD, out.data_ptr(), _lib.stream())
+  got = out.float().cpu()
+  assert helpers.rel(got[:, PAD:PAD + T, PAD:PAD + T, :3], want) < 4e-3
+  assert got[:, :PAD].abs().max() == 0 and got[..., 3:].abs().max() == 0      # zero border, zero pad channels
+  d = torch.randn(n, T, T, 3)
+  (want * d).sum().backward()
+  dimg = torch.zeros(n, S, S, 3, device="cuda")
+  ops._call("xmc_resize_bilinear_bwd", d.cuda().data_ptr(), n, S, T, dimg.data_ptr(), _lib.stream())
+  assert helpers.rel(dimg, img.grad) < 1e-5

@@ -136,5 +136,12 @@ def ptr(t):
   return t.data_ptr()
 
 
+_RAW_STREAM = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream():
+  """Raw cudaStream_t of torch's current stream on the current device (every kernel of the library launches on it).
+  The raw getter is ~10x cheaper than building a torch.cuda.Stream object, and this runs once per kernel launch."""
+  if _RAW_STREAM is not None:
+    return _RAW_STREAM(torch.cuda.current_device())
   return torch.cuda.current_stream().cuda_stream

@@ -7,13 +7,38 @@
 
 namespace xmc {
 
-// jax.image.resize(..., "bilinear") when up-sampling: half-pixel centres, 2-tap triangle weights, renormalised at the
-// borders (== index clamping). Writes a zero-bordered, 8-channel bf16 buffer [N, Tp, Tp, 8] (image at offset pad_lo)
-// so that the stride-2 7x7 stem can read (kw, c) as one contiguous 56-element run per output pixel.
+// jax.image.resize(..., "bilinear") (pretrained_model_utils.py:118-121): half-pixel centres, triangle kernel widened by
+// the down-scaling factor (anti-aliasing: kernel scale ks = max(S/T, 1)), taps outside the image dropped and the rest
+// renormalised. Up-sampling (128 -> 224) has 2 taps per axis, the 256 -> 224 case up to 3; kMaxTaps bounds S/T <= 1.5.
+// One axis: output index o -> taps j in [lo, lo+cnt) with normalised weights w[].
+constexpr int kMaxTaps = 4;
+__device__ __forceinline__ int resize_taps(int o, int S, float inv_scale, float ks, float* w) {
+  const float center = (o + 0.5f) * inv_scale - 0.5f;
+  int lo = (int)ceilf(center - ks), hi = (int)floorf(center + ks);
+  lo = max(lo, 0);
+  hi = min(hi, S - 1);
+  int cnt = hi - lo + 1;
+  if (cnt > kMaxTaps) cnt = kMaxTaps;
+  float sum = 0.f;
+#pragma unroll
+  for (int t = 0; t < kMaxTaps; ++t) {
+    const float v = (t < cnt) ? fmaxf(0.f, 1.f - fabsf((float)(lo + t) - center) / ks) : 0.f;
+    w[t] = v;
+    sum += v;
+  }
+  const float inv = sum > 0.f ? 1.f / sum : 0.f;
+#pragma unroll
+  for (int t = 0; t < kMaxTaps; ++t) w[t] *= inv;
+  return lo;
+}
+
+// Writes a zero-bordered, 8-channel bf16 buffer [N, Tp, Tp, 8] (image at offset pad_lo) so that the stride-2 7x7 stem
+// can read (kw, c) as one contiguous 56-element run per output pixel.
 __global__ void resize_bilinear_pad_kernel(const float* __restrict__ img, int N, int S, int T, int Tp, int pad_lo,
                                            bf16* __restrict__ out) {
   const long long total = (long long)N * Tp * Tp;
-  const float scale = (float)S / (float)T;
+  const float inv_scale = (float)S / (float)T;
+  const float ks = fmaxf(inv_scale, 1.f);
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int xp = idx % Tp, yp = (idx / Tp) % Tp;
@@ -23,17 +48,20 @@ __global__ void resize_bilinear_pad_kernel(const float* __restrict__ img, int N,
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i] = 0.f;
     if (x >= 0 && x < T && y >= 0 && y < T) {
-      const float sx = (x + 0.5f) * scale - 0.5f, sy = (y + 0.5f) * scale - 0.5f;
-      const float fx0 = floorf(sx), fy0 = floorf(sy);
-      const float wx = sx - fx0, wy = sy - fy0;
-      const int x0 = max(0, min(S - 1, (int)fx0)), x1 = max(0, min(S - 1, (int)fx0 + 1));
-      const int y0 = max(0, min(S - 1, (int)fy0)), y1 = max(0, min(S - 1, (int)fy0 + 1));
+      float wx[kMaxTaps], wy[kMaxTaps];
+      const int x0 = resize_taps(x, S, inv_scale, ks, wx);
+      const int y0 = resize_taps(y, S, inv_scale, ks, wy);
       const float* b = img + n * S * S * 3;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float v00 = b[(y0 * S + x0) * 3 + c], v01 = b[(y0 * S + x1) * 3 + c];
-        const float v10 = b[(y1 * S + x0) * 3 + c], v11 = b[(y1 * S + x1) * 3 + c];
-        o[c] = (1.f - wy) * ((1.f - wx) * v00 + wx * v01) + wy * ((1.f - wx) * v10 + wx * v11);
+      for (int ty = 0; ty < kMaxTaps; ++ty) {
+        if (wy[ty] == 0.f) continue;
+#pragma unroll
+        for (int tx = 0; tx < kMaxTaps; ++tx) {
+          if (wx[tx] == 0.f) continue;
+          const float wgt = wy[ty] * wx[tx];
+          const float* px = b + ((long long)(y0 + ty) * S + x0 + tx) * 3;
+          o[0] += wgt * px[0]; o[1] += wgt * px[1]; o[2] += wgt * px[2];
+        }
       }
     }
     store8(out + idx * 8, o);
@@ -44,24 +72,27 @@ __global__ void resize_bilinear_pad_kernel(const float* __restrict__ img, int N,
 __global__ void resize_bilinear_bwd_kernel(const float* __restrict__ dout, int N, int S, int T,
                                            float* __restrict__ dimg) {
   const long long total = (long long)N * T * T;
-  const float scale = (float)S / (float)T;
+  const float inv_scale = (float)S / (float)T;
+  const float ks = fmaxf(inv_scale, 1.f);
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int x = idx % T, y = (idx / T) % T;
     const long long n = idx / ((long long)T * T);
-    const float sx = (x + 0.5f) * scale - 0.5f, sy = (y + 0.5f) * scale - 0.5f;
-    const float fx0 = floorf(sx), fy0 = floorf(sy);
-    const float wx = sx - fx0, wy = sy - fy0;
-    const int x0 = max(0, min(S - 1, (int)fx0)), x1 = max(0, min(S - 1, (int)fx0 + 1));
-    const int y0 = max(0, min(S - 1, (int)fy0)), y1 = max(0, min(S - 1, (int)fy0 + 1));
+    float wx[kMaxTaps], wy[kMaxTaps];
+    const int x0 = resize_taps(x, S, inv_scale, ks, wx);
+    const int y0 = resize_taps(y, S, inv_scale, ks, wy);
     float* b = dimg + n * S * S * 3;
+    const float g0 = dout[idx * 3], g1 = dout[idx * 3 + 1], g2 = dout[idx * 3 + 2];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float g = dout[idx * 3 + c];
-      atomicAdd(b + (y0 * S + x0) * 3 + c, (1.f - wy) * (1.f - wx) * g);
-      atomicAdd(b + (y0 * S + x1) * 3 + c, (1.f - wy) * wx * g);
-      atomicAdd(b + (y1 * S + x0) * 3 + c, wy * (1.f - wx) * g);
-      atomicAdd(b + (y1 * S + x1) * 3 + c, wy * wx * g);
+    for (int ty = 0; ty < kMaxTaps; ++ty) {
+      if (wy[ty] == 0.f) continue;
+#pragma unroll
+      for (int tx = 0; tx < kMaxTaps; ++tx) {
+        if (wx[tx] == 0.f) continue;
+        const float wgt = wy[ty] * wx[tx];
+        float* px = b + ((long long)(y0 + ty) * S + x0 + tx) * 3;
+        atomicAdd(px, wgt * g0); atomicAdd(px + 1, wgt * g1); atomicAdd(px + 2, wgt * g2);
+      }
     }
   }
 }
@@ -242,7 +273,7 @@ using namespace xmc;
 
 extern "C" int xmc_resize_bilinear_pad(const float* img, int N, int S, int T, int Tp, int pad_lo, void* out,
                                        void* stream) {
-  if (!img || !out || N < 1 || S < 1 || T < S || Tp < T + pad_lo) return XMC_EINVAL;
+  if (!img || !out || N < 1 || S < 1 || T < 1 || 2 * S > 3 * T || Tp < T + pad_lo) return XMC_EINVAL;
   resize_bilinear_pad_kernel<<<grid1((long long)N * Tp * Tp, 256), 256, 0, (cudaStream_t)stream>>>(img, N, S, T, Tp,
                                                                                                    pad_lo, (bf16*)out);
   XMC_LAUNCH_CHECK();
@@ -250,7 +281,7 @@ extern "C" int xmc_resize_bilinear_pad(const float* img, int N, int S, int T, in
 }
 
 extern "C" int xmc_resize_bilinear_bwd(const float* dout, int N, int S, int T, float* dimg, void* stream) {
-  if (!dout || !dimg || N < 1 || S < 1 || T < S) return XMC_EINVAL;
+  if (!dout || !dimg || N < 1 || S < 1 || T < 1 || 2 * S > 3 * T) return XMC_EINVAL;
   resize_bilinear_bwd_kernel<<<grid1((long long)N * T * T, 256), 256, 0, (cudaStream_t)stream>>>(dout, N, S, T, dimg);
   XMC_LAUNCH_CHECK();
   return XMC_OK;
