@@ -99,6 +99,57 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// Lean epilogue for the commonest short-K case, compiled without any of the generic machinery (no mask, alpha == 1,
+// bf16 output, 32-byte aligned pitches, Cout % 16 == 0, bias staged in shared memory): kRes adds the residual.
+template <bool kRes>
+__device__ __forceinline__ void fwd_epilogue_tile_lean(const FwdParams& p, uint32_t t_addr, int nt, bool row_ok,
+                                                       long long pix, long long rpix, const float* bias_s, int half) {
+  const int col0 = nt * p.BN;
+  const int ncols = p.Cout - col0;
+  const float* b_row = bias_s + col0;
+  bf16* o_row = reinterpret_cast<bf16*>(p.out) + pix * p.ldOut + col0;
+  const bf16* r_row = kRes ? p.residual + rpix * p.ldRes + col0 : nullptr;
+  const bool relu = p.relu != 0;
+  for (int c0 = half * 16; c0 < p.BN; c0 += 16 * kEpiParts) {
+    uint32_t v[16];
+    tmem_ld16(t_addr + c0, v);
+    uint4 r0, r1;
+    const bool live = row_ok && c0 < ncols;
+    if (kRes && live) ldg256(r_row + c0, r0, r1);
+    tmem_ld_wait();
+    if (live) {
+      float f[16];
+      const float4* b4 = reinterpret_cast<const float4*>(b_row + c0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 bz = b4[i];
+        f[4 * i] = __uint_as_float(v[4 * i]) + bz.x;
+        f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + bz.y;
+        f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + bz.z;
+        f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + bz.w;
+      }
+      if (kRes) {
+        const uint32_t rw_[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          f[2 * i] += bf16_bits_to_float(rw_[i] & 0xFFFFu);
+          f[2 * i + 1] += bf16_bits_to_float(rw_[i] >> 16);
+        }
+      }
+      if (relu) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+      }
+      uint4 a, b;
+      a.x = pack_bf16x2(f[0], f[1]);   a.y = pack_bf16x2(f[2], f[3]);
+      a.z = pack_bf16x2(f[4], f[5]);   a.w = pack_bf16x2(f[6], f[7]);
+      b.x = pack_bf16x2(f[8], f[9]);   b.y = pack_bf16x2(f[10], f[11]);
+      b.z = pack_bf16x2(f[12], f[13]); b.w = pack_bf16x2(f[14], f[15]);
+      stg256(o_row + c0, a, b);
+    }
+  }
+}
+
 // Epilogue of one 128 x BN output tile for one warp: t_addr = TMEM address of the warp's 32 lanes in the tile's
 // accumulator, (row_ok, pix, rpix) = this lane's output row, `part` = which of the kEpiParts warps sharing the lane
 // quarter this is. Shared by the streaming and the resident-weights forward kernels.
@@ -244,6 +295,7 @@ __device__ __forceinline__ void fwd_epilogue_tile(const FwdParams& p, uint32_t t
 // =====================================================================================================================
 // Forward / dgrad / dense / batched GEMM:  D[pixels, Cout] = sum_taps A_tap[pixels, C] * B[Cout, tap*C + c]
 // =====================================================================================================================
+template <int kMode>  // 0: generic epilogue; 1 / 2: lean epilogue (bias [+ residual]), see fwd_epilogue_tile_lean
 __global__ void __launch_bounds__(kThreadsFwd, 1)
 gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -395,7 +447,9 @@ gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
-      fwd_epilogue_tile(p, t_addr, nt, row_ok, pix, rpix, bias_s, half);
+      if (kMode == 1) fwd_epilogue_tile_lean<false>(p, t_addr, nt, row_ok, pix, rpix, bias_s, half);
+      else if (kMode == 2) fwd_epilogue_tile_lean<true>(p, t_addr, nt, row_ok, pix, rpix, bias_s, half);
+      else fwd_epilogue_tile(p, t_addr, nt, row_ok, pix, rpix, bias_s, half);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -1056,12 +1110,27 @@ extern "C" int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* w
     if (r) return r;
   }
   if (!g_attr_set_fwd) {
-    XMC_CUDA_CHECK(cudaFuncSetAttribute(gemm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFwd));
+    XMC_CUDA_CHECK(cudaFuncSetAttribute(gemm_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFwd));
+    XMC_CUDA_CHECK(cudaFuncSetAttribute(gemm_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFwd));
+    XMC_CUDA_CHECK(cudaFuncSetAttribute(gemm_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFwd));
     g_attr_set_fwd = true;
   }
   const int total = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles * p.parities;
   const int grid = total < num_sms() ? total : num_sms();
-  gemm_fwd_kernel<<<grid, kThreadsFwd, kSmemFwd, (cudaStream_t)stream>>>(tmA, tmB, p);
+  static int lean_mode = -1;  // XMC_LEAN_EPI=0 forces the generic epilogue (debugging aid)
+  if (lean_mode < 0) {
+    const char* e = getenv("XMC_LEAN_EPI");
+    lean_mode = e ? atoi(e) : 1;
+  }
+  auto al32p = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
+  const bool lean = lean_mode && p.bias_smem && !mask && d->alpha == 1.f && d->out_dtype == 0 && p.vec_ok == 2 &&
+                    (d->Cout % 16) == 0 && (!residual || al32p(residual));
+  if (lean && !residual)
+    gemm_fwd_kernel<1><<<grid, kThreadsFwd, kSmemFwd, (cudaStream_t)stream>>>(tmA, tmB, p);
+  else if (lean)
+    gemm_fwd_kernel<2><<<grid, kThreadsFwd, kSmemFwd, (cudaStream_t)stream>>>(tmA, tmB, p);
+  else
+    gemm_fwd_kernel<0><<<grid, kThreadsFwd, kSmemFwd, (cudaStream_t)stream>>>(tmA, tmB, p);
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }
