@@ -153,6 +153,13 @@ int xmc_cast_f32_to_bf16(const float* src, long long rows, int cols, long long l
 int xmc_cast_bf16_to_f32(const void* src, long long rows, int cols, long long ld_src, float* dst, long long ld_dst,
                          int accumulate, void* stream);
 /* dst[b*reps + r][c] = src[b][c]  (jnp.tile of global_cond, xmc_net.py:233-234) and its transpose */
+/* Input-contract producer for decoded examples (COCODataset.preprocess, xmcgan/libml/coco_dataset.py:127-167):
+ * xmc_prep_image:   out[n] = clip(flip[n] ? fliplr(img[n]) : img[n], 0, 1), fp32 [N,H,W,3]
+ * xmc_prep_caption: picks caption idx[n] of M: emb_out [N,L,E] = emb[n][idx[n]], len_out [N] = (float)len[n][idx[n]],
+ *                   sent_out [N,E] = sum over all L word slots of emb_out / len_out  (coco_dataset.py:139-142,156-158) */
+int xmc_prep_image(const float* img, const unsigned char* flip, int N, int H, int W, float* out, void* stream);
+int xmc_prep_caption(const float* emb, const int* len, const int* idx, int N, int M, int L, int E, float* emb_out,
+                     float* len_out, float* sent_out, void* stream);
 int xmc_bcast_rows(const void* src, int B, int reps, int cols, int ld_src, void* dst, int ld_dst, void* stream);
 int xmc_sum_rows(const void* src, int B, int reps, int cols, int ld_src, float* dst, int ld_dst, int accumulate,
                  void* stream);

@@ -861,3 +861,21 @@ def resnet50_random_variables(seed=0, head_scale=0.05, residual_scale=0.3):
     return out
 
   return {"params": fill(pshapes), "batch_stats": fill(sshapes)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# input contract: COCODataset.preprocess (xmcgan/libml/coco_dataset.py:127-167) for decoded, already resized examples
+# ----------------------------------------------------------------------------------------------------------------------
+def preprocess_batch(features, flip, sentence_idx, z):
+  """Deterministic part of coco_dataset.py:131-166 given the three random draws (flip [N] bool, sentence_idx [N], z).
+  image: flip_left_right then clip_by_value(0, 1) (:135-136); sentence_feat = reduce_sum(embedding, -2) / max_len over
+  ALL word slots (:139-142); the chosen caption's embedding / max_len / sentence_embedding (:154-159)."""
+  img = features["image"].float()
+  emb = features["caption/embedding"].float()
+  lens = features["caption/max_len"].float()[..., None]          # [N, M, 1]
+  img = torch.where(torch.as_tensor(flip).bool()[:, None, None, None], img.flip(2), img).clamp(0.0, 1.0)
+  sent = emb.sum(dim=-2) / lens                                     # [N, M, E]
+  n = torch.arange(img.shape[0])
+  idx = torch.as_tensor(sentence_idx).long()
+  return {"image": img, "embedding": emb[n, idx], "max_len": lens[n, idx], "sentence_embedding": sent[n, idx],
+          "z": torch.as_tensor(z).float()}

@@ -687,3 +687,35 @@ def test_bilinear_resize_to_224_matches_jax_semantics(S):
   dimg = torch.zeros(n, S, S, 3, device="cuda")
   ops._call("xmc_resize_bilinear_bwd", d.cuda().data_ptr(), n, S, T, dimg.data_ptr(), _lib.stream())
   assert helpers.rel(dimg, img.grad) < 1e-5
+
+
+@gpu
+def test_input_contract_producer_matches_oracle():
+  """libml.coco_dataset.preprocess (COCODataset.preprocess, coco_dataset.py:127-167) vs the oracle restatement on the
+  same random draws: flipped / clipped image, chosen caption embedding and max_len are index / clamp ops -> exact;
+  sentence_embedding = sum over 17 word slots / len in the same summation order -> exact as well. With
+  return_text=True the shortest caption is chosen (an argsort index op), and the result drives a train_step."""
+  _, engine, ops, train_utils, xmc_gan, xmc_net = _mods()
+  from xmcgan_image_generation_b200.libml import coco_dataset
+  torch.manual_seed(31)
+  N, S, M, L, E = 6, 128, 5, 17, 64
+  feats = {"image": torch.rand(N, S, S, 3) * 1.2 - 0.1,                 # some values outside [0,1]: clip matters
+           "caption/embedding": torch.randn(N, M, L, E) * 0.5,
+           "caption/max_len": torch.randint(3, L + 1, (N, M))}
+  flip = torch.tensor([1, 0, 1, 1, 0, 0], dtype=torch.bool)
+  idx = torch.tensor([0, 4, 2, 1, 3, 3])
+  z = torch.randn(N, 8)
+  want = orc.preprocess_batch(feats, flip, idx, z)
+  got = coco_dataset.preprocess(feats, flip=flip, sentence_idx=idx, z=z)
+  for k in ("image", "embedding", "max_len", "sentence_embedding", "z"):
+    assert got[k].shape == want[k].shape, k
+    assert torch.equal(got[k].cpu(), want[k]), k
+  short = coco_dataset.preprocess(feats, rng=3, z_dim=8, return_text=True)
+  want_idx = feats["caption/max_len"].argmin(dim=1)
+  assert torch.equal(short["max_len"].cpu()[:, 0], feats["caption/max_len"].float().gather(1, want_idx[:, None])[:, 0])
+  rnd = coco_dataset.preprocess(feats, rng=5, z_dim=8)
+  assert rnd["z"].shape == (N, 8) and rnd["image"].min() >= 0 and rnd["image"].max() <= 1
+  cfg = helpers.small_config(batch_size=N // 2)
+  gen, disc, state = train_utils.create_train_state(cfg, 1, rnd)
+  state, m = train_utils.train_step(None, state, rnd, xmc_gan, gen, disc, cfg, {})
+  assert all(torch.isfinite(torch.tensor(v)) for v in m.compute().values())

@@ -489,6 +489,49 @@ static int fill_bnp(const XmcBnDesc* d, BnP* p) {
   return XMC_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Input contract producer (COCODataset.preprocess, xmcgan/libml/coco_dataset.py:127-167) for already decoded / resized
+// examples: per-example left-right flip + clip to [0,1]; pick sentence idx[n] of the M captions: embedding[n] =
+// emb[n][idx], max_len[n] = len[n][idx], sentence_embedding[n] = sum_words(emb[n][idx]) / len[n][idx] (the sum runs
+// over ALL L word slots, padded ones included, exactly as tf.reduce_sum(embedding, axis=-2) does).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void prep_image_kernel(const float* __restrict__ img, const unsigned char* __restrict__ flip, int N, int H,
+                                  int W, float* __restrict__ out) {
+  const long long total = (long long)N * H * W;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int w = idx % W;
+    const long long row = idx / W;           // n*H + h
+    const int n = (int)(row / H);
+    const int ws = flip[n] ? W - 1 - w : w;
+    const float* s = img + (row * W + ws) * 3;
+    float* o = out + idx * 3;
+    o[0] = fminf(fmaxf(s[0], 0.f), 1.f);
+    o[1] = fminf(fmaxf(s[1], 0.f), 1.f);
+    o[2] = fminf(fmaxf(s[2], 0.f), 1.f);
+  }
+}
+
+// one block per example; threads along the feature dimension
+__global__ void prep_caption_kernel(const float* __restrict__ emb, const int* __restrict__ len,
+                                    const int* __restrict__ idx, int M, int L, int E, float* __restrict__ emb_out,
+                                    float* __restrict__ len_out, float* __restrict__ sent_out) {
+  const int n = blockIdx.x;
+  const int j = idx[n];
+  const float* src = emb + ((long long)n * M + j) * L * E;
+  const float ml = (float)len[(long long)n * M + j];
+  if (threadIdx.x == 0) len_out[n] = ml;
+  for (int f = threadIdx.x; f < E; f += blockDim.x) {
+    float acc = 0.f;
+    for (int w = 0; w < L; ++w) {
+      const float v = src[(long long)w * E + f];
+      emb_out[((long long)n * L + w) * E + f] = v;
+      acc += v;
+    }
+    sent_out[(long long)n * E + f] = acc / ml;
+  }
+}
+
 }  // namespace xmc
 
 using namespace xmc;
@@ -678,6 +721,23 @@ extern "C" int xmc_sum_rows(const void* src, int B, int reps, int cols, int ld_s
   if (!src || !dst || B < 1 || reps < 1 || cols < 1) return XMC_EINVAL;
   sum_rows_kernel<<<dim3(ceil_div(cols, 128), B), 128, 0, (cudaStream_t)stream>>>((const bf16*)src, B, reps, cols,
                                                                                  ld_src, dst, ld_dst, accumulate);
+  XMC_LAUNCH_CHECK();
+  return XMC_OK;
+}
+
+extern "C" int xmc_prep_image(const float* img, const unsigned char* flip, int N, int H, int W, float* out,
+                              void* stream) {
+  if (!img || !flip || !out || N < 1 || H < 1 || W < 1) return XMC_EINVAL;
+  const long long total = (long long)N * H * W;
+  prep_image_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(img, flip, N, H, W, out);
+  XMC_LAUNCH_CHECK();
+  return XMC_OK;
+}
+
+extern "C" int xmc_prep_caption(const float* emb, const int* len, const int* idx, int N, int M, int L, int E,
+                                float* emb_out, float* len_out, float* sent_out, void* stream) {
+  if (!emb || !len || !idx || !emb_out || !len_out || !sent_out || N < 1 || M < 1 || L < 1 || E < 1) return XMC_EINVAL;
+  prep_caption_kernel<<<N, 256, 0, (cudaStream_t)stream>>>(emb, len, idx, M, L, E, emb_out, len_out, sent_out);
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }
