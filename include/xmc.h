@@ -176,7 +176,7 @@ typedef struct {
   int taps, cin, cout;
   int ld_fwd, ld_dg;
   int sn;                 /* spectral-norm slot, or -1 */
-  int tile_begin;         /* prefix sum of ceil(taps*cin/32)*ceil(cout/32) */
+  int tile_begin;         /* prefix sum of ceil(taps*cin/64)*ceil(cout/64) */
   int reserved;
   long long cscale_off;   /* per-output-channel scale inside the fp32 `cscale` buffer (folded eval BatchNorm), or -1 */
 } XmcPrepEntry;

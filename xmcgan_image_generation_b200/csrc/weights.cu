@@ -132,24 +132,30 @@ __global__ void sn_bwd_apply_kernel(const XmcSnEntry* __restrict__ tab, int n, f
 }
 
 // ------------------------------------------------------------------------------------------------- weight prep
-__global__ void prep_weights_kernel(const XmcPrepEntry* __restrict__ tab, int n, const float* __restrict__ params,
-                                    const float* __restrict__ sn_scalars, int n_sn, bf16* __restrict__ arena,
-                                    float* __restrict__ bias_arena, const float* __restrict__ cscale) {
-  __shared__ float tile[32][33];
+// One block = a 64 (k = tap*Cin+ci) x 64 (cout) tile, 256 threads as 64 x 4: 16 independent row loads per thread, the
+// dgrad copy is written in the read orientation (128-byte runs along cout), the forward copy after a transpose through
+// shared memory (128-byte runs along k).
+constexpr int kPrepTile = 64;
+__global__ void __launch_bounds__(256)
+prep_weights_kernel(const XmcPrepEntry* __restrict__ tab, int n, const float* __restrict__ params,
+                    const float* __restrict__ sn_scalars, int n_sn, bf16* __restrict__ arena,
+                    float* __restrict__ bias_arena, const float* __restrict__ cscale) {
+  __shared__ float tile[kPrepTile][kPrepTile + 1];
   const int e = find_entry(tab, n, (int)blockIdx.x, &XmcPrepEntry::tile_begin);
   const XmcPrepEntry en = tab[e];
   const int local = (int)blockIdx.x - en.tile_begin;
   const int K = en.taps * en.cin;
-  const int ctiles = (en.cout + 31) / 32;
+  const int ctiles = (en.cout + kPrepTile - 1) / kPrepTile;
   const int kt = local / ctiles, ct = local - kt * ctiles;
   const float scale = (en.sn >= 0) ? sn_scalars[2 * n_sn + en.sn] : 1.f;
-  const int c = ct * 32 + threadIdx.x;
-  for (int r = threadIdx.y; r < 32; r += 8) {
-    const int k = kt * 32 + r;
+  const int c = ct * kPrepTile + threadIdx.x;
+  const float cs = (en.cscale_off >= 0 && c < en.cout) ? cscale[en.cscale_off + c] : 1.f;
+#pragma unroll 4
+  for (int r = threadIdx.y; r < kPrepTile; r += 4) {
+    const int k = kt * kPrepTile + r;
     float v = 0.f;
     if (k < K && c < en.cout) {
-      v = params[en.w_off + (long long)k * en.cout + c] * scale;
-      if (en.cscale_off >= 0) v *= cscale[en.cscale_off + c];
+      v = params[en.w_off + (long long)k * en.cout + c] * scale * cs;
       if (en.wk_dg_off >= 0) {
         const int tap = k / en.cin, ci = k - tap * en.cin;
         arena[en.wk_dg_off + (long long)ci * en.ld_dg + (long long)(en.taps - 1 - tap) * en.cout + c] =
@@ -160,14 +166,15 @@ __global__ void prep_weights_kernel(const XmcPrepEntry* __restrict__ tab, int n,
   }
   __syncthreads();
   if (en.wk_fwd_off >= 0) {
-    const int k = kt * 32 + threadIdx.x;
-    for (int r = threadIdx.y; r < 32; r += 8) {
-      const int cc = ct * 32 + r;
-      if (k < K && cc < en.cout) arena[en.wk_fwd_off + (long long)cc * en.ld_fwd + k] = __float2bfloat16(tile[threadIdx.x][r]);
+    const int k = kt * kPrepTile + threadIdx.x;
+    for (int r = threadIdx.y; r < kPrepTile; r += 4) {
+      const int cc = ct * kPrepTile + r;
+      if (k < K && cc < en.cout)
+        arena[en.wk_fwd_off + (long long)cc * en.ld_fwd + k] = __float2bfloat16(tile[threadIdx.x][r]);
     }
   }
   if (local == 0 && en.bias_off >= 0 && en.bias_dst_off >= 0) {
-    for (int i = threadIdx.y * 32 + threadIdx.x; i < en.cout; i += 256)
+    for (int i = threadIdx.y * kPrepTile + threadIdx.x; i < en.cout; i += 256)
       bias_arena[en.bias_dst_off + i] = params[en.bias_off + i];
   }
 }
@@ -302,7 +309,7 @@ extern "C" int xmc_prep_weights(const XmcPrepEntry* table_dev, int n, int total_
                                 const float* sn_scalars, int n_sn, void* arena, float* bias_arena,
                                 const float* cscale, void* stream) {
   if (!table_dev || n < 1 || total_tiles < 1 || !params || !arena) return XMC_EINVAL;
-  prep_weights_kernel<<<total_tiles, dim3(32, 8), 0, (cudaStream_t)stream>>>(table_dev, n, params, sn_scalars, n_sn,
+  prep_weights_kernel<<<total_tiles, dim3(64, 4), 0, (cudaStream_t)stream>>>(table_dev, n, params, sn_scalars, n_sn,
                                                                             (bf16*)arena, bias_arena, cscale);
   XMC_LAUNCH_CHECK();
   return XMC_OK;

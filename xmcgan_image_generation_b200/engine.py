@@ -119,7 +119,7 @@ class _PrepTable:
     e.taps, e.cin, e.cout = taps, cin, cout
     e.ld_fwd, e.ld_dg, e.sn = ld_fwd, ld_dg, sn
     e.tile_begin = self.tiles
-    self.tiles += ((taps * cin + 31) // 32) * ((cout + 31) // 32)
+    self.tiles += ((taps * cin + 63) // 64) * ((cout + 63) // 64)   # 64 x 64 tiles of xmc_prep_weights
     self.entries.append(e)
 
   def upload(self):
