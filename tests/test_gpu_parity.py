@@ -482,8 +482,11 @@ def test_train_step_with_pretrained_image_contrastive():
   got = metrics.compute()
   ostate, want = orc.train_step(ostate, batch, cfg, pol, pretrained_fn=pre)
   scale = max(abs(v) for v in want.values())
+  # 1e-2 of the largest metric: the metrics of train_g_d are taken AFTER train_d's Adam step, whose first update is
+  # sign-like (m / sqrt(v) = g / |g|): parameters with a noise-level gradient move by +-lr with a sign the split-K
+  # atomics decide, and at B=3 that shows up as a 5e-3 .. 6.5e-3 run-to-run spread of g_loss (measured over 14 runs)
   for k in ("d_loss", "g_loss", "c_loss_d", "c_loss_g", "c_loss_g_pretrained"):
-    assert abs(got[k] - want[k]) < 5e-3 * scale, (k, got[k], want[k])
+    assert abs(got[k] - want[k]) < 1e-2 * scale, (k, got[k], want[k])
   assert got["c_loss_g_pretrained"] > 0
   for (p, a), (_, b) in zip(orc.tree_leaves(state.g_optimizer.target.to_cpu_tree()), orc.tree_leaves(ostate["g_params"])):
     assert helpers.rel(a, b) < 5e-3, (p, helpers.rel(a, b))
