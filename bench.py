@@ -201,6 +201,19 @@ def run_b200(args):
   for _ in range(args.warmup):
     state, metrics = train_utils.train_step(None, state, dev, xmc_gan, generator, discriminator, config, additional)
   barrier()
+  eager_step = lambda batch: train_utils.train_step(None, state, batch, xmc_gan, generator, discriminator, config,
+                                                    additional)
+  launches_per_step = None
+  if args.graph:
+    # the public graphed entry point: the whole train_step replayed from one CUDA graph (train_utils.GraphedTrainStep)
+    n0 = ops.LAUNCHES[0]
+    graphed = train_utils.GraphedTrainStep(state, dev, xmc_gan, generator, discriminator, config, additional, warmup=1)
+    launches_per_step = (ops.LAUNCHES[0] - n0) // 2   # one eager warm-up step + the captured step
+    state = graphed.state
+    step_fn = graphed
+    barrier()
+  else:
+    step_fn = eager_step
 
   # ---- timed: inputs resident in HBM -----------------------------------------------------------------------------------
   sampler = ClockSampler(local)
@@ -211,11 +224,11 @@ def run_b200(args):
   barrier()
   e0.record()
   for _ in range(args.steps):
-    state, metrics = train_utils.train_step(None, state, dev, xmc_gan, generator, discriminator, config, additional)
+    state, metrics = step_fn(dev)
   e1.record()
   barrier()
   ms_dev = max_over_ranks(e0.elapsed_time(e1))
-  launches = ops.LAUNCHES[0] - launches0
+  launches = ops.LAUNCHES[0] - launches0 if launches_per_step is None else launches_per_step * args.steps
   clocks = sampler.stop() if rank == 0 else None
   last = metrics.compute()
 
@@ -241,8 +254,11 @@ def run_b200(args):
   barrier()
   e0.record()
   for _ in range(args.steps):
-    step_in = {k: v.cuda(non_blocking=True) for k, v in pinned.items()}
-    state, metrics = train_utils.train_step(None, state, step_in, xmc_gan, generator, discriminator, config, additional)
+    if args.graph:   # the graphed step copies the pinned host batch into its static device buffers itself
+      state, metrics = step_fn(pinned)
+    else:
+      step_in = {k: v.cuda(non_blocking=True) for k, v in pinned.items()}
+      state, metrics = eager_step(step_in)
     last = metrics.compute()  # device -> host read of the step's result
   e1.record()
   barrier()
@@ -285,6 +301,7 @@ def run_b200(args):
                              "train_d + train_g_d, Adam, EMA, grad all-reduce",
                  "global_batch": B * world, "parallelism": f"dp{world}",
                  "pretrained_image_contrastive": pretrained, "word_contrastive": bool(config.word_contrastive),
+                 "cuda_graph": bool(args.graph),
                  "l2": "per-step working set (several GB of activations) >> 126 MB L2; no explicit flush",
                  "algorithmic_tflop_per_step_per_gpu": round(alg_tf, 2),
                  "model_tflops_per_gpu": round(alg_tf / (ms_dev / args.steps / 1e3), 1)},
@@ -371,6 +388,8 @@ def main():
                   help="switch the frozen ResNet-50 image-image InfoNCE branch off (reference default: on)")
   ap.add_argument("--no-word-contrastive", action="store_true",
                   help="BASELINE config 5 (attention ablation): discriminator-side word_loss off (xmc_net.py:112)")
+  ap.add_argument("--graph", type=int, default=1,
+                  help="1: time train_utils.GraphedTrainStep (train_step replayed from a CUDA graph); 0: eager train_step")
   ap.add_argument("--dump-gemm", default=None, help="write per-shape GEMM timings (JSON) to this file")
   args = ap.parse_args()
   if args.warmup < 3 and args.impl == "b200":

@@ -211,9 +211,13 @@ int xmc_prep_weights(const XmcPrepEntry* table_dev, int n, int total_tiles, cons
 int xmc_subpixel_prep(const float* w, const float* scale, int Cin, int Cout, void* wf, void* vd, void* stream);
 /* flax.optim.Adam.apply_gradient (weight_decay 0) in place on flat buffers, gradient pre-scaled by grad_scale
  * (1/world after a sum all-reduce == lax.pmean); optional polyak EMA of the updated parameters
- * (xmcgan/xmc_gan.py:172-177,252). bias_corr = 1 - beta^t. n must be a multiple of 4. */
+ * (xmcgan/xmc_gan.py:172-177,252). bias_corr = 1 - beta^t. n must be a multiple of 4.
+ * step_dev: optional device int holding the number of steps taken so far; when given, the bias corrections are
+ * computed on the device from t = *step_dev + 1 (bias_corr1/2 are ignored) and *step_dev is incremented afterwards, so
+ * that the launch can be replayed from a CUDA graph. */
 int xmc_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
-             float bias_corr1, float bias_corr2, float grad_scale, float* ema, float ema_decay, void* stream);
+             float bias_corr1, float bias_corr2, float grad_scale, float* ema, float ema_decay, int* step_dev,
+             void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Row l2-normalisation xhat = x*rsqrt(max(sum x^2, eps)) (attention_lib.l2_normalize, attention_lib.py:30-33), one

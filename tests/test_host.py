@@ -26,7 +26,7 @@ def test_abi_rejects_bad_descriptors_without_touching_the_gpu():
   assert L.xmc_conv2d_fwd(ctypes.byref(d), None, None, None, None, None, None, None) == -1
   w = _lib.WgradDesc()
   assert L.xmc_conv2d_wgrad(ctypes.byref(w), None, None, None, None) == -1
-  assert L.xmc_adam(None, None, None, None, 16, 0.1, 0.5, 0.9, 1e-8, 0.5, 0.1, 1.0, None, 0.0, None) == -1
+  assert L.xmc_adam(None, None, None, None, 16, 0.1, 0.5, 0.9, 1e-8, 0.5, 0.1, 1.0, None, 0.0, None, None) == -1
 
 
 def test_parameter_counts_match_reference():

@@ -242,7 +242,13 @@ subpixel_prep_kernel(const float* __restrict__ w, const float* __restrict__ scal
 // ------------------------------------------------------------------------------------------------- Adam (+EMA)
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float inv_c1,
-                            float inv_c2, float gscale, float* __restrict__ ema, float decay) {
+                            float inv_c2, float gscale, float* __restrict__ ema, float decay,
+                            const int* __restrict__ step_dev) {
+  if (step_dev) {  // step count t kept on the device (CUDA-graph replays cannot take new host scalars)
+    const float t = (float)(*step_dev + 1);
+    inv_c1 = 1.f / (1.f - powf(b1, t));
+    inv_c2 = 1.f / (1.f - powf(b2, t));
+  }
   const long long n4 = n >> 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
@@ -324,9 +330,11 @@ extern "C" int xmc_subpixel_prep(const float* w, const float* scale, int Cin, in
   return XMC_OK;
 }
 
+__global__ void inc_i32_kernel(int* x) { *x += 1; }
+
 extern "C" int xmc_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                         float eps, float bias_corr1, float bias_corr2, float grad_scale, float* ema, float ema_decay,
-                        void* stream) {
+                        int* step_dev, void* stream) {
   if (!p || !g || !m || !v || n < 4 || (n & 3)) return XMC_EINVAL;
   if (!aligned16(p) || !aligned16(g) || !aligned16(m) || !aligned16(v) || (ema && !aligned16(ema))) return XMC_EALIGN;
   long long blocks = ceil_div_ll(n / 4, 256);
@@ -334,7 +342,11 @@ extern "C" int xmc_adam(float* p, const float* g, float* m, float* v, long long 
   if (blocks > cap) blocks = cap;
   adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps,
                                                                   1.f / bias_corr1, 1.f / bias_corr2, grad_scale, ema,
-                                                                  ema_decay);
+                                                                  ema_decay, step_dev);
   XMC_LAUNCH_CHECK();
+  if (step_dev) {
+    inc_i32_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+    XMC_LAUNCH_CHECK();
+  }
   return XMC_OK;
 }

@@ -99,6 +99,56 @@ def generate_batch(rng, state, batch, generator, config, collect_all=False):
   return out
 
 
+class GraphedTrainStep:
+  """train_step captured once into a CUDA graph and replayed: the ~730 kernel launches of a step become one graph
+  launch (no per-launch host work, no inter-kernel launch gaps). Same semantics as train_step on the same state:
+
+      step = GraphedTrainStep(state, batch, xmc_gan, generator, discriminator, config, additional_data)
+      state, metrics = step(batch)        # every call = one train_step on `batch` (host or device tensors)
+
+  What makes the step replayable: the input batch lives in fixed device buffers (each call copies into them), the Adam
+  step counts live on the device (xmc_adam's step_dev), and the state buffers keep their addresses (new batch
+  statistics / u0 are copied back instead of swapping buffers). Construction runs `warmup` real train_steps eagerly
+  (kernel attributes, allocator pool, NCCL communicators) and one more while capturing — the capture does not execute,
+  so construction advances the state by exactly `warmup` steps."""
+
+  def __init__(self, state, batch, gan_model, generator, discriminator, config, additional_data, warmup=2):
+    from . import xmc_gan as _xg
+    self.config = config
+    self.static_batch = {k: v.clone() for k, v in xmc_net.batch_to_device(batch).items()}
+    g_eng, d_eng = _xg._engines(config, self.static_batch)
+    ws = _xg._workspace(state, g_eng, d_eng)
+    ws.graph_mode = True
+    for opt in (state.g_optimizer, state.d_optimizer):
+      opt.step_dev = torch.tensor([opt.step], device="cuda", dtype=torch.int32)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+      for _ in range(warmup):
+        state, _ = train_step(None, state, self.static_batch, gan_model, generator, discriminator, config,
+                              additional_data)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    steps_before = (state.step, state.g_optimizer.step, state.d_optimizer.step)
+    self.graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(self.graph):
+      self.state, self.metrics = train_step(None, state, self.static_batch, gan_model, generator, discriminator, config,
+                                            additional_data)
+    # capturing ran the Python side of one step (host counters advanced) without executing it on the device
+    self.state.step, self.state.g_optimizer.step, self.state.d_optimizer.step = steps_before
+    self._d_steps = config.d_step_per_g_step
+
+  def __call__(self, batch):
+    for k, dst in self.static_batch.items():
+      dst.copy_(torch.as_tensor(batch[k]).reshape(dst.shape), non_blocking=True)
+    self.graph.replay()
+    st = self.state
+    st.step += 1
+    st.g_optimizer.step += 1
+    st.d_optimizer.step += self._d_steps
+    return st, self.metrics
+
+
 def create_train_state(config, rng, init_batch):
   """train_utils.create_train_state (train_utils.py:133-193)."""
   dtype = torch.bfloat16 if config.dtype == "bfloat16" else torch.float32

@@ -80,6 +80,7 @@ class _Workspace:
     self.g_stats_alt = torch.empty_like(state.generator_state["batch_stats"].buf)
     self.u0_alt = torch.empty_like(state.discriminator_state["spectral_norm_stats"].buf) if d_eng.sn else None
     self.g_u0_alt = torch.empty_like(state.generator_state["spectral_norm_stats"].buf) if g_eng.sn else None
+    self.graph_mode = False  # True: state buffers keep their addresses (copies instead of pointer swaps)
 
 
 def _workspace(state, g_eng, d_eng):
@@ -98,10 +99,14 @@ def _engines(config, batch):
 def _adam(opt, grads, ema=None, decay=0.0):
   opt.step += 1
   t = opt.step
+  # graph mode (train_utils.GraphedTrainStep): the step count lives in a device int so that a replayed launch computes
+  # this step's bias corrections itself
+  step_dev = getattr(opt, "step_dev", None)
   ops._call("xmc_adam", opt.target.buf.data_ptr(), grads.data_ptr(), opt.m.data_ptr(), opt.v.data_ptr(),
             opt.target.buf.numel(), opt.learning_rate, opt.beta1, opt.beta2, opt.eps, 1.0 - opt.beta1 ** t,
             1.0 - opt.beta2 ** t, 1.0 / parallel.world_size(), ema.data_ptr() if ema is not None else None, decay,
-            ops._lib.stream())
+            step_dev.data_ptr() if step_dev is not None else None, ops._lib.stream(),
+            launches=2 if step_dev is not None else 1)
 
 
 def _forward_both(state, batch, config, ws, g_eng, d_eng, losses, keep_g_state, need_g):
@@ -129,6 +134,9 @@ def _swap_d_state(state, ws, d_eng):
   if not d_eng.sn:
     return state.discriminator_state
   old = state.discriminator_state["spectral_norm_stats"]
+  if ws.graph_mode:  # fixed buffer addresses: copy the new u0 back instead of swapping the two buffers
+    old.buf.copy_(ws.u0_alt)
+    return state.discriminator_state
   new = xmc_net.FlatTree(d_eng.u_layout, ws.u0_alt)
   ws.u0_alt = old.buf
   return {"spectral_norm_stats": new}
@@ -203,12 +211,18 @@ def train_g_d(rng, state, batch, generator, discriminator, config, additional_da
   _adam(state.g_optimizer, ws.g_grads, ema=state.ema_params.buf, decay=config.polyak_decay)
   g_eng.prepped_for = None  # xmc_adam rewrote the parameters through raw pointers
   old_stats = state.generator_state["batch_stats"]
-  new_g_state = {"batch_stats": xmc_net.FlatTree(g_eng.stats_layout, ws.g_stats_alt)}
-  ws.g_stats_alt = old_stats.buf
-  if g_eng.sn:
-    old_u0 = state.generator_state["spectral_norm_stats"]
-    new_g_state["spectral_norm_stats"] = xmc_net.FlatTree(g_eng.u_layout, ws.g_u0_alt)
-    ws.g_u0_alt = old_u0.buf
+  if ws.graph_mode:
+    old_stats.buf.copy_(ws.g_stats_alt)
+    if g_eng.sn:
+      state.generator_state["spectral_norm_stats"].buf.copy_(ws.g_u0_alt)
+    new_g_state = state.generator_state
+  else:
+    new_g_state = {"batch_stats": xmc_net.FlatTree(g_eng.stats_layout, ws.g_stats_alt)}
+    ws.g_stats_alt = old_stats.buf
+    if g_eng.sn:
+      old_u0 = state.generator_state["spectral_norm_stats"]
+      new_g_state["spectral_norm_stats"] = xmc_net.FlatTree(g_eng.u_layout, ws.g_u0_alt)
+      ws.g_u0_alt = old_u0.buf
   new_d_state = _swap_d_state(state, ws, d_eng)
   new_state = state.replace(step=state.step + 1, generator_state=new_g_state, discriminator_state=new_d_state)
   object.__setattr__(new_state, "_ws", ws)
