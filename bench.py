@@ -204,7 +204,11 @@ def run_b200(args):
   eager_step = lambda batch: train_utils.train_step(None, state, batch, xmc_gan, generator, discriminator, config,
                                                     additional)
   launches_per_step = None
-  if args.graph:
+  # --graph 1 (default): graph replay on a single GPU, eager train_step under torchrun. With N > 1 the replay itself
+  # works and is faster (2 GPUs: 43.4 vs 44.9 ms/step), but tearing the process group down while a graph holds captured
+  # NCCL kernels hung at exit in this environment, so it is opt-in there (--graph 2) until that is understood.
+  use_graph = args.graph == 2 or (args.graph == 1 and world == 1)
+  if use_graph:
     # the public graphed entry point: the whole train_step replayed from one CUDA graph (train_utils.GraphedTrainStep)
     n0 = ops.LAUNCHES[0]
     graphed = train_utils.GraphedTrainStep(state, dev, xmc_gan, generator, discriminator, config, additional, warmup=1)
@@ -254,7 +258,7 @@ def run_b200(args):
   barrier()
   e0.record()
   for _ in range(args.steps):
-    if args.graph:   # the graphed step copies the pinned host batch into its static device buffers itself
+    if use_graph:   # the graphed step copies the pinned host batch into its static device buffers itself
       state, metrics = step_fn(pinned)
     else:
       step_in = {k: v.cuda(non_blocking=True) for k, v in pinned.items()}
@@ -264,6 +268,9 @@ def run_b200(args):
   barrier()
   ms_e2e = max_over_ranks(e0.elapsed_time(e1))
 
+  if use_graph and world > 1:   # drop the captured NCCL work before the communicator goes away
+    del graphed, step_fn
+    torch.cuda.synchronize()
   if rank != 0:
     if world > 1:
       dist.destroy_process_group()
@@ -301,7 +308,7 @@ def run_b200(args):
                              "train_d + train_g_d, Adam, EMA, grad all-reduce",
                  "global_batch": B * world, "parallelism": f"dp{world}",
                  "pretrained_image_contrastive": pretrained, "word_contrastive": bool(config.word_contrastive),
-                 "cuda_graph": bool(args.graph),
+                 "cuda_graph": bool(use_graph),
                  "l2": "per-step working set (several GB of activations) >> 126 MB L2; no explicit flush",
                  "algorithmic_tflop_per_step_per_gpu": round(alg_tf, 2),
                  "model_tflops_per_gpu": round(alg_tf / (ms_dev / args.steps / 1e3), 1)},
@@ -388,8 +395,9 @@ def main():
                   help="switch the frozen ResNet-50 image-image InfoNCE branch off (reference default: on)")
   ap.add_argument("--no-word-contrastive", action="store_true",
                   help="BASELINE config 5 (attention ablation): discriminator-side word_loss off (xmc_net.py:112)")
-  ap.add_argument("--graph", type=int, default=1,
-                  help="1: time train_utils.GraphedTrainStep (train_step replayed from a CUDA graph); 0: eager train_step")
+  ap.add_argument("--graph", type=int, default=1, choices=[0, 1, 2],
+                  help="1: train_utils.GraphedTrainStep (train_step replayed from a CUDA graph) on one GPU, eager "
+                       "train_step under torchrun; 2: graph replay for any N; 0: eager everywhere")
   ap.add_argument("--dump-gemm", default=None, help="write per-shape GEMM timings (JSON) to this file")
   args = ap.parse_args()
   if args.warmup < 3 and args.impl == "b200":
