@@ -144,3 +144,22 @@ def test_product_path_has_no_cpu_fallback():
   c = helpers.small_config()
   with pytest.raises(Exception):
     train_utils.create_train_state(c, 0, helpers.make_batch(2, c))
+
+
+def test_bench_algorithmic_work_matches_survey():
+  """algorithmic TFLOP per train_step per device — 26.93 (128 px, B=56), 25.55 without the ResNet
+  branch, 3.800 (B=8), 37.73 (256 px, B=24). bench.py's model-FLOP figure is derived from these."""
+  import importlib.util
+  import os
+  spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(os.path.dirname(__file__)), "bench.py"))
+  bench = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(bench)
+  assert abs(bench.algorithmic_tflop_per_step(56) - 26.93) < 0.01
+  assert abs(bench.algorithmic_tflop_per_step(56, pretrained=False) - 25.55) < 0.01
+  assert abs(bench.algorithmic_tflop_per_step(8) - 3.800) < 0.005
+  assert abs(bench.algorithmic_tflop_per_step(24, True, 256) - 37.73) < 0.01
+  cfg = bench.make_config(256, False, False)
+  assert (cfg.image_size, cfg.pretrained_image_contrastive, cfg.word_contrastive) == (256, False, False)
+  b = bench.synth_batch(4, cfg, 1)
+  assert b["image"].shape == (4, 256, 256, 3) and b["max_len"].min() >= 3 and b["max_len"].max() <= 17
+  assert torch.allclose(b["sentence_embedding"], b["embedding"].sum(1) / b["max_len"])
