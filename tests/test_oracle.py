@@ -166,3 +166,71 @@ def test_golden_fixture():
   now = make_golden.compute()
   for k in gold.files:
     assert np.allclose(now[k], gold[k], rtol=2e-4, atol=1e-5), k
+
+
+def test_jax_image_resize_bilinear_weights_known_answer():
+  """get_pretrained_embs resizes with jax.image.resize(..., "bilinear") (pretrained_model_utils.py:118-121). Restated
+  from jax's compute_weight_mat: sample_f = (o + 0.5) / scale - 0.5, triangle kernel of width max(1/scale, 1) (the
+  anti-aliasing when down-sampling), taps outside the image dropped, weights renormalised. The oracle uses torch's
+  interpolate (antialias only when down-sampling): both must agree for 128 -> 224 and for 256 -> 224."""
+  import numpy as np
+
+  def weight_mat(S, T):
+    inv = S / T
+    ks = max(inv, 1.0)
+    M = np.zeros((T, S))
+    for o in range(T):
+      c = (o + 0.5) * inv - 0.5
+      j = np.arange(S)
+      w = np.maximum(0.0, 1.0 - np.abs(j - c) / ks)
+      M[o] = w / w.sum()
+    return M
+
+  for S in (128, 256):
+    x = torch.rand(2, S, S, 3, dtype=torch.float64)
+    M = torch.from_numpy(weight_mat(S, 224))
+    want = torch.einsum("ij,njkc,lk->nilc", M, x, M)
+    got = torch.nn.functional.interpolate(x.permute(0, 3, 1, 2), size=(224, 224), mode="bilinear", align_corners=False,
+                                          antialias=S > 224).permute(0, 2, 3, 1)
+    assert (got - want).abs().max() < 1e-6
+  # 2-tap rows when up-sampling, up to 3 when 256 -> 224; border rows keep their full weight on the edge pixel
+  assert (weight_mat(128, 224) > 0).sum(1).max() == 2 and (weight_mat(256, 224) > 0).sum(1).max() == 3
+  assert abs(weight_mat(128, 224)[0, 0] - 1.0) < 1e-12
+
+
+def test_preprocess_batch_known_answers():
+  """COCODataset.preprocess (coco_dataset.py:127-167) restated: flip is an exact index reversal along W, values are
+  clipped to [0,1], the sentence embedding sums ALL word slots (padded ones included) and divides by the caption's
+  length, and the chosen caption's tensors are plain gathers."""
+  img = torch.arange(2 * 2 * 3 * 3, dtype=torch.float32).reshape(2, 2, 3, 3) / 20.0 - 0.2
+  emb = torch.ones(2, 3, 4, 5)
+  emb[1, 2] = 2.0
+  lens = torch.tensor([[4, 2, 3], [1, 4, 2]])
+  out = orc.preprocess_batch({"image": img, "caption/embedding": emb, "caption/max_len": lens},
+                             flip=torch.tensor([True, False]), sentence_idx=torch.tensor([1, 2]), z=torch.zeros(2, 8))
+  assert torch.equal(out["image"][0], img[0].flip(1).clamp(0, 1)) and torch.equal(out["image"][1], img[1].clamp(0, 1))
+  assert out["image"].min() >= 0 and out["image"].max() <= 1
+  assert torch.equal(out["max_len"], torch.tensor([[2.0], [2.0]]))
+  assert torch.equal(out["embedding"][1], emb[1, 2])
+  assert torch.allclose(out["sentence_embedding"][0], torch.full((5,), 4 * 1.0 / 2))   # 4 slots summed / len 2
+  assert torch.allclose(out["sentence_embedding"][1], torch.full((5,), 4 * 2.0 / 2))
+
+
+def test_generator_spectral_norm_state_advances_only_in_train_g_d():
+  """xmc_gan.py:225 (train_d discards the generator's new collections) vs :159,181 (train_g_d keeps them), with
+  config.g_spectral_norm=True: u0 of every generator layer is one power-iteration step ahead after a train_step, not
+  two, and SpectralConv/SpectralDense replace every Conv/Dense name in the generator tree."""
+  cfg = helpers.small_config(gf_dim=8, df_dim=8, g_spectral_norm=True)
+  _, _, g_vars, d_vars = helpers.cpu_variables(cfg, E=16, seed=3)
+  names = {k for path, _ in orc.tree_leaves(g_vars["params"]) for k in path.split("/")}
+  assert not any(n.startswith(("Conv_", "Dense_")) for n in names)
+  state = orc.make_state(g_vars, d_vars)
+  batch = helpers.make_batch(4, cfg, E=16, L=5, seed=9, min_len=2)
+  new_state, _ = orc.train_step(state, batch, cfg, orc.FP32)
+  p = state["g_params"]["SpectralDense_1"]["kernel"]
+  u0 = state["generator_state"]["spectral_norm_stats"]["SpectralDense_1"]["u0"]
+  _, u1 = orc.spectral_normalize(p, u0)
+  got = new_state["generator_state"]["spectral_norm_stats"]["SpectralDense_1"]["u0"]
+  assert torch.allclose(got, u1, atol=1e-6)
+  _, u2 = orc.spectral_normalize(p, u1)
+  assert not torch.allclose(got, u2, atol=1e-4)
