@@ -55,7 +55,7 @@ class ClockSampler:
   def start(self):
     try:
       self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                    "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+                                    "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
       self.thread = threading.Thread(target=self._read, daemon=True)
       self.thread.start()
     except OSError:
@@ -288,7 +288,8 @@ def run_b200(args):
     roofline = {"bound": "tensor", "kernel": dom, "achieved": round(ach, 1), "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": round(ach / peak_tf, 4), "traffic": None,
                 "traffic_note": "aggregate over launches of many shapes; per-shape ncu DRAM bytes (= algorithmic "
-                                "bytes, inputs read once) are in profiles/r01_gemm_shape_classes.md",
+                                "bytes, inputs read once) are in profiles/r01_gemm_shape_classes.md, r01_resident_full.md, "
+                                "r01_wgrad_tap3_full.md; the forward figure includes conv3x3_resident_kernel launches",
                 "peak_source": peak_src,
                 "launches_timed": gemm[dom]["launches"],
                 "share_of_step": round(gemm[dom]["ms"] / ms_instr, 3),
