@@ -30,7 +30,10 @@ def test_native_library_is_loaded():
 
 @gpu
 @pytest.mark.parametrize("N,H,W,C,Cout,k", [(2, 16, 16, 64, 64, 3), (3, 32, 32, 96, 192, 3), (16, 4, 4, 192, 64, 3),
-                                             (1, 128, 128, 96, 96, 3), (5, 8, 8, 64, 32, 1), (2, 4, 4, 16, 16, 3)])
+                                             (1, 128, 128, 96, 96, 3), (5, 8, 8, 64, 32, 1), (2, 4, 4, 16, 16, 3),
+                                             # resident-weights / halo-row kernel and tap3 wgrad: two W tiles with a
+                                             # 16-channel ragged chunk, a single 64-channel chunk, non-square maps
+                                             (1, 4, 256, 80, 48, 3), (2, 2, 128, 64, 96, 3), (1, 6, 128, 96, 32, 3)])
 def test_conv_forward_and_wgrad_match_oracle(N, H, W, C, Cout, k):
   """tcgen05 implicit-GEMM conv vs the oracle's conv2d on bf16-rounded operands: fp32 results within 1e-4 rel."""
   _, _, ops, *_ = _mods()
