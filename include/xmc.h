@@ -30,6 +30,9 @@ const char* xmc_strerror(int code);
 /* Last CUDA error string seen by this thread inside the library (diagnostics only). */
 const char* xmc_last_cuda_error(void);
 int xmc_version(void);
+/* sizeof of the ABI structs as compiled into the library: 0 XmcConvDesc, 1 XmcWgradDesc, 2 XmcBnDesc, 3 XmcPrepEntry,
+ * 4 XmcSnEntry (-1 otherwise). A binding checks its own mirror of a struct against this before the first call. */
+int xmc_sizeof(int which);
 int xmc_num_sms(void);
 
 /* ------------------------------------------------------------------------------------------------------------

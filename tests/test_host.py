@@ -16,7 +16,10 @@ def test_library_exports_every_declared_symbol():
   L = _lib.lib()
   for name in decl:
     assert hasattr(L, name), name
-  assert L.xmc_version() >= 100
+  assert L.xmc_version() >= 101
+  # struct mirrors: the loader refuses a layout mismatch; spot-check two sizes against the header by hand
+  assert L.xmc_sizeof(0) == ctypes.sizeof(_lib.ConvDesc) and L.xmc_sizeof(1) == ctypes.sizeof(_lib.WgradDesc)
+  assert L.xmc_sizeof(2) == ctypes.sizeof(_lib.BnDesc) == 11 * 4 and L.xmc_sizeof(99) == -1
   assert L.xmc_strerror(-1).decode().startswith("invalid")
 
 

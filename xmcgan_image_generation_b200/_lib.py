@@ -120,6 +120,10 @@ def lib():
     fn = getattr(L, name)  # AttributeError here means the .so does not export a declared symbol
     fn.restype = res
     fn.argtypes = args
+  # the ctypes mirrors above must have the layout the library was compiled with
+  for which, cls in enumerate((ConvDesc, WgradDesc, BnDesc, PrepEntry, SnEntry)):
+    if L.xmc_sizeof(which) != ctypes.sizeof(cls):
+      raise XmcError(f"ABI mismatch: sizeof({cls.__name__}) = {ctypes.sizeof(cls)}, library says {L.xmc_sizeof(which)}")
   _LIB = L
   return L
 

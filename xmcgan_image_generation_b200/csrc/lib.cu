@@ -37,5 +37,15 @@ extern "C" const char* xmc_strerror(int code) {
 }
 
 extern "C" const char* xmc_last_cuda_error(void) { return xmc::g_err; }
-extern "C" int xmc_version(void) { return 100; }
+extern "C" int xmc_version(void) { return 101; }
+extern "C" int xmc_sizeof(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(XmcConvDesc);
+    case 1: return (int)sizeof(XmcWgradDesc);
+    case 2: return (int)sizeof(XmcBnDesc);
+    case 3: return (int)sizeof(XmcPrepEntry);
+    case 4: return (int)sizeof(XmcSnEntry);
+    default: return -1;
+  }
+}
 extern "C" int xmc_num_sms(void) { return xmc::num_sms(); }
