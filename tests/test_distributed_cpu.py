@@ -37,7 +37,13 @@ def _worker(rank, world, port, out):
   mean = flat / world
   loss = torch.tensor([r["d_loss"].item()])
   parallel.all_reduce_sum_(loss)
-  out[rank] = (local, mean, loss / world)
+  # cross-replica BatchNorm groups (device_utils.get_device_groups, xmc_net.py:196-200): a group spanning both ranks
+  # sums the per-channel statistics over the group; a group of one replica means "no exchange" (None)
+  grp = parallel.bn_group(2 * 4, 4)
+  stats = torch.tensor([float(rank + 1), 10.0 * (rank + 1)])
+  parallel.all_reduce_sum_(stats, group=grp[0])
+  solo = parallel.bn_group(4, 4)
+  out[rank] = (local, mean, loss / world, (grp[1], stats.tolist(), solo))
   dist.destroy_process_group()
 
 
@@ -47,7 +53,8 @@ def test_two_rank_gradient_and_metric_mean():
   mgr = mp.Manager()
   out = mgr.dict()
   mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
-  (l0, m0, s0), (l1, m1, s1) = out[0], out[1]
+  (l0, m0, s0, g0), (l1, m1, s1, g1) = out[0], out[1]
+  assert g0 == g1 == (2, [3.0, 30.0], None)
   assert torch.allclose(m0, m1)
   assert torch.allclose(m0, (l0 + l1) / 2, rtol=1e-6, atol=1e-8)
   assert not torch.allclose(l0, l1)  # different shards -> different local gradients
