@@ -87,7 +87,7 @@ typedef struct {
   int Cb, ldB;             /* xb channels (GEMM N) and pixel pitch */
   int KH, KW, pad_h, pad_w;
   int batched;             /* 1: one output matrix per image n (no reduction over n) */
-  int out_mode;            /* 0 fp32 atomic accumulate, 1 fp32 store, 2 bf16 store (1,2 force a single K split) */
+  int out_mode;            /* 0 fp32 accumulate (dw += ..., deterministic), 1 fp32 store, 2 bf16 store (1,2: one K split) */
   int ldOut;
   long long out_tap_stride, out_batch_stride;
   float alpha;
@@ -103,7 +103,14 @@ typedef struct {
   long long pitchWA, pitchHA, pitchNA;
 } XmcWgradDesc;
 
-int xmc_conv2d_wgrad(const XmcWgradDesc* d, const void* xa, const void* xb, void* dw, void* stream);
+/* out_mode 0 is DETERMINISTIC: when the reduction over pixels is split across CTAs (or sub-pixel parity taps share a
+ * destination) every CTA stores its partial tile into the caller's workspace and a second kernel adds the partials
+ * to dw in a fixed order — two launches on the same inputs give bit-identical results (XLA's behaviour; round 1 used
+ * red.global.add). xmc_conv2d_wgrad_workspace_bytes reports the bytes needed (0 when no second stage is needed);
+ * workspace must be 16-byte aligned and may be reused by the next launch on the same stream. */
+int xmc_conv2d_wgrad_workspace_bytes(const XmcWgradDesc* d, long long* bytes);
+int xmc_conv2d_wgrad(const XmcWgradDesc* d, const void* xa, const void* xb, void* dw, void* workspace,
+                     long long workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Conditional batch normalisation (train mode), fused with relu and nearest 2x upsampling.
@@ -124,17 +131,22 @@ typedef struct {
   int replicas;
 } XmcBnDesc;
 
-int xmc_bn_stats(const void* x, long long P, int C, int ld, float* sums /*[2C], zeroed by caller*/, void* stream);
+/* Reductions are DETERMINISTIC (no atomics): a kernel with `rows` thread blocks leaves one partial row per block in
+ * the caller's `partials` buffer (rows x width floats) and a second kernel adds the rows in index order. `rows` is
+ * the caller's choice (any value >= 1; a few per SM for large tensors, see xmc_num_sms). */
+int xmc_sum_partials(const float* partials, int rows, int width, float* out /*[width]*/, int accumulate, void* stream);
+/* sums[2C] = per-channel (sum x, sum x^2) over P pixels (overwritten); partials: rows x 2C floats of scratch */
+int xmc_bn_stats(const void* x, long long P, int C, int ld, float* sums, float* partials, int rows, void* stream);
 int xmc_bn_finalize(const float* sums, long long P, int C, float eps, float momentum, const float* ra_mean,
                     const float* ra_var, float* new_ra_mean, float* new_ra_var, float* mean_rstd /*[2C]*/,
                     void* stream);
 int xmc_bn_eval_stats(const float* ra_mean, const float* ra_var, int C, float eps, float* mean_rstd, void* stream);
 int xmc_bn_apply(const XmcBnDesc* d, const void* x, const float* mean_rstd, const void* gb, void* y, void* stream);
-/* backward, pass 1: dgb (fp32, same row/column layout as gb) = d(gamma), d(beta); sums[2C] (zeroed by caller) +=
- * per-channel sum(dxhat), sum(dxhat*xhat). dy has the upsampled shape when d->upsample. For Hc == 1 the gamma/beta
- * columns of dgb are accumulated atomically and must be zero-filled by the caller; for Hc > 1 they are overwritten. */
+/* backward, pass 1: dgb (fp32, same row/column layout as gb) = d(gamma), d(beta) (overwritten); sums[2C] =
+ * per-channel sum(dxhat), sum(dxhat*xhat) (overwritten). dy has the upsampled shape when d->upsample.
+ * partials: rows x 2C floats of scratch (see xmc_sum_partials). */
 int xmc_bn_bwd_reduce(const XmcBnDesc* d, const void* dy, const void* x, const float* mean_rstd, const void* gb,
-                      float* dgb, float* sums, void* stream);
+                      float* dgb, float* sums, float* partials, int rows, void* stream);
 /* backward, pass 2: dx = rstd*(dxhat - mean(dxhat) - xhat*mean(dxhat*xhat)) */
 int xmc_bn_bwd_apply(const XmcBnDesc* d, const void* dy, const void* x, const float* mean_rstd, const void* gb,
                      const float* sums, void* dx, void* stream);
@@ -146,8 +158,8 @@ int xmc_pool2(const void* a, const void* b, const void* low, int N, int Hout, in
               void* out_relu, void* stream);
 /* transpose of pool2: g[n,2h+i,2w+j,c] = scale * dout[n,h,w,c] */
 int xmc_unpool2(const void* dout, int N, int Hin, int Win, int C, float scale, void* g, void* stream);
-/* out[c] += sum_p x[p][c] (bias gradients) */
-int xmc_colsum(const void* x, long long P, int C, int ld, float* out, void* stream);
+/* out[c] += sum_p x[p][c] (bias gradients); partials: rows x C floats of scratch, may be NULL when rows == 1 */
+int xmc_colsum(const void* x, long long P, int C, int ld, float* out, float* partials, int rows, void* stream);
 /* x_pool[n][c] = sum_hw relu(x[n,hw,c]) (xmcgan/nets/xmc_net.py:97-98) and its backward */
 int xmc_relu_sumhw(const void* x, int N, int HW, int C, float* out, void* stream);
 int xmc_relu_sumhw_bwd(const void* x, const float* dout, int N, int HW, int C, void* dx, void* stream);
@@ -187,7 +199,7 @@ typedef struct {
 typedef struct {
   long long w_off;        /* kernel viewed as [rows][cols] = [taps*cin][cout] */
   long long t_off;        /* row-vector workspace offset (t = W u0^T) */
-  long long s_off;        /* column-vector workspace offset (s = t W) */
+  long long s_off;        /* workspace offset of the [ceil(rows/256)][cols] row-tile partials of s = t W */
   long long u_off;        /* offset of u0 inside the spectral_norm_stats buffers */
   int rows, cols;
   int row_block_begin;    /* prefix sum of ceil(rows/8) */
@@ -197,13 +209,15 @@ typedef struct {
 } XmcSnEntry;
 
 /* One power-iteration step for every layer of the table (layers.py:94-101 / :211-221). scalars: float[4*n] =
- * sum_t2 | norm_t | 1/(sigma+eps) | <dW,W>. Writes the new u0 to u0_new (old state is left untouched). */
+ * unused | norm_t | 1/(sigma+eps) | <dW,W>. Writes the new u0 to u0_new (old state is left untouched). Deterministic:
+ * s_ws holds per-row-tile partial sums (sum over layers of ceil(rows/256)*cols floats) that are added in tile order. */
 int xmc_sn_forward(const XmcSnEntry* table_dev, int n, float eps, const float* params, const float* u0, float* u0_new,
                    float* t_ws, float* s_ws, long long s_ws_floats, float* scalars, int total_row_blocks,
                    int total_col_tiles, void* stream);
-/* grads (holding d/dW~) -> d/dW in place: dW = dW~/s' - <dW~,W>/s'^2 * v0^T u1 (u1, v0 stop-gradient). */
+/* grads (holding d/dW~) -> d/dW in place: dW = dW~/s' - <dW~,W>/s'^2 * v0^T u1 (u1, v0 stop-gradient).
+ * dot_partials: total_elem_blocks floats of scratch (block partials of <dW~,W>, added in a fixed order). */
 int xmc_sn_backward(const XmcSnEntry* table_dev, int n, const float* params, float* grads, const float* t_ws,
-                    const float* u0_new, float* scalars, int total_elem_blocks, void* stream);
+                    const float* u0_new, float* scalars, float* dot_partials, int total_elem_blocks, void* stream);
 int xmc_prep_weights(const XmcPrepEntry* table_dev, int n, int total_tiles, const float* params,
                      const float* sn_scalars, int n_sn, void* arena, float* bias_arena, const float* cscale,
                      void* stream);
@@ -217,10 +231,12 @@ int xmc_subpixel_prep(const float* w, const float* scale, int Cin, int Cout, voi
  * (xmcgan/xmc_gan.py:172-177,252). bias_corr = 1 - beta^t. n must be a multiple of 4.
  * step_dev: optional device int holding the number of steps taken so far; when given, the bias corrections are
  * computed on the device from t = *step_dev + 1 (bias_corr1/2 are ignored) and *step_dev is incremented afterwards, so
- * that the launch can be replayed from a CUDA graph. */
-int xmc_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
-             float bias_corr1, float bias_corr2, float grad_scale, float* ema, float ema_decay, int* step_dev,
-             void* stream);
+ * that the launch can be replayed from a CUDA graph.
+ * The hyper-parameters are doubles: flax forms (1 - beta) and the bias corrections in Python double precision before
+ * they meet the fp32 arrays; 1.f - 0.999f is 1.3e-5 off, which is visible in the second moment. */
+int xmc_adam(float* p, const float* g, float* m, float* v, long long n, double lr, double beta1, double beta2,
+             double eps, double bias_corr1, double bias_corr2, double grad_scale, float* ema, double ema_decay,
+             int* step_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Row l2-normalisation xhat = x*rsqrt(max(sum x^2, eps)) (attention_lib.l2_normalize, attention_lib.py:30-33), one
@@ -306,9 +322,10 @@ int xmc_conv_c3_in(const void* x, const void* w, int ldw, const float* bias, int
 /* mode 0: y fp32 (+= if accumulate); mode 1: y = (tanh(v)+1)/2 fp32 plus bf16 copy y_bf16 */
 int xmc_conv_c3_out(const void* x, const void* w, int ldw, const float* bias, int N, int H, int W, int Cin, int KH,
                     int KW, int mode, int accumulate, float* y, void* y_bf16, void* stream);
-/* out[tap_o*s_tap + c3*s_c3 + c*s_c] += sum_p x3[p+shift(tap)][c3]*y[p][c], tap_o = flip ? taps-1-tap : tap */
+/* out[tap_o*s_tap + c3*s_c3 + c*s_c] += sum_p x3[p+shift(tap)][c3]*y[p][c], tap_o = flip ? taps-1-tap : tap.
+ * Deterministic: partials = N*ceil(H/8)*ceil(W/64) x (KH*KW*3*C) floats of scratch, added in block order. */
 int xmc_wgrad_c3(const void* x3, const void* y, int N, int H, int W, int C, int KH, int KW, int flip, long long s_tap,
-                 int s_c3, int s_c, float* out, void* stream);
+                 int s_c3, int s_c, float* out, float* partials, void* stream);
 int xmc_pool2_small(const void* a, int N, int Hout, int Wout, int C, float scale, void* out, void* stream);
 int xmc_unpool2_add_f32(const float* d, int N, int Hin, int Win, int C, float scale, float* g, void* stream);
 int xmc_tanh01_bwd(const float* dimg, const float* img, long long n, void* dpre, void* stream);

@@ -1,0 +1,103 @@
+"""Sharp single-op GPU checks added in round 2: Adam + EMA (host-side and device-side step count), determinism."""
+import pytest
+import torch
+
+from oracle import xmc_oracle as orc
+from tests import helpers
+
+gpu = pytest.mark.gpu
+
+
+@gpu
+@pytest.mark.parametrize("use_step_dev", [False, True])
+def test_adam_and_ema_single_op_matches_oracle(use_step_dev):
+  """xmc_adam (flax.optim.Adam.apply_gradient, created train_utils.py:181-186, applied xmc_gan.py:172-173, + the
+  polyak EMA of :174-177) for steps t = 1..4 on one flat buffer, with gradient scaling 1/world folded in, vs
+  orc.adam_apply: parameters / moments 2e-6 rel-L2 (fp32 arithmetic, different operation order), EMA 1e-6. With
+  step_dev the bias corrections come from the device-side step count (the CUDA-graph path), host values ignored."""
+  from xmcgan_image_generation_b200 import _lib, ops
+  torch.manual_seed(7)
+  n = 4096 + 36
+  p0 = torch.randn(n) * 0.05
+  lr, b1, b2, eps, decay, world = 4e-4, 0.5, 0.999, 1e-8, 0.999, 4
+  p = p0.cuda()
+  m, v, ema = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda"), p0.cuda()
+  step_dev = torch.zeros(1, dtype=torch.int32, device="cuda") if use_step_dev else None
+  o_p, o_opt, o_ema = {"w": p0.clone()}, orc.adam_init({"w": p0}), p0.clone()
+  for t in range(1, 5):
+    g = torch.randn(n) * (10.0 ** -t)            # magnitudes from 1e-1 down to 1e-4
+    g[::7] = 0.0                                 # exact zeros: update must be exactly -lr*m_hat/(sqrt(v_hat)+eps)
+    gsum = (g * world).cuda()                    # what the sum all-reduce leaves in the buffer
+    bogus = 0.123 if use_step_dev else None      # host bias corrections must be ignored when step_dev is given
+    ops._call("xmc_adam", p.data_ptr(), gsum.data_ptr(), m.data_ptr(), v.data_ptr(), n, lr, b1, b2, eps,
+              bogus or 1.0 - b1 ** t, bogus or 1.0 - b2 ** t, 1.0 / world, ema.data_ptr(), decay,
+              step_dev.data_ptr() if use_step_dev else None, _lib.stream())
+    o_p, o_opt = orc.adam_apply(o_p, o_opt, {"w": g}, lr, b1, b2)
+    o_ema = o_ema * decay + (1 - decay) * o_p["w"]
+    # the update itself, not only the parameters (whose relative change per step is tiny)
+    assert helpers.rel(p.cpu() - p0, o_p["w"] - p0) < 1e-4, t
+    assert helpers.rel(p, o_p["w"]) < 2e-6 and helpers.rel(m, o_opt["m"]["w"]) < 2e-6
+    assert helpers.rel(v, o_opt["v"]["w"]) < 2e-6 and helpers.rel(ema, o_ema) < 1e-6
+  if use_step_dev:
+    assert int(step_dev.item()) == 4
+
+
+def _state(cfg, seed):
+  from tests.test_gpu_parity import _build
+  from xmcgan_image_generation_b200 import train_utils
+  g_vars, d_vars, g_params, g_stats, d_params, d_u = _build(cfg, seed=seed)
+  return train_utils.TrainState(0, train_utils.Optimizer(g_params, cfg.g_lr, cfg.beta1, cfg.beta2),
+                                train_utils.Optimizer(d_params, cfg.d_lr, cfg.beta1, cfg.beta2),
+                                {"batch_stats": g_stats}, {"spectral_norm_stats": d_u}, g_params.clone())
+
+
+@gpu
+@pytest.mark.parametrize("pretrained", [False, True])
+def test_train_step_is_bit_reproducible(pretrained):
+  """The reference (one XLA executable) is run-to-run deterministic. So is this path: the weight-gradient split-K goes
+  through an fp32 workspace and a fixed-order second stage, BatchNorm / bias / spectral-norm reductions are two-stage
+  without atomics, the bilinear-resize transpose is a gather. Two runs of two train_steps from the same state on the
+  same batches must agree in EVERY bit of the metrics and of the new state (with and without the ResNet branch)."""
+  from xmcgan_image_generation_b200 import train_utils, xmc_gan
+  cfg = helpers.small_config(pretrained_image_contrastive=pretrained)
+  additional = xmc_gan.create_additional_data(cfg, variables=orc.resnet50_random_variables(2)) if pretrained else {}
+  batches = [helpers.make_batch(6, cfg, seed=60 + i) for i in range(2)]
+  runs = []
+  for _ in range(2):
+    state = _state(cfg, 19)
+    ms = []
+    for b in batches:
+      state, m = train_utils.train_step(None, state, b, xmc_gan, None, None, cfg, additional)
+      ms.append(m.compute())
+    runs.append((state, ms))
+  (s1, m1), (s2, m2) = runs
+  assert m1 == m2, (m1, m2)
+  for name, a, b in (("g", s1.g_optimizer.target.buf, s2.g_optimizer.target.buf),
+                     ("d", s1.d_optimizer.target.buf, s2.d_optimizer.target.buf),
+                     ("g.m", s1.g_optimizer.m, s2.g_optimizer.m), ("g.v", s1.g_optimizer.v, s2.g_optimizer.v),
+                     ("d.m", s1.d_optimizer.m, s2.d_optimizer.m), ("d.v", s1.d_optimizer.v, s2.d_optimizer.v),
+                     ("ema", s1.ema_params.buf, s2.ema_params.buf)):
+    assert torch.equal(a, b), name
+  for key, coll in (("generator_state", "batch_stats"), ("discriminator_state", "spectral_norm_stats")):
+    for (path, a), (_, b) in zip(orc.tree_leaves(getattr(s1, key)[coll].to_cpu_tree()),
+                                 orc.tree_leaves(getattr(s2, key)[coll].to_cpu_tree())):
+      assert torch.equal(a, b), (coll, path)
+
+
+@gpu
+def test_wgrad_split_k_is_deterministic_and_matches_single_pass():
+  """The layer with the deepest K split (3x3, 96 -> 96 at 128x128: 1 output tile per tap, ~49 splits) twice on the
+  same inputs: bit-identical; and accumulate semantics: a second launch into the same buffer doubles it exactly."""
+  from xmcgan_image_generation_b200 import ops
+  torch.manual_seed(3)
+  N, S, C = 4, 128, 96
+  x = (torch.randn(N, S, S, C, device="cuda") * 0.5).to(torch.bfloat16)
+  dy = (torch.randn(N, S, S, C, device="cuda") * 0.1).to(torch.bfloat16)
+  outs = []
+  for _ in range(2):
+    dw = torch.zeros(9 * C * C, device="cuda")
+    ops.wgrad(x, dy, 3, dw, out_mode=0, ld_out=C, tap_stride=C * C)
+    outs.append(dw)
+  assert torch.equal(outs[0], outs[1])
+  ops.wgrad(x, dy, 3, outs[0], out_mode=0, ld_out=C, tap_stride=C * C)
+  assert torch.equal(outs[0], 2 * outs[1])

@@ -8,6 +8,10 @@ from oracle import xmc_oracle as orc
 from tests import helpers
 
 gpu = pytest.mark.gpu
+# per-leaf gradient bars vs the oracle with rounded cotangents: (rel-L2, cosine). The 256 px variant runs at width 8
+# with batch 2 (its BatchNorm statistics come from very few elements per channel at 4x4).
+GRAD_TOL = (3e-2, 0.999)
+GRAD_TOL_256 = (6e-2, 0.998)
 
 
 def _mods():
@@ -265,32 +269,35 @@ def test_generator_and_discriminator_apply_match_oracle():
     assert helpers.rel(a, b) < 1e-4, p
 
 
-def _assert_grad_tree(got_tree, ref_tree, ref32_tree, tol):
-  """Per-leaf rel-L2 against the bf16-policy oracle. The oracle does not model the bf16 storage of activation
-  GRADIENTS, so the per-leaf tolerance is max(tol, 3 x the distance between the bf16-policy and the fp32 oracle
-  gradients of that leaf) — the oracle's own measure of how sensitive that leaf is to bf16 rounding. Leaves whose
-  true gradient is (numerically) zero — biases in front of a BatchNorm — are compared in absolute terms."""
+def grad_tree_report(got_tree, ref_tree, tol, min_cos):
+  """Per-leaf comparison of a gradient tree with the oracle's (bf16 policy with rounded cotangents): rel-L2 <= tol and
+  cosine >= min_cos for every leaf whose true gradient is not numerically zero; the others (biases in front of a
+  BatchNorm) are compared in absolute terms against the largest leaf. Returns ((worst rel, its leaf, lowest cosine,
+  its leaf), [violations])."""
   ref = orc.tree_leaves(ref_tree)
-  ref32 = orc.tree_leaves(ref32_tree)
   scale = max(r.norm().item() for _, r in ref)
-  bad = []
-  for (path, g), (_, r), (_, r32) in zip(orc.tree_leaves(got_tree), ref, ref32):
+  bad, worst_e, worst_c = [], (0.0, None), (1.0, None)
+  for (path, g), (_, r) in zip(orc.tree_leaves(got_tree), ref):
+    g = g.float().cpu()
     if r.norm().item() > 1e-4 * scale:
-      e, noise = helpers.rel(g, r), helpers.rel(r, r32)
-      cos = torch.nn.functional.cosine_similarity(g.float().cpu().reshape(-1), r.reshape(-1), dim=0).item()
-      # direction: cosine > 0.99, relaxed to 0.95 on leaves the oracle itself marks as bf16-sensitive
-      if not (e < max(tol, 3 * noise) and cos > (0.95 if (tol > 0.1 or noise > 0.05) else 0.99)):
-        bad.append((path, round(e, 4), round(noise, 4), round(cos, 5)))
-    elif (g.float().cpu() - r).norm().item() > 1e-3 * scale:
-      bad.append((path, "abs", (g.float().cpu() - r).norm().item(), scale))
-  assert not bad, bad
+      e = helpers.rel(g, r)
+      cos = torch.nn.functional.cosine_similarity(g.reshape(-1), r.reshape(-1), dim=0).item()
+      worst_e = max(worst_e, (e, path))
+      worst_c = min(worst_c, (cos, path))
+      if not (e <= tol and cos >= min_cos):
+        bad.append((path, round(e, 4), round(cos, 5)))
+    elif (g - r).norm().item() > 1e-3 * scale:
+      bad.append((path, "abs", (g - r).norm().item(), scale))
+  return (worst_e[0], worst_e[1], worst_c[0], worst_c[1]), bad
 
 
 @gpu
 @pytest.mark.parametrize("variant", ["default", "no_sn", "no_word", "ragged", "px256", "g_sn"])
 def test_both_pullbacks_match_oracle(variant):
-  """d(d_loss)/d(params_d) and d(g_loss)/d(params_g) from ONE forward (xmc_gan.py:162-167) vs oracle autograd.
-  Tolerance 6e-2 rel-L2 per leaf vs the bf16-policy oracle (bf16 storage of activation gradients), losses 2e-3."""
+  """d(d_loss)/d(params_d) and d(g_loss)/d(params_g) from ONE forward (xmc_gan.py:162-167) vs oracle autograd under
+  Policy("bfloat16", round_grads=True) — the bf16 policy that also rounds activation COTANGENTS at the storage points,
+  which is what the CUDA path (and the reference's bf16 graph) does. Per leaf: rel-L2 <= GRAD_TOL, cosine >= GRAD_COS;
+  losses 2e-3 of their term sizes."""
   _, engine, ops, _, _, xmc_net = _mods()
   kw = {"no_sn": dict(d_spectral_norm=False), "no_word": dict(word_contrastive=False),
         "px256": dict(image_size=256, gf_dim=8, df_dim=8), "g_sn": dict(g_spectral_norm=True)}.get(variant, {})
@@ -298,7 +305,7 @@ def test_both_pullbacks_match_oracle(variant):
   B = {"ragged": 3, "px256": 2}.get(variant, 4)
   # 256 px: one more block in G and D, batch 2, width 8 — the configuration most sensitive to bf16 perturbations
   # (the oracle's own bf16-vs-fp32 gradients differ by > 10 % there); the sharp backward checks are the single-op tests
-  tol = 2e-1 if variant == "px256" else 6e-2
+  tol, min_cos = GRAD_TOL_256 if variant == "px256" else GRAD_TOL
   g_vars, d_vars, g_params, g_stats, d_params, d_u = _build(cfg, seed=4)
   batch = helpers.make_batch(B, cfg, seed=2, min_len=1 if variant == "ragged" else 3)
   dev = xmc_net.batch_to_device(batch)
@@ -323,16 +330,17 @@ def test_both_pullbacks_match_oracle(variant):
   g_eng.sn_backward(g_params.buf, g_grads, g_u_new)
   torch.cuda.synchronize()
   state = orc.make_state(g_vars, d_vars if d_eng.sn else {"params": d_vars["params"]})
-  r = orc.d_losses_and_grads(state, batch, cfg, orc.Policy("bfloat16"), want_g=True)
-  r32 = orc.d_losses_and_grads(state, batch, cfg, orc.FP32, want_g=True)
+  r = orc.d_losses_and_grads(state, batch, cfg, orc.Policy("bfloat16", round_grads=True), want_g=True)
   l = losses.cpu()
   # the totals are sums of terms of mixed sign (hinge_g = -mean(fake logit)): tolerance relative to the term sizes
   d_scale = (l[0].abs() + l[2].abs() + l[4].abs()).item()
   g_scale = (l[1].abs() + l[3].abs() + l[5].abs() + l[6].abs()).item()
   assert abs((l[0] + l[2] + l[4]).item() - r["d_loss"].item()) < 2e-3 * d_scale
   assert abs((l[1] + l[3] + l[5] + l[6]).item() - r["g_loss"].item()) < 2e-3 * g_scale
-  _assert_grad_tree(xmc_net.FlatTree(d_eng.layout, d_grads).to_cpu_tree(), r["d_grad"], r32["d_grad"], tol)
-  _assert_grad_tree(xmc_net.FlatTree(g_eng.layout, g_grads).to_cpu_tree(), r["g_grad"], r32["g_grad"], tol)
+  for name, lay, flat in (("d_grad", d_eng.layout, d_grads), ("g_grad", g_eng.layout, g_grads)):
+    worst, bad = grad_tree_report(xmc_net.FlatTree(lay, flat).to_cpu_tree(), r[name], tol, min_cos)
+    print(f"\n[{variant}] {name}: worst leaf rel-L2 {worst[0]:.3e} ({worst[1]}), lowest cosine {worst[2]:.5f} ({worst[3]})")
+    assert not bad, bad
 
 
 @gpu
@@ -465,34 +473,88 @@ def test_resnet_pieces_forward_and_backward_sharp():
     assert helpers.rel(dx, x.grad) < 3e-2, (pre, helpers.rel(dx, x.grad))
 
 
-@gpu
-def test_train_step_with_pretrained_image_contrastive():
-  """The reference's default configuration (pretrained_image_contrastive=True) through train_step vs the oracle."""
+def _pretrained_setup(seed=8):
   _, engine, ops, train_utils, xmc_gan, xmc_net = _mods()
   cfg = helpers.small_config(pretrained_image_contrastive=True)
   B = 3
   variables = orc.resnet50_random_variables(2)
-  g_vars, d_vars, g_params, g_stats, d_params, d_u = _build(cfg, seed=8)
-  batch = helpers.make_batch(2 * B, cfg, seed=9)
+  g_vars, d_vars, g_params, g_stats, d_params, d_u = _build(cfg, seed=seed)
+  batch = helpers.make_batch(2 * B, cfg, seed=seed + 1)
   ostate = orc.make_state(g_vars, d_vars)
   state = train_utils.TrainState(0, train_utils.Optimizer(g_params, cfg.g_lr, cfg.beta1, cfg.beta2),
                                  train_utils.Optimizer(d_params, cfg.d_lr, cfg.beta1, cfg.beta2),
                                  {"batch_stats": g_stats}, {"spectral_norm_stats": d_u}, g_params.clone())
   additional = xmc_gan.create_additional_data(cfg, variables=variables)
-  pol = orc.Policy("bfloat16")
+  pol = orc.Policy("bfloat16", round_grads=True)
   pre = lambda real, fake: orc.calculate_contrastive_loss_on_pretrained(variables, real, fake, pol)
+  return cfg, batch, state, ostate, additional, pol, pre
+
+
+@gpu
+def test_train_step_with_pretrained_image_contrastive():
+  """The reference's default configuration (pretrained_image_contrastive=True) through train_step vs the oracle, from
+  a mid-training optimiser state (helpers.warm_adam): all five metrics within 5e-3 of the largest, generator
+  parameter updates per leaf rel-L2 5e-2."""
+  _, engine, ops, train_utils, xmc_gan, xmc_net = _mods()
+  cfg, batch, state, ostate, additional, pol, pre = _pretrained_setup()
+  helpers.warm_adam(state, ostate)
+  g_old = state.g_optimizer.target.to_cpu_tree()
+  o_old = ostate["g_params"]
   state, metrics = train_utils.train_step(None, state, batch, xmc_gan, None, None, cfg, additional)
   got = metrics.compute()
   ostate, want = orc.train_step(ostate, batch, cfg, pol, pretrained_fn=pre)
   scale = max(abs(v) for v in want.values())
-  # 1e-2 of the largest metric: the metrics of train_g_d are taken AFTER train_d's Adam step, whose first update is
-  # sign-like (m / sqrt(v) = g / |g|): parameters with a noise-level gradient move by +-lr with a sign the split-K
-  # atomics decide, and at B=3 that shows up as a 5e-3 .. 6.5e-3 run-to-run spread of g_loss (measured over 14 runs)
+  print("\n[pretrained, warm Adam]", {k: (round(got[k], 5), round(want[k], 5)) for k in want})
   for k in ("d_loss", "g_loss", "c_loss_d", "c_loss_g", "c_loss_g_pretrained"):
-    assert abs(got[k] - want[k]) < 1e-2 * scale, (k, got[k], want[k])
+    assert abs(got[k] - want[k]) < 5e-3 * scale, (k, got[k], want[k])
   assert got["c_loss_g_pretrained"] > 0
-  for (p, a), (_, b) in zip(orc.tree_leaves(state.g_optimizer.target.to_cpu_tree()), orc.tree_leaves(ostate["g_params"])):
-    assert helpers.rel(a, b) < 5e-3, (p, helpers.rel(a, b))
+  rows = []
+  for (p, a), (_, a0), (_, b), (_, b0) in zip(orc.tree_leaves(state.g_optimizer.target.to_cpu_tree()),
+                                              orc.tree_leaves(g_old), orc.tree_leaves(ostate["g_params"]),
+                                              orc.tree_leaves(o_old)):
+    if (b - b0).norm() > 0:
+      rows.append((helpers.rel(a - a0, b - b0), p))
+  print("  worst generator update leaf:", max(rows))
+  assert max(rows)[0] < 5e-2, max(rows)
+
+
+@gpu
+def test_cold_start_train_step_with_pretrained_branch_is_sharp_once_the_sign_step_is_shared():
+  """Cold start (Adam t = 1) of the same configuration. train_g_d's metrics are taken AFTER train_d's first Adam
+  update, which is -lr * sign(g): hinge_g jumps from -8.4 to +7.4 here, and an element whose gradient sits at
+  rounding-noise level moves by +-lr on a coin flip of the implementation's rounding (the fp32 and the bf16 policy of
+  the ORACLE differ by 0.17 in g_loss for that reason; tools/bias_bisect.py, profiles/r02_bias_bisect.md). So the two
+  halves are checked separately and each sharply: (1) train_d's update: the updated discriminator parameters agree in
+  SIGN of the step on all but a small share of the elements; (2) train_g_d from the SAME updated discriminator (the
+  oracle continues from the CUDA path's parameters): all five metrics within 5e-3."""
+  _, engine, ops, train_utils, xmc_gan, xmc_net = _mods()
+  cfg, batch, state, ostate, additional, pol, pre = _pretrained_setup()
+  d_old = state.d_optimizer.target.to_cpu_tree()
+  b0, b1 = train_utils.split_input_dict(xmc_net.batch_to_device(batch), 2)
+  ob0, ob1 = orc.split_input_dict(batch, 2)
+  state = xmc_gan.train_d(None, state, b0, None, None, cfg)
+  ostate1, _ = orc.train_d(ostate, ob0, cfg, pol)
+  d_new = state.d_optimizer.target.to_cpu_tree()
+  same = total = 0
+  for (p, a), (_, a0), (_, b), (_, b0_) in zip(orc.tree_leaves(d_new), orc.tree_leaves(d_old),
+                                               orc.tree_leaves(ostate1["d_params"]), orc.tree_leaves(ostate["d_params"])):
+    same += int((torch.sign(a - a0) == torch.sign(b - b0_)).sum())
+    total += a.numel()
+  print(f"\n[cold start] train_d sign-step agreement {same / total:.4%}")
+  assert same / total > 0.97
+  # the oracle continues from the CUDA path's discriminator (parameters, moments, u0): same starting point for train_g_d
+  ostate1["d_params"] = d_new
+  ostate1["d_opt"] = {"step": 1,
+                      "m": xmc_net.FlatTree(state.d_optimizer.target.layout, state.d_optimizer.m).to_cpu_tree(),
+                      "v": xmc_net.FlatTree(state.d_optimizer.target.layout, state.d_optimizer.v).to_cpu_tree()}
+  ostate1["discriminator_state"] = {"spectral_norm_stats": state.discriminator_state["spectral_norm_stats"].to_cpu_tree()}
+  state, metrics = xmc_gan.train_g_d(None, state, b1, None, None, cfg, additional)
+  got = metrics.compute()
+  _, want, _ = orc.train_g_d(ostate1, ob1, cfg, pol, pre)
+  scale = max(abs(v) for v in want.values())
+  print("  ", {k: (round(got[k], 5), round(want[k], 5)) for k in want})
+  for k in ("d_loss", "g_loss", "c_loss_d", "c_loss_g", "c_loss_g_pretrained"):
+    assert abs(got[k] - want[k]) < 5e-3 * scale, (k, got[k], want[k])
 
 
 @gpu
@@ -626,9 +688,7 @@ def test_generate_batch_and_checkpoint_round_trip(tmp_path):
   assert torch.equal(other.ema_params.buf, state.ema_params.buf)
   state, m1 = train_utils.train_step(None, state, batch, xmc_gan, None, None, cfg, {})
   other, m2 = train_utils.train_step(None, other, batch, xmc_gan, None, None, cfg, {})
-  a, b = m1.compute(), m2.compute()
-  for k in a:
-    assert abs(a[k] - b[k]) <= 1e-3 * max(1.0, abs(a[k])), (k, a[k], b[k])   # atomics order only
+  assert m1.compute() == m2.compute()   # deterministic reductions: the restored copy continues bit for bit
 
 
 @gpu
@@ -730,14 +790,9 @@ def test_input_contract_producer_matches_oracle():
 @gpu
 def test_graphed_train_step_equals_eager_train_step():
   """train_utils.GraphedTrainStep (the whole train_step replayed from one CUDA graph) against the eager train_step on
-  an identically initialised state and the same 5 batches. Both sides carry their own atomics order and Adam's first
-  updates are sign-like (m / sqrt(v) = g / |g|), so trajectories drift apart by ~1 % of the largest metric within a
-  few steps; the checks are chosen to be sharp where the graph machinery could be wrong and tolerant of that drift:
-    * first step's metrics 1.5e-2, second 3e-2 of the largest metric (later ones only loosely);
-    * the NORM of the first two steps' parameter updates matches within 3 % (a stale device step count would change
-      Adam's bias correction: 1.5x at t=1 vs t=2) and the updates point the same way (cosine > 0.7);
-    * step counters on host and device exact; batch statistics (1e-2) / u0 (5e-2) after the first step: in graph mode
-      they are copied back into fixed buffers instead of swapped."""
+  an identically initialised state and the same 5 batches. Every reduction of the CUDA path has a fixed summation
+  order (deterministic split-K, two-stage statistics), so the two are compared BIT FOR BIT: metrics of every step,
+  parameters, Adam moments, EMA, batch statistics and u0 after 5 steps, host and device step counters."""
   _, engine, ops, train_utils, xmc_gan, xmc_net = _mods()
   cfg = helpers.small_config()
   B = 3
@@ -753,49 +808,30 @@ def test_graphed_train_step_equals_eager_train_step():
   def run(step_of):
     st = fresh()
     fn = step_of(st)
-    metrics, deltas, first = [], [], None
-    prev = (st.g_optimizer.target.buf.clone(), st.d_optimizer.target.buf.clone())
+    metrics = []
     for b in batches:
       st, m = fn(st, b)
       metrics.append(m.compute())
-      if first is None:  # mutable collections after ONE step (before the trajectories drift)
-        first = (st.generator_state["batch_stats"].to_cpu_tree(),
-                 st.discriminator_state["spectral_norm_stats"].to_cpu_tree())
-      cur = (st.g_optimizer.target.buf.clone(), st.d_optimizer.target.buf.clone())
-      deltas.append(tuple(c - p for c, p in zip(cur, prev)))
-      prev = cur
-    return st, metrics, deltas, first
+    return st, metrics
 
-  eager, em, ed, ef = run(lambda st: (lambda s, b: train_utils.train_step(None, s, b, xmc_gan, None, None, cfg, {})))
+  eager, em = run(lambda st: (lambda s, b: train_utils.train_step(None, s, b, xmc_gan, None, None, cfg, {})))
 
   def graphed(st):
     step = train_utils.GraphedTrainStep(st, batches[0], xmc_gan, None, None, cfg, {}, warmup=0)
     return lambda s, b: step(b)
 
-  st, gm, gd, gf = run(graphed)
+  st, gm = run(graphed)
   assert (st.step, st.d_optimizer.step, st.g_optimizer.step) == (5, 10, 5)
   assert int(st.d_optimizer.step_dev.item()) == 10 and int(st.g_optimizer.step_dev.item()) == 5
-  report = []
   for i, (a, b) in enumerate(zip(gm, em)):
-    scale = max(abs(v) for v in b.values())
-    report.append(("metric", i, max(abs(a[k] - b[k]) for k in b) / scale))
-  for i, (dg, de) in enumerate(zip(gd, ed)):
-    for x, y in zip(dg, de):
-      report.append(("delta", i, (x.norm() / y.norm()).item(),
-                     torch.nn.functional.cosine_similarity(x, y, dim=0).item()))
-  print("GRAPH-VS-EAGER", report)
-  for kind, i, *vals in report:
-    if kind == "metric":
-      # the trajectories of this tiny GAN are chaotic: by the fifth step two EAGER runs differ by 5 % as well
-      # measured spread over repeated runs: 0.3-0.8 % at the first step, up to 3 % by the fifth
-      assert vals[0] < (1.5e-2 if i == 0 else 3e-2 if i == 1 else 2.5e-1), (kind, i, vals)
-    else:
-      # measured: 1.000-1.008 at the first two steps (a wrong bias correction would give 1.5 / 1.17), 0.93-1.04 later
-      lo, hi = (0.97, 1.03) if i < 2 else (0.85, 1.15)
-      assert lo < vals[0] < hi and vals[1] > (0.7 if i < 2 else 0.3), (kind, i, vals)
+    assert a == b, (i, a, b)
+  for name, x, y in (("g", st.g_optimizer.target.buf, eager.g_optimizer.target.buf),
+                     ("d", st.d_optimizer.target.buf, eager.d_optimizer.target.buf),
+                     ("g.m", st.g_optimizer.m, eager.g_optimizer.m), ("d.v", st.d_optimizer.v, eager.d_optimizer.v),
+                     ("ema", st.ema_params.buf, eager.ema_params.buf)):
+    assert torch.equal(x, y), name
   # leaf by leaf (the alignment padding between leaves of a flat buffer is not state)
-  for tol, got_t, want_t in ((1e-2, gf[0], ef[0]), (5e-2, gf[1], ef[1])):
-    for (path, a), (_, b) in zip(orc.tree_leaves(got_t), orc.tree_leaves(want_t)):
-      assert helpers.rel(a, b) < tol, (path, helpers.rel(a, b))
-  last = orc.tree_leaves(st.generator_state["batch_stats"].to_cpu_tree())
-  assert any(not torch.equal(a, b) for (_, a), (_, b) in zip(last, orc.tree_leaves(gf[0])))   # ... and keep moving
+  for got_t, want_t in ((st.generator_state["batch_stats"], eager.generator_state["batch_stats"]),
+                        (st.discriminator_state["spectral_norm_stats"], eager.discriminator_state["spectral_norm_stats"])):
+    for (path, a), (_, b) in zip(orc.tree_leaves(got_t.to_cpu_tree()), orc.tree_leaves(want_t.to_cpu_tree())):
+      assert torch.equal(a, b), path

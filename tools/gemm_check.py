@@ -58,7 +58,11 @@ def wgrad(xa, xb, KH, KW, out_mode=0, batched=False, alpha=1.0):
   nb = N if batched else 1
   dt = torch.bfloat16 if out_mode == 2 else torch.float32
   out = torch.zeros((nb, KH * KW, Ca, Cb), device=dev, dtype=dt)
-  _lib.check(L.xmc_conv2d_wgrad(ctypes.byref(d), _lib.ptr(xa), _lib.ptr(xb), _lib.ptr(out), _lib.stream()))
+  need = ctypes.c_longlong(0)
+  _lib.check(L.xmc_conv2d_wgrad_workspace_bytes(ctypes.byref(d), ctypes.byref(need)))
+  ws = torch.empty(max(need.value, 16), device=dev, dtype=torch.uint8)
+  _lib.check(L.xmc_conv2d_wgrad(ctypes.byref(d), _lib.ptr(xa), _lib.ptr(xb), _lib.ptr(out), _lib.ptr(ws), need.value,
+                                _lib.stream()))
   torch.cuda.synchronize()
   return out
 

@@ -83,7 +83,7 @@ class SnEntry(ctypes.Structure):
   ]
 
 
-_CTYPE = {"int": ctypes.c_int, "long long": ctypes.c_longlong, "float": ctypes.c_float}
+_CTYPE = {"int": ctypes.c_int, "long long": ctypes.c_longlong, "float": ctypes.c_float, "double": ctypes.c_double}
 
 
 def declared_functions(header=HEADER):

@@ -7,9 +7,11 @@
 namespace xmc {
 
 // ---------------------------------------------------------------------------------------------------------------------
-// BatchNorm statistics: sums[c] += sum_p x[p][c], sums[C+c] += sum_p x[p][c]^2   (flax nn.BatchNorm, fp32 stats)
+// BatchNorm statistics (flax nn.BatchNorm, fp32 stats): block b leaves its partial sums in row b of
+// partials[gridDim.x][2C] ([c] = sum_p x[p][c], [C+c] = sum_p x[p][c]^2); sum_partials_kernel adds the rows in a fixed
+// order. No atomics anywhere: two runs on the same input are bit-identical.
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void bn_stats_kernel(const bf16* __restrict__ x, long long P, int C, int ld, float* __restrict__ sums) {
+__global__ void bn_stats_kernel(const bf16* __restrict__ x, long long P, int C, int ld, float* __restrict__ partials) {
   extern __shared__ float sm[];  // [lanes][cv*16]
   const int cv = C >> 3;
   const int cvb = min(cv - blockIdx.y * 256, 256);  // channel vectors handled by this blockIdx.y
@@ -38,8 +40,18 @@ __global__ void bn_stats_kernel(const bf16* __restrict__ x, long long P, int C, 
     for (int l = 0; l < lanes; ++l) a += sm[l * cvb * 16 + t];
     const int vv = t >> 4, i = t & 15;
     const int c = (blockIdx.y * 256 + vv) * 8 + (i & 7);
-    atomicAdd(sums + (i >> 3) * C + c, a);
+    partials[(long long)blockIdx.x * 2 * C + (i >> 3) * C + c] = a;
   }
+}
+
+// out[j] (+)= sum_r partials[r][j], rows added in index order (the deterministic second stage of every reduction here)
+__global__ void sum_partials_kernel(const float* __restrict__ partials, int rows, int width, float* __restrict__ out,
+                                    int accumulate) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= width) return;
+  float a = 0.f;
+  for (int r = 0; r < rows; ++r) a += partials[(long long)r * width + j];
+  out[j] = accumulate ? out[j] + a : a;
 }
 
 __global__ void bn_finalize_kernel(const float* __restrict__ sums, float invP, int C, float eps, float momentum,
@@ -134,19 +146,17 @@ __device__ __forceinline__ void bn_load_grad(const BnP& p, const bf16* dy, int n
 }
 
 // One thread owns one 8-channel vector v and a stream of (cond row, pixel-split) units: for each unit it walks the
-// (H/Hc)^2 pixels of that cond cell, so dgamma/dbeta need no cross-thread reduction (plain stores; atomics only when a
-// per-image cell is split over several threads). The per-channel BN terms S1 = sum dxhat, S2 = sum dxhat*xhat stay in
-// registers over ALL units of the thread, are combined per block in shared memory and leave through one global atomic
-// per channel per BLOCK of a grid sized by the SM count (the first version issued them per 256 items: at 16x16 that was
-// 8 M atomics on 1536 addresses and 30x the HBM time of the layer).
+// (H/Hc)^2 pixels of that cond cell (or every psplit-th pixel row of it), so dgamma/dbeta need no cross-block reduction.
+// The psplit parts of one cond row sit in consecutive `ri` slots of the same block (rpi % psplit == 0) and are combined
+// through shared memory in a fixed order. The per-channel BN terms S1 = sum dxhat, S2 = sum dxhat*xhat stay in
+// registers over ALL units of the thread, are combined per block in shared memory (fixed order) and leave as row
+// blockIdx.x of partials[gridDim.x][2C]; sum_partials_kernel finishes. No atomics: bit-identical from run to run.
 __global__ void bn_bwd_reduce_kernel(BnP p, const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                      const float* __restrict__ mr, const bf16* __restrict__ gb,
-                                     float* __restrict__ dgb, float* __restrict__ sums, long long total_rows,
+                                     float* __restrict__ dgb, float* __restrict__ partials, long long total_rows,
                                      int psplit, int rpi) {
-  extern __shared__ float sm[];  // [cv][16]
+  extern __shared__ float sm[];  // [rpi][cv][16]
   const int cv = p.C >> 3;
-  for (int t = threadIdx.x; t < cv * 16; t += blockDim.x) sm[t] = 0.f;
-  __syncthreads();
   const int v = threadIdx.x % cv, ri = threadIdx.x / cv;  // blockDim.x == cv * rpi
   const int c = v * 8;
   const int side = 1 << p.s;
@@ -157,55 +167,80 @@ __global__ void bn_bwd_reduce_kernel(BnP p, const bf16* __restrict__ dy, const b
     rstd[i] = mr[p.C + c + i];
     s1[i] = s2[i] = 0.f;
   }
+  float* slot = sm + ((long long)ri * cv + v) * 16;
   const long long units = total_rows * psplit;
-  for (long long u = (long long)blockIdx.x * rpi + ri; u < units; u += (long long)gridDim.x * rpi) {
+  // every thread of the block runs the same number of iterations (the shared-memory combine below needs barriers)
+  const long long iters = (units + (long long)gridDim.x * rpi - 1) / ((long long)gridDim.x * rpi);
+  for (long long it = 0; it < iters; ++it) {
+    const long long u = (it * gridDim.x + blockIdx.x) * rpi + ri;
+    const bool live = u < units;
     const int sp = (int)(u % psplit);  // pixel-split index (psplit > 1 only for per-image cells, Hc == 1)
     const long long row = u / psplit;
-    const int wc = row % p.Hc, hc = (row / p.Hc) % p.Hc, n = row / (p.Hc * p.Hc);
-    float gm[8], bt[8], dg[8], db[8];
-    load8(gb + row * p.ldG + p.goff + c, gm);
-    load8(gb + row * p.ldG + p.boff + c, bt);
+    float dg[8], db[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) dg[i] = db[i] = 0.f;
-    for (int a = sp; a < side; a += psplit) {
-      const int h = hc * side + a;
-      for (int b = 0; b < side; ++b) {
-        const int w = wc * side + b;
-        float f[8], g[8];
-        load8(x + (((long long)n * p.H + h) * p.W + w) * p.C + c, f);
-        bn_load_grad(p, dy, n, h, w, c, g);
+    if (live) {
+      const int wc = row % p.Hc, hc = (row / p.Hc) % p.Hc, n = row / (p.Hc * p.Hc);
+      float gm[8], bt[8];
+      load8(gb + row * p.ldG + p.goff + c, gm);
+      load8(gb + row * p.ldG + p.boff + c, bt);
+      for (int a = sp; a < side; a += psplit) {
+        const int h = hc * side + a;
+        for (int b = 0; b < side; ++b) {
+          const int w = wc * side + b;
+          float f[8], g[8];
+          load8(x + (((long long)n * p.H + h) * p.W + w) * p.C + c, f);
+          bn_load_grad(p, dy, n, h, w, c, g);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float xh = (f[i] - mean[i]) * rstd[i];
-          float gi = g[i];
-          if (p.relu && (xh * (gm[i] + 1.f) + bt[i]) <= 0.f) gi = 0.f;
-          dg[i] += gi * xh;
-          db[i] += gi;
-          const float dxh = gi * (gm[i] + 1.f);
-          s1[i] += dxh;
-          s2[i] += dxh * xh;
+          for (int i = 0; i < 8; ++i) {
+            const float xh = (f[i] - mean[i]) * rstd[i];
+            float gi = g[i];
+            if (p.relu && (xh * (gm[i] + 1.f) + bt[i]) <= 0.f) gi = 0.f;
+            dg[i] += gi * xh;
+            db[i] += gi;
+            const float dxh = gi * (gm[i] + 1.f);
+            s1[i] += dxh;
+            s2[i] += dxh * xh;
+          }
         }
       }
     }
-    float* og = dgb + row * p.ldG + p.goff + c;
-    float* ob = dgb + row * p.ldG + p.boff + c;
     if (psplit == 1) {
+      if (live) {
+        float* og = dgb + row * p.ldG + p.goff + c;
+        float* ob = dgb + row * p.ldG + p.boff + c;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { og[i] = dg[i]; ob[i] = db[i]; }
+        for (int i = 0; i < 8; ++i) { og[i] = dg[i]; ob[i] = db[i]; }
+      }
     } else {
+      // the psplit parts of a row occupy slots ri = k*psplit .. k*psplit + psplit-1 of this block: part 0 adds them up
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { atomicAdd(og + i, dg[i]); atomicAdd(ob + i, db[i]); }
+      for (int i = 0; i < 8; ++i) { slot[i] = dg[i]; slot[8 + i] = db[i]; }
+      __syncthreads();
+      if (live && sp == 0) {
+        float* og = dgb + row * p.ldG + p.goff + c;
+        float* ob = dgb + row * p.ldG + p.boff + c;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float a = 0.f, b = 0.f;
+          for (int k = 0; k < psplit; ++k) {
+            a += slot[(long long)k * cv * 16 + i];
+            b += slot[(long long)k * cv * 16 + 8 + i];
+          }
+          og[i] = a; ob[i] = b;
+        }
+      }
+      __syncthreads();
     }
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    atomicAdd(sm + v * 16 + i, s1[i]);
-    atomicAdd(sm + v * 16 + 8 + i, s2[i]);
-  }
+  for (int i = 0; i < 8; ++i) { slot[i] = s1[i]; slot[8 + i] = s2[i]; }
   __syncthreads();
   for (int t = threadIdx.x; t < cv * 16; t += blockDim.x) {
+    float a = 0.f;
+    for (int r = 0; r < rpi; ++r) a += sm[(long long)r * cv * 16 + t];
     const int vv = t >> 4, k = (t >> 3) & 1, i = t & 7;
-    atomicAdd(sums + k * p.C + vv * 8 + i, sm[t]);
+    partials[(long long)blockIdx.x * 2 * p.C + k * p.C + vv * 8 + i] = a;
   }
 }
 
@@ -325,7 +360,8 @@ __global__ void unpool2_kernel(const bf16* __restrict__ dout, int N, int H, int 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// out[c] += sum_p x[p][c]  (bias gradients)
+// out[c] += sum_p x[p][c]  (bias gradients). gridDim.x == 1: the block adds its sums to out directly; otherwise block b
+// stores them in row b of out (= partials[gridDim.x][C]) and sum_partials_kernel finishes in a fixed order.
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void colsum_kernel(const bf16* __restrict__ x, long long P, int C, int ld, float* __restrict__ out) {
   extern __shared__ float sm[];
@@ -351,7 +387,9 @@ __global__ void colsum_kernel(const bf16* __restrict__ x, long long P, int C, in
   for (int t = threadIdx.x; t < cvb * 8; t += blockDim.x) {
     float a = 0.f;
     for (int l = 0; l < lanes; ++l) a += sm[l * cvb * 8 + t];
-    atomicAdd(out + (blockIdx.y * 256 + (t >> 3)) * 8 + (t & 7), a);
+    const int c = (blockIdx.y * 256 + (t >> 3)) * 8 + (t & 7);
+    if (gridDim.x == 1) out[c] += a;
+    else out[(long long)blockIdx.x * C + c] = a;
   }
 }
 
@@ -368,7 +406,10 @@ __global__ void colsum_scalar_kernel(const bf16* __restrict__ x, long long P, in
     if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) atomicAdd(out + c, sm[0]);
+  if (threadIdx.x == 0) {
+    if (gridDim.x == 1) out[c] += sm[0];
+    else out[(long long)blockIdx.x * C + c] = sm[0];
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -536,20 +577,29 @@ __global__ void prep_caption_kernel(const float* __restrict__ emb, const int* __
 
 using namespace xmc;
 
-extern "C" int xmc_bn_stats(const void* x, long long P, int C, int ld, float* sums, void* stream) {
-  if (!x || !sums || P < 1 || C < 8 || (C % 8) || (ld % 8)) return XMC_EINVAL;
+static int launch_sum_partials(const float* partials, int rows, int width, float* out, int accumulate,
+                               cudaStream_t stream) {
+  sum_partials_kernel<<<ceil_div(width, 128), 128, 0, stream>>>(partials, rows, width, out, accumulate);
+  XMC_LAUNCH_CHECK();
+  return XMC_OK;
+}
+
+extern "C" int xmc_sum_partials(const float* partials, int rows, int width, float* out, int accumulate, void* stream) {
+  if (!partials || !out || rows < 1 || width < 1) return XMC_EINVAL;
+  return launch_sum_partials(partials, rows, width, out, accumulate, (cudaStream_t)stream);
+}
+
+extern "C" int xmc_bn_stats(const void* x, long long P, int C, int ld, float* sums, float* partials, int rows,
+                            void* stream) {
+  if (!x || !sums || !partials || rows < 1 || P < 1 || C < 8 || (C % 8) || (ld % 8)) return XMC_EINVAL;
   const int cv = C / 8;
   const int ny = ceil_div(cv, 256);
   const int cvb = cv < 256 ? cv : 256;
   const int lanes = 256 / cvb;
-  long long gx = ceil_div_ll(P, (long long)lanes * 8);
-  const long long cap = (long long)num_sms() * 4;
-  if (gx > cap) gx = cap;
-  if (gx < 1) gx = 1;
   const size_t smem = (size_t)lanes * cvb * 16 * sizeof(float);
-  bn_stats_kernel<<<dim3((unsigned)gx, ny), 256, smem, (cudaStream_t)stream>>>((const bf16*)x, P, C, ld, sums);
+  bn_stats_kernel<<<dim3((unsigned)rows, ny), 256, smem, (cudaStream_t)stream>>>((const bf16*)x, P, C, ld, partials);
   XMC_LAUNCH_CHECK();
-  return XMC_OK;
+  return launch_sum_partials(partials, rows, 2 * C, sums, 0, (cudaStream_t)stream);
 }
 
 extern "C" int xmc_bn_finalize(const float* sums, long long P, int C, float eps, float momentum, const float* ra_mean,
@@ -586,33 +636,34 @@ extern "C" int xmc_bn_apply(const XmcBnDesc* d, const void* x, const float* mean
 }
 
 extern "C" int xmc_bn_bwd_reduce(const XmcBnDesc* d, const void* dy, const void* x, const float* mean_rstd,
-                                 const void* gb, float* dgb, float* sums, void* stream) {
+                                 const void* gb, float* dgb, float* sums, float* partials, int rows, void* stream) {
   BnP p;
   int r = fill_bnp(d, &p);
   if (r) return r;
-  if (!dy || !x || !mean_rstd || !gb || !dgb || !sums) return XMC_EINVAL;
+  if (!dy || !x || !mean_rstd || !gb || !dgb || !sums || !partials || rows < 1) return XMC_EINVAL;
   const int cv = p.C / 8;
-  const size_t smem = (size_t)cv * 16 * sizeof(float);
-  if (smem > 48 * 1024) return XMC_EINVAL;
-  const long long rows = (long long)p.N * p.Hc * p.Hc;
-  // per-image cells (ConditionalBatchNorm) have few rows and many pixels: split the pixel rows over several threads,
-  // which then accumulate dgamma/dbeta atomically (the caller zero-fills dgb for Hc == 1)
+  const long long cond_rows = (long long)p.N * p.Hc * p.Hc;
+  // per-image cells (ConditionalBatchNorm) have few rows and many pixels: the pixel rows of a cell are split over
+  // psplit threads of the SAME block, whose dgamma/dbeta parts are combined through shared memory in a fixed order
   int psplit = 1;
   if (p.Hc == 1) {
     const int side = 1 << p.s;
     psplit = side < 8 ? side : 8;
+    while (psplit > 1 && cv * psplit > 768) psplit >>= 1;
   }
-  // block = rpi units x cv channel vectors; grid sized by the machine, every thread streams over its units
-  const int rpi = cv >= 256 ? 1 : 256 / cv;
+  // block = rpi units x cv channel vectors (rpi a multiple of psplit); every thread streams over its units
+  int rpi = cv >= 256 ? 1 : 256 / cv;
+  rpi = rpi / psplit * psplit;
+  if (rpi < psplit) rpi = psplit;
   const int threads = cv * rpi;
-  if (threads > 1024) return XMC_EINVAL;
-  long long gx = ceil_div_ll(rows * psplit, rpi);
-  const long long cap = (long long)num_sms() * 8;
-  if (gx > cap) gx = cap;
+  const size_t smem = (size_t)threads * 16 * sizeof(float);
+  if (threads > 1024 || smem > 48 * 1024) return XMC_EINVAL;
+  long long gx = ceil_div_ll(cond_rows * psplit, rpi);
+  if (gx > rows) gx = rows;
   bn_bwd_reduce_kernel<<<(unsigned)gx, threads, smem, (cudaStream_t)stream>>>(
-      p, (const bf16*)dy, (const bf16*)x, mean_rstd, (const bf16*)gb, dgb, sums, rows, psplit, rpi);
+      p, (const bf16*)dy, (const bf16*)x, mean_rstd, (const bf16*)gb, dgb, partials, cond_rows, psplit, rpi);
   XMC_LAUNCH_CHECK();
-  return XMC_OK;
+  return launch_sum_partials(partials, (int)gx, 2 * p.C, sums, 0, (cudaStream_t)stream);
 }
 
 extern "C" int xmc_bn_bwd_apply(const XmcBnDesc* d, const void* dy, const void* x, const float* mean_rstd,
@@ -650,28 +701,31 @@ extern "C" int xmc_unpool2(const void* dout, int N, int Hin, int Win, int C, flo
   return XMC_OK;
 }
 
-extern "C" int xmc_colsum(const void* x, long long P, int C, int ld, float* out, void* stream) {
-  if (!x || !out || P < 1 || C < 1) return XMC_EINVAL;
+extern "C" int xmc_colsum(const void* x, long long P, int C, int ld, float* out, float* partials, int rows,
+                          void* stream) {
+  if (!x || !out || P < 1 || C < 1 || rows < 1 || (rows > 1 && !partials)) return XMC_EINVAL;
+  // one block (per channel group) adds straight into out; several blocks leave partial rows that are added in order
   if (C % 8 || ld % 8) {
     long long gx = ceil_div_ll(P, 256 * 16);
-    if (gx > 512) gx = 512;
+    if (gx > rows) gx = rows;
     if (gx < 1) gx = 1;
-    colsum_scalar_kernel<<<dim3((unsigned)gx, C), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, P, C, ld, out);
+    colsum_scalar_kernel<<<dim3((unsigned)gx, C), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, P, C, ld,
+                                                                                 gx == 1 ? out : partials);
     XMC_LAUNCH_CHECK();
-    return XMC_OK;
+    return gx == 1 ? XMC_OK : launch_sum_partials(partials, (int)gx, C, out, 1, (cudaStream_t)stream);
   }
   const int cv = C / 8;
   const int ny = ceil_div(cv, 256);
   const int cvb = cv < 256 ? cv : 256;
   const int lanes = 256 / cvb;
   long long gx = ceil_div_ll(P, (long long)lanes * 8);
-  const long long cap = (long long)num_sms() * 4;
-  if (gx > cap) gx = cap;
+  if (gx > rows) gx = rows;
   if (gx < 1) gx = 1;
   const size_t smem = (size_t)lanes * cvb * 8 * sizeof(float);
-  colsum_kernel<<<dim3((unsigned)gx, ny), 256, smem, (cudaStream_t)stream>>>((const bf16*)x, P, C, ld, out);
+  colsum_kernel<<<dim3((unsigned)gx, ny), 256, smem, (cudaStream_t)stream>>>((const bf16*)x, P, C, ld,
+                                                                            gx == 1 ? out : partials);
   XMC_LAUNCH_CHECK();
-  return XMC_OK;
+  return gx == 1 ? XMC_OK : launch_sum_partials(partials, (int)gx, C, out, 1, (cudaStream_t)stream);
 }
 
 extern "C" int xmc_relu_sumhw(const void* x, int N, int HW, int C, float* out, void* stream) {

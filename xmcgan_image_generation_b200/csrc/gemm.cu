@@ -8,6 +8,7 @@
 // SAME padding, image borders, ragged M/N/K edges and channel counts that are not a multiple of 64 are all handled
 // by TMA out-of-bounds zero fill; nothing is ever im2col'ed in memory.
 #include <cudaTypedefs.h>
+#include <mutex>
 #include <stdlib.h>
 #include <string.h>
 #include "common.h"
@@ -74,6 +75,13 @@ struct WgradParams {
   long long out_tap_stride, out_batch_stride;
   float alpha;
   int vec_ok;
+  // deterministic accumulation (out_mode 0). ws == nullptr: every output element has exactly one owner item, which
+  // adds its tile with a plain read-modify-write. ws != nullptr (K split across CTAs, or sub-pixel parity taps that
+  // share destinations): every item stores its partial tile into ws[split][batch][source tap][Ca][Cb] and
+  // wgrad_reduce_kernel adds the partials to the destination in a fixed order.
+  float* ws;
+  long long ws_split_stride;  // floats between consecutive K splits
+  int ws_taps;                // source-tap slots per batch entry
 };
 
 __device__ __forceinline__ uint8_t* align_1024(uint8_t* p) {
@@ -832,6 +840,10 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int j2 = 0; j2 < nkw; ++j2) dest[ndest++] = (kh0 + i) * 3 + kw0 + j2;
       }
       const long long obase0 = (long long)bz * p.out_batch_stride + (long long)m * p.ldOut;
+      // partial-tile slot of this item in the workspace (deterministic split-K / shared destinations)
+      float* ws_row = p.ws ? p.ws + (long long)split * p.ws_split_stride +
+                                 (((long long)bz * p.ws_taps + (p.tap3 ? tap * 3 + kw3 : tap)) * p.Ca + m) * p.Cb
+                           : nullptr;
       for (int c0 = 0; c0 < p.BN; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(t_addr + c0, v);
@@ -843,6 +855,14 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           float f[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
+          if (ws_row) {  // Cb % 8 == 0 and a 16-byte aligned workspace: vector stores are always legal here
+            float* o = ws_row + col;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (4 * i < nvalid)
+                reinterpret_cast<float4*>(o)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+            continue;
+          }
           for (int di = 0; di < ndest; ++di) {
             const long long obase = obase0 + (long long)dest[di] * p.out_tap_stride;
             if (p.out_mode == 2) {
@@ -873,16 +893,18 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     if (i < nvalid) o[i] = f[i];
                 }
               } else {
+                // out_mode 0 without a workspace: this item is the only writer of these elements in this launch
                 if (vec) {
 #pragma unroll
-                  for (int i = 0; i < 4; ++i)
-                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4 * i), "f"(f[4 * i]),
-                                 "f"(f[4 * i + 1]), "f"(f[4 * i + 2]), "f"(f[4 * i + 3])
-                                 : "memory");
+                  for (int i = 0; i < 4; ++i) {
+                    float4 t = reinterpret_cast<float4*>(o)[i];
+                    t.x += f[4 * i]; t.y += f[4 * i + 1]; t.z += f[4 * i + 2]; t.w += f[4 * i + 3];
+                    reinterpret_cast<float4*>(o)[i] = t;
+                  }
                 } else {
 #pragma unroll
                   for (int i = 0; i < 16; ++i)
-                    if (i < nvalid) atomicAdd(o + i, f[i]);
+                    if (i < nvalid) o[i] += f[i];
                 }
               }
             }
@@ -905,6 +927,62 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// =====================================================================================================================
+// Second stage of the deterministic weight-gradient accumulation: out[b][t][ca][cb] += sum over the source taps of
+// destination tap t (one, or the four parity taps of sub-pixel mode) and over the K splits, in a FIXED order, of the
+// partial tiles gemm_wgrad_kernel left in the workspace. Replaces the red.global.add epilogue of round 1, whose
+// summation order depended on CTA scheduling (two runs on the same inputs differed in the last bits).
+// =====================================================================================================================
+struct WgradReduceParams {
+  const float* ws;
+  float* out;
+  int ksplit, nbatch, src_taps, dst_taps, Ca, Cb, ldOut, subpixel, vec_ok;
+  long long ws_split_stride, out_tap_stride, out_batch_stride;
+};
+
+__global__ void wgrad_reduce_kernel(const WgradReduceParams p) {
+  const int cb4 = p.Cb >> 2;
+  const long long total = (long long)p.nbatch * p.dst_taps * p.Ca * cb4;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(idx % cb4);
+    long long rem = idx / cb4;
+    const int m = (int)(rem % p.Ca);
+    rem /= p.Ca;
+    const int t = (int)(rem % p.dst_taps);
+    const int bz = (int)(rem / p.dst_taps);
+    int src[4], nsrc = 1;
+    src[0] = t;
+    if (p.subpixel) {
+      // destination (kh, kw) collects the parity taps (a,dh) with kh in S(a,dh): S(0,0)={0}, S(0,1)={1,2},
+      // S(1,0)={0,1}, S(1,1)={2} (see gemm_wgrad_kernel); source tap index = a<<3 | dh<<2 | b<<1 | dw
+      const int kh = t / 3, kw = t - kh * 3;
+      const int ah[2] = {kh == 0 ? 0 : (kh == 1 ? 1 : 1), kh == 0 ? 2 : (kh == 1 ? 2 : 3)};  // (a<<1|dh) pairs
+      const int aw[2] = {kw == 0 ? 0 : (kw == 1 ? 1 : 1), kw == 0 ? 2 : (kw == 1 ? 2 : 3)};
+      nsrc = 0;
+      for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j) src[nsrc++] = (ah[i] << 2) | aw[j];
+    }
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < nsrc; ++i) {
+      const float* w = p.ws + (((long long)bz * p.src_taps + src[i]) * p.Ca + m) * p.Cb + c4 * 4;
+      for (int sp = 0; sp < p.ksplit; ++sp) {
+        const float4 v = *reinterpret_cast<const float4*>(w + (long long)sp * p.ws_split_stride);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    }
+    float* o = p.out + (long long)bz * p.out_batch_stride + (long long)t * p.out_tap_stride + (long long)m * p.ldOut +
+               c4 * 4;
+    if (p.vec_ok) {
+      float4 cur = *reinterpret_cast<float4*>(o);
+      cur.x += acc.x; cur.y += acc.y; cur.z += acc.z; cur.w += acc.w;
+      *reinterpret_cast<float4*>(o) = cur;
+    } else {
+      o[0] += acc.x; o[1] += acc.y; o[2] += acc.z; o[3] += acc.w;
+    }
+  }
 }
 
 // =====================================================================================================================
@@ -980,11 +1058,42 @@ static int pick_bn_fwd(int cout, long long m_tiles, int kiters, int sms) {
   return best;
 }
 
-static bool g_attr_set_fwd = false, g_attr_set_wgrad = false;
-
 }  // namespace xmc
 
 using namespace xmc;
+
+// The opt-in for more than 48 KB of dynamic shared memory is a per-DEVICE function attribute: one process may drive
+// several GPUs (the reference's pmap mode; an XLA custom call), so the "already set" flags are kept per device and
+// guarded by a mutex (launches from several host threads).
+enum { kAttrFwd = 0, kAttrRes = 1, kAttrWgrad = 2, kAttrKinds = 3 };
+static cudaError_t ensure_smem_attr(int kind) {
+  constexpr int kMaxDev = 64;
+  static std::mutex mu;
+  static bool done[kMaxDev][kAttrKinds] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const bool cached = dev >= 0 && dev < kMaxDev;
+  std::lock_guard<std::mutex> lock(mu);
+  if (cached && done[dev][kind]) return cudaSuccess;
+  switch (kind) {
+    case kAttrFwd:
+      e = cudaFuncSetAttribute(gemm_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFwd);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(gemm_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFwd);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(gemm_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFwd);
+      break;
+    case kAttrRes:
+      e = cudaFuncSetAttribute(conv3x3_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemRes);
+      break;
+    default:
+      e = cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+      break;
+  }
+  if (e == cudaSuccess && cached) done[dev][kind] = true;
+  return e;
+}
 
 extern "C" int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* wk, const float* bias,
                               const void* residual, const void* mask, void* y, void* stream) {
@@ -1037,11 +1146,8 @@ extern "C" int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* w
   p.bias_smem = (bias && d->Cout <= kBiasMax && aligned16(bias)) ? 1 : 0;
 
   // ---- resident-weights path for the wide 3x3 layers (see conv3x3_resident_kernel) ------------------------------------
-  static int resident_mode = -1;  // XMC_RESIDENT=0 switches the path off (debugging aid)
-  if (resident_mode < 0) {
-    const char* e = getenv("XMC_RESIDENT");
-    resident_mode = e ? atoi(e) : 1;
-  }
+  // XMC_RESIDENT=0 switches the path off (debugging aid; process-global, read once)
+  static const int resident_mode = [] { const char* e = getenv("XMC_RESIDENT"); return e ? atoi(e) : 1; }();
   const int bn_res = ceil_div(d->Cout, 16) * 16;
   const bool res_ok = resident_mode > 0 && d->KH == 3 && d->KW == 3 && d->pad_h == 1 && d->pad_w == 1 &&
                       p.strideH == 1 && p.strideW == 1 && !d->batched && !d->subpixel && d->pitchW <= 0 &&
@@ -1071,12 +1177,7 @@ extern "C" int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* w
       r = make_tmap(&tmB2, wk, 3, dims, str, box2, nullptr, CU_TENSOR_MAP_SWIZZLE_64B);
       if (r) return r;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-      XMC_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          kSmemRes));
-      attr_set = true;
-    }
+    XMC_CUDA_CHECK(ensure_smem_attr(kAttrRes));
     const int total = p.tiles_w * (d->H / 2) * d->N;
     const int grid = total < num_sms() ? total : num_sms();
     conv3x3_resident_kernel<<<grid, kThreadsFwd, kSmemRes, (cudaStream_t)stream>>>(tmA, tmB, tmB2, p);
@@ -1109,19 +1210,11 @@ extern "C" int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* w
     int r = make_tmap(&tmB, wk, 3, dims, str, box);
     if (r) return r;
   }
-  if (!g_attr_set_fwd) {
-    XMC_CUDA_CHECK(cudaFuncSetAttribute(gemm_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFwd));
-    XMC_CUDA_CHECK(cudaFuncSetAttribute(gemm_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFwd));
-    XMC_CUDA_CHECK(cudaFuncSetAttribute(gemm_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFwd));
-    g_attr_set_fwd = true;
-  }
+  XMC_CUDA_CHECK(ensure_smem_attr(kAttrFwd));
   const int total = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles * p.parities;
   const int grid = total < num_sms() ? total : num_sms();
-  static int lean_mode = -1;  // XMC_LEAN_EPI=0 forces the generic epilogue (debugging aid)
-  if (lean_mode < 0) {
-    const char* e = getenv("XMC_LEAN_EPI");
-    lean_mode = e ? atoi(e) : 1;
-  }
+  // XMC_LEAN_EPI=0 forces the generic epilogue (debugging aid; process-global, read once)
+  static const int lean_mode = [] { const char* e = getenv("XMC_LEAN_EPI"); return e ? atoi(e) : 1; }();
   auto al32p = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
   const bool lean = lean_mode && p.bias_smem && !mask && d->alpha == 1.f && d->out_dtype == 0 && p.vec_ok == 2 &&
                     (d->Cout % 16) == 0 && (!residual || al32p(residual));
@@ -1135,14 +1228,13 @@ extern "C" int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* w
   return XMC_OK;
 }
 
-extern "C" int xmc_conv2d_wgrad(const XmcWgradDesc* d, const void* xa, const void* xb, void* dw, void* stream) {
-  if (!d || !xa || !xb || !dw) return XMC_EINVAL;
+// Validates the descriptor and fills the launch plan (tiling, K split, work items). Shared by the workspace query and
+// the launch so that both always agree.
+static int plan_wgrad(const XmcWgradDesc* d, WgradParams& p) {
+  if (!d) return XMC_EINVAL;
   if (d->N < 1 || d->H < 1 || d->W < 1 || d->Ca < 1 || d->Cb < 1 || d->KH < 1 || d->KW < 1) return XMC_EINVAL;
   if ((d->ldA % 8) || (d->ldB % 8) || (d->pitchWA <= 0 && d->ldA < d->Ca) || d->ldB < d->Cb) return XMC_EINVAL;
   if ((d->Ca % 8) || (d->Cb % 8)) return XMC_EINVAL;
-  if (!aligned16(xa) || !aligned16(xb)) return XMC_EALIGN;
-
-  WgradParams p;
   memset(&p, 0, sizeof(p));
   p.tw = d->W < 64 ? d->W : 64;
   p.th = 64 / p.tw; if (p.th > d->H) p.th = d->H;
@@ -1158,12 +1250,9 @@ extern "C" int xmc_conv2d_wgrad(const XmcWgradDesc* d, const void* xa, const voi
   if (d->subpixel && (d->KH != 3 || d->KW != 3 || d->out_mode != 0 || d->batched)) return XMC_EINVAL;
   // tap3: for 3x3 kernels on rows of >= 64 pixels whose three kw accumulators fit TMEM (Cb <= 160), a work item is a
   // filter ROW: one 66-pixel halo chunk of xa and one chunk of xb feed three taps (3x less operand traffic; these
-  // narrow-channel layers are L2 -> SM bandwidth bound). XMC_WGRAD_TAP3=0 switches it off (debugging aid).
-  static int tap3_mode = -1;
-  if (tap3_mode < 0) {
-    const char* e = getenv("XMC_WGRAD_TAP3");
-    tap3_mode = e ? atoi(e) : 1;
-  }
+  // narrow-channel layers are L2 -> SM bandwidth bound). XMC_WGRAD_TAP3=0 switches it off (debugging aid, read once per
+  // process).
+  static const int tap3_mode = [] { const char* e = getenv("XMC_WGRAD_TAP3"); return e ? atoi(e) : 1; }();
   p.tap3 = (tap3_mode && d->KH == 3 && d->KW == 3 && d->pad_h == 1 && d->pad_w == 1 && !d->subpixel && !d->batched &&
             d->pitchWA <= 0 && d->out_mode == 0 && d->W >= 64 && p.n_tiles == 1 && 3 * (((p.BN + 31) / 32) * 32) <= 512)
                ? 1 : 0;
@@ -1174,7 +1263,7 @@ extern "C" int xmc_conv2d_wgrad(const XmcWgradDesc* d, const void* xa, const voi
   int ksplit = 1;
   if (d->out_mode == 0) {
     // Split K (pixels) across CTAs so that the grid fills whole waves of SMs: pick the split with the best
-    // last-wave utilisation (ties -> fewer splits = fewer atomics), keeping >= 8 chunks (512 pixels) per CTA.
+    // last-wave utilisation (ties -> fewer splits = smaller workspace), keeping >= 8 chunks (512 pixels) per CTA.
     const int sms = num_sms();
     const int max_split = p.total_chunks / 8 > 0 ? p.total_chunks / 8 : 1;
     double best_score = -1.0;
@@ -1198,12 +1287,50 @@ extern "C" int xmc_conv2d_wgrad(const XmcWgradDesc* d, const void* xa, const voi
   p.Ca = d->Ca; p.Cb = d->Cb; p.batched = d->batched;
   p.slab_bytes = (uint32_t)(64 * p.tw * p.th * p.tn * 2);
   p.idesc = make_idesc_bf16(128, p.BN, 1, 1);
-  p.out = dw; p.out_mode = d->out_mode; p.ldOut = d->ldOut;
+  p.out_mode = d->out_mode; p.ldOut = d->ldOut;
   p.out_tap_stride = d->out_tap_stride; p.out_batch_stride = d->out_batch_stride;
   p.alpha = d->alpha;
+  // source-tap slots of the workspace: tap3 items carry three kw accumulators each
+  p.ws_taps = d->subpixel ? 16 : d->KH * d->KW;
+  p.ws_split_stride = (long long)nbatch * p.ws_taps * d->Ca * d->Cb;
+  return XMC_OK;
+}
+
+// A workspace is needed whenever an output element has more than one producer item: K split across CTAs, or the
+// sub-pixel parity taps (each destination tap sums four of them).
+static bool wgrad_needs_ws(const XmcWgradDesc* d, const WgradParams& p) {
+  return d->out_mode == 0 && (p.ksplit > 1 || d->subpixel);
+}
+
+extern "C" int xmc_conv2d_wgrad_workspace_bytes(const XmcWgradDesc* d, long long* bytes) {
+  if (!bytes) return XMC_EINVAL;
+  WgradParams p;
+  const int r = plan_wgrad(d, p);
+  if (r) return r;
+  *bytes = wgrad_needs_ws(d, p) ? (long long)p.ksplit * p.ws_split_stride * (long long)sizeof(float) : 0;
+  return XMC_OK;
+}
+
+extern "C" int xmc_conv2d_wgrad(const XmcWgradDesc* d, const void* xa, const void* xb, void* dw, void* workspace,
+                                long long workspace_bytes, void* stream) {
+  if (!d || !xa || !xb || !dw) return XMC_EINVAL;
+  WgradParams p;
+  {
+    const int r = plan_wgrad(d, p);
+    if (r) return r;
+  }
+  if (!aligned16(xa) || !aligned16(xb)) return XMC_EALIGN;
+  p.out = dw;
   const int unit = d->out_mode == 2 ? 8 : 4;
   p.vec_ok = (aligned16(dw) && d->ldOut % unit == 0 && d->out_tap_stride % unit == 0 &&
               d->out_batch_stride % unit == 0) ? 1 : 0;
+  const bool use_ws = wgrad_needs_ws(d, p);
+  if (use_ws) {
+    const long long need = (long long)p.ksplit * p.ws_split_stride * (long long)sizeof(float);
+    if (!workspace || workspace_bytes < need) return XMC_EINVAL;
+    if (!aligned16(workspace)) return XMC_EALIGN;
+    p.ws = reinterpret_cast<float*>(workspace);
+  }
 
   CUtensorMap tmA, tmB;
   if (d->pitchWA > 0) {
@@ -1234,12 +1361,24 @@ extern "C" int xmc_conv2d_wgrad(const XmcWgradDesc* d, const void* xa, const voi
     int r = make_tmap(&tmB, xb, 4, dims, str, box, est);
     if (r) return r;
   }
-  if (!g_attr_set_wgrad) {
-    XMC_CUDA_CHECK(cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    g_attr_set_wgrad = true;
-  }
+  XMC_CUDA_CHECK(ensure_smem_attr(kAttrWgrad));
   const int grid = p.total_items < num_sms() ? p.total_items : num_sms();
   gemm_wgrad_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(tmA, tmB, p);
   XMC_LAUNCH_CHECK();
+  if (use_ws) {
+    WgradReduceParams r;
+    r.ws = p.ws; r.out = reinterpret_cast<float*>(dw);
+    r.ksplit = p.ksplit; r.nbatch = d->batched ? d->N : 1; r.src_taps = p.ws_taps;
+    r.dst_taps = d->KH * d->KW; r.Ca = d->Ca; r.Cb = d->Cb; r.ldOut = d->ldOut; r.subpixel = p.subpixel;
+    r.vec_ok = p.vec_ok;
+    r.ws_split_stride = p.ws_split_stride; r.out_tap_stride = d->out_tap_stride;
+    r.out_batch_stride = d->out_batch_stride;
+    const long long total = (long long)r.nbatch * r.dst_taps * r.Ca * (r.Cb / 4);
+    long long blocks = ceil_div_ll(total, 256);
+    const long long cap = (long long)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    wgrad_reduce_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(r);
+    XMC_LAUNCH_CHECK();
+  }
   return XMC_OK;
 }

@@ -1,4 +1,5 @@
 // Library-level plumbing of libxmc.so: error strings, device queries.
+#include <atomic>
 #include <stdio.h>
 #include <string.h>
 #include "common.h"
@@ -12,16 +13,21 @@ void set_cuda_error(cudaError_t e) {
   (void)cudaGetLastError();  // clear the sticky-less error state
 }
 
+// SM count of the CURRENT device (cached per device: one process may drive several GPUs).
 int num_sms() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    int v = 0;
-    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
-    sms = v;
+  constexpr int kMaxDev = 64;
+  static std::atomic<int> sms[kMaxDev];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  const bool cached = dev >= 0 && dev < kMaxDev;
+  if (cached) {
+    const int v = sms[dev].load(std::memory_order_relaxed);
+    if (v > 0) return v;
   }
-  return sms;
+  int v = 0;
+  if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
+  if (cached) sms[dev].store(v, std::memory_order_relaxed);
+  return v;
 }
 
 }  // namespace xmc

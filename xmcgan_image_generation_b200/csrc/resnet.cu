@@ -68,32 +68,61 @@ __global__ void resize_bilinear_pad_kernel(const float* __restrict__ img, int N,
   }
 }
 
-// transpose of the resize: dimg[n, src] += w * dout[n, dst]
+// transpose of the resize as a GATHER (one thread per source pixel, fixed summation order -> deterministic; round 1
+// scattered with atomics): dimg[n, sy, sx] += sum over the destination pixels (oy, ox) whose taps cover (sy, sx) of
+// wy * wx * dout[n, oy, ox]. Per axis the candidates are the outputs whose centre lies within ks (+ a safety margin
+// of one output) of the source index; each candidate's exact normalised weight comes from resize_taps.
+constexpr int kMaxCand = 10;
+__device__ __forceinline__ int resize_candidates(int s, int S, int T, float inv_scale, float ks, float* w) {
+  int lo_o = (int)floorf((s - ks + 0.5f) / inv_scale - 0.5f) - 1;
+  int hi_o = (int)ceilf((s + ks + 0.5f) / inv_scale - 0.5f) + 1;
+  lo_o = max(lo_o, 0);
+  hi_o = min(hi_o, T - 1);
+  if (hi_o - lo_o + 1 > kMaxCand) hi_o = lo_o + kMaxCand - 1;
+#pragma unroll
+  for (int k = 0; k < kMaxCand; ++k) {
+    float wv = 0.f;
+    const int o = lo_o + k;
+    if (o <= hi_o) {
+      float t[kMaxTaps];
+      const int lo = resize_taps(o, S, inv_scale, ks, t);
+      const int d = s - lo;
+#pragma unroll
+      for (int j = 0; j < kMaxTaps; ++j)
+        if (j == d) wv = t[j];
+    }
+    w[k] = wv;
+  }
+  return lo_o;
+}
+
 __global__ void resize_bilinear_bwd_kernel(const float* __restrict__ dout, int N, int S, int T,
                                            float* __restrict__ dimg) {
-  const long long total = (long long)N * T * T;
+  const long long total = (long long)N * S * S;
   const float inv_scale = (float)S / (float)T;
   const float ks = fmaxf(inv_scale, 1.f);
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    const int x = idx % T, y = (idx / T) % T;
-    const long long n = idx / ((long long)T * T);
-    float wx[kMaxTaps], wy[kMaxTaps];
-    const int x0 = resize_taps(x, S, inv_scale, ks, wx);
-    const int y0 = resize_taps(y, S, inv_scale, ks, wy);
-    float* b = dimg + n * S * S * 3;
-    const float g0 = dout[idx * 3], g1 = dout[idx * 3 + 1], g2 = dout[idx * 3 + 2];
+    const int sx = idx % S, sy = (idx / S) % S;
+    const long long n = idx / ((long long)S * S);
+    float wx[kMaxCand], wy[kMaxCand];
+    const int ox0 = resize_candidates(sx, S, T, inv_scale, ks, wx);
+    const int oy0 = resize_candidates(sy, S, T, inv_scale, ks, wy);
+    const float* b = dout + n * T * T * 3;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 #pragma unroll
-    for (int ty = 0; ty < kMaxTaps; ++ty) {
+    for (int ty = 0; ty < kMaxCand; ++ty) {
       if (wy[ty] == 0.f) continue;
 #pragma unroll
-      for (int tx = 0; tx < kMaxTaps; ++tx) {
+      for (int tx = 0; tx < kMaxCand; ++tx) {
         if (wx[tx] == 0.f) continue;
         const float wgt = wy[ty] * wx[tx];
-        float* px = b + ((long long)(y0 + ty) * S + x0 + tx) * 3;
-        atomicAdd(px, wgt * g0); atomicAdd(px + 1, wgt * g1); atomicAdd(px + 2, wgt * g2);
+        const float* px = b + ((long long)(oy0 + ty) * T + ox0 + tx) * 3;
+        a0 += wgt * px[0]; a1 += wgt * px[1]; a2 += wgt * px[2];
       }
     }
+    float* o = dimg + idx * 3;
+    o[0] += a0; o[1] += a1; o[2] += a2;
   }
 }
 
@@ -281,8 +310,9 @@ extern "C" int xmc_resize_bilinear_pad(const float* img, int N, int S, int T, in
 }
 
 extern "C" int xmc_resize_bilinear_bwd(const float* dout, int N, int S, int T, float* dimg, void* stream) {
-  if (!dout || !dimg || N < 1 || S < 1 || T < 1 || 2 * S > 3 * T) return XMC_EINVAL;
-  resize_bilinear_bwd_kernel<<<grid1((long long)N * T * T, 256), 256, 0, (cudaStream_t)stream>>>(dout, N, S, T, dimg);
+  // 2S <= 3T bounds the taps per output (kMaxTaps), T <= 3S the outputs per source pixel (kMaxCand)
+  if (!dout || !dimg || N < 1 || S < 1 || T < 1 || 2 * S > 3 * T || T > 3 * S) return XMC_EINVAL;
+  resize_bilinear_bwd_kernel<<<grid1((long long)N * S * S, 256), 256, 0, (cudaStream_t)stream>>>(dout, N, S, T, dimg);
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }

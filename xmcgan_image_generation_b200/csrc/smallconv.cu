@@ -174,7 +174,7 @@ conv_c3_out_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, int l
 // per pixel feed 54 FMAs).
 template <int KS>
 __global__ void wgrad_c3_kernel(const bf16* __restrict__ x3, const bf16* __restrict__ y, int N, int H, int W, int C,
-                                int flip, long long s_tap, int s_c3, int s_c, float* __restrict__ out) {
+                                float* __restrict__ partials) {
   extern __shared__ float xs[];  // [(rows+2ph)][64+2pw][3]
   constexpr int KH = KS, KW = KS;
   constexpr int ph = KH / 2, pw = KW / 2;
@@ -258,15 +258,26 @@ __global__ void wgrad_c3_kernel(const bf16* __restrict__ x3, const bf16* __restr
       }
     }
   }
+  // block partial [tap*3 + c3][C] (plain stores); wgrad_c3_finish_kernel adds the blocks in index order
+  float* part = partials + (long long)blockIdx.x * taps * 3 * C;
 #pragma unroll
-  for (int tap = 0; tap < taps; ++tap) {
-    const int tap_o = flip ? taps - 1 - tap : tap;
-#pragma unroll
-    for (int c3 = 0; c3 < 3; ++c3) {
-      atomicAdd(out + tap_o * s_tap + c3 * s_c3 + (long long)c * s_c, acc[0][tap * 3 + c3]);
-      if (c + 1 < C) atomicAdd(out + tap_o * s_tap + c3 * s_c3 + (long long)(c + 1) * s_c, acc[1][tap * 3 + c3]);
-    }
+  for (int i = 0; i < taps * 3; ++i) {
+    part[(long long)i * C + c] = acc[0][i];
+    if (c + 1 < C) part[(long long)i * C + c + 1] = acc[1][i];
   }
+}
+
+// out[tap_o*s_tap + c3*s_c3 + c*s_c] += sum_blocks partials[block][tap*3 + c3][c], blocks added in index order
+__global__ void wgrad_c3_finish_kernel(const float* __restrict__ partials, int blocks, int taps, int C, int flip,
+                                       long long s_tap, int s_c3, int s_c, float* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int width = taps * 3 * C;
+  if (idx >= width) return;
+  float a = 0.f;
+  for (int b = 0; b < blocks; ++b) a += partials[(long long)b * width + idx];
+  const int c = idx % C, i = idx / C, c3 = i % 3, tap = i / 3;
+  const int tap_o = flip ? taps - 1 - tap : tap;
+  out[tap_o * s_tap + c3 * s_c3 + (long long)c * s_c] += a;
 }
 
 // scalar-channel 2x2 mean pool of a bf16 [N,2H,2W,C] tensor (the 3-channel image, common.py:131)
@@ -420,8 +431,8 @@ extern "C" int xmc_conv_c3_out(const void* x, const void* w, int ldw, const floa
 }
 
 extern "C" int xmc_wgrad_c3(const void* x3, const void* y, int N, int H, int W, int C, int KH, int KW, int flip,
-                            long long s_tap, int s_c3, int s_c, float* out, void* stream) {
-  if (!x3 || !y || !out || C < 2 || (C % 2) || C > 2048 || KH * KW > 9) return XMC_EINVAL;
+                            long long s_tap, int s_c3, int s_c, float* out, float* partials, void* stream) {
+  if (!x3 || !y || !out || !partials || C < 2 || (C % 2) || C > 2048 || KH * KW > 9) return XMC_EINVAL;
   const int ph = KH / 2, pw = KW / 2;
   const size_t smem = (size_t)(8 + 2 * ph) * (64 + 2 * pw) * kImgC * sizeof(float);
   const int blocks = N * ceil_div(H, 8) * ceil_div(W, 64);
@@ -429,10 +440,14 @@ extern "C" int xmc_wgrad_c3(const void* x3, const void* y, int N, int H, int W, 
   if (KH != KW || (KH != 1 && KH != 3)) return XMC_EINVAL;
   if (KH == 3)
     wgrad_c3_kernel<3><<<blocks, threads, smem, (cudaStream_t)stream>>>((const bf16*)x3, (const bf16*)y, N, H, W, C,
-                                                                       flip, s_tap, s_c3, s_c, out);
+                                                                       partials);
   else
     wgrad_c3_kernel<1><<<blocks, threads, smem, (cudaStream_t)stream>>>((const bf16*)x3, (const bf16*)y, N, H, W, C,
-                                                                       flip, s_tap, s_c3, s_c, out);
+                                                                       partials);
+  XMC_LAUNCH_CHECK();
+  const int width = KH * KW * 3 * C;
+  wgrad_c3_finish_kernel<<<ceil_div(width, 128), 128, 0, (cudaStream_t)stream>>>(partials, blocks, KH * KW, C, flip,
+                                                                                s_tap, s_c3, s_c, out);
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }

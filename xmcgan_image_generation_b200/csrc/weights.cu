@@ -20,9 +20,10 @@ __device__ __forceinline__ int find_entry(const E* tab, int n, int block, int E:
 }
 
 // ------------------------------------------------------------------------------------------------- spectral norm
-// scalars layout (SoA, n = number of SN layers): [0,n) sum_t2 | [n,2n) norm_t | [2n,3n) inv_sigma | [3n,4n) dot
+// scalars layout (SoA, n = number of SN layers): [0,n) unused | [n,2n) norm_t | [2n,3n) inv_sigma | [3n,4n) dot
+// All reductions are two-stage with a fixed summation order (no atomics): bit-identical from run to run.
 __global__ void sn_rowdot_kernel(const XmcSnEntry* __restrict__ tab, int n, const float* __restrict__ params,
-                                 const float* __restrict__ u0, float* __restrict__ t_ws, float* __restrict__ scalars) {
+                                 const float* __restrict__ u0, float* __restrict__ t_ws) {
   const int e = find_entry(tab, n, (int)blockIdx.x, &XmcSnEntry::row_block_begin);
   const XmcSnEntry en = tab[e];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -34,14 +35,6 @@ __global__ void sn_rowdot_kernel(const XmcSnEntry* __restrict__ tab, int n, cons
     for (int c = lane; c < en.cols; c += 32) t += w[c] * u[c];
     t = warp_sum(t);
     if (lane == 0) t_ws[en.t_off + k] = t;
-  }
-  __shared__ float sm[8];
-  if (lane == 0) sm[warp] = (k < en.rows) ? t * t : 0.f;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float a = 0.f;
-    for (int i = 0; i < 8; ++i) a += sm[i];
-    atomicAdd(scalars + e, a);
   }
 }
 
@@ -67,25 +60,37 @@ __global__ void sn_colsum_kernel(const XmcSnEntry* __restrict__ tab, int n, cons
     float a = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) a += sm[i][threadIdx.x];
-    atomicAdd(s_ws + en.s_off + c, a);
+    s_ws[en.s_off + (long long)rt * en.cols + c] = a;  // partial of row tile rt; sn_finalize adds the tiles in order
   }
 }
 
-__global__ void sn_finalize_kernel(const XmcSnEntry* __restrict__ tab, int n, float eps, const float* __restrict__ s_ws,
-                                   float* __restrict__ u_new, float* __restrict__ scalars) {
+__global__ void sn_finalize_kernel(const XmcSnEntry* __restrict__ tab, int n, float eps, const float* __restrict__ t_ws,
+                                   const float* __restrict__ s_ws, float* __restrict__ u_new,
+                                   float* __restrict__ scalars) {
   __shared__ float sm[32];
   const int e = blockIdx.x;
   const XmcSnEntry en = tab[e];
-  const float norm_t = rsqrtf(scalars[e] + eps);  // v0 = t * norm_t   (layers.py:213 / :96)
+  float tt = 0.f;
+  for (int k = threadIdx.x; k < en.rows; k += blockDim.x) {
+    const float t = t_ws[en.t_off + k];
+    tt += t * t;
+  }
+  tt = block_sum(tt, sm);
+  const float norm_t = rsqrtf(tt + eps);  // v0 = t * norm_t   (layers.py:213 / :96)
+  const int rtiles = (en.rows + 255) / 256;
+  auto col = [&](int c) {                 // (t W)[c]: the row-tile partials of sn_colsum_kernel, added in tile order
+    float a = 0.f;
+    for (int rt = 0; rt < rtiles; ++rt) a += s_ws[en.s_off + (long long)rt * en.cols + c];
+    return a;
+  };
   float ss = 0.f;
   for (int c = threadIdx.x; c < en.cols; c += blockDim.x) {
-    const float s = s_ws[en.s_off + c] * norm_t;  // (v0 W)[c]
-    ss += s * s;
+    const float s_ = col(c) * norm_t;  // (v0 W)[c]
+    ss += s_ * s_;
   }
   ss = block_sum(ss, sm);
   const float norm_s = rsqrtf(ss + eps);          // u1 = (v0 W) * norm_s  (layers.py:214 / :97)
-  for (int c = threadIdx.x; c < en.cols; c += blockDim.x)
-    u_new[en.u_off + c] = s_ws[en.s_off + c] * norm_t * norm_s;
+  for (int c = threadIdx.x; c < en.cols; c += blockDim.x) u_new[en.u_off + c] = col(c) * norm_t * norm_s;
   if (threadIdx.x == 0) {
     const float sigma = ss * norm_s;              // v0 W u1^T
     scalars[n + e] = norm_t;
@@ -95,7 +100,7 @@ __global__ void sn_finalize_kernel(const XmcSnEntry* __restrict__ tab, int n, fl
 
 // dot[e] = <dWtilde, W>
 __global__ void sn_bwd_dot_kernel(const XmcSnEntry* __restrict__ tab, int n, const float* __restrict__ params,
-                                  const float* __restrict__ grads, float* __restrict__ scalars) {
+                                  const float* __restrict__ grads, float* __restrict__ dot_partials) {
   __shared__ float sm[32];
   const int e = find_entry(tab, n, (int)blockIdx.x, &XmcSnEntry::elem_block_begin);
   const XmcSnEntry en = tab[e];
@@ -108,7 +113,20 @@ __global__ void sn_bwd_dot_kernel(const XmcSnEntry* __restrict__ tab, int n, con
     if (idx < total) a += grads[en.w_off + idx] * params[en.w_off + idx];
   }
   a = block_sum(a, sm);
-  if (threadIdx.x == 0) atomicAdd(scalars + 3 * n + e, a);
+  if (threadIdx.x == 0) dot_partials[blockIdx.x] = a;
+}
+
+// scalars[3n + e] = sum of entry e's block partials (fixed order: thread-strided, then the block tree)
+__global__ void sn_bwd_dot_finish_kernel(const XmcSnEntry* __restrict__ tab, int n, int total_elem_blocks,
+                                         const float* __restrict__ dot_partials, float* __restrict__ scalars) {
+  __shared__ float sm[32];
+  const int e = blockIdx.x;
+  const int b0 = tab[e].elem_block_begin;
+  const int b1 = (e + 1 < n) ? tab[e + 1].elem_block_begin : total_elem_blocks;
+  float a = 0.f;
+  for (int b = b0 + threadIdx.x; b < b1; b += blockDim.x) a += dot_partials[b];
+  a = block_sum(a, sm);
+  if (threadIdx.x == 0) scalars[3 * n + e] = a;
 }
 
 // dW = dWtilde/sigma' - <dWtilde,W>/sigma'^2 * v0^T u1     (sigma' = sigma + eps; u1, v0 are stop-gradient)
@@ -240,14 +258,23 @@ subpixel_prep_kernel(const float* __restrict__ w, const float* __restrict__ scal
 }
 
 // ------------------------------------------------------------------------------------------------- Adam (+EMA)
+// Scalars of one Adam step, formed in double on the host (or from the device step count) and rounded to fp32 once:
+// flax.optim.Adam multiplies fp32 arrays by the Python doubles (1 - beta), 1 / (1 - beta^t).
+struct AdamScalars {
+  float lr, b1, b2, omb1, omb2, eps, c1, c2, gscale, decay, omdecay;
+  double b1d, b2d;
+};
+
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                            float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float inv_c1,
-                            float inv_c2, float gscale, float* __restrict__ ema, float decay,
+                            float* __restrict__ v, long long n, const AdamScalars sc, float* __restrict__ ema,
                             const int* __restrict__ step_dev) {
+  const float lr = sc.lr, b1 = sc.b1, b2 = sc.b2, omb1 = sc.omb1, omb2 = sc.omb2, eps = sc.eps, gscale = sc.gscale;
+  const float decay = sc.decay, omdecay = sc.omdecay;
+  float c1 = sc.c1, c2 = sc.c2;  // bias corrections 1 - beta^t
   if (step_dev) {  // step count t kept on the device (CUDA-graph replays cannot take new host scalars)
-    const float t = (float)(*step_dev + 1);
-    inv_c1 = 1.f / (1.f - powf(b1, t));
-    inv_c2 = 1.f / (1.f - powf(b2, t));
+    const double t = (double)(*step_dev + 1);
+    c1 = (float)(1.0 - pow(sc.b1d, t));
+    c2 = (float)(1.0 - pow(sc.b2d, t));
   }
   const long long n4 = n >> 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
@@ -260,19 +287,19 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float gk = ga[k] * gscale;
-      ma[k] = b1 * ma[k] + (1.f - b1) * gk;
-      va[k] = b2 * va[k] + (1.f - b2) * gk * gk;
-      pa[k] = pa[k] - lr * (ma[k] * inv_c1) / (sqrtf(va[k] * inv_c2) + eps);
+      ma[k] = b1 * ma[k] + omb1 * gk;
+      va[k] = b2 * va[k] + omb2 * gk * gk;
+      pa[k] = pa[k] - lr * (ma[k] / c1) / (sqrtf(va[k] / c2) + eps);  // the operation order of flax.optim.Adam
     }
     reinterpret_cast<float4*>(p)[i] = pp;
     reinterpret_cast<float4*>(m)[i] = mm;
     reinterpret_cast<float4*>(v)[i] = vv;
     if (ema) {
       float4 ee = reinterpret_cast<float4*>(ema)[i];
-      ee.x = ee.x * decay + (1.f - decay) * pp.x;
-      ee.y = ee.y * decay + (1.f - decay) * pp.y;
-      ee.z = ee.z * decay + (1.f - decay) * pp.z;
-      ee.w = ee.w * decay + (1.f - decay) * pp.w;
+      ee.x = ee.x * decay + omdecay * pp.x;
+      ee.y = ee.y * decay + omdecay * pp.y;
+      ee.z = ee.z * decay + omdecay * pp.z;
+      ee.w = ee.w * decay + omdecay * pp.w;
       reinterpret_cast<float4*>(ema)[i] = ee;
     }
   }
@@ -287,24 +314,24 @@ extern "C" int xmc_sn_forward(const XmcSnEntry* table_dev, int n, float eps, con
                               int total_row_blocks, int total_col_tiles, void* stream) {
   if (!table_dev || n < 1 || !params || !u0 || !u0_new || !t_ws || !s_ws || !scalars) return XMC_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
-  XMC_CUDA_CHECK(cudaMemsetAsync(scalars, 0, sizeof(float) * 4 * n, st));
-  XMC_CUDA_CHECK(cudaMemsetAsync(s_ws, 0, sizeof(float) * s_ws_floats, st));
-  sn_rowdot_kernel<<<total_row_blocks, 256, 0, st>>>(table_dev, n, params, u0, t_ws, scalars);
+  (void)s_ws_floats;
+  sn_rowdot_kernel<<<total_row_blocks, 256, 0, st>>>(table_dev, n, params, u0, t_ws);
   XMC_LAUNCH_CHECK();
   sn_colsum_kernel<<<total_col_tiles, dim3(32, 8), 0, st>>>(table_dev, n, params, t_ws, s_ws);
   XMC_LAUNCH_CHECK();
-  sn_finalize_kernel<<<n, 256, 0, st>>>(table_dev, n, eps, s_ws, u0_new, scalars);
+  sn_finalize_kernel<<<n, 256, 0, st>>>(table_dev, n, eps, t_ws, s_ws, u0_new, scalars);
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }
 
 extern "C" int xmc_sn_backward(const XmcSnEntry* table_dev, int n, const float* params, float* grads,
-                               const float* t_ws, const float* u0_new, float* scalars, int total_elem_blocks,
-                               void* stream) {
-  if (!table_dev || n < 1 || !params || !grads || !t_ws || !u0_new || !scalars) return XMC_EINVAL;
+                               const float* t_ws, const float* u0_new, float* scalars, float* dot_partials,
+                               int total_elem_blocks, void* stream) {
+  if (!table_dev || n < 1 || !params || !grads || !t_ws || !u0_new || !scalars || !dot_partials) return XMC_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
-  XMC_CUDA_CHECK(cudaMemsetAsync(scalars + 3 * n, 0, sizeof(float) * n, st));
-  sn_bwd_dot_kernel<<<total_elem_blocks, 256, 0, st>>>(table_dev, n, params, grads, scalars);
+  sn_bwd_dot_kernel<<<total_elem_blocks, 256, 0, st>>>(table_dev, n, params, grads, dot_partials);
+  XMC_LAUNCH_CHECK();
+  sn_bwd_dot_finish_kernel<<<n, 256, 0, st>>>(table_dev, n, total_elem_blocks, dot_partials, scalars);
   XMC_LAUNCH_CHECK();
   sn_bwd_apply_kernel<<<total_elem_blocks, 256, 0, st>>>(table_dev, n, grads, t_ws, u0_new, scalars);
   XMC_LAUNCH_CHECK();
@@ -332,17 +359,22 @@ extern "C" int xmc_subpixel_prep(const float* w, const float* scale, int Cin, in
 
 __global__ void inc_i32_kernel(int* x) { *x += 1; }
 
-extern "C" int xmc_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
-                        float eps, float bias_corr1, float bias_corr2, float grad_scale, float* ema, float ema_decay,
-                        int* step_dev, void* stream) {
+extern "C" int xmc_adam(float* p, const float* g, float* m, float* v, long long n, double lr, double beta1,
+                        double beta2, double eps, double bias_corr1, double bias_corr2, double grad_scale, float* ema,
+                        double ema_decay, int* step_dev, void* stream) {
   if (!p || !g || !m || !v || n < 4 || (n & 3)) return XMC_EINVAL;
   if (!aligned16(p) || !aligned16(g) || !aligned16(m) || !aligned16(v) || (ema && !aligned16(ema))) return XMC_EALIGN;
   long long blocks = ceil_div_ll(n / 4, 256);
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps,
-                                                                  1.f / bias_corr1, 1.f / bias_corr2, grad_scale, ema,
-                                                                  ema_decay, step_dev);
+  AdamScalars sc;
+  sc.lr = (float)lr; sc.b1 = (float)beta1; sc.b2 = (float)beta2;
+  sc.omb1 = (float)(1.0 - beta1); sc.omb2 = (float)(1.0 - beta2);
+  sc.eps = (float)eps;
+  sc.c1 = (float)bias_corr1; sc.c2 = (float)bias_corr2;
+  sc.gscale = (float)grad_scale; sc.decay = (float)ema_decay; sc.omdecay = (float)(1.0 - ema_decay);
+  sc.b1d = beta1; sc.b2d = beta2;
+  adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, sc, ema, step_dev);
   XMC_LAUNCH_CHECK();
   if (step_dev) {
     inc_i32_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);

@@ -147,7 +147,7 @@ class _SnTable:
     e.rows, e.cols = rows, cols
     e.row_block_begin, e.col_tile_begin, e.elem_block_begin = self._rb, self._ct, self._eb
     self._t += _r4(rows)
-    self._s += _r4(cols)
+    self._s += _r4(((rows + 255) // 256) * cols)   # row-tile partials of s = t W (added in order by sn_finalize)
     self._rb += (rows + 7) // 8
     self._ct += ((rows + 255) // 256) * ((cols + 31) // 32)
     self._eb += (rows * cols + 2047) // 2048
@@ -164,17 +164,19 @@ class _SnTable:
     self.t_ws = torch.zeros(self._t, device="cuda")
     self.s_ws = torch.zeros(self._s, device="cuda")
     self.scalars = torch.zeros(4 * self.n, device="cuda")
+    self.dot_ws = torch.zeros(max(self._eb, 1), device="cuda")
 
   def forward(self, params, u0, u0_new):
     """One power-iteration step for every layer: u0_new, and 1/(sigma+eps) into scalars[2n + slot]."""
     ops._call("xmc_sn_forward", self.dev.data_ptr(), self.n, 1e-10, params.data_ptr(), u0.data_ptr(),
               u0_new.data_ptr(), self.t_ws.data_ptr(), self.s_ws.data_ptr(), self._s, self.scalars.data_ptr(),
-              self._rb, self._ct, _lib.stream(), launches=5)
+              self._rb, self._ct, _lib.stream(), launches=3)
 
   def backward(self, params, grads, u0_new):
     """grads holds d/dW~ for every registered kernel -> d/dW in place (sigma is differentiable, u/v are not)."""
     ops._call("xmc_sn_backward", self.dev.data_ptr(), self.n, params.data_ptr(), grads.data_ptr(),
-              self.t_ws.data_ptr(), u0_new.data_ptr(), self.scalars.data_ptr(), self._eb, _lib.stream(), launches=3)
+              self.t_ws.data_ptr(), u0_new.data_ptr(), self.scalars.data_ptr(), self.dot_ws.data_ptr(), self._eb,
+              _lib.stream(), launches=3)
 
   def inv_sigma(self, slot):
     return self.scalars[2 * self.n + slot:]
@@ -483,7 +485,7 @@ class GeneratorEngine:
     S = d_img.shape[1]
     gbC, gbL, R, Hc16 = ctx["gbC"], ctx["gbL"], ctx["R"], ctx["Hc"]
     grp = ctx["bn_group"]
-    dgbC = ops.zeros((B, self.NC), F32)  # ConditionalBatchNorm d(gamma), d(beta) are accumulated atomically
+    dgbC = ops.empty((B, self.NC), F32)  # every column is overwritten by its layer's bn_bwd
     dgbL = ops.empty((B * R, self.NL), F32)
 
     # output head: tanh, conv3x3 (C -> 3)
@@ -918,8 +920,10 @@ class DiscriminatorEngine:
     if wg:
       ops.c3_wgrad(b0["xpad"][sl], dc1, 0, 3 * df, df, 1, grads[r0.w_off:])
       ops.colsum(dc1, grads[r0.b_off:])
-      ops._call("xmc_wgrad_c3", xp.data_ptr(), dout.data_ptr(), n, S // 2, S // 2, df, 1, 1, 0, 3 * df, df, 1,
-                grads[r2.w_off:].data_ptr(), _lib.stream())
+      h2 = S // 2
+      part = ops.empty(n * ((h2 + 7) // 8) * ((h2 + 63) // 64) * 3 * df, F32)
+      ops._call("xmc_wgrad_c3", xp.data_ptr(), dout.data_ptr(), n, h2, h2, df, 1, 1, 0, 3 * df, df, 1,
+                grads[r2.w_off:].data_ptr(), part.data_ptr(), _lib.stream(), launches=2)
       ops.colsum(dout, grads[r2.b_off:])
     if not want_image_grad:
       return None

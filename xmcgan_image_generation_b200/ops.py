@@ -113,7 +113,13 @@ def wgrad(xa, xb, kh, out, *, out_mode=0, batched=False, ld_out=None, tap_stride
   d.out_batch_stride = batch_stride
   d.alpha = alpha
   d.subpixel = 1 if subpixel else 0
-  _call("xmc_conv2d_wgrad", ctypes.byref(d), ptr(xa), ptr(xb), ptr(out), stream())
+  # deterministic accumulation: partial tiles of a split reduction go through a caller-owned workspace and are added in
+  # a fixed order by a second kernel (counted as a launch); the caching allocator hands the same block back each step
+  need = ctypes.c_longlong(0)
+  _lib.check(_lib.lib().xmc_conv2d_wgrad_workspace_bytes(ctypes.byref(d), ctypes.byref(need)))
+  ws = torch.empty(need.value, device="cuda", dtype=torch.uint8) if need.value else None
+  _call("xmc_conv2d_wgrad", ctypes.byref(d), ptr(xa), ptr(xb), ptr(out), ptr(ws), need.value, stream(),
+        launches=2 if need.value else 1)
   return out
 
 
@@ -167,12 +173,23 @@ def _bn_desc(N, H, W, C, Hc, ldG, goff, boff, relu, upsample):
   return d
 
 
+_SMS = [0]
+
+
+def partial_rows(units, per_sm=4):
+  """Thread blocks (= partial rows) of a two-stage deterministic reduction over `units` work units: a few per SM."""
+  if not _SMS[0]:
+    _SMS[0] = _lib.lib().xmc_num_sms()
+  return int(max(1, min(per_sm * _SMS[0], units)))
+
+
 def bn_stats(x):
   C = x.shape[-1]
   P = x.numel() // C
-  sums = zeros(2 * C)
-  LAUNCHES[0] += 1  # the zero fill
-  _call("xmc_bn_stats", ptr(x), P, C, C, ptr(sums), stream())
+  sums = empty(2 * C, F32)
+  rows = partial_rows(P // 64)
+  part = empty(rows * 2 * C, F32)
+  _call("xmc_bn_stats", ptr(x), P, C, C, ptr(sums), ptr(part), rows, stream(), launches=2)
   return sums, P
 
 
@@ -204,9 +221,11 @@ def bn_bwd(dy, x, mr, gb, dgb, Hc, goff, boff, relu, upsample, group=None):
   N, H, W, C = x.shape
   assert gb.stride(0) == dgb.stride(0)
   d = _bn_desc(N, H, W, C, Hc, gb.stride(0), goff, boff, relu, upsample)
-  sums = zeros(2 * C)
-  LAUNCHES[0] += 1
-  _call("xmc_bn_bwd_reduce", ctypes.byref(d), ptr(dy), ptr(x), ptr(mr), ptr(gb), ptr(dgb), ptr(sums), stream())
+  sums = empty(2 * C, F32)
+  rows = partial_rows(N * Hc * Hc * 8, per_sm=8)   # the library clamps to the blocks it can fill
+  part = empty(rows * 2 * C, F32)
+  _call("xmc_bn_bwd_reduce", ctypes.byref(d), ptr(dy), ptr(x), ptr(mr), ptr(gb), ptr(dgb), ptr(sums), ptr(part), rows,
+        stream(), launches=2)
   if group is not None:
     from . import parallel
     parallel.all_reduce_sum_(sums, group=group[0])
@@ -237,7 +256,9 @@ def colsum(x, out, c=None):
   C = x.shape[-1] if c is None else c
   _check_dense_rows(x)
   P = x.numel() // x.shape[-1]
-  _call("xmc_colsum", ptr(x), P, C, _pix_ld(x), ptr(out), stream())
+  rows = partial_rows(P // 512)   # small tensors: one block adds straight into `out`
+  part = empty(rows * C, F32) if rows > 1 else None
+  _call("xmc_colsum", ptr(x), P, C, _pix_ld(x), ptr(out), ptr(part), rows, stream(), launches=2 if rows > 1 else 1)
 
 
 def relu_sumhw(x):
