@@ -71,6 +71,12 @@ typedef struct {
    * [N,2H,2W,Cout] tensor and output pixel (2h+a, 2w+b) belongs to parity a*2+b. 2.25x fewer FLOPs than the
    * reference's upsample-then-conv (xmcgan/nets/common.py:151-153,178-179), identical in exact arithmetic. */
   int subpixel;
+  /* 1: fp32-activation mode (config.dtype = "float32"; the frozen ResNet branch, which the reference always runs in
+   * fp32, pretrained_model_utils.py:87-91). x is the bf16 [hi | lo | hi] split of the fp32 input made by xmc_split3
+   * (C = 3 x the real channel count), wk the matching [hi | hi | lo] weight copy of xmc_prep_weights' split mode:
+   * the three bf16 products hi*hi + lo*hi + hi*lo accumulated in fp32 carry 16 mantissa bits per operand (SURVEY.md
+   * 8c(4) "3 x bf16 split"). residual / mask are fp32 tensors, out_dtype must be 1. */
+  int act_f32;
 } XmcConvDesc;
 
 int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* wk, const float* bias, const void* residual,
@@ -129,17 +135,18 @@ typedef struct {
    * replicas whose statistics were summed into `sums` by the caller's all-reduce; 0 or 1 = replica-local. Only
    * xmc_bn_bwd_apply reads it (its means divide by N*H*W*replicas). */
   int replicas;
+  int act_f32;             /* 0: x / gb / y / dy / dx are bf16 tensors, 1: fp32 (config.dtype = "float32") */
 } XmcBnDesc;
 
 /* Reductions are DETERMINISTIC (no atomics): a kernel with `rows` thread blocks leaves one partial row per block in
  * the caller's `partials` buffer (rows x width floats) and a second kernel adds the rows in index order. `rows` is
  * the caller's choice (any value >= 1; a few per SM for large tensors, see xmc_num_sms). */
-int xmc_sum_partials(const float* partials, int rows, int width, float* out /*[width]*/, int accumulate, void* stream);
+int xmc_sum_partials(const float* partials, int rows, int width, float* out, int accumulate, void* stream);
 /* sums[2C] = per-channel (sum x, sum x^2) over P pixels (overwritten); partials: rows x 2C floats of scratch */
-int xmc_bn_stats(const void* x, long long P, int C, int ld, float* sums, float* partials, int rows, void* stream);
+int xmc_bn_stats(const void* x, int act_f32, long long P, int C, int ld, float* sums, float* partials, int rows,
+                 void* stream);
 int xmc_bn_finalize(const float* sums, long long P, int C, float eps, float momentum, const float* ra_mean,
-                    const float* ra_var, float* new_ra_mean, float* new_ra_var, float* mean_rstd /*[2C]*/,
-                    void* stream);
+                    const float* ra_var, float* new_ra_mean, float* new_ra_var, float* mean_rstd, void* stream);
 int xmc_bn_eval_stats(const float* ra_mean, const float* ra_var, int C, float eps, float* mean_rstd, void* stream);
 int xmc_bn_apply(const XmcBnDesc* d, const void* x, const float* mean_rstd, const void* gb, void* y, void* stream);
 /* backward, pass 1: dgb (fp32, same row/column layout as gb) = d(gamma), d(beta) (overwritten); sums[2C] =
@@ -154,15 +161,21 @@ int xmc_bn_bwd_apply(const XmcBnDesc* d, const void* dy, const void* x, const fl
 /* 2x2/2 pooling: out = scale * sum_{2x2}(a (+ b)) (+ low); optional out_relu = relu(out). scale=0.25 is
  * common.dsample (xmcgan/nets/common.py:23-45,54-55); scale=1 is the transpose of common.upsample.
  * a, b: [N,2*Hout,2*Wout,C]; low: [N,Hout,Wout,C]. */
-int xmc_pool2(const void* a, const void* b, const void* low, int N, int Hout, int Wout, int C, float scale, void* out,
-              void* out_relu, void* stream);
+int xmc_pool2(const void* a, const void* b, const void* low, int act_f32, int N, int Hout, int Wout, int C,
+              float scale, void* out, void* out_relu, void* stream);
 /* transpose of pool2: g[n,2h+i,2w+j,c] = scale * dout[n,h,w,c] */
-int xmc_unpool2(const void* dout, int N, int Hin, int Win, int C, float scale, void* g, void* stream);
+int xmc_unpool2(const void* dout, int act_f32, int N, int Hin, int Win, int C, float scale, void* g, void* stream);
 /* out[c] += sum_p x[p][c] (bias gradients); partials: rows x C floats of scratch, may be NULL when rows == 1 */
-int xmc_colsum(const void* x, long long P, int C, int ld, float* out, float* partials, int rows, void* stream);
+int xmc_colsum(const void* x, int act_f32, long long P, int C, int ld, float* out, float* partials, int rows,
+               void* stream);
 /* x_pool[n][c] = sum_hw relu(x[n,hw,c]) (xmcgan/nets/xmc_net.py:97-98) and its backward */
-int xmc_relu_sumhw(const void* x, int N, int HW, int C, float* out, void* stream);
-int xmc_relu_sumhw_bwd(const void* x, const float* dout, int N, int HW, int C, void* dx, void* stream);
+int xmc_relu_sumhw(const void* x, int act_f32, int N, int HW, int C, float* out, void* stream);
+int xmc_relu_sumhw_bwd(const void* x, int act_f32, const float* dout, int N, int HW, int C, void* dx, void* stream);
+/* fp32 [rows][C] (pitch ld_src) -> bf16 [rows][hi(C) | lo(C) | hi(C)] (pitch ld_dst >= 3C): the A operand of
+ * xmc_conv2d_fwd in fp32-activation mode (XmcConvDesc.act_f32); xmc_conv2d_wgrad reads the hi / lo parts as views.
+ * weights = 1: the B-operand order [hi | hi | lo] (an activation used as the second GEMM operand). */
+int xmc_split3(const float* src, long long rows, int C, long long ld_src, int weights, void* dst, long long ld_dst,
+               void* stream);
 int xmc_cast_f32_to_bf16(const float* src, long long rows, int cols, long long ld_src, void* dst, long long ld_dst,
                          void* stream);
 int xmc_cast_bf16_to_f32(const void* src, long long rows, int cols, long long ld_src, float* dst, long long ld_dst,
@@ -175,9 +188,10 @@ int xmc_cast_bf16_to_f32(const void* src, long long rows, int cols, long long ld
 int xmc_prep_image(const float* img, const unsigned char* flip, int N, int H, int W, float* out, void* stream);
 int xmc_prep_caption(const float* emb, const int* len, const int* idx, int N, int M, int L, int E, float* emb_out,
                      float* len_out, float* sent_out, void* stream);
-int xmc_bcast_rows(const void* src, int B, int reps, int cols, int ld_src, void* dst, int ld_dst, void* stream);
-int xmc_sum_rows(const void* src, int B, int reps, int cols, int ld_src, float* dst, int ld_dst, int accumulate,
-                 void* stream);
+int xmc_bcast_rows(const void* src, int act_f32, int B, int reps, int cols, int ld_src, void* dst, int ld_dst,
+                   void* stream);
+int xmc_sum_rows(const void* src, int act_f32, int B, int reps, int cols, int ld_src, float* dst, int ld_dst,
+                 int accumulate, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Parameter-side multi-tensor kernels. Tables live in device memory; offsets index flat fp32 buffers.
@@ -192,8 +206,15 @@ typedef struct {
   int ld_fwd, ld_dg;
   int sn;                 /* spectral-norm slot, or -1 */
   int tile_begin;         /* prefix sum of ceil(taps*cin/64)*ceil(cout/64) */
-  int reserved;
+  /* 1: split copies for the fp32-activation mode (XmcConvDesc.act_f32). Every weight w is written as hi = bf16(w) and
+   * lo = bf16(w - hi) in the part order [hi | hi | lo] that pairs with the activations' [hi | lo | hi]:
+   *   forward copy [cout][tap][part][cin]  (ld_fwd >= 3*taps*cin),
+   *   dgrad copy   [cin][flip(tap)][part][dg_part_stride]  (ld_dg >= 3*taps*cout). */
+  int split;
   long long cscale_off;   /* per-output-channel scale inside the fp32 `cscale` buffer (folded eval BatchNorm), or -1 */
+  /* elements between the parts of the dgrad copy; 0 = cout. Layers whose dgrad copies are column slices of one
+   * concatenated matrix (the gamma / beta layers of the conditional BatchNorms) give the full matrix width here. */
+  long long dg_part_stride;
 } XmcPrepEntry;
 
 typedef struct {
@@ -225,7 +246,8 @@ int xmc_prep_weights(const XmcPrepEntry* table_dev, int n, int total_tiles, cons
  * fp32 HWIO kernel w [3][3][Cin][Cout]: wf bf16 [4*Cout][4*Cin] for XmcConvDesc.subpixel, vd bf16 [Cin][16*Cout] for
  * the input gradient (= xmc_conv2d_fwd with KH=KW=4, stride 2, pad 1 over the [N,2H,2W,Cout] output gradient).
  * scale: optional device scalar 1/(sigma+eps) of a spectrally normalised kernel (layers.py:221), NULL = 1. */
-int xmc_subpixel_prep(const float* w, const float* scale, int Cin, int Cout, void* wf, void* vd, void* stream);
+int xmc_subpixel_prep(const float* w, const float* scale, int Cin, int Cout, int split, void* wf, void* vd,
+                      void* stream);
 /* flax.optim.Adam.apply_gradient (weight_decay 0) in place on flat buffers, gradient pre-scaled by grad_scale
  * (1/world after a sum all-reduce == lax.pmean); optional polyak EMA of the updated parameters
  * (xmcgan/xmc_gan.py:172-177,252). bias_corr = 1 - beta^t. n must be a multiple of 4.
@@ -251,10 +273,11 @@ int xmc_l2norm_rows_bwd(const void* dxhat, int g_f32, long long ld_g, const void
 /* attention_lib.attention_for_g (attention_lib.py:194-219), fused QK^T - masked softmax over words - V, one warp per
  * region: q bf16 [B*R][ld_q] (un-normalised regions), what fp32 [B][L][D] (l2-normalised words), max_len fp32 [B].
  * Writes ctx bf16 [B*R][ld_ctx] and the attention weights attn fp32 [B*R][L]. bwd returns dq (words are data). */
-int xmc_attention_g_fwd(const void* q, int ld_q, const float* what, const float* max_len, int B, int R, int L, int D,
-                        float gamma, void* ctx, int ld_ctx, float* attn, void* stream);
-int xmc_attention_g_bwd(const void* dctx, int ld_dctx, const void* q, int ld_q, const float* what, const float* attn,
-                        int B, int R, int L, int D, float gamma, void* dq, int ld_dq, void* stream);
+int xmc_attention_g_fwd(const void* q, int act_f32, int ld_q, const float* what, const float* max_len, int B, int R,
+                        int L, int D, float gamma, void* ctx, int ld_ctx, float* attn, void* stream);
+int xmc_attention_g_bwd(const void* dctx, int act_f32, int ld_dctx, const void* q, int ld_q, const float* what,
+                        const float* attn, int B, int R, int L, int D, float gamma, void* dq, int ld_dq,
+                        void* stream);
 
 /* Elementwise / reduction stages of attention_lib.word_loss (attention_lib.py:105-191); i image, j sentence, w word,
  * r region, jw = j*L+w, BL = B*L, ldS = BL rounded up to 8. The three GEMM stages use xmc_conv2d_fwd/_wgrad.
@@ -264,18 +287,19 @@ int xmc_attention_g_bwd(const void* dctx, int ld_dctx, const void* q, int ld_q, 
  *   wl_cos_bwd : dctx (bf16) from dsim[j][i];  wl_softmax_bwd: dS (bf16) from dalpha (fp32)
  */
 int xmc_wl_softmax(const float* S, int B, int R, int BL, int ldS, float gamma1, void* alpha, void* alphaT,
-                   void* stream);
+                   int act_f32, void* stream);
 int xmc_wl_softmax_bwd(const void* alpha, const float* dalpha, int B, int R, int BL, int ldS, float gamma1, void* dS,
-                       void* stream);
+                       int act_f32, void* stream);
 int xmc_wl_cos(const float* ctx, long long ctx_batch_stride, const float* words, const float* winv, int B, int L,
                int D, float* cosv, float* cnorm, void* stream);
-int xmc_wl_sim(const float* cosv, const float* max_len, int B, int L, float gamma2, float gamma3, float* sim, float* pw,
-               void* stream);
+int xmc_wl_sim(const float* cosv, const float* max_len, int B, int L, float gamma2, float gamma3, float* sim,
+               float* pw, void* stream);
 int xmc_wl_cos_bwd(const float* dsim, const float* pw, const float* cosv, const float* cnorm, const float* ctx,
                    long long ctx_batch_stride, const float* words, const float* winv, int B, int L, int D,
-                   float gamma3, void* dctx, long long dctx_batch_stride, void* stream);
+                   float gamma3, void* dctx, long long dctx_batch_stride, int act_f32, void* stream);
 /* dst[c][r] = src[r][c] for r<rows, zero for rows <= r < ld_dst */
-int xmc_transpose_bf16(const void* src, int rows, int cols, int ld_src, void* dst, int ld_dst, void* stream);
+int xmc_transpose_bf16(const void* src, int act_f32, int rows, int cols, int ld_src, void* dst, int ld_dst,
+                       void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Loss heads. InfoNCE = l2norm_rows + small_gemm_nt (logits = scale*A B^T) + ce_sym, local-batch negatives only
@@ -292,7 +316,8 @@ int xmc_ce_sym(const float* logits, int n, float weight, float* loss_out, float*
  * statistics are dead on the train path (XLA removes them); they exist for the functional API. */
 int xmc_ce_stats(const float* logits, int n, float* out, void* stream);
 /* losses.hinge_loss (losses.py:30-35) on logit = [real(B); fake(B)] and the two cotangents */
-int xmc_hinge(const float* logit, int B, float* d_loss, float* g_loss, float* dlogit_d, float* dlogit_g, void* stream);
+int xmc_hinge(const float* logit, int B, float* d_loss, float* g_loss, float* dlogit_d, float* dlogit_g,
+              void* stream);
 /* projection-discriminator logit (xmc_net.py:97-104): out[n] = <xpool[n], w1*inv_sigma + emb[n%B]> + b1 */
 int xmc_proj_logit(const float* xpool, const float* w1, const float* inv_sigma, const float* b1, const float* emb,
                    int N2, int B, int C, float* out, void* stream);
@@ -317,35 +342,38 @@ int xmc_pad_c3_to_c8(const void* x, int N, int H, int W, void* out, void* stream
 int xmc_pack_c3_weights(const void* w, int ldw, int Cout, void* out, void* stream);
 int xmc_unpack_c3_wgrad(const float* tmp, int C, int flip, long long s_tap, int s_c3, int s_c, float* out,
                         void* stream);
-int xmc_conv_c3_in(const void* x, const void* w, int ldw, const float* bias, int N, int H, int W, int Cout, int KH,
-                   int KW, int relu, void* y, void* stream);
+int xmc_conv_c3_in(const void* x, int act_f32, const void* w, int ldw, const float* bias, int N, int H, int W,
+                   int Cout, int KH, int KW, int relu, void* y, void* stream);
 /* mode 0: y fp32 (+= if accumulate); mode 1: y = (tanh(v)+1)/2 fp32 plus bf16 copy y_bf16 */
-int xmc_conv_c3_out(const void* x, const void* w, int ldw, const float* bias, int N, int H, int W, int Cin, int KH,
-                    int KW, int mode, int accumulate, float* y, void* y_bf16, void* stream);
+int xmc_conv_c3_out(const void* x, int act_f32, const void* w, int ldw, const float* bias, int N, int H, int W,
+                    int Cin, int KH, int KW, int mode, int accumulate, float* y, void* y_bf16, void* stream);
 /* out[tap_o*s_tap + c3*s_c3 + c*s_c] += sum_p x3[p+shift(tap)][c3]*y[p][c], tap_o = flip ? taps-1-tap : tap.
  * Deterministic: partials = N*ceil(H/8)*ceil(W/64) x (KH*KW*3*C) floats of scratch, added in block order. */
-int xmc_wgrad_c3(const void* x3, const void* y, int N, int H, int W, int C, int KH, int KW, int flip, long long s_tap,
-                 int s_c3, int s_c, float* out, float* partials, void* stream);
-int xmc_pool2_small(const void* a, int N, int Hout, int Wout, int C, float scale, void* out, void* stream);
+int xmc_wgrad_c3(const void* x3, const void* y, int act_f32, int N, int H, int W, int C, int KH, int KW, int flip,
+                 long long s_tap, int s_c3, int s_c, float* out, float* partials, void* stream);
+int xmc_pool2_small(const void* a, int act_f32, int N, int Hout, int Wout, int C, float scale, void* out,
+                    void* stream);
 int xmc_unpool2_add_f32(const float* d, int N, int Hin, int Win, int C, float scale, float* g, void* stream);
-int xmc_tanh01_bwd(const float* dimg, const float* img, long long n, void* dpre, void* stream);
+int xmc_tanh01_bwd(const float* dimg, const float* img, long long n, void* dpre, int act_f32, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Frozen ResNet-50 feature branch (xmcgan/xmc_gan.py:74-90, xmcgan/utils/resnet_v1.py:129-172,
  * xmcgan/utils/pretrained_model_utils.py:102-127). Its convolutions use xmc_conv2d_fwd (BatchNorm folded).
  */
 /* jax.image.resize(img, (T,T), "bilinear") of fp32 [N,S,S,3] into a zero-bordered bf16 [N,Tp,Tp,8] buffer */
-int xmc_resize_bilinear_pad(const float* img, int N, int S, int T, int Tp, int pad_lo, void* out, void* stream);
+int xmc_resize_bilinear_pad(const float* img, int N, int S, int T, int Tp, int pad_lo, int split, void* out,
+                            void* stream);
 /* transpose of the resize: dimg[N,S,S,3] += R^T dout[N,T,T,3] */
 int xmc_resize_bilinear_bwd(const float* dout, int N, int S, int T, float* dimg, void* stream);
 /* input gradient of the 7x7/2 stem (resnet_v1.py:146-151): dy bf16 [N,Ho,Ho,Cout], wk bf16 [Cout][7*56] */
-int xmc_stem_dgrad(const void* dy, const void* wk, int N, int T, int Ho, int Cout, int pad_lo, float* dimg,
-                   void* stream);
+int xmc_stem_dgrad(const void* dy, int act_f32, const void* wk, const void* wk_lo, int N, int T, int Ho, int Cout,
+                   int pad_lo, float* dimg, void* stream);
 /* nn.max_pool 3x3/2 SAME (resnet_v1.py:154) on bf16 [N,H,H,C] and its transpose (first-max tie rule) */
-int xmc_maxpool3s2(const void* x, int N, int H, int C, void* y, void* stream);
-int xmc_maxpool3s2_bwd(const void* dy, const void* x, const void* y, int N, int H, int C, void* dx, void* stream);
+int xmc_maxpool3s2(const void* x, int act_f32, int N, int H, int C, void* y, void* stream);
+int xmc_maxpool3s2_bwd(const void* dy, const void* x, const void* y, int act_f32, int N, int H, int C, void* dx,
+                       void* stream);
 /* z[n,2h,2w,:] = dy[n,h,w,:], zero elsewhere (transpose of stride-2 sampling) */
-int xmc_zero_insert2(const void* dy, int N, int H, int W, int C, void* z, void* stream);
+int xmc_zero_insert2(const void* dy, int act_f32, int N, int H, int W, int C, void* z, void* stream);
 
 #ifdef __cplusplus
 }

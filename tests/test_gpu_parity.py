@@ -12,6 +12,9 @@ gpu = pytest.mark.gpu
 # with batch 2 (its BatchNorm statistics come from very few elements per channel at 4x4).
 GRAD_TOL = (3e-2, 0.999)
 GRAD_TOL_256 = (6e-2, 0.998)
+# generator leaves below the 16x16 stage in bf16 mode (see tests/test_gpu_baseline_width.py): conditioned at ~20x the
+# bf16 epsilon (the oracle's bf16 and fp32 policies differ by this much there); their sharp check is the fp32 mode
+GRAD_TOL_DEEP = (2e-1, 0.98)
 
 
 def _mods():
@@ -269,11 +272,16 @@ def test_generator_and_discriminator_apply_match_oracle():
     assert helpers.rel(a, b) < 1e-4, p
 
 
-def grad_tree_report(got_tree, ref_tree, tol, min_cos):
-  """Per-leaf comparison of a gradient tree with the oracle's (bf16 policy with rounded cotangents): rel-L2 <= tol and
-  cosine >= min_cos for every leaf whose true gradient is not numerically zero; the others (biases in front of a
-  BatchNorm) are compared in absolute terms against the largest leaf. Returns ((worst rel, its leaf, lowest cosine,
-  its leaf), [violations])."""
+def _is_deep_generator_leaf(path):
+  """Generator leaves below the 16x16 stage: the z / sentence dense layers and the two 4x4 -> 16x16 GenBlocks."""
+  return path.startswith(("Dense_", "SpectralDense_", "GenBlock_"))
+
+
+def grad_tree_report(got_tree, ref_tree, tol, min_cos, deep_tol=None, deep_cos=None):
+  """Per-leaf comparison of a gradient tree with the oracle's: rel-L2 <= tol and cosine >= min_cos for every leaf
+  whose true gradient is not numerically zero; the others (biases in front of a BatchNorm) are compared in absolute
+  terms against the largest leaf. deep_tol / deep_cos: separate bars for the generator leaves below the 16x16 stage.
+  Returns ((worst rel, its leaf, lowest cosine, its leaf), [violations])."""
   ref = orc.tree_leaves(ref_tree)
   scale = max(r.norm().item() for _, r in ref)
   bad, worst_e, worst_c = [], (0.0, None), (1.0, None)
@@ -284,16 +292,18 @@ def grad_tree_report(got_tree, ref_tree, tol, min_cos):
       cos = torch.nn.functional.cosine_similarity(g.reshape(-1), r.reshape(-1), dim=0).item()
       worst_e = max(worst_e, (e, path))
       worst_c = min(worst_c, (cos, path))
-      if not (e <= tol and cos >= min_cos):
-        bad.append((path, round(e, 4), round(cos, 5)))
+      t, c = (deep_tol, deep_cos) if (deep_tol is not None and _is_deep_generator_leaf(path)) else (tol, min_cos)
+      if not (e <= t and cos >= c):
+        bad.append((path, round(e, 4), round(cos, 6)))
     elif (g - r).norm().item() > 1e-3 * scale:
       bad.append((path, "abs", (g - r).norm().item(), scale))
   return (worst_e[0], worst_e[1], worst_c[0], worst_c[1]), bad
 
 
 @gpu
+@pytest.mark.parametrize("dtype", ["bfloat16", "float32"])
 @pytest.mark.parametrize("variant", ["default", "no_sn", "no_word", "ragged", "px256", "g_sn"])
-def test_both_pullbacks_match_oracle(variant):
+def test_both_pullbacks_match_oracle(variant, dtype):
   """d(d_loss)/d(params_d) and d(g_loss)/d(params_g) from ONE forward (xmc_gan.py:162-167) vs oracle autograd under
   Policy("bfloat16", round_grads=True) — the bf16 policy that also rounds activation COTANGENTS at the storage points,
   which is what the CUDA path (and the reference's bf16 graph) does. Per leaf: rel-L2 <= GRAD_TOL, cosine >= GRAD_COS;
@@ -301,11 +311,14 @@ def test_both_pullbacks_match_oracle(variant):
   _, engine, ops, _, _, xmc_net = _mods()
   kw = {"no_sn": dict(d_spectral_norm=False), "no_word": dict(word_contrastive=False),
         "px256": dict(image_size=256, gf_dim=8, df_dim=8), "g_sn": dict(g_spectral_norm=True)}.get(variant, {})
-  cfg = helpers.small_config(**kw)
+  cfg = helpers.small_config(dtype=dtype, **kw)
+  fp32 = dtype == "float32"
   B = {"ragged": 3, "px256": 2}.get(variant, 4)
   # 256 px: one more block in G and D, batch 2, width 8 — the configuration most sensitive to bf16 perturbations
   # (the oracle's own bf16-vs-fp32 gradients differ by > 10 % there); the sharp backward checks are the single-op tests
   tol, min_cos = GRAD_TOL_256 if variant == "px256" else GRAD_TOL
+  if fp32:   # fp32 mode vs the fp32 oracle: SURVEY.md 8c(4) bars on every leaf
+    tol, min_cos = 1.5e-2, 0.9999
   g_vars, d_vars, g_params, g_stats, d_params, d_u = _build(cfg, seed=4)
   batch = helpers.make_batch(B, cfg, seed=2, min_len=1 if variant == "ragged" else 3)
   dev = xmc_net.batch_to_device(batch)
@@ -316,8 +329,9 @@ def test_both_pullbacks_match_oracle(variant):
   g_eng.prep_weights(g_params.buf, g_u, g_u_new)
   u_new = torch.empty_like(d_u.buf)
   d_eng.prep_weights(d_params.buf, d_u.buf if d_eng.sn else None, u_new if d_eng.sn else None)
-  all_images = ops.empty((2 * B, S, S, 3))
-  ops.cast_to_bf16(dev["image"].reshape(-1, 3), all_images[:B].view(-1, 3))
+  with ops.act_dtype(g_eng.act):
+    all_images = ops.empty((2 * B, S, S, 3))
+    ops.cast_to_bf16(dev["image"].reshape(-1, 3), all_images[:B].view(-1, 3))
   img, gctx = g_eng.forward(g_params.buf, g_stats.buf, dev, dev["z"], train=True, fake_bf16=all_images[B:])
   losses = torch.zeros(16, device="cuda")
   _, dctx = d_eng.forward(d_params.buf, all_images, dev, losses, need_g=True)
@@ -330,7 +344,8 @@ def test_both_pullbacks_match_oracle(variant):
   g_eng.sn_backward(g_params.buf, g_grads, g_u_new)
   torch.cuda.synchronize()
   state = orc.make_state(g_vars, d_vars if d_eng.sn else {"params": d_vars["params"]})
-  r = orc.d_losses_and_grads(state, batch, cfg, orc.Policy("bfloat16", round_grads=True), want_g=True)
+  r = orc.d_losses_and_grads(state, batch, cfg, orc.FP32 if fp32 else orc.Policy("bfloat16", round_grads=True),
+                             want_g=True)
   l = losses.cpu()
   # the totals are sums of terms of mixed sign (hinge_g = -mean(fake logit)): tolerance relative to the term sizes
   d_scale = (l[0].abs() + l[2].abs() + l[4].abs()).item()
@@ -338,8 +353,9 @@ def test_both_pullbacks_match_oracle(variant):
   assert abs((l[0] + l[2] + l[4]).item() - r["d_loss"].item()) < 2e-3 * d_scale
   assert abs((l[1] + l[3] + l[5] + l[6]).item() - r["g_loss"].item()) < 2e-3 * g_scale
   for name, lay, flat in (("d_grad", d_eng.layout, d_grads), ("g_grad", g_eng.layout, g_grads)):
-    worst, bad = grad_tree_report(xmc_net.FlatTree(lay, flat).to_cpu_tree(), r[name], tol, min_cos)
-    print(f"\n[{variant}] {name}: worst leaf rel-L2 {worst[0]:.3e} ({worst[1]}), lowest cosine {worst[2]:.5f} ({worst[3]})")
+    deep = GRAD_TOL_DEEP if (name == "g_grad" and not fp32) else (None, None)
+    worst, bad = grad_tree_report(xmc_net.FlatTree(lay, flat).to_cpu_tree(), r[name], tol, min_cos, *deep)
+    print(f"\n[{variant} {dtype}] {name}: worst leaf rel-L2 {worst[0]:.3e} ({worst[1]}), lowest cosine {worst[2]:.5f} ({worst[3]})")
     assert not bad, bad
 
 
@@ -494,7 +510,7 @@ def _pretrained_setup(seed=8):
 def test_train_step_with_pretrained_image_contrastive():
   """The reference's default configuration (pretrained_image_contrastive=True) through train_step vs the oracle, from
   a mid-training optimiser state (helpers.warm_adam): all five metrics within 5e-3 of the largest, generator
-  parameter updates per leaf rel-L2 5e-2."""
+  parameter updates per leaf rel-L2 5e-2 (2e-1 below the 16x16 stage)."""
   _, engine, ops, train_utils, xmc_gan, xmc_net = _mods()
   cfg, batch, state, ostate, additional, pol, pre = _pretrained_setup()
   helpers.warm_adam(state, ostate)
@@ -508,14 +524,7 @@ def test_train_step_with_pretrained_image_contrastive():
   for k in ("d_loss", "g_loss", "c_loss_d", "c_loss_g", "c_loss_g_pretrained"):
     assert abs(got[k] - want[k]) < 5e-3 * scale, (k, got[k], want[k])
   assert got["c_loss_g_pretrained"] > 0
-  rows = []
-  for (p, a), (_, a0), (_, b), (_, b0) in zip(orc.tree_leaves(state.g_optimizer.target.to_cpu_tree()),
-                                              orc.tree_leaves(g_old), orc.tree_leaves(ostate["g_params"]),
-                                              orc.tree_leaves(o_old)):
-    if (b - b0).norm() > 0:
-      rows.append((helpers.rel(a - a0, b - b0), p))
-  print("  worst generator update leaf:", max(rows))
-  assert max(rows)[0] < 5e-2, max(rows)
+  helpers.check_updates("g", state.g_optimizer.target.to_cpu_tree(), g_old, ostate["g_params"], o_old, cfg.g_lr)
 
 
 @gpu
@@ -575,7 +584,7 @@ def test_subpixel_conv_equals_upsample_then_conv(N, H, C, Cout):
   wf = ops.empty((4 * Cout, 4 * C))
   vd = ops.empty((C, 16 * Cout))
   kd = kern.detach().cuda().contiguous()
-  ops._call("xmc_subpixel_prep", kd.data_ptr(), None, C, Cout, wf.data_ptr(), vd.data_ptr(), _lib.stream())
+  ops._call("xmc_subpixel_prep", kd.data_ptr(), None, C, Cout, 0, wf.data_ptr(), vd.data_ptr(), _lib.stream())
   xd = x.detach().cuda().to(torch.bfloat16)
   got = ops.conv_fwd(xd, wf, 2, Cout, bias=bias.cuda(), ldb=4 * C, pad=1, subpixel=True, out_dtype=torch.float32)
   assert got.shape == (N, 2 * H, 2 * H, Cout)
@@ -665,7 +674,7 @@ def test_generate_batch_and_checkpoint_round_trip(tmp_path):
                                  {"batch_stats": g_stats}, {"spectral_norm_stats": d_u}, g_params.clone())
   state, _ = train_utils.train_step(None, state, batch, xmc_gan, None, None, cfg, {})   # EMA != params afterwards
   gen = functools.partial(xmc_net.Generator, config=cfg)
-  out = train_utils.generate_batch(0, state, batch, gen, cfg)
+  out = train_utils.generate_batch(0, state, batch, gen, cfg, z=batch["z"])
   assert set(out) == {"generated_image_batch", "ema_generated_image_batch", "ori_image_batch"}
   assert out["generated_image_batch"].shape == (1, 2 * 128, 2 * 128, 3)
   pol = orc.Policy("bfloat16")
@@ -744,7 +753,7 @@ def test_bilinear_resize_to_224_matches_jax_semantics(S):
   want = torch.nn.functional.interpolate(img.permute(0, 3, 1, 2), size=(T, T), mode="bilinear", align_corners=False,
                                          antialias=S > T).permute(0, 2, 3, 1)
   out = ops.empty((n, TP, TP, 8))
-  ops._call("xmc_resize_bilinear_pad", img.detach().cuda().data_ptr(), n, S, T, TP, PAD, out.data_ptr(), _lib.stream())
+  ops._call("xmc_resize_bilinear_pad", img.detach().cuda().data_ptr(), n, S, T, TP, PAD, 0, out.data_ptr(), _lib.stream())
   got = out.float().cpu()
   assert helpers.rel(got[:, PAD:PAD + T, PAD:PAD + T, :3], want) < 4e-3
   assert got[:, :PAD].abs().max() == 0 and got[..., 3:].abs().max() == 0      # zero border, zero pad channels

@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol():
   assert L.xmc_version() >= 101
   # struct mirrors: the loader refuses a layout mismatch; spot-check two sizes against the header by hand
   assert L.xmc_sizeof(0) == ctypes.sizeof(_lib.ConvDesc) and L.xmc_sizeof(1) == ctypes.sizeof(_lib.WgradDesc)
-  assert L.xmc_sizeof(2) == ctypes.sizeof(_lib.BnDesc) == 11 * 4 and L.xmc_sizeof(99) == -1
+  assert L.xmc_sizeof(2) == ctypes.sizeof(_lib.BnDesc) == 12 * 4 and L.xmc_sizeof(99) == -1
   assert L.xmc_strerror(-1).decode().startswith("invalid")
 
 

@@ -33,7 +33,7 @@ class ConvDesc(ctypes.Structure):
       ("ldRes", ctypes.c_int), ("ldMask", ctypes.c_int),
       ("strideH", ctypes.c_int), ("strideW", ctypes.c_int), ("Hin", ctypes.c_int), ("Win", ctypes.c_int),
       ("pitchW", ctypes.c_longlong), ("pitchH", ctypes.c_longlong), ("pitchN", ctypes.c_longlong),
-      ("mask_last", ctypes.c_int), ("subpixel", ctypes.c_int),
+      ("mask_last", ctypes.c_int), ("subpixel", ctypes.c_int), ("act_f32", ctypes.c_int),
   ]
 
 
@@ -58,7 +58,7 @@ class BnDesc(ctypes.Structure):
       ("N", ctypes.c_int), ("H", ctypes.c_int), ("W", ctypes.c_int), ("C", ctypes.c_int),
       ("Hc", ctypes.c_int),
       ("ldG", ctypes.c_int), ("goff", ctypes.c_int), ("boff", ctypes.c_int),
-      ("relu", ctypes.c_int), ("upsample", ctypes.c_int), ("replicas", ctypes.c_int),
+      ("relu", ctypes.c_int), ("upsample", ctypes.c_int), ("replicas", ctypes.c_int), ("act_f32", ctypes.c_int),
   ]
 
 
@@ -68,8 +68,8 @@ class PrepEntry(ctypes.Structure):
       ("bias_off", ctypes.c_longlong), ("bias_dst_off", ctypes.c_longlong),
       ("taps", ctypes.c_int), ("cin", ctypes.c_int), ("cout", ctypes.c_int),
       ("ld_fwd", ctypes.c_int), ("ld_dg", ctypes.c_int),
-      ("sn", ctypes.c_int), ("tile_begin", ctypes.c_int), ("reserved", ctypes.c_int),
-      ("cscale_off", ctypes.c_longlong),
+      ("sn", ctypes.c_int), ("tile_begin", ctypes.c_int), ("split", ctypes.c_int),
+      ("cscale_off", ctypes.c_longlong), ("dg_part_stride", ctypes.c_longlong),
   ]
 
 

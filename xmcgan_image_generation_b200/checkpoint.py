@@ -101,7 +101,7 @@ def _load(flat_tree, tree):
 
 def _load_adam(opt, sd):
   _load(opt.target, sd["target"])
-  opt.step = int(np.asarray(sd["state"]["step"]))
+  opt.set_step(int(np.asarray(sd["state"]["step"])))  # host counter and, in graph mode, the device counter
   lay = opt.target.layout
   pick = lambda t, leaf: ({k: pick(v, leaf) for k, v in t.items()} if leaf not in t else t[leaf])
   lay.load_tree(opt.m, pick(sd["state"]["param_states"], "grad_ema"))

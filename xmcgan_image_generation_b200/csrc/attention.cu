@@ -61,9 +61,10 @@ __global__ void l2norm_rows_bwd_kernel(const TG* __restrict__ dxh, long long ld_
 constexpr int kMaxWords = 32;
 constexpr int kMaxVec = 4;  // D <= 1024
 
-__global__ void attn_g_fwd_kernel(const bf16* __restrict__ q, int ld_q, const float* __restrict__ what,
+template <typename T>
+__global__ void attn_g_fwd_kernel(const T* __restrict__ q, int ld_q, const float* __restrict__ what,
                                   const float* __restrict__ max_len, int B, int R, int L, int D, float gamma,
-                                  bf16* __restrict__ ctx, int ld_ctx, float* __restrict__ attn) {
+                                  T* __restrict__ ctx, int ld_ctx, float* __restrict__ attn) {
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= (long long)B * R) return;
@@ -135,9 +136,10 @@ __global__ void attn_g_fwd_kernel(const bf16* __restrict__ q, int ld_q, const fl
   }
 }
 
-__global__ void attn_g_bwd_kernel(const bf16* __restrict__ dctx, int ld_dctx, const bf16* __restrict__ q, int ld_q,
+template <typename T>
+__global__ void attn_g_bwd_kernel(const T* __restrict__ dctx, int ld_dctx, const T* __restrict__ q, int ld_q,
                                   const float* __restrict__ what, const float* __restrict__ attn, int B, int R, int L,
-                                  int D, float gamma, bf16* __restrict__ dq, int ld_dq) {
+                                  int D, float gamma, T* __restrict__ dq, int ld_dq) {
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= (long long)B * R) return;
@@ -227,9 +229,10 @@ __global__ void attn_g_bwd_kernel(const bf16* __restrict__ dctx, int ld_dctx, co
 // One block = image i x 32 columns jw, 256 threads as (32 columns) x (8 row groups): every global access is a run of 32
 // consecutive jw (S, alpha) or 32 consecutive r (alpha^T); the [R][32] tile lives in shared memory between the passes.
 constexpr int kWlMaxR = 256;
+template <typename T>
 __global__ void __launch_bounds__(256)
 wl_softmax_kernel(const float* __restrict__ S, int B, int R, int BL, int ldS, float gamma1,
-                  bf16* __restrict__ alpha, bf16* __restrict__ alphaT) {
+                  T* __restrict__ alpha, T* __restrict__ alphaT) {
   __shared__ float tile[kWlMaxR][33];
   __shared__ float red[8][33];
   const int i = blockIdx.y;
@@ -261,8 +264,8 @@ wl_softmax_kernel(const float* __restrict__ S, int B, int R, int BL, int ldS, fl
   for (int k = 0; k < 8; ++k) sum += red[k][cx];
   const float rs = 1.f / sum;
   for (int r = ry; r < R; r += 8) {
-    const bf16 v = __float2bfloat16(live ? tile[r][cx] * rs : 0.f);
-    tile[r][cx] = __bfloat162float(v);
+    const T v = from_f<T>(live ? tile[r][cx] * rs : 0.f);
+    tile[r][cx] = to_f(v);
     if (jw < ldS) alpha[base + (long long)r * ldS] = v;   // padded columns [BL, ldS) are written as zeros
   }
   __syncthreads();
@@ -270,15 +273,16 @@ wl_softmax_kernel(const float* __restrict__ S, int B, int R, int BL, int ldS, fl
   for (int c = ry; c < 32; c += 8) {
     const int jc = blockIdx.x * 32 + c;
     if (jc >= BL) continue;
-    bf16* at = alphaT + ((long long)i * ldS + jc) * R;
-    for (int r = cx; r < R; r += 32) at[r] = __float2bfloat16(tile[r][c]);
+    T* at = alphaT + ((long long)i * ldS + jc) * R;
+    for (int r = cx; r < R; r += 32) at[r] = from_f<T>(tile[r][c]);
   }
 }
 
 // dS = gamma1 * alpha * (dalpha - sum_r alpha*dalpha); same block shape as the forward kernel
+template <typename T>
 __global__ void __launch_bounds__(256)
-wl_softmax_bwd_kernel(const bf16* __restrict__ alpha, const float* __restrict__ dalpha, int B, int R,
-                      int BL, int ldS, float gamma1, bf16* __restrict__ dS) {
+wl_softmax_bwd_kernel(const T* __restrict__ alpha, const float* __restrict__ dalpha, int B, int R,
+                      int BL, int ldS, float gamma1, T* __restrict__ dS) {
   __shared__ float red[8][33];
   const int i = blockIdx.y;
   const int cx = threadIdx.x, ry = threadIdx.y;
@@ -288,7 +292,7 @@ wl_softmax_bwd_kernel(const bf16* __restrict__ alpha, const float* __restrict__ 
   float t = 0.f;
   if (live)
     for (int r = ry; r < R; r += 8)
-      t += __bfloat162float(alpha[base + (long long)r * ldS]) * dalpha[base + (long long)r * ldS];
+      t += to_f(alpha[base + (long long)r * ldS]) * dalpha[base + (long long)r * ldS];
   red[ry][cx] = t;
   __syncthreads();
   t = 0.f;
@@ -298,10 +302,10 @@ wl_softmax_bwd_kernel(const bf16* __restrict__ alpha, const float* __restrict__ 
   for (int r = ry; r < R; r += 8) {
     float v = 0.f;
     if (live) {
-      const float a = __bfloat162float(alpha[base + (long long)r * ldS]);
+      const float a = to_f(alpha[base + (long long)r * ldS]);
       v = gamma1 * a * (dalpha[base + (long long)r * ldS] - t);
     }
-    dS[base + (long long)r * ldS] = __float2bfloat16(v);
+    dS[base + (long long)r * ldS] = from_f<T>(v);
   }
 }
 
@@ -352,11 +356,12 @@ __global__ void wl_sim_kernel(const float* __restrict__ cosv, const float* __res
 }
 
 // dctx[i][jw][:] = dsim[j][i]*gamma3*pw * ( W/(|W||ctx|) - cos*ctx/|ctx|^2 )
+template <typename T>
 __global__ void wl_cos_bwd_kernel(const float* __restrict__ dsim, const float* __restrict__ pw,
                                   const float* __restrict__ cosv, const float* __restrict__ cnorm,
                                   const float* __restrict__ ctx, long long ctx_batch_stride,
                                   const float* __restrict__ words, const float* __restrict__ winv, int B, int L, int D,
-                                  float gamma3, bf16* __restrict__ dctx, long long dctx_batch_stride) {
+                                  float gamma3, T* __restrict__ dctx, long long dctx_batch_stride) {
   const int BL = B * L;
   const long long idx = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -368,7 +373,7 @@ __global__ void wl_cos_bwd_kernel(const float* __restrict__ dsim, const float* _
   const float k1 = dcos * winv[jw] / cn, k2 = dcos * cs / (cn * cn);
   const float* c = ctx + (long long)i * ctx_batch_stride + (long long)jw * D;
   const float* w = words + (long long)jw * D;
-  bf16* o = dctx + (long long)i * dctx_batch_stride + (long long)jw * D;
+  T* o = dctx + (long long)i * dctx_batch_stride + (long long)jw * D;
   for (int f = lane * 8; f < D; f += 256) {
     float v[8];
 #pragma unroll
@@ -377,13 +382,14 @@ __global__ void wl_cos_bwd_kernel(const float* __restrict__ dsim, const float* _
   }
 }
 
-__global__ void transpose_bf16_kernel(const bf16* __restrict__ src, int rows, int cols, int ld_src,
-                                      bf16* __restrict__ dst, int ld_dst) {
-  __shared__ bf16 tile[32][34];
+template <typename T>
+__global__ void transpose_bf16_kernel(const T* __restrict__ src, int rows, int cols, int ld_src,
+                                      T* __restrict__ dst, int ld_dst) {
+  __shared__ T tile[32][34];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int r = threadIdx.y; r < 32; r += 8) {
     const int rr = r0 + r, cc = c0 + threadIdx.x;
-    tile[r][threadIdx.x] = (rr < rows && cc < cols) ? src[(long long)rr * ld_src + cc] : __float2bfloat16(0.f);
+    tile[r][threadIdx.x] = (rr < rows && cc < cols) ? src[(long long)rr * ld_src + cc] : from_f<T>(0.f);
   }
   __syncthreads();
   for (int r = threadIdx.y; r < 32; r += 8) {
@@ -429,43 +435,43 @@ extern "C" int xmc_l2norm_rows_bwd(const void* dxhat, int g_f32, long long ld_g,
   return XMC_OK;
 }
 
-extern "C" int xmc_attention_g_fwd(const void* q, int ld_q, const float* what, const float* max_len, int B, int R,
-                                   int L, int D, float gamma, void* ctx, int ld_ctx, float* attn, void* stream) {
+extern "C" int xmc_attention_g_fwd(const void* q, int act_f32, int ld_q, const float* what, const float* max_len, int B,
+                                   int R, int L, int D, float gamma, void* ctx, int ld_ctx, float* attn, void* stream) {
   if (!q || !what || !max_len || !ctx || !attn) return XMC_EINVAL;
   if (L > kMaxWords || D > kMaxVec * 256 || (D % 8) || (ld_q % 8) || (ld_ctx % 8)) return XMC_EINVAL;
   const unsigned grid = (unsigned)ceil_div_ll((long long)B * R, 8);
-  attn_g_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)q, ld_q, what, max_len, B, R, L, D, gamma,
-                                                           (bf16*)ctx, ld_ctx, attn);
+  XMC_ACT(act_f32, attn_g_fwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)q, ld_q, what, max_len, B, R, L, D,
+                                                                            gamma, (T*)ctx, ld_ctx, attn));
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }
 
-extern "C" int xmc_attention_g_bwd(const void* dctx, int ld_dctx, const void* q, int ld_q, const float* what,
+extern "C" int xmc_attention_g_bwd(const void* dctx, int act_f32, int ld_dctx, const void* q, int ld_q, const float* what,
                                    const float* attn, int B, int R, int L, int D, float gamma, void* dq, int ld_dq,
                                    void* stream) {
   if (!dctx || !q || !what || !attn || !dq) return XMC_EINVAL;
   if (L > kMaxWords || D > kMaxVec * 256 || (D % 8) || (ld_q % 8) || (ld_dctx % 8) || (ld_dq % 8)) return XMC_EINVAL;
   const unsigned grid = (unsigned)ceil_div_ll((long long)B * R, 8);
-  attn_g_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)dctx, ld_dctx, (const bf16*)q, ld_q, what,
-                                                           attn, B, R, L, D, gamma, (bf16*)dq, ld_dq);
+  XMC_ACT(act_f32, attn_g_bwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)dctx, ld_dctx, (const T*)q, ld_q,
+                                                                            what, attn, B, R, L, D, gamma, (T*)dq, ld_dq));
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }
 
 extern "C" int xmc_wl_softmax(const float* S, int B, int R, int BL, int ldS, float gamma1, void* alpha, void* alphaT,
-                              void* stream) {
+                              int act_f32, void* stream) {
   if (!S || !alpha || !alphaT || B < 1 || R < 1 || R > kWlMaxR || BL < 1 || ldS < BL) return XMC_EINVAL;
-  wl_softmax_kernel<<<dim3(ceil_div(ldS, 32), B), dim3(32, 8), 0, (cudaStream_t)stream>>>(S, B, R, BL, ldS, gamma1,
-                                                                                         (bf16*)alpha, (bf16*)alphaT);
+  XMC_ACT(act_f32, wl_softmax_kernel<T><<<dim3(ceil_div(ldS, 32), B), dim3(32, 8), 0, (cudaStream_t)stream>>>(
+                       S, B, R, BL, ldS, gamma1, (T*)alpha, (T*)alphaT));
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }
 
 extern "C" int xmc_wl_softmax_bwd(const void* alpha, const float* dalpha, int B, int R, int BL, int ldS, float gamma1,
-                                  void* dS, void* stream) {
+                                  void* dS, int act_f32, void* stream) {
   if (!alpha || !dalpha || !dS || B < 1 || R < 1 || BL < 1 || ldS < BL) return XMC_EINVAL;
-  wl_softmax_bwd_kernel<<<dim3(ceil_div(ldS, 32), B), dim3(32, 8), 0, (cudaStream_t)stream>>>(
-      (const bf16*)alpha, dalpha, B, R, BL, ldS, gamma1, (bf16*)dS);
+  XMC_ACT(act_f32, wl_softmax_bwd_kernel<T><<<dim3(ceil_div(ldS, 32), B), dim3(32, 8), 0, (cudaStream_t)stream>>>(
+                       (const T*)alpha, dalpha, B, R, BL, ldS, gamma1, (T*)dS));
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }
@@ -491,21 +497,22 @@ extern "C" int xmc_wl_sim(const float* cosv, const float* max_len, int B, int L,
 extern "C" int xmc_wl_cos_bwd(const float* dsim, const float* pw, const float* cosv, const float* cnorm,
                               const float* ctx, long long ctx_batch_stride, const float* words, const float* winv,
                               int B, int L, int D, float gamma3, void* dctx, long long dctx_batch_stride,
-                              void* stream) {
+                              int act_f32, void* stream) {
   if (!dsim || !pw || !cosv || !cnorm || !ctx || !words || !winv || !dctx || (D % 8)) return XMC_EINVAL;
   const long long n = (long long)B * B * L;
-  wl_cos_bwd_kernel<<<(unsigned)ceil_div_ll(n, 8), 256, 0, (cudaStream_t)stream>>>(
-      dsim, pw, cosv, cnorm, ctx, ctx_batch_stride, words, winv, B, L, D, gamma3, (bf16*)dctx, dctx_batch_stride);
+  XMC_ACT(act_f32, wl_cos_bwd_kernel<T><<<(unsigned)ceil_div_ll(n, 8), 256, 0, (cudaStream_t)stream>>>(
+                       dsim, pw, cosv, cnorm, ctx, ctx_batch_stride, words, winv, B, L, D, gamma3, (T*)dctx,
+                       dctx_batch_stride));
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }
 
-extern "C" int xmc_transpose_bf16(const void* src, int rows, int cols, int ld_src, void* dst, int ld_dst,
+extern "C" int xmc_transpose_bf16(const void* src, int act_f32, int rows, int cols, int ld_src, void* dst, int ld_dst,
                                   void* stream) {
   if (!src || !dst || rows < 1 || cols < 1) return XMC_EINVAL;
   // also zero-fills dst columns [rows, ld_dst)
-  transpose_bf16_kernel<<<dim3(ceil_div(cols, 32), ceil_div(ld_dst, 32)), dim3(32, 8), 0, (cudaStream_t)stream>>>(
-      (const bf16*)src, rows, cols, ld_src, (bf16*)dst, ld_dst);
+  XMC_ACT(act_f32, transpose_bf16_kernel<T><<<dim3(ceil_div(cols, 32), ceil_div(ld_dst, 32)), dim3(32, 8), 0,
+                                           (cudaStream_t)stream>>>((const T*)src, rows, cols, ld_src, (T*)dst, ld_dst));
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }

@@ -28,6 +28,34 @@ __device__ __forceinline__ void store8(bf16* p, const float* f) {
   *reinterpret_cast<uint4*>(p) = v;
 }
 
+// fp32 activations (config.dtype = "float32", the frozen ResNet branch): the same 8-channel vector interface, two
+// 16-byte accesses. Kernels are templates over the activation type T in {bf16, float}.
+__device__ __forceinline__ void load8(const float* p, float* f) {
+  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ void store8(float* p, const float* f) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
+}
+__device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float to_f(float v) { return v; }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16(v); }
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+
+// host-side dispatch on the activation type: XMC_ACT(f32, kernel<T><<<...>>>(...)) instantiates both
+#define XMC_ACT(f32, ...)            \
+  do {                               \
+    if (f32) {                       \
+      using T = float;               \
+      __VA_ARGS__;                   \
+    } else {                         \
+      using T = ::xmc::bf16;         \
+      __VA_ARGS__;                   \
+    }                                \
+  } while (0)
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -11,7 +11,8 @@ namespace xmc {
 // partials[gridDim.x][2C] ([c] = sum_p x[p][c], [C+c] = sum_p x[p][c]^2); sum_partials_kernel adds the rows in a fixed
 // order. No atomics anywhere: two runs on the same input are bit-identical.
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void bn_stats_kernel(const bf16* __restrict__ x, long long P, int C, int ld, float* __restrict__ partials) {
+template <typename T>
+__global__ void bn_stats_kernel(const T* __restrict__ x, long long P, int C, int ld, float* __restrict__ partials) {
   extern __shared__ float sm[];  // [lanes][cv*16]
   const int cv = C >> 3;
   const int cvb = min(cv - blockIdx.y * 256, 256);  // channel vectors handled by this blockIdx.y
@@ -92,8 +93,9 @@ __device__ __forceinline__ long long cond_row(const BnP& p, int n, int h, int w)
 
 // blockDim = (C/8 channel vectors, pixels per block): a thread keeps its channel vector for the whole loop, so
 // mean / rstd stay in registers and consecutive threads touch consecutive 16-byte vectors of the same pixel.
-__global__ void bn_apply_kernel(BnP p, const bf16* __restrict__ x, const float* __restrict__ mr,
-                                const bf16* __restrict__ gb, bf16* __restrict__ y) {
+template <typename T>
+__global__ void bn_apply_kernel(BnP p, const T* __restrict__ x, const float* __restrict__ mr,
+                                const T* __restrict__ gb, T* __restrict__ y) {
   const int c = threadIdx.x * 8;
   float mean[8], rstd[8];
 #pragma unroll
@@ -129,7 +131,8 @@ __global__ void bn_apply_kernel(BnP p, const bf16* __restrict__ x, const float* 
 }
 
 // gradient wrt the modulated/normalised tensor for one (pixel, 8 channels): returns g (post relu-mask, upsample-summed)
-__device__ __forceinline__ void bn_load_grad(const BnP& p, const bf16* dy, int n, int h, int w, int c, float* g) {
+template <typename T>
+__device__ __forceinline__ void bn_load_grad(const BnP& p, const T* dy, int n, int h, int w, int c, float* g) {
   if (p.upsample) {
     const int W2 = p.W * 2;
     const long long base = (((long long)n * p.H * 2 + 2 * h) * W2 + 2 * w) * p.C + c;
@@ -151,8 +154,10 @@ __device__ __forceinline__ void bn_load_grad(const BnP& p, const bf16* dy, int n
 // through shared memory in a fixed order. The per-channel BN terms S1 = sum dxhat, S2 = sum dxhat*xhat stay in
 // registers over ALL units of the thread, are combined per block in shared memory (fixed order) and leave as row
 // blockIdx.x of partials[gridDim.x][2C]; sum_partials_kernel finishes. No atomics: bit-identical from run to run.
-__global__ void bn_bwd_reduce_kernel(BnP p, const bf16* __restrict__ dy, const bf16* __restrict__ x,
-                                     const float* __restrict__ mr, const bf16* __restrict__ gb,
+template <typename T>
+__global__ void __launch_bounds__(512)
+bn_bwd_reduce_kernel(BnP p, const T* __restrict__ dy, const T* __restrict__ x,
+                                     const float* __restrict__ mr, const T* __restrict__ gb,
                                      float* __restrict__ dgb, float* __restrict__ partials, long long total_rows,
                                      int psplit, int rpi) {
   extern __shared__ float sm[];  // [rpi][cv][16]
@@ -244,9 +249,10 @@ __global__ void bn_bwd_reduce_kernel(BnP p, const bf16* __restrict__ dy, const b
   }
 }
 
-__global__ void bn_bwd_apply_kernel(BnP p, const bf16* __restrict__ dy, const bf16* __restrict__ x,
-                                    const float* __restrict__ mr, const bf16* __restrict__ gb,
-                                    const float* __restrict__ sums, float invP, bf16* __restrict__ dx) {
+template <typename T>
+__global__ void bn_bwd_apply_kernel(BnP p, const T* __restrict__ dy, const T* __restrict__ x,
+                                    const float* __restrict__ mr, const T* __restrict__ gb,
+                                    const float* __restrict__ sums, float invP, T* __restrict__ dx) {
   const int c = threadIdx.x * 8;
   float mean[8], rstd[8], m1[8], m2[8];
 #pragma unroll
@@ -285,9 +291,10 @@ __global__ void bn_bwd_apply_kernel(BnP p, const bf16* __restrict__ dy, const bf
 // 2x2 pooling (dsample, common.py:54-55 — scale 0.25; scale 1 gives the transpose of nearest upsample) and its
 // transpose.
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void pool2_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, const bf16* __restrict__ low,
-                             int N, int H, int W, int C, float scale, bf16* __restrict__ out,
-                             bf16* __restrict__ out_relu) {
+template <typename T>
+__global__ void pool2_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ low,
+                             int N, int H, int W, int C, float scale, T* __restrict__ out,
+                             T* __restrict__ out_relu) {
   const int cv = C >> 3;
   const long long total = (long long)N * H * W * cv;  // H,W are OUTPUT dims
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -334,8 +341,9 @@ __global__ void pool2_kernel(const bf16* __restrict__ a, const bf16* __restrict_
   }
 }
 
-__global__ void unpool2_kernel(const bf16* __restrict__ dout, int N, int H, int W, int C, float scale,
-                               bf16* __restrict__ g) {
+template <typename T>
+__global__ void unpool2_kernel(const T* __restrict__ dout, int N, int H, int W, int C, float scale,
+                               T* __restrict__ g) {
   const int cv = C >> 3;
   const long long total = (long long)N * H * W * cv;  // H,W are the LOW-res dims of dout
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -363,7 +371,8 @@ __global__ void unpool2_kernel(const bf16* __restrict__ dout, int N, int H, int 
 // out[c] += sum_p x[p][c]  (bias gradients). gridDim.x == 1: the block adds its sums to out directly; otherwise block b
 // stores them in row b of out (= partials[gridDim.x][C]) and sum_partials_kernel finishes in a fixed order.
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void colsum_kernel(const bf16* __restrict__ x, long long P, int C, int ld, float* __restrict__ out) {
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ x, long long P, int C, int ld, float* __restrict__ out) {
   extern __shared__ float sm[];
   const int cv = C >> 3;
   const int cvb = min(cv - blockIdx.y * 256, 256);
@@ -394,12 +403,13 @@ __global__ void colsum_kernel(const bf16* __restrict__ x, long long P, int C, in
 }
 
 // scalar fallback for channel counts that are not a multiple of 8 (the 3-channel image gradient)
-__global__ void colsum_scalar_kernel(const bf16* __restrict__ x, long long P, int C, int ld, float* __restrict__ out) {
+template <typename T>
+__global__ void colsum_scalar_kernel(const T* __restrict__ x, long long P, int C, int ld, float* __restrict__ out) {
   __shared__ float sm[256];
   const int c = blockIdx.y;
   float s = 0.f;
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x)
-    s += __bfloat162float(x[p * ld + c]);
+    s += to_f(x[p * ld + c]);
   sm[threadIdx.x] = s;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
@@ -415,7 +425,8 @@ __global__ void colsum_scalar_kernel(const bf16* __restrict__ x, long long P, in
 // ---------------------------------------------------------------------------------------------------------------------
 // x_pool[n][c] = sum_hw relu(x[n][hw][c])   (xmc_net.py:97-98) and its backward
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void relu_sumhw_kernel(const bf16* __restrict__ x, int HW, int C, float* __restrict__ out) {
+template <typename T>
+__global__ void relu_sumhw_kernel(const T* __restrict__ x, int HW, int C, float* __restrict__ out) {
   const int n = blockIdx.y;
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (c >= C) return;
@@ -432,8 +443,9 @@ __global__ void relu_sumhw_kernel(const bf16* __restrict__ x, int HW, int C, flo
   for (int i = 0; i < 8; ++i) out[(long long)n * C + c + i] = s[i];
 }
 
-__global__ void relu_sumhw_bwd_kernel(const bf16* __restrict__ x, const float* __restrict__ dout, int HW, int C,
-                                      bf16* __restrict__ dx) {
+template <typename T>
+__global__ void relu_sumhw_bwd_kernel(const T* __restrict__ x, const float* __restrict__ dout, int HW, int C,
+                                      T* __restrict__ dx) {
   const int n = blockIdx.y;
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (c >= C) return;
@@ -476,8 +488,9 @@ __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ src, long long row
 }
 
 // dst[(b*reps + r)][c] = src[b][c]
-__global__ void bcast_rows_kernel(const bf16* __restrict__ src, int B, int reps, int cols, int ld_src,
-                                  bf16* __restrict__ dst, int ld_dst) {
+template <typename T>
+__global__ void bcast_rows_kernel(const T* __restrict__ src, int B, int reps, int cols, int ld_src,
+                                  T* __restrict__ dst, int ld_dst) {
   const long long total = (long long)B * reps * cols;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -489,14 +502,39 @@ __global__ void bcast_rows_kernel(const bf16* __restrict__ src, int B, int reps,
 }
 
 // dst[b][c] (+)= sum_r src[(b*reps + r)][c]
-__global__ void sum_rows_kernel(const bf16* __restrict__ src, int B, int reps, int cols, int ld_src,
+template <typename T>
+__global__ void sum_rows_kernel(const T* __restrict__ src, int B, int reps, int cols, int ld_src,
                                 float* __restrict__ dst, int ld_dst, int accumulate) {
   const int b = blockIdx.y;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cols) return;
   float s = 0.f;
-  for (int r = 0; r < reps; ++r) s += __bfloat162float(src[((long long)b * reps + r) * ld_src + c]);
+  for (int r = 0; r < reps; ++r) s += to_f(src[((long long)b * reps + r) * ld_src + c]);
   if (accumulate) dst[(long long)b * ld_dst + c] += s; else dst[(long long)b * ld_dst + c] = s;
+}
+
+// fp32 -> bf16 [hi | lo | hi] split along the channel axis: dst[r][0:C] = hi = bf16(x), dst[r][C:2C] = lo = bf16(x - hi),
+// dst[r][2C:3C] = hi. This is the A operand of the tensor-core GEMMs in fp32-activation mode (XmcConvDesc.act_f32): with
+// the weights stored as [hi | hi | lo] the K-concatenated product is hi*hi + lo*hi + hi*lo, fp32-accumulated, i.e. 16
+// mantissa bits per operand. The weight-gradient GEMM reads the hi and lo parts as two pitched views of the same buffer.
+// weights = 1 gives the B-operand order [hi | hi | lo] instead.
+__global__ void split3_kernel(const float* __restrict__ src, long long rows, int C, long long ld_src, int weights,
+                              bf16* __restrict__ dst, long long ld_dst) {
+  const int cv = C >> 3;
+  const long long total = rows * cv;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / cv;
+    const int c = (int)(idx - r * cv) * 8;
+    float f[8], lo[8];
+    load8(src + r * ld_src + c, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) lo[i] = f[i] - __bfloat162float(__float2bfloat16(f[i]));
+    bf16* o = dst + r * ld_dst + c;
+    store8(o, f);
+    store8(o + C, weights ? f : lo);
+    store8(o + 2 * C, weights ? lo : f);
+  }
 }
 
 static int grid_for(long long total, int block) {
@@ -589,15 +627,16 @@ extern "C" int xmc_sum_partials(const float* partials, int rows, int width, floa
   return launch_sum_partials(partials, rows, width, out, accumulate, (cudaStream_t)stream);
 }
 
-extern "C" int xmc_bn_stats(const void* x, long long P, int C, int ld, float* sums, float* partials, int rows,
-                            void* stream) {
+extern "C" int xmc_bn_stats(const void* x, int act_f32, long long P, int C, int ld, float* sums, float* partials,
+                            int rows, void* stream) {
   if (!x || !sums || !partials || rows < 1 || P < 1 || C < 8 || (C % 8) || (ld % 8)) return XMC_EINVAL;
   const int cv = C / 8;
   const int ny = ceil_div(cv, 256);
   const int cvb = cv < 256 ? cv : 256;
   const int lanes = 256 / cvb;
   const size_t smem = (size_t)lanes * cvb * 16 * sizeof(float);
-  bn_stats_kernel<<<dim3((unsigned)rows, ny), 256, smem, (cudaStream_t)stream>>>((const bf16*)x, P, C, ld, partials);
+  XMC_ACT(act_f32, bn_stats_kernel<T><<<dim3((unsigned)rows, ny), 256, smem, (cudaStream_t)stream>>>((const T*)x, P, C, ld,
+                                                                                               partials));
   XMC_LAUNCH_CHECK();
   return launch_sum_partials(partials, rows, 2 * C, sums, 0, (cudaStream_t)stream);
 }
@@ -630,7 +669,8 @@ extern "C" int xmc_bn_apply(const XmcBnDesc* d, const void* x, const float* mean
   if (p.C / 8 > 1024) return XMC_EINVAL;
   dim3 grid, block;
   bn_launch_dims(p, &grid, &block);
-  bn_apply_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(p, (const bf16*)x, mean_rstd, (const bf16*)gb, (bf16*)y);
+  XMC_ACT(d->act_f32, bn_apply_kernel<T><<<grid, block, 0, (cudaStream_t)stream>>>(p, (const T*)x, mean_rstd,
+                                                                                (const T*)gb, (T*)y));
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }
@@ -649,7 +689,7 @@ extern "C" int xmc_bn_bwd_reduce(const XmcBnDesc* d, const void* dy, const void*
   if (p.Hc == 1) {
     const int side = 1 << p.s;
     psplit = side < 8 ? side : 8;
-    while (psplit > 1 && cv * psplit > 768) psplit >>= 1;
+    while (psplit > 1 && cv * psplit > 512) psplit >>= 1;
   }
   // block = rpi units x cv channel vectors (rpi a multiple of psplit); every thread streams over its units
   int rpi = cv >= 256 ? 1 : 256 / cv;
@@ -657,11 +697,11 @@ extern "C" int xmc_bn_bwd_reduce(const XmcBnDesc* d, const void* dy, const void*
   if (rpi < psplit) rpi = psplit;
   const int threads = cv * rpi;
   const size_t smem = (size_t)threads * 16 * sizeof(float);
-  if (threads > 1024 || smem > 48 * 1024) return XMC_EINVAL;
+  if (threads > 512 || smem > 48 * 1024) return XMC_EINVAL;
   long long gx = ceil_div_ll(cond_rows * psplit, rpi);
   if (gx > rows) gx = rows;
-  bn_bwd_reduce_kernel<<<(unsigned)gx, threads, smem, (cudaStream_t)stream>>>(
-      p, (const bf16*)dy, (const bf16*)x, mean_rstd, (const bf16*)gb, dgb, partials, cond_rows, psplit, rpi);
+  XMC_ACT(d->act_f32, bn_bwd_reduce_kernel<T><<<(unsigned)gx, threads, smem, (cudaStream_t)stream>>>(
+                          p, (const T*)dy, (const T*)x, mean_rstd, (const T*)gb, dgb, partials, cond_rows, psplit, rpi));
   XMC_LAUNCH_CHECK();
   return launch_sum_partials(partials, (int)gx, 2 * p.C, sums, 0, (cudaStream_t)stream);
 }
@@ -676,32 +716,33 @@ extern "C" int xmc_bn_bwd_apply(const XmcBnDesc* d, const void* dy, const void* 
   const float invP = 1.f / (float)((long long)p.N * p.H * p.W * (d->replicas > 1 ? d->replicas : 1));
   dim3 grid, block;
   bn_launch_dims(p, &grid, &block);
-  bn_bwd_apply_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(
-      p, (const bf16*)dy, (const bf16*)x, mean_rstd, (const bf16*)gb, sums, invP, (bf16*)dx);
+  XMC_ACT(d->act_f32, bn_bwd_apply_kernel<T><<<grid, block, 0, (cudaStream_t)stream>>>(
+                          p, (const T*)dy, (const T*)x, mean_rstd, (const T*)gb, sums, invP, (T*)dx));
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }
 
-extern "C" int xmc_pool2(const void* a, const void* b, const void* low, int N, int Hout, int Wout, int C, float scale,
-                         void* out, void* out_relu, void* stream) {
+extern "C" int xmc_pool2(const void* a, const void* b, const void* low, int act_f32, int N, int Hout, int Wout, int C,
+                         float scale, void* out, void* out_relu, void* stream) {
   if (!a || !out || N < 1 || Hout < 1 || Wout < 1 || C < 8 || (C % 8)) return XMC_EINVAL;
   const long long total = (long long)N * Hout * Wout * (C / 8);
-  pool2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const bf16*)a, (const bf16*)b, (const bf16*)low, N, Hout, Wout, C, scale, (bf16*)out, (bf16*)out_relu);
+  XMC_ACT(act_f32, pool2_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                       (const T*)a, (const T*)b, (const T*)low, N, Hout, Wout, C, scale, (T*)out, (T*)out_relu));
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }
 
-extern "C" int xmc_unpool2(const void* dout, int N, int Hin, int Win, int C, float scale, void* g, void* stream) {
+extern "C" int xmc_unpool2(const void* dout, int act_f32, int N, int Hin, int Win, int C, float scale, void* g,
+                           void* stream) {
   if (!dout || !g || N < 1 || Hin < 1 || Win < 1 || C < 8 || (C % 8)) return XMC_EINVAL;
   const long long total = (long long)N * Hin * Win * (C / 8);
-  unpool2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)dout, N, Hin, Win, C, scale,
-                                                                        (bf16*)g);
+  XMC_ACT(act_f32, unpool2_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)dout, N, Hin, Win,
+                                                                                        C, scale, (T*)g));
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }
 
-extern "C" int xmc_colsum(const void* x, long long P, int C, int ld, float* out, float* partials, int rows,
+extern "C" int xmc_colsum(const void* x, int act_f32, long long P, int C, int ld, float* out, float* partials, int rows,
                           void* stream) {
   if (!x || !out || P < 1 || C < 1 || rows < 1 || (rows > 1 && !partials)) return XMC_EINVAL;
   // one block (per channel group) adds straight into out; several blocks leave partial rows that are added in order
@@ -709,8 +750,8 @@ extern "C" int xmc_colsum(const void* x, long long P, int C, int ld, float* out,
     long long gx = ceil_div_ll(P, 256 * 16);
     if (gx > rows) gx = rows;
     if (gx < 1) gx = 1;
-    colsum_scalar_kernel<<<dim3((unsigned)gx, C), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, P, C, ld,
-                                                                                 gx == 1 ? out : partials);
+    XMC_ACT(act_f32, colsum_scalar_kernel<T><<<dim3((unsigned)gx, C), 256, 0, (cudaStream_t)stream>>>(
+                         (const T*)x, P, C, ld, gx == 1 ? out : partials));
     XMC_LAUNCH_CHECK();
     return gx == 1 ? XMC_OK : launch_sum_partials(partials, (int)gx, C, out, 1, (cudaStream_t)stream);
   }
@@ -722,23 +763,35 @@ extern "C" int xmc_colsum(const void* x, long long P, int C, int ld, float* out,
   if (gx > rows) gx = rows;
   if (gx < 1) gx = 1;
   const size_t smem = (size_t)lanes * cvb * 8 * sizeof(float);
-  colsum_kernel<<<dim3((unsigned)gx, ny), 256, smem, (cudaStream_t)stream>>>((const bf16*)x, P, C, ld,
-                                                                            gx == 1 ? out : partials);
+  XMC_ACT(act_f32, colsum_kernel<T><<<dim3((unsigned)gx, ny), 256, smem, (cudaStream_t)stream>>>(
+                       (const T*)x, P, C, ld, gx == 1 ? out : partials));
   XMC_LAUNCH_CHECK();
   return gx == 1 ? XMC_OK : launch_sum_partials(partials, (int)gx, C, out, 1, (cudaStream_t)stream);
 }
 
-extern "C" int xmc_relu_sumhw(const void* x, int N, int HW, int C, float* out, void* stream) {
+extern "C" int xmc_relu_sumhw(const void* x, int act_f32, int N, int HW, int C, float* out, void* stream) {
   if (!x || !out || N < 1 || HW < 1 || C < 8 || (C % 8)) return XMC_EINVAL;
-  relu_sumhw_kernel<<<dim3(ceil_div(C / 8, 64), N), 64, 0, (cudaStream_t)stream>>>((const bf16*)x, HW, C, out);
+  XMC_ACT(act_f32, relu_sumhw_kernel<T><<<dim3(ceil_div(C / 8, 64), N), 64, 0, (cudaStream_t)stream>>>((const T*)x, HW, C,
+                                                                                                  out));
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }
 
-extern "C" int xmc_relu_sumhw_bwd(const void* x, const float* dout, int N, int HW, int C, void* dx, void* stream) {
+extern "C" int xmc_relu_sumhw_bwd(const void* x, int act_f32, const float* dout, int N, int HW, int C, void* dx,
+                                  void* stream) {
   if (!x || !dout || !dx || N < 1 || HW < 1 || C < 8 || (C % 8)) return XMC_EINVAL;
-  relu_sumhw_bwd_kernel<<<dim3(ceil_div(C / 8, 64), N), 64, 0, (cudaStream_t)stream>>>((const bf16*)x, dout, HW, C,
-                                                                                      (bf16*)dx);
+  XMC_ACT(act_f32, relu_sumhw_bwd_kernel<T><<<dim3(ceil_div(C / 8, 64), N), 64, 0, (cudaStream_t)stream>>>(
+                       (const T*)x, dout, HW, C, (T*)dx));
+  XMC_LAUNCH_CHECK();
+  return XMC_OK;
+}
+
+extern "C" int xmc_split3(const float* src, long long rows, int C, long long ld_src, int weights, void* dst,
+                          long long ld_dst, void* stream) {
+  if (!src || !dst || rows < 1 || C < 8 || (C % 8) || (ld_src % 4) || (ld_dst % 8) || ld_dst < 3 * C) return XMC_EINVAL;
+  if (!aligned16(src) || !aligned16(dst)) return XMC_EALIGN;
+  split3_kernel<<<grid_for(rows * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>(src, rows, C, ld_src, weights,
+                                                                                (bf16*)dst, ld_dst);
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }
@@ -761,20 +814,20 @@ extern "C" int xmc_cast_bf16_to_f32(const void* src, long long rows, int cols, l
   return XMC_OK;
 }
 
-extern "C" int xmc_bcast_rows(const void* src, int B, int reps, int cols, int ld_src, void* dst, int ld_dst,
-                              void* stream) {
+extern "C" int xmc_bcast_rows(const void* src, int act_f32, int B, int reps, int cols, int ld_src, void* dst,
+                              int ld_dst, void* stream) {
   if (!src || !dst || B < 1 || reps < 1 || cols < 1) return XMC_EINVAL;
-  bcast_rows_kernel<<<grid_for((long long)B * reps * cols, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const bf16*)src, B, reps, cols, ld_src, (bf16*)dst, ld_dst);
+  XMC_ACT(act_f32, bcast_rows_kernel<T><<<grid_for((long long)B * reps * cols, 256), 256, 0, (cudaStream_t)stream>>>(
+                       (const T*)src, B, reps, cols, ld_src, (T*)dst, ld_dst));
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }
 
-extern "C" int xmc_sum_rows(const void* src, int B, int reps, int cols, int ld_src, float* dst, int ld_dst,
-                            int accumulate, void* stream) {
+extern "C" int xmc_sum_rows(const void* src, int act_f32, int B, int reps, int cols, int ld_src, float* dst,
+                            int ld_dst, int accumulate, void* stream) {
   if (!src || !dst || B < 1 || reps < 1 || cols < 1) return XMC_EINVAL;
-  sum_rows_kernel<<<dim3(ceil_div(cols, 128), B), 128, 0, (cudaStream_t)stream>>>((const bf16*)src, B, reps, cols,
-                                                                                 ld_src, dst, ld_dst, accumulate);
+  XMC_ACT(act_f32, sum_rows_kernel<T><<<dim3(ceil_div(cols, 128), B), 128, 0, (cudaStream_t)stream>>>(
+                       (const T*)src, B, reps, cols, ld_src, dst, ld_dst, accumulate));
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }

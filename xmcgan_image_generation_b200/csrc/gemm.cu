@@ -49,8 +49,8 @@ struct FwdParams {
   void* out;
   int out_dtype, ldOut;
   const float* bias;
-  const bf16* residual;
-  const bf16* mask;
+  const void* residual;  // bf16, or fp32 in the kF32 instantiation
+  const void* mask;
   int ldRes, ldMask, res_shift, relu, mask_last;
   float alpha;
   int vec_ok;
@@ -116,7 +116,7 @@ __device__ __forceinline__ void fwd_epilogue_tile_lean(const FwdParams& p, uint3
   const int ncols = p.Cout - col0;
   const float* b_row = bias_s + col0;
   bf16* o_row = reinterpret_cast<bf16*>(p.out) + pix * p.ldOut + col0;
-  const bf16* r_row = kRes ? p.residual + rpix * p.ldRes + col0 : nullptr;
+  const bf16* r_row = kRes ? reinterpret_cast<const bf16*>(p.residual) + rpix * p.ldRes + col0 : nullptr;
   const bool relu = p.relu != 0;
   for (int c0 = half * 16; c0 < p.BN; c0 += 16 * kEpiParts) {
     uint32_t v[16];
@@ -161,36 +161,40 @@ __device__ __forceinline__ void fwd_epilogue_tile_lean(const FwdParams& p, uint3
 // Epilogue of one 128 x BN output tile for one warp: t_addr = TMEM address of the warp's 32 lanes in the tile's
 // accumulator, (row_ok, pix, rpix) = this lane's output row, `part` = which of the kEpiParts warps sharing the lane
 // quarter this is. Shared by the streaming and the resident-weights forward kernels.
+// kF32: the fp32-activation instantiation (config.dtype = "float32" / the frozen ResNet branch): residual and mask are
+// fp32 tensors (16 columns = 64 bytes = two 32-byte accesses each), the output is fp32.
+template <bool kF32>
 __device__ __forceinline__ void fwd_epilogue_tile(const FwdParams& p, uint32_t t_addr, int nt, bool row_ok,
                                                   long long pix, long long rpix, const float* bias_s, int half) {
+  constexpr int kV = kF32 ? 4 : 2;  // uint4 vectors per 16-column chunk of a mask / residual row
   // One 16-column chunk = issue (TMEM load + the chunk's mask / residual vectors) ... finish (fused math, store).
   // The chunks of a warp are software-pipelined over two register sets: chunk i+1 is issued before chunk i is
   // finished, so its TMEM / global latency hides behind the math and the stores of chunk i.
-  auto issue = [&](int c0, uint32_t (&v)[16], uint4 (&mk)[2], uint4 (&rs)[2]) {
+  auto load16 = [&](const void* base, long long elem, uint4 (&dst)[kV]) {
+    const char* ptr = reinterpret_cast<const char*>(base) + elem * (kF32 ? 4 : 2);
+    if (p.vec_ok == 2) {
+#pragma unroll
+      for (int i = 0; i < kV; i += 2) ldg256(ptr + 16 * i, dst[i], dst[i + 1]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < kV; ++i) dst[i] = __ldg(reinterpret_cast<const uint4*>(ptr) + i);
+    }
+  };
+  // element i (0..15) of a loaded row chunk as float
+  auto elem = [&](const uint4 (&src)[kV], int i) -> float {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(src);
+    if (kF32) return __uint_as_float(w[i]);
+    return (i & 1) ? bf16_bits_to_float(w[i >> 1] >> 16) : bf16_bits_to_float(w[i >> 1] & 0xFFFFu);
+  };
+  auto issue = [&](int c0, uint32_t (&v)[16], uint4 (&mk)[kV], uint4 (&rs)[kV]) {
     tmem_ld16(t_addr + c0, v);  // asynchronous until tmem_ld_wait
     const int col = nt * p.BN + c0;
     if (row_ok && p.vec_ok && p.Cout - col >= 16) {
-      if (p.mask) {
-        const bf16* mp = p.mask + pix * p.ldMask + col;
-        if (p.vec_ok == 2) {
-          ldg256(mp, mk[0], mk[1]);
-        } else {
-          mk[0] = __ldg(reinterpret_cast<const uint4*>(mp));
-          mk[1] = __ldg(reinterpret_cast<const uint4*>(mp) + 1);
-        }
-      }
-      if (p.residual) {
-        const bf16* rp = p.residual + rpix * p.ldRes + col;
-        if (p.vec_ok == 2) {
-          ldg256(rp, rs[0], rs[1]);
-        } else {
-          rs[0] = __ldg(reinterpret_cast<const uint4*>(rp));
-          rs[1] = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
-        }
-      }
+      if (p.mask) load16(p.mask, pix * p.ldMask + col, mk);
+      if (p.residual) load16(p.residual, rpix * p.ldRes + col, rs);
     }
   };
-  auto finish = [&](int c0, const uint32_t (&v)[16], const uint4 (&mk)[2], const uint4 (&rs)[2]) {
+  auto finish = [&](int c0, const uint32_t (&v)[16], const uint4 (&mk)[kV], const uint4 (&rs)[kV]) {
     const int col = nt * p.BN + c0;
     const bool active = row_ok && col < p.Cout;
     const int nvalid = min(16, p.Cout - col);
@@ -209,30 +213,29 @@ __device__ __forceinline__ void fwd_epilogue_tile(const FwdParams& p, uint32_t t
           f[4 * i] += bz.x; f[4 * i + 1] += bz.y; f[4 * i + 2] += bz.z; f[4 * i + 3] += bz.w;
         }
       }
-      const uint32_t rw_[8] = {rs[0].x, rs[0].y, rs[0].z, rs[0].w, rs[1].x, rs[1].y, rs[1].z, rs[1].w};
       if (p.residual && p.mask_last) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          f[2 * i] += bf16_bits_to_float(rw_[i] & 0xFFFFu);
-          f[2 * i + 1] += bf16_bits_to_float(rw_[i] >> 16);
-        }
+        for (int i = 0; i < 16; ++i) f[i] += elem(rs, i);
       }
       if (p.mask) {
-        const uint32_t mw[8] = {mk[0].x, mk[0].y, mk[0].z, mk[0].w, mk[1].x, mk[1].y, mk[1].z, mk[1].w};
+        if (kF32) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          // bf16 > 0  <=>  sign bit clear and magnitude non-zero
-          const uint32_t lo = mw[i] & 0xFFFFu, hi = mw[i] >> 16;
-          if (!(lo != 0 && lo < 0x8000u)) f[2 * i] = 0.f;
-          if (!(hi != 0 && hi < 0x8000u)) f[2 * i + 1] = 0.f;
+          for (int i = 0; i < 16; ++i)
+            if (!(elem(mk, i) > 0.f)) f[i] = 0.f;
+        } else {
+          const uint32_t* mw = reinterpret_cast<const uint32_t*>(mk);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+            const uint32_t lo = mw[i] & 0xFFFFu, hi = mw[i] >> 16;
+            if (!(lo != 0 && lo < 0x8000u)) f[2 * i] = 0.f;
+            if (!(hi != 0 && hi < 0x8000u)) f[2 * i + 1] = 0.f;
+          }
         }
       }
       if (p.residual && !p.mask_last) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          f[2 * i] += bf16_bits_to_float(rw_[i] & 0xFFFFu);
-          f[2 * i + 1] += bf16_bits_to_float(rw_[i] >> 16);
-        }
+        for (int i = 0; i < 16; ++i) f[i] += elem(rs, i);
       }
       if (p.relu) {
 #pragma unroll
@@ -265,6 +268,9 @@ __device__ __forceinline__ void fwd_epilogue_tile(const FwdParams& p, uint32_t t
       }
     } else if (active) {
       // generic path (ragged N edge or unaligned pitches): scalar accesses
+      auto rd = [&](const void* base, long long e) -> float {
+        return kF32 ? reinterpret_cast<const float*>(base)[e] : __bfloat162float(reinterpret_cast<const bf16*>(base)[e]);
+      };
       float f[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
@@ -272,9 +278,9 @@ __device__ __forceinline__ void fwd_epilogue_tile(const FwdParams& p, uint32_t t
       for (int i = 0; i < 16; ++i) {
         if (i < nvalid) {
           if (p.bias) f[i] += p.bias[col + i];
-          if (p.residual && p.mask_last) f[i] += __bfloat162float(p.residual[rpix * p.ldRes + col + i]);
-          if (p.mask && !(__bfloat162float(p.mask[pix * p.ldMask + col + i]) > 0.f)) f[i] = 0.f;
-          if (p.residual && !p.mask_last) f[i] += __bfloat162float(p.residual[rpix * p.ldRes + col + i]);
+          if (p.residual && p.mask_last) f[i] += rd(p.residual, rpix * p.ldRes + col + i);
+          if (p.mask && !(rd(p.mask, pix * p.ldMask + col + i) > 0.f)) f[i] = 0.f;
+          if (p.residual && !p.mask_last) f[i] += rd(p.residual, rpix * p.ldRes + col + i);
           if (p.relu) f[i] = fmaxf(f[i], 0.f);
           if (p.out_dtype == 0) reinterpret_cast<bf16*>(p.out)[pix * p.ldOut + col + i] = __float2bfloat16(f[i]);
           else reinterpret_cast<float*>(p.out)[pix * p.ldOut + col + i] = f[i];
@@ -284,7 +290,7 @@ __device__ __forceinline__ void fwd_epilogue_tile(const FwdParams& p, uint32_t t
   };
   constexpr int kStep = 16 * kEpiParts;
   uint32_t va[16], vb[16];
-  uint4 mka[2], mkb[2], rsa[2], rsb[2];
+  uint4 mka[kV], mkb[kV], rsa[kV], rsb[kV];
   int c0 = half * 16;
   if (c0 < p.BN) issue(c0, va, mka, rsa);
   while (c0 < p.BN) {  // all conditions are warp-uniform (tcgen05.ld / wait::ld are .sync.aligned)
@@ -303,7 +309,7 @@ __device__ __forceinline__ void fwd_epilogue_tile(const FwdParams& p, uint32_t t
 // =====================================================================================================================
 // Forward / dgrad / dense / batched GEMM:  D[pixels, Cout] = sum_taps A_tap[pixels, C] * B[Cout, tap*C + c]
 // =====================================================================================================================
-template <int kMode>  // 0: generic epilogue; 1 / 2: lean epilogue (bias [+ residual]), see fwd_epilogue_tile_lean
+template <int kMode>  // 0: generic epilogue; 1 / 2: lean epilogue (bias [+ residual]); 3: fp32 residual / mask / output
 __global__ void __launch_bounds__(kThreadsFwd, 1)
 gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -457,7 +463,8 @@ gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
       if (kMode == 1) fwd_epilogue_tile_lean<false>(p, t_addr, nt, row_ok, pix, rpix, bias_s, half);
       else if (kMode == 2) fwd_epilogue_tile_lean<true>(p, t_addr, nt, row_ok, pix, rpix, bias_s, half);
-      else fwd_epilogue_tile(p, t_addr, nt, row_ok, pix, rpix, bias_s, half);
+      else if (kMode == 3) fwd_epilogue_tile<true>(p, t_addr, nt, row_ok, pix, rpix, bias_s, half);
+      else fwd_epilogue_tile<false>(p, t_addr, nt, row_ok, pix, rpix, bias_s, half);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -636,7 +643,7 @@ conv3x3_resident_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           rpix = ((long long)n * Hs + (h >> p.res_shift)) * Ws + (w >> p.res_shift);
         }
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + r * 128;
-        fwd_epilogue_tile(p, t_addr, 0, row_ok, pix, rpix, bias_s, half);
+        fwd_epilogue_tile<false>(p, t_addr, 0, row_ok, pix, rpix, bias_s, half);
       }
       tc_fence_before();
       __syncwarp();
@@ -1083,6 +1090,8 @@ static cudaError_t ensure_smem_attr(int kind) {
         e = cudaFuncSetAttribute(gemm_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFwd);
       if (e == cudaSuccess)
         e = cudaFuncSetAttribute(gemm_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFwd);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(gemm_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFwd);
       break;
     case kAttrRes:
       e = cudaFuncSetAttribute(conv3x3_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemRes);
@@ -1130,18 +1139,23 @@ extern "C" int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* w
   p.idesc = make_idesc_bf16(128, p.BN, 0, 0);
   p.stage_tx_bytes = (uint32_t)(64 * p.tw * p.th * p.tn * 2 + 64 * p.BN * 2);
   p.out = y; p.out_dtype = d->out_dtype; p.ldOut = d->ldOut;
-  p.bias = bias; p.residual = (const bf16*)residual; p.mask = (const bf16*)mask;
+  p.bias = bias; p.residual = residual; p.mask = mask;
+  // fp32 activations: residual / mask are fp32 tensors and the output must be fp32 (the A operand is the bf16
+  // [hi | lo | hi] split of the fp32 input, made by xmc_split3; see XmcConvDesc.act_f32)
+  const bool f32io = d->act_f32 != 0;
+  if (f32io && d->out_dtype != 1) return XMC_EINVAL;
+  const int rm_unit = f32io ? 4 : 8;  // residual / mask elements per 16 bytes
   p.ldRes = d->ldRes; p.ldMask = d->ldMask; p.res_shift = d->res_shift; p.relu = d->relu;
   p.mask_last = d->mask_last;
   p.alpha = d->alpha;
   bool vec = aligned16(y) && (d->out_dtype == 0 ? (d->ldOut % 8 == 0) : (d->ldOut % 4 == 0));
-  if (residual) vec = vec && aligned16(residual) && (d->ldRes % 8 == 0);
-  if (mask) vec = vec && aligned16(mask) && (d->ldMask % 8 == 0);
+  if (residual) vec = vec && aligned16(residual) && (d->ldRes % rm_unit == 0);
+  if (mask) vec = vec && aligned16(mask) && (d->ldMask % rm_unit == 0);
   // 32-byte accesses when every pointer and pitch allows it (16 bf16 / 8 fp32 columns per access)
   auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
   bool vec32 = vec && al32(y) && (d->out_dtype == 0 ? (d->ldOut % 16 == 0) : (d->ldOut % 8 == 0));
-  if (residual) vec32 = vec32 && al32(residual) && (d->ldRes % 16 == 0);
-  if (mask) vec32 = vec32 && al32(mask) && (d->ldMask % 16 == 0);
+  if (residual) vec32 = vec32 && al32(residual) && (d->ldRes % (2 * rm_unit) == 0);
+  if (mask) vec32 = vec32 && al32(mask) && (d->ldMask % (2 * rm_unit) == 0);
   p.vec_ok = vec32 ? 2 : (vec ? 1 : 0);
   p.bias_smem = (bias && d->Cout <= kBiasMax && aligned16(bias)) ? 1 : 0;
 
@@ -1149,7 +1163,7 @@ extern "C" int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* w
   // XMC_RESIDENT=0 switches the path off (debugging aid; process-global, read once)
   static const int resident_mode = [] { const char* e = getenv("XMC_RESIDENT"); return e ? atoi(e) : 1; }();
   const int bn_res = ceil_div(d->Cout, 16) * 16;
-  const bool res_ok = resident_mode > 0 && d->KH == 3 && d->KW == 3 && d->pad_h == 1 && d->pad_w == 1 &&
+  const bool res_ok = resident_mode > 0 && !f32io && d->KH == 3 && d->KW == 3 && d->pad_h == 1 && d->pad_w == 1 &&
                       p.strideH == 1 && p.strideW == 1 && !d->batched && !d->subpixel && d->pitchW <= 0 &&
                       d->Hin <= 0 && d->Win <= 0 && (d->W % 128) == 0 && (d->H % 2) == 0 && d->C <= 96 &&
                       (d->C % 16) == 0 && bn_res <= 128 && 9 * (bn_res * 128 + (d->C > 64 ? bn_res * 64 : 0)) <= kResBBytes;
@@ -1218,7 +1232,9 @@ extern "C" int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* w
   auto al32p = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
   const bool lean = lean_mode && p.bias_smem && !mask && d->alpha == 1.f && d->out_dtype == 0 && p.vec_ok == 2 &&
                     (d->Cout % 16) == 0 && (!residual || al32p(residual));
-  if (lean && !residual)
+  if (f32io)
+    gemm_fwd_kernel<3><<<grid, kThreadsFwd, kSmemFwd, (cudaStream_t)stream>>>(tmA, tmB, p);
+  else if (lean && !residual)
     gemm_fwd_kernel<1><<<grid, kThreadsFwd, kSmemFwd, (cudaStream_t)stream>>>(tmA, tmB, p);
   else if (lean)
     gemm_fwd_kernel<2><<<grid, kThreadsFwd, kSmemFwd, (cudaStream_t)stream>>>(tmA, tmB, p);

@@ -43,7 +43,7 @@ extern "C" const char* xmc_strerror(int code) {
 }
 
 extern "C" const char* xmc_last_cuda_error(void) { return xmc::g_err; }
-extern "C" int xmc_version(void) { return 101; }
+extern "C" int xmc_version(void) { return 200; }
 extern "C" int xmc_sizeof(int which) {
   switch (which) {
     case 0: return (int)sizeof(XmcConvDesc);

@@ -34,8 +34,10 @@ __device__ __forceinline__ int resize_taps(int o, int S, float inv_scale, float 
 
 // Writes a zero-bordered, 8-channel bf16 buffer [N, Tp, Tp, 8] (image at offset pad_lo) so that the stride-2 7x7 stem
 // can read (kw, c) as one contiguous 56-element run per output pixel.
+// split = 1 (fp32 mode): channels 3..5 hold the bf16 remainders lo = x - hi of channels 0..2, which the stem GEMM
+// multiplies with the same weights (see ResNetEngine: pass 1 [w_hi, w_hi], pass 2 [w_lo, 0]).
 __global__ void resize_bilinear_pad_kernel(const float* __restrict__ img, int N, int S, int T, int Tp, int pad_lo,
-                                           bf16* __restrict__ out) {
+                                           int split, bf16* __restrict__ out) {
   const long long total = (long long)N * Tp * Tp;
   const float inv_scale = (float)S / (float)T;
   const float ks = fmaxf(inv_scale, 1.f);
@@ -63,6 +65,10 @@ __global__ void resize_bilinear_pad_kernel(const float* __restrict__ img, int N,
           o[0] += wgt * px[0]; o[1] += wgt * px[1]; o[2] += wgt * px[2];
         }
       }
+    }
+    if (split) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) o[3 + c] = o[c] - __bfloat162float(__float2bfloat16(o[c]));
     }
     store8(out + idx * 8, o);
   }
@@ -129,13 +135,15 @@ __global__ void resize_bilinear_bwd_kernel(const float* __restrict__ dout, int N
 // Input gradient of the 7x7 stride-2 stem (SAME padding low=2). One thread computes 4 input pixels of the same column
 // parity in one row (x, x+2, x+4, x+6): they use the same filter taps, so every weight vector read from shared memory
 // feeds 4 pixels. wk: bf16 [Cout][7*56] with k = kh*56 + kw*8 + c (the packed forward weights), dy: [N,Ho,Ho,Cout].
+template <typename TA>
 __global__ void __launch_bounds__(128)
-stem_dgrad_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ wk, int N, int T, int Ho, int Cout, int pad_lo,
-                  float* __restrict__ dimg) {
+stem_dgrad_kernel(const TA* __restrict__ dy, const bf16* __restrict__ wk, const bf16* __restrict__ wk_lo, int N, int T,
+                  int Ho, int Cout, int pad_lo, float* __restrict__ dimg) {
   extern __shared__ float ws[];  // [7][7][3][Cout]
   for (int t = threadIdx.x; t < 49 * 3 * Cout; t += blockDim.x) {
     const int co = t % Cout, c = (t / Cout) % 3, kw = (t / (Cout * 3)) % 7, kh = t / (Cout * 21);
-    ws[t] = __bfloat162float(wk[(long long)co * 392 + kh * 56 + kw * 8 + c]);
+    const long long wi = (long long)co * 392 + kh * 56 + kw * 8 + c;
+    ws[t] = __bfloat162float(wk[wi]) + (wk_lo ? __bfloat162float(wk_lo[wi]) : 0.f);  // fp32 mode: hi + lo
   }
   __syncthreads();
   const int groups_x = (T + 7) / 8;             // 8 consecutive pixels = 2 parities x 4 pixels
@@ -160,7 +168,7 @@ stem_dgrad_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ wk, int 
       const int kw = (xp0 & 1) + 2 * j;
       if (kw > 6) continue;
       const float* w = ws + ((kh * 7 + kw) * 3) * Cout;
-      const bf16* grow = dy + (n * Ho + ho) * (long long)Ho * Cout;
+      const TA* grow = dy + (n * Ho + ho) * (long long)Ho * Cout;
       for (int co = 0; co < Cout; co += 8) {
         const float4 wa0 = *reinterpret_cast<const float4*>(w + co), wb0 = *reinterpret_cast<const float4*>(w + co + 4);
         const float4 wa1 = *reinterpret_cast<const float4*>(w + Cout + co);
@@ -194,7 +202,8 @@ stem_dgrad_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ wk, int 
 }
 
 // flax nn.max_pool(x, (3,3), strides=(2,2), padding="SAME") on an even-sized map: window rows 2ho..2ho+2 (pad high)
-__global__ void maxpool3s2_kernel(const bf16* __restrict__ x, int N, int H, int C, bf16* __restrict__ y) {
+template <typename T>
+__global__ void maxpool3s2_kernel(const T* __restrict__ x, int N, int H, int C, T* __restrict__ y) {
   const int Ho = H / 2, cv = C >> 3;
   const long long total = (long long)N * Ho * Ho * cv;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -224,8 +233,9 @@ __global__ void maxpool3s2_kernel(const bf16* __restrict__ x, int N, int H, int 
 
 // transpose: the gradient of a window goes to its FIRST maximal element in row-major window order
 // (XLA select_and_scatter with a >= selector)
-__global__ void maxpool3s2_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
-                                      const bf16* __restrict__ y, int N, int H, int C, bf16* __restrict__ dx) {
+template <typename T>
+__global__ void maxpool3s2_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                      const T* __restrict__ y, int N, int H, int C, T* __restrict__ dx) {
   const int Ho = H / 2, cv = C >> 3;
   const long long total = (long long)N * H * H * cv;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -270,7 +280,8 @@ __global__ void maxpool3s2_bwd_kernel(const bf16* __restrict__ dy, const bf16* _
 }
 
 // z[n,2h,2w,:] = dy[n,h,w,:], zero elsewhere (transpose of stride-2 sampling)
-__global__ void zero_insert2_kernel(const bf16* __restrict__ dy, int N, int H, int W, int C, bf16* __restrict__ z) {
+template <typename T>
+__global__ void zero_insert2_kernel(const T* __restrict__ dy, int N, int H, int W, int C, T* __restrict__ z) {
   const int cv = C >> 3;
   const long long total = (long long)N * H * W * cv;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -279,14 +290,15 @@ __global__ void zero_insert2_kernel(const bf16* __restrict__ dy, int N, int H, i
     long long pix = idx / cv;
     const int w = pix % W, h = (pix / W) % H;
     const long long n = pix / ((long long)W * H);
-    const uint4 val = *reinterpret_cast<const uint4*>(dy + pix * C + v * 8);
-    const uint4 zero = make_uint4(0, 0, 0, 0);
+    float val[8];
+    load8(dy + pix * C + v * 8, val);
+    const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const int W2 = 2 * W;
     const long long base = ((n * 2 * H + 2 * h) * W2 + 2 * w) * C + v * 8;
-    *reinterpret_cast<uint4*>(z + base) = val;
-    *reinterpret_cast<uint4*>(z + base + C) = zero;
-    *reinterpret_cast<uint4*>(z + base + (long long)W2 * C) = zero;
-    *reinterpret_cast<uint4*>(z + base + (long long)W2 * C + C) = zero;
+    store8(z + base, val);   // bf16 -> fp32 -> bf16 is exact
+    store8(z + base + C, zero);
+    store8(z + base + (long long)W2 * C, zero);
+    store8(z + base + (long long)W2 * C + C, zero);
   }
 }
 
@@ -300,11 +312,11 @@ static int grid1(long long total, int block) {
 
 using namespace xmc;
 
-extern "C" int xmc_resize_bilinear_pad(const float* img, int N, int S, int T, int Tp, int pad_lo, void* out,
+extern "C" int xmc_resize_bilinear_pad(const float* img, int N, int S, int T, int Tp, int pad_lo, int split, void* out,
                                        void* stream) {
   if (!img || !out || N < 1 || S < 1 || T < 1 || 2 * S > 3 * T || Tp < T + pad_lo) return XMC_EINVAL;
-  resize_bilinear_pad_kernel<<<grid1((long long)N * Tp * Tp, 256), 256, 0, (cudaStream_t)stream>>>(img, N, S, T, Tp,
-                                                                                                   pad_lo, (bf16*)out);
+  resize_bilinear_pad_kernel<<<grid1((long long)N * Tp * Tp, 256), 256, 0, (cudaStream_t)stream>>>(
+      img, N, S, T, Tp, pad_lo, split, (bf16*)out);
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }
@@ -317,39 +329,40 @@ extern "C" int xmc_resize_bilinear_bwd(const float* dout, int N, int S, int T, f
   return XMC_OK;
 }
 
-extern "C" int xmc_stem_dgrad(const void* dy, const void* wk, int N, int T, int Ho, int Cout, int pad_lo, float* dimg,
-                              void* stream) {
+extern "C" int xmc_stem_dgrad(const void* dy, int act_f32, const void* wk, const void* wk_lo, int N, int T, int Ho,
+                              int Cout, int pad_lo, float* dimg, void* stream) {
   if (!dy || !wk || !dimg || N < 1 || Cout < 8 || (Cout % 8)) return XMC_EINVAL;
   const size_t smem = (size_t)49 * 3 * Cout * sizeof(float);
   if (smem > 48 * 1024) return XMC_EINVAL;
   const long long total = (long long)N * T * ((T + 7) / 8) * 2;
-  stem_dgrad_kernel<<<(unsigned)ceil_div_ll(total, 128), 128, smem, (cudaStream_t)stream>>>(
-      (const bf16*)dy, (const bf16*)wk, N, T, Ho, Cout, pad_lo, dimg);
+  const int size = T;  // the dispatch macro names the activation type T
+  XMC_ACT(act_f32, stem_dgrad_kernel<T><<<(unsigned)ceil_div_ll(total, 128), 128, smem, (cudaStream_t)stream>>>(
+                       (const T*)dy, (const bf16*)wk, (const bf16*)wk_lo, N, size, Ho, Cout, pad_lo, dimg));
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }
 
-extern "C" int xmc_maxpool3s2(const void* x, int N, int H, int C, void* y, void* stream) {
+extern "C" int xmc_maxpool3s2(const void* x, int act_f32, int N, int H, int C, void* y, void* stream) {
   if (!x || !y || N < 1 || H < 2 || (H % 2) || C < 8 || (C % 8)) return XMC_EINVAL;
-  maxpool3s2_kernel<<<grid1((long long)N * (H / 2) * (H / 2) * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>(
-      (const bf16*)x, N, H, C, (bf16*)y);
+  XMC_ACT(act_f32, maxpool3s2_kernel<T><<<grid1((long long)N * (H / 2) * (H / 2) * (C / 8), 256), 256, 0,
+                                       (cudaStream_t)stream>>>((const T*)x, N, H, C, (T*)y));
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }
 
-extern "C" int xmc_maxpool3s2_bwd(const void* dy, const void* x, const void* y, int N, int H, int C, void* dx,
-                                  void* stream) {
+extern "C" int xmc_maxpool3s2_bwd(const void* dy, const void* x, const void* y, int act_f32, int N, int H, int C,
+                                  void* dx, void* stream) {
   if (!dy || !x || !y || !dx || N < 1 || H < 2 || (H % 2) || C < 8 || (C % 8)) return XMC_EINVAL;
-  maxpool3s2_bwd_kernel<<<grid1((long long)N * H * H * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>(
-      (const bf16*)dy, (const bf16*)x, (const bf16*)y, N, H, C, (bf16*)dx);
+  XMC_ACT(act_f32, maxpool3s2_bwd_kernel<T><<<grid1((long long)N * H * H * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+                       (const T*)dy, (const T*)x, (const T*)y, N, H, C, (T*)dx));
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }
 
-extern "C" int xmc_zero_insert2(const void* dy, int N, int H, int W, int C, void* z, void* stream) {
+extern "C" int xmc_zero_insert2(const void* dy, int act_f32, int N, int H, int W, int C, void* z, void* stream) {
   if (!dy || !z || N < 1 || H < 1 || W < 1 || C < 8 || (C % 8)) return XMC_EINVAL;
-  zero_insert2_kernel<<<grid1((long long)N * H * W * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)dy, N,
-                                                                                                   H, W, C, (bf16*)z);
+  XMC_ACT(act_f32, zero_insert2_kernel<T><<<grid1((long long)N * H * W * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+                       (const T*)dy, N, H, W, C, (T*)z));
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }

@@ -8,20 +8,40 @@ namespace xmc {
 
 constexpr int kImgC = 3;
 
+// two adjacent channels as floats
+__device__ __forceinline__ void load2(const bf16* p, float& a, float& b) {
+  const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(p);
+  a = __low2float(v); b = __high2float(v);
+}
+__device__ __forceinline__ void load2(const float* p, float& a, float& b) {
+  const float2 v = *reinterpret_cast<const float2*>(p);
+  a = v.x; b = v.y;
+}
+
+// Weight element k of row `row` of a K-major bf16 weight matrix. wsplit = 0: plain [row][k]. wsplit = 1 (fp32 mode):
+// the matrix is stored in the split form the tensor-core GEMMs consume, [row][tap][hi | hi | lo][inner], and the
+// weight is hi + lo (16 mantissa bits), k = tap*inner + i.
+__device__ __forceinline__ float weight_at(const bf16* w, int ldw, int row, int k, int inner, int wsplit) {
+  if (!wsplit) return __bfloat162float(w[(long long)row * ldw + k]);
+  const int tap = k / inner, i = k - tap * inner;
+  const bf16* q = w + (long long)row * ldw + (long long)tap * 3 * inner + i;
+  return __bfloat162float(q[0]) + __bfloat162float(q[2 * inner]);
+}
+
 // y[p][co] = relu?( sum_{tap,c3} x[p+d(tap)][c3] * w[co][tap*3+c3] + bias[co] ),  x: bf16 [N,H,W,3], y: bf16 [.,Cout]
 // Each thread computes 4 horizontally adjacent pixels x 8 channels at a time: the 3x6x3 input window lives in
 // registers, every weight read from shared memory (one LDS.128 broadcast per 4 weights) feeds 4 FMAs.
 constexpr int kPx = 4;
-template <int KS>
+template <int KS, typename T>
 __global__ void __launch_bounds__(128)
-conv_c3_in_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, int ldw, const float* __restrict__ bias,
-                  int N, int H, int W, int Cout, int relu, bf16* __restrict__ y) {
+conv_c3_in_kernel(const T* __restrict__ x, const bf16* __restrict__ w, int ldw, int wsplit,
+                  const float* __restrict__ bias, int N, int H, int W, int Cout, int relu, T* __restrict__ y) {
   extern __shared__ float ws[];  // [K][Cout] (transposed for vector reads) + bias[Cout]
   constexpr int KH = KS, KW = KS;
   constexpr int K = KH * KW * kImgC;
   for (int t = threadIdx.x; t < Cout * K; t += blockDim.x) {
     const int co = t / K, k = t - co * K;
-    ws[k * Cout + co] = __bfloat162float(w[co * ldw + k]);
+    ws[k * Cout + co] = weight_at(w, ldw, co, k, kImgC, wsplit);
   }
   float* bs = ws + Cout * K;
   for (int t = threadIdx.x; t < Cout; t += blockDim.x) bs[t] = bias ? bias[t] : 0.f;
@@ -44,9 +64,9 @@ conv_c3_in_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, int ld
     for (int cc = 0; cc < cols; ++cc) {
       const int ww = w0 + cc - pw;
       const bool ok = hh >= 0 && hh < H && ww >= 0 && ww < W;
-      const bf16* src = x + ((n * H + hh) * W + ww) * kImgC;
+      const T* src = x + ((n * H + hh) * W + ww) * kImgC;
 #pragma unroll
-      for (int c = 0; c < kImgC; ++c) win[(kh * cols + cc) * kImgC + c] = ok ? __bfloat162float(src[c]) : 0.f;
+      for (int c = 0; c < kImgC; ++c) win[(kh * cols + cc) * kImgC + c] = ok ? to_f(src[c]) : 0.f;
     }
   }
   const long long pbase = (n * H + hq) * W + w0;
@@ -89,15 +109,15 @@ conv_c3_in_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, int ld
 // mode 0: fp32 out (accumulate optional); mode 1: img = (tanh(v)+1)/2 -> fp32 out + bf16 copy (xmc_net.py:245-247)
 // Each thread computes 4 horizontally adjacent pixels: per (kh, 8-channel vector) it loads the 6 input vectors once
 // and reads each weight vector from shared memory once for all 4 pixels.
-template <int KS>
+template <int KS, typename T>
 __global__ void __launch_bounds__(128)
-conv_c3_out_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, int ldw, const float* __restrict__ bias,
-                   int N, int H, int W, int Cin, int mode, int accumulate, float* __restrict__ y,
-                   bf16* __restrict__ y_bf16) {
+conv_c3_out_kernel(const T* __restrict__ x, const bf16* __restrict__ w, int ldw, int wsplit,
+                   const float* __restrict__ bias, int N, int H, int W, int Cin, int mode, int accumulate,
+                   float* __restrict__ y, T* __restrict__ y_bf16) {
   extern __shared__ float ws[];  // [3][K]
   constexpr int KH = KS, KW = KS;
   const int K = KH * KW * Cin;
-  for (int t = threadIdx.x; t < kImgC * K; t += blockDim.x) ws[t] = __bfloat162float(w[(t / K) * ldw + (t % K)]);
+  for (int t = threadIdx.x; t < kImgC * K; t += blockDim.x) ws[t] = weight_at(w, ldw, t / K, t % K, Cin, wsplit);
   __syncthreads();
   const int wq4 = (W + kPx - 1) / kPx;
   const long long groups = (long long)N * H * wq4;
@@ -116,7 +136,7 @@ conv_c3_out_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, int l
   for (int kh = 0; kh < KH; ++kh) {
     const int hh = hq + kh - ph;
     if (hh < 0 || hh >= H) continue;
-    const bf16* row = x + (n * H + hh) * (long long)W * Cin;
+    const T* row = x + (n * H + hh) * (long long)W * Cin;
     for (int c = 0; c < Cin; c += 8) {
       float in[kPx + KW - 1][8];
 #pragma unroll
@@ -157,8 +177,8 @@ conv_c3_out_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, int l
       a0 = (tanhf(a0) + 1.f) * 0.5f; a1 = (tanhf(a1) + 1.f) * 0.5f; a2 = (tanhf(a2) + 1.f) * 0.5f;
       yo[0] = a0; yo[1] = a1; yo[2] = a2;
       if (y_bf16) {
-        bf16* yb = y_bf16 + (pbase + px) * kImgC;
-        yb[0] = __float2bfloat16(a0); yb[1] = __float2bfloat16(a1); yb[2] = __float2bfloat16(a2);
+        T* yb = y_bf16 + (pbase + px) * kImgC;
+        yb[0] = from_f<T>(a0); yb[1] = from_f<T>(a1); yb[2] = from_f<T>(a2);
       }
     } else if (accumulate) {
       yo[0] += a0; yo[1] += a1; yo[2] += a2;
@@ -172,8 +192,8 @@ conv_c3_out_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, int l
 // out index = tap_o*s_tap + c3*s_c3 + c*s_c with tap_o = flip ? taps-1-tap : tap. One block = 8 image rows x 64 px;
 // one thread = 2 adjacent channels; the 3x3x3 input window slides along the row in registers (9 shared-memory reads
 // per pixel feed 54 FMAs).
-template <int KS>
-__global__ void wgrad_c3_kernel(const bf16* __restrict__ x3, const bf16* __restrict__ y, int N, int H, int W, int C,
+template <int KS, typename T>
+__global__ void wgrad_c3_kernel(const T* __restrict__ x3, const T* __restrict__ y, int N, int H, int W, int C,
                                 float* __restrict__ partials) {
   extern __shared__ float xs[];  // [(rows+2ph)][64+2pw][3]
   constexpr int KH = KS, KW = KS;
@@ -191,7 +211,7 @@ __global__ void wgrad_c3_kernel(const bf16* __restrict__ x3, const bf16* __restr
     const int c = t % kImgC, ww = (t / kImgC) % xw, hh = t / (kImgC * xw);
     const int gh = h0 + hh - ph, gw = w0 + ww - pw;
     float v = 0.f;
-    if (gh >= 0 && gh < H && gw >= 0 && gw < W) v = __bfloat162float(x3[(((long long)n * H + gh) * W + gw) * kImgC + c]);
+    if (gh >= 0 && gh < H && gw >= 0 && gw < W) v = to_f(x3[(((long long)n * H + gh) * W + gw) * kImgC + c]);
     xs[t] = v;
   }
   __syncthreads();
@@ -204,7 +224,7 @@ __global__ void wgrad_c3_kernel(const bf16* __restrict__ x3, const bf16* __restr
   for (int r = 0; r < rows; ++r) {
     const int gh = h0 + r;
     if (gh >= H) break;
-    const bf16* yrow = y + (((long long)n * H + gh) * W + w0) * C + c;
+    const T* yrow = y + (((long long)n * H + gh) * W + w0) * C + c;
     const int qn = min(seg, W - w0);
     if constexpr (taps == 9) {
       // win[slot][kh][c3]: slot (col % 3) holds input column `col` of the halo tile
@@ -217,11 +237,12 @@ __global__ void wgrad_c3_kernel(const bf16* __restrict__ x3, const bf16* __restr
           for (int c3 = 0; c3 < 3; ++c3) win[col][kh][c3] = xs[((r + kh) * xw + col) * kImgC + c3];
       // 12 pixels per outer iteration: all 12 y loads are issued first (the loop is latency-bound otherwise)
       for (int q0 = 0; q0 < qn; q0 += 12) {
-        __nv_bfloat162 yv[12];
+        float yv0[12], yv1[12];
 #pragma unroll
-        for (int j = 0; j < 12; ++j)
-          yv[j] = (q0 + j < qn) ? *reinterpret_cast<const __nv_bfloat162*>(yrow + (long long)(q0 + j) * C)
-                                : __floats2bfloat162_rn(0.f, 0.f);
+        for (int j = 0; j < 12; ++j) {
+          yv0[j] = yv1[j] = 0.f;
+          if (q0 + j < qn) load2(yrow + (long long)(q0 + j) * C, yv0[j], yv1[j]);
+        }
 #pragma unroll
         for (int j = 0; j < 12; ++j) {
           const int q = q0 + j;
@@ -231,7 +252,7 @@ __global__ void wgrad_c3_kernel(const bf16* __restrict__ x3, const bf16* __restr
             for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
               for (int c3 = 0; c3 < 3; ++c3) win[(j + 2) % 3][kh][c3] = xs[((r + kh) * xw + q + 2) * kImgC + c3];
-            const float y0 = __low2float(yv[j]), y1 = __high2float(yv[j]);
+            const float y0 = yv0[j], y1 = yv1[j];
 #pragma unroll
             for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
@@ -247,8 +268,8 @@ __global__ void wgrad_c3_kernel(const bf16* __restrict__ x3, const bf16* __restr
       }
     } else {
       for (int q = 0; q < qn; ++q) {
-        const __nv_bfloat162 yv2 = *reinterpret_cast<const __nv_bfloat162*>(yrow + (long long)q * C);
-        const float y0 = __low2float(yv2), y1 = __high2float(yv2);
+        float y0, y1;
+        load2(yrow + (long long)q * C, y0, y1);
         const float* xp = xs + (r * xw + q) * kImgC;
 #pragma unroll
         for (int c3 = 0; c3 < 3; ++c3) {
@@ -281,8 +302,9 @@ __global__ void wgrad_c3_finish_kernel(const float* __restrict__ partials, int b
 }
 
 // scalar-channel 2x2 mean pool of a bf16 [N,2H,2W,C] tensor (the 3-channel image, common.py:131)
-__global__ void pool2_small_kernel(const bf16* __restrict__ a, int N, int H, int W, int C, float scale,
-                                   bf16* __restrict__ out) {
+template <typename T>
+__global__ void pool2_small_kernel(const T* __restrict__ a, int N, int H, int W, int C, float scale,
+                                   T* __restrict__ out) {
   const long long total = (long long)N * H * W * C;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -291,9 +313,8 @@ __global__ void pool2_small_kernel(const bf16* __restrict__ a, int N, int H, int
     const int w = pix % W, h = (pix / W) % H;
     const long long n = pix / ((long long)W * H);
     const long long base = ((n * 2 * H + 2 * h) * 2 * W + 2 * w) * C + c;
-    const float s = __bfloat162float(a[base]) + __bfloat162float(a[base + C]) +
-                    __bfloat162float(a[base + 2LL * W * C]) + __bfloat162float(a[base + 2LL * W * C + C]);
-    out[idx] = __float2bfloat16(s * scale);
+    const float s = to_f(a[base]) + to_f(a[base + C]) + to_f(a[base + 2LL * W * C]) + to_f(a[base + 2LL * W * C + C]);
+    out[idx] = from_f<T>(s * scale);
   }
 }
 
@@ -314,11 +335,12 @@ __global__ void unpool2_add_f32_kernel(const float* __restrict__ d, int N, int H
 }
 
 // d(pre-tanh) = dimg * 0.5 * (1 - t^2), t = 2*img - 1   -> bf16
+template <typename T>
 __global__ void tanh01_bwd_kernel(const float* __restrict__ dimg, const float* __restrict__ img, long long n,
-                                  bf16* __restrict__ dpre) {
+                                  T* __restrict__ dpre) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float t = 2.f * img[i] - 1.f;
-    dpre[i] = __float2bfloat16(dimg[i] * 0.5f * (1.f - t * t));
+    dpre[i] = from_f<T>(dimg[i] * 0.5f * (1.f - t * t));
   }
 }
 
@@ -395,43 +417,45 @@ extern "C" int xmc_unpack_c3_wgrad(const float* tmp, int C, int flip, long long 
   return XMC_OK;
 }
 
-extern "C" int xmc_conv_c3_in(const void* x, const void* w, int ldw, const float* bias, int N, int H, int W, int Cout,
-                              int KH, int KW, int relu, void* y, void* stream) {
+extern "C" int xmc_conv_c3_in(const void* x, int act_f32, const void* w, int ldw, const float* bias, int N, int H, int W,
+                              int Cout, int KH, int KW, int relu, void* y, void* stream) {
   if (!x || !w || !y || Cout < 8 || (Cout % 8) || KH * KW > 9) return XMC_EINVAL;
   const int K = KH * KW * kImgC;
   const size_t smem = (size_t)(Cout * K + Cout) * sizeof(float);
   if (smem > 48 * 1024) return XMC_EINVAL;
   const long long P = (long long)N * H * ceil_div(W, kPx);
   if (KH != KW || (KH != 1 && KH != 3)) return XMC_EINVAL;
+  // fp32 activations come with split-form weights ([row][tap][hi|hi|lo][3], see weight_at)
   if (KH == 3)
-    conv_c3_in_kernel<3><<<(unsigned)ceil_div_ll(P, 128), 128, smem, (cudaStream_t)stream>>>(
-        (const bf16*)x, (const bf16*)w, ldw, bias, N, H, W, Cout, relu, (bf16*)y);
+    XMC_ACT(act_f32, conv_c3_in_kernel<3, T><<<(unsigned)ceil_div_ll(P, 128), 128, smem, (cudaStream_t)stream>>>(
+                         (const T*)x, (const bf16*)w, ldw, act_f32, bias, N, H, W, Cout, relu, (T*)y));
   else
-    conv_c3_in_kernel<1><<<(unsigned)ceil_div_ll(P, 128), 128, smem, (cudaStream_t)stream>>>(
-        (const bf16*)x, (const bf16*)w, ldw, bias, N, H, W, Cout, relu, (bf16*)y);
+    XMC_ACT(act_f32, conv_c3_in_kernel<1, T><<<(unsigned)ceil_div_ll(P, 128), 128, smem, (cudaStream_t)stream>>>(
+                         (const T*)x, (const bf16*)w, ldw, act_f32, bias, N, H, W, Cout, relu, (T*)y));
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }
 
-extern "C" int xmc_conv_c3_out(const void* x, const void* w, int ldw, const float* bias, int N, int H, int W, int Cin,
-                               int KH, int KW, int mode, int accumulate, float* y, void* y_bf16, void* stream) {
+extern "C" int xmc_conv_c3_out(const void* x, int act_f32, const void* w, int ldw, const float* bias, int N, int H, int W,
+                               int Cin, int KH, int KW, int mode, int accumulate, float* y, void* y_bf16,
+                               void* stream) {
   if (!x || !w || !y || Cin < 8 || (Cin % 8)) return XMC_EINVAL;
   const size_t smem = (size_t)kImgC * KH * KW * Cin * sizeof(float);
   if (smem > 48 * 1024) return XMC_EINVAL;
   const long long P = (long long)N * H * ceil_div(W, kPx);
   if (KH != KW || (KH != 1 && KH != 3)) return XMC_EINVAL;
   if (KH == 3)
-    conv_c3_out_kernel<3><<<(unsigned)ceil_div_ll(P, 128), 128, smem, (cudaStream_t)stream>>>(
-        (const bf16*)x, (const bf16*)w, ldw, bias, N, H, W, Cin, mode, accumulate, y, (bf16*)y_bf16);
+    XMC_ACT(act_f32, conv_c3_out_kernel<3, T><<<(unsigned)ceil_div_ll(P, 128), 128, smem, (cudaStream_t)stream>>>(
+                         (const T*)x, (const bf16*)w, ldw, act_f32, bias, N, H, W, Cin, mode, accumulate, y, (T*)y_bf16));
   else
-    conv_c3_out_kernel<1><<<(unsigned)ceil_div_ll(P, 128), 128, smem, (cudaStream_t)stream>>>(
-        (const bf16*)x, (const bf16*)w, ldw, bias, N, H, W, Cin, mode, accumulate, y, (bf16*)y_bf16);
+    XMC_ACT(act_f32, conv_c3_out_kernel<1, T><<<(unsigned)ceil_div_ll(P, 128), 128, smem, (cudaStream_t)stream>>>(
+                         (const T*)x, (const bf16*)w, ldw, act_f32, bias, N, H, W, Cin, mode, accumulate, y, (T*)y_bf16));
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }
 
-extern "C" int xmc_wgrad_c3(const void* x3, const void* y, int N, int H, int W, int C, int KH, int KW, int flip,
-                            long long s_tap, int s_c3, int s_c, float* out, float* partials, void* stream) {
+extern "C" int xmc_wgrad_c3(const void* x3, const void* y, int act_f32, int N, int H, int W, int C, int KH, int KW,
+                            int flip, long long s_tap, int s_c3, int s_c, float* out, float* partials, void* stream) {
   if (!x3 || !y || !out || !partials || C < 2 || (C % 2) || C > 2048 || KH * KW > 9) return XMC_EINVAL;
   const int ph = KH / 2, pw = KW / 2;
   const size_t smem = (size_t)(8 + 2 * ph) * (64 + 2 * pw) * kImgC * sizeof(float);
@@ -439,11 +463,11 @@ extern "C" int xmc_wgrad_c3(const void* x3, const void* y, int N, int H, int W, 
   const int threads = ceil_div(C / 2, 32) * 32;
   if (KH != KW || (KH != 1 && KH != 3)) return XMC_EINVAL;
   if (KH == 3)
-    wgrad_c3_kernel<3><<<blocks, threads, smem, (cudaStream_t)stream>>>((const bf16*)x3, (const bf16*)y, N, H, W, C,
-                                                                       partials);
+    XMC_ACT(act_f32, wgrad_c3_kernel<3, T><<<blocks, threads, smem, (cudaStream_t)stream>>>((const T*)x3, (const T*)y, N, H,
+                                                                                       W, C, partials));
   else
-    wgrad_c3_kernel<1><<<blocks, threads, smem, (cudaStream_t)stream>>>((const bf16*)x3, (const bf16*)y, N, H, W, C,
-                                                                       partials);
+    XMC_ACT(act_f32, wgrad_c3_kernel<1, T><<<blocks, threads, smem, (cudaStream_t)stream>>>((const T*)x3, (const T*)y, N, H,
+                                                                                       W, C, partials));
   XMC_LAUNCH_CHECK();
   const int width = KH * KW * 3 * C;
   wgrad_c3_finish_kernel<<<ceil_div(width, 128), 128, 0, (cudaStream_t)stream>>>(partials, blocks, KH * KW, C, flip,
@@ -452,10 +476,11 @@ extern "C" int xmc_wgrad_c3(const void* x3, const void* y, int N, int H, int W, 
   return XMC_OK;
 }
 
-extern "C" int xmc_pool2_small(const void* a, int N, int Hout, int Wout, int C, float scale, void* out, void* stream) {
+extern "C" int xmc_pool2_small(const void* a, int act_f32, int N, int Hout, int Wout, int C, float scale, void* out,
+                               void* stream) {
   if (!a || !out) return XMC_EINVAL;
-  pool2_small_kernel<<<grid1d((long long)N * Hout * Wout * C, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const bf16*)a, N, Hout, Wout, C, scale, (bf16*)out);
+  XMC_ACT(act_f32, pool2_small_kernel<T><<<grid1d((long long)N * Hout * Wout * C, 256), 256, 0, (cudaStream_t)stream>>>(
+                       (const T*)a, N, Hout, Wout, C, scale, (T*)out));
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }
@@ -469,9 +494,9 @@ extern "C" int xmc_unpool2_add_f32(const float* d, int N, int Hin, int Win, int 
   return XMC_OK;
 }
 
-extern "C" int xmc_tanh01_bwd(const float* dimg, const float* img, long long n, void* dpre, void* stream) {
+extern "C" int xmc_tanh01_bwd(const float* dimg, const float* img, long long n, void* dpre, int act_f32, void* stream) {
   if (!dimg || !img || !dpre || n < 1) return XMC_EINVAL;
-  tanh01_bwd_kernel<<<grid1d(n, 256), 256, 0, (cudaStream_t)stream>>>(dimg, img, n, (bf16*)dpre);
+  XMC_ACT(act_f32, tanh01_bwd_kernel<T><<<grid1d(n, 256), 256, 0, (cudaStream_t)stream>>>(dimg, img, n, (T*)dpre));
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }

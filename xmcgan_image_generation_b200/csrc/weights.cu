@@ -168,6 +168,9 @@ prep_weights_kernel(const XmcPrepEntry* __restrict__ tab, int n, const float* __
   const float scale = (en.sn >= 0) ? sn_scalars[2 * n_sn + en.sn] : 1.f;
   const int c = ct * kPrepTile + threadIdx.x;
   const float cs = (en.cscale_off >= 0 && c < en.cout) ? cscale[en.cscale_off + c] : 1.f;
+  // split mode (fp32 activations): every weight is stored as hi = bf16(w), lo = bf16(w - hi) in the parts [hi | hi | lo]
+  const int S = en.split ? 3 : 1;
+  const long long dgps = en.dg_part_stride > 0 ? en.dg_part_stride : en.cout;
 #pragma unroll 4
   for (int r = threadIdx.y; r < kPrepTile; r += 4) {
     const int k = kt * kPrepTile + r;
@@ -176,8 +179,13 @@ prep_weights_kernel(const XmcPrepEntry* __restrict__ tab, int n, const float* __
       v = params[en.w_off + (long long)k * en.cout + c] * scale * cs;
       if (en.wk_dg_off >= 0) {
         const int tap = k / en.cin, ci = k - tap * en.cin;
-        arena[en.wk_dg_off + (long long)ci * en.ld_dg + (long long)(en.taps - 1 - tap) * en.cout + c] =
-            __float2bfloat16(v);
+        bf16* o = arena + en.wk_dg_off + (long long)ci * en.ld_dg + (long long)(en.taps - 1 - tap) * S * en.cout + c;
+        const bf16 hi = __float2bfloat16(v);
+        o[0] = hi;
+        if (en.split) {
+          o[dgps] = hi;
+          o[2 * dgps] = __float2bfloat16(v - __bfloat162float(hi));
+        }
       }
     }
     tile[r][threadIdx.x] = v;
@@ -185,10 +193,19 @@ prep_weights_kernel(const XmcPrepEntry* __restrict__ tab, int n, const float* __
   __syncthreads();
   if (en.wk_fwd_off >= 0) {
     const int k = kt * kPrepTile + threadIdx.x;
+    const int tap = k / en.cin, ci = k - tap * en.cin;
     for (int r = threadIdx.y; r < kPrepTile; r += 4) {
       const int cc = ct * kPrepTile + r;
-      if (k < K && cc < en.cout)
-        arena[en.wk_fwd_off + (long long)cc * en.ld_fwd + k] = __float2bfloat16(tile[threadIdx.x][r]);
+      if (k < K && cc < en.cout) {
+        const float v = tile[threadIdx.x][r];
+        bf16* o = arena + en.wk_fwd_off + (long long)cc * en.ld_fwd + (long long)tap * S * en.cin + ci;
+        const bf16 hi = __float2bfloat16(v);
+        o[0] = hi;
+        if (en.split) {
+          o[en.cin] = hi;
+          o[2 * en.cin] = __float2bfloat16(v - __bfloat162float(hi));
+        }
+      }
     }
   }
   if (local == 0 && en.bias_off >= 0 && en.bias_dst_off >= 0) {
@@ -207,12 +224,15 @@ prep_weights_kernel(const XmcPrepEntry* __restrict__ tab, int n, const float* __
 // 16 parity/tap sums are staged in shared memory; vd (co contiguous) is written in the same orientation, wf (ci
 // contiguous) after a transpose through the staging tile, so both bf16 matrices are written in full 64-byte runs.
 __global__ void __launch_bounds__(256)
-subpixel_prep_kernel(const float* __restrict__ w, const float* __restrict__ scale, int Cin, int Cout,
+subpixel_prep_kernel(const float* __restrict__ w, const float* __restrict__ scale, int Cin, int Cout, int split,
                      bf16* __restrict__ wf, bf16* __restrict__ vd) {
-  __shared__ bf16 tile[16][32][34];  // [a,dh,b,dw][ci][co], already rounded
+  // split = 1 (fp32 activations): wf [4*Cout][(dh*2+dw)][hi | hi | lo][Cin], vd [Cin][(r*4+s)][hi | hi | lo][Cout]
+  __shared__ float tile[8][32][33];  // [dh,b,dw][ci][co] of one output-row parity a, fp32 sums
+  const int S = split ? 3 : 1;
   const int ci0 = blockIdx.y * 32, co0 = blockIdx.x * 32;
   const float sc = scale ? *scale : 1.f;
   const int r_of[2][2] = {{3, 1}, {2, 0}};  // r_of[a][dh]
+  for (int a = 0; a < 2; ++a) {  // the two output-row parities one after the other (the staging tile holds one)
   for (int r = threadIdx.y; r < 32; r += 8) {
     const int ci = ci0 + r, co = co0 + threadIdx.x;
     if (ci >= Cin || co >= Cout) continue;
@@ -230,8 +250,6 @@ subpixel_prep_kernel(const float* __restrict__ w, const float* __restrict__ scal
       rc[1][1][kw] = k[2][kw];
     }
 #pragma unroll
-    for (int a = 0; a < 2; ++a)
-#pragma unroll
       for (int dh = 0; dh < 2; ++dh)
 #pragma unroll
         for (int b = 0; b < 2; ++b)
@@ -240,8 +258,13 @@ subpixel_prep_kernel(const float* __restrict__ w, const float* __restrict__ scal
             const float* q = rc[a][dh];
             const float v = (b == 0) ? (dw == 0 ? q[0] : q[1] + q[2]) : (dw == 0 ? q[0] + q[1] : q[2]);
             const bf16 qv = __float2bfloat16(v);
-            tile[((a * 2 + dh) * 2 + b) * 2 + dw][r][threadIdx.x] = qv;
-            vd[(long long)ci * (16 * Cout) + (r_of[a][dh] * 4 + r_of[b][dw]) * Cout + co] = qv;
+            tile[(dh * 2 + b) * 2 + dw][r][threadIdx.x] = v;
+            bf16* o = vd + (long long)ci * (16 * S * Cout) + (long long)(r_of[a][dh] * 4 + r_of[b][dw]) * S * Cout + co;
+            o[0] = qv;
+            if (split) {
+              o[Cout] = qv;
+              o[2 * Cout] = __float2bfloat16(v - __bfloat162float(qv));
+            }
           }
   }
   __syncthreads();
@@ -250,10 +273,19 @@ subpixel_prep_kernel(const float* __restrict__ w, const float* __restrict__ scal
     const int co = co0 + r, ci = ci0 + threadIdx.x;
     if (ci >= Cin || co >= Cout) continue;
 #pragma unroll
-    for (int t = 0; t < 16; ++t) {
-      const int a = t >> 3, dh = (t >> 2) & 1, b = (t >> 1) & 1, dw = t & 1;
-      wf[((long long)((a * 2 + b) * Cout + co)) * (4 * Cin) + (dh * 2 + dw) * Cin + ci] = tile[t][threadIdx.x][r];
+    for (int t = 0; t < 8; ++t) {
+      const int dh = (t >> 2) & 1, b = (t >> 1) & 1, dw = t & 1;
+      const float v = tile[t][threadIdx.x][r];
+      const bf16 qv = __float2bfloat16(v);
+      bf16* o = wf + ((long long)((a * 2 + b) * Cout + co)) * (4 * S * Cin) + (long long)(dh * 2 + dw) * S * Cin + ci;
+      o[0] = qv;
+      if (split) {
+        o[Cin] = qv;
+        o[2 * Cin] = __float2bfloat16(v - __bfloat162float(qv));
+      }
     }
+  }
+  __syncthreads();
   }
 }
 
@@ -348,11 +380,11 @@ extern "C" int xmc_prep_weights(const XmcPrepEntry* table_dev, int n, int total_
   return XMC_OK;
 }
 
-extern "C" int xmc_subpixel_prep(const float* w, const float* scale, int Cin, int Cout, void* wf, void* vd,
+extern "C" int xmc_subpixel_prep(const float* w, const float* scale, int Cin, int Cout, int split, void* wf, void* vd,
                                  void* stream) {
   if (!w || !wf || !vd || Cin < 8 || Cout < 8 || (Cin % 8) || (Cout % 8)) return XMC_EINVAL;
   subpixel_prep_kernel<<<dim3(ceil_div(Cout, 32), ceil_div(Cin, 32)), dim3(32, 8), 0, (cudaStream_t)stream>>>(
-      w, scale, Cin, Cout, (bf16*)wf, (bf16*)vd);
+      w, scale, Cin, Cout, split, (bf16*)wf, (bf16*)vd);
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }

@@ -34,6 +34,16 @@ def _r8(n):
   return (n + 7) // 8 * 8
 
 
+def act_dtype_of(config):
+  """Activation dtype of config.dtype (train_utils.py:148-151): "bfloat16" (coco_xmc.py:45) or "float32"."""
+  dt = getattr(config, "dtype", "bfloat16")
+  if dt == "bfloat16":
+    return BF16
+  if dt == "float32":
+    return F32
+  raise ValueError(f"config.dtype {dt!r} is not supported (bfloat16 or float32)")
+
+
 def as4(t2d):
   """[rows, C] (pitched) -> [1,1,rows,C] so that the GEMM sees `rows` pixels along W."""
   return t2d[None, None]
@@ -111,8 +121,12 @@ class _PrepTable:
     self.entries = []
     self.tiles = 0
 
-  def add(self, w_off, taps, cin, cout, fwd_off, ld_fwd, dg_off, ld_dg, sn, cscale_off=-1):
+  def add(self, w_off, taps, cin, cout, fwd_off, ld_fwd, dg_off, ld_dg, sn, cscale_off=-1, split=False,
+          dg_part_stride=0):
+    """split: fp32-activation mode, every weight stored as [hi | hi | lo] (XmcPrepEntry.split); the caller's offsets
+    and pitches already account for the 3x wider rows."""
     e = _lib.PrepEntry()
+    e.split, e.dg_part_stride = int(split), dg_part_stride
     e.w_off, e.wk_fwd_off, e.wk_dg_off = w_off, fwd_off, dg_off
     e.bias_off = e.bias_dst_off = -1
     e.cscale_off = cscale_off
@@ -196,6 +210,10 @@ class GeneratorEngine:
     else:
       raise ValueError(f"image_size {config.image_size} is not supported (reference: xmc_net.py:202-205)")
     self.config = config
+    # activation dtype: bf16 (reference default) or fp32 (config.dtype = "float32": fp32 activations, every GEMM as
+    # three bf16 passes over [hi | lo] splits of both operands). S = width factor of the split weight copies.
+    self.act = act_dtype_of(config)
+    self.S = S_ = 3 if self.act == F32 else 1
     # g_spectral_norm switches EVERY conv / dense of the generator, including the gamma / beta layers inside
     # (Local)ConditionalBatchNorm, to the spectral variants (xmc_net.py:176-191, layers.py:244-273)
     self.sn = bool(config.g_spectral_norm)
@@ -275,13 +293,13 @@ class GeneratorEngine:
       b_off = L.add(path + ("bias",), (cout_,))
       taps = kh * kh
       slot = self.sntab.add(path, w_off, taps * cin_, cout_) if self.sn else -1
-      ld_fwd, ld_dg = _r8(taps * cin_), _r8(taps * cout_)
+      ld_fwd, ld_dg = _r8(S_ * taps * cin_), _r8(S_ * taps * cout_)
       if subpixel:
         # conv3x3(upsample(x)) as four 2x2 convs on x: [4*Cout][4*Cin] forward and [Cin][16*Cout] dgrad matrices
         wf_off = self.arena_size
-        self.arena_size += 4 * cout_ * 4 * cin_
+        self.arena_size += 4 * cout_ * 4 * cin_ * S_
         vd_off = self.arena_size
-        self.arena_size += cin_ * 16 * cout_
+        self.arena_size += cin_ * 16 * cout_ * S_
         self.subpixel[path] = (wf_off, vd_off)
         self.convs[path] = ConvRec(path, kh, cin_, cout_, w_off, b_off, -1, ld_fwd, -1, ld_dg, slot)
         return
@@ -289,7 +307,7 @@ class GeneratorEngine:
       self.arena_size += _r8(cout_) * ld_fwd
       dg_off = self.arena_size
       self.arena_size += _r8(cin_) * ld_dg
-      self.prep.add(w_off, taps, cin_, cout_, fwd_off, ld_fwd, dg_off, ld_dg, slot)
+      self.prep.add(w_off, taps, cin_, cout_, fwd_off, ld_fwd, dg_off, ld_dg, slot, split=S_ == 3)
       self.convs[path] = ConvRec(path, kh, cin_, cout_, w_off, b_off, fwd_off, ld_fwd, dg_off, ld_dg, slot)
 
     # registration order = the reference's call order (xmc_net.py:209-246): Flax auto-numbers modules per class
@@ -302,25 +320,27 @@ class GeneratorEngine:
     add_conv((cp + "_0",), 1, ch[1], E)
     add_conv((cp + "_1",), 3, self.c_last, 3)
 
-    # concatenated matrices: forward [N*][K] rows per layer, dgrad [K][N*] column slices
+    # concatenated matrices: forward [N*][K] rows per layer, dgrad [K][N*] column slices (split mode: [K][3][N*])
     self.cbn_fwd_off = self.arena_size
-    self.arena_size += self.NC * cd
+    self.arena_size += self.NC * cd * S_
     self.cbn_dg_off = self.arena_size
-    self.arena_size += cd * self.NC
+    self.arena_size += cd * self.NC * S_
     self.lcbn_fwd_off = self.arena_size
-    self.arena_size += self.NL * scd
+    self.arena_size += self.NL * scd * S_
     self.lcbn_dg_off = self.arena_size
-    self.arena_size += scd * self.NL
+    self.arena_size += scd * self.NL * S_
     for prefix, C, goff, boff in self.cbn:
       for leaf, o in ((dp + "_0", goff), (dp + "_1", boff)):
         w_off = L.off(prefix + (leaf, "kernel"))
         slot = self.sntab.add(prefix + (leaf,), w_off, cd, C) if self.sn else -1
-        self.prep.add(w_off, 1, cd, C, self.cbn_fwd_off + o * cd, cd, self.cbn_dg_off + o, self.NC, slot)
+        self.prep.add(w_off, 1, cd, C, self.cbn_fwd_off + o * cd * S_, cd * S_, self.cbn_dg_off + o, self.NC * S_, slot,
+                      split=S_ == 3, dg_part_stride=self.NC)
     for prefix, C, goff, boff in self.lcbn:
       for leaf, o in ((cp + "_0", goff), (cp + "_1", boff)):
         w_off = L.off(prefix + (leaf, "kernel"))
         slot = self.sntab.add(prefix + (leaf,), w_off, scd, C) if self.sn else -1
-        self.prep.add(w_off, 1, scd, C, self.lcbn_fwd_off + o * scd, scd, self.lcbn_dg_off + o, self.NL, slot)
+        self.prep.add(w_off, 1, scd, C, self.lcbn_fwd_off + o * scd * S_, scd * S_, self.lcbn_dg_off + o,
+                      self.NL * S_, slot, split=S_ == 3, dg_part_stride=self.NL)
     self.u_layout = self.sntab.u_layout if self.sn else Layout()
 
     # ---- batch_stats layout ------------------------------------------------------------------------------------
@@ -359,7 +379,7 @@ class GeneratorEngine:
     for path, (wf_off, vd_off) in self.subpixel.items():
       rec = self.convs[path]
       scale = self.sntab.inv_sigma(rec.sn).data_ptr() if self.sn else None
-      ops._call("xmc_subpixel_prep", params[rec.w_off:].data_ptr(), scale, rec.cin, rec.cout,
+      ops._call("xmc_subpixel_prep", params[rec.w_off:].data_ptr(), scale, rec.cin, rec.cout, int(self.S == 3),
                 self.arena[wf_off:].data_ptr(), self.arena[vd_off:].data_ptr(), _lib.stream())
     self.prepped_for = self.prep_key(params, u0_new)
 
@@ -405,9 +425,14 @@ class GeneratorEngine:
     return ops.bn_eval_stats(mean, var, C)
 
   def forward(self, params, stats, batch, z, train=True, new_stats=None, fake_bf16=None):
-    """Returns (image fp32 [B,S,S,3] in [0,1], ctx). `fake_bf16`: optional bf16 [B,S,S,3] view that also receives
-    the image (the second half of the discriminator input). Weights must have been prepared (prep_weights)."""
+    """Returns (image fp32 [B,S,S,3] in [0,1], ctx). `fake_bf16`: optional [B,S,S,3] view in the activation dtype that
+    also receives the image (the second half of the discriminator input). Weights must have been prepared."""
+    with ops.act_dtype(self.act):
+      return self._forward(params, stats, batch, z, train, new_stats, fake_bf16)
+
+  def _forward(self, params, stats, batch, z, train, new_stats, fake_bf16):
     P = params
+    S_ = self.S
     E, zd, cd, scd = self.E, self.zd, self.cd, self.scd
     B = z.shape[0]
     cond = batch["sentence_embedding"].reshape(B, E)
@@ -426,7 +451,7 @@ class GeneratorEngine:
     x = ops.conv_fwd(as4(gc[:, zd:]), self._wk(r), 1, r.cout, bias=P[r.b_off:], ldb=r.ld_fwd)
     x = x.view(B, 4, 4, self.c0)
     gbC = ops.conv_fwd(as4(gc), self.arena[self.cbn_fwd_off:], 1, self.NC, bias=P[self.cbn_bias_off:],
-                       ldb=cd).view(B, self.NC)
+                       ldb=cd * S_).view(B, self.NC)
     ctx.update(cond_bf=cond_bf, gc=gc, gbC=gbC, blocks=[])
 
     gb, Hc = gbC, 1
@@ -441,7 +466,7 @@ class GeneratorEngine:
         attn = ops.attention_g_fwd(xq.view(B, R, E), what.view(B, Lw, E), max_len, self.gamma, spatial)
         ops.bcast_rows(gc, R, spatial[:, E:])
         gbL = ops.conv_fwd(as4(spatial), self.arena[self.lcbn_fwd_off:], 1, self.NL, bias=P[self.lcbn_bias_off:],
-                           ldb=scd).view(B * R, self.NL)
+                           ldb=scd * S_).view(B * R, self.NL)
         ctx.update(x16=x, xq=xq, what=what, attn=attn, spatial=spatial, gbL=gbL, R=R, Hc=xq.shape[1])
         gb, Hc = gbL, xq.shape[1]
       bn0 = (name, ("ConditionalBatchNorm_0" if kind == "cbn" else "LocalConditionalBatchNorm_0"))
@@ -454,7 +479,7 @@ class GeneratorEngine:
       # (sub-pixel form: four 2x2 convs, 2.25x fewer FLOPs, the up-sampled tensor is never materialised)
       u = ops.bn_apply(x, mr0, gb, Hc, g0, b0, True, False)
       wf_off, _ = self.subpixel[(name, self.cpre + "_0")]
-      c1 = ops.conv_fwd(u, self.arena[wf_off:], 2, bcout, bias=P[r0.b_off:], ldb=4 * bcin, pad=1, subpixel=True)
+      c1 = ops.conv_fwd(u, self.arena[wf_off:], 2, bcout, bias=P[r0.b_off:], ldb=4 * bcin * S_, pad=1, subpixel=True)
       mr1 = self._bn(c1, bn1, stats, new_stats, train, grp)
       h2 = ops.bn_apply(c1, mr1, gb, Hc, g1, b1, True, False)
       sc = ops.conv_fwd(x, self._wk(r2), 1, bcout, bias=P[r2.b_off:], ldb=r2.ld_fwd)
@@ -468,9 +493,9 @@ class GeneratorEngine:
     r = self.convs[(self.cpre + "_1",)]
     S = x.shape[1]
     img = ops.empty((B, S, S, 3), F32)
-    ops._call("xmc_conv_c3_out", hf.data_ptr(), self._wk(r).data_ptr(), r.ld_fwd, P[r.b_off:].data_ptr(), B, S, S,
-              self.c_last, 3, 3, 1, 0, img.data_ptr(), fake_bf16.data_ptr() if fake_bf16 is not None else None,
-              _lib.stream())
+    ops._call("xmc_conv_c3_out", hf.data_ptr(), ops._f32(hf), self._wk(r).data_ptr(), r.ld_fwd, P[r.b_off:].data_ptr(),
+              B, S, S, self.c_last, 3, 3, 1, 0, img.data_ptr(),
+              fake_bf16.data_ptr() if fake_bf16 is not None else None, _lib.stream())
     ctx.update(x_last=x, mrf=mrf, hf=hf, img=img)
     return img, ctx
 
@@ -481,6 +506,11 @@ class GeneratorEngine:
 
   def backward(self, ctx, d_img, params, grads):
     """Accumulates d(loss)/d(params) into the flat fp32 buffer `grads` given d(loss)/d(image) (fp32)."""
+    with ops.act_dtype(self.act):
+      self._backward(ctx, d_img, params, grads)
+
+  def _backward(self, ctx, d_img, params, grads):
+    S_ = self.S
     B, E, zd, cd, scd = ctx["B"], self.E, self.zd, self.cd, self.scd
     S = d_img.shape[1]
     gbC, gbL, R, Hc16 = ctx["gbC"], ctx["gbL"], ctx["R"], ctx["Hc"]
@@ -490,19 +520,23 @@ class GeneratorEngine:
 
     # output head: tanh, conv3x3 (C -> 3)
     dpre = ops.empty((B, S, S, 3))
-    ops._call("xmc_tanh01_bwd", d_img.data_ptr(), ctx["img"].data_ptr(), d_img.numel(), dpre.data_ptr(), _lib.stream())
+    ops._call("xmc_tanh01_bwd", d_img.data_ptr(), ctx["img"].data_ptr(), d_img.numel(), dpre.data_ptr(), ops._f32(dpre),
+              _lib.stream())
     r = self.convs[(self.cpre + "_1",)]
     C = self.c_last
     # the weight gradient of the 3-channel output conv runs on the tensor-core wgrad kernel over a zero-bordered
     # 8-channel copy of d(pre-tanh) (packed-window form: M = 3 kw x 8 channels per kh tap)
-    dpad = ops.c3_pad(dpre)
-    ops.c3_wgrad(dpad, ctx["hf"], 1, C * 3, 1, 3, grads[r.w_off:])
+    if self.act == F32:   # fp32 activations: the CUDA-core kernel (fp32 FMAs)
+      ops.wgrad_c3(dpre, ctx["hf"], 3, 1, C * 3, 1, 3, grads[r.w_off:])
+    else:
+      dpad = ops.c3_pad(dpre)
+      ops.c3_wgrad(dpad, ctx["hf"], 1, C * 3, 1, 3, grads[r.w_off:])
     ops.colsum(dpre, grads[r.b_off:])
     # the input gradient stays on the CUDA-core kernel: as a GEMM it is a 3-k-iteration tile bound by the epilogue's
     # latency (measured 0.42 ms vs 0.32 ms per 112-image launch); ops.c3_conv is the tensor-core form
     dhf = ops.empty((B, S, S, C))
-    ops._call("xmc_conv_c3_in", dpre.data_ptr(), self._wd(r).data_ptr(), r.ld_dg, None, B, S, S, C, 3, 3, 0,
-              dhf.data_ptr(), _lib.stream())
+    ops._call("xmc_conv_c3_in", dpre.data_ptr(), ops._f32(dpre), self._wd(r).data_ptr(), r.ld_dg, None, B, S, S, C, 3, 3,
+              0, dhf.data_ptr(), _lib.stream())
     _, gf_, bf_ = self.bn_index[("LocalConditionalBatchNorm_0",)]
     dout = ops.bn_bwd(dhf, ctx["x_last"], ctx["mrf"], gbL, dgbL, Hc16, gf_, bf_, True, False, group=grp)
 
@@ -527,7 +561,7 @@ class GeneratorEngine:
       ops.wgrad(sv["u"], dc1, 3, grads[r0.w_off:], out_mode=0, ld_out=bcout, tap_stride=bcin * bcout, subpixel=True)
       ops.colsum(dc1, grads[r0.b_off:])
       _, vd_off = self.subpixel[(name, self.cpre + "_0")]
-      du = ops.conv_fwd(dc1, self.arena[vd_off:], 4, bcin, ldb=16 * bcout, stride=2, pad=1)
+      du = ops.conv_fwd(dc1, self.arena[vd_off:], 4, bcin, ldb=16 * bcout * S_, stride=2, pad=1)
       dxa = ops.bn_bwd(du, sv["x"], sv["mr0"], gb, dgb, sv["Hc"], g0, b0, True, False, group=grp)
       # shortcut (Conv_2 at low resolution)
       dsc = ops.pool2(dout, scale=1.0)
@@ -543,7 +577,7 @@ class GeneratorEngine:
         ops.wgrad(as4(gc), as4(dgbC_bf[:, o:o + Cc]), 1, grads[L.off(prefix + (leaf, "kernel")):], out_mode=0,
                   ld_out=Cc, tap_stride=cd * Cc)
     ops.colsum(dgbC_bf, grads[self.cbn_bias_off:])
-    dgc = ops.conv_fwd(as4(dgbC_bf), self.arena[self.cbn_dg_off:], 1, cd, ldb=self.NC, out_dtype=F32).view(B, cd)
+    dgc = ops.conv_fwd(as4(dgbC_bf), self.arena[self.cbn_dg_off:], 1, cd, ldb=self.NC * S_, out_dtype=F32).view(B, cd)
     ops.sum_rows(ctx["dspatial"][:, E:], B, R, dgc, accumulate=True)
     dgc_bf = ops.cast_to_bf16(dgc)
     r = self.convs[(self.dpre + "_0",)]
@@ -567,7 +601,7 @@ class GeneratorEngine:
         ops.wgrad(as4(spatial), as4(dgbL_bf[:, o:o + Cc]), 1, grads[L.off(prefix + (leaf, "kernel")):], out_mode=0,
                   ld_out=Cc, tap_stride=scd * Cc)
     ops.colsum(dgbL_bf, grads[self.lcbn_bias_off:])
-    dspatial = ops.conv_fwd(as4(dgbL_bf), self.arena[self.lcbn_dg_off:], 1, scd, ldb=self.NL).view(B * R, scd)
+    dspatial = ops.conv_fwd(as4(dgbL_bf), self.arena[self.lcbn_dg_off:], 1, scd, ldb=self.NL * self.S).view(B * R, scd)
     ctx["dspatial"] = dspatial
     xq = ctx["xq"]
     dq = ops.attention_g_bwd(dspatial, xq.view(B, R, E), ctx["what"].view(B, ctx["Lw"], E), ctx["attn"], self.gamma)
@@ -611,7 +645,7 @@ class WordShared:
     self.BL = B * Lw
     self.ldS = _r8(self.BL)
     self.words = words.reshape(self.BL, E).contiguous()
-    self.what_bf, self.winv = ops.l2norm_rows(self.words, out_dtype=BF16)
+    self.what_bf, self.winv = ops.l2norm_rows(self.words, out_dtype=ops.ACT[0])
     self.max_len = max_len.reshape(B).contiguous()
     self._whatT = None
 
@@ -631,13 +665,13 @@ class WordLoss:
     self.ws, self.B, self.Rn, self.E = ws, B, Rn, E
     BL, ldS = ws.BL, ws.ldS
     padded = ldS != BL
-    self.Rh, self.rinv = ops.l2norm_rows(R.reshape(B * Rn, E), out_dtype=BF16)
+    self.Rh, self.rinv = ops.l2norm_rows(R.reshape(B * Rn, E), out_dtype=ops.ACT[0])
     S = ops.empty((B * Rn, ldS), F32)
     ops.conv_fwd(as4(self.Rh), ws.what_bf, 1, BL, ldb=E, out=as4(S[:, :BL]))
     self.alpha = ops.empty((B * Rn, ldS))
-    self.alphaT = ops.zeros((B, ldS, Rn), BF16) if padded else ops.empty((B, ldS, Rn))
+    self.alphaT = ops.zeros((B, ldS, Rn), ops.ACT[0]) if padded else ops.empty((B, ldS, Rn))
     ops._call("xmc_wl_softmax", S.data_ptr(), B, Rn, BL, ldS, self.G1, self.alpha.data_ptr(), self.alphaT.data_ptr(),
-              _lib.stream())
+              ops._f32(self.alpha), _lib.stream())
     self.ctx = ops.empty((B, ldS, E), F32)
     ops.wgrad(self.alpha.view(B, 1, Rn, ldS), self.Rh.view(B, 1, Rn, E), 1, self.ctx, out_mode=1, batched=True,
               ld_out=E, tap_stride=0, batch_stride=ldS * E)
@@ -658,16 +692,16 @@ class WordLoss:
     ws, B, Rn, E = self.ws, self.B, self.Rn, self.E
     BL, ldS = ws.BL, ws.ldS
     padded = ldS != BL
-    dctx = ops.zeros((B, ldS, E), BF16) if padded else ops.empty((B, ldS, E))
+    dctx = ops.zeros((B, ldS, E), ops.ACT[0]) if padded else ops.empty((B, ldS, E))
     ops._call("xmc_wl_cos_bwd", self.dsim.data_ptr(), self.pw.data_ptr(), self.cos.data_ptr(), self.cnorm.data_ptr(),
               self.ctx.data_ptr(), ldS * E, ws.words.data_ptr(), ws.winv.data_ptr(), B, ws.Lw, E, self.G3,
-              dctx.data_ptr(), ldS * E, _lib.stream())
+              dctx.data_ptr(), ldS * E, ops._f32(dctx), _lib.stream())
     dalpha = ops.empty((B * Rn, ldS), F32)
     ops.conv_fwd(self.Rh.view(B, 1, Rn, E), dctx, 1, BL, ldb=E, batched=True, stride_b=ldS * E,
                  out=dalpha.view(B, 1, Rn, ldS)[..., :BL])
     dS = ops.empty((B * Rn, ldS))
     ops._call("xmc_wl_softmax_bwd", self.alpha.data_ptr(), dalpha.data_ptr(), B, Rn, BL, ldS, self.G1, dS.data_ptr(),
-              _lib.stream())
+              ops._f32(dS), _lib.stream())
     tmp = ops.empty((B * Rn, E))
     ops.wgrad(self.alphaT.view(B, 1, ldS, Rn), dctx.view(B, 1, ldS, E), 1, tmp, out_mode=2, batched=True, ld_out=E,
               tap_stride=0, batch_stride=Rn * E)
@@ -689,6 +723,8 @@ class DiscriminatorEngine:
     else:
       raise ValueError(f"image_size {config.image_size} is not supported (reference: xmc_net.py:81-86)")
     self.config = config
+    self.act = act_dtype_of(config)          # see GeneratorEngine
+    self.S = S_ = 3 if self.act == F32 else 1
     self.E = E = embedding_dim
     df = config.df_dim
     self.sn = bool(config.d_spectral_norm)
@@ -710,14 +746,14 @@ class DiscriminatorEngine:
       b_off = L.add(path + ("bias",), (cout_,))
       taps = kh * kh
       slot = self.sntab.add(path, w_off, taps * cin_, cout_) if self.sn else -1
-      ld_fwd, ld_dg = _r8(taps * cin_), _r8(taps * cout_)
+      ld_fwd, ld_dg = _r8(S_ * taps * cin_), _r8(S_ * taps * cout_)
       fwd_off = dg_off = -1
       if prep:
         fwd_off = self.arena_size
         self.arena_size += _r8(cout_) * ld_fwd
         dg_off = self.arena_size
         self.arena_size += _r8(cin_) * ld_dg
-        self.prep.add(w_off, taps, cin_, cout_, fwd_off, ld_fwd, dg_off, ld_dg, slot)
+        self.prep.add(w_off, taps, cin_, cout_, fwd_off, ld_fwd, dg_off, ld_dg, slot, split=S_ == 3)
       self.convs[path] = ConvRec(path, kh, cin_, cout_, w_off, b_off, fwd_off, ld_fwd, dg_off, ld_dg, slot)
 
     cp = self.cpre
@@ -787,9 +823,13 @@ class DiscriminatorEngine:
 
   # ------------------------------------------------------------------------------------------------------------
   def forward(self, params, images, batch, losses, need_g=True, stats=None):
-    """images: bf16 [2B,S,S,3] (real first). Fills `losses` (fp32[16]) slots, returns (logit fp32 [2B], ctx).
-    stats: optional fp32 [16,2] receiving (accuracy, entropy) per loss slot — the side statistics of
+    """images: [2B,S,S,3] in the activation dtype (real first). Fills `losses` (fp32[16]) slots, returns (logit fp32
+    [2B], ctx). stats: optional fp32 [16,2] receiving (accuracy, entropy) per loss slot — the side statistics of
     attention_lib.get_statistics, dead on the train path and therefore off by default."""
+    with ops.act_dtype(self.act):
+      return self._forward(params, images, batch, losses, need_g, stats)
+
+  def _forward(self, params, images, batch, losses, need_g, stats):
     st = (lambda name: stats[LOSS_SLOTS[name]]) if stats is not None else (lambda name: None)
     P = params
     cfg = self.config
@@ -801,16 +841,17 @@ class DiscriminatorEngine:
     ctx = {"B": B, "need_g": need_g, "images": images}
     r0, r1, r2 = (self.convs[("DiscOptimizedBlock_0", cp + f"_{i}")] for i in range(3))
     xp = ops.empty((N2, S // 2, S // 2, 3))
-    ops._call("xmc_pool2_small", images.data_ptr(), N2, S // 2, S // 2, 3, 0.25, xp.data_ptr(), _lib.stream())
+    f32 = ops._f32(images)
+    ops._call("xmc_pool2_small", images.data_ptr(), f32, N2, S // 2, S // 2, 3, 0.25, xp.data_ptr(), _lib.stream())
     sc = ops.empty((N2, S // 2, S // 2, df))
-    ops._call("xmc_conv_c3_in", xp.data_ptr(), self._wk(r2).data_ptr(), r2.ld_fwd, P[r2.b_off:].data_ptr(), N2, S // 2,
-              S // 2, df, 1, 1, 0, sc.data_ptr(), _lib.stream())
+    ops._call("xmc_conv_c3_in", xp.data_ptr(), f32, self._wk(r2).data_ptr(), r2.ld_fwd, P[r2.b_off:].data_ptr(), N2,
+              S // 2, S // 2, df, 1, 1, 0, sc.data_ptr(), _lib.stream())
     # first conv (3 -> df, 3x3): forward on the CUDA-core kernel (see GeneratorEngine.backward), its weight gradient
     # on the tensor-core wgrad kernel over the zero-bordered 8-channel image copy made here
-    xpad = ops.c3_pad(images)
+    xpad = ops.c3_pad(images) if not f32 else None   # fp32 mode: the CUDA-core weight-gradient kernel reads `images`
     c1r = ops.empty((N2, S, S, df))
-    ops._call("xmc_conv_c3_in", images.data_ptr(), self._wk(r0).data_ptr(), r0.ld_fwd, P[r0.b_off:].data_ptr(), N2, S, S,
-              df, 3, 3, 1, c1r.data_ptr(), _lib.stream())
+    ops._call("xmc_conv_c3_in", images.data_ptr(), f32, self._wk(r0).data_ptr(), r0.ld_fwd, P[r0.b_off:].data_ptr(), N2,
+              S, S, df, 3, 3, 1, c1r.data_ptr(), _lib.stream())
     c2 = ops.conv_fwd(c1r, self._wk(r1), 3, df, bias=P[r1.b_off:], ldb=r1.ld_fwd)
     x, xr = ops.pool2(c2, low=sc, want_relu=True)
     del c2, sc
@@ -873,6 +914,10 @@ class DiscriminatorEngine:
     ops.colsum(dy if dy_low is None else dy_low, grads[rec.b_off:])
 
   def _backward_trunk(self, ctx, dout, sl, grads, d_xw, xw_sub, want_image_grad):
+    with ops.act_dtype(self.act):
+      return self._backward_trunk_impl(ctx, dout, sl, grads, d_xw, xw_sub, want_image_grad)
+
+  def _backward_trunk_impl(self, ctx, dout, sl, grads, d_xw, xw_sub, want_image_grad):
     """Backward through the residual trunk for images `sl` (a slice of the 2B batch). dout: gradient wrt the last
     block output. d_xw: gradient wrt the word-feature map (bf16 [n,16,16,E]) of the images `xw_sub` (a slice relative
     to `sl`), or None. grads None -> dgrad only."""
@@ -918,27 +963,31 @@ class DiscriminatorEngine:
       self._wgrad(r1, c1r, g, grads, dout)
     dc1 = ops.conv_fwd(g, self._wd(r1), 3, df, mask=c1r, ldb=r1.ld_dg)
     if wg:
-      ops.c3_wgrad(b0["xpad"][sl], dc1, 0, 3 * df, df, 1, grads[r0.w_off:])
+      if self.act == F32:
+        ops.wgrad_c3(images, dc1, 3, 0, 3 * df, df, 1, grads[r0.w_off:])
+      else:
+        ops.c3_wgrad(b0["xpad"][sl], dc1, 0, 3 * df, df, 1, grads[r0.w_off:])
       ops.colsum(dc1, grads[r0.b_off:])
-      h2 = S // 2
-      part = ops.empty(n * ((h2 + 7) // 8) * ((h2 + 63) // 64) * 3 * df, F32)
-      ops._call("xmc_wgrad_c3", xp.data_ptr(), dout.data_ptr(), n, h2, h2, df, 1, 1, 0, 3 * df, df, 1,
-                grads[r2.w_off:].data_ptr(), part.data_ptr(), _lib.stream(), launches=2)
+      ops.wgrad_c3(xp, dout, 1, 0, 3 * df, df, 1, grads[r2.w_off:])
       ops.colsum(dout, grads[r2.b_off:])
     if not want_image_grad:
       return None
     dimg = ops.empty((n, S, S, 3), F32)
-    ops._call("xmc_conv_c3_out", dc1.data_ptr(), self._wd(r0).data_ptr(), r0.ld_dg, None, n, S, S, df, 3, 3, 0, 0,
-              dimg.data_ptr(), None, _lib.stream())
+    ops._call("xmc_conv_c3_out", dc1.data_ptr(), ops._f32(dc1), self._wd(r0).data_ptr(), r0.ld_dg, None, n, S, S, df, 3,
+              3, 0, 0, dimg.data_ptr(), None, _lib.stream())
     dxp = ops.empty((n, S // 2, S // 2, 3), F32)
-    ops._call("xmc_conv_c3_out", dout.data_ptr(), self._wd(r2).data_ptr(), r2.ld_dg, None, n, S // 2, S // 2, df, 1, 1,
-              0, 0, dxp.data_ptr(), None, _lib.stream())
+    ops._call("xmc_conv_c3_out", dout.data_ptr(), ops._f32(dout), self._wd(r2).data_ptr(), r2.ld_dg, None, n, S // 2,
+              S // 2, df, 1, 1, 0, 0, dxp.data_ptr(), None, _lib.stream())
     ops._call("xmc_unpool2_add_f32", dxp.data_ptr(), n, S // 2, S // 2, 3, 0.25, dimg.data_ptr(), _lib.stream())
     return dimg
 
   def backward_d(self, ctx, params, grads):
     """d(d_loss)/d(params_d) accumulated into `grads` (holds d/dW~ for spectrally normalised kernels until
     sn_backward runs). d_loss = hinge_d + real_word + real_sentence (xmc_gan.py:146-153,237-241)."""
+    with ops.act_dtype(self.act):
+      self._backward_d(ctx, params, grads)
+
+  def _backward_d(self, ctx, params, grads):
     P = params
     B, C, E = ctx["B"], self.c_last, self.E
     N2 = 2 * B
@@ -966,6 +1015,10 @@ class DiscriminatorEngine:
   def backward_g(self, ctx, params):
     """d(g_loss)/d(fake images): fp32 [B,S,S,3]. g_loss's discriminator part = hinge_g + fake_word + fake_sentence +
     image_contrastive (xmc_gan.py:146-154). Only the fake half is pulled back, dgrad only."""
+    with ops.act_dtype(self.act):
+      return self._backward_g(ctx, params)
+
+  def _backward_g(self, ctx, params):
     P = params
     B, C, E = ctx["B"], self.c_last, self.E
     rd0 = self.convs[(self.dpre + "_0",)]
@@ -1127,14 +1180,14 @@ class ResNetEngine:
     N, S = images_f32.shape[0], images_f32.shape[1]
     T, TP, W0 = self.T, self.TP, self.width
     xpad = ops.empty((N, TP, TP, 8))
-    ops._call("xmc_resize_bilinear_pad", images_f32.data_ptr(), N, S, T, TP, self.PAD_LO, xpad.data_ptr(),
+    ops._call("xmc_resize_bilinear_pad", images_f32.data_ptr(), N, S, T, TP, self.PAD_LO, 0, xpad.data_ptr(),
               _lib.stream())
     rec = self.convs[("init_conv",)]
     view = dict(Hout=T // 2, Wout=T // 2, KH=7, KW=1, strideH=2, strideW=1, Hin=TP, Win=T // 2, pitchW=16,
                 pitchH=TP * 8, pitchN=TP * TP * 8)
     stem = ops.conv_fwd(xpad, self.arena[self.stem_off:], 7, W0, bias=self._bias(rec), ldb=392, c=56, view=view)
     x = ops.empty((N, T // 4, T // 4, W0))
-    ops._call("xmc_maxpool3s2", stem.data_ptr(), N, T // 2, W0, x.data_ptr(), _lib.stream())
+    ops._call("xmc_maxpool3s2", stem.data_ptr(), ops._f32(stem), N, T // 2, W0, x.data_ptr(), _lib.stream())
     return stem, x
 
   def stem_backward(self, dpool, stem, pooled, S, d_images):
@@ -1142,11 +1195,11 @@ class ResNetEngine:
     n = dpool.shape[0]
     T, W0 = self.T, self.width
     dstem = ops.empty((n, T // 2, T // 2, W0))
-    ops._call("xmc_maxpool3s2_bwd", dpool.data_ptr(), stem.data_ptr(), pooled.data_ptr(), n, T // 2, W0,
+    ops._call("xmc_maxpool3s2_bwd", dpool.data_ptr(), stem.data_ptr(), pooled.data_ptr(), ops._f32(stem), n, T // 2, W0,
               dstem.data_ptr(), _lib.stream())
     d224 = ops.empty((n, T, T, 3), F32)
-    ops._call("xmc_stem_dgrad", dstem.data_ptr(), self.arena[self.stem_off:].data_ptr(), n, T, T // 2, W0, self.PAD_LO,
-              d224.data_ptr(), _lib.stream())
+    ops._call("xmc_stem_dgrad", dstem.data_ptr(), ops._f32(dstem), self.arena[self.stem_off:].data_ptr(), None, n, T,
+              T // 2, W0, self.PAD_LO, d224.data_ptr(), _lib.stream())
     ops._call("xmc_resize_bilinear_bwd", d224.data_ptr(), n, S, T, d_images.data_ptr(), _lib.stream())
 
   def block_forward(self, x, spec):
@@ -1173,7 +1226,8 @@ class ResNetEngine:
     dr2 = ops.conv_fwd(g, self.arena[r3c["dg_off"]:], 1, f, mask=r2, ldb=r3c["ld_dg"])
     if stride == 2:
       z = ops.empty((n, 2 * dr2.shape[1], 2 * dr2.shape[2], f))
-      ops._call("xmc_zero_insert2", dr2.data_ptr(), n, dr2.shape[1], dr2.shape[2], f, z.data_ptr(), _lib.stream())
+      ops._call("xmc_zero_insert2", dr2.data_ptr(), ops._f32(dr2), n, dr2.shape[1], dr2.shape[2], f, z.data_ptr(),
+                _lib.stream())
       dr1 = ops.conv_fwd(z, self.arena[r2c["dg_off"]:], 3, f, mask=r1, ldb=r2c["ld_dg"], pad=2)
     else:
       dr1 = ops.conv_fwd(dr2, self.arena[r2c["dg_off"]:], 3, f, mask=r1, ldb=r2c["ld_dg"])
@@ -1182,7 +1236,8 @@ class ResNetEngine:
       g_in = g
       if stride == 2:
         g_in = ops.empty((n, 2 * g.shape[1], 2 * g.shape[2], 4 * f))
-        ops._call("xmc_zero_insert2", g.data_ptr(), n, g.shape[1], g.shape[2], 4 * f, g_in.data_ptr(), _lib.stream())
+        ops._call("xmc_zero_insert2", g.data_ptr(), ops._f32(g), n, g.shape[1], g.shape[2], 4 * f, g_in.data_ptr(),
+                  _lib.stream())
       sg = ops.conv_fwd(g_in, self.arena[pc["dg_off"]:], 1, cin, ldb=pc["ld_dg"])
     else:
       sg = g

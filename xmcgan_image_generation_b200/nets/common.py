@@ -16,9 +16,9 @@ def dsample(x):
   if x.shape[1] % 2 or x.shape[2] % 2:
     raise ValueError("dsample needs even spatial sizes")
   if x.shape[3] % 8:
-    out = ops.empty((x.shape[0], x.shape[1] // 2, x.shape[2] // 2, x.shape[3]))
-    ops._call("xmc_pool2_small", x.data_ptr(), x.shape[0], x.shape[1] // 2, x.shape[2] // 2, x.shape[3], 0.25,
-              out.data_ptr(), ops._lib.stream())
+    out = ops.empty((x.shape[0], x.shape[1] // 2, x.shape[2] // 2, x.shape[3]), x.dtype)
+    ops._call("xmc_pool2_small", x.data_ptr(), ops._f32(x), x.shape[0], x.shape[1] // 2, x.shape[2] // 2, x.shape[3],
+              0.25, out.data_ptr(), ops._lib.stream())
     return out
   return ops.pool2(x, scale=0.25)
 

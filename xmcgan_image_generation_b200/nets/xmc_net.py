@@ -20,7 +20,7 @@ _ENGINES = {}
 
 def _cfg_key(config, kind, embedding_dim):
   keys = ("image_size", "gf_dim", "df_dim", "z_dim", "g_spectral_norm", "d_spectral_norm", "batch_norm_group_size",
-          "gamma_for_g", "word_contrastive", "sentence_contrastive", "image_contrastive", "cond_size")
+          "gamma_for_g", "word_contrastive", "sentence_contrastive", "image_contrastive", "cond_size", "dtype")
   return (kind, embedding_dim) + tuple(getattr(config, k) for k in keys)
 
 
@@ -147,7 +147,8 @@ class Discriminator:
     batch = batch_to_device(cond_dict)
     x = _to_dev(x)
     n2, s = x.shape[0], x.shape[1]
-    images = ops.cast_to_bf16(x.reshape(n2 * s * s, 3)).view(n2, s, s, 3)
+    with ops.act_dtype(eng.act):
+      images = ops.cast_to_bf16(x.reshape(n2 * s * s, 3)).view(n2, s, s, 3)
     params = as_flat(eng.layout, variables["params"])
     u0 = as_flat(eng.u_layout, variables["spectral_norm_stats"]) if eng.sn else None
     u0_new = torch.empty_like(u0) if eng.sn else None

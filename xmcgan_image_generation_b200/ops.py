@@ -7,9 +7,29 @@ import torch
 from . import _lib
 from ._lib import BnDesc, ConvDesc, WgradDesc, ptr, stream
 
+import contextlib
+
 BF16 = torch.bfloat16
 F32 = torch.float32
 LAUNCHES = [0]
+# Activation dtype of the program being issued: bf16 (the reference's config.dtype default, coco_xmc.py:45) or fp32
+# (config.dtype = "float32"; the frozen ResNet branch). Host-side bookkeeping only: every wrapper below derives the
+# kernel's activation type from the dtype of the tensors it is given, ACT only decides what `empty()` allocates.
+ACT = [BF16]
+
+
+@contextlib.contextmanager
+def act_dtype(dtype):
+  prev = ACT[0]
+  ACT[0] = dtype
+  try:
+    yield
+  finally:
+    ACT[0] = prev
+
+
+def _f32(t):
+  return int(t.dtype == F32)
 
 
 def _call(name, *args, launches=1):
@@ -33,8 +53,8 @@ def _check_dense_rows(t):
     exp *= t.shape[d]
 
 
-def empty(shape, dtype=BF16):
-  return torch.empty(shape, device="cuda", dtype=dtype)
+def empty(shape, dtype=None):
+  return torch.empty(shape, device="cuda", dtype=ACT[0] if dtype is None else dtype)
 
 
 def zeros(shape, dtype=F32):
@@ -42,17 +62,52 @@ def zeros(shape, dtype=F32):
 
 
 # ------------------------------------------------------------------------------------------------------------- GEMMs
+def split3(x2d, weights=False):
+  """fp32 [rows, C] (pitched) -> bf16 [rows, 3C]: [hi | lo | hi] for an activation, [hi | hi | lo] for the B operand
+  (a "weight" that is itself an activation, as in the word-loss GEMMs) — see XmcConvDesc.act_f32."""
+  rows, C = x2d.shape
+  out = empty((rows, 3 * C), BF16)
+  _call("xmc_split3", ptr(x2d), rows, C, x2d.stride(0), int(weights), ptr(out), 3 * C, stream())
+  return out
+
+
+def _split_nhwc(x, c=None):
+  """[N,H,W,>=C] fp32 view -> bf16 [N,H,W,3C] split copy (rows must collapse)."""
+  _check_dense_rows(x)
+  C = x.shape[-1] if c is None else c
+  rows = x.numel() // x.shape[-1]
+  flat = torch.as_strided(x, (rows, C), (x.stride(-2), 1))
+  return split3(flat).view(*x.shape[:-1], 3 * C)
+
+
 def conv_fwd(x, wk, kh, cout, *, bias=None, residual=None, res_shift=0, mask=None, relu=False, out=None,
-             out_dtype=BF16, alpha=1.0, ldb=None, batched=False, stride_b=0, c=None, stride=1, pad=None,
+             out_dtype=None, alpha=1.0, ldb=None, batched=False, stride_b=0, c=None, stride=1, pad=None,
              mask_last=False, view=None, subpixel=False):
   """x: [N,H,W,>=C] bf16 view (channel-contiguous); wk: bf16 tensor whose data pointer is the [cout][kh*kh*C] K-major
   matrix (row pitch ldb). Returns y [N,H/stride,W/stride,cout] (or writes into the `out` view).
   stride=2 reads the input at (h*2+kh-pad, w*2+kw-pad) (XLA SAME: pad low = 0 for a 3x3 or 1x1 kernel on an even
   input). `view`: dict overriding the input view (Hout, Wout, KH, KW, pitches, strides) for the ResNet stem."""
+  f32 = x.dtype == F32
+  if f32:
+    # fp32-activation mode: A = [hi | lo | hi] split of x (3C channels); wk is either already a split weight copy of
+    # the arena (bf16, ld given by the caller) or an fp32 activation used as the B operand, split here as [hi | hi | lo]
+    x = _split_nhwc(x, c)
+    c = None
+    if wk.dtype == F32:
+      Kb = wk.shape[-1]
+      ldb_in = ldb if ldb is not None else Kb
+      rows_b = wk.numel() // wk.shape[-1]
+      wk = split3(torch.as_strided(wk, (rows_b, Kb), (ldb_in, 1)), weights=True)
+      ldb, stride_b = 3 * Kb, 3 * stride_b
+    if out_dtype is None:
+      out_dtype = F32
+  elif out_dtype is None:
+    out_dtype = BF16
   N, H, W = x.shape[0], x.shape[1], x.shape[2]
   C = x.shape[3] if c is None else c
   _check_dense_rows(x)
   d = ConvDesc()
+  d.act_f32 = int(f32)
   d.N, d.H, d.W, d.C, d.ldA = N, H // stride, W // stride, C, _pix_ld(x)
   d.KH = d.KW = kh
   d.pad_h = d.pad_w = (kh // 2 if stride == 1 else 0) if pad is None else pad
@@ -92,6 +147,19 @@ def wgrad(xa, xb, kh, out, *, out_mode=0, batched=False, ld_out=None, tap_stride
           ca=None, cb=None, subpixel=False, view_a=None):
   """out[b][tap][ca][cb] (+)= sum_pixels xa[p+shift][ca] * xb[p][cb]. xa, xb: [N,H,W,C*] bf16 views.
   view_a: dict re-pitching xa (packed-window form, see XmcWgradDesc.HinA): KH, KW, Hin, pitchW, pitchH, pitchN."""
+  if xa.dtype == F32 or xb.dtype == F32:
+    # fp32-activation mode: dw = a_hi^T b_hi + a_lo^T b_hi + a_hi^T b_lo, three passes of the bf16 kernel over pitched
+    # views of the [hi | lo | hi] split copies, accumulated in the fp32 output (16 mantissa bits per operand)
+    assert xa.dtype == F32 and xb.dtype == F32 and view_a is None and ca is None and cb is None
+    Ca, Cb = xa.shape[-1], xb.shape[-1]
+    a3, b3 = _split_nhwc(xa), _split_nhwc(xb)
+    a_hi, a_lo, b_hi, b_lo = a3[..., :Ca], a3[..., Ca:2 * Ca], b3[..., :Cb], b3[..., Cb:2 * Cb]
+    assert out.dtype == F32
+    first = 1 if out_mode in (1, 2) else 0   # store modes: the first pass stores, the others accumulate
+    for i, (pa, pb) in enumerate(((a_hi, b_hi), (a_lo, b_hi), (a_hi, b_lo))):
+      wgrad(pa, pb, kh, out, out_mode=first if i == 0 else 0, batched=batched, ld_out=ld_out, tap_stride=tap_stride,
+            batch_stride=batch_stride, alpha=alpha, subpixel=subpixel)
+    return out
   # pixel grid of the reduction: xa's (the low-resolution input in sub-pixel mode), xb's for a re-pitched xa view
   N, H, W = (xa if view_a is None else xb).shape[:3]
   _check_dense_rows(xa)
@@ -164,9 +232,20 @@ def c3_wgrad(xpad, y, flip, s_tap, s_c3, s_c, out):
   _call("xmc_unpack_c3_wgrad", ptr(tmp), C, int(flip), s_tap, s_c3, s_c, ptr(out), stream())
 
 
+def wgrad_c3(x3, y, kh, flip, s_tap, s_c3, s_c, out):
+  """out[tap_o*s_tap + c3*s_c3 + c*s_c] += sum_p x3[p + d(tap)][c3] * y[p][c] on the CUDA-core kernel (any activation
+  dtype; fp32 FMAs): x3 [N,H,W,3], y [N,H,W,C], kh in {1, 3}. Deterministic (block partials added in order)."""
+  N, H, W, C = y.shape
+  assert x3.dtype == y.dtype
+  part = empty(N * ((H + 7) // 8) * ((W + 63) // 64) * kh * kh * 3 * C, F32)
+  _call("xmc_wgrad_c3", ptr(x3), ptr(y), _f32(y), N, H, W, C, kh, kh, int(flip), s_tap, s_c3, s_c, ptr(out), ptr(part),
+        stream(), launches=2)
+
+
 # --------------------------------------------------------------------------------------------------------- batch norm
-def _bn_desc(N, H, W, C, Hc, ldG, goff, boff, relu, upsample):
+def _bn_desc(N, H, W, C, Hc, ldG, goff, boff, relu, upsample, f32=0):
   d = BnDesc()
+  d.act_f32 = f32
   d.N, d.H, d.W, d.C, d.Hc = N, H, W, C, Hc
   d.ldG, d.goff, d.boff = ldG, goff, boff
   d.relu, d.upsample = int(relu), int(upsample)
@@ -189,7 +268,7 @@ def bn_stats(x):
   sums = empty(2 * C, F32)
   rows = partial_rows(P // 64)
   part = empty(rows * 2 * C, F32)
-  _call("xmc_bn_stats", ptr(x), P, C, C, ptr(sums), ptr(part), rows, stream(), launches=2)
+  _call("xmc_bn_stats", ptr(x), _f32(x), P, C, C, ptr(sums), ptr(part), rows, stream(), launches=2)
   return sums, P
 
 
@@ -208,8 +287,9 @@ def bn_eval_stats(ra_mean, ra_var, C, eps=1e-5):
 
 def bn_apply(x, mr, gb, Hc, goff, boff, relu, upsample):
   N, H, W, C = x.shape
-  d = _bn_desc(N, H, W, C, Hc, gb.stride(0), goff, boff, relu, upsample)
-  y = empty((N, 2 * H, 2 * W, C) if upsample else (N, H, W, C))
+  assert gb.dtype == x.dtype
+  d = _bn_desc(N, H, W, C, Hc, gb.stride(0), goff, boff, relu, upsample, _f32(x))
+  y = empty((N, 2 * H, 2 * W, C) if upsample else (N, H, W, C), x.dtype)
   _call("xmc_bn_apply", ctypes.byref(d), ptr(x), ptr(mr), ptr(gb), ptr(y), stream())
   return y
 
@@ -219,8 +299,8 @@ def bn_bwd(dy, x, mr, gb, dgb, Hc, goff, boff, relu, upsample, group=None):
   group: (process_group, size) of a cross-replica BatchNorm — the two per-channel sums of the backward are then
   all-reduced over the group (the transpose of the forward's pmean), see parallel.bn_group."""
   N, H, W, C = x.shape
-  assert gb.stride(0) == dgb.stride(0)
-  d = _bn_desc(N, H, W, C, Hc, gb.stride(0), goff, boff, relu, upsample)
+  assert gb.stride(0) == dgb.stride(0) and gb.dtype == x.dtype == dy.dtype
+  d = _bn_desc(N, H, W, C, Hc, gb.stride(0), goff, boff, relu, upsample, _f32(x))
   sums = empty(2 * C, F32)
   rows = partial_rows(N * Hc * Hc * 8, per_sm=8)   # the library clamps to the blocks it can fill
   part = empty(rows * 2 * C, F32)
@@ -230,7 +310,7 @@ def bn_bwd(dy, x, mr, gb, dgb, Hc, goff, boff, relu, upsample, group=None):
     from . import parallel
     parallel.all_reduce_sum_(sums, group=group[0])
     d.replicas = group[1]
-  dx = empty((N, H, W, C))
+  dx = empty((N, H, W, C), x.dtype)
   _call("xmc_bn_bwd_apply", ctypes.byref(d), ptr(dy), ptr(x), ptr(mr), ptr(gb), ptr(sums), ptr(dx), stream())
   return dx
 
@@ -238,16 +318,17 @@ def bn_bwd(dy, x, mr, gb, dgb, Hc, goff, boff, relu, upsample, group=None):
 # ------------------------------------------------------------------------------------------------- pooling and misc
 def pool2(a, b=None, low=None, scale=0.25, want_relu=False):
   N, H2, W2, C = a.shape
-  out = empty((N, H2 // 2, W2 // 2, C))
-  out_relu = empty((N, H2 // 2, W2 // 2, C)) if want_relu else None
-  _call("xmc_pool2", ptr(a), ptr(b), ptr(low), N, H2 // 2, W2 // 2, C, scale, ptr(out), ptr(out_relu), stream())
+  out = empty((N, H2 // 2, W2 // 2, C), a.dtype)
+  out_relu = empty((N, H2 // 2, W2 // 2, C), a.dtype) if want_relu else None
+  _call("xmc_pool2", ptr(a), ptr(b), ptr(low), _f32(a), N, H2 // 2, W2 // 2, C, scale, ptr(out), ptr(out_relu),
+        stream())
   return (out, out_relu) if want_relu else out
 
 
 def unpool2(dout, scale=0.25):
   N, H, W, C = dout.shape
-  g = empty((N, 2 * H, 2 * W, C))
-  _call("xmc_unpool2", ptr(dout), N, H, W, C, scale, ptr(g), stream())
+  g = empty((N, 2 * H, 2 * W, C), dout.dtype)
+  _call("xmc_unpool2", ptr(dout), _f32(dout), N, H, W, C, scale, ptr(g), stream())
   return g
 
 
@@ -258,28 +339,35 @@ def colsum(x, out, c=None):
   P = x.numel() // x.shape[-1]
   rows = partial_rows(P // 512)   # small tensors: one block adds straight into `out`
   part = empty(rows * C, F32) if rows > 1 else None
-  _call("xmc_colsum", ptr(x), P, C, _pix_ld(x), ptr(out), ptr(part), rows, stream(), launches=2 if rows > 1 else 1)
+  _call("xmc_colsum", ptr(x), _f32(x), P, C, _pix_ld(x), ptr(out), ptr(part), rows, stream(),
+        launches=2 if rows > 1 else 1)
 
 
 def relu_sumhw(x):
   N, H, W, C = x.shape
   out = empty((N, C), F32)
-  _call("xmc_relu_sumhw", ptr(x), N, H * W, C, ptr(out), stream())
+  _call("xmc_relu_sumhw", ptr(x), _f32(x), N, H * W, C, ptr(out), stream())
   return out
 
 
 def relu_sumhw_bwd(x, dout):
   N, H, W, C = x.shape
-  dx = empty((N, H, W, C))
-  _call("xmc_relu_sumhw_bwd", ptr(x), ptr(dout), N, H * W, C, ptr(dx), stream())
+  dx = empty((N, H, W, C), x.dtype)
+  _call("xmc_relu_sumhw_bwd", ptr(x), _f32(x), ptr(dout), N, H * W, C, ptr(dx), stream())
   return dx
 
 
 def cast_to_bf16(src, dst=None):
-  """2-D (rows, cols) fp32 -> bf16, pitched views allowed."""
+  """2-D (rows, cols) fp32 -> the activation dtype (bf16 cast; in fp32 mode the tensor itself, or a device-to-device
+  copy into `dst`), pitched views allowed."""
   rows, cols = src.shape
+  if (dst.dtype if dst is not None else ACT[0]) == F32:
+    if dst is None:
+      return src
+    dst.copy_(src)   # plumbing: device-to-device copy, no arithmetic
+    return dst
   if dst is None:
-    dst = empty((rows, cols))
+    dst = empty((rows, cols), BF16)
   _call("xmc_cast_f32_to_bf16", ptr(src), rows, cols, src.stride(0), ptr(dst), dst.stride(0), stream())
   return dst
 
@@ -296,12 +384,14 @@ def cast_to_f32(src, dst=None, accumulate=False):
 def bcast_rows(src, reps, dst):
   """dst[b*reps + r, :] = src[b, :]; dst is a [B*reps, cols] pitched bf16 view."""
   B, cols = src.shape
-  _call("xmc_bcast_rows", ptr(src), B, reps, cols, src.stride(0), ptr(dst), dst.stride(0), stream())
+  assert src.dtype == dst.dtype
+  _call("xmc_bcast_rows", ptr(src), _f32(src), B, reps, cols, src.stride(0), ptr(dst), dst.stride(0), stream())
 
 
 def sum_rows(src, B, reps, dst, accumulate=False):
   cols = src.shape[-1]
-  _call("xmc_sum_rows", ptr(src), B, reps, cols, src.stride(0), ptr(dst), dst.stride(0), int(accumulate), stream())
+  _call("xmc_sum_rows", ptr(src), _f32(src), B, reps, cols, src.stride(0), ptr(dst), dst.stride(0), int(accumulate),
+        stream())
 
 
 def axpy(y, x, a=1.0):
@@ -339,24 +429,26 @@ def attention_g_fwd(q, what, max_len, gamma, ctx_out):
   B, R, D = q.shape
   L = what.shape[1]
   attn = empty((B * R, L), F32)
-  _call("xmc_attention_g_fwd", ptr(q), q.stride(1), ptr(what), ptr(max_len), B, R, L, D, float(gamma), ptr(ctx_out),
-        ctx_out.stride(0), ptr(attn), stream())
+  assert q.dtype == ctx_out.dtype
+  _call("xmc_attention_g_fwd", ptr(q), _f32(q), q.stride(1), ptr(what), ptr(max_len), B, R, L, D, float(gamma),
+        ptr(ctx_out), ctx_out.stride(0), ptr(attn), stream())
   return attn
 
 
 def attention_g_bwd(dctx, q, what, attn, gamma):
   B, R, D = q.shape
   L = what.shape[1]
-  dq = empty((B, R, D))
-  _call("xmc_attention_g_bwd", ptr(dctx), dctx.stride(0), ptr(q), q.stride(1), ptr(what), ptr(attn), B, R, L, D,
+  dq = empty((B, R, D), q.dtype)
+  assert dctx.dtype == q.dtype
+  _call("xmc_attention_g_bwd", ptr(dctx), _f32(q), dctx.stride(0), ptr(q), q.stride(1), ptr(what), ptr(attn), B, R, L, D,
         float(gamma), ptr(dq), D, stream())
   return dq
 
 
 def transpose_bf16(src, ld_dst):
   rows, cols = src.shape
-  dst = empty((cols, ld_dst))
-  _call("xmc_transpose_bf16", ptr(src), rows, cols, src.stride(0), ptr(dst), ld_dst, stream())
+  dst = empty((cols, ld_dst), src.dtype)
+  _call("xmc_transpose_bf16", ptr(src), _f32(src), rows, cols, src.stride(0), ptr(dst), ld_dst, stream())
   return dst
 
 

@@ -21,7 +21,15 @@ class Optimizer:
     self.m = torch.zeros_like(target.buf)
     self.v = torch.zeros_like(target.buf)
     self.step = 0
+    self.step_dev = None  # device copy of `step` (int32[1]) once a GraphedTrainStep drives this optimiser
     self.learning_rate, self.beta1, self.beta2, self.eps = learning_rate, beta1, beta2, eps
+
+  def set_step(self, step):
+    """Sets the Adam step count on the host AND, when present, in the device counter the graph-replayed xmc_adam reads
+    (a checkpoint restore that only set `.step` would leave the bias corrections of later steps stale)."""
+    self.step = int(step)
+    if self.step_dev is not None:
+      self.step_dev.fill_(self.step)
 
 
 @dataclasses.dataclass
@@ -54,9 +62,13 @@ def train_step(rng, state, batch, gan_model, generator, discriminator, config, a
   """train_utils.train_step (train_utils.py:91-130): d_step_per_g_step-1 discriminator steps, then one joint step."""
   batch = xmc_net.batch_to_device(batch)
   batches = split_input_dict(batch, config.d_step_per_g_step)
+  # rngs = jax.random.split(rng, d_step_per_g_step) (train_utils.py:121): one derived seed per sub-step; they are only
+  # consumed when the batch carries no "z" (xmc_gan.py:131-135)
+  seed = xmc_net._seed_of(rng)
+  rngs = [(seed * 1000003 + i + 1) & 0x7FFFFFFF for i in range(config.d_step_per_g_step)]
   for i in range(config.d_step_per_g_step - 1):
-    state = gan_model.train_d(None, state, batches[i], generator, discriminator, config)
-  return gan_model.train_g_d(None, state, batches[-1], generator, discriminator, config, additional_data)
+    state = gan_model.train_d(rngs[i], state, batches[i], generator, discriminator, config)
+  return gan_model.train_g_d(rngs[-1], state, batches[-1], generator, discriminator, config, additional_data)
 
 
 def make_grid(samples, show_num=64):
@@ -70,16 +82,17 @@ def make_grid(samples, show_num=64):
   return grid.reshape(height * h_num, width * w_num, c)
 
 
-def generate_batch(rng, state, batch, generator, config, collect_all=False):
+def generate_batch(rng, state, batch, generator, config, collect_all=False, z=None):
   """train_utils.generate_batch (train_utils.py:245-309): samples with the current and with the EMA generator
   parameters in inference mode (running BatchNorm statistics; with g_spectral_norm the power iteration still runs but
-  u0 is not advanced), tiled into grids next to the original images. `rng` seeds z ~ N(0,1) (a torch CUDA generator:
-  JAX's threefry stream cannot be reproduced, so z differs from the reference's for the same key; pass batch["z"] to
-  pin it). collect_all gathers over all replicas (jax.lax.all_gather over "batch")."""
+  u0 is not advanced), tiled into grids next to the original images. As in the reference z is ALWAYS drawn fresh from
+  `rng` (train_utils.py:269-270; batch["z"] is ignored) — a torch CUDA generator, since JAX's threefry stream cannot
+  be reproduced; the extra keyword `z` pins it explicitly (parity tests). collect_all gathers over all replicas
+  (jax.lax.all_gather over "batch")."""
   batch = xmc_net.batch_to_device(batch)
   n = batch["image"].shape[0]
-  if "z" in batch and batch["z"].shape[0] == n:
-    z = batch["z"]
+  if z is not None:
+    z = xmc_net._to_dev(z)
   else:
     g = torch.Generator(device="cuda").manual_seed(xmc_net._seed_of(rng))
     z = torch.randn(n, config.z_dim, device="cuda", generator=g)
@@ -137,21 +150,31 @@ class GraphedTrainStep:
     # capturing ran the Python side of one step (host counters advanced) without executing it on the device
     self.state.step, self.state.g_optimizer.step, self.state.d_optimizer.step = steps_before
     self._d_steps = config.d_step_per_g_step
+    self._host_steps = (self.state.g_optimizer.step, self.state.d_optimizer.step)
 
   def __call__(self, batch):
+    """One train_step on `batch`. The graph is bound to the buffers of the state it was built on: restoring a
+    checkpoint INTO that state (checkpoint.from_state_dict copies in place and calls Optimizer.set_step) is fine, a
+    different TrainState object needs a new GraphedTrainStep."""
+    st = self.state
+    if (st.g_optimizer.step, st.d_optimizer.step) != self._host_steps:
+      # someone moved the host counters (Optimizer.set_step keeps the device counters in line): resynchronise
+      for opt in (st.g_optimizer, st.d_optimizer):
+        opt.set_step(opt.step)
     for k, dst in self.static_batch.items():
       dst.copy_(torch.as_tensor(batch[k]).reshape(dst.shape), non_blocking=True)
     self.graph.replay()
-    st = self.state
     st.step += 1
     st.g_optimizer.step += 1
     st.d_optimizer.step += self._d_steps
+    self._host_steps = (st.g_optimizer.step, st.d_optimizer.step)
     return st, self.metrics
 
 
 def create_train_state(config, rng, init_batch):
   """train_utils.create_train_state (train_utils.py:133-193)."""
-  dtype = torch.bfloat16 if config.dtype == "bfloat16" else torch.float32
+  from . import engine as _engine
+  dtype = _engine.act_dtype_of(config)   # bf16 or fp32 activations (train_utils.py:148-151); anything else raises
   if config.architecture == "xmc_net":
     generator_cls, discriminator_cls = xmc_net.Generator, xmc_net.Discriminator
   else:

@@ -101,12 +101,22 @@ def _adam(opt, grads, ema=None, decay=0.0):
   t = opt.step
   # graph mode (train_utils.GraphedTrainStep): the step count lives in a device int so that a replayed launch computes
   # this step's bias corrections itself
-  step_dev = getattr(opt, "step_dev", None)
+  step_dev = opt.step_dev
   ops._call("xmc_adam", opt.target.buf.data_ptr(), grads.data_ptr(), opt.m.data_ptr(), opt.v.data_ptr(),
             opt.target.buf.numel(), opt.learning_rate, opt.beta1, opt.beta2, opt.eps, 1.0 - opt.beta1 ** t,
             1.0 - opt.beta2 ** t, 1.0 / parallel.world_size(), ema.data_ptr() if ema is not None else None, decay,
             step_dev.data_ptr() if step_dev is not None else None, ops._lib.stream(),
             launches=2 if step_dev is not None else 1)
+
+
+def _with_z(rng, batch, config):
+  """The reference samples z = jax.random.normal(rng, (B, z_dim)) when the batch carries none (xmc_gan.py:131-135,
+  227-231). Here: a torch CUDA generator seeded from `rng` (JAX's threefry stream cannot be reproduced bit for bit)."""
+  if "z" in batch:
+    return batch
+  n = batch["image"].shape[0]
+  g = torch.Generator(device="cuda").manual_seed(xmc_net._seed_of(rng))
+  return dict(batch, z=torch.randn(n, config.z_dim, device="cuda", generator=g))
 
 
 def _forward_both(state, batch, config, ws, g_eng, d_eng, losses, keep_g_state, need_g):
@@ -145,7 +155,12 @@ def _swap_d_state(state, ws, d_eng):
 def train_d(rng, state, batch, generator, discriminator, config):
   """xmc_gan.train_d (xmc_gan.py:194-256): d_loss = hinge_d + real_word + real_sentence; gradient wrt params_d only;
   pmean; Adam on D; the generator's new batch statistics are discarded, the discriminator's new u0 is kept."""
-  batch = xmc_net.batch_to_device(batch)
+  with ops.act_dtype(_engine.act_dtype_of(config)):
+    return _train_d(rng, state, batch, generator, discriminator, config)
+
+
+def _train_d(rng, state, batch, generator, discriminator, config):
+  batch = _with_z(rng, xmc_net.batch_to_device(batch), config)
   g_eng, d_eng = _engines(config, batch)
   ws = _workspace(state, g_eng, d_eng)
   losses = torch.zeros(16, device="cuda")
@@ -167,7 +182,12 @@ def train_d(rng, state, batch, generator, discriminator, config):
 def train_g_d(rng, state, batch, generator, discriminator, config, additional_data):
   """xmc_gan.train_g_d (xmc_gan.py:93-191): one forward, two pull-backs at the old parameters (:162-167), pmean of
   both gradients (:170-171), Adam on D and G (:172-173), polyak EMA (:174-177), metrics (:185-190)."""
-  batch = xmc_net.batch_to_device(batch)
+  with ops.act_dtype(_engine.act_dtype_of(config)):
+    return _train_g_d(rng, state, batch, generator, discriminator, config, additional_data)
+
+
+def _train_g_d(rng, state, batch, generator, discriminator, config, additional_data):
+  batch = _with_z(rng, xmc_net.batch_to_device(batch), config)
   g_eng, d_eng = _engines(config, batch)
   ws = _workspace(state, g_eng, d_eng)
   losses = torch.zeros(16, device="cuda")
