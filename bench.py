@@ -182,7 +182,8 @@ def run_b200(args):
   generator, discriminator, state = train_utils.create_train_state(config, 42, host)
   # frozen ResNet-50 with synthetic weights (the reference's checkpoint is not shipped): same seed on every rank
   additional = xmc_gan.create_additional_data(
-      config, variables=engine.ResNetEngine().random_variables(7) if pretrained else None)
+      config, variables=engine.ResNetEngine().random_variables(7) if pretrained else None,
+      image_model_dtype=args.resnet_dtype)
 
   def barrier():
     if world > 1:
@@ -310,7 +311,7 @@ def run_b200(args):
       "config": {"workload": f"coco_xmc.py {config.image_size}px, per-GPU sub-batch B={B} (2B real images per step), "
                              "train_d + train_g_d, Adam, EMA, grad all-reduce",
                  "global_batch": B * world, "parallelism": f"dp{world}",
-                 "pretrained_image_contrastive": pretrained, "word_contrastive": bool(config.word_contrastive),
+                 "pretrained_image_contrastive": pretrained, "resnet_dtype": args.resnet_dtype if pretrained else None, "word_contrastive": bool(config.word_contrastive),
                  "cuda_graph": bool(use_graph),
                  "l2": "per-step working set (several GB of activations) >> 126 MB L2; no explicit flush",
                  "algorithmic_tflop_per_step_per_gpu": round(alg_tf, 2),
@@ -398,6 +399,8 @@ def main():
                   help="switch the frozen ResNet-50 image-image InfoNCE branch off (reference default: on)")
   ap.add_argument("--no-word-contrastive", action="store_true",
                   help="BASELINE config 5 (attention ablation): discriminator-side word_loss off (xmc_net.py:112)")
+  ap.add_argument("--resnet-dtype", default="float32", choices=["float32", "bfloat16"],
+                  help="precision of the frozen ResNet-50 branch: float32 = the reference's (default), bfloat16 = faster")
   ap.add_argument("--graph", type=int, default=1, choices=[0, 1, 2],
                   help="1: train_utils.GraphedTrainStep (train_step replayed from a CUDA graph) on one GPU, eager "
                        "train_step under torchrun; 2: graph replay for any N; 0: eager everywhere")

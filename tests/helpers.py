@@ -46,12 +46,12 @@ def rel(a, b):
   return ((a - b).norm() / (b.norm() + 1e-12)).item()
 
 
-def warm_adam(state, ostate, t=100, v0=1e-4):
+def warm_adam(state, ostate, t=100, v0=1e-2):
   """Puts the product TrainState and the oracle state into the same mid-training optimiser state: step t, first
   moments 0, second moments v0 everywhere. Adam's very first update is -lr * g / (|g| + eps) = -lr * sign(g): any
   element whose gradient sits at rounding-noise level moves by +-lr on a coin flip, which makes quantities measured
-  after it (train_g_d's metrics follow train_d's update) ill-conditioned. With v0 = (1e-2)^2 the update is linear in
-  g wherever |g| << 0.3 (and of a realistic size: ~15 lr g) and sign-like only where the sign is robust, so the comparison measures the gradient."""
+  after it (train_g_d's metrics follow train_d's update) ill-conditioned. With v0 = (1e-1)^2 the update is ~1.5 lr g,
+  linear in g wherever |g| << 3 and sign-like only where the sign is robust, so the comparison measures the gradient."""
   from oracle import xmc_oracle as orc
   for opt, key in ((state.g_optimizer, "g_opt"), (state.d_optimizer, "d_opt")):
     opt.step = t

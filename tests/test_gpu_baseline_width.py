@@ -103,18 +103,20 @@ def engine_slots():
 def test_forward_and_both_pullbacks_at_baseline_width():
   """128 px, gf = df = 96, E = 768, B = 8, bf16 (the reference default): generated image 2e-2 rel-L2, logits 3e-2, the
   five contrastive losses 5e-3, d_loss / g_loss 2e-3 of their term sizes, new u0 1e-4, new batch statistics 1e-2.
-  Gradients per leaf vs the oracle whose bf16 policy also rounds cotangents: discriminator and the generator from the
-  16x16 stage up 3e-2 / cosine 0.999. The generator leaves BELOW the 16x16 stage (Dense_0/1, GenBlock_0/1 and their
-  conditional BatchNorms) are conditioned at ~20x the bf16 epsilon: the oracle's own bf16 and fp32 policies differ by
-  0.10 rel-L2 / cosine 0.995 there at these sizes (4x4 / 8x8 BatchNorm statistics over B*16 elements), so they get
-  1.6e-1 / 0.985 here and their sharp check is the fp32-mode test below."""
+  Gradients per leaf vs the oracle whose bf16 policy also rounds cotangents: discriminator 3e-2 / cosine 0.999
+  (measured 1.6e-2 / 0.9999). The generator's gradients come down through the whole discriminator and then the
+  generator; their distance grows with depth from 3 % (128x128 end) to 12 % (4x4 end: Dense_1, GenBlock_0), exactly
+  like the distance between the ORACLE's own bf16 and fp32 policies on the same leaves (0.10 rel-L2 / cosine 0.995 at
+  Dense_1; rounding cotangents as well moves the oracle by only 5e-3): bf16 conditioning, not a formula error. They
+  get 1.6e-1 / 0.985 here as a sanity bound; the sharp check of every backward formula at this width is the fp32-mode
+  test below (cosine >= 0.9999 on every leaf of both networks)."""
   _check_forward_and_pullbacks(_full_config(), 8, 768, 21, 3e-2, 0.999, 1.6e-1, 0.985)
 
 
 @gpu
 def test_forward_and_both_pullbacks_at_256px_full_width():
   """BASELINE config 4's network (image_size = 256, gf = df = 96: one more block in G and D) at B = 2."""
-  _check_forward_and_pullbacks(_full_config(image_size=256, batch_size=4), 2, 768, 31, 4e-2, 0.999, 2e-1, 0.98)
+  _check_forward_and_pullbacks(_full_config(image_size=256, batch_size=4), 2, 768, 31, 5e-2, 0.999, 2e-1, 0.98)
 
 
 @gpu
@@ -129,8 +131,13 @@ def test_fp32_mode_forward_and_both_pullbacks_at_baseline_width():
 @gpu
 def test_train_step_at_baseline_width_matches_oracle():
   """One full train_step (train_d + train_g_d, Adam x3, EMA) at gf = df = 96, E = 768, B = 8 per sub-batch, from a
-  mid-training optimiser state (non-zero Adam moments, t = 100: the update is linear in the gradient instead of the
-  sign-like first step): metrics 5e-3 of the largest, parameter UPDATES 5e-2 rel-L2 per leaf (2e-1 below the generator's 16x16 stage), EMA 1e-5, step counters exact."""
+  mid-training optimiser state (helpers.warm_adam). train_g_d's metrics are taken after train_d's update of 88 M
+  discriminator parameters, which turns a 1.6 % gradient difference (bf16) into a 0.6 % difference of hinge_g, so the
+  two halves are checked separately and each sharply:
+    (1) train_d: the discriminator UPDATE per leaf rel-L2 5e-2 vs the oracle's;
+    (2) train_g_d from the SAME updated discriminator (the oracle continues from the CUDA path's parameters / moments
+        / u0): all metrics within 2e-3 of the largest, generator and discriminator updates per leaf (5e-2; 2e-1 bf16
+        sanity bound on the generator, see above), EMA 1e-5, step counters exact."""
   _, engine, ops, train_utils, xmc_gan, xmc_net = _mods()
   cfg = _full_config()
   B, E = 8, 768
@@ -141,21 +148,34 @@ def test_train_step_at_baseline_width_matches_oracle():
                                  train_utils.Optimizer(d_params, cfg.d_lr, cfg.beta1, cfg.beta2),
                                  {"batch_stats": g_stats}, {"spectral_norm_stats": d_u}, g_params.clone())
   helpers.warm_adam(state, ostate)
-  g_old, d_old = g_params.to_cpu_tree(), d_params.to_cpu_tree()
-  state, metrics = train_utils.train_step(None, state, batch, xmc_gan, None, None, cfg, {})
+  pol = orc.Policy("bfloat16", round_grads=True)
+  b0, b1 = train_utils.split_input_dict(xmc_net.batch_to_device(batch), 2)
+  ob0, ob1 = orc.split_input_dict(batch, 2)
+  # ---- (1) train_d ----------------------------------------------------------------------------------------------
+  d_old = d_params.to_cpu_tree()
+  state = xmc_gan.train_d(None, state, b0, None, None, cfg)
+  ostate1, _ = orc.train_d(ostate, ob0, cfg, pol)
+  d_mid = state.d_optimizer.target.to_cpu_tree()
+  helpers.check_updates("train_d: d", d_mid, d_old, ostate1["d_params"], d_vars["params"], cfg.d_lr)
+  # ---- (2) train_g_d from the same discriminator -------------------------------------------------------------------
+  lay = state.d_optimizer.target.layout
+  ostate1["d_params"] = d_mid
+  ostate1["d_opt"] = {"step": state.d_optimizer.step, "m": xmc_net.FlatTree(lay, state.d_optimizer.m).to_cpu_tree(),
+                      "v": xmc_net.FlatTree(lay, state.d_optimizer.v).to_cpu_tree()}
+  ostate1["discriminator_state"] = {"spectral_norm_stats": state.discriminator_state["spectral_norm_stats"].to_cpu_tree()}
+  g_old = state.g_optimizer.target.to_cpu_tree()
+  state, metrics = xmc_gan.train_g_d(None, state, b1, None, None, cfg, {})
   got = metrics.compute()
-  ostate, want = orc.train_step(ostate, batch, cfg, orc.Policy("bfloat16", round_grads=True))
+  ostate2, want, _ = orc.train_g_d(ostate1, ob1, cfg, pol)
   scale = max(abs(v) for v in want.values())
   print("\n[train_step @ baseline width]", {k: (round(got[k], 5), round(want[k], 5)) for k in want})
   for k in ("d_loss", "g_loss", "c_loss_d", "c_loss_g"):
-    assert abs(got[k] - want[k]) < 5e-3 * scale, (k, got[k], want[k])
+    assert abs(got[k] - want[k]) < 2e-3 * scale, (k, got[k], want[k])
   assert (state.step, state.d_optimizer.step, state.g_optimizer.step) == (1, 102, 101)
-  # the UPDATES (new - old parameters) per leaf: rel-L2 5e-2 (sharper than comparing parameters, whose relative change
-  # per step is ~1e-2); 2e-1 on the generator leaves below the 16x16 stage (bf16 conditioning, see above)
-  helpers.check_updates("g", state.g_optimizer.target.to_cpu_tree(), g_old, ostate["g_params"], g_vars["params"],
-                        cfg.g_lr)
-  helpers.check_updates("d", state.d_optimizer.target.to_cpu_tree(), d_old, ostate["d_params"], d_vars["params"],
+  helpers.check_updates("train_g_d: g", state.g_optimizer.target.to_cpu_tree(), g_old, ostate2["g_params"],
+                        g_vars["params"], cfg.g_lr)
+  helpers.check_updates("train_g_d: d", state.d_optimizer.target.to_cpu_tree(), d_mid, ostate2["d_params"], d_mid,
                         cfg.d_lr)
   worst = max((helpers.rel(a, b), p) for (p, a), (_, b) in
-              zip(orc.tree_leaves(state.ema_params.to_cpu_tree()), orc.tree_leaves(ostate["ema_params"])))
+              zip(orc.tree_leaves(state.ema_params.to_cpu_tree()), orc.tree_leaves(ostate2["ema_params"])))
   assert worst[0] < 1e-5, worst

@@ -11,12 +11,14 @@ import bench
 from xmcgan_image_generation_b200 import engine, train_utils, xmc_gan
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 56
+RESNET_DTYPE = sys.argv[2] if len(sys.argv) > 2 else "float32"
 config = bench.make_config(128, True)
 config.batch_size = B
 host = bench.synth_batch(2 * B, config, 42)
 dev = {k: v.cuda() for k, v in host.items()}
 gen, disc, state = train_utils.create_train_state(config, 42, host)
-add = xmc_gan.create_additional_data(config, variables=engine.ResNetEngine().random_variables(7))
+add = xmc_gan.create_additional_data(config, variables=engine.ResNetEngine().random_variables(7),
+                                     image_model_dtype=RESNET_DTYPE)
 for _ in range(3):
   state, m = train_utils.train_step(None, state, dev, xmc_gan, gen, disc, config, add)
 torch.cuda.synchronize()

@@ -45,28 +45,23 @@ __global__ void bn_stats_kernel(const T* __restrict__ x, long long P, int C, int
   }
 }
 
-// out[j] (+)= sum_r partials[r][j], rows added in index order (the deterministic second stage of every reduction here)
+// out[j] (+)= sum_r partials[r][j] in a FIXED order (the deterministic second stage of every reduction here): block =
+// 32 columns x 8 row lanes; lane l adds rows l, l+8, l+16, ... in index order, the 8 lane sums are then added in lane
+// order. The order depends only on (rows, width), never on scheduling.
 __global__ void sum_partials_kernel(const float* __restrict__ partials, int rows, int width, float* __restrict__ out,
                                     int accumulate) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= width) return;
+  __shared__ float sm[8][33];
+  const int j = blockIdx.x * 32 + threadIdx.x;
   float a = 0.f;
-  for (int r = 0; r < rows; ++r) a += partials[(long long)r * width + j];
-  out[j] = accumulate ? out[j] + a : a;
-}
-
-__global__ void bn_finalize_kernel(const float* __restrict__ sums, float invP, int C, float eps, float momentum,
-                                   const float* ra_mean, const float* ra_var, float* new_ra_mean, float* new_ra_var,
-                                   float* mean_rstd) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const float mean = sums[c] * invP;
-  const float var = sums[C + c] * invP - mean * mean;
-  mean_rstd[c] = mean;
-  mean_rstd[C + c] = rsqrtf(var + eps);
-  if (new_ra_mean) {
-    new_ra_mean[c] = momentum * ra_mean[c] + (1.f - momentum) * mean;
-    new_ra_var[c] = momentum * ra_var[c] + (1.f - momentum) * var;
+  if (j < width)
+    for (int r = threadIdx.y; r < rows; r += 8) a += partials[(long long)r * width + j];
+  sm[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.y == 0 && j < width) {
+    float t = 0.f;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) t += sm[l][threadIdx.x];
+    out[j] = accumulate ? out[j] + t : t;
   }
 }
 
@@ -617,7 +612,7 @@ using namespace xmc;
 
 static int launch_sum_partials(const float* partials, int rows, int width, float* out, int accumulate,
                                cudaStream_t stream) {
-  sum_partials_kernel<<<ceil_div(width, 128), 128, 0, stream>>>(partials, rows, width, out, accumulate);
+  sum_partials_kernel<<<ceil_div(width, 32), dim3(32, 8), 0, stream>>>(partials, rows, width, out, accumulate);
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }

@@ -1278,19 +1278,25 @@ static int plan_wgrad(const XmcWgradDesc* d, WgradParams& p) {
   const int base_ctas = m_tiles * p.n_tiles * taps * nbatch;
   int ksplit = 1;
   if (d->out_mode == 0) {
-    // Split K (pixels) across CTAs so that the grid fills whole waves of SMs: pick the split with the best
-    // last-wave utilisation (ties -> fewer splits = smaller workspace), keeping >= 8 chunks (512 pixels) per CTA.
+    // Split K (pixels) across CTAs with a small cost model (microseconds): tensor time = waves x chunks per CTA x
+    // (four 128 x BN x 16 MMAs = 2 BN cycles per 64-pixel chunk) + one epilogue per item, plus — as soon as the
+    // reduction is split — the partial tiles' round trip through the workspace and the second-stage launch. Layers
+    // with large weights (1536 x 1536 x 9 = 85 MB per split) therefore stay unsplit even if their last wave is
+    // ragged; narrow layers (96 x 96) split ~50 ways. Keeps >= 8 chunks (512 pixels) per CTA.
     const int sms = num_sms();
     const int max_split = p.total_chunks / 8 > 0 ? p.total_chunks / 8 : 1;
-    double best_score = -1.0;
+    const double clk_mhz = 1600.0, hbm_bytes_per_us = 5.0e6;
+    const double tile_bytes = 4.0 * (double)taps * d->Ca * d->Cb * nbatch * (p.tap3 ? 3 : 1);
+    double best_cost = 1e300;
     for (int ks = 1; ks <= max_split && ks <= 1024; ++ks) {
       const int cps = ceil_div(p.total_chunks, ks);
       const int ks_eff = ceil_div(p.total_chunks, cps);
       const long long ctas = (long long)base_ctas * ks_eff;
       const long long waves = (ctas + sms - 1) / sms;
-      const double eff = (double)ctas / (double)(waves * sms);
-      const double score = eff - 1e-4 * ks_eff;
-      if (score > best_score) { best_score = score; ksplit = ks_eff; }
+      const double epi = 1500.0 + 12.0 * p.BN * (p.tap3 ? 3 : 1);
+      double cost = (double)waves * ((double)cps * 2.0 * p.BN * (p.tap3 ? 3 : 1) + epi) / clk_mhz;
+      if (ks_eff > 1) cost += 3.0 + (2.0 * ks_eff + 2.0) * tile_bytes / hbm_bytes_per_us;
+      if (cost < best_cost * 0.999) { best_cost = cost; ksplit = ks_eff; }
       if (ctas > 16LL * sms) break;
     }
   }

@@ -288,17 +288,25 @@ __global__ void wgrad_c3_kernel(const T* __restrict__ x3, const T* __restrict__ 
   }
 }
 
-// out[tap_o*s_tap + c3*s_c3 + c*s_c] += sum_blocks partials[block][tap*3 + c3][c], blocks added in index order
+// out[tap_o*s_tap + c3*s_c3 + c*s_c] += sum_blocks partials[block][tap*3 + c3][c] in a fixed order: 32 outputs x 8 block
+// lanes per thread block, lane l adds blocks l, l+8, ... in index order, the lane sums are added in lane order.
 __global__ void wgrad_c3_finish_kernel(const float* __restrict__ partials, int blocks, int taps, int C, int flip,
                                        long long s_tap, int s_c3, int s_c, float* __restrict__ out) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float sm[8][33];
+  const int idx = blockIdx.x * 32 + threadIdx.x;
   const int width = taps * 3 * C;
-  if (idx >= width) return;
   float a = 0.f;
-  for (int b = 0; b < blocks; ++b) a += partials[(long long)b * width + idx];
+  if (idx < width)
+    for (int b = threadIdx.y; b < blocks; b += 8) a += partials[(long long)b * width + idx];
+  sm[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.y != 0 || idx >= width) return;
+  float t = 0.f;
+#pragma unroll
+  for (int l = 0; l < 8; ++l) t += sm[l][threadIdx.x];
   const int c = idx % C, i = idx / C, c3 = i % 3, tap = i / 3;
   const int tap_o = flip ? taps - 1 - tap : tap;
-  out[tap_o * s_tap + c3 * s_c3 + (long long)c * s_c] += a;
+  out[tap_o * s_tap + c3 * s_c3 + (long long)c * s_c] += t;
 }
 
 // scalar-channel 2x2 mean pool of a bf16 [N,2H,2W,C] tensor (the 3-channel image, common.py:131)
@@ -470,8 +478,8 @@ extern "C" int xmc_wgrad_c3(const void* x3, const void* y, int act_f32, int N, i
                                                                                        W, C, partials));
   XMC_LAUNCH_CHECK();
   const int width = KH * KW * 3 * C;
-  wgrad_c3_finish_kernel<<<ceil_div(width, 128), 128, 0, (cudaStream_t)stream>>>(partials, blocks, KH * KW, C, flip,
-                                                                                s_tap, s_c3, s_c, out);
+  wgrad_c3_finish_kernel<<<ceil_div(width, 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(partials, blocks, KH * KW, C,
+                                                                                       flip, s_tap, s_c3, s_c, out);
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }

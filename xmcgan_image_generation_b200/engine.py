@@ -1050,12 +1050,19 @@ RESNET50_STAGES = [3, 4, 6, 3]
 class ResNetEngine:
   """resnet_v1.ResNet50 in eval mode (xmcgan/utils/resnet_v1.py:129-180) behind get_pretrained_embs
   (pretrained_model_utils.py:102-127): forward on [real; fake] images, input gradient for the fake half.
-  Eval BatchNorm is folded into the bf16 weights / an fp32 bias once at construction; operands are bf16 with fp32
-  accumulation (the reference runs this network in fp32)."""
+  Eval BatchNorm is folded into the weights / an fp32 bias once at construction.
+  dtype: "float32" (default — the reference builds this network without a dtype, i.e. always fp32,
+  pretrained_model_utils.py:87-91): fp32 activations, every convolution as three bf16 tensor-core passes over hi / lo
+  splits of both operands (16 mantissa bits per operand, fp32 accumulation). "bfloat16": bf16
+  activations and operands, 1/3 of the tensor work and half the activation traffic (a stated deviation)."""
   T, PAD_LO, TP = 224, 2, 229  # 7x7/2 SAME on 224: pad (2,3)
 
-  def __init__(self, num_classes=1000, width=64):
+  def __init__(self, num_classes=1000, width=64, dtype="float32"):
     self.width, self.num_classes = width, num_classes
+    if dtype not in ("float32", "bfloat16"):
+      raise ValueError(f"dtype {dtype!r} is not supported (float32 or bfloat16)")
+    self.act = F32 if dtype == "float32" else BF16
+    self.S = S_ = 3 if self.act == F32 else 1
     L = self.layout = Layout()
     S = self.stats_layout = Layout()
     self.convs = collections.OrderedDict()  # path -> dict(kh, cin, cout, stride, bn)
@@ -1076,13 +1083,13 @@ class ResNetEngine:
       rec = dict(kh=kh, cin=cin, cout=cout, stride=stride, bn=bn_path, w_off=w_off, cs_off=self.cscale_size)
       self.cscale_size += _r4(cout)
       if cin >= 8:
-        rec["ld_fwd"], rec["ld_dg"] = _r8(taps * cin), _r8(taps * cout)
+        rec["ld_fwd"], rec["ld_dg"] = _r8(S_ * taps * cin), _r8(S_ * taps * cout)
         rec["fwd_off"] = self.arena_size
         self.arena_size += _r8(cout) * rec["ld_fwd"]
         rec["dg_off"] = self.arena_size
         self.arena_size += _r8(cin) * rec["ld_dg"]
         self.prep.add(w_off, taps, cin, cout, rec["fwd_off"], rec["ld_fwd"], rec["dg_off"], rec["ld_dg"], -1,
-                      cscale_off=rec["cs_off"])
+                      cscale_off=rec["cs_off"], split=S_ == 3)
       self.convs[path] = rec
 
     add_conv(("init_conv",), ("init_bn",), 7, 3, width, 2)
@@ -1104,12 +1111,17 @@ class ResNetEngine:
     self.c_last = cin
     self.head_w = L.add(("head", "kernel"), (cin, num_classes))
     self.head_b = L.add(("head", "bias"), (num_classes,))
+    if num_classes % 8:
+      raise ValueError("num_classes must be a multiple of 8")
     self.head_fwd = self.arena_size
-    self.arena_size += _r8(num_classes) * cin
+    self.arena_size += num_classes * cin * S_
     self.head_dg = self.arena_size
-    self.arena_size += cin * _r8(num_classes)
-    self.prep.add(self.head_w, 1, cin, num_classes, self.head_fwd, cin, self.head_dg, _r8(num_classes), -1)
+    self.arena_size += cin * num_classes * S_
+    self.prep.add(self.head_w, 1, cin, num_classes, self.head_fwd, cin * S_, self.head_dg, num_classes * S_, -1,
+                  split=S_ == 3)
     self.stem_off = self.arena_size          # packed stem weights [width][7*56]: k = kh*56 + kw*8 + c
+    self.arena_size += width * 392
+    self.stem_lo_off = self.arena_size       # fp32 mode: the bf16 remainders of the stem weights, same packing
     self.arena_size += width * 392
 
   def random_variables(self, seed=0, head_scale=0.05, residual_scale=0.3):
@@ -1167,9 +1179,19 @@ class ResNetEngine:
     # x 8 padded channels are ONE contiguous 56-element run of the zero-bordered 8-channel image
     rec = self.convs[("init_conv",)]
     w = L.view(self.params, ("init_conv", "kernel")) * self.cscale[rec["cs_off"]:rec["cs_off"] + self.width]
-    packed = torch.zeros(self.width, 7, 7, 8, device="cuda")
-    packed[:, :, :, :3] = w.permute(3, 0, 1, 2)
-    self.arena[self.stem_off:self.stem_off + self.width * 392] = packed.reshape(self.width, 392).to(BF16).reshape(-1)
+    n_stem = self.width * 392
+    wt = w.permute(3, 0, 1, 2)
+    hi = wt.to(BF16)
+    packed = torch.zeros(self.width, 7, 7, 8, device="cuda", dtype=BF16)
+    packed[:, :, :, :3] = hi
+    if self.act == F32:
+      # fp32 mode: the resized image carries [hi(3) | lo(3) | 0 0] per pixel (xmc_resize_bilinear_pad split = 1).
+      # pass 1 multiplies both parts with w_hi (channels 0-2 and 3-5), pass 2 adds hi * w_lo (channels 0-2 only).
+      packed[:, :, :, 3:6] = hi
+      lo = torch.zeros(self.width, 7, 7, 8, device="cuda", dtype=BF16)
+      lo[:, :, :, :3] = (wt - hi.float()).to(BF16)
+      self.arena[self.stem_lo_off:self.stem_lo_off + n_stem] = lo.reshape(-1)
+    self.arena[self.stem_off:self.stem_off + n_stem] = packed.reshape(-1)
     torch.cuda.synchronize()
 
   def _bias(self, rec):
@@ -1179,14 +1201,19 @@ class ResNetEngine:
     """bilinear resize to 224 -> 7x7/2 conv (+ folded init_bn, no ReLU) -> 3x3/2 max-pool. Returns (stem, pooled)."""
     N, S = images_f32.shape[0], images_f32.shape[1]
     T, TP, W0 = self.T, self.TP, self.width
-    xpad = ops.empty((N, TP, TP, 8))
-    ops._call("xmc_resize_bilinear_pad", images_f32.data_ptr(), N, S, T, TP, self.PAD_LO, 0, xpad.data_ptr(),
+    f32 = self.act == F32
+    xpad = ops.empty((N, TP, TP, 8), BF16)
+    ops._call("xmc_resize_bilinear_pad", images_f32.data_ptr(), N, S, T, TP, self.PAD_LO, int(f32), xpad.data_ptr(),
               _lib.stream())
     rec = self.convs[("init_conv",)]
     view = dict(Hout=T // 2, Wout=T // 2, KH=7, KW=1, strideH=2, strideW=1, Hin=TP, Win=T // 2, pitchW=16,
                 pitchH=TP * 8, pitchN=TP * TP * 8)
-    stem = ops.conv_fwd(xpad, self.arena[self.stem_off:], 7, W0, bias=self._bias(rec), ldb=392, c=56, view=view)
-    x = ops.empty((N, T // 4, T // 4, W0))
+    stem = ops.conv_fwd(xpad, self.arena[self.stem_off:], 7, W0, bias=self._bias(rec), ldb=392, c=56, view=view,
+                        pre_split=f32)
+    if f32:   # second pass: + image_hi * w_lo, added through the residual input (same element read then written)
+      ops.conv_fwd(xpad, self.arena[self.stem_lo_off:], 7, W0, ldb=392, c=56, view=view, pre_split=True, residual=stem,
+                   out=stem)
+    x = ops.empty((N, T // 4, T // 4, W0), self.act)
     ops._call("xmc_maxpool3s2", stem.data_ptr(), ops._f32(stem), N, T // 2, W0, x.data_ptr(), _lib.stream())
     return stem, x
 
@@ -1194,12 +1221,13 @@ class ResNetEngine:
     """d(loss)/d(pooled) bf16 -> accumulates d(loss)/d(images) (fp32 [n,S,S,3]) through max-pool, stem and resize."""
     n = dpool.shape[0]
     T, W0 = self.T, self.width
-    dstem = ops.empty((n, T // 2, T // 2, W0))
+    dstem = ops.empty((n, T // 2, T // 2, W0), self.act)
     ops._call("xmc_maxpool3s2_bwd", dpool.data_ptr(), stem.data_ptr(), pooled.data_ptr(), ops._f32(stem), n, T // 2, W0,
               dstem.data_ptr(), _lib.stream())
     d224 = ops.empty((n, T, T, 3), F32)
-    ops._call("xmc_stem_dgrad", dstem.data_ptr(), ops._f32(dstem), self.arena[self.stem_off:].data_ptr(), None, n, T,
-              T // 2, W0, self.PAD_LO, d224.data_ptr(), _lib.stream())
+    ops._call("xmc_stem_dgrad", dstem.data_ptr(), ops._f32(dstem), self.arena[self.stem_off:].data_ptr(),
+              self.arena[self.stem_lo_off:].data_ptr() if self.act == F32 else None, n, T, T // 2, W0, self.PAD_LO,
+              d224.data_ptr(), _lib.stream())
     ops._call("xmc_resize_bilinear_bwd", d224.data_ptr(), n, S, T, d_images.data_ptr(), _lib.stream())
 
   def block_forward(self, x, spec):
@@ -1225,7 +1253,7 @@ class ResNetEngine:
     r1c, r2c, r3c = (self.convs[pre + (f"conv{i}",)] for i in (1, 2, 3))
     dr2 = ops.conv_fwd(g, self.arena[r3c["dg_off"]:], 1, f, mask=r2, ldb=r3c["ld_dg"])
     if stride == 2:
-      z = ops.empty((n, 2 * dr2.shape[1], 2 * dr2.shape[2], f))
+      z = ops.empty((n, 2 * dr2.shape[1], 2 * dr2.shape[2], f), dr2.dtype)
       ops._call("xmc_zero_insert2", dr2.data_ptr(), ops._f32(dr2), n, dr2.shape[1], dr2.shape[2], f, z.data_ptr(),
                 _lib.stream())
       dr1 = ops.conv_fwd(z, self.arena[r2c["dg_off"]:], 3, f, mask=r1, ldb=r2c["ld_dg"], pad=2)
@@ -1235,7 +1263,7 @@ class ResNetEngine:
       pc = self.convs[pre + ("proj_conv",)]
       g_in = g
       if stride == 2:
-        g_in = ops.empty((n, 2 * g.shape[1], 2 * g.shape[2], 4 * f))
+        g_in = ops.empty((n, 2 * g.shape[1], 2 * g.shape[2], 4 * f), g.dtype)
         ops._call("xmc_zero_insert2", g.data_ptr(), ops._f32(g), n, g.shape[1], g.shape[2], 4 * f, g_in.data_ptr(),
                   _lib.stream())
       sg = ops.conv_fwd(g_in, self.arena[pc["dg_off"]:], 1, cin, ldb=pc["ld_dg"])
@@ -1246,6 +1274,10 @@ class ResNetEngine:
 
   def forward(self, images_f32):
     """images_f32: fp32 [N,S,S,3] in [0,1]. Returns (logits fp32 [N,num_classes], ctx)."""
+    with ops.act_dtype(self.act):
+      return self._forward(images_f32)
+
+  def _forward(self, images_f32):
     N, S = images_f32.shape[0], images_f32.shape[1]
     stem, x = self.stem_forward(images_f32)
     ctx = {"N": N, "S": S, "stem": stem, "pool0": x, "blocks": []}
@@ -1257,7 +1289,7 @@ class ResNetEngine:
     feat_bf = ops.cast_to_bf16(feat)
     hw = x.shape[1] * x.shape[2]
     logits = ops.conv_fwd(as4(feat_bf), self.arena[self.head_fwd:], 1, self.num_classes,
-                          bias=self.params[self.head_b:], ldb=self.c_last, alpha=1.0 / hw,
+                          bias=self.params[self.head_b:], ldb=self.c_last * self.S, alpha=1.0 / hw,
                           out_dtype=F32).view(N, self.num_classes)
     ctx["hw"] = hw
     return logits, ctx
@@ -1265,12 +1297,15 @@ class ResNetEngine:
   def backward(self, ctx, dlogits, n0, d_images):
     """dlogits: fp32 [n, num_classes] for images [n0, n0+n). Accumulates d(loss)/d(images) into d_images fp32
     [n,S,S,3] (the 128-px images, i.e. through the bilinear resize as well)."""
+    with ops.act_dtype(self.act):
+      self._backward(ctx, dlogits, n0, d_images)
+
+  def _backward(self, ctx, dlogits, n0, d_images):
     n = dlogits.shape[0]
     sl = slice(n0, n0 + n)
-    ncp = _r8(self.num_classes)
-    dl_bf = ops.zeros((n, ncp), BF16) if ncp != self.num_classes else ops.empty((n, ncp))
-    ops.cast_to_bf16(dlogits, dl_bf[:, :self.num_classes])
-    dfeat = ops.conv_fwd(as4(dl_bf), self.arena[self.head_dg:], 1, self.c_last, ldb=ncp, alpha=1.0 / ctx["hw"],
+    ncp = self.num_classes
+    dl_bf = ops.cast_to_bf16(dlogits.reshape(n, ncp))
+    dfeat = ops.conv_fwd(as4(dl_bf), self.arena[self.head_dg:], 1, self.c_last, ldb=ncp * self.S, alpha=1.0 / ctx["hw"],
                          out_dtype=F32).view(n, self.c_last)
     dout = ops.relu_sumhw_bwd(ctx["x_last"][sl], dfeat)   # includes the relu mask of the last block output
     for i in range(len(self.blocks) - 1, -1, -1):

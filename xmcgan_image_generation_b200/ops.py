@@ -82,13 +82,13 @@ def _split_nhwc(x, c=None):
 
 def conv_fwd(x, wk, kh, cout, *, bias=None, residual=None, res_shift=0, mask=None, relu=False, out=None,
              out_dtype=None, alpha=1.0, ldb=None, batched=False, stride_b=0, c=None, stride=1, pad=None,
-             mask_last=False, view=None, subpixel=False):
+             mask_last=False, view=None, subpixel=False, pre_split=False):
   """x: [N,H,W,>=C] bf16 view (channel-contiguous); wk: bf16 tensor whose data pointer is the [cout][kh*kh*C] K-major
   matrix (row pitch ldb). Returns y [N,H/stride,W/stride,cout] (or writes into the `out` view).
   stride=2 reads the input at (h*2+kh-pad, w*2+kw-pad) (XLA SAME: pad low = 0 for a 3x3 or 1x1 kernel on an even
   input). `view`: dict overriding the input view (Hout, Wout, KH, KW, pitches, strides) for the ResNet stem."""
-  f32 = x.dtype == F32
-  if f32:
+  f32 = x.dtype == F32 or pre_split   # pre_split: x already is a bf16 split operand, I/O tensors are fp32
+  if f32 and not pre_split:
     # fp32-activation mode: A = [hi | lo | hi] split of x (3C channels); wk is either already a split weight copy of
     # the arena (bf16, ld given by the caller) or an fp32 activation used as the B operand, split here as [hi | hi | lo]
     x = _split_nhwc(x, c)
@@ -99,10 +99,8 @@ def conv_fwd(x, wk, kh, cout, *, bias=None, residual=None, res_shift=0, mask=Non
       rows_b = wk.numel() // wk.shape[-1]
       wk = split3(torch.as_strided(wk, (rows_b, Kb), (ldb_in, 1)), weights=True)
       ldb, stride_b = 3 * Kb, 3 * stride_b
-    if out_dtype is None:
-      out_dtype = F32
-  elif out_dtype is None:
-    out_dtype = BF16
+  if out_dtype is None:
+    out_dtype = F32 if f32 else BF16
   N, H, W = x.shape[0], x.shape[1], x.shape[2]
   C = x.shape[3] if c is None else c
   _check_dense_rows(x)
@@ -337,7 +335,8 @@ def colsum(x, out, c=None):
   C = x.shape[-1] if c is None else c
   _check_dense_rows(x)
   P = x.numel() // x.shape[-1]
-  rows = partial_rows(P // 512)   # small tensors: one block adds straight into `out`
+  # small tensors: one block adds straight into `out`; larger ones use a machine-sized grid of partial rows
+  rows = 1 if P * C <= 65536 else partial_rows((P + 63) // 64)
   part = empty(rows * C, F32) if rows > 1 else None
   _call("xmc_colsum", ptr(x), _f32(x), P, C, _pix_ld(x), ptr(out), ptr(part), rows, stream(),
         launches=2 if rows > 1 else 1)

@@ -45,18 +45,20 @@ def calculate_contrastive_loss(result_dict):
   return real_loss, fake_loss + result_dict["image_contrastive_loss"]
 
 
-def create_additional_data(config, variables=None, checkpoint_path="data/resnet_pretrained.npy"):
+def create_additional_data(config, variables=None, checkpoint_path="data/resnet_pretrained.npy",
+                           image_model_dtype="float32"):
   """xmc_gan.create_additional_data (xmc_gan.py:43-55) + pretrained_model_utils.get_pretrained_model (:65-99): returns
   {"image_model", "image_model_state"} for the frozen ResNet-50. `variables` ({"params","batch_stats"} with the
   names of resnet_v1.py) takes precedence; otherwise the reference's .npy checkpoint is loaded from `checkpoint_path`
-  (not shipped with the reference, README.md:60-63)."""
+  (not shipped with the reference, README.md:60-63). image_model_dtype: "float32" = the reference's precision for this
+  network (it is built without a dtype, pretrained_model_utils.py:87-91); "bfloat16" is the faster stated deviation."""
   if not config.pretrained_image_contrastive:
     return {}
   if variables is None:
     import numpy as np
     data = np.load(checkpoint_path, allow_pickle=True).item()  # same format as pretrained_model_utils.py:95-98
     variables = {"params": data["params"], "batch_stats": data["batch_stats"]}
-  model = _engine.ResNetEngine()
+  model = _engine.ResNetEngine(dtype=image_model_dtype)
   model.load(variables)
   return {"image_model": model, "image_model_state": variables}
 
