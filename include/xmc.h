@@ -171,6 +171,9 @@ int xmc_colsum(const void* x, int act_f32, long long P, int C, int ld, float* ou
 /* x_pool[n][c] = sum_hw relu(x[n,hw,c]) (xmcgan/nets/xmc_net.py:97-98) and its backward */
 int xmc_relu_sumhw(const void* x, int act_f32, int N, int HW, int C, float* out, void* stream);
 int xmc_relu_sumhw_bwd(const void* x, int act_f32, const float* dout, int N, int HW, int C, void* dx, void* stream);
+/* y = relu(a) when b is NULL (flax nn.relu), else y = a + b (the residual add of nets/common.py's blocks): the
+ * stand-alone elementwise ops of the module-level API. n elements (multiple of 8), contiguous. */
+int xmc_relu_or_add(const void* a, const void* b, int act_f32, long long n, void* y, void* stream);
 /* fp32 [rows][C] (pitch ld_src) -> bf16 [rows][hi(C) | lo(C) | hi(C)] (pitch ld_dst >= 3C): the A operand of
  * xmc_conv2d_fwd in fp32-activation mode (XmcConvDesc.act_f32); xmc_conv2d_wgrad reads the hi / lo parts as views.
  * weights = 1: the B-operand order [hi | hi | lo] (an activation used as the second GEMM operand). */
@@ -314,6 +317,8 @@ int xmc_ce_sym(const float* logits, int n, float weight, float* loss_out, float*
 /* attention_lib.get_statistics (attention_lib.py:36-43) for both directions of an [n][n] logit matrix with identity
  * labels: out[0] = accuracy (argmax == label, first maximum wins; bit-exact index op), out[1] = entropy. These side
  * statistics are dead on the train path (XLA removes them); they exist for the functional API. */
+/* losses.tf_cross_entropy_loss_with_logits (losses.py:47-51) for arbitrary labels [rows][n]: one loss per row */
+int xmc_softmax_xent(const float* labels, const float* logits, long long rows, int n, float* out, void* stream);
 int xmc_ce_stats(const float* logits, int n, float* out, void* stream);
 /* losses.hinge_loss (losses.py:30-35) on logit = [real(B); fake(B)] and the two cotangents */
 int xmc_hinge(const float* logit, int B, float* d_loss, float* g_loss, float* dlogit_d, float* dlogit_g,

@@ -65,6 +65,21 @@ __global__ void sum_partials_kernel(const float* __restrict__ partials, int rows
   }
 }
 
+__global__ void bn_finalize_kernel(const float* __restrict__ sums, float invP, int C, float eps, float momentum,
+                                   const float* ra_mean, const float* ra_var, float* new_ra_mean, float* new_ra_var,
+                                   float* mean_rstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float mean = sums[c] * invP;
+  const float var = sums[C + c] * invP - mean * mean;   // flax: E[x^2] - E[x]^2, no clamp
+  mean_rstd[c] = mean;
+  mean_rstd[C + c] = rsqrtf(var + eps);
+  if (new_ra_mean) {
+    new_ra_mean[c] = momentum * ra_mean[c] + (1.f - momentum) * mean;
+    new_ra_var[c] = momentum * ra_var[c] + (1.f - momentum) * var;
+  }
+}
+
 // eval-mode: mean_rstd from running statistics
 __global__ void bn_eval_kernel(const float* ra_mean, const float* ra_var, int C, float eps, float* mean_rstd) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -532,6 +547,25 @@ __global__ void split3_kernel(const float* __restrict__ src, long long rows, int
   }
 }
 
+// y = relu(a) (b == nullptr) or y = a + b: the two stand-alone elementwise ops of the module-level API (nn.relu and the
+// residual `x + x0` of the blocks in nets/common.py); the fused engine folds both into GEMM epilogues instead.
+template <typename T>
+__global__ void relu_or_add_kernel(const T* __restrict__ a, const T* __restrict__ b, long long n8, T* __restrict__ y) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float f[8], g[8];
+    load8(a + i * 8, f);
+    if (b) {
+      load8(b + i * 8, g);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] += g[k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.f);
+    }
+    store8(y + i * 8, f);
+  }
+}
+
 static int grid_for(long long total, int block) {
   long long g = (total + block - 1) / block;
   const long long cap = (long long)num_sms() * 16;
@@ -777,6 +811,15 @@ extern "C" int xmc_relu_sumhw_bwd(const void* x, int act_f32, const float* dout,
   if (!x || !dout || !dx || N < 1 || HW < 1 || C < 8 || (C % 8)) return XMC_EINVAL;
   XMC_ACT(act_f32, relu_sumhw_bwd_kernel<T><<<dim3(ceil_div(C / 8, 64), N), 64, 0, (cudaStream_t)stream>>>(
                        (const T*)x, dout, HW, C, (T*)dx));
+  XMC_LAUNCH_CHECK();
+  return XMC_OK;
+}
+
+extern "C" int xmc_relu_or_add(const void* a, const void* b, int act_f32, long long n, void* y, void* stream) {
+  if (!a || !y || n < 8 || (n % 8)) return XMC_EINVAL;
+  if (!aligned16(a) || !aligned16(y) || (b && !aligned16(b))) return XMC_EALIGN;
+  XMC_ACT(act_f32, relu_or_add_kernel<T><<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+                       (const T*)a, (const T*)b, n / 8, (T*)y));
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }

@@ -70,6 +70,28 @@ __global__ void ce_sym_kernel(const float* __restrict__ logits, int n, float wei
   }
 }
 
+// losses.tf_cross_entropy_loss_with_logits (losses.py:47-51) for arbitrary labels: out[r] = -sum_k labels[r][k] *
+// log_softmax(logits[r])[k]. One warp per row, max-subtracted, warp-shuffle reductions.
+__global__ void softmax_xent_kernel(const float* __restrict__ labels, const float* __restrict__ logits, long long rows,
+                                    int n, float* __restrict__ out) {
+  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float* lg = logits + r * n;
+  const float* lb = labels + r * n;
+  float mx = -3.0e38f;
+  for (int k = lane; k < n; k += 32) mx = fmaxf(mx, lg[k]);
+  mx = warp_max(mx);
+  float s = 0.f;
+  for (int k = lane; k < n; k += 32) s += expf(lg[k] - mx);
+  s = warp_sum(s);
+  const float lse = mx + logf(s);
+  float acc = 0.f;
+  for (int k = lane; k < n; k += 32) acc += lb[k] * (lg[k] - lse);
+  acc = warp_sum(acc);
+  if (lane == 0) out[r] = -acc;
+}
+
 // get_statistics (attention_lib.py:36-43) of a square logit matrix with identity labels, both directions at once:
 // out[0] = accuracy = 0.5 * (mean_i [argmax_j logits[i][j] == i] + mean_j [argmax_i logits[i][j] == j])  (first maximum
 // wins, as jnp.argmax), out[1] = entropy = 0.5 * (mean row entropy + mean column entropy) with -sum p log(p + 1e-8).
@@ -213,6 +235,14 @@ extern "C" int xmc_ce_sym(const float* logits, int n, float weight, float* loss_
   if (!logits || !loss_out || n < 1 || n > 2048) return XMC_EINVAL;
   const size_t smem = (size_t)(2 * n + 32) * sizeof(float);
   ce_sym_kernel<<<1, 512, smem, (cudaStream_t)stream>>>(logits, n, weight, loss_out, dlogits);
+  XMC_LAUNCH_CHECK();
+  return XMC_OK;
+}
+
+extern "C" int xmc_softmax_xent(const float* labels, const float* logits, long long rows, int n, float* out,
+                                void* stream) {
+  if (!labels || !logits || !out || rows < 1 || n < 1) return XMC_EINVAL;
+  softmax_xent_kernel<<<(unsigned)ceil_div_ll(rows, 8), 256, 0, (cudaStream_t)stream>>>(labels, logits, rows, n, out);
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }

@@ -35,6 +35,38 @@ def contrastive_loss(image_feat, cond_feat, l2_norm=True, temperature=0.1, sync_
   return slot[0], stats[0], stats[1]
 
 
+def attention(region_feat, word_feat, gamma, mask=None):
+  """attention_lib.attention (attention_lib.py:105-127): l2-normalise both, alpha = softmax over REGIONS (axis -2) of
+  gamma * R^ W^^T (+ mask * -1e9), region_context = alpha^T R^ -> [batch, words, feat]. Kernel program: l2norm_rows,
+  one tcgen05 GEMM for the scores, the tiled region-softmax kernel, one batched tcgen05 A^T B GEMM for the context.
+  `mask`: None or the reference's word-padding mask (1 for padded words, constant over regions): a padded word's whole
+  column is shifted by -1e9, which a softmax over regions cancels exactly, so it does not change the result (the
+  reference relies on the later word mask, attention_lib.py:164-165)."""
+  r = _dev(region_feat).to(torch.bfloat16)
+  w = _dev(word_feat)
+  B, R, D = r.shape
+  L = w.shape[1]
+  if w.shape[0] != B:
+    raise ValueError("region_feat and word_feat must have the same batch size")
+  rh, _ = ops.l2norm_rows(r.reshape(B * R, D), out_dtype=ops.BF16)
+  wh, _ = ops.l2norm_rows(w.reshape(B * L, D), out_dtype=ops.BF16)
+  ldS = (L + 7) // 8 * 8
+  S = ops.zeros((B, R, ldS), ops.F32)
+  # scores of image b against ITS OWN words: one GEMM per batch entry (batched B operand)
+  ops.conv_fwd(rh.view(B, 1, R, D), wh.view(B, L, D), 1, L, ldb=D, batched=True, stride_b=L * D,
+               out=S.view(B, 1, R, ldS)[..., :L])
+  alpha = ops.empty((B, R, ldS), ops.BF16)
+  alphaT = ops.zeros((B, ldS, R), ops.BF16)
+  # the region-softmax kernel works on [images][R][columns]; here every "image" has its own L columns
+  for b in range(B):   # B small launches (functional API; the fused word_loss handles all pairs in one)
+    ops._call("xmc_wl_softmax", S[b].data_ptr(), 1, R, L, ldS, float(gamma), alpha[b].data_ptr(), alphaT[b].data_ptr(), 0,
+              ops.stream())
+  ctx = ops.empty((B, ldS, D), ops.F32)
+  ops.wgrad(alpha.view(B, 1, R, ldS), rh.view(B, 1, R, D), 1, ctx, out_mode=1, batched=True, ld_out=D, tap_stride=0,
+            batch_stride=ldS * D)
+  return ctx[:, :L]
+
+
 def word_loss(image_feat, word_feat, max_len, gamma1=5, gamma2=5, gamma3=50):
   """attention_lib.word_loss (attention_lib.py:130-191)."""
   if (gamma1, gamma2, gamma3) != (5, 5, 50):

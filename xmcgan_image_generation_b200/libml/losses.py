@@ -35,3 +35,17 @@ def symmetric_identity_cross_entropy(logits):
   out = ops.empty(1, ops.F32)
   ops.ce_sym(logits, out, want_grad=False)
   return out[0]
+
+
+def tf_cross_entropy_loss_with_logits(labels, logits):
+  """losses.tf_cross_entropy_loss_with_logits (losses.py:47-51): -sum(labels * log_softmax(logits), axis=-1), one
+  value per row, for arbitrary (soft or one-hot) labels."""
+  labels = torch.as_tensor(labels).to("cuda", torch.float32).contiguous()
+  logits = torch.as_tensor(logits).to("cuda", torch.float32).contiguous()
+  if labels.shape != logits.shape:
+    raise ValueError("labels and logits must have the same shape")
+  n = logits.shape[-1]
+  rows = logits.numel() // n
+  out = ops.empty(rows, ops.F32)
+  ops._call("xmc_softmax_xent", labels.data_ptr(), logits.data_ptr(), rows, n, out.data_ptr(), ops.stream())
+  return out.view(logits.shape[:-1])

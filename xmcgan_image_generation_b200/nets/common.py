@@ -1,13 +1,22 @@
-"""Counterparts of the resampling helpers of xmcgan/nets/common.py on CUDA bf16 NHWC tensors. The residual blocks
-themselves (GenBlock, GenSpatialBlock, DiscBlock, DiscOptimizedBlock; common.py:58-186) are executed by engine.py as
-fused kernel programs and are reachable through nets.xmc_net.Generator / Discriminator."""
+"""Counterparts of xmcgan/nets/common.py on CUDA NHWC tensors: the resampling helpers (common.py:23-55) and the
+residual blocks as module-level callables with the reference's constructor arguments and Flax call surface
+(DiscBlock :58-79, DiscOptimizedBlock :117-133, GenBlock :136-160, GenSpatialBlock :163-186), written as the reference
+writes them (relu, upsample / dsample, conv_fn / dense_fn / norm_fn sub-modules with Flax auto-naming). Forward values;
+training runs the same mathematics as fused forward + backward kernel programs in engine.py (sub-pixel convolutions,
+shortcut before the upsample, pooling after the residual add — exact rearrangements), which these blocks are tested
+against."""
 import torch
 
 from .. import ops
+from ..libml import layers
 
 
 def _bf16(x):
-  return torch.as_tensor(x).to("cuda", torch.bfloat16).contiguous()
+  """Plumbing: accepts CUDA bf16 / fp32 tensors as they are, anything else is moved to the device as bf16."""
+  x = torch.as_tensor(x)
+  if x.is_cuda and x.dtype in (torch.bfloat16, torch.float32):
+    return x.contiguous()
+  return x.to("cuda", torch.bfloat16).contiguous()
 
 
 def dsample(x):
@@ -31,3 +40,85 @@ def upsample(x, factor=2):
   if x.shape[3] % 8:
     raise ValueError("channel count must be a multiple of 8")
   return ops.unpool2(x, scale=1.0)
+
+
+class DiscBlock(layers.Module):
+  """common.DiscBlock (common.py:58-79)."""
+
+  def __init__(self, filters, downsample, conv_fn, activation_fn=layers.relu, dtype=None, name=None):
+    self.filters, self.downsample, self.conv_fn, self.activation_fn, self.name = (filters, downsample, conv_fn,
+                                                                                   activation_fn, name)
+
+  def forward(self, scope, x):
+    needs_projection = self.downsample or x.shape[-1] != self.filters
+    x0 = x
+    x = self.activation_fn(x)
+    x = scope.call(self.conv_fn(self.filters, kernel_size=(3, 3)), x)
+    x = self.activation_fn(x)
+    x = scope.call(self.conv_fn(self.filters, kernel_size=(3, 3)), x)
+    if needs_projection:
+      x0 = scope.call(self.conv_fn(self.filters, kernel_size=(1, 1)), x0)
+    if self.downsample:
+      x = dsample(x)
+      x0 = dsample(x0)
+    return layers.add(x0, x)
+
+
+class DiscOptimizedBlock(layers.Module):
+  """common.DiscOptimizedBlock (common.py:117-133); the 3-channel image is zero-padded to 8 channels for the
+  tensor-core convolution of this module-level form (the padded channels meet zero weights rows: exact)."""
+
+  def __init__(self, filters, conv_fn, activation_fn=layers.relu, dtype=None, name=None):
+    self.filters, self.conv_fn, self.activation_fn, self.name = filters, conv_fn, activation_fn, name
+
+  def forward(self, scope, x):
+    x0 = x
+    x = scope.call(self.conv_fn(self.filters, kernel_size=(3, 3)), x)
+    x = self.activation_fn(x)
+    x = scope.call(self.conv_fn(self.filters, kernel_size=(3, 3)), x)
+    x = dsample(x)
+    x0 = dsample(x0)
+    x0 = scope.call(self.conv_fn(self.filters, kernel_size=(1, 1)), x0)
+    return layers.add(x, x0)
+
+
+class GenBlock(layers.Module):
+  """common.GenBlock (common.py:136-160)."""
+
+  def __init__(self, filters, conv_fn, dense_fn, norm_fn, activation_fn=layers.relu, dtype=None, name=None):
+    self.filters, self.conv_fn, self.dense_fn, self.norm_fn = filters, conv_fn, dense_fn, norm_fn
+    self.activation_fn, self.name = activation_fn, name
+
+  def forward(self, scope, x, cond):
+    x0 = x
+    x = scope.call(layers.ConditionalBatchNorm(norm_fn=self.norm_fn, dense_fn=self.dense_fn), x, cond)
+    x = self.activation_fn(x)
+    x = upsample(x)
+    x = scope.call(self.conv_fn(self.filters, kernel_size=(3, 3), use_bias=True), x)
+    x = scope.call(layers.ConditionalBatchNorm(norm_fn=self.norm_fn, dense_fn=self.dense_fn), x, cond)
+    x = self.activation_fn(x)
+    x = scope.call(self.conv_fn(self.filters, kernel_size=(3, 3), use_bias=True), x)
+    x0 = upsample(x0)
+    x0 = scope.call(self.conv_fn(self.filters, kernel_size=(1, 1), use_bias=True), x0)
+    return layers.add(x, x0)
+
+
+class GenSpatialBlock(layers.Module):
+  """common.GenSpatialBlock (common.py:163-186)."""
+
+  def __init__(self, filters, conv_fn, dense_fn, norm_fn, activation_fn=layers.relu, dtype=None, name=None):
+    self.filters, self.conv_fn, self.dense_fn, self.norm_fn = filters, conv_fn, dense_fn, norm_fn
+    self.activation_fn, self.name = activation_fn, name
+
+  def forward(self, scope, x, cond0, cond1):
+    x0 = x
+    x = scope.call(layers.LocalConditionalBatchNorm(norm_fn=self.norm_fn, conv_fn=self.conv_fn), x, cond0)
+    x = self.activation_fn(x)
+    x = upsample(x)
+    x = scope.call(self.conv_fn(self.filters, kernel_size=(3, 3), use_bias=True), x)
+    x = scope.call(layers.LocalConditionalBatchNorm(norm_fn=self.norm_fn, conv_fn=self.conv_fn), x, cond1)
+    x = self.activation_fn(x)
+    x = scope.call(self.conv_fn(self.filters, kernel_size=(3, 3), use_bias=True), x)
+    x0 = upsample(x0)
+    x0 = scope.call(self.conv_fn(self.filters, kernel_size=(1, 1), use_bias=True), x0)
+    return layers.add(x, x0)
