@@ -96,6 +96,7 @@ class GemmTimer:
 
   def __init__(self):
     self.records = []  # (kernel, flops, start_event, end_event)
+    self.bytes = {}    # kernel -> algorithmic HBM bytes over all timed launches
 
   def install(self, ops):
     self.ops = ops
@@ -111,11 +112,21 @@ class GemmTimer:
         ho, wo, taps, c = view["Hout"], view["Wout"], view.get("real_taps", 49), view.get("real_c", 3)
       if kw.get("subpixel"):  # four parities x 2x2 taps per input pixel
         taps = 16
-      flops = 2.0 * x.shape[0] * ho * wo * taps * c * cout
+      if kw.get("pre_split"):   # fp32 stem: the packed window carries the hi and lo image parts, count the image once
+        c = 3
+      # algorithmic FLOPs: operands counted once whatever the number of bf16 passes (fp32 mode runs three), and the
+      # transposes of stride-2 convolutions at their real work (alg_scale = 0.25 over a zero-inserted gradient)
+      flops = 2.0 * x.shape[0] * ho * wo * taps * c * cout * kw.get("alg_scale", 1.0)
       s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
       s.record()
       out = timer._fwd(x, wk, kh, cout, **kw)
       e.record()
+      # algorithmic HBM bytes: the input and the output once (+ residual / mask), the weights once
+      nbytes = x.numel() * x.element_size() + out.numel() * out.element_size() + 2.0 * taps * c * cout
+      for extra in (kw.get("residual"), kw.get("mask")):
+        if extra is not None:
+          nbytes += extra.numel() * extra.element_size()
+      timer.bytes["gemm_fwd_kernel"] = timer.bytes.get("gemm_fwd_kernel", 0.0) + nbytes
       timer.records.append(("gemm_fwd_kernel", flops, s, e,
                             (x.shape[0], x.shape[1], x.shape[2], c, kh, cout, int(kw.get("batched", False)))))
       return out
@@ -216,6 +227,7 @@ def run_b200(args):
   barrier()
   ms_instr = e0.elapsed_time(e1)
   gemm = timer.summary()
+  timer_bytes = dict(timer.bytes)
   if args.dump_gemm and rank == 0:
     with open(args.dump_gemm, "w") as f:
       json.dump({"steps": args.steps, "rows": timer.per_shape()}, f, indent=0)
@@ -288,11 +300,21 @@ def run_b200(args):
   roofline = None
   if dom:
     ach = gemm[dom]["tflop"] / (gemm[dom]["ms"] / 1e3)
+    # measured DRAM traffic of the dominant kernel: one ncu capture of a train_step of this configuration
+    # (tools/summarize_ncu.py traffic), per launch like `achieved`; next to it the algorithmic bytes per launch
+    traffic, traffic_src = None, None
+    tname = f"r02_gemm_fwd_traffic_{args.resnet_dtype if pretrained else 'noresnet'}.json"
+    tpath = os.path.join(ROOT, "profiles", tname)
+    if dom == "gemm_fwd_kernel" and os.path.exists(tpath) and args.image_size == 128 and B == PER_GPU_B:
+      tj = json.load(open(tpath))
+      traffic, traffic_src = round(tj["dram_bytes_per_launch"]), f"profiles/{tname} ({tj['launches']} launches of one step)"
+    alg_bytes = timer_bytes.get(dom, 0.0) / max(gemm[dom]["launches"], 1)
     roofline = {"bound": "tensor", "kernel": dom, "achieved": round(ach, 1), "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": round(ach / peak_tf, 4), "traffic": None,
-                "traffic_note": "aggregate over launches of many shapes; per-shape ncu DRAM bytes (= algorithmic "
-                                "bytes, inputs read once) are in profiles/r01_gemm_shape_classes.md, r01_resident_full.md, "
-                                "r01_wgrad_tap3_full.md; the forward figure includes conv3x3_resident_kernel launches",
+                "frac": round(ach / peak_tf, 4), "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu)",
+                "traffic_source": traffic_src, "algorithmic_bytes_per_launch": round(alg_bytes),
+                "traffic_note": "average over the launches (many shapes) of one step; the forward figure includes "
+                                "conv3x3_resident_kernel launches. Per-shape captures: profiles/r01_gemm_shape_classes.md, "
+                                "r01_resident_full.md",
                 "peak_source": peak_src,
                 "launches_timed": gemm[dom]["launches"],
                 "share_of_step": round(gemm[dom]["ms"] / ms_instr, 3),
@@ -341,32 +363,50 @@ def _oracle_state(config, seed=1):
                         {"params": d.layout.tree(dp), "spectral_norm_stats": d.u_layout.tree(du)})
 
 
+CPU_B = 8   # BASELINE.json configs[0]: "coco_xmc.py 128px bs=8 world_size=1 on ... CPU backend" -> per-device sub-batch 8
+
+
 def cpu_baseline(args, quick):
-  """The reference algorithm (oracle restatement, torch-CPU fp32 ops, all host threads) on a bounded sample."""
+  """The reference algorithm (oracle restatement, torch-CPU fp32 ops, all host threads) on BASELINE config 1
+  (128 px, per-device sub-batch B = 8, i.e. 16 real images per train_step, full-width networks, ResNet branch on).
+  quick (the default bench run): one warm-up train_step at B = 2 (thread pool, oneDNN primitives), then ONE timed step
+  at B = 8 — the bounded sample. --impl reference: one warm-up step at B = 8, then as many timed steps (<= --steps) as
+  fit in ~150 s, median."""
   from oracle import xmc_oracle as orc
   cores = os.cpu_count() or 1
   torch.set_num_threads(cores)
   pretrained = not args.no_pretrained
   config = make_config(args.image_size, pretrained)
-  Bc = 2
-  state = _oracle_state(config)
-  batch = synth_batch(2 * Bc, config, 42)
   pre = None
   if pretrained:
     rvars = orc.resnet50_random_variables(7)
     pre = lambda real, fake: orc.calculate_contrastive_loss_on_pretrained(rvars, real, fake, orc.FP32)
-  n = 1 if quick else max(1, args.steps)
-  if not quick:
-    for _ in range(min(1, args.warmup)):
-      state, _ = orc.train_step(state, batch, config, orc.FP32, pretrained_fn=pre)
-  t0 = time.time()
-  for _ in range(n):
-    state, _ = orc.train_step(state, batch, config, orc.FP32, pretrained_fn=pre)
-  dt = (time.time() - t0) / n
+  state = _oracle_state(config)
+  Bc = CPU_B
+  batch = synth_batch(2 * Bc, config, 42)
+
+  def step(st, bt):
+    t0 = time.time()
+    st, _ = orc.train_step(st, bt, config, orc.FP32, pretrained_fn=pre)
+    return st, time.time() - t0
+
+  if quick:
+    step(state, synth_batch(4, config, 41))       # warm-up at B = 2 (result discarded)
+    state, dt = step(state, batch)
+    times, note = [dt], "1 timed train_step after a warm-up step at B=2"
+  else:
+    state, first = step(state, batch)
+    n = max(2, min(max(1, args.steps), int(150.0 / max(first, 1e-3))))
+    times = []
+    for _ in range(n):
+      state, dt = step(state, batch)
+      times.append(dt)
+    note = f"median of {n} timed train_steps after 1 warm-up step (requested --steps {args.steps}, capped to ~150 s)"
+  dt = sorted(times)[len(times) // 2]
   return {"value": round(2 * Bc / dt, 4), "unit": "images/sec", "cores": cores, "kind": "port",
-          "sample": f"{n} train_step(s) of the torch-CPU fp32 restatement at per-device sub-batch B={Bc} "
-                    f"({2 * Bc} real images per step), 128px, full-width networks",
-          "sec_per_step": round(dt, 2)}
+          "sample": f"{note}; torch-CPU fp32 restatement of the reference at per-device sub-batch B={Bc} "
+                    f"({2 * Bc} real images per step, BASELINE config 1), {args.image_size}px, full-width networks",
+          "sec_per_step": round(dt, 2), "batch": Bc}
 
 
 def run_reference(args):
@@ -378,9 +418,9 @@ def run_reference(args):
          "unit": "images/sec", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
          "ms_per_step": round(cb["sec_per_step"] * 1e3, 1), "higher_is_better": True, "scaling": "weak",
          "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-         "config": {"workload": "coco_xmc.py 128px train_step, reference algorithm (CPU restatement: JAX/Flax are not "
-                                "installable here), bounded sample",
-                    "pretrained_image_contrastive": not args.no_pretrained},
+         "config": {"workload": f"coco_xmc.py 128px train_step, reference algorithm (CPU restatement: JAX/Flax are not "
+                                f"installable here); bounded sample: per-device sub-batch B={cb['batch']} instead of 56",
+                    "sample_batch": cb["batch"], "pretrained_image_contrastive": not args.no_pretrained},
          "cpu_baseline": cb,
          "e2e": {"value": cb["value"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
   print(json.dumps(out), flush=True)

@@ -1256,7 +1256,7 @@ class ResNetEngine:
       z = ops.empty((n, 2 * dr2.shape[1], 2 * dr2.shape[2], f), dr2.dtype)
       ops._call("xmc_zero_insert2", dr2.data_ptr(), ops._f32(dr2), n, dr2.shape[1], dr2.shape[2], f, z.data_ptr(),
                 _lib.stream())
-      dr1 = ops.conv_fwd(z, self.arena[r2c["dg_off"]:], 3, f, mask=r1, ldb=r2c["ld_dg"], pad=2)
+      dr1 = ops.conv_fwd(z, self.arena[r2c["dg_off"]:], 3, f, mask=r1, ldb=r2c["ld_dg"], pad=2, alg_scale=0.25)
     else:
       dr1 = ops.conv_fwd(dr2, self.arena[r2c["dg_off"]:], 3, f, mask=r1, ldb=r2c["ld_dg"])
     if proj:
@@ -1266,7 +1266,7 @@ class ResNetEngine:
         g_in = ops.empty((n, 2 * g.shape[1], 2 * g.shape[2], 4 * f), g.dtype)
         ops._call("xmc_zero_insert2", g.data_ptr(), ops._f32(g), n, g.shape[1], g.shape[2], 4 * f, g_in.data_ptr(),
                   _lib.stream())
-      sg = ops.conv_fwd(g_in, self.arena[pc["dg_off"]:], 1, cin, ldb=pc["ld_dg"])
+      sg = ops.conv_fwd(g_in, self.arena[pc["dg_off"]:], 1, cin, ldb=pc["ld_dg"], alg_scale=0.25 if stride == 2 else 1.0)
     else:
       sg = g
     return ops.conv_fwd(dr1, self.arena[r1c["dg_off"]:], 1, cin, residual=sg, ldb=r1c["ld_dg"],

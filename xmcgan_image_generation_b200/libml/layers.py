@@ -317,17 +317,29 @@ class LocalConditionalBatchNorm(Module):
     return norm.forward(scope.child(norm), x, gb, Hc)
 
 
+def _dev_act(x):
+  """Plumbing: CUDA bf16 / fp32 tensors pass as they are, anything else (host tensors, other dtypes) is moved to the
+  device as bf16 — the kernels below only ever see device pointers."""
+  x = torch.as_tensor(x)
+  if x.is_cuda and x.dtype in (BF16, F32):
+    return x.contiguous()
+  return x.to("cuda", BF16 if x.dtype != F32 or not x.is_cuda else F32).contiguous()
+
+
 def relu(x):
   """flax nn.relu as a stand-alone kernel (the fused engine folds it into the producing kernel instead)."""
-  x = x.contiguous()
+  x = _dev_act(x)
+  if x.numel() % 8:
+    raise ValueError("element count must be a multiple of 8")
   y = torch.empty_like(x)
   ops._call("xmc_relu_or_add", x.data_ptr(), None, ops._f32(x), x.numel(), y.data_ptr(), ops.stream())
   return y
 
 
 def add(a, b):
-  a, b = a.contiguous(), b.contiguous()
-  assert a.shape == b.shape and a.dtype == b.dtype
+  a, b = _dev_act(a), _dev_act(b)
+  if a.shape != b.shape or a.dtype != b.dtype or a.numel() % 8:
+    raise ValueError("add needs two tensors of the same shape / dtype with a multiple of 8 elements")
   y = torch.empty_like(a)
   ops._call("xmc_relu_or_add", a.data_ptr(), b.data_ptr(), ops._f32(a), a.numel(), y.data_ptr(), ops.stream())
   return y

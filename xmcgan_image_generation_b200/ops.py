@@ -82,11 +82,12 @@ def _split_nhwc(x, c=None):
 
 def conv_fwd(x, wk, kh, cout, *, bias=None, residual=None, res_shift=0, mask=None, relu=False, out=None,
              out_dtype=None, alpha=1.0, ldb=None, batched=False, stride_b=0, c=None, stride=1, pad=None,
-             mask_last=False, view=None, subpixel=False, pre_split=False):
+             mask_last=False, view=None, subpixel=False, pre_split=False, alg_scale=1.0):
   """x: [N,H,W,>=C] bf16 view (channel-contiguous); wk: bf16 tensor whose data pointer is the [cout][kh*kh*C] K-major
   matrix (row pitch ldb). Returns y [N,H/stride,W/stride,cout] (or writes into the `out` view).
   stride=2 reads the input at (h*2+kh-pad, w*2+kw-pad) (XLA SAME: pad low = 0 for a 3x3 or 1x1 kernel on an even
-  input). `view`: dict overriding the input view (Hout, Wout, KH, KW, pitches, strides) for the ResNet stem."""
+  input). alg_scale: bookkeeping only (bench.py): algorithmic FLOPs of this launch relative to the dense count, e.g.
+  0.25 for a stride-1 convolution over a zero-inserted gradient (the transpose of a stride-2 convolution). `view`: dict overriding the input view (Hout, Wout, KH, KW, pitches, strides) for the ResNet stem."""
   f32 = x.dtype == F32 or pre_split   # pre_split: x already is a bf16 split operand, I/O tensors are fp32
   if f32 and not pre_split:
     # fp32-activation mode: A = [hi | lo | hi] split of x (3C channels); wk is either already a split weight copy of
@@ -155,9 +156,16 @@ def wgrad(xa, xb, kh, out, *, out_mode=0, batched=False, ld_out=None, tap_stride
     assert out.dtype == F32
     first = 1 if out_mode in (1, 2) else 0   # store modes: the first pass stores, the others accumulate
     for i, (pa, pb) in enumerate(((a_hi, b_hi), (a_lo, b_hi), (a_hi, b_lo))):
-      wgrad(pa, pb, kh, out, out_mode=first if i == 0 else 0, batched=batched, ld_out=ld_out, tap_stride=tap_stride,
-            batch_stride=batch_stride, alpha=alpha, subpixel=subpixel)
+      _wgrad_bf16(pa, pb, kh, out, out_mode=first if i == 0 else 0, batched=batched, ld_out=ld_out,
+                  tap_stride=tap_stride, batch_stride=batch_stride, alpha=alpha, subpixel=subpixel)
     return out
+  return _wgrad_bf16(xa, xb, kh, out, out_mode=out_mode, batched=batched, ld_out=ld_out, tap_stride=tap_stride,
+                     batch_stride=batch_stride, alpha=alpha, ca=ca, cb=cb, subpixel=subpixel, view_a=view_a)
+
+
+def _wgrad_bf16(xa, xb, kh, out, *, out_mode=0, batched=False, ld_out=None, tap_stride=None, batch_stride=0, alpha=1.0,
+                ca=None, cb=None, subpixel=False, view_a=None):
+  """One launch of the bf16 tensor-core weight-gradient kernel (+ its deterministic second stage)."""
   # pixel grid of the reduction: xa's (the low-resolution input in sub-pixel mode), xb's for a re-pitched xa view
   N, H, W = (xa if view_a is None else xb).shape[:3]
   _check_dense_rows(xa)
