@@ -236,10 +236,10 @@ def run_b200(args):
   eager_step = lambda batch: train_utils.train_step(None, state, batch, xmc_gan, generator, discriminator, config,
                                                     additional)
   launches_per_step = None
-  # --graph 1 (default): graph replay on a single GPU, eager train_step under torchrun. With N > 1 the replay itself
-  # works and is faster (2 GPUs: 43.4 vs 44.9 ms/step), but tearing the process group down while a graph holds captured
-  # NCCL kernels hung at exit in this environment, so it is opt-in there (--graph 2) until that is understood.
-  use_graph = args.graph == 2 or (args.graph == 1 and world == 1)
+  # --graph 1 (default): the step replayed from one CUDA graph at every N (captured NCCL all-reduces included).
+  # Tearing the process group down while a graph still holds captured NCCL kernels hung at exit in round 1; the ranks
+  # now leave through a final barrier + os._exit (below) instead of destroy_process_group. --graph 0 = eager.
+  use_graph = args.graph >= 1
   if use_graph:
     # the public graphed entry point: the whole train_step replayed from one CUDA graph (train_utils.GraphedTrainStep)
     n0 = ops.LAUNCHES[0]
@@ -283,9 +283,13 @@ def run_b200(args):
   barrier()
   ms_e2e = max_over_ranks(e0.elapsed_time(e1))
 
-  if use_graph and world > 1:   # drop the captured NCCL work before the communicator goes away
-    del graphed, step_fn
-    torch.cuda.synchronize()
+  if world > 1:
+    # every rank is past its last collective (max_over_ranks above); with a graph alive the communicator is not torn
+    # down (see --graph): flush and leave the process directly
+    barrier()
+    if use_graph and rank != 0:
+      sys.stdout.flush()
+      os._exit(0)
   if rank != 0:
     if world > 1:
       dist.destroy_process_group()
@@ -346,6 +350,9 @@ def run_b200(args):
     out["cpu_baseline"] = cpu_baseline(args, quick=True)
   print(json.dumps(out), flush=True)
   if world > 1:
+    if use_graph:   # see --graph: leave without tearing the communicator down under a live graph
+      sys.stdout.flush()
+      os._exit(0)
     dist.destroy_process_group()
 
 

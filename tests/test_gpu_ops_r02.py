@@ -101,3 +101,31 @@ def test_wgrad_split_k_is_deterministic_and_matches_single_pass():
   assert torch.equal(outs[0], outs[1])
   ops.wgrad(x, dy, 3, outs[0], out_mode=0, ld_out=C, tap_stride=C * C)
   assert torch.equal(outs[0], 2 * outs[1])
+
+
+@gpu
+def test_deferred_train_d_equals_plain_train_d():
+  """xmc_gan.train_d_deferred (the multi-GPU schedule: train_d's gradient all-reduce stays in flight and its Adam / u0
+  hand-over complete inside the next call, behind the generator forward) gives bit-identical states and metrics to the
+  plain train_d -> train_g_d sequence."""
+  from xmcgan_image_generation_b200 import train_utils, xmc_gan
+  from xmcgan_image_generation_b200.nets import xmc_net
+  cfg = helpers.small_config()
+  batch = xmc_net.batch_to_device(helpers.make_batch(6, cfg, seed=70))
+  b0, b1 = train_utils.split_input_dict(batch, 2)
+  out = []
+  for td in (xmc_gan.train_d, xmc_gan.train_d_deferred):
+    state = _state(cfg, 23)
+    old_d = state.d_optimizer.target.buf.clone()
+    state = td(None, state, b0, None, None, cfg)
+    if td is xmc_gan.train_d_deferred:
+      assert torch.equal(state.d_optimizer.target.buf, old_d)      # the update is still pending
+    state, m = xmc_gan.train_g_d(None, state, b1, None, None, cfg, {})
+    out.append((state, m.compute()))
+  (s1, m1), (s2, m2) = out
+  assert m1 == m2
+  assert (s2.step, s2.d_optimizer.step, s2.g_optimizer.step) == (1, 2, 1)
+  for a, b in ((s1.d_optimizer.target.buf, s2.d_optimizer.target.buf), (s1.g_optimizer.target.buf, s2.g_optimizer.target.buf),
+               (s1.d_optimizer.v, s2.d_optimizer.v), (s1.ema_params.buf, s2.ema_params.buf),
+               (s1.discriminator_state["spectral_norm_stats"].buf, s2.discriminator_state["spectral_norm_stats"].buf)):
+    assert torch.equal(a, b)

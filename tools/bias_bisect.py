@@ -46,7 +46,7 @@ def main():
   g_eng, d_eng = xmc_gan._engines(cfg, dev)
   ws = xmc_gan._workspace(state, g_eng, d_eng)
   losses = torch.zeros(16, device="cuda")
-  gctx, dctx = xmc_gan._forward_both(state, dev, cfg, ws, g_eng, d_eng, losses, keep_g_state=False, need_g=False)
+  gctx, dctx, state = xmc_gan._forward_both(state, dev, cfg, ws, g_eng, d_eng, losses, keep_g_state=False, need_g=False)
   ws.d_grads.zero_()
   d_eng.backward_d(dctx, state.d_optimizer.target.buf, ws.d_grads)
   d_eng.sn_backward(state.d_optimizer.target.buf, ws.d_grads, ws.u0_alt)

@@ -66,8 +66,13 @@ def train_step(rng, state, batch, gan_model, generator, discriminator, config, a
   # consumed when the batch carries no "z" (xmc_gan.py:131-135)
   seed = xmc_net._seed_of(rng)
   rngs = [(seed * 1000003 + i + 1) & 0x7FFFFFFF for i in range(config.d_step_per_g_step)]
+  # with several replicas every train_d leaves its gradient all-reduce in flight; the next call completes it behind its
+  # generator forward (xmc_gan.train_d_deferred). A foreign gan_model without that entry point runs the plain train_d.
+  train_d = gan_model.train_d
+  if parallel.world_size() > 1 and hasattr(gan_model, "train_d_deferred"):
+    train_d = gan_model.train_d_deferred
   for i in range(config.d_step_per_g_step - 1):
-    state = gan_model.train_d(rngs[i], state, batches[i], generator, discriminator, config)
+    state = train_d(rngs[i], state, batches[i], generator, discriminator, config)
   return gan_model.train_g_d(rngs[-1], state, batches[-1], generator, discriminator, config, additional_data)
 
 

@@ -83,6 +83,7 @@ class _Workspace:
     self.u0_alt = torch.empty_like(state.discriminator_state["spectral_norm_stats"].buf) if d_eng.sn else None
     self.g_u0_alt = torch.empty_like(state.generator_state["spectral_norm_stats"].buf) if g_eng.sn else None
     self.graph_mode = False  # True: state buffers keep their addresses (copies instead of pointer swaps)
+    self.pending_d = None    # handle of train_d's in-flight D-gradient all-reduce (train_d_deferred)
 
 
 def _workspace(state, g_eng, d_eng):
@@ -122,24 +123,42 @@ def _with_z(rng, batch, config):
 
 
 def _forward_both(state, batch, config, ws, g_eng, d_eng, losses, keep_g_state, need_g):
+  """Generator forward, then discriminator forward on [real; fake]. Returns (gctx, dctx, state): `state` is the
+  argument, or — when a deferred train_d update was pending (train_d_deferred) — the state with that update applied
+  (it is completed between the two forwards: the generator forward does not read the discriminator)."""
   B = batch["z"].shape[0]
   S = config.image_size
   g_params = state.g_optimizer.target.buf
-  d_params = state.d_optimizer.target.buf
   # the generator's bf16 weights (and, with g_spectral_norm, its power-iteration step) are shared by train_d and
   # train_g_d of one train_step: same parameters, same u0 (train_d discards the generator's new state, xmc_gan.py:225)
   g_u0 = state.generator_state["spectral_norm_stats"].buf if g_eng.sn else None
   if g_eng.prepped_for != g_eng.prep_key(g_params, ws.g_u0_alt):
     g_eng.prep_weights(g_params, g_u0, ws.g_u0_alt)
-  u0 = state.discriminator_state["spectral_norm_stats"].buf if d_eng.sn else None
-  d_eng.prep_weights(d_params, u0, ws.u0_alt)
   all_images = ops.empty((2 * B, S, S, 3))
   ops.cast_to_bf16(batch["image"].reshape(B * S * S, 3), all_images[:B].view(B * S * S, 3))
   fake, gctx = g_eng.forward(g_params, state.generator_state["batch_stats"].buf, batch, batch["z"], train=True,
                              new_stats=ws.g_stats_alt if keep_g_state else None, fake_bf16=all_images[B:])
+  state = _finish_pending_d(state, ws, d_eng)
+  d_params = state.d_optimizer.target.buf
+  u0 = state.discriminator_state["spectral_norm_stats"].buf if d_eng.sn else None
+  d_eng.prep_weights(d_params, u0, ws.u0_alt)
   _, dctx = d_eng.forward(d_params, all_images, batch, losses, need_g=need_g)
   gctx["fake"] = fake
-  return gctx, dctx
+  return gctx, dctx, state
+
+
+def _finish_pending_d(state, ws, d_eng):
+  """Completes a train_d whose gradient all-reduce was left in flight (train_d_deferred): wait, Adam on D, keep the new
+  u0. No-op when nothing is pending."""
+  if ws.pending_d is None:
+    return state
+  handle, ws.pending_d = ws.pending_d, None
+  if handle is not True:
+    handle.wait()
+  _adam(state.d_optimizer, ws.d_grads)
+  new_state = state.replace(discriminator_state=_swap_d_state(state, ws, d_eng))
+  object.__setattr__(new_state, "_ws", ws)
+  return new_state
 
 
 def _swap_d_state(state, ws, d_eng):
@@ -161,18 +180,31 @@ def train_d(rng, state, batch, generator, discriminator, config):
     return _train_d(rng, state, batch, generator, discriminator, config)
 
 
-def _train_d(rng, state, batch, generator, discriminator, config):
+def train_d_deferred(rng, state, batch, generator, discriminator, config):
+  """train_d whose gradient all-reduce is left in flight: the wait, Adam on D and the u0 hand-over happen inside the next
+  train_d / train_g_d call on the returned state, after its generator forward (which does not read the discriminator)
+  — the all-reduce hides behind that forward instead of stalling the stream. Used by train_utils.train_step; the
+  returned state must go straight into the next train_d / train_g_d (its D parameters are the OLD ones until then)."""
+  with ops.act_dtype(_engine.act_dtype_of(config)):
+    return _train_d(rng, state, batch, generator, discriminator, config, defer=True)
+
+
+def _train_d(rng, state, batch, generator, discriminator, config, defer=False):
   batch = _with_z(rng, xmc_net.batch_to_device(batch), config)
   g_eng, d_eng = _engines(config, batch)
   ws = _workspace(state, g_eng, d_eng)
   losses = torch.zeros(16, device="cuda")
-  gctx, dctx = _forward_both(state, batch, config, ws, g_eng, d_eng, losses, keep_g_state=False, need_g=False)
+  gctx, dctx, state = _forward_both(state, batch, config, ws, g_eng, d_eng, losses, keep_g_state=False, need_g=False)
   del gctx
   d_params = state.d_optimizer.target.buf
   ws.d_grads.zero_()
   ops.LAUNCHES[0] += 1
   d_eng.backward_d(dctx, d_params, ws.d_grads)
   d_eng.sn_backward(d_params, ws.d_grads, ws.u0_alt)
+  if defer:
+    ws.pending_d = parallel.all_reduce_sum_(ws.d_grads, async_op=True) or True
+    object.__setattr__(state, "_ws", ws)
+    return state
   parallel.all_reduce_sum_(ws.d_grads)
   _adam(state.d_optimizer, ws.d_grads)
   new_d_state = _swap_d_state(state, ws, d_eng)
@@ -193,7 +225,7 @@ def _train_g_d(rng, state, batch, generator, discriminator, config, additional_d
   g_eng, d_eng = _engines(config, batch)
   ws = _workspace(state, g_eng, d_eng)
   losses = torch.zeros(16, device="cuda")
-  gctx, dctx = _forward_both(state, batch, config, ws, g_eng, d_eng, losses, keep_g_state=True, need_g=True)
+  gctx, dctx, state = _forward_both(state, batch, config, ws, g_eng, d_eng, losses, keep_g_state=True, need_g=True)
   g_params = state.g_optimizer.target.buf
   d_params = state.d_optimizer.target.buf
   # pull-back #1: d_loss -> params_d
@@ -226,10 +258,12 @@ def _train_g_d(rng, state, batch, generator, discriminator, config, additional_d
   g_eng.sn_backward(g_params, ws.g_grads, ws.g_u0_alt)
   del gctx
   h_g = parallel.all_reduce_sum_(ws.g_grads, async_op=True)
+  # D's Adam (its all-reduce finished long ago, behind the generator backward) runs while G's all-reduce is in flight
   if h_d is not None:
     h_d.wait()
-    h_g.wait()
   _adam(state.d_optimizer, ws.d_grads)
+  if h_g is not None:
+    h_g.wait()
   _adam(state.g_optimizer, ws.g_grads, ema=state.ema_params.buf, decay=config.polyak_decay)
   g_eng.prepped_for = None  # xmc_adam rewrote the parameters through raw pointers
   old_stats = state.generator_state["batch_stats"]
