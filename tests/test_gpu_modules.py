@@ -166,7 +166,8 @@ def test_residual_block_modules(spectral):
 @gpu
 def test_attention_and_generic_cross_entropy():
   """attention_lib.attention (attention_lib.py:105-127; softmax over REGIONS, context from the normalised regions):
-  5e-3 (bf16 operands); a word-padding mask does not change it. losses.tf_cross_entropy_loss_with_logits
+  5e-3 (bf16 operands); with a word-padding mask the padded words get uniform attention (fp32 absorption of the
+  scores by the -1e9 shift), as in the reference. losses.tf_cross_entropy_loss_with_logits
   (losses.py:47-51) with soft labels: 1e-6."""
   from xmcgan_image_generation_b200.libml import attention_lib, losses
   g = torch.Generator().manual_seed(11)

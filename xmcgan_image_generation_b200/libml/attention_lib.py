@@ -39,9 +39,11 @@ def attention(region_feat, word_feat, gamma, mask=None):
   """attention_lib.attention (attention_lib.py:105-127): l2-normalise both, alpha = softmax over REGIONS (axis -2) of
   gamma * R^ W^^T (+ mask * -1e9), region_context = alpha^T R^ -> [batch, words, feat]. Kernel program: l2norm_rows,
   one tcgen05 GEMM for the scores, the tiled region-softmax kernel, one batched tcgen05 A^T B GEMM for the context.
-  `mask`: None or the reference's word-padding mask (1 for padded words, constant over regions): a padded word's whole
-  column is shifted by -1e9, which a softmax over regions cancels exactly, so it does not change the result (the
-  reference relies on the later word mask, attention_lib.py:164-165)."""
+  `mask`: None or the reference's word-padding mask (1 for padded words, constant over regions). The reference adds
+  -1e9 to a padded word's whole column BEFORE the softmax over regions; in fp32, gamma * cos - 1e9 rounds to exactly
+  -1e9 for every region (|gamma * cos| < 32 = half an ulp of 1e9), so a padded word gets the UNIFORM attention 1 / R
+  and its context is the mean of the normalised regions. Reproduced here by clearing those score columns (a fill)
+  before the softmax kernel. (word_loss drops these words again through its word mask, attention_lib.py:164-165.)"""
   r = _dev(region_feat).to(torch.bfloat16)
   w = _dev(word_feat)
   B, R, D = r.shape
@@ -55,6 +57,13 @@ def attention(region_feat, word_feat, gamma, mask=None):
   # scores of image b against ITS OWN words: one GEMM per batch entry (batched B operand)
   ops.conv_fwd(rh.view(B, 1, R, D), wh.view(B, L, D), 1, L, ldb=D, batched=True, stride_b=L * D,
                out=S.view(B, 1, R, ldS)[..., :L])
+  if mask is not None:
+    if abs(float(gamma)) >= 32.0:
+      raise NotImplementedError("the -1e9 shift only absorbs the scores exactly for |gamma| < 32")
+    pad_from = (L - _dev(mask)[:, 0, :].sum(-1)).long().tolist()   # index glue: the mask is [arange(L) >= max_len]
+    for b, ml in enumerate(pad_from):
+      if ml < L:
+        S[b, :, ml:L].zero_()   # fill: equal scores -> uniform softmax over regions, as the reference's fp32 gives
   alpha = ops.empty((B, R, ldS), ops.BF16)
   alphaT = ops.zeros((B, ldS, R), ops.BF16)
   # the region-softmax kernel works on [images][R][columns]; here every "image" has its own L columns
