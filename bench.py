@@ -104,7 +104,12 @@ class GemmTimer:
     timer = self
 
     def conv_fwd(x, wk, kh, cout, **kw):
-      c = kw.get("c") or x.shape[3]
+      xp = kw.get("x_pair")
+      if xp is not None:   # fp32 mode: bf16 [.., hi | lo] operand from the producing epilogue; x may be None
+        c = xp.shape[3] // 2
+        x = x if x is not None else xp[..., :c]
+      else:
+        c = kw.get("c") or x.shape[3]
       st = kw.get("stride", 1)
       ho, wo, taps = x.shape[1] // st, x.shape[2] // st, kh * kh
       view = kw.get("view")
@@ -122,7 +127,9 @@ class GemmTimer:
       out = timer._fwd(x, wk, kh, cout, **kw)
       e.record()
       # algorithmic HBM bytes: the input and the output once (+ residual / mask), the weights once
-      nbytes = x.numel() * x.element_size() + out.numel() * out.element_size() + 2.0 * taps * c * cout
+      first = out[0] if isinstance(out, tuple) else out
+      nbytes = x.numel() * 4.0 if xp is not None else x.numel() * x.element_size()
+      nbytes += first.numel() * first.element_size() * (2 if isinstance(out, tuple) else 1) + 2.0 * taps * c * cout
       for extra in (kw.get("residual"), kw.get("mask")):
         if extra is not None:
           nbytes += extra.numel() * extra.element_size()

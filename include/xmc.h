@@ -75,12 +75,18 @@ typedef struct {
    * fp32, pretrained_model_utils.py:87-91). x is the bf16 [hi | lo | hi] split of the fp32 input made by xmc_split3
    * (C = 3 x the real channel count), wk the matching [hi | hi | lo] weight copy of xmc_prep_weights' split mode:
    * the three bf16 products hi*hi + lo*hi + hi*lo accumulated in fp32 carry 16 mantissa bits per operand (SURVEY.md
-   * 8c(4) "3 x bf16 split"). residual / mask are fp32 tensors, out_dtype must be 1. */
+   * 8c(4) "3 x bf16 split"). residual / mask are fp32 tensors, out_dtype must be 1.
+   * 2: the same with the two-part operand: x is bf16 [.., hi(Cr) | lo(Cr)] (Cr = C / 3 real channels, Cr % 64 == 0,
+   * from xmc_split3 mode 2 or from a previous launch's y_pair) and the kernel reads the hi part twice. */
   int act_f32;
+  int ldPair;              /* pixel pitch of y_pair (>= 2 * Cout), see xmc_conv2d_fwd */
 } XmcConvDesc;
 
+/* y_pair: optional (NULL) second output in fp32-activation mode: the result once more as bf16 [.., hi(Cout) |
+ * lo(Cout)] with pixel pitch d->ldPair — the operand form the next launch consumes with act_f32 = 2, so that a chain of
+ * convolutions needs no separate split pass. Needs Cout % 16 == 0 and 32-byte aligned pointers / pitches. */
 int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* wk, const float* bias, const void* residual,
-                   const void* mask, void* y, void* stream);
+                   const void* mask, void* y, void* y_pair, void* stream);
 
 /* Weight gradient / "A^T B" GEMM with both operands pixel-major (MN-major UMMA descriptors), split-K over pixels:
  *   dw[b][tap][ca][cb] (+)= alpha * sum_{pixels p of batch b} xa[p + shift(tap)][ca] * xb[p][cb]
@@ -176,8 +182,9 @@ int xmc_relu_sumhw_bwd(const void* x, int act_f32, const float* dout, int N, int
 int xmc_relu_or_add(const void* a, const void* b, int act_f32, long long n, void* y, void* stream);
 /* fp32 [rows][C] (pitch ld_src) -> bf16 [rows][hi(C) | lo(C) | hi(C)] (pitch ld_dst >= 3C): the A operand of
  * xmc_conv2d_fwd in fp32-activation mode (XmcConvDesc.act_f32); xmc_conv2d_wgrad reads the hi / lo parts as views.
- * weights = 1: the B-operand order [hi | hi | lo] (an activation used as the second GEMM operand). */
-int xmc_split3(const float* src, long long rows, int C, long long ld_src, int weights, void* dst, long long ld_dst,
+ * mode 0: [hi | lo | hi]; mode 1: the B-operand order [hi | hi | lo] (an activation used as the second GEMM
+ * operand); mode 2: the two-part form [hi | lo] (ld_dst >= 2C) for XmcConvDesc.act_f32 = 2. */
+int xmc_split3(const float* src, long long rows, int C, long long ld_src, int mode, void* dst, long long ld_dst,
                void* stream);
 int xmc_cast_f32_to_bf16(const float* src, long long rows, int cols, long long ld_src, void* dst, long long ld_dst,
                          void* stream);

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
 def test_abi_rejects_bad_descriptors_without_touching_the_gpu():
   L = _lib.lib()
   d = _lib.ConvDesc()
-  assert L.xmc_conv2d_fwd(ctypes.byref(d), None, None, None, None, None, None, None) == -1
+  assert L.xmc_conv2d_fwd(ctypes.byref(d), None, None, None, None, None, None, None, None) == -1
   w = _lib.WgradDesc()
   assert L.xmc_conv2d_wgrad(ctypes.byref(w), None, None, None, None, 0, None) == -1
   need = ctypes.c_longlong(-1)

@@ -36,7 +36,7 @@ def conv_fwd(x, wk, KH, KW, bias=None, residual=None, mask=None, relu=0, res_shi
   d.ldRes = residual.stride(2) if residual is not None else 0
   d.ldMask = mask.stride(2) if mask is not None else 0
   _lib.check(L.xmc_conv2d_fwd(ctypes.byref(d), _lib.ptr(x), _lib.ptr(wk), _lib.ptr(bias), _lib.ptr(residual),
-                              _lib.ptr(mask), _lib.ptr(y), _lib.stream()))
+                              _lib.ptr(mask), _lib.ptr(y), None, _lib.stream()))
   torch.cuda.synchronize()
   return y
 

@@ -527,8 +527,9 @@ __global__ void sum_rows_kernel(const T* __restrict__ src, int B, int reps, int 
 // dst[r][2C:3C] = hi. This is the A operand of the tensor-core GEMMs in fp32-activation mode (XmcConvDesc.act_f32): with
 // the weights stored as [hi | hi | lo] the K-concatenated product is hi*hi + lo*hi + hi*lo, fp32-accumulated, i.e. 16
 // mantissa bits per operand. The weight-gradient GEMM reads the hi and lo parts as two pitched views of the same buffer.
-// weights = 1 gives the B-operand order [hi | hi | lo] instead.
-__global__ void split3_kernel(const float* __restrict__ src, long long rows, int C, long long ld_src, int weights,
+// mode 1 gives the B-operand order [hi | hi | lo] instead; mode 2 the two-part "pair" form [hi | lo] (the forward GEMM
+// reads its hi part twice through the tensor map, XmcConvDesc.act_f32 = 2; the weight-gradient GEMM only needs views).
+__global__ void split3_kernel(const float* __restrict__ src, long long rows, int C, long long ld_src, int mode,
                               bf16* __restrict__ dst, long long ld_dst) {
   const int cv = C >> 3;
   const long long total = rows * cv;
@@ -542,8 +543,8 @@ __global__ void split3_kernel(const float* __restrict__ src, long long rows, int
     for (int i = 0; i < 8; ++i) lo[i] = f[i] - __bfloat162float(__float2bfloat16(f[i]));
     bf16* o = dst + r * ld_dst + c;
     store8(o, f);
-    store8(o + C, weights ? f : lo);
-    store8(o + 2 * C, weights ? lo : f);
+    store8(o + C, mode == 1 ? f : lo);
+    if (mode != 2) store8(o + 2 * C, mode == 1 ? lo : f);
   }
 }
 
@@ -824,11 +825,13 @@ extern "C" int xmc_relu_or_add(const void* a, const void* b, int act_f32, long l
   return XMC_OK;
 }
 
-extern "C" int xmc_split3(const float* src, long long rows, int C, long long ld_src, int weights, void* dst,
+extern "C" int xmc_split3(const float* src, long long rows, int C, long long ld_src, int mode, void* dst,
                           long long ld_dst, void* stream) {
-  if (!src || !dst || rows < 1 || C < 8 || (C % 8) || (ld_src % 4) || (ld_dst % 8) || ld_dst < 3 * C) return XMC_EINVAL;
+  if (!src || !dst || rows < 1 || C < 8 || (C % 8) || (ld_src % 4) || (ld_dst % 8) || mode < 0 || mode > 2 ||
+      ld_dst < (mode == 2 ? 2 : 3) * C)
+    return XMC_EINVAL;
   if (!aligned16(src) || !aligned16(dst)) return XMC_EALIGN;
-  split3_kernel<<<grid_for(rows * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>(src, rows, C, ld_src, weights,
+  split3_kernel<<<grid_for(rows * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>(src, rows, C, ld_src, mode,
                                                                                 (bf16*)dst, ld_dst);
   XMC_LAUNCH_CHECK();
   return XMC_OK;

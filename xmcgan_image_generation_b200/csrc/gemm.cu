@@ -55,6 +55,11 @@ struct FwdParams {
   float alpha;
   int vec_ok;
   int bias_smem;  // 1: the bias vector (Cout <= kBiasMax floats) is staged in shared memory by the epilogue warps
+  // fp32-activation mode with the two-part operand (act_f32 = 2): the A tensor is bf16 [.., hi(pairC) | lo(pairC)] and
+  // the K chunks of a tap run hi, lo, hi again (the weights stay [hi | hi | lo], 3 * pairC per tap)
+  int pairC;
+  bf16* out_pair;  // optional second output of the fp32 epilogue: the result as bf16 [.., hi(Cout) | lo(Cout)]
+  int ldPair;
 };
 
 struct WgradParams {
@@ -241,6 +246,18 @@ __device__ __forceinline__ void fwd_epilogue_tile(const FwdParams& p, uint32_t t
 #pragma unroll
         for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
       }
+      if (kF32 && p.out_pair) {
+        // the result once more as the next GEMM's operand: hi = bf16(v), lo = bf16(v - hi), 16 columns = 32 bytes each
+        bf16* o = p.out_pair + pix * p.ldPair + col;
+        uint32_t h[8], l[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          h[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+          l[i] = pack_bf16x2(f[2 * i] - bf16_bits_to_float(h[i] & 0xFFFFu), f[2 * i + 1] - bf16_bits_to_float(h[i] >> 16));
+        }
+        stg256(o, make_uint4(h[0], h[1], h[2], h[3]), make_uint4(h[4], h[5], h[6], h[7]));
+        stg256(o + p.Cout, make_uint4(l[0], l[1], l[2], l[3]), make_uint4(l[4], l[5], l[6], l[7]));
+      }
       if (p.out_dtype == 0) {
         bf16* o = reinterpret_cast<bf16*>(p.out) + pix * p.ldOut + col;
         uint4 a, b;
@@ -379,7 +396,12 @@ gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             mbar_wait(empty_bar(stage), phase ^ 1);
             mbar_arrive_expect_tx(full_bar(stage), p.stage_tx_bytes);
             const uint32_t sa = sbase + stage * kStageBytes;
-            tma_load_4d(sa, &tmA, full_bar(stage), c * 64, w0 * p.strideW + kw - pad_w,
+            int ca = c * 64;
+            if (p.pairC) {  // chunk c of [hi | lo | hi] -> channel offset inside the stored [hi | lo]
+              const int per = p.pairC >> 6, part = c / per;
+              ca = (part == 1 ? p.pairC : 0) + (c - part * per) * 64;
+            }
+            tma_load_4d(sa, &tmA, full_bar(stage), ca, w0 * p.strideW + kw - pad_w,
                         h0 * p.strideH + kh - pad_h, n0);
             tma_load_3d(sa + kABytes, &tmB, full_bar(stage), tap * p.C + c * 64, par * p.Cout + nt * p.BN,
                         p.batched ? n0 : 0);
@@ -1105,11 +1127,11 @@ static cudaError_t ensure_smem_attr(int kind) {
 }
 
 extern "C" int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* wk, const float* bias,
-                              const void* residual, const void* mask, void* y, void* stream) {
+                              const void* residual, const void* mask, void* y, void* y_pair, void* stream) {
   if (!d || !x || !wk || !y) return XMC_EINVAL;
   if (d->N < 1 || d->H < 1 || d->W < 1 || d->C < 1 || d->Cout < 1 || d->KH < 1 || d->KW < 1) return XMC_EINVAL;
   if ((d->ldA % 8) || (d->ldB % 8) || d->ldB < d->KH * d->KW * d->C) return XMC_EINVAL;
-  if (d->pitchW <= 0 && d->ldA < d->C) return XMC_EINVAL;
+  if (d->pitchW <= 0 && d->ldA < (d->act_f32 == 2 ? d->C / 3 * 2 : d->C)) return XMC_EINVAL;
   if (d->C % 8) return XMC_EINVAL;
   if (!aligned16(x) || !aligned16(wk)) return XMC_EALIGN;
   if (d->batched && (d->strideB_batch % 8)) return XMC_EINVAL;
@@ -1144,6 +1166,18 @@ extern "C" int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* w
   // [hi | lo | hi] split of the fp32 input, made by xmc_split3; see XmcConvDesc.act_f32)
   const bool f32io = d->act_f32 != 0;
   if (f32io && d->out_dtype != 1) return XMC_EINVAL;
+  if (d->act_f32 == 2) {   // two-part operand [hi | lo]: d->C = 3 * real channels, real channels % 64 == 0
+    if (d->C % 3 || (d->C / 3) % 64) return XMC_EINVAL;
+    p.pairC = d->C / 3;
+  }
+  if (y_pair) {
+    // second output [hi | lo] of the result: needs the vector path (asserted below) and Cout % 16 == 0
+    if (!f32io || (d->Cout % 16) || (d->ldPair % 16) || d->ldPair < 2 * d->Cout ||
+        (reinterpret_cast<uintptr_t>(y_pair) & 31))
+      return XMC_EINVAL;
+    p.out_pair = reinterpret_cast<bf16*>(y_pair);
+    p.ldPair = d->ldPair;
+  }
   const int rm_unit = f32io ? 4 : 8;  // residual / mask elements per 16 bytes
   p.ldRes = d->ldRes; p.ldMask = d->ldMask; p.res_shift = d->res_shift; p.relu = d->relu;
   p.mask_last = d->mask_last;
@@ -1157,6 +1191,7 @@ extern "C" int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* w
   if (residual) vec32 = vec32 && al32(residual) && (d->ldRes % (2 * rm_unit) == 0);
   if (mask) vec32 = vec32 && al32(mask) && (d->ldMask % (2 * rm_unit) == 0);
   p.vec_ok = vec32 ? 2 : (vec ? 1 : 0);
+  if (y_pair && p.vec_ok != 2) return XMC_EALIGN;
   p.bias_smem = (bias && d->Cout <= kBiasMax && aligned16(bias)) ? 1 : 0;
 
   // ---- resident-weights path for the wide 3x3 layers (see conv3x3_resident_kernel) ------------------------------------
@@ -1208,7 +1243,7 @@ extern "C" int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* w
     const uint64_t pN = d->pitchN > 0 ? (uint64_t)d->pitchN : pH * Hin;
     if ((pW % 8) || (pH % 8) || (pN % 8)) return XMC_EINVAL;
     if (p.tw * p.strideW > 256 || p.th * p.strideH > 256) return XMC_EINVAL;
-    uint64_t dims[4] = {(uint64_t)d->C, (uint64_t)Win, (uint64_t)Hin, (uint64_t)d->N};
+    uint64_t dims[4] = {(uint64_t)(p.pairC ? 2 * p.pairC : d->C), (uint64_t)Win, (uint64_t)Hin, (uint64_t)d->N};
     uint64_t str[3] = {pW * 2, pH * 2, pN * 2};
     uint32_t box[4] = {64, (uint32_t)(p.tw * p.strideW), (uint32_t)(p.th * p.strideH), (uint32_t)p.tn};
     uint32_t est[4] = {1, (uint32_t)p.strideW, (uint32_t)p.strideH, 1};

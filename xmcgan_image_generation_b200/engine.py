@@ -1230,47 +1230,79 @@ class ResNetEngine:
               d224.data_ptr(), _lib.stream())
     ops._call("xmc_resize_bilinear_bwd", d224.data_ptr(), n, S, T, d_images.data_ptr(), _lib.stream())
 
-  def block_forward(self, x, spec):
+  def block_forward(self, x, spec, x_pair=None, want_pair=False):
+    """One bottleneck block. fp32 mode: the convolutions hand their results on as bf16 [hi | lo] operands written by the
+    producing epilogue (ops.conv_fwd want_pair / x_pair), so the chain needs one split pass (of the block input, shared
+    by conv1 and the projection) or none (x_pair given). Returns (out, stash[, out_pair if want_pair])."""
     pre, cin, f, stride, proj = spec
     r1c, r2c, r3c = (self.convs[pre + (f"conv{i}",)] for i in (1, 2, 3))
-    r1 = ops.conv_fwd(x, self.arena[r1c["fwd_off"]:], 1, f, bias=self._bias(r1c), relu=True, ldb=r1c["ld_fwd"])
-    r2 = ops.conv_fwd(r1, self.arena[r2c["fwd_off"]:], 3, f, bias=self._bias(r2c), relu=True, ldb=r2c["ld_fwd"],
-                      stride=stride)
+    f32 = x.dtype == F32
+    if f32 and x_pair is None:
+      x_pair = ops._split_nhwc(x, pair=True)
+    kw = dict(want_pair=True) if f32 else {}
+    pick = (lambda r: r) if f32 else (lambda r: (r, None))
+    r1, r1p = pick(ops.conv_fwd(x, self.arena[r1c["fwd_off"]:], 1, f, bias=self._bias(r1c), relu=True,
+                                ldb=r1c["ld_fwd"], x_pair=x_pair, **kw))
+    r2, r2p = pick(ops.conv_fwd(r1, self.arena[r2c["fwd_off"]:], 3, f, bias=self._bias(r2c), relu=True,
+                                ldb=r2c["ld_fwd"], stride=stride, x_pair=r1p, **kw))
     if proj:
       pc = self.convs[pre + ("proj_conv",)]
-      sc = ops.conv_fwd(x, self.arena[pc["fwd_off"]:], 1, 4 * f, bias=self._bias(pc), ldb=pc["ld_fwd"], stride=stride)
+      sc = ops.conv_fwd(x, self.arena[pc["fwd_off"]:], 1, 4 * f, bias=self._bias(pc), ldb=pc["ld_fwd"], stride=stride,
+                        x_pair=x_pair)
     else:
       sc = x
-    out = ops.conv_fwd(r2, self.arena[r3c["fwd_off"]:], 1, 4 * f, bias=self._bias(r3c), residual=sc, relu=True,
-                       ldb=r3c["ld_fwd"])
-    return out, dict(x=x, r1=r1, r2=r2)
+    res = ops.conv_fwd(r2, self.arena[r3c["fwd_off"]:], 1, 4 * f, bias=self._bias(r3c), residual=sc, relu=True,
+                       ldb=r3c["ld_fwd"], x_pair=r2p, want_pair=want_pair and f32)
+    out, out_pair = res if (want_pair and f32) else (res, None)
+    stash = dict(x=x, r1=r1, r2=r2)
+    return (out, stash, out_pair) if want_pair else (out, stash)
 
-  def block_backward(self, g, x, r1, r2, spec, mask_input):
+  def _zero_insert(self, t, c):
+    """z[n,2h,2w,:] = t[n,h,w,:], zero elsewhere (the transpose of a stride-2 sampling), on a [.., c]-channel tensor."""
+    n, h, w = t.shape[0], t.shape[1], t.shape[2]
+    z = ops.empty((n, 2 * h, 2 * w, c), t.dtype)
+    ops._call("xmc_zero_insert2", t.data_ptr(), ops._f32(t), n, h, w, c, z.data_ptr(), _lib.stream())
+    return z
+
+  def block_backward(self, g, x, r1, r2, spec, mask_input, g_pair=None, want_pair=False):
     """g: gradient wrt the block output, already multiplied by [output > 0]. Returns the gradient wrt the block input
-    (multiplied by [input > 0] when mask_input: the input is the previous block's relu output)."""
+    (multiplied by [input > 0] when mask_input: the input is the previous block's relu output). fp32 mode: gradients
+    travel between the convolutions as [hi | lo] operands (see block_forward); the zero insertion of the stride-2
+    transposes acts on that operand directly (a pure copy), the fp32 zero-inserted tensor is never made."""
     pre, cin, f, stride, proj = spec
-    n = g.shape[0]
     r1c, r2c, r3c = (self.convs[pre + (f"conv{i}",)] for i in (1, 2, 3))
-    dr2 = ops.conv_fwd(g, self.arena[r3c["dg_off"]:], 1, f, mask=r2, ldb=r3c["ld_dg"])
+    f32 = g.dtype == F32
+    if f32 and g_pair is None:
+      g_pair = ops._split_nhwc(g, pair=True)
+    kw = dict(want_pair=True) if f32 else {}
+    pick = (lambda r: r) if f32 else (lambda r: (r, None))
+    dr2, dr2p = pick(ops.conv_fwd(g, self.arena[r3c["dg_off"]:], 1, f, mask=r2, ldb=r3c["ld_dg"], x_pair=g_pair, **kw))
     if stride == 2:
-      z = ops.empty((n, 2 * dr2.shape[1], 2 * dr2.shape[2], f), dr2.dtype)
-      ops._call("xmc_zero_insert2", dr2.data_ptr(), ops._f32(dr2), n, dr2.shape[1], dr2.shape[2], f, z.data_ptr(),
-                _lib.stream())
-      dr1 = ops.conv_fwd(z, self.arena[r2c["dg_off"]:], 3, f, mask=r1, ldb=r2c["ld_dg"], pad=2, alg_scale=0.25)
+      if f32:
+        dr1, dr1p = ops.conv_fwd(None, self.arena[r2c["dg_off"]:], 3, f, mask=r1, ldb=r2c["ld_dg"], pad=2,
+                                 alg_scale=0.25, x_pair=self._zero_insert(dr2p, 2 * f), want_pair=True)
+      else:
+        dr1, dr1p = ops.conv_fwd(self._zero_insert(dr2, f), self.arena[r2c["dg_off"]:], 3, f, mask=r1,
+                                 ldb=r2c["ld_dg"], pad=2, alg_scale=0.25), None
     else:
-      dr1 = ops.conv_fwd(dr2, self.arena[r2c["dg_off"]:], 3, f, mask=r1, ldb=r2c["ld_dg"])
+      dr1, dr1p = pick(ops.conv_fwd(dr2, self.arena[r2c["dg_off"]:], 3, f, mask=r1, ldb=r2c["ld_dg"], x_pair=dr2p, **kw))
     if proj:
       pc = self.convs[pre + ("proj_conv",)]
-      g_in = g
+      g_in, g_in_pair = g, g_pair
       if stride == 2:
-        g_in = ops.empty((n, 2 * g.shape[1], 2 * g.shape[2], 4 * f), g.dtype)
-        ops._call("xmc_zero_insert2", g.data_ptr(), ops._f32(g), n, g.shape[1], g.shape[2], 4 * f, g_in.data_ptr(),
-                  _lib.stream())
-      sg = ops.conv_fwd(g_in, self.arena[pc["dg_off"]:], 1, cin, ldb=pc["ld_dg"], alg_scale=0.25 if stride == 2 else 1.0)
+        if f32:
+          g_in, g_in_pair = None, self._zero_insert(g_pair, 8 * f)
+        else:
+          g_in = self._zero_insert(g, 4 * f)
+      sg = ops.conv_fwd(g_in, self.arena[pc["dg_off"]:], 1, cin, ldb=pc["ld_dg"], alg_scale=0.25 if stride == 2 else 1.0,
+                        x_pair=g_in_pair)
     else:
       sg = g
-    return ops.conv_fwd(dr1, self.arena[r1c["dg_off"]:], 1, cin, residual=sg, ldb=r1c["ld_dg"],
-                        mask=x if mask_input else None, mask_last=True)
+    res = ops.conv_fwd(dr1, self.arena[r1c["dg_off"]:], 1, cin, residual=sg, ldb=r1c["ld_dg"],
+                       mask=x if mask_input else None, mask_last=True, x_pair=dr1p, want_pair=want_pair and f32)
+    if want_pair:
+      return res if f32 else (res, None)
+    return res
 
   def forward(self, images_f32):
     """images_f32: fp32 [N,S,S,3] in [0,1]. Returns (logits fp32 [N,num_classes], ctx)."""
@@ -1281,8 +1313,9 @@ class ResNetEngine:
     N, S = images_f32.shape[0], images_f32.shape[1]
     stem, x = self.stem_forward(images_f32)
     ctx = {"N": N, "S": S, "stem": stem, "pool0": x, "blocks": []}
+    xp = None
     for spec in self.blocks:
-      x, sv = self.block_forward(x, spec)
+      x, sv, xp = self.block_forward(x, spec, x_pair=xp, want_pair=True)
       ctx["blocks"].append(sv)
     ctx["x_last"] = x
     feat = ops.relu_sumhw(x)  # the block output is already >= 0: this is the plain spatial sum
@@ -1308,8 +1341,10 @@ class ResNetEngine:
     dfeat = ops.conv_fwd(as4(dl_bf), self.arena[self.head_dg:], 1, self.c_last, ldb=ncp * self.S, alpha=1.0 / ctx["hw"],
                          out_dtype=F32).view(n, self.c_last)
     dout = ops.relu_sumhw_bwd(ctx["x_last"][sl], dfeat)   # includes the relu mask of the last block output
+    dpair = None
     for i in range(len(self.blocks) - 1, -1, -1):
       sv = ctx["blocks"][i]
       # the first block's input (max-pool output) is not a relu output (no ReLU after init_bn, resnet_v1.py:146-154)
-      dout = self.block_backward(dout, sv["x"][sl], sv["r1"][sl], sv["r2"][sl], self.blocks[i], mask_input=i > 0)
+      dout, dpair = self.block_backward(dout, sv["x"][sl], sv["r1"][sl], sv["r2"][sl], self.blocks[i],
+                                        mask_input=i > 0, g_pair=dpair, want_pair=True)
     self.stem_backward(dout, ctx["stem"][sl], ctx["pool0"][sl], ctx["S"], d_images)

@@ -62,51 +62,70 @@ def zeros(shape, dtype=F32):
 
 
 # ------------------------------------------------------------------------------------------------------------- GEMMs
-def split3(x2d, weights=False):
+def split3(x2d, weights=False, pair=False):
   """fp32 [rows, C] (pitched) -> bf16 [rows, 3C]: [hi | lo | hi] for an activation, [hi | hi | lo] for the B operand
-  (a "weight" that is itself an activation, as in the word-loss GEMMs) — see XmcConvDesc.act_f32."""
+  (a "weight" that is itself an activation, as in the word-loss GEMMs); pair=True: the two-part form [rows, 2C] =
+  [hi | lo] — see XmcConvDesc.act_f32."""
   rows, C = x2d.shape
-  out = empty((rows, 3 * C), BF16)
-  _call("xmc_split3", ptr(x2d), rows, C, x2d.stride(0), int(weights), ptr(out), 3 * C, stream())
+  parts = 2 if pair else 3
+  out = empty((rows, parts * C), BF16)
+  _call("xmc_split3", ptr(x2d), rows, C, x2d.stride(0), 2 if pair else int(weights), ptr(out), parts * C, stream())
   return out
 
 
-def _split_nhwc(x, c=None):
-  """[N,H,W,>=C] fp32 view -> bf16 [N,H,W,3C] split copy (rows must collapse)."""
+def pair_ok(C):
+  """The forward GEMM can read the two-part operand [hi | lo] when the channel count is a multiple of 64."""
+  return C % 64 == 0
+
+
+def _split_nhwc(x, c=None, pair=False):
+  """[N,H,W,>=C] fp32 view -> bf16 [N,H,W,3C] split copy, or [N,H,W,2C] with pair=True (rows must collapse)."""
   _check_dense_rows(x)
   C = x.shape[-1] if c is None else c
   rows = x.numel() // x.shape[-1]
   flat = torch.as_strided(x, (rows, C), (x.stride(-2), 1))
-  return split3(flat).view(*x.shape[:-1], 3 * C)
+  return split3(flat, pair=pair).view(*x.shape[:-1], (2 if pair else 3) * C)
 
 
 def conv_fwd(x, wk, kh, cout, *, bias=None, residual=None, res_shift=0, mask=None, relu=False, out=None,
              out_dtype=None, alpha=1.0, ldb=None, batched=False, stride_b=0, c=None, stride=1, pad=None,
-             mask_last=False, view=None, subpixel=False, pre_split=False, alg_scale=1.0):
+             mask_last=False, view=None, subpixel=False, pre_split=False, alg_scale=1.0, x_pair=None,
+             want_pair=False):
   """x: [N,H,W,>=C] bf16 view (channel-contiguous); wk: bf16 tensor whose data pointer is the [cout][kh*kh*C] K-major
   matrix (row pitch ldb). Returns y [N,H/stride,W/stride,cout] (or writes into the `out` view).
   stride=2 reads the input at (h*2+kh-pad, w*2+kw-pad) (XLA SAME: pad low = 0 for a 3x3 or 1x1 kernel on an even
   input). alg_scale: bookkeeping only (bench.py): algorithmic FLOPs of this launch relative to the dense count, e.g.
-  0.25 for a stride-1 convolution over a zero-inserted gradient (the transpose of a stride-2 convolution). `view`: dict overriding the input view (Hout, Wout, KH, KW, pitches, strides) for the ResNet stem."""
+  0.25 for a stride-1 convolution over a zero-inserted gradient (the transpose of a stride-2 convolution).
+  fp32-activation mode, chains of convolutions: want_pair=True also returns the result as the bf16 two-part operand
+  [.., hi | lo] (written by the epilogue), x_pair= passes such an operand in place of splitting x here; x may then be
+  None (shape taken from x_pair). `view`: dict overriding the input view (Hout, Wout, KH, KW, pitches, strides) for the ResNet stem."""
+  pairC = 0
+  if x_pair is not None:   # fp32 mode, operand already in the two-part form (a previous launch's want_pair output)
+    pairC = x_pair.shape[-1] // 2
+    x, pre_split, c = x_pair, True, 3 * pairC
+  elif x is not None and x.dtype == F32 and view is None and c is None and pair_ok(x.shape[-1]):
+    pairC = x.shape[-1]
+    x, pre_split, c = _split_nhwc(x, pair=True), True, 3 * pairC
   f32 = x.dtype == F32 or pre_split   # pre_split: x already is a bf16 split operand, I/O tensors are fp32
   if f32 and not pre_split:
-    # fp32-activation mode: A = [hi | lo | hi] split of x (3C channels); wk is either already a split weight copy of
-    # the arena (bf16, ld given by the caller) or an fp32 activation used as the B operand, split here as [hi | hi | lo]
+    # fp32-activation mode, channel counts that are not a multiple of 64: A = [hi | lo | hi] split of x (3C channels)
     x = _split_nhwc(x, c)
     c = None
-    if wk.dtype == F32:
-      Kb = wk.shape[-1]
-      ldb_in = ldb if ldb is not None else Kb
-      rows_b = wk.numel() // wk.shape[-1]
-      wk = split3(torch.as_strided(wk, (rows_b, Kb), (ldb_in, 1)), weights=True)
-      ldb, stride_b = 3 * Kb, 3 * stride_b
+  if f32 and wk.dtype == F32:
+    # wk is either already a split weight copy of the arena (bf16, ld given by the caller) or, as here, an fp32
+    # activation used as the B operand (word-loss GEMMs): split as [hi | hi | lo]
+    Kb = wk.shape[-1]
+    ldb_in = ldb if ldb is not None else Kb
+    rows_b = wk.numel() // wk.shape[-1]
+    wk = split3(torch.as_strided(wk, (rows_b, Kb), (ldb_in, 1)), weights=True)
+    ldb, stride_b = 3 * Kb, 3 * stride_b
   if out_dtype is None:
     out_dtype = F32 if f32 else BF16
   N, H, W = x.shape[0], x.shape[1], x.shape[2]
   C = x.shape[3] if c is None else c
   _check_dense_rows(x)
   d = ConvDesc()
-  d.act_f32 = int(f32)
+  d.act_f32 = 2 if pairC else int(f32)
   d.N, d.H, d.W, d.C, d.ldA = N, H // stride, W // stride, C, _pix_ld(x)
   d.KH = d.KW = kh
   d.pad_h = d.pad_w = (kh // 2 if stride == 1 else 0) if pad is None else pad
@@ -138,8 +157,14 @@ def conv_fwd(x, wk, kh, cout, *, bias=None, residual=None, res_shift=0, mask=Non
   d.res_shift = res_shift
   d.ldRes = _pix_ld(residual) if residual is not None else 0
   d.ldMask = _pix_ld(mask) if mask is not None else 0
-  _call("xmc_conv2d_fwd", ctypes.byref(d), ptr(x), ptr(wk), ptr(bias), ptr(residual), ptr(mask), ptr(out), stream())
-  return out
+  out_pair = None
+  if want_pair:
+    assert f32 and cout % 16 == 0
+    out_pair = empty(tuple(out.shape[:-1]) + (2 * cout,), BF16)
+    d.ldPair = 2 * cout
+  _call("xmc_conv2d_fwd", ctypes.byref(d), ptr(x), ptr(wk), ptr(bias), ptr(residual), ptr(mask), ptr(out),
+        ptr(out_pair), stream())
+  return (out, out_pair) if want_pair else out
 
 
 def wgrad(xa, xb, kh, out, *, out_mode=0, batched=False, ld_out=None, tap_stride=None, batch_stride=0, alpha=1.0,
@@ -148,10 +173,10 @@ def wgrad(xa, xb, kh, out, *, out_mode=0, batched=False, ld_out=None, tap_stride
   view_a: dict re-pitching xa (packed-window form, see XmcWgradDesc.HinA): KH, KW, Hin, pitchW, pitchH, pitchN."""
   if xa.dtype == F32 or xb.dtype == F32:
     # fp32-activation mode: dw = a_hi^T b_hi + a_lo^T b_hi + a_hi^T b_lo, three passes of the bf16 kernel over pitched
-    # views of the [hi | lo | hi] split copies, accumulated in the fp32 output (16 mantissa bits per operand)
+    # views of the [hi | lo] split copies, accumulated in the fp32 output (16 mantissa bits per operand)
     assert xa.dtype == F32 and xb.dtype == F32 and view_a is None and ca is None and cb is None
     Ca, Cb = xa.shape[-1], xb.shape[-1]
-    a3, b3 = _split_nhwc(xa), _split_nhwc(xb)
+    a3, b3 = _split_nhwc(xa, pair=True), _split_nhwc(xb, pair=True)   # [hi | lo]: only the two views are read
     a_hi, a_lo, b_hi, b_lo = a3[..., :Ca], a3[..., Ca:2 * Ca], b3[..., :Cb], b3[..., Cb:2 * Cb]
     assert out.dtype == F32
     first = 1 if out_mode in (1, 2) else 0   # store modes: the first pass stores, the others accumulate
