@@ -127,10 +127,10 @@ class GemmTimer:
       out = timer._fwd(x, wk, kh, cout, **kw)
       e.record()
       # algorithmic HBM bytes: the input and the output once (+ residual / mask), the weights once
-      first = out[0] if isinstance(out, tuple) else out
+      outs = [t for t in (out if isinstance(out, tuple) else (out,)) if t is not None]
       nbytes = x.numel() * 4.0 if xp is not None else x.numel() * x.element_size()
-      nbytes += first.numel() * first.element_size() * (2 if isinstance(out, tuple) else 1) + 2.0 * taps * c * cout
-      for extra in (kw.get("residual"), kw.get("mask")):
+      nbytes += sum(t.numel() * t.element_size() for t in outs) + 2.0 * taps * c * cout
+      for extra in (kw.get("residual"), kw.get("mask"), kw.get("residual_pair"), kw.get("mask_pair")):
         if extra is not None:
           nbytes += extra.numel() * extra.element_size()
       timer.bytes["gemm_fwd_kernel"] = timer.bytes.get("gemm_fwd_kernel", 0.0) + nbytes

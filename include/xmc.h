@@ -80,6 +80,10 @@ typedef struct {
    * from xmc_split3 mode 2 or from a previous launch's y_pair) and the kernel reads the hi part twice. */
   int act_f32;
   int ldPair;              /* pixel pitch of y_pair (>= 2 * Cout), see xmc_conv2d_fwd */
+  /* fp32-activation mode: residual / mask given as two-part bf16 tensors [.., hi(Cout) | lo(Cout)] (ldRes / ldMask in
+   * bf16 elements) instead of fp32 ones: residual = hi + lo, mask = [hi > 0]. With y_pair as the only output (y NULL) a
+   * chain of convolutions never materialises fp32 activations. */
+  int res_pair, mask_pair;
 } XmcConvDesc;
 
 /* y_pair: optional (NULL) second output in fp32-activation mode: the result once more as bf16 [.., hi(Cout) |

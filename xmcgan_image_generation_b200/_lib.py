@@ -34,6 +34,7 @@ class ConvDesc(ctypes.Structure):
       ("strideH", ctypes.c_int), ("strideW", ctypes.c_int), ("Hin", ctypes.c_int), ("Win", ctypes.c_int),
       ("pitchW", ctypes.c_longlong), ("pitchH", ctypes.c_longlong), ("pitchN", ctypes.c_longlong),
       ("mask_last", ctypes.c_int), ("subpixel", ctypes.c_int), ("act_f32", ctypes.c_int), ("ldPair", ctypes.c_int),
+      ("res_pair", ctypes.c_int), ("mask_pair", ctypes.c_int),
   ]
 
 

@@ -60,6 +60,9 @@ struct FwdParams {
   int pairC;
   bf16* out_pair;  // optional second output of the fp32 epilogue: the result as bf16 [.., hi(Cout) | lo(Cout)]
   int ldPair;
+  // fp32 epilogue reading its residual / mask from two-part bf16 tensors [.., hi(Cout) | lo(Cout)] (pitch ldRes / ldMask
+  // in bf16 elements): residual = hi + lo, mask = sign of hi. `out` may then be null (pair output only).
+  int res_pair, mask_pair;
 };
 
 struct WgradParams {
@@ -195,9 +198,29 @@ __device__ __forceinline__ void fwd_epilogue_tile(const FwdParams& p, uint32_t t
     tmem_ld16(t_addr + c0, v);  // asynchronous until tmem_ld_wait
     const int col = nt * p.BN + c0;
     if (row_ok && p.vec_ok && p.Cout - col >= 16) {
-      if (p.mask) load16(p.mask, pix * p.ldMask + col, mk);
-      if (p.residual) load16(p.residual, rpix * p.ldRes + col, rs);
+      if (kF32 && p.mask && p.mask_pair) {   // 16 bf16 hi values = 32 bytes
+        ldg256(reinterpret_cast<const bf16*>(p.mask) + pix * p.ldMask + col, mk[0], mk[1]);
+      } else if (p.mask) {
+        load16(p.mask, pix * p.ldMask + col, mk);
+      }
+      if (kF32 && p.residual && p.res_pair) {  // hi and lo parts, 32 bytes each
+        const bf16* rp = reinterpret_cast<const bf16*>(p.residual) + rpix * p.ldRes + col;
+        ldg256(rp, rs[0], rs[1]);
+        ldg256(rp + p.Cout, rs[kV - 2], rs[kV - 1]);
+      } else if (p.residual) {
+        load16(p.residual, rpix * p.ldRes + col, rs);
+      }
     }
+  };
+  // residual element i: fp32 / bf16 tensor, or hi + lo of a two-part tensor (fp32 instantiation only)
+  auto res_elem = [&](const uint4 (&src)[kV], int i) -> float {
+    if (kF32 && p.res_pair) {
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(src);
+      const uint32_t h = w[i >> 1], l = w[8 + (i >> 1)];
+      return (i & 1) ? bf16_bits_to_float(h >> 16) + bf16_bits_to_float(l >> 16)
+                     : bf16_bits_to_float(h & 0xFFFFu) + bf16_bits_to_float(l & 0xFFFFu);
+    }
+    return elem(src, i);
   };
   auto finish = [&](int c0, const uint32_t (&v)[16], const uint4 (&mk)[kV], const uint4 (&rs)[kV]) {
     const int col = nt * p.BN + c0;
@@ -220,10 +243,10 @@ __device__ __forceinline__ void fwd_epilogue_tile(const FwdParams& p, uint32_t t
       }
       if (p.residual && p.mask_last) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) f[i] += elem(rs, i);
+        for (int i = 0; i < 16; ++i) f[i] += res_elem(rs, i);
       }
       if (p.mask) {
-        if (kF32) {
+        if (kF32 && !p.mask_pair) {
 #pragma unroll
           for (int i = 0; i < 16; ++i)
             if (!(elem(mk, i) > 0.f)) f[i] = 0.f;
@@ -240,7 +263,7 @@ __device__ __forceinline__ void fwd_epilogue_tile(const FwdParams& p, uint32_t t
       }
       if (p.residual && !p.mask_last) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) f[i] += elem(rs, i);
+        for (int i = 0; i < 16; ++i) f[i] += res_elem(rs, i);
       }
       if (p.relu) {
 #pragma unroll
@@ -258,7 +281,9 @@ __device__ __forceinline__ void fwd_epilogue_tile(const FwdParams& p, uint32_t t
         stg256(o, make_uint4(h[0], h[1], h[2], h[3]), make_uint4(h[4], h[5], h[6], h[7]));
         stg256(o + p.Cout, make_uint4(l[0], l[1], l[2], l[3]), make_uint4(l[4], l[5], l[6], l[7]));
       }
-      if (p.out_dtype == 0) {
+      if (!p.out) {
+        // pair output only
+      } else if (p.out_dtype == 0) {
         bf16* o = reinterpret_cast<bf16*>(p.out) + pix * p.ldOut + col;
         uint4 a, b;
         a.x = pack_bf16x2(f[0], f[1]);   a.y = pack_bf16x2(f[2], f[3]);
@@ -1128,7 +1153,7 @@ static cudaError_t ensure_smem_attr(int kind) {
 
 extern "C" int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* wk, const float* bias,
                               const void* residual, const void* mask, void* y, void* y_pair, void* stream) {
-  if (!d || !x || !wk || !y) return XMC_EINVAL;
+  if (!d || !x || !wk || (!y && !y_pair)) return XMC_EINVAL;
   if (d->N < 1 || d->H < 1 || d->W < 1 || d->C < 1 || d->Cout < 1 || d->KH < 1 || d->KW < 1) return XMC_EINVAL;
   if ((d->ldA % 8) || (d->ldB % 8) || d->ldB < d->KH * d->KW * d->C) return XMC_EINVAL;
   if (d->pitchW <= 0 && d->ldA < (d->act_f32 == 2 ? d->C / 3 * 2 : d->C)) return XMC_EINVAL;
@@ -1179,19 +1204,23 @@ extern "C" int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* w
     p.ldPair = d->ldPair;
   }
   const int rm_unit = f32io ? 4 : 8;  // residual / mask elements per 16 bytes
+  if ((d->res_pair || d->mask_pair) && !f32io) return XMC_EINVAL;
+  p.res_pair = (residual && d->res_pair) ? 1 : 0;
+  p.mask_pair = (mask && d->mask_pair) ? 1 : 0;
   p.ldRes = d->ldRes; p.ldMask = d->ldMask; p.res_shift = d->res_shift; p.relu = d->relu;
   p.mask_last = d->mask_last;
   p.alpha = d->alpha;
-  bool vec = aligned16(y) && (d->out_dtype == 0 ? (d->ldOut % 8 == 0) : (d->ldOut % 4 == 0));
-  if (residual) vec = vec && aligned16(residual) && (d->ldRes % rm_unit == 0);
-  if (mask) vec = vec && aligned16(mask) && (d->ldMask % rm_unit == 0);
+  bool vec = !y || (aligned16(y) && (d->out_dtype == 0 ? (d->ldOut % 8 == 0) : (d->ldOut % 4 == 0)));
+  if (residual) vec = vec && aligned16(residual) && (d->ldRes % (p.res_pair ? 8 : rm_unit) == 0);
+  if (mask) vec = vec && aligned16(mask) && (d->ldMask % (p.mask_pair ? 8 : rm_unit) == 0);
   // 32-byte accesses when every pointer and pitch allows it (16 bf16 / 8 fp32 columns per access)
   auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
-  bool vec32 = vec && al32(y) && (d->out_dtype == 0 ? (d->ldOut % 16 == 0) : (d->ldOut % 8 == 0));
-  if (residual) vec32 = vec32 && al32(residual) && (d->ldRes % (2 * rm_unit) == 0);
-  if (mask) vec32 = vec32 && al32(mask) && (d->ldMask % (2 * rm_unit) == 0);
+  bool vec32 = vec && (!y || (al32(y) && (d->out_dtype == 0 ? (d->ldOut % 16 == 0) : (d->ldOut % 8 == 0))));
+  if (residual) vec32 = vec32 && al32(residual) && (d->ldRes % (p.res_pair ? 16 : 2 * rm_unit) == 0);
+  if (mask) vec32 = vec32 && al32(mask) && (d->ldMask % (p.mask_pair ? 16 : 2 * rm_unit) == 0);
   p.vec_ok = vec32 ? 2 : (vec ? 1 : 0);
-  if (y_pair && p.vec_ok != 2) return XMC_EALIGN;
+  // the two-part tensors are only handled by the 32-byte vector path (Cout % 16 == 0 keeps every chunk on it)
+  if ((y_pair || p.res_pair || p.mask_pair) && (p.vec_ok != 2 || (d->Cout % 16))) return XMC_EALIGN;
   p.bias_smem = (bias && d->Cout <= kBiasMax && aligned16(bias)) ? 1 : 0;
 
   // ---- resident-weights path for the wide 3x3 layers (see conv3x3_resident_kernel) ------------------------------------

@@ -1230,31 +1230,41 @@ class ResNetEngine:
               d224.data_ptr(), _lib.stream())
     ops._call("xmc_resize_bilinear_bwd", d224.data_ptr(), n, S, T, d_images.data_ptr(), _lib.stream())
 
-  def block_forward(self, x, spec, x_pair=None, want_pair=False):
-    """One bottleneck block. fp32 mode: the convolutions hand their results on as bf16 [hi | lo] operands written by the
-    producing epilogue (ops.conv_fwd want_pair / x_pair), so the chain needs one split pass (of the block input, shared
-    by conv1 and the projection) or none (x_pair given). Returns (out, stash[, out_pair if want_pair])."""
+  def block_forward(self, x, spec, x_pair=None, want_pair=False, want_f32=True):
+    """One bottleneck block. bf16 mode: x -> out (bf16 tensors). fp32 mode: activations travel between the convolutions
+    as two-part bf16 operands [.., hi | lo] written by the producing epilogue and consumed as A operand (K-chunk
+    remap), residual (hi + lo) and mask (sign of hi); fp32 tensors are only materialised where asked (want_f32: the
+    block output, e.g. for the pooling head). One split pass of the block input at most (none with x_pair).
+    Returns (out, stash[, out_pair if want_pair]); the stash holds what the backward needs (pairs in fp32 mode)."""
     pre, cin, f, stride, proj = spec
     r1c, r2c, r3c = (self.convs[pre + (f"conv{i}",)] for i in (1, 2, 3))
-    f32 = x.dtype == F32
-    if f32 and x_pair is None:
+    w = lambda rec, key="fwd_off": self.arena[rec[key]:]
+    if self.act != F32:
+      r1 = ops.conv_fwd(x, w(r1c), 1, f, bias=self._bias(r1c), relu=True, ldb=r1c["ld_fwd"])
+      r2 = ops.conv_fwd(r1, w(r2c), 3, f, bias=self._bias(r2c), relu=True, ldb=r2c["ld_fwd"], stride=stride)
+      sc = x
+      if proj:
+        pc = self.convs[pre + ("proj_conv",)]
+        sc = ops.conv_fwd(x, w(pc), 1, 4 * f, bias=self._bias(pc), ldb=pc["ld_fwd"], stride=stride)
+      out = ops.conv_fwd(r2, w(r3c), 1, 4 * f, bias=self._bias(r3c), residual=sc, relu=True, ldb=r3c["ld_fwd"])
+      stash = dict(x=x, r1=r1, r2=r2)
+      return (out, stash, None) if want_pair else (out, stash)
+    if x_pair is None:
       x_pair = ops._split_nhwc(x, pair=True)
-    kw = dict(want_pair=True) if f32 else {}
-    pick = (lambda r: r) if f32 else (lambda r: (r, None))
-    r1, r1p = pick(ops.conv_fwd(x, self.arena[r1c["fwd_off"]:], 1, f, bias=self._bias(r1c), relu=True,
-                                ldb=r1c["ld_fwd"], x_pair=x_pair, **kw))
-    r2, r2p = pick(ops.conv_fwd(r1, self.arena[r2c["fwd_off"]:], 3, f, bias=self._bias(r2c), relu=True,
-                                ldb=r2c["ld_fwd"], stride=stride, x_pair=r1p, **kw))
+    pair_only = dict(want_pair=True, want_f32=False)
+    _, r1p = ops.conv_fwd(None, w(r1c), 1, f, bias=self._bias(r1c), relu=True, ldb=r1c["ld_fwd"], x_pair=x_pair,
+                          **pair_only)
+    _, r2p = ops.conv_fwd(None, w(r2c), 3, f, bias=self._bias(r2c), relu=True, ldb=r2c["ld_fwd"], stride=stride,
+                          x_pair=r1p, **pair_only)
+    res_kw = dict(residual_pair=x_pair)
     if proj:
       pc = self.convs[pre + ("proj_conv",)]
-      sc = ops.conv_fwd(x, self.arena[pc["fwd_off"]:], 1, 4 * f, bias=self._bias(pc), ldb=pc["ld_fwd"], stride=stride,
-                        x_pair=x_pair)
-    else:
-      sc = x
-    res = ops.conv_fwd(r2, self.arena[r3c["fwd_off"]:], 1, 4 * f, bias=self._bias(r3c), residual=sc, relu=True,
-                       ldb=r3c["ld_fwd"], x_pair=r2p, want_pair=want_pair and f32)
-    out, out_pair = res if (want_pair and f32) else (res, None)
-    stash = dict(x=x, r1=r1, r2=r2)
+      _, scp = ops.conv_fwd(None, w(pc), 1, 4 * f, bias=self._bias(pc), ldb=pc["ld_fwd"], stride=stride, x_pair=x_pair,
+                            **pair_only)
+      res_kw = dict(residual_pair=scp)
+    out, out_pair = ops.conv_fwd(None, w(r3c), 1, 4 * f, bias=self._bias(r3c), relu=True, ldb=r3c["ld_fwd"], x_pair=r2p,
+                                 want_pair=True, want_f32=want_f32, **res_kw)
+    stash = dict(x=x_pair, r1=r1p, r2=r2p)
     return (out, stash, out_pair) if want_pair else (out, stash)
 
   def _zero_insert(self, t, c):
@@ -1264,45 +1274,47 @@ class ResNetEngine:
     ops._call("xmc_zero_insert2", t.data_ptr(), ops._f32(t), n, h, w, c, z.data_ptr(), _lib.stream())
     return z
 
-  def block_backward(self, g, x, r1, r2, spec, mask_input, g_pair=None, want_pair=False):
-    """g: gradient wrt the block output, already multiplied by [output > 0]. Returns the gradient wrt the block input
-    (multiplied by [input > 0] when mask_input: the input is the previous block's relu output). fp32 mode: gradients
-    travel between the convolutions as [hi | lo] operands (see block_forward); the zero insertion of the stride-2
-    transposes acts on that operand directly (a pure copy), the fp32 zero-inserted tensor is never made."""
+  def block_backward(self, g, x, r1, r2, spec, mask_input, g_pair=None, want_pair=False, want_f32=True):
+    """g: gradient wrt the block output, already multiplied by [output > 0]; x, r1, r2: the forward's stash. Returns the
+    gradient wrt the block input (multiplied by [input > 0] when mask_input: the input is the previous block's relu
+    output). fp32 mode: gradients and masks are two-part operands as in block_forward; the zero insertion of the
+    stride-2 transposes acts on the operand directly (a pure copy)."""
     pre, cin, f, stride, proj = spec
     r1c, r2c, r3c = (self.convs[pre + (f"conv{i}",)] for i in (1, 2, 3))
-    f32 = g.dtype == F32
-    if f32 and g_pair is None:
-      g_pair = ops._split_nhwc(g, pair=True)
-    kw = dict(want_pair=True) if f32 else {}
-    pick = (lambda r: r) if f32 else (lambda r: (r, None))
-    dr2, dr2p = pick(ops.conv_fwd(g, self.arena[r3c["dg_off"]:], 1, f, mask=r2, ldb=r3c["ld_dg"], x_pair=g_pair, **kw))
-    if stride == 2:
-      if f32:
-        dr1, dr1p = ops.conv_fwd(None, self.arena[r2c["dg_off"]:], 3, f, mask=r1, ldb=r2c["ld_dg"], pad=2,
-                                 alg_scale=0.25, x_pair=self._zero_insert(dr2p, 2 * f), want_pair=True)
+    w = lambda rec: self.arena[rec["dg_off"]:]
+    if self.act != F32:
+      dr2 = ops.conv_fwd(g, w(r3c), 1, f, mask=r2, ldb=r3c["ld_dg"])
+      if stride == 2:
+        dr1 = ops.conv_fwd(self._zero_insert(dr2, f), w(r2c), 3, f, mask=r1, ldb=r2c["ld_dg"], pad=2, alg_scale=0.25)
       else:
-        dr1, dr1p = ops.conv_fwd(self._zero_insert(dr2, f), self.arena[r2c["dg_off"]:], 3, f, mask=r1,
-                                 ldb=r2c["ld_dg"], pad=2, alg_scale=0.25), None
+        dr1 = ops.conv_fwd(dr2, w(r2c), 3, f, mask=r1, ldb=r2c["ld_dg"])
+      sg = g
+      if proj:
+        pc = self.convs[pre + ("proj_conv",)]
+        g_in = self._zero_insert(g, 4 * f) if stride == 2 else g
+        sg = ops.conv_fwd(g_in, w(pc), 1, cin, ldb=pc["ld_dg"], alg_scale=0.25 if stride == 2 else 1.0)
+      dx = ops.conv_fwd(dr1, w(r1c), 1, cin, residual=sg, ldb=r1c["ld_dg"], mask=x if mask_input else None,
+                        mask_last=True)
+      return (dx, None) if want_pair else dx
+    if g_pair is None:
+      g_pair = ops._split_nhwc(g, pair=True)
+    pair_only = dict(want_pair=True, want_f32=False)
+    _, dr2p = ops.conv_fwd(None, w(r3c), 1, f, mask_pair=r2, ldb=r3c["ld_dg"], x_pair=g_pair, **pair_only)
+    if stride == 2:
+      _, dr1p = ops.conv_fwd(None, w(r2c), 3, f, mask_pair=r1, ldb=r2c["ld_dg"], pad=2, alg_scale=0.25,
+                             x_pair=self._zero_insert(dr2p, 2 * f), **pair_only)
     else:
-      dr1, dr1p = pick(ops.conv_fwd(dr2, self.arena[r2c["dg_off"]:], 3, f, mask=r1, ldb=r2c["ld_dg"], x_pair=dr2p, **kw))
+      _, dr1p = ops.conv_fwd(None, w(r2c), 3, f, mask_pair=r1, ldb=r2c["ld_dg"], x_pair=dr2p, **pair_only)
+    res_kw = dict(residual_pair=g_pair)
     if proj:
       pc = self.convs[pre + ("proj_conv",)]
-      g_in, g_in_pair = g, g_pair
-      if stride == 2:
-        if f32:
-          g_in, g_in_pair = None, self._zero_insert(g_pair, 8 * f)
-        else:
-          g_in = self._zero_insert(g, 4 * f)
-      sg = ops.conv_fwd(g_in, self.arena[pc["dg_off"]:], 1, cin, ldb=pc["ld_dg"], alg_scale=0.25 if stride == 2 else 1.0,
-                        x_pair=g_in_pair)
-    else:
-      sg = g
-    res = ops.conv_fwd(dr1, self.arena[r1c["dg_off"]:], 1, cin, residual=sg, ldb=r1c["ld_dg"],
-                       mask=x if mask_input else None, mask_last=True, x_pair=dr1p, want_pair=want_pair and f32)
-    if want_pair:
-      return res if f32 else (res, None)
-    return res
+      gp = self._zero_insert(g_pair, 8 * f) if stride == 2 else g_pair
+      _, sgp = ops.conv_fwd(None, w(pc), 1, cin, ldb=pc["ld_dg"], alg_scale=0.25 if stride == 2 else 1.0, x_pair=gp,
+                            **pair_only)
+      res_kw = dict(residual_pair=sgp)
+    dx, dxp = ops.conv_fwd(None, w(r1c), 1, cin, ldb=r1c["ld_dg"], mask_pair=x if mask_input else None, mask_last=True,
+                           x_pair=dr1p, want_pair=True, want_f32=want_f32, **res_kw)
+    return (dx, dxp) if want_pair else dx
 
   def forward(self, images_f32):
     """images_f32: fp32 [N,S,S,3] in [0,1]. Returns (logits fp32 [N,num_classes], ctx)."""
@@ -1314,8 +1326,9 @@ class ResNetEngine:
     stem, x = self.stem_forward(images_f32)
     ctx = {"N": N, "S": S, "stem": stem, "pool0": x, "blocks": []}
     xp = None
-    for spec in self.blocks:
-      x, sv, xp = self.block_forward(x, spec, x_pair=xp, want_pair=True)
+    for i, spec in enumerate(self.blocks):
+      # fp32 mode: only the last block's output is materialised in fp32 (for the pooling head)
+      x, sv, xp = self.block_forward(x, spec, x_pair=xp, want_pair=True, want_f32=i == len(self.blocks) - 1)
       ctx["blocks"].append(sv)
     ctx["x_last"] = x
     feat = ops.relu_sumhw(x)  # the block output is already >= 0: this is the plain spatial sum
@@ -1346,5 +1359,5 @@ class ResNetEngine:
       sv = ctx["blocks"][i]
       # the first block's input (max-pool output) is not a relu output (no ReLU after init_bn, resnet_v1.py:146-154)
       dout, dpair = self.block_backward(dout, sv["x"][sl], sv["r1"][sl], sv["r2"][sl], self.blocks[i],
-                                        mask_input=i > 0, g_pair=dpair, want_pair=True)
+                                        mask_input=i > 0, g_pair=dpair, want_pair=True, want_f32=i == 0)
     self.stem_backward(dout, ctx["stem"][sl], ctx["pool0"][sl], ctx["S"], d_images)

@@ -90,7 +90,7 @@ def _split_nhwc(x, c=None, pair=False):
 def conv_fwd(x, wk, kh, cout, *, bias=None, residual=None, res_shift=0, mask=None, relu=False, out=None,
              out_dtype=None, alpha=1.0, ldb=None, batched=False, stride_b=0, c=None, stride=1, pad=None,
              mask_last=False, view=None, subpixel=False, pre_split=False, alg_scale=1.0, x_pair=None,
-             want_pair=False):
+             want_pair=False, want_f32=True, residual_pair=None, mask_pair=None):
   """x: [N,H,W,>=C] bf16 view (channel-contiguous); wk: bf16 tensor whose data pointer is the [cout][kh*kh*C] K-major
   matrix (row pitch ldb). Returns y [N,H/stride,W/stride,cout] (or writes into the `out` view).
   stride=2 reads the input at (h*2+kh-pad, w*2+kw-pad) (XLA SAME: pad low = 0 for a 3x3 or 1x1 kernel on an even
@@ -98,7 +98,9 @@ def conv_fwd(x, wk, kh, cout, *, bias=None, residual=None, res_shift=0, mask=Non
   0.25 for a stride-1 convolution over a zero-inserted gradient (the transpose of a stride-2 convolution).
   fp32-activation mode, chains of convolutions: want_pair=True also returns the result as the bf16 two-part operand
   [.., hi | lo] (written by the epilogue), x_pair= passes such an operand in place of splitting x here; x may then be
-  None (shape taken from x_pair). `view`: dict overriding the input view (Hout, Wout, KH, KW, pitches, strides) for the ResNet stem."""
+  None (shape taken from x_pair). residual_pair / mask_pair: residual / mask given as such two-part tensors (value =
+  hi + lo, mask = [hi > 0]); want_f32=False (with want_pair) skips the fp32 output, so a chain of convolutions never
+  materialises fp32 activations. `view`: dict overriding the input view (Hout, Wout, KH, KW, pitches, strides) for the ResNet stem."""
   pairC = 0
   if x_pair is not None:   # fp32 mode, operand already in the two-part form (a previous launch's want_pair output)
     pairC = x_pair.shape[-1] // 2
@@ -146,12 +148,22 @@ def conv_fwd(x, wk, kh, cout, *, bias=None, residual=None, res_shift=0, mask=Non
   d.ldB = ldb if ldb is not None else d.KH * d.KW * C
   d.batched = 1 if batched else 0
   d.strideB_batch = stride_b
-  if out is None:
-    out = empty((N, H, W, cout), out_dtype)
+  if not want_f32:
+    assert want_pair and f32 and out is None
+    d.out_dtype, d.ldOut = 1, cout
   else:
-    _check_dense_rows(out)
-  d.out_dtype = 0 if out.dtype == BF16 else 1
-  d.ldOut = _pix_ld(out)
+    if out is None:
+      out = empty((N, H, W, cout), out_dtype)
+    else:
+      _check_dense_rows(out)
+    d.out_dtype = 0 if out.dtype == BF16 else 1
+    d.ldOut = _pix_ld(out)
+  if residual_pair is not None:
+    assert residual is None and f32
+    residual, d.res_pair = residual_pair, 1
+  if mask_pair is not None:
+    assert mask is None and f32
+    mask, d.mask_pair = mask_pair, 1
   d.alpha = alpha
   d.relu = 1 if relu else 0
   d.res_shift = res_shift
@@ -160,7 +172,7 @@ def conv_fwd(x, wk, kh, cout, *, bias=None, residual=None, res_shift=0, mask=Non
   out_pair = None
   if want_pair:
     assert f32 and cout % 16 == 0
-    out_pair = empty(tuple(out.shape[:-1]) + (2 * cout,), BF16)
+    out_pair = empty((N, H, W, 2 * cout), BF16)
     d.ldPair = 2 * cout
   _call("xmc_conv2d_fwd", ctypes.byref(d), ptr(x), ptr(wk), ptr(bias), ptr(residual), ptr(mask), ptr(out),
         ptr(out_pair), stream())
