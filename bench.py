@@ -144,7 +144,8 @@ class GemmTimer:
       taps = 16 if kw.get("subpixel") else kh * kh
       if kw.get("view_a") is not None:  # packed-window 3-channel image wgrad: 9 taps x 3 real channels
         taps, ca = 9, 3
-      g = xb if kw.get("view_a") is not None else xa  # pixel grid of the reduction
+      # pixel grid of the reduction (pool-fused mode: the low-resolution gradient's)
+      g = xb if (kw.get("view_a") is not None or kw.get("subpixel") == 2) else xa
       flops = 2.0 * g.shape[0] * g.shape[1] * g.shape[2] * taps * ca * cb
       s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
       s.record()

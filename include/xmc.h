@@ -109,7 +109,10 @@ typedef struct {
   float alpha;
   /* 1: weight gradient of conv3x3(nearest_upsample2x(xa)): xa is the low-resolution [N,H,W,Ca] input, xb the
    * [N,2H,2W,Cb] output gradient (read with stride 2, one parity per tap); the 16 parity/tap products are added to
-   * the 9 taps of dw ([3][3][Ca][Cb]) they belong to. KH=KW=3, out_mode 0. */
+   * the 9 taps of dw ([3][3][Ca][Cb]) they belong to. KH=KW=3, out_mode 0.
+   * 2: weight gradient of dsample(conv3x3(xa)) (pool-fused form, xmc_poolconv_prep): xa is the full-resolution
+   * [N,2H,2W,Ca] input (read with stride 2, one 4x4 tap per work item), xb the LOW-resolution [N,H,W,Cb] output
+   * gradient; the 16 tap products are folded into the 9 taps of dw (pass alpha = 0.25 for the mean). */
   int subpixel;
   /* Optional re-pitched view of xa (all 0 = dense [N,H,W,ldA]): xa is read through a tensor map of extents
    * (Ca, W, HinA, N) with element pitches (pitchWA, pitchHA, pitchNA); tap (kh, kw) reads position
@@ -260,6 +263,14 @@ int xmc_prep_weights(const XmcPrepEntry* table_dev, int n, int total_tiles, cons
  * fp32 HWIO kernel w [3][3][Cin][Cout]: wf bf16 [4*Cout][4*Cin] for XmcConvDesc.subpixel, vd bf16 [Cin][16*Cout] for
  * the input gradient (= xmc_conv2d_fwd with KH=KW=4, stride 2, pad 1 over the [N,2H,2W,Cout] output gradient).
  * scale: optional device scalar 1/(sigma+eps) of a spectrally normalised kernel (layers.py:221), NULL = 1. */
+/* Weights of the pool-fused form of dsample(conv3x3(x)) (xmcgan/nets/common.py:66-78,125-132) from the fp32 HWIO
+ * kernel w [3][3][Cin][Cout]: wf4 bf16 [Cout][16*Cin] for xmc_conv2d_fwd with KH=KW=4, stride 2, pad 1 on the
+ * full-resolution input (the 2x2 mean and its 1/4 are folded into the 16 summed taps: 2.25x fewer FLOPs than
+ * conv-then-pool, no full-resolution output), wdg bf16 [4*Cin][4*Cout] for its input gradient = xmc_conv2d_fwd in
+ * sub-pixel mode on the low-resolution output gradient. scale / split as xmc_subpixel_prep. The weight gradient is
+ * XmcWgradDesc.subpixel = 2. */
+int xmc_poolconv_prep(const float* w, const float* scale, int Cin, int Cout, int split, void* wf4, void* wdg,
+                      void* stream);
 int xmc_subpixel_prep(const float* w, const float* scale, int Cin, int Cout, int split, void* wf, void* vd,
                       void* stream);
 /* flax.optim.Adam.apply_gradient (weight_decay 0) in place on flat buffers, gradient pre-scaled by grad_scale

@@ -129,3 +129,46 @@ def test_deferred_train_d_equals_plain_train_d():
                (s1.d_optimizer.v, s2.d_optimizer.v), (s1.ema_params.buf, s2.ema_params.buf),
                (s1.discriminator_state["spectral_norm_stats"].buf, s2.discriminator_state["spectral_norm_stats"].buf)):
     assert torch.equal(a, b)
+
+
+@gpu
+@pytest.mark.parametrize("dtype", ["bfloat16", "float32"])
+@pytest.mark.parametrize("N,H,C,Cout", [(2, 16, 64, 64), (3, 8, 96, 96), (1, 64, 32, 32), (2, 4, 192, 192)])
+def test_pool_fused_conv_equals_conv_then_dsample(N, H, C, Cout, dtype):
+  """dsample(conv3x3(x) + b) (the tail of DiscBlock / DiscOptimizedBlock, common.py:66-78,125-132) computed as ONE
+  4x4 / stride-2 convolution with summed weights (xmc_poolconv_prep), its input gradient in sub-pixel form from the
+  half-resolution output gradient (with the relu mask of x), and its weight gradient (XmcWgradDesc.subpixel = 2),
+  against the oracle's conv2d -> dsample and autograd. bf16: forward 5e-3 (summed weights rounded once), gradients
+  1e-2; fp32 mode (3 x bf16 split): 2e-5 / 1e-4."""
+  from xmcgan_image_generation_b200 import _lib, ops
+  fp32 = dtype == "float32"
+  adt = torch.float32 if fp32 else torch.bfloat16
+  q = (lambda t: t) if fp32 else (lambda t: t.to(torch.bfloat16).float())
+  S = 3 if fp32 else 1
+  torch.manual_seed(H * 7 + C)
+  x = q(torch.relu(torch.randn(N, H, H, C))).requires_grad_(True)      # a relu output, as in the blocks
+  kern = (torch.randn(3, 3, C, Cout) * 0.05).requires_grad_(True)
+  bias = torch.randn(Cout)
+  res = q(torch.randn(N, H // 2, H // 2, Cout) * 0.3)
+  want = orc.dsample(orc.conv2d(x, kern, bias, orc.FP32, round_out=False)) + res
+  dy = q(torch.randn(N, H // 2, H // 2, Cout) * 0.1)
+  (want * dy).sum().backward()
+  wf4 = ops.empty((Cout, 16 * C * S), torch.bfloat16)
+  wdg = ops.empty((4 * C, 4 * Cout * S), torch.bfloat16)
+  kd = kern.detach().cuda().contiguous()
+  ops._call("xmc_poolconv_prep", kd.data_ptr(), None, C, Cout, int(fp32), wf4.data_ptr(), wdg.data_ptr(), _lib.stream())
+  xd = x.detach().cuda().to(adt)
+  with ops.act_dtype(adt):
+    got = ops.conv_fwd(xd, wf4, 4, Cout, bias=bias.cuda(), residual=res.cuda().to(adt), ldb=16 * C * S, stride=2, pad=1,
+                       out_dtype=torch.float32)
+    assert got.shape == (N, H // 2, H // 2, Cout)
+    e_fwd = helpers.rel(got, want)
+    dyd = dy.cuda().to(adt)
+    dx = ops.conv_fwd(dyd, wdg, 2, C, ldb=4 * Cout * S, pad=1, subpixel=True, mask=xd, out_dtype=torch.float32)
+    e_dx = helpers.rel(dx, x.grad * (x.detach() > 0))
+    dw = torch.zeros(9 * C * Cout, device="cuda")
+    ops.wgrad(xd, dyd, 3, dw, out_mode=0, ld_out=Cout, tap_stride=C * Cout, alpha=0.25, subpixel=2)
+    e_dw = helpers.rel(dw.view(3, 3, C, Cout), kern.grad)
+  print(f"\\n[pool-fused {dtype} N{N} H{H} C{C}] fwd {e_fwd:.2e} dx {e_dx:.2e} dw {e_dw:.2e}")
+  t_fwd, t_bwd = (2e-5, 1e-4) if fp32 else (5e-3, 1e-2)
+  assert e_fwd < t_fwd and e_dx < t_bwd and e_dw < t_bwd

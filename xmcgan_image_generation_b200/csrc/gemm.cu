@@ -75,6 +75,7 @@ struct WgradParams {
   int batched;
   int items_per_split, total_items;
   int subpixel;         // 1: 16 parity taps (a,dh,b,dw); B is the 2x up-sampled gradient read with stride 2
+                        // 2: pool-fused: 16 taps (r,s) of the 4x4/stride-2 form; A is the 2x larger input read with stride 2
   int tap3;             // 1: items are filter rows; the three kw taps share one 66-pixel halo chunk of A (3 accumulators)
   uint32_t slab_bytes;  // bytes one TMA box writes
   uint32_t idesc;
@@ -783,8 +784,12 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         int split, bz, tap, mt, nt;
         decode(item, split, bz, tap, mt, nt);
         // A shift (ah, aw) and B start (bh + bs*h0, bw + bs*w0) of this tap
-        int ah, aw, bh = 0, bw = 0, bs = 1;
-        if (p.subpixel) {
+        int ah, aw, bh = 0, bw = 0, bs = 1, as = 1;
+        if (p.subpixel == 2) {
+          // pool-fused conv3x3 -> 2x2 mean: tap = r*4 + s of the equivalent 4x4 / stride-2 / pad-1 convolution:
+          // x[2i + r - 1, 2j + s - 1] * dy_low[i, j]
+          ah = (tap >> 2) - 1; aw = (tap & 3) - 1; as = 2;
+        } else if (p.subpixel) {
           // tap = a<<3 | dh<<2 | b<<1 | dw : x[i+dh-(1-a), j+dw-(1-b)] * dy[2i+a, 2j+b]
           const int a = (tap >> 3) & 1, dh = (tap >> 2) & 1, b = (tap >> 1) & 1, dw = tap & 1;
           ah = dh - (1 - a); aw = dw - (1 - b); bh = a; bw = b; bs = 2;
@@ -806,8 +811,8 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_wait(empty_bar(stage), phase ^ 1);
           mbar_arrive_expect_tx(full_bar(stage), p.tap3 ? tx3 : tx);
           const uint32_t sa = sbase + stage * kStageBytes;
-          tma_load_4d(sa, &tmA, full_bar(stage), m0, w0 + aw, h0 + ah, n0);
-          tma_load_4d(sa + a_slab, &tmA, full_bar(stage), m0 + 64, w0 + aw, h0 + ah, n0);
+          tma_load_4d(sa, &tmA, full_bar(stage), m0, as * w0 + aw, as * h0 + ah, n0);
+          tma_load_4d(sa + a_slab, &tmA, full_bar(stage), m0 + 64, as * w0 + aw, as * h0 + ah, n0);
           for (int s = 0; s < p.nslabs; ++s)
             tma_load_4d(sa + 2 * a_slab + s * 8192, &tmB, full_bar(stage), n_off + s * 64, bs * w0 + bw, bs * h0 + bh,
                         n0);
@@ -1009,7 +1014,13 @@ __global__ void wgrad_reduce_kernel(const WgradReduceParams p) {
     const int bz = (int)(rem / p.dst_taps);
     int src[4], nsrc = 1;
     src[0] = t;
-    if (p.subpixel) {
+    if (p.subpixel == 2) {
+      // pool-fused form: destination (kh, kw) = sum of the 4x4 taps (r, s) with r in {kh, kh+1}, s in {kw, kw+1}
+      const int kh = t / 3, kw = t - kh * 3;
+      nsrc = 0;
+      for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j) src[nsrc++] = (kh + i) * 4 + kw + j;
+    } else if (p.subpixel) {
       // destination (kh, kw) collects the parity taps (a,dh) with kh in S(a,dh): S(0,0)={0}, S(0,1)={1,2},
       // S(1,0)={0,1}, S(1,1)={2} (see gemm_wgrad_kernel); source tap index = a<<3 | dh<<2 | b<<1 | dw
       const int kh = t / 3, kw = t - kh * 3;
@@ -1171,7 +1182,7 @@ extern "C" int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* w
   p.strideH = d->strideH > 0 ? d->strideH : 1;
   p.strideW = d->strideW > 0 ? d->strideW : 1;
   p.parities = d->subpixel ? 4 : 1;
-  if (d->subpixel && (d->KH != 2 || d->KW != 2 || d->pad_h != 1 || d->pad_w != 1 || residual || mask || d->batched))
+  if (d->subpixel && (d->KH != 2 || d->KW != 2 || d->pad_h != 1 || d->pad_w != 1 || residual || d->batched))
     return XMC_EINVAL;
   if (p.strideH > 8 || p.strideW > 8) return XMC_EINVAL;
   p.tw = d->W < 128 ? d->W : 128;
@@ -1327,7 +1338,7 @@ static int plan_wgrad(const XmcWgradDesc* d, WgradParams& p) {
   p.n_tiles = ceil_div(d->Cb, p.BN);
   p.nslabs = ceil_div(p.BN, 64);
   const int m_tiles = ceil_div(d->Ca, 128);
-  if (d->subpixel && (d->KH != 3 || d->KW != 3 || d->out_mode != 0 || d->batched)) return XMC_EINVAL;
+  if (d->subpixel && (d->KH != 3 || d->KW != 3 || d->out_mode != 0 || d->batched || d->subpixel > 2)) return XMC_EINVAL;
   // tap3: for 3x3 kernels on rows of >= 64 pixels whose three kw accumulators fit TMEM (Cb <= 160), a work item is a
   // filter ROW: one 66-pixel halo chunk of xa and one chunk of xb feed three taps (3x less operand traffic; these
   // narrow-channel layers are L2 -> SM bandwidth bound). XMC_WGRAD_TAP3=0 switches it off (debugging aid, read once per
@@ -1337,7 +1348,7 @@ static int plan_wgrad(const XmcWgradDesc* d, WgradParams& p) {
             d->pitchWA <= 0 && d->out_mode == 0 && d->W >= 64 && p.n_tiles == 1 && 3 * (((p.BN + 31) / 32) * 32) <= 512)
                ? 1 : 0;
   const int taps = d->subpixel ? 16 : (p.tap3 ? 3 : d->KH * d->KW);
-  p.subpixel = d->subpixel ? 1 : 0;
+  p.subpixel = d->subpixel;
   const int nbatch = d->batched ? d->N : 1;
   const int base_ctas = m_tiles * p.n_tiles * taps * nbatch;
   int ksplit = 1;
@@ -1429,15 +1440,20 @@ extern "C" int xmc_conv2d_wgrad(const XmcWgradDesc* d, const void* xa, const voi
     int r = make_tmap(&tmA, xa, 4, dims, str, box);
     if (r) return r;
   } else {
-    uint64_t dims[4] = {(uint64_t)d->Ca, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
-    uint64_t str[3] = {(uint64_t)d->ldA * 2, (uint64_t)d->ldA * 2 * d->W, (uint64_t)d->ldA * 2 * d->W * d->H};
-    uint32_t box[4] = {64, (uint32_t)(p.tap3 ? p.tw + 2 : p.tw), (uint32_t)p.th, (uint32_t)p.tn};
-    int r = make_tmap(&tmA, xa, 4, dims, str, box);
+    // pool-fused mode (subpixel == 2): xa is the [N,2H,2W,Ca] input, traversed with stride 2 (one 4x4 tap per item)
+    const int as = d->subpixel == 2 ? 2 : 1;
+    if (p.tw * as > 256 || p.th * as > 256) return XMC_EINVAL;
+    uint64_t dims[4] = {(uint64_t)d->Ca, (uint64_t)d->W * as, (uint64_t)d->H * as, (uint64_t)d->N};
+    uint64_t str[3] = {(uint64_t)d->ldA * 2, (uint64_t)d->ldA * 2 * d->W * as,
+                       (uint64_t)d->ldA * 2 * d->W * as * d->H * as};
+    uint32_t box[4] = {64, (uint32_t)((p.tap3 ? p.tw + 2 : p.tw) * as), (uint32_t)(p.th * as), (uint32_t)p.tn};
+    uint32_t est[4] = {1, (uint32_t)as, (uint32_t)as, 1};
+    int r = make_tmap(&tmA, xa, 4, dims, str, box, est);
     if (r) return r;
   }
   {
-    // sub-pixel mode: xb is the [N,2H,2W,Cb] gradient, traversed with stride 2 (one parity per tap)
-    const int bs = d->subpixel ? 2 : 1;
+    // sub-pixel mode (subpixel == 1): xb is the [N,2H,2W,Cb] gradient, traversed with stride 2 (one parity per tap)
+    const int bs = d->subpixel == 1 ? 2 : 1;
     if (p.tw * bs > 256 || p.th * bs > 256) return XMC_EINVAL;
     uint64_t dims[4] = {(uint64_t)d->Cb, (uint64_t)d->W * bs, (uint64_t)d->H * bs, (uint64_t)d->N};
     uint64_t str[3] = {(uint64_t)d->ldB * 2, (uint64_t)d->ldB * 2 * d->W * bs,

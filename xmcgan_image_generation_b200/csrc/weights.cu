@@ -289,6 +289,64 @@ subpixel_prep_kernel(const float* __restrict__ w, const float* __restrict__ scal
   }
 }
 
+// ------------------------------------------------------------------------------------------------- pool-fused prep
+// dsample(conv3x3(x)) (the tail of DiscBlock / DiscOptimizedBlock, common.py:66-78,125-132: a 3x3 convolution whose
+// output is 2x2-mean-pooled) == ONE 4x4 / stride-2 / pad-1 convolution with the summed weights
+//   W4[r][s] = 0.25 * sum_{kh in K(r)} sum_{kw in K(s)} W[kh][kw],   K(0)={0}, K(1)={0,1}, K(2)={1,2}, K(3)={2}
+// (output pixel q averages the conv outputs at 2q+a, a in {0,1}, which read input 2q+a+kh-1 = 2q+r-1 with r = a+kh):
+// 16 taps per low-resolution output instead of 4 x 9 = 2.25x fewer FLOPs, and the full-resolution conv output is
+// never written — the mirror image of the generator's sub-pixel convolution. Writes
+//   wf4 [Cout][(r*4+s)*Cin + ci]            forward: xmc_conv2d_fwd KH=KW=4, stride 2, pad 1 on the full-res input
+//   wdg [(a*2+b)*Cin + ci][(dh*2+dw)*Cout + co] input gradient: xmc_conv2d_fwd in sub-pixel mode on the LOW-res output
+//       gradient (parity (a,b) of the full-res input pixel, window row dh <-> r = {3,1} for a = 0, {2,0} for a = 1)
+// split = 1: every K group stored as [hi | hi | lo] (fp32-activation mode). One block = 32 (ci) x 32 (co); the four
+// taps of one row r are staged in shared memory so that both matrices are written in contiguous runs.
+__global__ void __launch_bounds__(256)
+poolconv_prep_kernel(const float* __restrict__ w, const float* __restrict__ scale, int Cin, int Cout, int split,
+                     bf16* __restrict__ wf4, bf16* __restrict__ wdg) {
+  __shared__ float tile[4][32][33];  // [s][ci][co] of one tap row r
+  const int S = split ? 3 : 1;
+  const int ci0 = blockIdx.y * 32, co0 = blockIdx.x * 32;
+  const float sc = 0.25f * (scale ? *scale : 1.f);
+  auto put = [&](bf16* o, long long part_stride, float v) {
+    const bf16 hi = __float2bfloat16(v);
+    o[0] = hi;
+    if (split) {
+      o[part_stride] = hi;
+      o[2 * part_stride] = __float2bfloat16(v - __bfloat162float(hi));
+    }
+  };
+  for (int r = 0; r < 4; ++r) {
+    const int kh0 = r == 0 ? 0 : r - 1, kh1 = r == 3 ? 2 : r;   // K(r) = [kh0, kh1] clipped to 0..2
+    const int a = (r == 3 || r == 1) ? 0 : 1, dh = (r == 3 || r == 2) ? 0 : 1;  // r = 3,1 -> a = 0; r = 2,0 -> a = 1
+    for (int rr = threadIdx.y; rr < 32; rr += 8) {
+      const int ci = ci0 + rr, co = co0 + threadIdx.x;
+      if (ci >= Cin || co >= Cout) continue;
+      float col[3] = {0.f, 0.f, 0.f};  // sum over kh in K(r) for each kw
+      for (int kh = kh0; kh <= min(kh1, 2); ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) col[kw] += w[((long long)(kh * 3 + kw) * Cin + ci) * Cout + co];
+      const float v4[4] = {col[0] * sc, (col[0] + col[1]) * sc, (col[1] + col[2]) * sc, col[2] * sc};
+#pragma unroll
+      for (int s2 = 0; s2 < 4; ++s2) {
+        tile[s2][rr][threadIdx.x] = v4[s2];
+        const int b = (s2 == 3 || s2 == 1) ? 0 : 1, dw = (s2 == 3 || s2 == 2) ? 0 : 1;
+        put(wdg + ((long long)((a * 2 + b) * Cin + ci)) * (4 * S * Cout) + (long long)(dh * 2 + dw) * S * Cout + co, Cout,
+            v4[s2]);
+      }
+    }
+    __syncthreads();
+    for (int rr = threadIdx.y; rr < 32; rr += 8) {
+      const int co = co0 + rr, ci = ci0 + threadIdx.x;
+      if (ci >= Cin || co >= Cout) continue;
+#pragma unroll
+      for (int s2 = 0; s2 < 4; ++s2)
+        put(wf4 + (long long)co * (16 * S * Cin) + (long long)(r * 4 + s2) * S * Cin + ci, Cin, tile[s2][threadIdx.x][rr]);
+    }
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------------------------- Adam (+EMA)
 // Scalars of one Adam step, formed in double on the host (or from the device step count) and rounded to fp32 once:
 // flax.optim.Adam multiplies fp32 arrays by the Python doubles (1 - beta), 1 / (1 - beta^t).
@@ -385,6 +443,15 @@ extern "C" int xmc_subpixel_prep(const float* w, const float* scale, int Cin, in
   if (!w || !wf || !vd || Cin < 8 || Cout < 8 || (Cin % 8) || (Cout % 8)) return XMC_EINVAL;
   subpixel_prep_kernel<<<dim3(ceil_div(Cout, 32), ceil_div(Cin, 32)), dim3(32, 8), 0, (cudaStream_t)stream>>>(
       w, scale, Cin, Cout, split, (bf16*)wf, (bf16*)vd);
+  XMC_LAUNCH_CHECK();
+  return XMC_OK;
+}
+
+extern "C" int xmc_poolconv_prep(const float* w, const float* scale, int Cin, int Cout, int split, void* wf4, void* wdg,
+                                 void* stream) {
+  if (!w || !wf4 || !wdg || Cin < 8 || Cout < 8 || (Cin % 8) || (Cout % 8)) return XMC_EINVAL;
+  poolconv_prep_kernel<<<dim3(ceil_div(Cout, 32), ceil_div(Cin, 32)), dim3(32, 8), 0, (cudaStream_t)stream>>>(
+      w, scale, Cin, Cout, split, (bf16*)wf4, (bf16*)wdg);
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }

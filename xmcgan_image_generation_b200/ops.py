@@ -203,8 +203,9 @@ def wgrad(xa, xb, kh, out, *, out_mode=0, batched=False, ld_out=None, tap_stride
 def _wgrad_bf16(xa, xb, kh, out, *, out_mode=0, batched=False, ld_out=None, tap_stride=None, batch_stride=0, alpha=1.0,
                 ca=None, cb=None, subpixel=False, view_a=None):
   """One launch of the bf16 tensor-core weight-gradient kernel (+ its deterministic second stage)."""
-  # pixel grid of the reduction: xa's (the low-resolution input in sub-pixel mode), xb's for a re-pitched xa view
-  N, H, W = (xa if view_a is None else xb).shape[:3]
+  # pixel grid of the reduction: xa's (the low-resolution input in sub-pixel mode), xb's for a re-pitched xa view and
+  # in pool-fused mode (subpixel == 2: xa is the 2x larger input, xb the low-resolution gradient)
+  N, H, W = (xa if (view_a is None and subpixel != 2) else xb).shape[:3]
   _check_dense_rows(xa)
   _check_dense_rows(xb)
   d = WgradDesc()
@@ -223,7 +224,7 @@ def _wgrad_bf16(xa, xb, kh, out, *, out_mode=0, batched=False, ld_out=None, tap_
   d.out_tap_stride = d.Ca * d.Cb if tap_stride is None else tap_stride
   d.out_batch_stride = batch_stride
   d.alpha = alpha
-  d.subpixel = 1 if subpixel else 0
+  d.subpixel = int(subpixel)
   # deterministic accumulation: partial tiles of a split reduction go through a caller-owned workspace and are added in
   # a fixed order by a second kernel (counted as a launch); the caching allocator hands the same block back each step
   need = ctypes.c_longlong(0)
@@ -366,6 +367,13 @@ def pool2(a, b=None, low=None, scale=0.25, want_relu=False):
   _call("xmc_pool2", ptr(a), ptr(b), ptr(low), _f32(a), N, H2 // 2, W2 // 2, C, scale, ptr(out), ptr(out_relu),
         stream())
   return (out, out_relu) if want_relu else out
+
+
+def relu(x):
+  """y = max(x, 0) as a stand-alone pass (where no producing kernel can fold it in)."""
+  y = torch.empty_like(x)
+  _call("xmc_relu_or_add", ptr(x), None, _f32(x), x.numel(), ptr(y), stream())
+  return y
 
 
 def unpool2(dout, scale=0.25):
