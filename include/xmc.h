@@ -392,9 +392,10 @@ int xmc_resize_bilinear_pad(const float* img, int N, int S, int T, int Tp, int p
                             void* stream);
 /* transpose of the resize: dimg[N,S,S,3] += R^T dout[N,T,T,3] */
 int xmc_resize_bilinear_bwd(const float* dout, int N, int S, int T, float* dimg, void* stream);
-/* input gradient of the 7x7/2 stem (resnet_v1.py:146-151): dy bf16 [N,Ho,Ho,Cout], wk bf16 [Cout][7*56] */
-int xmc_stem_dgrad(const void* dy, int act_f32, const void* wk, const void* wk_lo, int N, int T, int Ho, int Cout,
-                   int pad_lo, float* dimg, void* stream);
+/* Input gradient of the 7x7 / stride-2 stem, col2im half: cols fp32 [N,Ho,Ho,ldc] holds, per stem output pixel, the
+ * 147 products (kh, kw, c) of dy with the transposed stem matrix (made by xmc_conv2d_fwd as a 1x1 convolution over dy);
+ * dimg [N,T,T,3] = the gather over the taps that hit each input pixel (overwritten). */
+int xmc_stem_col2im(const float* cols, int N, int T, int Ho, int ldc, int pad_lo, float* dimg, void* stream);
 /* nn.max_pool 3x3/2 SAME (resnet_v1.py:154) on bf16 [N,H,H,C] and its transpose (first-max tie rule) */
 int xmc_maxpool3s2(const void* x, int act_f32, int N, int H, int C, void* y, void* stream);
 int xmc_maxpool3s2_bwd(const void* dy, const void* x, const void* y, int act_f32, int N, int H, int C, void* dx,

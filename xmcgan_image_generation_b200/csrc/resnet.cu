@@ -132,72 +132,33 @@ __global__ void resize_bilinear_bwd_kernel(const float* __restrict__ dout, int N
   }
 }
 
-// Input gradient of the 7x7 stride-2 stem (SAME padding low=2). One thread computes 4 input pixels of the same column
-// parity in one row (x, x+2, x+4, x+6): they use the same filter taps, so every weight vector read from shared memory
-// feeds 4 pixels. wk: bf16 [Cout][7*56] with k = kh*56 + kw*8 + c (the packed forward weights), dy: [N,Ho,Ho,Cout].
-template <typename TA>
-__global__ void __launch_bounds__(128)
-stem_dgrad_kernel(const TA* __restrict__ dy, const bf16* __restrict__ wk, const bf16* __restrict__ wk_lo, int N, int T,
-                  int Ho, int Cout, int pad_lo, float* __restrict__ dimg) {
-  extern __shared__ float ws[];  // [7][7][3][Cout]
-  for (int t = threadIdx.x; t < 49 * 3 * Cout; t += blockDim.x) {
-    const int co = t % Cout, c = (t / Cout) % 3, kw = (t / (Cout * 3)) % 7, kh = t / (Cout * 21);
-    const long long wi = (long long)co * 392 + kh * 56 + kw * 8 + c;
-    ws[t] = __bfloat162float(wk[wi]) + (wk_lo ? __bfloat162float(wk_lo[wi]) : 0.f);  // fp32 mode: hi + lo
-  }
-  __syncthreads();
-  const int groups_x = (T + 7) / 8;             // 8 consecutive pixels = 2 parities x 4 pixels
-  const long long total = (long long)N * T * groups_x * 2;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int par = idx & 1;
-  const int gx = (idx >> 1) % groups_x;
-  const int y = (idx / (2 * groups_x)) % T;
-  const long long n = idx / ((long long)2 * groups_x * T);
-  const int x0 = gx * 8 + par;                  // pixels x0, x0+2, x0+4, x0+6
-  const int yp = y + pad_lo;
-  const int xp0 = x0 + pad_lo;
-  float acc[4][3];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = 0.f;
-  for (int ho = max(0, (yp - 5) >> 1); ho <= min(Ho - 1, yp >> 1); ++ho) {
-    const int kh = yp - 2 * ho;
-    if (kh < 0 || kh > 6) continue;
-    // taps for this column parity: kw = (xp0 & 1) + 2j, output column of pixel i: wo = (xp0 >> 1) + i - j
-    for (int j = 0; j < 4; ++j) {
-      const int kw = (xp0 & 1) + 2 * j;
-      if (kw > 6) continue;
-      const float* w = ws + ((kh * 7 + kw) * 3) * Cout;
-      const TA* grow = dy + (n * Ho + ho) * (long long)Ho * Cout;
-      for (int co = 0; co < Cout; co += 8) {
-        const float4 wa0 = *reinterpret_cast<const float4*>(w + co), wb0 = *reinterpret_cast<const float4*>(w + co + 4);
-        const float4 wa1 = *reinterpret_cast<const float4*>(w + Cout + co);
-        const float4 wb1 = *reinterpret_cast<const float4*>(w + Cout + co + 4);
-        const float4 wa2 = *reinterpret_cast<const float4*>(w + 2 * Cout + co);
-        const float4 wb2 = *reinterpret_cast<const float4*>(w + 2 * Cout + co + 4);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int wo = (xp0 >> 1) + i - j;
-          if (wo < 0 || wo >= Ho) continue;
-          float f[8];
-          load8(grow + (long long)wo * Cout + co, f);
-          acc[i][0] += f[0] * wa0.x + f[1] * wa0.y + f[2] * wa0.z + f[3] * wa0.w + f[4] * wb0.x + f[5] * wb0.y +
-                       f[6] * wb0.z + f[7] * wb0.w;
-          acc[i][1] += f[0] * wa1.x + f[1] * wa1.y + f[2] * wa1.z + f[3] * wa1.w + f[4] * wb1.x + f[5] * wb1.y +
-                       f[6] * wb1.z + f[7] * wb1.w;
-          acc[i][2] += f[0] * wa2.x + f[1] * wa2.y + f[2] * wa2.z + f[3] * wa2.w + f[4] * wb2.x + f[5] * wb2.y +
-                       f[6] * wb2.z + f[7] * wb2.w;
-        }
+// Input gradient of the 7x7 stride-2 stem (SAME padding low = pad_lo), second half. The first half is a tensor-core
+// GEMM (xmc_conv2d_fwd as a 1x1 convolution): cols[n, ho, wo, (kh*7+kw)*3 + c] = sum_co dy[n, ho, wo, co] * W[kh][kw][c][co]
+// (147 useful columns, pitch ldc). This kernel is the col2im gather: every input pixel (y, x) adds the <= 4 x 4 taps
+// (kh, kw) whose output position ((y + pad_lo - kh) / 2, (x + pad_lo - kw) / 2) is integral and inside the map. Each
+// cols element is read exactly once; fixed summation order (deterministic). Round 1 ran the whole transposed
+// convolution on CUDA cores (1.3 ms bf16 / 1.95 ms fp32 per step); GEMM + gather: see DESIGN.md.
+__global__ void stem_col2im_kernel(const float* __restrict__ cols, int N, int T, int Ho, int ldc, int pad_lo,
+                                   float* __restrict__ dimg) {
+  const long long total = (long long)N * T * T;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int x = idx % T, y = (idx / T) % T;
+    const long long n = idx / ((long long)T * T);
+    const int yp = y + pad_lo, xp = x + pad_lo;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int kh = yp & 1; kh < 7; kh += 2) {
+      const int ho = (yp - kh) >> 1;
+      if (ho < 0 || ho >= Ho) continue;
+      for (int kw = xp & 1; kw < 7; kw += 2) {
+        const int wo = (xp - kw) >> 1;
+        if (wo < 0 || wo >= Ho) continue;
+        const float* c = cols + ((n * Ho + ho) * Ho + wo) * ldc + (kh * 7 + kw) * 3;
+        a0 += c[0]; a1 += c[1]; a2 += c[2];
       }
     }
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int x = x0 + 2 * i;
-    if (x < T) {
-      float* o = dimg + ((n * T + y) * T + x) * 3;
-      o[0] = acc[i][0]; o[1] = acc[i][1]; o[2] = acc[i][2];
-    }
+    float* o = dimg + idx * 3;
+    o[0] = a0; o[1] = a1; o[2] = a2;
   }
 }
 
@@ -329,15 +290,9 @@ extern "C" int xmc_resize_bilinear_bwd(const float* dout, int N, int S, int T, f
   return XMC_OK;
 }
 
-extern "C" int xmc_stem_dgrad(const void* dy, int act_f32, const void* wk, const void* wk_lo, int N, int T, int Ho,
-                              int Cout, int pad_lo, float* dimg, void* stream) {
-  if (!dy || !wk || !dimg || N < 1 || Cout < 8 || (Cout % 8)) return XMC_EINVAL;
-  const size_t smem = (size_t)49 * 3 * Cout * sizeof(float);
-  if (smem > 48 * 1024) return XMC_EINVAL;
-  const long long total = (long long)N * T * ((T + 7) / 8) * 2;
-  const int size = T;  // the dispatch macro names the activation type T
-  XMC_ACT(act_f32, stem_dgrad_kernel<T><<<(unsigned)ceil_div_ll(total, 128), 128, smem, (cudaStream_t)stream>>>(
-                       (const T*)dy, (const bf16*)wk, (const bf16*)wk_lo, N, size, Ho, Cout, pad_lo, dimg));
+extern "C" int xmc_stem_col2im(const float* cols, int N, int T, int Ho, int ldc, int pad_lo, float* dimg, void* stream) {
+  if (!cols || !dimg || N < 1 || T < 1 || Ho < 1 || ldc < 147) return XMC_EINVAL;
+  stem_col2im_kernel<<<grid1((long long)N * T * T, 256), 256, 0, (cudaStream_t)stream>>>(cols, N, T, Ho, ldc, pad_lo, dimg);
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }

@@ -1169,6 +1169,10 @@ class ResNetEngine:
     self.arena_size += width * 392
     self.stem_lo_off = self.arena_size       # fp32 mode: the bf16 remainders of the stem weights, same packing
     self.arena_size += width * 392
+    # transposed stem matrix for the input gradient: [160 rows = (kh*7+kw)*3+c, 147 used][K = width (x S)]
+    self.stemT_rows = 160
+    self.stemT_off = self.arena_size
+    self.arena_size += self.stemT_rows * width * S_
 
   def random_variables(self, seed=0, head_scale=0.05, residual_scale=0.3):
     """Synthetic frozen weights for benchmarking (the reference's data/resnet_pretrained.npy is not shipped,
@@ -1238,6 +1242,12 @@ class ResNetEngine:
       lo[:, :, :, :3] = (wt - hi.float()).to(BF16)
       self.arena[self.stem_lo_off:self.stem_lo_off + n_stem] = lo.reshape(-1)
     self.arena[self.stem_off:self.stem_off + n_stem] = packed.reshape(-1)
+    # input gradient of the stem as a GEMM: rows (kh, kw, c), K = output channels; fp32 mode: [hi | hi | lo] along K
+    wT = torch.zeros(self.stemT_rows, self.width, device="cuda")
+    wT[:147] = w.reshape(147, self.width)
+    hiT = wT.to(BF16)
+    parts = [hiT] if self.act != F32 else [hiT, hiT, (wT - hiT.float()).to(BF16)]
+    self.arena[self.stemT_off:self.stemT_off + self.stemT_rows * self.width * self.S] = torch.cat(parts, 1).reshape(-1)
     torch.cuda.synchronize()
 
   def _bias(self, rec):
@@ -1270,10 +1280,12 @@ class ResNetEngine:
     dstem = ops.empty((n, T // 2, T // 2, W0), self.act)
     ops._call("xmc_maxpool3s2_bwd", dpool.data_ptr(), stem.data_ptr(), pooled.data_ptr(), ops._f32(stem), n, T // 2, W0,
               dstem.data_ptr(), _lib.stream())
+    # transposed 7x7/2 convolution = tensor-core GEMM (dy x W^T, 147 columns per stem pixel) + col2im gather
+    with ops.act_dtype(self.act):
+      cols = ops.conv_fwd(dstem, self.arena[self.stemT_off:], 1, self.stemT_rows, ldb=W0 * self.S, out_dtype=F32)
     d224 = ops.empty((n, T, T, 3), F32)
-    ops._call("xmc_stem_dgrad", dstem.data_ptr(), ops._f32(dstem), self.arena[self.stem_off:].data_ptr(),
-              self.arena[self.stem_lo_off:].data_ptr() if self.act == F32 else None, n, T, T // 2, W0, self.PAD_LO,
-              d224.data_ptr(), _lib.stream())
+    ops._call("xmc_stem_col2im", cols.data_ptr(), n, T, T // 2, self.stemT_rows, self.PAD_LO, d224.data_ptr(),
+              _lib.stream())
     ops._call("xmc_resize_bilinear_bwd", d224.data_ptr(), n, S, T, d_images.data_ptr(), _lib.stream())
 
   def block_forward(self, x, spec, x_pair=None, want_pair=False, want_f32=True):
