@@ -101,7 +101,7 @@ __device__ __forceinline__ float bf16_bits_to_float(uint32_t h) { return __uint_
 
 // 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256); addresses must be 32-byte aligned
 __device__ __forceinline__ void ldg256(const void* p, uint4& a, uint4& b) {
-  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
                : "l"(p));
 }
@@ -118,7 +118,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 
 // Lean epilogue for the commonest short-K case, compiled without any of the generic machinery (no mask, alpha == 1,
 // bf16 output, 32-byte aligned pitches, Cout % 16 == 0, bias staged in shared memory): kRes adds the residual.
-template <bool kRes>
+template <bool kRes, int kParts = kEpiParts>
 __device__ __forceinline__ void fwd_epilogue_tile_lean(const FwdParams& p, uint32_t t_addr, int nt, bool row_ok,
                                                        long long pix, long long rpix, const float* bias_s, int half) {
   const int col0 = nt * p.BN;
@@ -127,7 +127,7 @@ __device__ __forceinline__ void fwd_epilogue_tile_lean(const FwdParams& p, uint3
   bf16* o_row = reinterpret_cast<bf16*>(p.out) + pix * p.ldOut + col0;
   const bf16* r_row = kRes ? reinterpret_cast<const bf16*>(p.residual) + rpix * p.ldRes + col0 : nullptr;
   const bool relu = p.relu != 0;
-  for (int c0 = half * 16; c0 < p.BN; c0 += 16 * kEpiParts) {
+  for (int c0 = half * 16; c0 < p.BN; c0 += 16 * kParts) {
     uint32_t v[16];
     tmem_ld16(t_addr + c0, v);
     uint4 r0, r1;
@@ -172,7 +172,7 @@ __device__ __forceinline__ void fwd_epilogue_tile_lean(const FwdParams& p, uint3
 // quarter this is. Shared by the streaming and the resident-weights forward kernels.
 // kF32: the fp32-activation instantiation (config.dtype = "float32" / the frozen ResNet branch): residual and mask are
 // fp32 tensors (16 columns = 64 bytes = two 32-byte accesses each), the output is fp32.
-template <bool kF32>
+template <bool kF32, int kParts = kEpiParts>
 __device__ __forceinline__ void fwd_epilogue_tile(const FwdParams& p, uint32_t t_addr, int nt, bool row_ok,
                                                   long long pix, long long rpix, const float* bias_s, int half) {
   constexpr int kV = kF32 ? 4 : 2;  // uint4 vectors per 16-column chunk of a mask / residual row
@@ -331,7 +331,7 @@ __device__ __forceinline__ void fwd_epilogue_tile(const FwdParams& p, uint32_t t
       }
     }
   };
-  constexpr int kStep = 16 * kEpiParts;
+  constexpr int kStep = 16 * kParts;
   uint32_t va[16], vb[16];
   uint4 mka[kV], mkb[kV], rsa[kV], rsb[kV];
   int c0 = half * 16;
@@ -352,9 +352,16 @@ __device__ __forceinline__ void fwd_epilogue_tile(const FwdParams& p, uint32_t t
 // =====================================================================================================================
 // Forward / dgrad / dense / batched GEMM:  D[pixels, Cout] = sum_taps A_tap[pixels, C] * B[Cout, tap*C + c]
 // =====================================================================================================================
+// Epilogue warps per TMEM lane quarter of an instantiation. The fp32 epilogue (kMode 3) keeps twice the residual / mask
+// registers in flight; at 14 warps the register file caps a thread at 128 registers and it spilled its loop state to
+// local memory (the reloads were the top stall of the ResNet branch's 1x1 layers) — 10 warps leave it 200.
+template <int kMode> struct FwdParts { static constexpr int v = kMode == 3 ? 2 : kEpiParts; };
+
 template <int kMode>  // 0: generic epilogue; 1 / 2: lean epilogue (bias [+ residual]); 3: fp32 residual / mask / output
-__global__ void __launch_bounds__(kThreadsFwd, 1)
+__global__ void __launch_bounds__(64 + 128 * FwdParts<kMode>::v, 1)
 gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FwdParams p) {
+  constexpr int kParts = FwdParts<kMode>::v;
+  constexpr int kThreadsK = 64 + 128 * kParts;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_1024(smem_raw);
   const uint32_t sbase = smem_u32(smem);
@@ -376,7 +383,7 @@ gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4 * kEpiParts);
+      mbar_init(tempty_bar(a), 4 * kParts);
     }
     fence_barrier_init();
   }
@@ -391,8 +398,8 @@ gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   float* bias_s = reinterpret_cast<float*>(smem + kStages * kStageBytes + kBarBytes);
   if (p.bias_smem && warp >= 2) {
-    for (int i = threadIdx.x - 64; i < p.Cout; i += kThreadsFwd - 64) bias_s[i] = p.bias[i];
-    asm volatile("bar.sync 1, %0;" ::"n"(kThreadsFwd - 64) : "memory");  // epilogue warps only
+    for (int i = threadIdx.x - 64; i < p.Cout; i += kThreadsK - 64) bias_s[i] = p.bias[i];
+    asm volatile("bar.sync 1, %0;" ::"n"(kThreadsK - 64) : "memory");  // epilogue warps only
   }
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   const int total_tiles = m_tiles * p.n_tiles * p.parities;
@@ -509,10 +516,10 @@ gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
-      if (kMode == 1) fwd_epilogue_tile_lean<false>(p, t_addr, nt, row_ok, pix, rpix, bias_s, half);
-      else if (kMode == 2) fwd_epilogue_tile_lean<true>(p, t_addr, nt, row_ok, pix, rpix, bias_s, half);
-      else if (kMode == 3) fwd_epilogue_tile<true>(p, t_addr, nt, row_ok, pix, rpix, bias_s, half);
-      else fwd_epilogue_tile<false>(p, t_addr, nt, row_ok, pix, rpix, bias_s, half);
+      if (kMode == 1) fwd_epilogue_tile_lean<false, kParts>(p, t_addr, nt, row_ok, pix, rpix, bias_s, half);
+      else if (kMode == 2) fwd_epilogue_tile_lean<true, kParts>(p, t_addr, nt, row_ok, pix, rpix, bias_s, half);
+      else if (kMode == 3) fwd_epilogue_tile<true, kParts>(p, t_addr, nt, row_ok, pix, rpix, bias_s, half);
+      else fwd_epilogue_tile<false, kParts>(p, t_addr, nt, row_ok, pix, rpix, bias_s, half);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -1308,7 +1315,7 @@ extern "C" int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* w
   const bool lean = lean_mode && p.bias_smem && !mask && d->alpha == 1.f && d->out_dtype == 0 && p.vec_ok == 2 &&
                     (d->Cout % 16) == 0 && (!residual || al32p(residual));
   if (f32io)
-    gemm_fwd_kernel<3><<<grid, kThreadsFwd, kSmemFwd, (cudaStream_t)stream>>>(tmA, tmB, p);
+    gemm_fwd_kernel<3><<<grid, 64 + 128 * FwdParts<3>::v, kSmemFwd, (cudaStream_t)stream>>>(tmA, tmB, p);
   else if (lean && !residual)
     gemm_fwd_kernel<1><<<grid, kThreadsFwd, kSmemFwd, (cudaStream_t)stream>>>(tmA, tmB, p);
   else if (lean)
