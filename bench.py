@@ -134,8 +134,10 @@ class GemmTimer:
         if extra is not None:
           nbytes += extra.numel() * extra.element_size()
       timer.bytes["gemm_fwd_kernel"] = timer.bytes.get("gemm_fwd_kernel", 0.0) + nbytes
+      # bf16 tensor-core passes the launch executes: 3 for fp32 operands (hi*hi + lo*hi + hi*lo), 2 for the fp32 stem
+      passes = 3 if (xp is not None or x.dtype == torch.float32) else 2 if kw.get("pre_split") else 1
       timer.records.append(("gemm_fwd_kernel", flops, s, e,
-                            (x.shape[0], x.shape[1], x.shape[2], c, kh, cout, int(kw.get("batched", False)))))
+                            (x.shape[0], x.shape[1], x.shape[2], c, kh, cout, int(kw.get("batched", False))), passes))
       return out
 
     def wgrad(xa, xb, kh, out, **kw):
@@ -152,7 +154,8 @@ class GemmTimer:
       r = timer._wgrad(xa, xb, kh, out, **kw)
       e.record()
       timer.records.append(("gemm_wgrad_kernel", flops, s, e,
-                            (g.shape[0], g.shape[1], g.shape[2], ca, kh, cb, int(kw.get("batched", False)))))
+                            (g.shape[0], g.shape[1], g.shape[2], ca, kh, cb, int(kw.get("batched", False))),
+                            3 if xa.dtype == torch.float32 else 1))
       return r
 
     ops.conv_fwd, ops.wgrad = conv_fwd, wgrad
@@ -162,16 +165,23 @@ class GemmTimer:
 
   def summary(self):
     agg = {}
-    for k, fl, s, e, _ in self.records:
-      a = agg.setdefault(k, [0, 0.0, 0.0])
+    for k, fl, s, e, _, passes in self.records:
+      a = agg.setdefault(k, [0, 0.0, 0.0, 0.0, {}])
+      ms = s.elapsed_time(e)
       a[0] += 1
       a[1] += fl
-      a[2] += s.elapsed_time(e)
-    return {k: {"launches": v[0], "tflop": v[1] / 1e12, "ms": v[2]} for k, v in agg.items()}
+      a[2] += ms
+      a[3] += fl * passes
+      b = a[4].setdefault("bf16 operands" if passes == 1 else "fp32 operands (3 bf16 passes)", [0, 0.0, 0.0])
+      b[0] += 1
+      b[1] += fl
+      b[2] += ms
+    return {k: {"launches": v[0], "tflop": v[1] / 1e12, "ms": v[2], "executed_tflop": v[3] / 1e12,
+                "by_operand": v[4]} for k, v in agg.items()}
 
   def per_shape(self):
     agg = {}
-    for k, fl, s, e, shp in self.records:
+    for k, fl, s, e, shp, _ in self.records:
       a = agg.setdefault((k,) + shp, [0, 0.0, 0.0])
       a[0] += 1
       a[1] += fl
@@ -328,6 +338,14 @@ def run_b200(args):
                                 "conv3x3_resident_kernel launches. Per-shape captures: profiles/r01_gemm_shape_classes.md, "
                                 "r01_resident_full.md",
                 "peak_source": peak_src,
+                # `achieved` counts every multiply once whatever the operand precision; the frozen ResNet branch runs
+                # fp32 operands as three bf16 tensor-core passes, so the tensor pipe executes `executed` TFLOP/s
+                "executed": {"achieved": round(gemm[dom]["executed_tflop"] / (gemm[dom]["ms"] / 1e3), 1),
+                             "frac": round(gemm[dom]["executed_tflop"] / (gemm[dom]["ms"] / 1e3) / peak_tf, 4)},
+                "by_operand": {k: {"launches_per_step": v[0] // args.steps, "ms_per_step": round(v[2] / args.steps, 2),
+                                   "achieved": round(v[1] / 1e12 / (v[2] / 1e3), 1),
+                                   "frac": round(v[1] / 1e12 / (v[2] / 1e3) / peak_tf, 4)}
+                               for k, v in gemm[dom]["by_operand"].items()},
                 "launches_timed": gemm[dom]["launches"],
                 "share_of_step": round(gemm[dom]["ms"] / ms_instr, 3),
                 "timed_in": "second pass of the same K steps with per-launch CUDA events "
