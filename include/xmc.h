@@ -34,6 +34,11 @@ int xmc_version(void);
  * 4 XmcSnEntry (-1 otherwise). A binding checks its own mirror of a struct against this before the first call. */
 int xmc_sizeof(int which);
 int xmc_num_sms(void);
+/* Caps the grid of the persistent tensor-core kernels (xmc_conv2d_fwd, xmc_conv2d_wgrad) at `sms` thread blocks so that
+ * a collective kernel (NCCL all-reduce of the gradients, reference: jax.lax.pmean in xmc_gan.py:170-171) launched on
+ * another stream finds free SMs instead of queueing behind 148 resident one-per-SM blocks. 0 = no limit. Results do not
+ * depend on the limit (work is planned on the full SM count). Host-side state, read at launch time. */
+int xmc_set_sm_limit(int sms);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution / dense / batched GEMM on tcgen05 tensor cores (bf16 operands, fp32 accumulate).
@@ -277,13 +282,14 @@ int xmc_subpixel_prep(const float* w, const float* scale, int Cin, int Cout, int
  * (1/world after a sum all-reduce == lax.pmean); optional polyak EMA of the updated parameters
  * (xmcgan/xmc_gan.py:172-177,252). bias_corr = 1 - beta^t. n must be a multiple of 4.
  * step_dev: optional device int holding the number of steps taken so far; when given, the bias corrections are
- * computed on the device from t = *step_dev + 1 (bias_corr1/2 are ignored) and *step_dev is incremented afterwards, so
- * that the launch can be replayed from a CUDA graph.
+ * computed on the device from t = *step_dev + 1 (bias_corr1/2 are ignored) and, with advance_step != 0, *step_dev is
+ * incremented afterwards, so that the launch can be replayed from a CUDA graph. A step applied in several calls over
+ * sub-ranges of the buffers (each as soon as its slice of the gradient all-reduce has arrived) advances on the last.
  * The hyper-parameters are doubles: flax forms (1 - beta) and the bias corrections in Python double precision before
  * they meet the fp32 arrays; 1.f - 0.999f is 1.3e-5 off, which is visible in the second moment. */
 int xmc_adam(float* p, const float* g, float* m, float* v, long long n, double lr, double beta1, double beta2,
              double eps, double bias_corr1, double bias_corr2, double grad_scale, float* ema, double ema_decay,
-             int* step_dev, void* stream);
+             int* step_dev, int advance_step, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Row l2-normalisation xhat = x*rsqrt(max(sum x^2, eps)) (attention_lib.l2_normalize, attention_lib.py:30-33), one

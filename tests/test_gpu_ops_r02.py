@@ -29,9 +29,14 @@ def test_adam_and_ema_single_op_matches_oracle(use_step_dev):
     g[::7] = 0.0                                 # exact zeros: update must be exactly -lr*m_hat/(sqrt(v_hat)+eps)
     gsum = (g * world).cuda()                    # what the sum all-reduce leaves in the buffer
     bogus = 0.123 if use_step_dev else None      # host bias corrections must be ignored when step_dev is given
-    ops._call("xmc_adam", p.data_ptr(), gsum.data_ptr(), m.data_ptr(), v.data_ptr(), n, lr, b1, b2, eps,
-              bogus or 1.0 - b1 ** t, bogus or 1.0 - b2 ** t, 1.0 / world, ema.data_ptr(), decay,
-              step_dev.data_ptr() if use_step_dev else None, _lib.stream())
+    # odd steps: the step applied in two calls over sub-ranges (as xmc_gan does, slice by slice of the all-reduce),
+    # the device step count advancing on the last call only
+    cuts = [0, (n // 8) * 4, n] if t % 2 else [0, n]
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+      ops._call("xmc_adam", p.data_ptr() + 4 * lo, gsum.data_ptr() + 4 * lo, m.data_ptr() + 4 * lo,
+                v.data_ptr() + 4 * lo, hi - lo, lr, b1, b2, eps, bogus or 1.0 - b1 ** t, bogus or 1.0 - b2 ** t,
+                1.0 / world, ema.data_ptr() + 4 * lo, decay, step_dev.data_ptr() if use_step_dev else None,
+                int(hi == n), _lib.stream())
     o_p, o_opt = orc.adam_apply(o_p, o_opt, {"w": g}, lr, b1, b2)
     o_ema = o_ema * decay + (1 - decay) * o_p["w"]
     # the update itself, not only the parameters (whose relative change per step is tiny)

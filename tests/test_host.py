@@ -31,7 +31,7 @@ def test_abi_rejects_bad_descriptors_without_touching_the_gpu():
   assert L.xmc_conv2d_wgrad(ctypes.byref(w), None, None, None, None, 0, None) == -1
   need = ctypes.c_longlong(-1)
   assert L.xmc_conv2d_wgrad_workspace_bytes(ctypes.byref(w), ctypes.byref(need)) == -1   # empty descriptor
-  assert L.xmc_adam(None, None, None, None, 16, 0.1, 0.5, 0.9, 1e-8, 0.5, 0.1, 1.0, None, 0.0, None, None) == -1
+  assert L.xmc_adam(None, None, None, None, 16, 0.1, 0.5, 0.9, 1e-8, 0.5, 0.1, 1.0, None, 0.0, None, 1, None) == -1
 
 
 def test_parameter_counts_match_reference():

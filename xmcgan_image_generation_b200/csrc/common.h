@@ -11,6 +11,7 @@ typedef __nv_bfloat16 bf16;
 
 void set_cuda_error(cudaError_t e);
 int num_sms();
+int grid_sms();  // SMs the persistent GEMM kernels may occupy (xmc_set_sm_limit)
 
 #define XMC_CUDA_CHECK(expr)                 \
   do {                                       \

@@ -1275,7 +1275,7 @@ extern "C" int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* w
     }
     XMC_CUDA_CHECK(ensure_smem_attr(kAttrRes));
     const int total = p.tiles_w * (d->H / 2) * d->N;
-    const int grid = total < num_sms() ? total : num_sms();
+    const int grid = total < grid_sms() ? total : grid_sms();
     conv3x3_resident_kernel<<<grid, kThreadsFwd, kSmemRes, (cudaStream_t)stream>>>(tmA, tmB, tmB2, p);
     XMC_LAUNCH_CHECK();
     return XMC_OK;
@@ -1308,7 +1308,7 @@ extern "C" int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* w
   }
   XMC_CUDA_CHECK(ensure_smem_attr(kAttrFwd));
   const int total = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles * p.parities;
-  const int grid = total < num_sms() ? total : num_sms();
+  const int grid = total < grid_sms() ? total : grid_sms();
   // XMC_LEAN_EPI=0 forces the generic epilogue (debugging aid; process-global, read once)
   static const int lean_mode = [] { const char* e = getenv("XMC_LEAN_EPI"); return e ? atoi(e) : 1; }();
   auto al32p = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
@@ -1471,7 +1471,7 @@ extern "C" int xmc_conv2d_wgrad(const XmcWgradDesc* d, const void* xa, const voi
     if (r) return r;
   }
   XMC_CUDA_CHECK(ensure_smem_attr(kAttrWgrad));
-  const int grid = p.total_items < num_sms() ? p.total_items : num_sms();
+  const int grid = p.total_items < grid_sms() ? p.total_items : grid_sms();
   gemm_wgrad_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(tmA, tmB, p);
   XMC_LAUNCH_CHECK();
   if (use_ws) {

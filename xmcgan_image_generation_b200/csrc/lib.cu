@@ -30,7 +30,21 @@ int num_sms() {
   return v;
 }
 
+// Number of SMs the persistent tensor-core kernels may occupy (xmc_set_sm_limit): all of them unless the caller has
+// reserved some for a collective kernel that runs concurrently. Work decomposition (tile widths, K splits) is always
+// planned on the full SM count, so results do not depend on the limit.
+static std::atomic<int> g_sm_limit{0};
+int grid_sms() {
+  const int n = num_sms(), l = g_sm_limit.load(std::memory_order_relaxed);
+  return (l > 0 && l < n) ? l : n;
+}
+
 }  // namespace xmc
+
+extern "C" int xmc_set_sm_limit(int sms) {
+  xmc::g_sm_limit.store(sms > 0 ? sms : 0, std::memory_order_relaxed);
+  return XMC_OK;
+}
 
 extern "C" const char* xmc_strerror(int code) {
   switch (code) {

@@ -460,11 +460,12 @@ __global__ void inc_i32_kernel(int* x) { *x += 1; }
 
 extern "C" int xmc_adam(float* p, const float* g, float* m, float* v, long long n, double lr, double beta1,
                         double beta2, double eps, double bias_corr1, double bias_corr2, double grad_scale, float* ema,
-                        double ema_decay, int* step_dev, void* stream) {
+                        double ema_decay, int* step_dev, int advance_step, void* stream) {
   if (!p || !g || !m || !v || n < 4 || (n & 3)) return XMC_EINVAL;
   if (!aligned16(p) || !aligned16(g) || !aligned16(m) || !aligned16(v) || (ema && !aligned16(ema))) return XMC_EALIGN;
   long long blocks = ceil_div_ll(n / 4, 256);
-  const long long cap = (long long)num_sms() * 16;
+  // 4 resident blocks per SM (1024 threads, ~100 KB of loads in flight per SM) keep the kernel HBM-bound
+  long long cap = (long long)num_sms() * 4;
   if (blocks > cap) blocks = cap;
   AdamScalars sc;
   sc.lr = (float)lr; sc.b1 = (float)beta1; sc.b2 = (float)beta2;
@@ -475,7 +476,7 @@ extern "C" int xmc_adam(float* p, const float* g, float* m, float* v, long long 
   sc.b1d = beta1; sc.b2d = beta2;
   adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, sc, ema, step_dev);
   XMC_LAUNCH_CHECK();
-  if (step_dev) {
+  if (step_dev && advance_step) {
     inc_i32_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
     XMC_LAUNCH_CHECK();
   }

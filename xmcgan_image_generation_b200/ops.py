@@ -38,6 +38,36 @@ def _call(name, *args, launches=1):
   LAUNCHES[0] += launches
 
 
+# ---- SM reservation for a concurrent collective ------------------------------------------------------------------------
+# The tensor-core kernels are persistent (one thread block per SM, ~200 KB of shared memory): an NCCL kernel launched on
+# another stream cannot co-reside and either waits for a kernel boundary or, once resident, pushes the tail of every
+# GEMM grid into a second wave — measured on 8 GPUs, the "overlapped" all-reduces cost about their full duration. While
+# a gradient all-reduce is in flight the GEMM launches therefore leave `n` SMs free (xmc_set_sm_limit); the window
+# closes after `tflop` of executed GEMM work has been issued (about the all-reduce's duration) or at release_sms().
+_RESERVE = [0.0]
+
+
+def reserve_sms(n, tflop):
+  if n <= 0:
+    return release_sms()
+  _lib.check(_lib.lib().xmc_set_sm_limit(max(_lib.lib().xmc_num_sms() - n, 1)))
+  _RESERVE[0] = tflop * 1e12
+
+
+def release_sms():
+  if _RESERVE[0] != 0.0:
+    _lib.check(_lib.lib().xmc_set_sm_limit(0))
+    _RESERVE[0] = 0.0
+
+
+def _spend(flops):
+  if _RESERVE[0] > 0.0:
+    _RESERVE[0] -= flops
+    if _RESERVE[0] <= 0.0:
+      _RESERVE[0] = 1.0   # force release_sms to act
+      release_sms()
+
+
 def _pix_ld(t):
   """Pitch (elements) between consecutive pixels/rows of a tensor whose last dim is contiguous."""
   assert t.stride(-1) == 1
@@ -176,6 +206,7 @@ def conv_fwd(x, wk, kh, cout, *, bias=None, residual=None, res_shift=0, mask=Non
     d.ldPair = 2 * cout
   _call("xmc_conv2d_fwd", ctypes.byref(d), ptr(x), ptr(wk), ptr(bias), ptr(residual), ptr(mask), ptr(out),
         ptr(out_pair), stream())
+  _spend(2.0 * N * d.H * d.W * (4 if subpixel else d.KH * d.KW) * C * cout)
   return (out, out_pair) if want_pair else out
 
 
@@ -232,6 +263,7 @@ def _wgrad_bf16(xa, xb, kh, out, *, out_mode=0, batched=False, ld_out=None, tap_
   ws = torch.empty(need.value, device="cuda", dtype=torch.uint8) if need.value else None
   _call("xmc_conv2d_wgrad", ctypes.byref(d), ptr(xa), ptr(xb), ptr(out), ptr(ws), need.value, stream(),
         launches=2 if need.value else 1)
+  _spend(2.0 * N * H * W * (16 if subpixel else d.KH * d.KW) * d.Ca * d.Cb)
   return out
 
 

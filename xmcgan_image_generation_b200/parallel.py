@@ -2,8 +2,29 @@
 tests). The path is pure data parallelism: the only exchanges are the gradient mean (xmc_gan.py:170-171,251 —
 jax.lax.pmean) and the 5-scalar metric mean (xmc_gan.py:185-190). InfoNCE negatives, BatchNorm statistics and
 word-loss pairs stay rank-local exactly as in the reference (attention_lib.py:58-62; coco_xmc.py:44)."""
+import os
+
 import torch
 import torch.distributed as dist
+
+# SMs left to NCCL's thread blocks while a gradient all-reduce overlaps the persistent tensor-core GEMMs
+# (ops.reserve_sms / xmc_set_sm_limit); NCCL is held to the same number of thread blocks (NCCL_MAX_CTAS, read when the
+# communicator is created, i.e. after this module is imported). Opt-in (XMC_RESERVED_SMS=n): on 2 GPUs the hidden
+# all-reduces cost ~0.05 ms each as it is, and holding NCCL to 8 / 16 / 32 thread blocks made the step 1.4 / 0.5 / 0.5 ms
+# slower (`profiles/r02_nccl_overlap.md`).
+RESERVED_SMS = int(os.environ.get("XMC_RESERVED_SMS", "0"))
+if RESERVED_SMS > 0:
+  os.environ.setdefault("NCCL_MAX_CTAS", str(RESERVED_SMS))
+# Slices of the generator-gradient all-reduce (xmc_gan._all_reduce_sliced): Adam of slice i overlaps NCCL on slice i+1.
+# Opt-in as well: an NCCL thread block needs nearly a whole register file, so it only runs on SMs nothing else occupies,
+# and Adam (HBM-bound on all SMs) and the all-reduce end up taking turns: 4 slices measured +0.4 ms on 8 GPUs.
+G_SLICES = int(os.environ.get("XMC_G_SLICES", "1"))
+
+
+def reserve_tflop(nbytes):
+  """Executed GEMM work (TFLOP) issued on the reduced grid after an all-reduce of `nbytes` starts: about the
+  all-reduce's duration (>= 250 GB/s algorithmic bandwidth at RESERVED_SMS thread blocks) at ~800 TFLOP/s of GEMMs."""
+  return nbytes / 250e9 * 800.0
 
 
 def world_size():

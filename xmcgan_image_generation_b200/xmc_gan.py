@@ -99,17 +99,40 @@ def _engines(config, batch):
   return xmc_net.get_engine(config, "g", e), xmc_net.get_engine(config, "d", e)
 
 
-def _adam(opt, grads, ema=None, decay=0.0):
+def _adam(opt, grads, ema=None, decay=0.0, handles=None):
+  """One Adam step (+ EMA) on a flat parameter buffer. handles: [(lo, hi, work)] from _all_reduce_sliced — the step
+  is then applied slice by slice, each as soon as its part of the gradient sum has arrived, so that the update of one
+  slice runs while NCCL reduces the next."""
   opt.step += 1
   t = opt.step
   # graph mode (train_utils.GraphedTrainStep): the step count lives in a device int so that a replayed launch computes
   # this step's bias corrections itself
   step_dev = opt.step_dev
-  ops._call("xmc_adam", opt.target.buf.data_ptr(), grads.data_ptr(), opt.m.data_ptr(), opt.v.data_ptr(),
-            opt.target.buf.numel(), opt.learning_rate, opt.beta1, opt.beta2, opt.eps, 1.0 - opt.beta1 ** t,
-            1.0 - opt.beta2 ** t, 1.0 / parallel.world_size(), ema.data_ptr() if ema is not None else None, decay,
-            step_dev.data_ptr() if step_dev is not None else None, ops._lib.stream(),
-            launches=2 if step_dev is not None else 1)
+  n = opt.target.buf.numel()
+  for lo, hi, work in (handles or [(0, n, None)]):
+    if work is not None:
+      work.wait()
+    last = hi == n
+    ops._call("xmc_adam", opt.target.buf.data_ptr() + 4 * lo, grads.data_ptr() + 4 * lo, opt.m.data_ptr() + 4 * lo,
+              opt.v.data_ptr() + 4 * lo, hi - lo, opt.learning_rate, opt.beta1, opt.beta2, opt.eps,
+              1.0 - opt.beta1 ** t, 1.0 - opt.beta2 ** t, 1.0 / parallel.world_size(),
+              ema.data_ptr() + 4 * lo if ema is not None else None, decay,
+              step_dev.data_ptr() if step_dev is not None else None, int(last), ops._lib.stream(),
+              launches=2 if (step_dev is not None and last) else 1)
+
+
+def _all_reduce_sliced(flat, slices):
+  """Sum all-reduce of a flat gradient buffer as `slices` consecutive in-flight all-reduces (NCCL runs them in order on
+  its stream). Returns [(lo, hi, work)] for _adam, or None on one replica."""
+  if parallel.world_size() == 1:
+    return None
+  n = flat.numel()
+  per = ((n + slices - 1) // slices + 1023) // 1024 * 1024
+  out = []
+  for lo in range(0, n, per):
+    hi = min(lo + per, n)
+    out.append((lo, hi, parallel.all_reduce_sum_(flat[lo:hi], async_op=True)))
+  return out
 
 
 def _with_z(rng, batch, config):
@@ -147,6 +170,15 @@ def _forward_both(state, batch, config, ws, g_eng, d_eng, losses, keep_g_state, 
   return gctx, dctx, state
 
 
+def _all_reduce_async(flat):
+  """Sum all-reduce of a flat gradient buffer left in flight on NCCL's stream; the tensor-core GEMMs issued while it
+  runs leave parallel.RESERVED_SMS SMs to its thread blocks (ops.reserve_sms) for about its duration."""
+  handle = parallel.all_reduce_sum_(flat, async_op=True)
+  if handle is not None and parallel.RESERVED_SMS > 0:
+    ops.reserve_sms(parallel.RESERVED_SMS, parallel.reserve_tflop(flat.numel() * 4))
+  return handle
+
+
 def _finish_pending_d(state, ws, d_eng):
   """Completes a train_d whose gradient all-reduce was left in flight (train_d_deferred): wait, Adam on D, keep the new
   u0. No-op when nothing is pending."""
@@ -154,6 +186,7 @@ def _finish_pending_d(state, ws, d_eng):
     return state
   handle, ws.pending_d = ws.pending_d, None
   if handle is not True:
+    ops.release_sms()
     handle.wait()
   _adam(state.d_optimizer, ws.d_grads)
   new_state = state.replace(discriminator_state=_swap_d_state(state, ws, d_eng))
@@ -202,7 +235,7 @@ def _train_d(rng, state, batch, generator, discriminator, config, defer=False):
   d_eng.backward_d(dctx, d_params, ws.d_grads)
   d_eng.sn_backward(d_params, ws.d_grads, ws.u0_alt)
   if defer:
-    ws.pending_d = parallel.all_reduce_sum_(ws.d_grads, async_op=True) or True
+    ws.pending_d = _all_reduce_async(ws.d_grads) or True
     object.__setattr__(state, "_ws", ws)
     return state
   parallel.all_reduce_sum_(ws.d_grads)
@@ -233,7 +266,7 @@ def _train_g_d(rng, state, batch, generator, discriminator, config, additional_d
   ops.LAUNCHES[0] += 1
   d_eng.backward_d(dctx, d_params, ws.d_grads)
   d_eng.sn_backward(d_params, ws.d_grads, ws.u0_alt)
-  h_d = parallel.all_reduce_sum_(ws.d_grads, async_op=True)
+  h_d = _all_reduce_async(ws.d_grads)
   # pull-back #2: g_loss -> fake images -> params_g
   d_fake = d_eng.backward_g(dctx, d_params)
   del dctx
@@ -257,14 +290,15 @@ def _train_g_d(rng, state, batch, generator, discriminator, config, additional_d
   g_eng.backward(gctx, d_fake, g_params, ws.g_grads)
   g_eng.sn_backward(g_params, ws.g_grads, ws.g_u0_alt)
   del gctx
-  h_g = parallel.all_reduce_sum_(ws.g_grads, async_op=True)
-  # D's Adam (its all-reduce finished long ago, behind the generator backward) runs while G's all-reduce is in flight
+  # the generator's all-reduce is the one nothing hides (its largest leaves are the last ones the backward produces); D's
+  # Adam (whose all-reduce finished long ago, behind the generator backward) runs under it. parallel.G_SLICES > 1 issues
+  # it in slices with G's Adam + EMA of slice i under the all-reduce of slice i+1 (measured: no gain, see parallel.py)
+  h_g = _all_reduce_sliced(ws.g_grads, parallel.G_SLICES)
+  ops.release_sms()
   if h_d is not None:
     h_d.wait()
   _adam(state.d_optimizer, ws.d_grads)
-  if h_g is not None:
-    h_g.wait()
-  _adam(state.g_optimizer, ws.g_grads, ema=state.ema_params.buf, decay=config.polyak_decay)
+  _adam(state.g_optimizer, ws.g_grads, ema=state.ema_params.buf, decay=config.polyak_decay, handles=h_g)
   g_eng.prepped_for = None  # xmc_adam rewrote the parameters through raw pointers
   old_stats = state.generator_state["batch_stats"]
   if ws.graph_mode:
