@@ -23,11 +23,22 @@ __global__ void bn_stats_kernel(const T* __restrict__ x, long long P, int C, int
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = s2[i] = 0.f;
   if (pl < lanes) {
-    for (long long p = (long long)blockIdx.x * lanes + pl; p < P; p += (long long)gridDim.x * lanes) {
-      float f[8];
-      load8(x + p * ld + cvec * 8, f);
+    // four independent 16-byte loads in flight per thread (pixels p, p+st, p+2st, p+3st), added in pixel order
+    const long long st = (long long)gridDim.x * lanes;
+    for (long long p = (long long)blockIdx.x * lanes + pl; p < P; p += 4 * st) {
+      Raw8<T> r[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { s[i] += f[i]; s2[i] += f[i] * f[i]; }
+      for (int k = 0; k < 4; ++k) {
+        if (p + k * st < P) r[k].ld(x + (p + k * st) * ld + cvec * 8);
+        else r[k].zero();
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float f[8];
+        r[k].cvt(f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s[i] += f[i]; s2[i] += f[i] * f[i]; }
+      }
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -101,8 +112,12 @@ __device__ __forceinline__ long long cond_row(const BnP& p, int n, int h, int w)
   return ((long long)n * p.Hc + (h >> p.s)) * p.Hc + (w >> p.s);
 }
 
-// blockDim = (C/8 channel vectors, pixels per block): a thread keeps its channel vector for the whole loop, so
-// mean / rstd stay in registers and consecutive threads touch consecutive 16-byte vectors of the same pixel.
+// blockDim = (C/8 channel vectors, units per block). A unit is a run of `seg` = min(cell side, 8) consecutive pixels of
+// one image row inside one conditioning cell: gamma / beta are loaded once per unit (per pixel they were 2 of the 3
+// loads of every 16-byte output vector — L1 traffic, not HBM, bound the kernel at half the copy bandwidth), the pixels
+// of the unit are loaded raw four at a time. mean / rstd stay in registers for the whole loop.
+__device__ __forceinline__ int bn_seg_shift(const BnP& p) { return p.s < 3 ? p.s : 3; }
+
 template <typename T>
 __global__ void bn_apply_kernel(BnP p, const T* __restrict__ x, const float* __restrict__ mr,
                                 const T* __restrict__ gb, T* __restrict__ y) {
@@ -110,32 +125,47 @@ __global__ void bn_apply_kernel(BnP p, const T* __restrict__ x, const float* __r
   float mean[8], rstd[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { mean[i] = mr[c + i]; rstd[i] = mr[p.C + c + i]; }
-  const int HW = p.H * p.W;
-  const long long P = (long long)p.N * HW;
-  for (long long pix = (long long)blockIdx.x * blockDim.y + threadIdx.y; pix < P;
-       pix += (long long)gridDim.x * blockDim.y) {
-    const int n = (int)(pix / HW);
-    const int hw = (int)(pix - (long long)n * HW);
-    const int h = hw / p.W, w = hw - h * p.W;
-    float f[8], g[8], b[8], o[8];
-    load8(x + pix * p.C + c, f);
-    const long long row = cond_row(p, n, h, w);
+  const int sg = bn_seg_shift(p), seg = 1 << sg;
+  const int spr = p.W >> sg;   // units per image row
+  const long long units = (long long)p.N * p.H * spr;
+  constexpr int kB = 4;
+  for (long long u = (long long)blockIdx.x * blockDim.y + threadIdx.y; u < units;
+       u += (long long)gridDim.x * blockDim.y) {
+    const int ws = (int)(u % spr);
+    const long long t = u / spr;
+    const int h = (int)(t % p.H), n = (int)(t / p.H);
+    const int w0 = ws << sg;
+    float g[8], b[8];
+    const long long row = cond_row(p, n, h, w0);
     load8(gb + row * p.ldG + p.goff + c, g);
     load8(gb + row * p.ldG + p.boff + c, b);
+    const long long pix0 = ((long long)n * p.H + h) * p.W + w0;
+    for (int q0 = 0; q0 < seg; q0 += kB) {
+      Raw8<T> xr[kB];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float t = (f[i] - mean[i]) * rstd[i] * (g[i] + 1.f) + b[i];
-      o[i] = p.relu ? fmaxf(t, 0.f) : t;
-    }
-    if (p.upsample) {
-      const int W2 = p.W * 2;
-      const long long base = (((long long)n * p.H * 2 + 2 * h) * W2 + 2 * w) * p.C + c;
-      store8(y + base, o);
-      store8(y + base + p.C, o);
-      store8(y + base + (long long)W2 * p.C, o);
-      store8(y + base + (long long)W2 * p.C + p.C, o);
-    } else {
-      store8(y + pix * p.C + c, o);
+      for (int k = 0; k < kB; ++k)
+        if (q0 + k < seg) xr[k].ld(x + (pix0 + q0 + k) * p.C + c);
+#pragma unroll
+      for (int k = 0; k < kB; ++k) {
+        if (q0 + k >= seg) break;
+        float f[8], o[8];
+        xr[k].cvt(f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float v = (f[i] - mean[i]) * rstd[i] * (g[i] + 1.f) + b[i];
+          o[i] = p.relu ? fmaxf(v, 0.f) : v;
+        }
+        if (p.upsample) {
+          const int W2 = p.W * 2;
+          const long long base = (((long long)n * p.H * 2 + 2 * h) * W2 + 2 * (w0 + q0 + k)) * p.C + c;
+          store8(y + base, o);
+          store8(y + base + p.C, o);
+          store8(y + base + (long long)W2 * p.C, o);
+          store8(y + base + (long long)W2 * p.C + p.C, o);
+        } else {
+          store8(y + (pix0 + q0 + k) * p.C + c, o);
+        }
+      }
     }
   }
 }
@@ -170,18 +200,20 @@ bn_bwd_reduce_kernel(BnP p, const T* __restrict__ dy, const T* __restrict__ x,
                                      const float* __restrict__ mr, const T* __restrict__ gb,
                                      float* __restrict__ dgb, float* __restrict__ partials, long long total_rows,
                                      int psplit, int rpi) {
-  extern __shared__ float sm[];  // [rpi][cv][16]
+  extern __shared__ float sm[];  // [rpi][cv][16] combine slots, then mean[C], rstd[C]
   const int cv = p.C >> 3;
   const int v = threadIdx.x % cv, ri = threadIdx.x / cv;  // blockDim.x == cv * rpi
   const int c = v * 8;
   const int side = 1 << p.s;
-  float mean[8], rstd[8], s1[8], s2[8];
+  // per-channel mean / rstd live in shared memory (16 registers less per thread: the raw loads in flight need them)
+  float* s_mr = sm + (long long)blockDim.x * 16;
+  for (int t = threadIdx.x; t < 2 * p.C; t += blockDim.x) s_mr[t] = mr[t];
+  __syncthreads();
+  const float* mean = s_mr + c;
+  const float* rstd = s_mr + p.C + c;
+  float s1[8], s2[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    mean[i] = mr[c + i];
-    rstd[i] = mr[p.C + c + i];
-    s1[i] = s2[i] = 0.f;
-  }
+  for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
   float* slot = sm + ((long long)ri * cv + v) * 16;
   const long long units = total_rows * psplit;
   // every thread of the block runs the same number of iterations (the shared-memory combine below needs barriers)
@@ -199,25 +231,88 @@ bn_bwd_reduce_kernel(BnP p, const T* __restrict__ dy, const T* __restrict__ x,
       float gm[8], bt[8];
       load8(gb + row * p.ldG + p.goff + c, gm);
       load8(gb + row * p.ldG + p.boff + c, bt);
-      for (int a = sp; a < side; a += psplit) {
-        const int h = hc * side + a;
-        for (int b = 0; b < side; ++b) {
-          const int w = wc * side + b;
-          float f[8], g[8];
-          load8(x + (((long long)n * p.H + h) * p.W + w) * p.C + c, f);
-          bn_load_grad(p, dy, n, h, w, c, g);
+      // this thread's pixels of the cell, flattened: q -> (a = sp + (q >> s) * psplit, b = q & (side-1)); kB of them
+      // are loaded raw before the first is used (kB x 2 or kB x 5 independent 16-byte loads in flight)
+      const int cnt = ((side - sp + psplit - 1) / psplit) << p.s;
+      const long long img = (long long)n * p.H;
+      if (!p.upsample) {
+        constexpr int kB = sizeof(T) == 2 ? 4 : 2;
+        for (int q0 = 0; q0 < cnt; q0 += kB) {
+          Raw8<T> xr[kB], gr[kB];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float xh = (f[i] - mean[i]) * rstd[i];
-            float gi = g[i];
-            if (p.relu && (xh * (gm[i] + 1.f) + bt[i]) <= 0.f) gi = 0.f;
-            dg[i] += gi * xh;
-            db[i] += gi;
-            const float dxh = gi * (gm[i] + 1.f);
-            s1[i] += dxh;
-            s2[i] += dxh * xh;
+          for (int k = 0; k < kB; ++k) {
+            const int q = q0 + k;
+            if (q < cnt) {
+              const int h = hc * side + sp + (q >> p.s) * psplit, w = wc * side + (q & (side - 1));
+              const long long off = ((img + h) * p.W + w) * p.C + c;
+              xr[k].ld(x + off);
+              gr[k].ld(dy + off);
+            } else {
+              xr[k].zero();
+              gr[k].zero();
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < kB; ++k) {
+            float f[8], g[8];
+            xr[k].cvt(f);
+            gr[k].cvt(g);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float xh = (f[i] - mean[i]) * rstd[i];
+              float gi = g[i];
+              if (p.relu && (xh * (gm[i] + 1.f) + bt[i]) <= 0.f) gi = 0.f;
+              dg[i] += gi * xh;
+              db[i] += gi;
+            }
           }
         }
+      } else {
+        constexpr int kB = sizeof(T) == 2 ? 2 : 1;
+        const int W2 = p.W * 2;
+        for (int q0 = 0; q0 < cnt; q0 += kB) {
+          Raw8<T> xr[kB], gr[kB][4];
+#pragma unroll
+          for (int k = 0; k < kB; ++k) {
+            const int q = q0 + k;
+            if (q < cnt) {
+              const int h = hc * side + sp + (q >> p.s) * psplit, w = wc * side + (q & (side - 1));
+              xr[k].ld(x + ((img + h) * p.W + w) * p.C + c);
+              const long long base = ((2 * img + 2 * h) * W2 + 2 * w) * p.C + c;
+              gr[k][0].ld(dy + base);
+              gr[k][1].ld(dy + base + p.C);
+              gr[k][2].ld(dy + base + (long long)W2 * p.C);
+              gr[k][3].ld(dy + base + (long long)W2 * p.C + p.C);
+            } else {
+              xr[k].zero();
+#pragma unroll
+              for (int j = 0; j < 4; ++j) gr[k][j].zero();
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < kB; ++k) {
+            float f[8], a0[8], a1[8], a2[8], a3[8];
+            xr[k].cvt(f);
+            gr[k][0].cvt(a0);
+            gr[k][1].cvt(a1);
+            gr[k][2].cvt(a2);
+            gr[k][3].cvt(a3);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float xh = (f[i] - mean[i]) * rstd[i];
+              float gi = (a0[i] + a1[i]) + (a2[i] + a3[i]);
+              if (p.relu && (xh * (gm[i] + 1.f) + bt[i]) <= 0.f) gi = 0.f;
+              dg[i] += gi * xh;
+              db[i] += gi;
+            }
+          }
+        }
+      }
+      // BN terms of this cell: sum dxhat = (gamma+1) * sum g, sum dxhat*xhat = (gamma+1) * sum g*xhat
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s1[i] += (gm[i] + 1.f) * db[i];
+        s2[i] += (gm[i] + 1.f) * dg[i];
       }
     }
     if (psplit == 1) {
@@ -260,7 +355,7 @@ bn_bwd_reduce_kernel(BnP p, const T* __restrict__ dy, const T* __restrict__ x,
 }
 
 template <typename T>
-__global__ void bn_bwd_apply_kernel(BnP p, const T* __restrict__ dy, const T* __restrict__ x,
+__global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(BnP p, const T* __restrict__ dy, const T* __restrict__ x,
                                     const float* __restrict__ mr, const T* __restrict__ gb,
                                     const float* __restrict__ sums, float invP, T* __restrict__ dx) {
   const int c = threadIdx.x * 8;
@@ -272,28 +367,74 @@ __global__ void bn_bwd_apply_kernel(BnP p, const T* __restrict__ dy, const T* __
     m1[i] = sums[c + i] * invP;
     m2[i] = sums[p.C + c + i] * invP;
   }
-  const int HW = p.H * p.W;
-  const long long P = (long long)p.N * HW;
-  for (long long pix = (long long)blockIdx.x * blockDim.y + threadIdx.y; pix < P;
-       pix += (long long)gridDim.x * blockDim.y) {
-    const int n = (int)(pix / HW);
-    const int hw = (int)(pix - (long long)n * HW);
-    const int h = hw / p.W, w = hw - h * p.W;
-    float f[8], g[8], gm[8], bt[8], o[8];
-    load8(x + pix * p.C + c, f);
-    bn_load_grad(p, dy, n, h, w, c, g);
-    const long long row = cond_row(p, n, h, w);
+  // units of `seg` consecutive pixels inside one conditioning cell, as in bn_apply_kernel: gamma / beta once per unit
+  const int sg = bn_seg_shift(p), seg = 1 << sg;
+  const int spr = p.W >> sg;
+  const long long units = (long long)p.N * p.H * spr;
+  constexpr int kB = sizeof(T) == 2 ? 4 : 2;
+  for (long long u = (long long)blockIdx.x * blockDim.y + threadIdx.y; u < units;
+       u += (long long)gridDim.x * blockDim.y) {
+    const int ws = (int)(u % spr);
+    const long long t = u / spr;
+    const int h = (int)(t % p.H), n = (int)(t / p.H);
+    const int w0 = ws << sg;
+    float gm[8], bt[8];
+    const long long row = cond_row(p, n, h, w0);
     load8(gb + row * p.ldG + p.goff + c, gm);
     load8(gb + row * p.ldG + p.boff + c, bt);
+    const long long pix0 = ((long long)n * p.H + h) * p.W + w0;
+    // dx of one pixel from its x vector f and (upsample-summed) gradient g
+    auto emit = [&](int q, const float* f, const float* g) {
+      float o[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float xh = (f[i] - mean[i]) * rstd[i];
-      float gi = g[i];
-      if (p.relu && (xh * (gm[i] + 1.f) + bt[i]) <= 0.f) gi = 0.f;
-      const float dxh = gi * (gm[i] + 1.f);
-      o[i] = rstd[i] * (dxh - m1[i] - xh * m2[i]);
+      for (int i = 0; i < 8; ++i) {
+        const float xh = (f[i] - mean[i]) * rstd[i];
+        float gi = g[i];
+        if (p.relu && (xh * (gm[i] + 1.f) + bt[i]) <= 0.f) gi = 0.f;
+        const float dxh = gi * (gm[i] + 1.f);
+        o[i] = rstd[i] * (dxh - m1[i] - xh * m2[i]);
+      }
+      store8(dx + (pix0 + q) * p.C + c, o);
+    };
+    if (!p.upsample) {
+      for (int q0 = 0; q0 < seg; q0 += kB) {   // kB x 2 independent loads in flight
+        Raw8<T> xr[kB], gr[kB];
+#pragma unroll
+        for (int k = 0; k < kB; ++k)
+          if (q0 + k < seg) {
+            xr[k].ld(x + (pix0 + q0 + k) * p.C + c);
+            gr[k].ld(dy + (pix0 + q0 + k) * p.C + c);
+          }
+#pragma unroll
+        for (int k = 0; k < kB; ++k)
+          if (q0 + k < seg) {
+            float f[8], g[8];
+            xr[k].cvt(f);
+            gr[k].cvt(g);
+            emit(q0 + k, f, g);
+          }
+      }
+    } else {
+      const int W2 = p.W * 2;
+      for (int q = 0; q < seg; ++q) {          // 5 independent loads in flight
+        Raw8<T> xr, gr[4];
+        xr.ld(x + (pix0 + q) * p.C + c);
+        const long long base = (((long long)n * p.H * 2 + 2 * h) * W2 + 2 * (w0 + q)) * p.C + c;
+        gr[0].ld(dy + base);
+        gr[1].ld(dy + base + p.C);
+        gr[2].ld(dy + base + (long long)W2 * p.C);
+        gr[3].ld(dy + base + (long long)W2 * p.C + p.C);
+        float f[8], g[8], a1[8], a2[8], a3[8];
+        xr.cvt(f);
+        gr[0].cvt(g);
+        gr[1].cvt(a1);
+        gr[2].cvt(a2);
+        gr[3].cvt(a3);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = (g[i] + a1[i]) + (a2[i] + a3[i]);
+        emit(q, f, g);
+      }
     }
-    store8(dx + pix * p.C + c, o);
   }
 }
 
@@ -393,11 +534,22 @@ __global__ void colsum_kernel(const T* __restrict__ x, long long P, int C, int l
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = 0.f;
   if (pl < lanes) {
-    for (long long p = (long long)blockIdx.x * lanes + pl; p < P; p += (long long)gridDim.x * lanes) {
-      float f[8];
-      load8(x + p * ld + cvec * 8, f);
+    // four independent 16-byte loads in flight per thread, added in pixel order
+    const long long st = (long long)gridDim.x * lanes;
+    for (long long p = (long long)blockIdx.x * lanes + pl; p < P; p += 4 * st) {
+      Raw8<T> r[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) s[i] += f[i];
+      for (int k = 0; k < 4; ++k) {
+        if (p + k * st < P) r[k].ld(x + (p + k * st) * ld + cvec * 8);
+        else r[k].zero();
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float f[8];
+        r[k].cvt(f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[i] += f[i];
+      }
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) sm[(pl * cvb + v) * 8 + i] = s[i];
@@ -577,7 +729,7 @@ static int grid_for(long long total, int block) {
 static void bn_launch_dims(const BnP& p, dim3* grid, dim3* block) {
   const int cv = p.C / 8;
   const int py = 256 / cv > 0 ? 256 / cv : 1;
-  const long long P = (long long)p.N * p.H * p.W;
+  const long long P = ((long long)p.N * p.H * p.W) >> (p.s < 3 ? p.s : 3);   // units of min(cell side, 8) pixels
   long long g = (P + py - 1) / py;
   const long long cap = (long long)num_sms() * 16;
   if (g > cap) g = cap;
@@ -726,7 +878,7 @@ extern "C" int xmc_bn_bwd_reduce(const XmcBnDesc* d, const void* dy, const void*
   rpi = rpi / psplit * psplit;
   if (rpi < psplit) rpi = psplit;
   const int threads = cv * rpi;
-  const size_t smem = (size_t)threads * 16 * sizeof(float);
+  const size_t smem = ((size_t)threads * 16 + 2 * (size_t)p.C) * sizeof(float);
   if (threads > 512 || smem > 48 * 1024) return XMC_EINVAL;
   long long gx = ceil_div_ll(cond_rows * psplit, rpi);
   if (gx > rows) gx = rows;
