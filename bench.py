@@ -137,7 +137,8 @@ class GemmTimer:
       # bf16 tensor-core passes the launch executes: 3 for fp32 operands (hi*hi + lo*hi + hi*lo), 2 for the fp32 stem
       passes = 3 if (xp is not None or x.dtype == torch.float32) else 2 if kw.get("pre_split") else 1
       timer.records.append(("gemm_fwd_kernel", flops, s, e,
-                            (x.shape[0], x.shape[1], x.shape[2], c, kh, cout, int(kw.get("batched", False))), passes))
+                            (x.shape[0], x.shape[1], x.shape[2], c, kh, cout, int(kw.get("batched", False)),
+                             int(kw.get("subpixel", 0))), passes))
       return out
 
     def wgrad(xa, xb, kh, out, **kw):
@@ -154,8 +155,8 @@ class GemmTimer:
       r = timer._wgrad(xa, xb, kh, out, **kw)
       e.record()
       timer.records.append(("gemm_wgrad_kernel", flops, s, e,
-                            (g.shape[0], g.shape[1], g.shape[2], ca, kh, cb, int(kw.get("batched", False))),
-                            3 if xa.dtype == torch.float32 else 1))
+                            (g.shape[0], g.shape[1], g.shape[2], ca, kh, cb, int(kw.get("batched", False)),
+                             int(kw.get("subpixel", 0))), 3 if xa.dtype == torch.float32 else 1))
       return r
 
     ops.conv_fwd, ops.wgrad = conv_fwd, wgrad
@@ -186,7 +187,7 @@ class GemmTimer:
       a[0] += 1
       a[1] += fl
       a[2] += s.elapsed_time(e)
-    rows = [{"kernel": k[0], "N": k[1], "H": k[2], "W": k[3], "C": k[4], "k": k[5], "Cout": k[6], "batched": k[7],
+    rows = [{"kernel": k[0], "N": k[1], "H": k[2], "W": k[3], "C": k[4], "k": k[5], "Cout": k[6], "batched": k[7], "subpixel": k[8],
              "launches": v[0], "ms": round(v[2], 3), "tflops": round(v[1] / 1e12 / (v[2] / 1e3), 1)}
             for k, v in agg.items()]
     return sorted(rows, key=lambda r: -r["ms"])

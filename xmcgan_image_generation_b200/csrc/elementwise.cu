@@ -1,6 +1,7 @@
 // HBM-bound kernels of the XMC-GAN hot path: batch-norm statistics / conditional modulation (+relu, +nearest
 // upsample) and their backward, 2x2 pooling, bias-gradient column sums, casts and broadcasts.
 // All activation accesses are 16-byte vectors (8 bf16) with the channel index fastest -> fully coalesced.
+#include <stdlib.h>
 #include "common.h"
 #include "devutil.cuh"
 
@@ -23,15 +24,14 @@ __global__ void bn_stats_kernel(const T* __restrict__ x, long long P, int C, int
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = s2[i] = 0.f;
   if (pl < lanes) {
-    // four independent 16-byte loads in flight per thread (pixels p, p+st, p+2st, p+3st), added in pixel order
+    // four independent, unpredicated 16-byte loads in flight per thread (pixels p, p+st, p+2st, p+3st), added in pixel
+    // order; the tail runs one pixel at a time
     const long long st = (long long)gridDim.x * lanes;
-    for (long long p = (long long)blockIdx.x * lanes + pl; p < P; p += 4 * st) {
+    long long p = (long long)blockIdx.x * lanes + pl;
+    for (; p + 3 * st < P; p += 4 * st) {
       Raw8<T> r[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (p + k * st < P) r[k].ld(x + (p + k * st) * ld + cvec * 8);
-        else r[k].zero();
-      }
+      for (int k = 0; k < 4; ++k) r[k].ld(x + (p + k * st) * ld + cvec * 8);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         float f[8];
@@ -39,6 +39,12 @@ __global__ void bn_stats_kernel(const T* __restrict__ x, long long P, int C, int
 #pragma unroll
         for (int i = 0; i < 8; ++i) { s[i] += f[i]; s2[i] += f[i] * f[i]; }
       }
+    }
+    for (; p < P; p += st) {
+      float f[8];
+      load8(x + p * ld + cvec * 8, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i] += f[i]; s2[i] += f[i] * f[i]; }
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -117,6 +123,7 @@ __device__ __forceinline__ long long cond_row(const BnP& p, int n, int h, int w)
 // loads of every 16-byte output vector — L1 traffic, not HBM, bound the kernel at half the copy bandwidth), the pixels
 // of the unit are loaded raw four at a time. mean / rstd stay in registers for the whole loop.
 __device__ __forceinline__ int bn_seg_shift(const BnP& p) { return p.s < 3 ? p.s : 3; }
+template <int V> struct IntC { static constexpr int value = V; };
 
 template <typename T>
 __global__ void bn_apply_kernel(BnP p, const T* __restrict__ x, const float* __restrict__ mr,
@@ -140,14 +147,14 @@ __global__ void bn_apply_kernel(BnP p, const T* __restrict__ x, const float* __r
     load8(gb + row * p.ldG + p.goff + c, g);
     load8(gb + row * p.ldG + p.boff + c, b);
     const long long pix0 = ((long long)n * p.H + h) * p.W + w0;
-    for (int q0 = 0; q0 < seg; q0 += kB) {
-      Raw8<T> xr[kB];
+    // KB pixels from q0: KB unpredicated raw loads issued back to back, then the arithmetic and the stores
+    auto run = [&](auto kb, int q0) {
+      constexpr int KB = decltype(kb)::value;
+      Raw8<T> xr[KB];
 #pragma unroll
-      for (int k = 0; k < kB; ++k)
-        if (q0 + k < seg) xr[k].ld(x + (pix0 + q0 + k) * p.C + c);
+      for (int k = 0; k < KB; ++k) xr[k].ld(x + (pix0 + q0 + k) * p.C + c);
 #pragma unroll
-      for (int k = 0; k < kB; ++k) {
-        if (q0 + k >= seg) break;
+      for (int k = 0; k < KB; ++k) {
         float f[8], o[8];
         xr[k].cvt(f);
 #pragma unroll
@@ -166,7 +173,11 @@ __global__ void bn_apply_kernel(BnP p, const T* __restrict__ x, const float* __r
           store8(y + (pix0 + q0 + k) * p.C + c, o);
         }
       }
-    }
+    };
+    if (seg >= kB)
+      for (int q0 = 0; q0 < seg; q0 += kB) run(IntC<kB>{}, q0);
+    else
+      for (int q0 = 0; q0 < seg; ++q0) run(IntC<1>{}, q0);
   }
 }
 
@@ -235,78 +246,73 @@ bn_bwd_reduce_kernel(BnP p, const T* __restrict__ dy, const T* __restrict__ x,
       // are loaded raw before the first is used (kB x 2 or kB x 5 independent 16-byte loads in flight)
       const int cnt = ((side - sp + psplit - 1) / psplit) << p.s;
       const long long img = (long long)n * p.H;
-      if (!p.upsample) {
-        constexpr int kB = sizeof(T) == 2 ? 4 : 2;
-        for (int q0 = 0; q0 < cnt; q0 += kB) {
-          Raw8<T> xr[kB], gr[kB];
+      auto acc = [&](const float* f, const float* g) {
 #pragma unroll
-          for (int k = 0; k < kB; ++k) {
+        for (int i = 0; i < 8; ++i) {
+          const float xh = (f[i] - mean[i]) * rstd[i];
+          float gi = g[i];
+          if (p.relu && (xh * (gm[i] + 1.f) + bt[i]) <= 0.f) gi = 0.f;
+          dg[i] += gi * xh;
+          db[i] += gi;
+        }
+      };
+      if (!p.upsample) {
+        auto run = [&](auto kb, int q0) {   // KB x 2 independent, unpredicated loads, then the sums in pixel order
+          constexpr int KB = decltype(kb)::value;
+          Raw8<T> xr[KB], gr[KB];
+#pragma unroll
+          for (int k = 0; k < KB; ++k) {
             const int q = q0 + k;
-            if (q < cnt) {
-              const int h = hc * side + sp + (q >> p.s) * psplit, w = wc * side + (q & (side - 1));
-              const long long off = ((img + h) * p.W + w) * p.C + c;
-              xr[k].ld(x + off);
-              gr[k].ld(dy + off);
-            } else {
-              xr[k].zero();
-              gr[k].zero();
-            }
+            const int h = hc * side + sp + (q >> p.s) * psplit, w = wc * side + (q & (side - 1));
+            const long long off = ((img + h) * p.W + w) * p.C + c;
+            xr[k].ld(x + off);
+            gr[k].ld(dy + off);
           }
 #pragma unroll
-          for (int k = 0; k < kB; ++k) {
+          for (int k = 0; k < KB; ++k) {
             float f[8], g[8];
             xr[k].cvt(f);
             gr[k].cvt(g);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float xh = (f[i] - mean[i]) * rstd[i];
-              float gi = g[i];
-              if (p.relu && (xh * (gm[i] + 1.f) + bt[i]) <= 0.f) gi = 0.f;
-              dg[i] += gi * xh;
-              db[i] += gi;
-            }
+            acc(f, g);
           }
-        }
+        };
+        constexpr int kB = sizeof(T) == 2 ? 4 : 2;
+        int q0 = 0;
+        for (; q0 + kB <= cnt; q0 += kB) run(IntC<kB>{}, q0);
+        for (; q0 < cnt; ++q0) run(IntC<1>{}, q0);
       } else {
-        constexpr int kB = sizeof(T) == 2 ? 2 : 1;
         const int W2 = p.W * 2;
-        for (int q0 = 0; q0 < cnt; q0 += kB) {
-          Raw8<T> xr[kB], gr[kB][4];
+        auto run = [&](auto kb, int q0) {   // KB x 5 independent, unpredicated loads
+          constexpr int KB = decltype(kb)::value;
+          Raw8<T> xr[KB], gr[KB][4];
 #pragma unroll
-          for (int k = 0; k < kB; ++k) {
+          for (int k = 0; k < KB; ++k) {
             const int q = q0 + k;
-            if (q < cnt) {
-              const int h = hc * side + sp + (q >> p.s) * psplit, w = wc * side + (q & (side - 1));
-              xr[k].ld(x + ((img + h) * p.W + w) * p.C + c);
-              const long long base = ((2 * img + 2 * h) * W2 + 2 * w) * p.C + c;
-              gr[k][0].ld(dy + base);
-              gr[k][1].ld(dy + base + p.C);
-              gr[k][2].ld(dy + base + (long long)W2 * p.C);
-              gr[k][3].ld(dy + base + (long long)W2 * p.C + p.C);
-            } else {
-              xr[k].zero();
-#pragma unroll
-              for (int j = 0; j < 4; ++j) gr[k][j].zero();
-            }
+            const int h = hc * side + sp + (q >> p.s) * psplit, w = wc * side + (q & (side - 1));
+            xr[k].ld(x + ((img + h) * p.W + w) * p.C + c);
+            const long long base = ((2 * img + 2 * h) * W2 + 2 * w) * p.C + c;
+            gr[k][0].ld(dy + base);
+            gr[k][1].ld(dy + base + p.C);
+            gr[k][2].ld(dy + base + (long long)W2 * p.C);
+            gr[k][3].ld(dy + base + (long long)W2 * p.C + p.C);
           }
 #pragma unroll
-          for (int k = 0; k < kB; ++k) {
-            float f[8], a0[8], a1[8], a2[8], a3[8];
+          for (int k = 0; k < KB; ++k) {
+            float f[8], g[8], a1[8], a2[8], a3[8];
             xr[k].cvt(f);
-            gr[k][0].cvt(a0);
+            gr[k][0].cvt(g);
             gr[k][1].cvt(a1);
             gr[k][2].cvt(a2);
             gr[k][3].cvt(a3);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float xh = (f[i] - mean[i]) * rstd[i];
-              float gi = (a0[i] + a1[i]) + (a2[i] + a3[i]);
-              if (p.relu && (xh * (gm[i] + 1.f) + bt[i]) <= 0.f) gi = 0.f;
-              dg[i] += gi * xh;
-              db[i] += gi;
-            }
+            for (int i = 0; i < 8; ++i) g[i] = (g[i] + a1[i]) + (a2[i] + a3[i]);
+            acc(f, g);
           }
-        }
+        };
+        constexpr int kB = sizeof(T) == 2 ? 2 : 1;
+        int q0 = 0;
+        for (; q0 + kB <= cnt; q0 += kB) run(IntC<kB>{}, q0);
+        for (; q0 < cnt; ++q0) run(IntC<1>{}, q0);
       }
       // BN terms of this cell: sum dxhat = (gamma+1) * sum g, sum dxhat*xhat = (gamma+1) * sum g*xhat
 #pragma unroll
@@ -397,23 +403,26 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(BnP p, const T* __
       store8(dx + (pix0 + q) * p.C + c, o);
     };
     if (!p.upsample) {
-      for (int q0 = 0; q0 < seg; q0 += kB) {   // kB x 2 independent loads in flight
-        Raw8<T> xr[kB], gr[kB];
+      auto run = [&](auto kb, int q0) {        // KB x 2 independent, unpredicated loads in flight
+        constexpr int KB = decltype(kb)::value;
+        Raw8<T> xr[KB], gr[KB];
 #pragma unroll
-        for (int k = 0; k < kB; ++k)
-          if (q0 + k < seg) {
-            xr[k].ld(x + (pix0 + q0 + k) * p.C + c);
-            gr[k].ld(dy + (pix0 + q0 + k) * p.C + c);
-          }
+        for (int k = 0; k < KB; ++k) {
+          xr[k].ld(x + (pix0 + q0 + k) * p.C + c);
+          gr[k].ld(dy + (pix0 + q0 + k) * p.C + c);
+        }
 #pragma unroll
-        for (int k = 0; k < kB; ++k)
-          if (q0 + k < seg) {
-            float f[8], g[8];
-            xr[k].cvt(f);
-            gr[k].cvt(g);
-            emit(q0 + k, f, g);
-          }
-      }
+        for (int k = 0; k < KB; ++k) {
+          float f[8], g[8];
+          xr[k].cvt(f);
+          gr[k].cvt(g);
+          emit(q0 + k, f, g);
+        }
+      };
+      if (seg >= kB)
+        for (int q0 = 0; q0 < seg; q0 += kB) run(IntC<kB>{}, q0);
+      else
+        for (int q0 = 0; q0 < seg; ++q0) run(IntC<1>{}, q0);
     } else {
       const int W2 = p.W * 2;
       for (int q = 0; q < seg; ++q) {          // 5 independent loads in flight
@@ -522,7 +531,7 @@ __global__ void unpool2_kernel(const T* __restrict__ dout, int N, int H, int W, 
 // out[c] += sum_p x[p][c]  (bias gradients). gridDim.x == 1: the block adds its sums to out directly; otherwise block b
 // stores them in row b of out (= partials[gridDim.x][C]) and sum_partials_kernel finishes in a fixed order.
 // ---------------------------------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, int kU = 4>
 __global__ void colsum_kernel(const T* __restrict__ x, long long P, int C, int ld, float* __restrict__ out) {
   extern __shared__ float sm[];
   const int cv = C >> 3;
@@ -534,22 +543,27 @@ __global__ void colsum_kernel(const T* __restrict__ x, long long P, int C, int l
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = 0.f;
   if (pl < lanes) {
-    // four independent 16-byte loads in flight per thread, added in pixel order
+    // kU independent 16-byte loads in flight per thread (unpredicated, so that they are issued back to back), added in
+    // pixel order; the tail runs one pixel at a time
     const long long st = (long long)gridDim.x * lanes;
-    for (long long p = (long long)blockIdx.x * lanes + pl; p < P; p += 4 * st) {
-      Raw8<T> r[4];
+    long long p = (long long)blockIdx.x * lanes + pl;
+    for (; p + (kU - 1) * st < P; p += kU * st) {
+      Raw8<T> r[kU];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (p + k * st < P) r[k].ld(x + (p + k * st) * ld + cvec * 8);
-        else r[k].zero();
-      }
+      for (int k = 0; k < kU; ++k) r[k].ld(x + (p + k * st) * ld + cvec * 8);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < kU; ++k) {
         float f[8];
         r[k].cvt(f);
 #pragma unroll
         for (int i = 0; i < 8; ++i) s[i] += f[i];
       }
+    }
+    for (; p < P; p += st) {
+      float f[8];
+      load8(x + p * ld + cvec * 8, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[i] += f[i];
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) sm[(pl * cvb + v) * 8 + i] = s[i];
@@ -725,13 +739,14 @@ static int grid_for(long long total, int block) {
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
-// (C/8, pixels-per-block) thread block and a grid capped at 16 blocks per SM
-static void bn_launch_dims(const BnP& p, dim3* grid, dim3* block) {
+// (C/8, units-per-block) thread block and a grid of at most `per_sm` blocks per SM — the blocks that are resident at the
+// same time, so that the per-block prologue (mean / rstd from global memory) is paid once, not once per wave
+static void bn_launch_dims(const BnP& p, dim3* grid, dim3* block, int per_sm) {
   const int cv = p.C / 8;
   const int py = 256 / cv > 0 ? 256 / cv : 1;
   const long long P = ((long long)p.N * p.H * p.W) >> (p.s < 3 ? p.s : 3);   // units of min(cell side, 8) pixels
   long long g = (P + py - 1) / py;
-  const long long cap = (long long)num_sms() * 16;
+  const long long cap = (long long)num_sms() * per_sm;
   if (g > cap) g = cap;
   if (g < 1) g = 1;
   *grid = dim3((unsigned)g);
@@ -850,7 +865,7 @@ extern "C" int xmc_bn_apply(const XmcBnDesc* d, const void* x, const float* mean
   if (!x || !mean_rstd || !gb || !y) return XMC_EINVAL;
   if (p.C / 8 > 1024) return XMC_EINVAL;
   dim3 grid, block;
-  bn_launch_dims(p, &grid, &block);
+  bn_launch_dims(p, &grid, &block, d->act_f32 ? 2 : 3);   // 81 / 96 registers x <= 256 threads
   XMC_ACT(d->act_f32, bn_apply_kernel<T><<<grid, block, 0, (cudaStream_t)stream>>>(p, (const T*)x, mean_rstd,
                                                                                 (const T*)gb, (T*)y));
   XMC_LAUNCH_CHECK();
@@ -897,7 +912,7 @@ extern "C" int xmc_bn_bwd_apply(const XmcBnDesc* d, const void* dy, const void* 
   if (p.C / 8 > 1024) return XMC_EINVAL;
   const float invP = 1.f / (float)((long long)p.N * p.H * p.W * (d->replicas > 1 ? d->replicas : 1));
   dim3 grid, block;
-  bn_launch_dims(p, &grid, &block);
+  bn_launch_dims(p, &grid, &block, 2);                    // __launch_bounds__(256, 2)
   XMC_ACT(d->act_f32, bn_bwd_apply_kernel<T><<<grid, block, 0, (cudaStream_t)stream>>>(
                           p, (const T*)dy, (const T*)x, mean_rstd, (const T*)gb, sums, invP, (T*)dx));
   XMC_LAUNCH_CHECK();
@@ -945,7 +960,15 @@ extern "C" int xmc_colsum(const void* x, int act_f32, long long P, int C, int ld
   if (gx > rows) gx = rows;
   if (gx < 1) gx = 1;
   const size_t smem = (size_t)lanes * cvb * 8 * sizeof(float);
-  XMC_ACT(act_f32, colsum_kernel<T><<<dim3((unsigned)gx, ny), 256, smem, (cudaStream_t)stream>>>(
+  static const int u = getenv("XMC_COLSUM_U") ? atoi(getenv("XMC_COLSUM_U")) : 4;
+  if (u == 1)
+    XMC_ACT(act_f32, colsum_kernel<T, 1><<<dim3((unsigned)gx, ny), 256, smem, (cudaStream_t)stream>>>(
+                         (const T*)x, P, C, ld, gx == 1 ? out : partials));
+  else if (u == 2)
+    XMC_ACT(act_f32, colsum_kernel<T, 2><<<dim3((unsigned)gx, ny), 256, smem, (cudaStream_t)stream>>>(
+                         (const T*)x, P, C, ld, gx == 1 ? out : partials));
+  else
+  XMC_ACT(act_f32, colsum_kernel<T, 4><<<dim3((unsigned)gx, ny), 256, smem, (cudaStream_t)stream>>>(
                        (const T*)x, P, C, ld, gx == 1 ? out : partials));
   XMC_LAUNCH_CHECK();
   return gx == 1 ? XMC_OK : launch_sum_partials(partials, (int)gx, C, out, 1, (cudaStream_t)stream);

@@ -23,6 +23,9 @@ constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kBarBytes = 256;
 constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // + slack for 1024B alignment
 constexpr int kThreads = 192;     // wgrad kernel: TMA, MMA, 4 epilogue warps
+constexpr int kWgradStagesMax = 8; // wgrad kernel: ring depth for small stages (barrier slots)
+constexpr int kWgradRing = 224 * 1024;  // wgrad kernel: bytes of the operand ring (stage size and depth per launch)
+constexpr int kSmemWgrad = kWgradRing + kBarBytes + 1024;
 constexpr int kEpiParts = 3;      // forward kernel: epilogue warps per TMEM lane quarter
 constexpr int kThreadsFwd = 64 + 128 * kEpiParts;  // TMA warp, MMA warp, 4 * kEpiParts epilogue warps
 constexpr int kTmemCols = 512;
@@ -77,6 +80,11 @@ struct WgradParams {
   int subpixel;         // 1: 16 parity taps (a,dh,b,dw); B is the 2x up-sampled gradient read with stride 2
                         // 2: pool-fused: 16 taps (r,s) of the 4x4/stride-2 form; A is the 2x larger input read with stride 2
   int tap3;             // 1: items are filter rows; the three kw taps share one 66-pixel halo chunk of A (3 accumulators)
+  int tg;               // taps per item that share the B chunk (one A chunk and one accumulator each); 1 = one tap
+  int groups;           // items per (batch, output tile): tap groups (tg > 1), filter rows (tap3) or taps
+  int a_slabs;          // 64-channel slabs of A loaded per tap (1 when Ca <= 64)
+  int stages;           // depth of the shared-memory ring (192 KB / stage_bytes, at most kWgradStagesMax)
+  uint32_t stage_bytes;
   uint32_t slab_bytes;  // bytes one TMA box writes
   uint32_t idesc;
   void* out;
@@ -726,12 +734,14 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_1024(smem_raw);
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t bar_base = sbase + kStages * kStageBytes;
+  const uint32_t bar_base = sbase + kWgradRing;
+  constexpr int kSM = kWgradStagesMax;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + kStages * kStageBytes + 8 * (2 * kStages + 4));
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kSM + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kSM + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kSM + 2 + a); };
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + kWgradRing + 8 * (2 * kSM + 4));
+  const int nstages = p.stages;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -740,11 +750,11 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   // because they are part of the reduction dimension.
   if (p.slab_bytes < 8192) {
     uint4* z = reinterpret_cast<uint4*>(smem);
-    for (int i = threadIdx.x; i < kStages * kStageBytes / 16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < kWgradRing / 16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async();
   }
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < nstages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
@@ -771,59 +781,99 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     split = item / p.items_per_split;
     int rem = item - split * p.items_per_split;
     const int tiles = p.m_tiles * p.n_tiles;
-    bz = rem / (p.taps * tiles);
-    rem -= bz * p.taps * tiles;
-    tap = rem / tiles;
+    bz = rem / (p.groups * tiles);
+    rem -= bz * p.groups * tiles;
+    tap = rem / tiles;   // tap, filter row (tap3) or tap group (tg > 1)
     rem -= tap * tiles;
     mt = rem / p.n_tiles;
     nt = rem - mt * p.n_tiles;
   };
 
+  // tap groups (tg > 1): member k of group g. Plain and pool-fused taps: consecutive tap indices; sub-pixel parity
+  // taps a<<3 | dh<<2 | b<<1 | dw share B per (a, b): groups of 4 = (a, b) with members (dh, dw), of 2 = (a, dh, b)
+  // with members dw.
+  auto group_taps = [&](int g) { return min(p.tg, p.taps - g * p.tg); };
+  auto member_tap = [&](int g, int k) {
+    if (p.subpixel == 1) {
+      if (p.tg == 4) return ((g >> 1) << 3) | ((k >> 1) << 2) | ((g & 1) << 1) | (k & 1);
+      if (p.tg == 2) return ((g >> 2) << 3) | (((g >> 1) & 1) << 2) | ((g & 1) << 1) | k;
+    }
+    return g * p.tg + k;
+  };
+  // A shift (ah, aw), A stride, B start (bh, bw) and B stride of a tap
+  auto tap_geom = [&](int tap, int& ah, int& aw, int& as, int& bh, int& bw, int& bs) {
+    bh = 0; bw = 0; bs = 1; as = 1;
+    if (p.subpixel == 2) {
+      // pool-fused conv3x3 -> 2x2 mean: tap = r*4 + s of the equivalent 4x4 / stride-2 / pad-1 convolution:
+      // x[2i + r - 1, 2j + s - 1] * dy_low[i, j]
+      ah = (tap >> 2) - 1; aw = (tap & 3) - 1; as = 2;
+    } else if (p.subpixel) {
+      // tap = a<<3 | dh<<2 | b<<1 | dw : x[i+dh-(1-a), j+dw-(1-b)] * dy[2i+a, 2j+b]
+      const int a = (tap >> 3) & 1, dh = (tap >> 2) & 1, b = (tap >> 1) & 1, dw = tap & 1;
+      ah = dh - (1 - a); aw = dw - (1 - b); bh = a; bw = b; bs = 2;
+    } else {
+      const int kh = tap / p.KW, kw = tap - kh * p.KW;
+      ah = kh - p.pad_h; aw = kw - p.pad_w;
+    }
+  };
+  const uint32_t a_tap_bytes = (uint32_t)p.a_slabs * 8192u;   // tg > 1: one tap's A region inside a stage
+
   if (warp == 0) {
+    // Producer: one elected thread (UTMALDG takes uniform operands: per-lane boxes would be serialised by the compiler
+    // anyway). The per-chunk path is kept short — the tap shifts of a group are packed into two registers, the loops
+    // over taps / slabs are unrolled with predicates, the chunk coordinates advance incrementally (no divisions).
     if (elect_one()) {
       tma_prefetch_desc(&tmA);
       tma_prefetch_desc(&tmB);
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx = (2 + p.nslabs) * p.slab_bytes;
       const uint32_t tx3 = 2u * 66u * 128u + p.nslabs * p.slab_bytes;
       for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
         int split, bz, tap, mt, nt;
         decode(item, split, bz, tap, mt, nt);
-        // A shift (ah, aw) and B start (bh + bs*h0, bw + bs*w0) of this tap
-        int ah, aw, bh = 0, bw = 0, bs = 1, as = 1;
-        if (p.subpixel == 2) {
-          // pool-fused conv3x3 -> 2x2 mean: tap = r*4 + s of the equivalent 4x4 / stride-2 / pad-1 convolution:
-          // x[2i + r - 1, 2j + s - 1] * dy_low[i, j]
-          ah = (tap >> 2) - 1; aw = (tap & 3) - 1; as = 2;
-        } else if (p.subpixel) {
-          // tap = a<<3 | dh<<2 | b<<1 | dw : x[i+dh-(1-a), j+dw-(1-b)] * dy[2i+a, 2j+b]
-          const int a = (tap >> 3) & 1, dh = (tap >> 2) & 1, b = (tap >> 1) & 1, dw = tap & 1;
-          ah = dh - (1 - a); aw = dw - (1 - b); bh = a; bw = b; bs = 2;
-        } else {
-          const int kh = tap / p.KW, kw = tap - kh * p.KW;
-          ah = kh - p.pad_h; aw = kw - p.pad_w;
+        const int nt_item = p.tg > 1 ? group_taps(tap) : 1;
+        // A shifts of the member taps, one signed byte each (+8 bias); A stride; B start and stride
+        uint32_t ahp = 0, awp = 0;
+        int as = 1, bh = 0, bw = 0, bs = 1;
+        for (int k2 = 0; k2 < nt_item; ++k2) {
+          int ah, aw;
+          tap_geom(p.tg > 1 ? member_tap(tap, k2) : tap, ah, aw, as, bh, bw, bs);
+          if (p.tap3) {  // item = filter ROW kh: one 66-pixel halo chunk of A serves the three kw taps
+            ah = tap - p.pad_h; aw = -p.pad_w; bh = 0; bw = 0; bs = 1; as = 1;
+          }
+          ahp |= (uint32_t)(ah + 8) << (8 * k2);
+          awp |= (uint32_t)(aw + 8) << (8 * k2);
         }
-        if (p.tap3) {  // item = filter ROW kh: one 66-pixel halo chunk of A serves the three kw taps
-          ah = tap - p.pad_h; aw = -p.pad_w;
-        }
+        const uint32_t tx = p.tap3 ? tx3 : (uint32_t)(nt_item * p.a_slabs + p.nslabs) * p.slab_bytes;
+        const uint32_t a_stride = p.tap3 ? a_slab : 8192u;
+        const uint32_t b_off = p.tap3 ? 2 * a_slab : p.tg * a_tap_bytes;
+        const bool two_slabs = p.tap3 || p.a_slabs == 2;
         const int j0 = split * p.chunks_per_split;
         const int j1 = min(p.total_chunks, j0 + p.chunks_per_split);
         const int m0 = mt * 128, n_off = nt * p.BN;
+        int iw = j0 % p.chunks_w, ih = (j0 / p.chunks_w) % p.chunks_h, in = j0 / (p.chunks_w * p.chunks_h);
         for (int j = j0; j < j1; ++j) {
-          const int iw = j % p.chunks_w;
-          const int ih = (j / p.chunks_w) % p.chunks_h;
-          const int in = j / (p.chunks_w * p.chunks_h);
           const int w0 = iw * p.tw, h0 = ih * p.th, n0 = p.batched ? bz : in * p.tn;
           mbar_wait(empty_bar(stage), phase ^ 1);
-          mbar_arrive_expect_tx(full_bar(stage), p.tap3 ? tx3 : tx);
-          const uint32_t sa = sbase + stage * kStageBytes;
-          tma_load_4d(sa, &tmA, full_bar(stage), m0, as * w0 + aw, as * h0 + ah, n0);
-          tma_load_4d(sa + a_slab, &tmA, full_bar(stage), m0 + 64, as * w0 + aw, as * h0 + ah, n0);
-          for (int s = 0; s < p.nslabs; ++s)
-            tma_load_4d(sa + 2 * a_slab + s * 8192, &tmB, full_bar(stage), n_off + s * 64, bs * w0 + bw, bs * h0 + bh,
-                        n0);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          mbar_arrive_expect_tx(full_bar(stage), tx);
+          const uint32_t sa = sbase + stage * p.stage_bytes;
+          const uint32_t fb = full_bar(stage);
+#pragma unroll
+          for (int k2 = 0; k2 < 4; ++k2) {
+            if (k2 < nt_item) {
+              const int cw = as * w0 + (int)((awp >> (8 * k2)) & 0xff) - 8;
+              const int ch = as * h0 + (int)((ahp >> (8 * k2)) & 0xff) - 8;
+              tma_load_4d(sa + k2 * a_tap_bytes, &tmA, fb, m0, cw, ch, n0);
+              if (two_slabs) tma_load_4d(sa + k2 * a_tap_bytes + a_stride, &tmA, fb, m0 + 64, cw, ch, n0);
+            }
+          }
+          for (int s2 = 0; s2 < p.nslabs; ++s2)
+            tma_load_4d(sa + b_off + s2 * 8192, &tmB, fb, n_off + s2 * 64, bs * w0 + bw, bs * h0 + bh, n0);
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
+          if (++iw == p.chunks_w) {
+            iw = 0;
+            if (++ih == p.chunks_h) { ih = 0; ++in; }
+          }
         }
       }
     }
@@ -833,7 +883,9 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-      const int split = item / p.items_per_split;
+      int split, bz, tap, mt, nt;
+      decode(item, split, bz, tap, mt, nt);
+      const int nt_item = p.tg > 1 ? group_taps(tap) : 1;
       const int j0 = split * p.chunks_per_split;
       const int j1 = min(p.total_chunks, j0 + p.chunks_per_split);
       mbar_wait(tempty_bar(acc), acc_phase ^ 1);
@@ -843,11 +895,11 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t sa = sbase + stage * kStageBytes;
+          const uint32_t sa = sbase + stage * p.stage_bytes;
           // MN-major SW128: LBO = byte distance between 64-channel slabs, SBO = distance between 8-pixel groups.
-          const uint64_t adesc = make_smem_desc(sa, a_slab, 1024);
-          const uint64_t bdesc = make_smem_desc(sa + 2 * a_slab, 8192, 1024);
           if (p.tap3) {
+            const uint64_t adesc = make_smem_desc(sa, a_slab, 1024);
+            const uint64_t bdesc = make_smem_desc(sa + 2 * a_slab, 8192, 1024);
             // tap kw multiplies pixels kw .. kw+63 of the 66-pixel halo chunk (one pixel = one 128 B row; the start
             // address moves kw rows into the swizzle repeat, the XOR follows the absolute address) into its own
             // accumulator: three taps per loaded chunk
@@ -858,7 +910,19 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 umma_bf16(tmem_base + kw * acc_cols, adesc + 8 * kw + 128 * s, bdesc + 128 * s, p.idesc,
                           (j > j0 || s > 0) ? 1u : 0u);
             }
+          } else if (p.tg > 1) {
+            // tap group: every member tap has its own A chunk and accumulator, all multiply the one B chunk
+            const uint64_t bdesc = make_smem_desc(sa + p.tg * a_tap_bytes, 8192, 1024);
+            for (int k2 = 0; k2 < nt_item; ++k2) {
+              const uint64_t adesc = make_smem_desc(sa + k2 * a_tap_bytes, 8192, 1024);
+#pragma unroll
+              for (int s = 0; s < 4; ++s)
+                umma_bf16(tmem_base + k2 * acc_cols, adesc + 128 * s, bdesc + 128 * s, p.idesc,
+                          (j > j0 || s > 0) ? 1u : 0u);
+            }
           } else {
+            const uint64_t adesc = make_smem_desc(sa, 8192, 1024);
+            const uint64_t bdesc = make_smem_desc(sa + a_tap_bytes, 8192, 1024);
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
               // 16 pixels (K) per MMA = two 8-pixel groups = 2048 bytes: +128 in the (addr>>4) field
@@ -869,9 +933,9 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (j == j1 - 1) umma_commit(tfull_bar(acc));
         }
         __syncwarp();
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (++stage == nstages) { stage = 0; phase ^= 1; }
       }
-      if (p.tap3) {  // the three kw accumulators fill TMEM: single-buffered, the barrier pair just alternates phase
+      if (p.tap3 || p.tg > 1) {  // several accumulators fill TMEM: single-buffered, the barrier pair alternates phase
         acc_phase ^= 1;
       } else {
         acc ^= 1;
@@ -890,15 +954,18 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const bool row_ok = m < p.Ca;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      for (int kw3 = 0; kw3 < (p.tap3 ? 3 : 1); ++kw3) {
-      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (p.tap3 ? kw3 * acc_cols : acc * 256);
+      const int naccs = p.tap3 ? 3 : (p.tg > 1 ? group_taps(tap) : 1);
+      for (int kw3 = 0; kw3 < naccs; ++kw3) {
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (naccs > 1 || p.tg > 1 ? kw3 * acc_cols : acc * 256);
+      // tap this accumulator belongs to: filter row `tap` x kw (tap3), member kw3 of tap group `tap`, or `tap`
+      const int tap_id = p.tap3 ? tap * 3 + kw3 : (p.tg > 1 ? member_tap(tap, kw3) : tap);
       // destinations: a plain tap writes its own [Ca][Cb] matrix; a sub-pixel parity tap (a,dh,b,dw) is the gradient of
       // a SUM of 3x3 taps, W_a[dh] = sum_{kh in S(a,dh)} W[kh] with S(0,0)={0}, S(0,1)={1,2}, S(1,0)={0,1}, S(1,1)={2},
       // so it is added to every (kh, kw) in S(a,dh) x S(b,dw)
       int dest[4], ndest = 1;
-      dest[0] = p.tap3 ? tap * 3 + kw3 : tap;  // tap3: item = filter row `tap`, accumulator = kw
+      dest[0] = tap_id;
       if (p.subpixel) {
-        const int a = (tap >> 3) & 1, dh = (tap >> 2) & 1, b = (tap >> 1) & 1, dw = tap & 1;
+        const int a = (tap_id >> 3) & 1, dh = (tap_id >> 2) & 1, b = (tap_id >> 1) & 1, dw = tap_id & 1;
         const int kh0 = (a == 0) ? (dh == 0 ? 0 : 1) : (dh == 0 ? 0 : 2), nkh = (a != dh) ? 2 : 1;
         const int kw0 = (b == 0) ? (dw == 0 ? 0 : 1) : (dw == 0 ? 0 : 2), nkw = (b != dw) ? 2 : 1;
         ndest = 0;
@@ -908,7 +975,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const long long obase0 = (long long)bz * p.out_batch_stride + (long long)m * p.ldOut;
       // partial-tile slot of this item in the workspace (deterministic split-K / shared destinations)
       float* ws_row = p.ws ? p.ws + (long long)split * p.ws_split_stride +
-                                 (((long long)bz * p.ws_taps + (p.tap3 ? tap * 3 + kw3 : tap)) * p.Ca + m) * p.Cb
+                                 (((long long)bz * p.ws_taps + tap_id) * p.Ca + m) * p.Cb
                            : nullptr;
       for (int c0 = 0; c0 < p.BN; c0 += 16) {
         uint32_t v[16];
@@ -981,7 +1048,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
-      if (p.tap3) {
+      if (p.tap3 || p.tg > 1) {
         acc_phase ^= 1;
       } else {
         acc ^= 1;
@@ -1162,7 +1229,7 @@ static cudaError_t ensure_smem_attr(int kind) {
       e = cudaFuncSetAttribute(conv3x3_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemRes);
       break;
     default:
-      e = cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+      e = cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemWgrad);
       break;
   }
   if (e == cudaSuccess && cached) done[dev][kind] = true;
@@ -1354,29 +1421,61 @@ static int plan_wgrad(const XmcWgradDesc* d, WgradParams& p) {
   p.tap3 = (tap3_mode && d->KH == 3 && d->KW == 3 && d->pad_h == 1 && d->pad_w == 1 && !d->subpixel && !d->batched &&
             d->pitchWA <= 0 && d->out_mode == 0 && d->W >= 64 && p.n_tiles == 1 && 3 * (((p.BN + 31) / 32) * 32) <= 512)
                ? 1 : 0;
-  const int taps = d->subpixel ? 16 : (p.tap3 ? 3 : d->KH * d->KW);
+  const int taps = d->subpixel ? 16 : d->KH * d->KW;
   p.subpixel = d->subpixel;
   const int nbatch = d->batched ? d->N : 1;
-  const int base_ctas = m_tiles * p.n_tiles * taps * nbatch;
+  const int acc_cols = ((p.BN + 31) / 32) * 32;
+  p.a_slabs = (d->Ca <= 64 && !p.tap3) ? 1 : 2;
+  // Tap groups: the taps of one output tile all multiply the same B chunk (sub-pixel parity taps: per parity), so an
+  // item can take tg of them — tg A chunks, ONE B chunk, tg accumulators per ring stage. The kernel is bound by
+  // L2 -> SM operand traffic (ncu: 12-13 TB/s at 54 % tensor activity for 192 -> 384 at 32x32); per pixel and item the
+  // traffic drops from tg x (A + B) to tg x A + B. Limits: tg accumulators in the 512 TMEM columns, a stage of at most
+  // a third (BN <= 128) or a quarter (BN <= 192) of the 224 KB ring — the loop is latency-bound on the bytes in flight
+  // (ring / ~2 us loaded L2 latency = ~50 B/clk per SM), so grouping must not cost ring depth. Measured: 3 -> 96 packed
+  // window 395 -> 270 us, pool-fused 96 -> 96 316 -> 240 us, sub-pixel 192 -> 96 315 -> 250 us, 192 -> 384 at 32x32
+  // 203 -> 173 us; BN = 256 stays ungrouped (1536 -> 1536 at 4x4: 118 -> 152 us with 3 stages and an epilogue that is
+  // no longer overlapped). XMC_WGRAD_TG=1 switches the grouping off (debugging aid).
+  static const int tg_max = [] { const char* e = getenv("XMC_WGRAD_TG"); return e ? atoi(e) : 4; }();
+  p.tg = 1;
+  if (!p.tap3 && d->out_mode == 0 && taps > 1 && p.BN <= 192) {
+    const int tg_minst = p.BN <= 128 ? 3 : 4;   // ring stages a grouped item must keep
+    for (int tg = 4; tg >= 2; --tg) {
+      if (tg > tg_max || tg > taps || tg * acc_cols > 512) continue;
+      if (d->subpixel == 1 && tg == 3) continue;
+      if ((tg * p.a_slabs + p.nslabs) * 8192 > kWgradRing / tg_minst) continue;
+      p.tg = tg;
+      break;
+    }
+  }
+  p.groups = p.tap3 ? 3 : ceil_div(taps, p.tg);
+  p.stage_bytes = p.tap3 ? (uint32_t)(2 * 9216 + p.nslabs * 8192) : (uint32_t)((p.tg * p.a_slabs + p.nslabs) * 8192);
+  static const int stride48 = [] { const char* e = getenv("XMC_WGRAD_STRIDE48"); return e ? atoi(e) : 0; }();
+  if (stride48 && p.stage_bytes < (uint32_t)kStageBytes) p.stage_bytes = kStageBytes;
+  p.stages = kWgradRing / (int)p.stage_bytes;
+  if (p.stages > kWgradStagesMax) p.stages = kWgradStagesMax;
+  static const int max_stages = [] { const char* e = getenv("XMC_WGRAD_MAXSTAGES"); return e ? atoi(e) : 8; }();
+  if (p.stages > max_stages) p.stages = max_stages;
+  const int per_item = p.tap3 ? 3 : p.tg;   // accumulators (taps) an item computes
+  const int base_ctas = m_tiles * p.n_tiles * p.groups * nbatch;
   int ksplit = 1;
   if (d->out_mode == 0) {
     // Split K (pixels) across CTAs with a small cost model (microseconds): tensor time = waves x chunks per CTA x
-    // (four 128 x BN x 16 MMAs = 2 BN cycles per 64-pixel chunk) + one epilogue per item, plus — as soon as the
-    // reduction is split — the partial tiles' round trip through the workspace and the second-stage launch. Layers
-    // with large weights (1536 x 1536 x 9 = 85 MB per split) therefore stay unsplit even if their last wave is
+    // (four 128 x BN x 16 MMAs = 2 BN cycles per 64-pixel chunk and tap) + one epilogue per item, plus — as soon as
+    // the reduction is split — the partial tiles' round trip through the workspace and the second-stage launch.
+    // Layers with large weights (1536 x 1536 x 9 = 85 MB per split) therefore stay unsplit even if their last wave is
     // ragged; narrow layers (96 x 96) split ~50 ways. Keeps >= 8 chunks (512 pixels) per CTA.
     const int sms = num_sms();
     const int max_split = p.total_chunks / 8 > 0 ? p.total_chunks / 8 : 1;
     const double clk_mhz = 1600.0, hbm_bytes_per_us = 5.0e6;
-    const double tile_bytes = 4.0 * (double)taps * d->Ca * d->Cb * nbatch * (p.tap3 ? 3 : 1);
+    const double tile_bytes = 4.0 * (double)taps * d->Ca * d->Cb * nbatch;
     double best_cost = 1e300;
     for (int ks = 1; ks <= max_split && ks <= 1024; ++ks) {
       const int cps = ceil_div(p.total_chunks, ks);
       const int ks_eff = ceil_div(p.total_chunks, cps);
       const long long ctas = (long long)base_ctas * ks_eff;
       const long long waves = (ctas + sms - 1) / sms;
-      const double epi = 1500.0 + 12.0 * p.BN * (p.tap3 ? 3 : 1);
-      double cost = (double)waves * ((double)cps * 2.0 * p.BN * (p.tap3 ? 3 : 1) + epi) / clk_mhz;
+      const double epi = 1500.0 + 12.0 * p.BN * per_item;
+      double cost = (double)waves * ((double)cps * 2.0 * p.BN * per_item + epi) / clk_mhz;
       if (ks_eff > 1) cost += 3.0 + (2.0 * ks_eff + 2.0) * tile_bytes / hbm_bytes_per_us;
       if (cost < best_cost * 0.999) { best_cost = cost; ksplit = ks_eff; }
       if (ctas > 16LL * sms) break;
@@ -1472,7 +1571,7 @@ extern "C" int xmc_conv2d_wgrad(const XmcWgradDesc* d, const void* xa, const voi
   }
   XMC_CUDA_CHECK(ensure_smem_attr(kAttrWgrad));
   const int grid = p.total_items < grid_sms() ? p.total_items : grid_sms();
-  gemm_wgrad_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(tmA, tmB, p);
+  gemm_wgrad_kernel<<<grid, kThreads, kSmemWgrad, (cudaStream_t)stream>>>(tmA, tmB, p);
   XMC_LAUNCH_CHECK();
   if (use_ws) {
     WgradReduceParams r;
