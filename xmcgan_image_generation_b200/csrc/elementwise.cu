@@ -960,14 +960,6 @@ extern "C" int xmc_colsum(const void* x, int act_f32, long long P, int C, int ld
   if (gx > rows) gx = rows;
   if (gx < 1) gx = 1;
   const size_t smem = (size_t)lanes * cvb * 8 * sizeof(float);
-  static const int u = getenv("XMC_COLSUM_U") ? atoi(getenv("XMC_COLSUM_U")) : 4;
-  if (u == 1)
-    XMC_ACT(act_f32, colsum_kernel<T, 1><<<dim3((unsigned)gx, ny), 256, smem, (cudaStream_t)stream>>>(
-                         (const T*)x, P, C, ld, gx == 1 ? out : partials));
-  else if (u == 2)
-    XMC_ACT(act_f32, colsum_kernel<T, 2><<<dim3((unsigned)gx, ny), 256, smem, (cudaStream_t)stream>>>(
-                         (const T*)x, P, C, ld, gx == 1 ? out : partials));
-  else
   XMC_ACT(act_f32, colsum_kernel<T, 4><<<dim3((unsigned)gx, ny), 256, smem, (cudaStream_t)stream>>>(
                        (const T*)x, P, C, ld, gx == 1 ? out : partials));
   XMC_LAUNCH_CHECK();

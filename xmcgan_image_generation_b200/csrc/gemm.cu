@@ -375,6 +375,8 @@ gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar_base = sbase + kStages * kStageBytes;
   // barrier layout: full[kStages], empty[kStages], tfull[2], tempty[2], then tmem pointer
+  // (a deeper ring of smaller stages for narrow tiles was measured: no gain — unlike the weight-gradient kernel, this
+  // loop is not bound by the bytes in flight)
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
@@ -420,34 +422,56 @@ gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       tma_prefetch_desc(&tmB);
       int stage = 0;
       uint32_t phase = 0;
+      // tile -> (m tile = (in, ih, iw), parity, n tile) as a mixed-radix counter advanced by gridDim.x per step (digit
+      // steps computed once: no divisions per tile). Parity (a,b) of sub-pixel mode: output pixel (2h+a, 2w+b) reads
+      // the 2x2 input window starting at (h-(1-a), w-(1-b)) and the parity's own summed weights (rows par*Cout.. of B)
+      const int radix[4] = {p.n_tiles, p.parities, p.tiles_w, p.tiles_h};
+      int dig[5], stp[5];
+      {
+        int t = blockIdx.x, g = gridDim.x;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          dig[i] = t % radix[i]; t /= radix[i];
+          stp[i] = g % radix[i]; g /= radix[i];
+        }
+        dig[4] = t; stp[4] = g;
+      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        // tile -> (m tile, parity, n tile); parity (a,b) of sub-pixel mode: output pixel (2h+a, 2w+b) reads the 2x2
-        // input window starting at (h-(1-a), w-(1-b)) and the parity's own summed weights (rows par*Cout.. of B)
-        const int nt = tile % p.n_tiles;
-        const int t2 = tile / p.n_tiles;
-        const int par = t2 % p.parities, mt = t2 / p.parities;
-        const int iw = mt % p.tiles_w;
-        const int ih = (mt / p.tiles_w) % p.tiles_h;
-        const int in = mt / (p.tiles_w * p.tiles_h);
+        const int nt = dig[0], par = dig[1], iw = dig[2], ih = dig[3], in = dig[4];
+        {
+          int carry = 0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            int v = dig[i] + stp[i] + carry;
+            carry = v >= radix[i] ? 1 : 0;
+            dig[i] = v - (carry ? radix[i] : 0);
+          }
+          dig[4] += stp[4] + carry;
+        }
         const int w0 = iw * p.tw, h0 = ih * p.th, n0 = in * p.tn;
         const int pad_h = p.pad_h - (par >> 1), pad_w = p.pad_w - (par & 1);
+        // no divisions on the per-stage path (this thread's loop is on the critical path of the short-K layers)
+        const int per = p.pairC >> 6;   // two-part operand: 64-channel chunks per part
+        int kh = 0, kw = 0;
         for (int tap = 0; tap < taps; ++tap) {
-          const int kh = tap / p.KW, kw = tap - kh * p.KW;
+          int ca = 0, in_part = 0;
           for (int c = 0; c < p.cchunks; ++c) {
             mbar_wait(empty_bar(stage), phase ^ 1);
             mbar_arrive_expect_tx(full_bar(stage), p.stage_tx_bytes);
             const uint32_t sa = sbase + stage * kStageBytes;
-            int ca = c * 64;
-            if (p.pairC) {  // chunk c of [hi | lo | hi] -> channel offset inside the stored [hi | lo]
-              const int per = p.pairC >> 6, part = c / per;
-              ca = (part == 1 ? p.pairC : 0) + (c - part * per) * 64;
-            }
             tma_load_4d(sa, &tmA, full_bar(stage), ca, w0 * p.strideW + kw - pad_w,
                         h0 * p.strideH + kh - pad_h, n0);
             tma_load_3d(sa + kABytes, &tmB, full_bar(stage), tap * p.C + c * 64, par * p.Cout + nt * p.BN,
                         p.batched ? n0 : 0);
             if (++stage == kStages) { stage = 0; phase ^= 1; }
+            // next chunk's channel offset; two-part operand: chunks walk [hi | lo | hi] of the stored [hi | lo]
+            ca += 64;
+            if (p.pairC && ++in_part == per) {
+              in_part = 0;
+              ca = (ca == p.pairC) ? p.pairC : 0;   // after hi -> lo (offset pairC), after lo -> hi again (offset 0)
+            }
           }
+          if (++kw == p.KW) { kw = 0; ++kh; }
         }
       }
     }
@@ -1449,12 +1473,8 @@ static int plan_wgrad(const XmcWgradDesc* d, WgradParams& p) {
   }
   p.groups = p.tap3 ? 3 : ceil_div(taps, p.tg);
   p.stage_bytes = p.tap3 ? (uint32_t)(2 * 9216 + p.nslabs * 8192) : (uint32_t)((p.tg * p.a_slabs + p.nslabs) * 8192);
-  static const int stride48 = [] { const char* e = getenv("XMC_WGRAD_STRIDE48"); return e ? atoi(e) : 0; }();
-  if (stride48 && p.stage_bytes < (uint32_t)kStageBytes) p.stage_bytes = kStageBytes;
   p.stages = kWgradRing / (int)p.stage_bytes;
   if (p.stages > kWgradStagesMax) p.stages = kWgradStagesMax;
-  static const int max_stages = [] { const char* e = getenv("XMC_WGRAD_MAXSTAGES"); return e ? atoi(e) : 8; }();
-  if (p.stages > max_stages) p.stages = max_stages;
   const int per_item = p.tap3 ? 3 : p.tg;   // accumulators (taps) an item computes
   const int base_ctas = m_tiles * p.n_tiles * p.groups * nbatch;
   int ksplit = 1;
