@@ -46,10 +46,11 @@ conv_c3_in_kernel(const T* __restrict__ x, const bf16* __restrict__ w, int ldw, 
   float* bs = ws + Cout * K;
   for (int t = threadIdx.x; t < Cout; t += blockDim.x) bs[t] = bias ? bias[t] : 0.f;
   __syncthreads();
+  // persistent blocks (a few per SM): the weight staging above is paid once per block, not once per 512 pixels
   const int wq4 = (W + kPx - 1) / kPx;
   const long long groups = (long long)N * H * wq4;
-  const long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gidx >= groups) return;
+  for (long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x; gidx < groups;
+       gidx += (long long)gridDim.x * blockDim.x) {
   const int wg = gidx % wq4;
   const int hq = (gidx / wq4) % H;
   const long long n = gidx / ((long long)wq4 * H);
@@ -103,6 +104,7 @@ conv_c3_in_kernel(const T* __restrict__ x, const bf16* __restrict__ w, int ldw, 
       }
     }
   }
+  }
 }
 
 // y[p][c3] = sum_{tap,ci} x[p+d(tap)][ci] * w[c3][tap*Cin+ci] + bias[c3];  x: bf16 [N,H,W,Cin] (Cin % 8 == 0)
@@ -119,10 +121,11 @@ conv_c3_out_kernel(const T* __restrict__ x, const bf16* __restrict__ w, int ldw,
   const int K = KH * KW * Cin;
   for (int t = threadIdx.x; t < kImgC * K; t += blockDim.x) ws[t] = weight_at(w, ldw, t / K, t % K, Cin, wsplit);
   __syncthreads();
+  // persistent blocks: the weight staging above is paid once per block
   const int wq4 = (W + kPx - 1) / kPx;
   const long long groups = (long long)N * H * wq4;
-  const long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gidx >= groups) return;
+  for (long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x; gidx < groups;
+       gidx += (long long)gridDim.x * blockDim.x) {
   const int wg = gidx % wq4;
   const int hq = (gidx / wq4) % H;
   const long long n = gidx / ((long long)wq4 * H);
@@ -185,6 +188,7 @@ conv_c3_out_kernel(const T* __restrict__ x, const bf16* __restrict__ w, int ldw,
     } else {
       yo[0] = a0; yo[1] = a1; yo[2] = a2;
     }
+  }
   }
 }
 
@@ -434,11 +438,13 @@ extern "C" int xmc_conv_c3_in(const void* x, int act_f32, const void* w, int ldw
   const long long P = (long long)N * H * ceil_div(W, kPx);
   if (KH != KW || (KH != 1 && KH != 3)) return XMC_EINVAL;
   // fp32 activations come with split-form weights ([row][tap][hi|hi|lo][3], see weight_at)
+  long long blocks = ceil_div_ll(P, 128);
+  if (blocks > (long long)num_sms() * 4) blocks = (long long)num_sms() * 4;   // 126 registers x 128 threads: 4 per SM
   if (KH == 3)
-    XMC_ACT(act_f32, conv_c3_in_kernel<3, T><<<(unsigned)ceil_div_ll(P, 128), 128, smem, (cudaStream_t)stream>>>(
+    XMC_ACT(act_f32, conv_c3_in_kernel<3, T><<<(unsigned)blocks, 128, smem, (cudaStream_t)stream>>>(
                          (const T*)x, (const bf16*)w, ldw, act_f32, bias, N, H, W, Cout, relu, (T*)y));
   else
-    XMC_ACT(act_f32, conv_c3_in_kernel<1, T><<<(unsigned)ceil_div_ll(P, 128), 128, smem, (cudaStream_t)stream>>>(
+    XMC_ACT(act_f32, conv_c3_in_kernel<1, T><<<(unsigned)blocks, 128, smem, (cudaStream_t)stream>>>(
                          (const T*)x, (const bf16*)w, ldw, act_f32, bias, N, H, W, Cout, relu, (T*)y));
   XMC_LAUNCH_CHECK();
   return XMC_OK;
@@ -452,11 +458,13 @@ extern "C" int xmc_conv_c3_out(const void* x, int act_f32, const void* w, int ld
   if (smem > 48 * 1024) return XMC_EINVAL;
   const long long P = (long long)N * H * ceil_div(W, kPx);
   if (KH != KW || (KH != 1 && KH != 3)) return XMC_EINVAL;
+  long long blocks = ceil_div_ll(P, 128);
+  if (blocks > (long long)num_sms() * 4) blocks = (long long)num_sms() * 4;
   if (KH == 3)
-    XMC_ACT(act_f32, conv_c3_out_kernel<3, T><<<(unsigned)ceil_div_ll(P, 128), 128, smem, (cudaStream_t)stream>>>(
+    XMC_ACT(act_f32, conv_c3_out_kernel<3, T><<<(unsigned)blocks, 128, smem, (cudaStream_t)stream>>>(
                          (const T*)x, (const bf16*)w, ldw, act_f32, bias, N, H, W, Cin, mode, accumulate, y, (T*)y_bf16));
   else
-    XMC_ACT(act_f32, conv_c3_out_kernel<1, T><<<(unsigned)ceil_div_ll(P, 128), 128, smem, (cudaStream_t)stream>>>(
+    XMC_ACT(act_f32, conv_c3_out_kernel<1, T><<<(unsigned)blocks, 128, smem, (cudaStream_t)stream>>>(
                          (const T*)x, (const bf16*)w, ldw, act_f32, bias, N, H, W, Cin, mode, accumulate, y, (T*)y_bf16));
   XMC_LAUNCH_CHECK();
   return XMC_OK;
