@@ -177,3 +177,44 @@ def test_pool_fused_conv_equals_conv_then_dsample(N, H, C, Cout, dtype):
   print(f"\\n[pool-fused {dtype} N{N} H{H} C{C}] fwd {e_fwd:.2e} dx {e_dx:.2e} dw {e_dw:.2e}")
   t_fwd, t_bwd = (2e-5, 1e-4) if fp32 else (5e-3, 1e-2)
   assert e_fwd < t_fwd and e_dx < t_bwd and e_dw < t_bwd
+
+
+@gpu
+@pytest.mark.parametrize("mode,N,H,Ca,Cb", [
+    # plain 3x3: tg = 4 with one A slab (Ca <= 64); tg = 3 (96 -> 96: three groups of three taps); tg = 2 at BN = 192
+    # (five groups, the last with a single tap); BN = 256 stays ungrouped; ragged maps (partial pixel chunks)
+    (0, 3, 16, 48, 64), (0, 2, 16, 96, 96), (0, 2, 8, 192, 192), (0, 2, 8, 160, 176), (0, 1, 8, 64, 256),
+    (0, 3, 12, 96, 32), (0, 37, 16, 96, 96),
+    # sub-pixel parity taps: groups of four (per (a, b)) and of two (per (a, dh, b))
+    (1, 2, 8, 64, 96), (1, 2, 8, 192, 192), (1, 3, 6, 96, 48),
+    # pool-fused taps
+    (2, 2, 8, 96, 96), (2, 2, 8, 192, 192), (2, 3, 6, 64, 128)])
+def test_wgrad_tap_groups_match_oracle(mode, N, H, Ca, Cb):
+  """gemm_wgrad_kernel's tap groups (several taps per work item sharing one B chunk, see plan_wgrad) in all three
+  tap geometries, against the oracle's autograd: plain conv3x3 (ops.py wgrad), the sub-pixel form (weight gradient of
+  conv3x3(upsample2(x)), common.py:148-157) and the pool-fused form (dsample(conv3x3(x)), common.py:66-78). 1e-4 rel
+  on identical bf16 operands; the K split (N = 37) goes through the workspace and the fixed-order second stage."""
+  from xmcgan_image_generation_b200 import ops
+  torch.manual_seed(mode * 1000 + Ca + Cb + H)
+  q = lambda t: t.to(torch.bfloat16).float()
+  kern = (torch.randn(3, 3, Ca, Cb) * 0.05).requires_grad_(True)
+  if mode == 0:
+    x, dy = q(torch.randn(N, H, H, Ca)), q(torch.randn(N, H, H, Cb) * 0.1)
+    y = orc.conv2d(x, kern, None, orc.FP32, round_out=False)
+  elif mode == 1:
+    x, dy = q(torch.randn(N, H, H, Ca)), q(torch.randn(N, 2 * H, 2 * H, Cb) * 0.1)
+    y = orc.conv2d(orc.upsample(x), kern, None, orc.FP32, round_out=False)
+  else:
+    x, dy = q(torch.randn(N, 2 * H, 2 * H, Ca)), q(torch.randn(N, H, H, Cb) * 0.1)
+    y = orc.dsample(orc.conv2d(x, kern, None, orc.FP32, round_out=False))
+  (y * dy).sum().backward()
+  dw = torch.zeros(9 * Ca * Cb, device="cuda")
+  ops.wgrad(x.cuda().to(torch.bfloat16), dy.cuda().to(torch.bfloat16), 3, dw, out_mode=0, ld_out=Cb, tap_stride=Ca * Cb,
+            alpha=0.25 if mode == 2 else 1.0, subpixel=mode)
+  err = helpers.rel(dw.view(3, 3, Ca, Cb), kern.grad)
+  assert err < 1e-4, err
+  # accumulation into a non-zero destination, bit-identical on a second run
+  dw2 = torch.zeros(9 * Ca * Cb, device="cuda")
+  ops.wgrad(x.cuda().to(torch.bfloat16), dy.cuda().to(torch.bfloat16), 3, dw2, out_mode=0, ld_out=Cb,
+            tap_stride=Ca * Cb, alpha=0.25 if mode == 2 else 1.0, subpixel=mode)
+  assert torch.equal(dw, dw2)
