@@ -9,6 +9,13 @@ dtype.name, C-order bytes))), numpy scalars are ExtType(3, same tuple). State di
 "ema_params"}; a flax.optim.Optimizer serialises as {"target": params, "state": {"step": int32, "param_states": the
 params tree with leaves {"grad_ema", "grad_sq_ema"}}} (flax/optim/base.py, flax/optim/adam.py).
 
+Direction: a `ckpt-N.flax` written by the reference restores here; a directory written HERE holds only the
+`ckpt-N.flax` files — the reference's clu.checkpoint locates checkpoints through tf.train.CheckpointManager (the
+`checkpoint` state file + `ckpt-N.index/.data`), which are not written, so the reference's restore_or_initialize does
+not see it unless pointed at the file (flax.serialization.from_bytes on its bytes works: same state dict). The
+top-level `step` is written as an int32 array, the reference's initial TrainState.step is a Python int: restores
+identically, not byte-identical.
+
 Pure host code (numpy + msgpack): moves state between HBM buffers and files, never on the step path. PARITY UNPINNED by
 upstream: the reference ships no checkpoint fixture; tests pin the byte layout of a small tree by hand."""
 import os
