@@ -168,3 +168,49 @@ def test_bench_algorithmic_work_matches_survey():
   b = bench.synth_batch(4, cfg, 1)
   assert b["image"].shape == (4, 256, 256, 3) and b["max_len"].min() >= 3 and b["max_len"].max() <= 17
   assert torch.allclose(b["sentence_embedding"], b["embedding"].sum(1) / b["max_len"])
+
+
+def test_wgrad_planner_accepts_every_layer_shape_and_bounds_its_workspace():
+  """plan_wgrad (K split, tap groups, ring depth) through its CPU-callable face xmc_conv2d_wgrad_workspace_bytes: every
+  weight-gradient shape of the BASELINE configuration (gf = df = 96, B = 56 / 2B = 112, 128 px) in its three tap
+  geometries plans without error, a workspace exists exactly when an output element has several producers (the
+  sub-pixel / pool-fused forms always, plain taps only with a K split), holds a whole number of partial weight
+  tensors, and stays below 256 MB (the cost model charges the round trip, so wide layers are not split)."""
+  L = _lib.lib()
+
+  def plan(N, H, Ca, Cb, sub=0, k=3):
+    d = _lib.WgradDesc()
+    d.N, d.H, d.W, d.Ca, d.Cb, d.ldA, d.ldB = N, H, H, Ca, Cb, Ca, Cb
+    d.KH = d.KW = k
+    d.pad_h = d.pad_w = k // 2
+    d.out_mode, d.ldOut, d.out_tap_stride, d.alpha, d.subpixel = 0, Cb, Ca * Cb, 1.0, sub
+    need = ctypes.c_longlong(-1)
+    assert L.xmc_conv2d_wgrad_workspace_bytes(ctypes.byref(d), ctypes.byref(need)) == 0, (N, H, Ca, Cb, sub)
+    return need.value
+
+  chans = [(96, 96), (96, 192), (192, 192), (192, 384), (384, 384), (384, 768), (768, 768), (768, 1536), (1536, 1536)]
+  for N in (56, 112):
+    for ca, cb in chans:
+      for H in (4, 8, 16, 32, 64, 128):
+        if H * H * N * max(ca, cb) > 112 * 128 * 128 * 96:
+          continue
+        for sub in (0, 1, 2):
+          need = plan(N, H, ca, cb, sub)
+          taps = 16 if sub else 9
+          per_split = 4 * taps * ca * cb
+          assert need % per_split == 0 and need <= 256 << 20, (N, H, ca, cb, sub, need)
+          if sub:
+            assert need >= per_split
+  # a 1x1 conv of few pixels has one producer per element: no workspace
+  assert plan(2, 4, 64, 64, 0, k=1) == 0
+  # channel counts that are not multiples of 8 are rejected, not mis-planned
+  d = _lib.WgradDesc()
+  d.N, d.H, d.W, d.Ca, d.Cb, d.ldA, d.ldB, d.KH, d.KW = 1, 8, 8, 12, 16, 16, 16, 3, 3
+  need = ctypes.c_longlong(0)
+  assert L.xmc_conv2d_wgrad_workspace_bytes(ctypes.byref(d), ctypes.byref(need)) == -1
+
+
+def test_sm_limit_switch_is_a_plain_setter():
+  """xmc_set_sm_limit caps the persistent GEMM grids (host-side state, no GPU needed to set or clear it)."""
+  L = _lib.lib()
+  assert L.xmc_set_sm_limit(132) == 0 and L.xmc_set_sm_limit(0) == 0 and L.xmc_set_sm_limit(-5) == 0
