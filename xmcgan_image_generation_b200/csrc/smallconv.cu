@@ -32,6 +32,8 @@ __device__ __forceinline__ float weight_at(const bf16* w, int ldw, int row, int 
 // Each thread computes 4 horizontally adjacent pixels x 8 channels at a time: the 3x6x3 input window lives in
 // registers, every weight read from shared memory (one LDS.128 broadcast per 4 weights) feeds 4 FMAs.
 constexpr int kPx = 4;
+constexpr int kPxIn = 4;   // conv_c3_in: pixels per thread. ncu (r02_c3in): issue slots 55 % busy, 40 % of the stalls wait on the
+                           // weight LDS.128 stream; 2 (more warps) and 8 (fewer LDS per FFMA, 3 blocks per SM) were no faster
 template <int KS, typename T>
 __global__ void __launch_bounds__(128)
 conv_c3_in_kernel(const T* __restrict__ x, const bf16* __restrict__ w, int ldw, int wsplit,
@@ -47,16 +49,16 @@ conv_c3_in_kernel(const T* __restrict__ x, const bf16* __restrict__ w, int ldw, 
   for (int t = threadIdx.x; t < Cout; t += blockDim.x) bs[t] = bias ? bias[t] : 0.f;
   __syncthreads();
   // persistent blocks (a few per SM): the weight staging above is paid once per block, not once per 512 pixels
-  const int wq4 = (W + kPx - 1) / kPx;
+  const int wq4 = (W + kPxIn - 1) / kPxIn;
   const long long groups = (long long)N * H * wq4;
   for (long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x; gidx < groups;
        gidx += (long long)gridDim.x * blockDim.x) {
   const int wg = gidx % wq4;
   const int hq = (gidx / wq4) % H;
   const long long n = gidx / ((long long)wq4 * H);
-  const int w0 = wg * kPx;
+  const int w0 = wg * kPxIn;
   constexpr int ph = KH / 2, pw = KW / 2;
-  constexpr int cols = kPx + KW - 1;
+  constexpr int cols = kPxIn + KW - 1;
   float win[KH * cols * kImgC];  // [kh][col][c]
 #pragma unroll
   for (int kh = 0; kh < KH; ++kh) {
@@ -72,9 +74,9 @@ conv_c3_in_kernel(const T* __restrict__ x, const bf16* __restrict__ w, int ldw, 
   }
   const long long pbase = (n * H + hq) * W + w0;
   for (int c0 = 0; c0 < Cout; c0 += 8) {
-    float acc[kPx][8];
+    float acc[kPxIn][8];
 #pragma unroll
-    for (int px = 0; px < kPx; ++px)
+    for (int px = 0; px < kPxIn; ++px)
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[px][i] = bs[c0 + i];
 #pragma unroll
@@ -87,14 +89,14 @@ conv_c3_in_kernel(const T* __restrict__ x, const bf16* __restrict__ w, int ldw, 
           const float4 wa = *reinterpret_cast<const float4*>(wp);
           const float4 wb = *reinterpret_cast<const float4*>(wp + 4);
 #pragma unroll
-          for (int px = 0; px < kPx; ++px) {
+          for (int px = 0; px < kPxIn; ++px) {
             const float v = win[(kh * cols + px + kw) * kImgC + c];
             acc[px][0] += v * wa.x; acc[px][1] += v * wa.y; acc[px][2] += v * wa.z; acc[px][3] += v * wa.w;
             acc[px][4] += v * wb.x; acc[px][5] += v * wb.y; acc[px][6] += v * wb.z; acc[px][7] += v * wb.w;
           }
         }
 #pragma unroll
-    for (int px = 0; px < kPx; ++px) {
+    for (int px = 0; px < kPxIn; ++px) {
       if (w0 + px < W) {
         if (relu) {
 #pragma unroll
@@ -435,7 +437,7 @@ extern "C" int xmc_conv_c3_in(const void* x, int act_f32, const void* w, int ldw
   const int K = KH * KW * kImgC;
   const size_t smem = (size_t)(Cout * K + Cout) * sizeof(float);
   if (smem > 48 * 1024) return XMC_EINVAL;
-  const long long P = (long long)N * H * ceil_div(W, kPx);
+  const long long P = (long long)N * H * ceil_div(W, kPxIn);
   if (KH != KW || (KH != 1 && KH != 3)) return XMC_EINVAL;
   // fp32 activations come with split-form weights ([row][tap][hi|hi|lo][3], see weight_at)
   long long blocks = ceil_div_ll(P, 128);
