@@ -1,5 +1,6 @@
 // Small device helpers: 16-byte bf16x8 vector load/store, warp/block reductions.
 #pragma once
+#include "pdl.cuh"
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>

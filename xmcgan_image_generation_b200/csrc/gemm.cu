@@ -386,6 +386,7 @@ gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  pdl_launch_dependents();   // programmatic dependent launch: the prologue below may overlap the previous kernel's tail
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar(s), 1);
@@ -405,6 +406,7 @@ gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();                // ... nothing in global memory is touched before the previous kernel has completed
 
   float* bias_s = reinterpret_cast<float*>(smem + kStages * kStageBytes + kBarBytes);
   if (p.bias_smem && warp >= 2) {
@@ -598,6 +600,7 @@ conv3x3_resident_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     for (int s = 0; s < kResStages; ++s) {
       mbar_init(full_bar(s), 1);
@@ -618,6 +621,7 @@ conv3x3_resident_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
 
   float* bias_s = reinterpret_cast<float*>(bar_ptr + kBarBytes);
   if (p.bias_smem && warp >= 2) {
@@ -770,6 +774,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  pdl_launch_dependents();
   // A pixel chunk can hold fewer than 64 pixels (tiny tensors); rows the TMA never writes must read as zero
   // because they are part of the reduction dimension.
   if (p.slab_bytes < 8192) {
@@ -796,6 +801,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
   // A slab slot: 64 pixels x 128 B, or the 66-pixel halo chunk of tap3 mode rounded up to the 1024 B swizzle repeat
   const uint32_t a_slab = p.tap3 ? 9216u : 8192u;
   const uint32_t acc_cols = (uint32_t)((p.BN + 31) / 32) * 32u;  // tap3: column pitch of the three kw accumulators
@@ -1100,6 +1106,8 @@ struct WgradReduceParams {
 };
 
 __global__ void wgrad_reduce_kernel(const WgradReduceParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int cb4 = p.Cb >> 2;
   const long long total = (long long)p.nbatch * p.dst_taps * p.Ca * cb4;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -1367,7 +1375,8 @@ extern "C" int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* w
     XMC_CUDA_CHECK(ensure_smem_attr(kAttrRes));
     const int total = p.tiles_w * (d->H / 2) * d->N;
     const int grid = total < grid_sms() ? total : grid_sms();
-    conv3x3_resident_kernel<<<grid, kThreadsFwd, kSmemRes, (cudaStream_t)stream>>>(tmA, tmB, tmB2, p);
+    XMC_CUDA_CHECK(launch_pdl(conv3x3_resident_kernel, dim3(grid), dim3(kThreadsFwd), kSmemRes, (cudaStream_t)stream, tmA,
+                              tmB, tmB2, p));
     XMC_LAUNCH_CHECK();
     return XMC_OK;
   }
@@ -1406,13 +1415,17 @@ extern "C" int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* w
   const bool lean = lean_mode && p.bias_smem && !mask && d->alpha == 1.f && d->out_dtype == 0 && p.vec_ok == 2 &&
                     (d->Cout % 16) == 0 && (!residual || al32p(residual));
   if (f32io)
-    gemm_fwd_kernel<3><<<grid, 64 + 128 * FwdParts<3>::v, kSmemFwd, (cudaStream_t)stream>>>(tmA, tmB, p);
+    XMC_CUDA_CHECK(launch_pdl(gemm_fwd_kernel<3>, dim3(grid), dim3(64 + 128 * FwdParts<3>::v), kSmemFwd,
+                              (cudaStream_t)stream, tmA, tmB, p));
   else if (lean && !residual)
-    gemm_fwd_kernel<1><<<grid, kThreadsFwd, kSmemFwd, (cudaStream_t)stream>>>(tmA, tmB, p);
+    XMC_CUDA_CHECK(launch_pdl(gemm_fwd_kernel<1>, dim3(grid), dim3(kThreadsFwd), kSmemFwd, (cudaStream_t)stream, tmA, tmB,
+                              p));
   else if (lean)
-    gemm_fwd_kernel<2><<<grid, kThreadsFwd, kSmemFwd, (cudaStream_t)stream>>>(tmA, tmB, p);
+    XMC_CUDA_CHECK(launch_pdl(gemm_fwd_kernel<2>, dim3(grid), dim3(kThreadsFwd), kSmemFwd, (cudaStream_t)stream, tmA, tmB,
+                              p));
   else
-    gemm_fwd_kernel<0><<<grid, kThreadsFwd, kSmemFwd, (cudaStream_t)stream>>>(tmA, tmB, p);
+    XMC_CUDA_CHECK(launch_pdl(gemm_fwd_kernel<0>, dim3(grid), dim3(kThreadsFwd), kSmemFwd, (cudaStream_t)stream, tmA, tmB,
+                              p));
   XMC_LAUNCH_CHECK();
   return XMC_OK;
 }
@@ -1591,7 +1604,7 @@ extern "C" int xmc_conv2d_wgrad(const XmcWgradDesc* d, const void* xa, const voi
   }
   XMC_CUDA_CHECK(ensure_smem_attr(kAttrWgrad));
   const int grid = p.total_items < grid_sms() ? p.total_items : grid_sms();
-  gemm_wgrad_kernel<<<grid, kThreads, kSmemWgrad, (cudaStream_t)stream>>>(tmA, tmB, p);
+  XMC_CUDA_CHECK(launch_pdl(gemm_wgrad_kernel, dim3(grid), dim3(kThreads), kSmemWgrad, (cudaStream_t)stream, tmA, tmB, p));
   XMC_LAUNCH_CHECK();
   if (use_ws) {
     WgradReduceParams r;
@@ -1605,7 +1618,7 @@ extern "C" int xmc_conv2d_wgrad(const XmcWgradDesc* d, const void* xa, const voi
     long long blocks = ceil_div_ll(total, 256);
     const long long cap = (long long)num_sms() * 8;
     if (blocks > cap) blocks = cap;
-    wgrad_reduce_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(r);
+    XMC_CUDA_CHECK(launch_pdl(wgrad_reduce_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, r));
     XMC_LAUNCH_CHECK();
   }
   return XMC_OK;

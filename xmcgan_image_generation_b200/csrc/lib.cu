@@ -1,6 +1,7 @@
 // Library-level plumbing of libxmc.so: error strings, device queries.
 #include <atomic>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include "common.h"
 
@@ -37,6 +38,11 @@ static std::atomic<int> g_sm_limit{0};
 int grid_sms() {
   const int n = num_sms(), l = g_sm_limit.load(std::memory_order_relaxed);
   return (l > 0 && l < n) ? l : n;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("XMC_PDL"); return e ? atoi(e) != 0 : true; }();
+  return on;
 }
 
 }  // namespace xmc
