@@ -84,6 +84,7 @@ struct WgradParams {
   int groups;           // items per (batch, output tile): tap groups (tg > 1), filter rows (tap3) or taps
   int a_slabs;          // 64-channel slabs of A loaded per tap (1 when Ca <= 64)
   int stages;           // depth of the shared-memory ring (192 KB / stage_bytes, at most kWgradStagesMax)
+  int merge_a, merge_b; // 1: the 64-channel slabs of a tap's A chunk / of the B chunk arrive as ONE 5-D TMA box
   uint32_t stage_bytes;
   uint32_t slab_bytes;  // bytes one TMA box writes
   uint32_t idesc;
@@ -893,12 +894,20 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (k2 < nt_item) {
               const int cw = as * w0 + (int)((awp >> (8 * k2)) & 0xff) - 8;
               const int ch = as * h0 + (int)((ahp >> (8 * k2)) & 0xff) - 8;
-              tma_load_4d(sa + k2 * a_tap_bytes, &tmA, fb, m0, cw, ch, n0);
-              if (two_slabs) tma_load_4d(sa + k2 * a_tap_bytes + a_stride, &tmA, fb, m0 + 64, cw, ch, n0);
+              if (p.merge_a) {   // both slabs of the tap in one box (last coordinate = first slab)
+                tma_load_5d(sa + k2 * a_tap_bytes, &tmA, fb, 0, cw, ch, n0, m0 >> 6);
+              } else {
+                tma_load_4d(sa + k2 * a_tap_bytes, &tmA, fb, m0, cw, ch, n0);
+                if (two_slabs) tma_load_4d(sa + k2 * a_tap_bytes + a_stride, &tmA, fb, m0 + 64, cw, ch, n0);
+              }
             }
           }
-          for (int s2 = 0; s2 < p.nslabs; ++s2)
-            tma_load_4d(sa + b_off + s2 * 8192, &tmB, fb, n_off + s2 * 64, bs * w0 + bw, bs * h0 + bh, n0);
+          if (p.merge_b) {
+            tma_load_5d(sa + b_off, &tmB, fb, 0, bs * w0 + bw, bs * h0 + bh, n0, n_off >> 6);
+          } else {
+            for (int s2 = 0; s2 < p.nslabs; ++s2)
+              tma_load_4d(sa + b_off + s2 * 8192, &tmB, fb, n_off + s2 * 64, bs * w0 + bw, bs * h0 + bh, n0);
+          }
           if (++stage == nstages) { stage = 0; phase ^= 1; }
           if (++iw == p.chunks_w) {
             iw = 0;
@@ -1522,6 +1531,15 @@ static int plan_wgrad(const XmcWgradDesc* d, WgradParams& p) {
   p.total_items = base_ctas * p.ksplit;
   p.Ca = d->Ca; p.Cb = d->Cb; p.batched = d->batched;
   p.slab_bytes = (uint32_t)(64 * p.tw * p.th * p.tn * 2);
+  // One box per operand instead of one per 64-channel slab: the TMA unit spends a fixed ~100 cycles per box on top of
+  // ~128 B/clk (an 8 KB slab box: ~50 B/clk, which is where the narrow-slab loads of this kernel sat). A 5-D tensor map
+  // whose LAST dimension walks the slabs (stride 128 B) lands them slab-major in shared memory, exactly the layout the
+  // MN-major descriptors expect. Needs whole slabs in global memory (channels % 64 == 0), full 64-pixel chunks (the slab
+  // pitch in shared memory is then the 8 KB of a box row block) and, for B, tiles that start on a slab boundary.
+  static const int merge_mode = [] { const char* e = getenv("XMC_WGRAD_MERGE"); return e ? atoi(e) : 1; }();
+  p.merge_a = (merge_mode && !p.tap3 && p.a_slabs == 2 && d->Ca % 64 == 0 && p.slab_bytes == 8192 && d->pitchWA <= 0) ? 1 : 0;
+  p.merge_b = (merge_mode && p.nslabs > 1 && d->Cb % 64 == 0 && p.slab_bytes == 8192 &&
+               (p.n_tiles == 1 || p.BN % 64 == 0)) ? 1 : 0;
   p.idesc = make_idesc_bf16(128, p.BN, 1, 1);
   p.out_mode = d->out_mode; p.ldOut = d->ldOut;
   p.out_tap_stride = d->out_tap_stride; p.out_batch_stride = d->out_batch_stride;
@@ -1587,7 +1605,16 @@ extern "C" int xmc_conv2d_wgrad(const XmcWgradDesc* d, const void* xa, const voi
                        (uint64_t)d->ldA * 2 * d->W * as * d->H * as};
     uint32_t box[4] = {64, (uint32_t)((p.tap3 ? p.tw + 2 : p.tw) * as), (uint32_t)(p.th * as), (uint32_t)p.tn};
     uint32_t est[4] = {1, (uint32_t)as, (uint32_t)as, 1};
-    int r = make_tmap(&tmA, xa, 4, dims, str, box, est);
+    int r;
+    if (p.merge_a) {   // (64 channels, W, H, N, slab): the slab dimension last, 128 bytes apart
+      uint64_t dims5[5] = {64, dims[1], dims[2], dims[3], (uint64_t)(d->Ca / 64)};
+      uint64_t str5[4] = {str[0], str[1], str[2], 128};
+      uint32_t box5[5] = {64, box[1], box[2], box[3], 2};
+      uint32_t est5[5] = {1, est[1], est[2], 1, 1};
+      r = make_tmap(&tmA, xa, 5, dims5, str5, box5, est5);
+    } else {
+      r = make_tmap(&tmA, xa, 4, dims, str, box, est);
+    }
     if (r) return r;
   }
   {
@@ -1599,7 +1626,16 @@ extern "C" int xmc_conv2d_wgrad(const XmcWgradDesc* d, const void* xa, const voi
                        (uint64_t)d->ldB * 2 * d->W * bs * d->H * bs};
     uint32_t box[4] = {64, (uint32_t)(p.tw * bs), (uint32_t)(p.th * bs), (uint32_t)p.tn};
     uint32_t est[4] = {1, (uint32_t)bs, (uint32_t)bs, 1};
-    int r = make_tmap(&tmB, xb, 4, dims, str, box, est);
+    int r;
+    if (p.merge_b) {
+      uint64_t dims5[5] = {64, dims[1], dims[2], dims[3], (uint64_t)(d->Cb / 64)};
+      uint64_t str5[4] = {str[0], str[1], str[2], 128};
+      uint32_t box5[5] = {64, box[1], box[2], box[3], (uint32_t)p.nslabs};
+      uint32_t est5[5] = {1, est[1], est[2], 1, 1};
+      r = make_tmap(&tmB, xb, 5, dims5, str5, box5, est5);
+    } else {
+      r = make_tmap(&tmB, xb, 4, dims, str, box, est);
+    }
     if (r) return r;
   }
   XMC_CUDA_CHECK(ensure_smem_attr(kAttrWgrad));
