@@ -84,6 +84,7 @@ struct WgradParams {
   int groups;           // items per (batch, output tile): tap groups (tg > 1), filter rows (tap3) or taps
   int a_slabs;          // 64-channel slabs of A loaded per tap (1 when Ca <= 64)
   int stages;           // depth of the shared-memory ring (192 KB / stage_bytes, at most kWgradStagesMax)
+  int debug;            // profiling aid (XMC_WGRAD_DEBUG): 1 = no MMAs (fetch pipeline alone), 2 = no loads (MMA pipeline alone)
   int merge_a, merge_b; // 1: the 64-channel slabs of a tap's A chunk / of the B chunk arrive as ONE 5-D TMA box
   uint32_t stage_bytes;
   uint32_t slab_bytes;  // bytes one TMA box writes
@@ -886,12 +887,12 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int j = j0; j < j1; ++j) {
           const int w0 = iw * p.tw, h0 = ih * p.th, n0 = p.batched ? bz : in * p.tn;
           mbar_wait(empty_bar(stage), phase ^ 1);
-          mbar_arrive_expect_tx(full_bar(stage), tx);
+          mbar_arrive_expect_tx(full_bar(stage), p.debug == 2 ? 0u : tx);
           const uint32_t sa = sbase + stage * p.stage_bytes;
           const uint32_t fb = full_bar(stage);
 #pragma unroll
           for (int k2 = 0; k2 < 4; ++k2) {
-            if (k2 < nt_item) {
+            if (k2 < nt_item && p.debug != 2) {
               const int cw = as * w0 + (int)((awp >> (8 * k2)) & 0xff) - 8;
               const int ch = as * h0 + (int)((ahp >> (8 * k2)) & 0xff) - 8;
               if (p.merge_a) {   // both slabs of the tap in one box (last coordinate = first slab)
@@ -902,7 +903,8 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               }
             }
           }
-          if (p.merge_b) {
+          if (p.debug == 2) {
+          } else if (p.merge_b) {
             tma_load_5d(sa + b_off, &tmB, fb, 0, bs * w0 + bw, bs * h0 + bh, n0, n_off >> 6);
           } else {
             for (int s2 = 0; s2 < p.nslabs; ++s2)
@@ -936,7 +938,8 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (elect_one()) {
           const uint32_t sa = sbase + stage * p.stage_bytes;
           // MN-major SW128: LBO = byte distance between 64-channel slabs, SBO = distance between 8-pixel groups.
-          if (p.tap3) {
+          if (p.debug == 1 && j > j0) {
+          } else if (p.tap3) {
             const uint64_t adesc = make_smem_desc(sa, a_slab, 1024);
             const uint64_t bdesc = make_smem_desc(sa + 2 * a_slab, 8192, 1024);
             // tap kw multiplies pixels kw .. kw+63 of the 66-pixel halo chunk (one pixel = one 128 B row; the start
@@ -1537,6 +1540,8 @@ static int plan_wgrad(const XmcWgradDesc* d, WgradParams& p) {
   // MN-major descriptors expect. Needs whole slabs in global memory (channels % 64 == 0), full 64-pixel chunks (the slab
   // pitch in shared memory is then the 8 KB of a box row block) and, for B, tiles that start on a slab boundary.
   static const int merge_mode = [] { const char* e = getenv("XMC_WGRAD_MERGE"); return e ? atoi(e) : 1; }();
+  static const int debug_mode = [] { const char* e = getenv("XMC_WGRAD_DEBUG"); return e ? atoi(e) : 0; }();
+  p.debug = debug_mode;
   p.merge_a = (merge_mode && !p.tap3 && p.a_slabs == 2 && d->Ca % 64 == 0 && p.slab_bytes == 8192 && d->pitchWA <= 0) ? 1 : 0;
   p.merge_b = (merge_mode && p.nslabs > 1 && d->Cb % 64 == 0 && p.slab_bytes == 8192 &&
                (p.n_tiles == 1 || p.BN % 64 == 0)) ? 1 : 0;
