@@ -108,13 +108,14 @@ typedef struct {
   int Cb, ldB;             /* xb channels (GEMM N) and pixel pitch */
   int KH, KW, pad_h, pad_w;
   int batched;             /* 1: one output matrix per image n (no reduction over n) */
-  int out_mode;            /* 0 fp32 accumulate (dw += ..., deterministic), 1 fp32 store, 2 bf16 store (1,2: one K split) */
+  int out_mode;            /* 0 fp32 accumulate (dw += ...), 1 fp32 store (dw = ...; saves the read of dw), 2 bf16 store
+                            * (one K split). 0 and 1 are deterministic and take every decomposition (K split, tap groups) */
   int ldOut;
   long long out_tap_stride, out_batch_stride;
   float alpha;
   /* 1: weight gradient of conv3x3(nearest_upsample2x(xa)): xa is the low-resolution [N,H,W,Ca] input, xb the
    * [N,2H,2W,Cb] output gradient (read with stride 2, one parity per tap); the 16 parity/tap products are added to
-   * the 9 taps of dw ([3][3][Ca][Cb]) they belong to. KH=KW=3, out_mode 0.
+   * the 9 taps of dw ([3][3][Ca][Cb]) they belong to. KH=KW=3, out_mode 0 or 1.
    * 2: weight gradient of dsample(conv3x3(xa)) (pool-fused form, xmc_poolconv_prep): xa is the full-resolution
    * [N,2H,2W,Ca] input (read with stride 2, one 4x4 tap per work item), xb the LOW-resolution [N,H,W,Cb] output
    * gradient; the 16 tap products are folded into the 9 taps of dw (pass alpha = 0.25 for the mean). */

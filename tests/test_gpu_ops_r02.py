@@ -218,3 +218,8 @@ def test_wgrad_tap_groups_match_oracle(mode, N, H, Ca, Cb):
   ops.wgrad(x.cuda().to(torch.bfloat16), dy.cuda().to(torch.bfloat16), 3, dw2, out_mode=0, ld_out=Cb,
             tap_stride=Ca * Cb, alpha=0.25 if mode == 2 else 1.0, subpixel=mode)
   assert torch.equal(dw, dw2)
+  # store mode (out_mode 1: dw = ..., no read of the destination) overwrites whatever the buffer held, same bits
+  dw3 = torch.full((9 * Ca * Cb,), 123.0, device="cuda")
+  ops.wgrad(x.cuda().to(torch.bfloat16), dy.cuda().to(torch.bfloat16), 3, dw3, out_mode=1, ld_out=Cb,
+            tap_stride=Ca * Cb, alpha=0.25 if mode == 2 else 1.0, subpixel=mode)
+  assert torch.equal(dw, dw3)

@@ -1114,6 +1114,7 @@ struct WgradReduceParams {
   const float* ws;
   float* out;
   int ksplit, nbatch, src_taps, dst_taps, Ca, Cb, ldOut, subpixel, vec_ok;
+  int store;   // 1: out = sum (XmcWgradDesc.out_mode 1), 0: out += sum
   long long ws_split_stride, out_tap_stride, out_batch_stride;
 };
 
@@ -1158,7 +1159,13 @@ __global__ void wgrad_reduce_kernel(const WgradReduceParams p) {
     }
     float* o = p.out + (long long)bz * p.out_batch_stride + (long long)t * p.out_tap_stride + (long long)m * p.ldOut +
                c4 * 4;
-    if (p.vec_ok) {
+    if (p.store) {
+      if (p.vec_ok) {
+        *reinterpret_cast<float4*>(o) = acc;
+      } else {
+        o[0] = acc.x; o[1] = acc.y; o[2] = acc.z; o[3] = acc.w;
+      }
+    } else if (p.vec_ok) {
       float4 cur = *reinterpret_cast<float4*>(o);
       cur.x += acc.x; cur.y += acc.y; cur.z += acc.z; cur.w += acc.w;
       *reinterpret_cast<float4*>(o) = cur;
@@ -1461,14 +1468,17 @@ static int plan_wgrad(const XmcWgradDesc* d, WgradParams& p) {
   p.n_tiles = ceil_div(d->Cb, p.BN);
   p.nslabs = ceil_div(p.BN, 64);
   const int m_tiles = ceil_div(d->Ca, 128);
-  if (d->subpixel && (d->KH != 3 || d->KW != 3 || d->out_mode != 0 || d->batched || d->subpixel > 2)) return XMC_EINVAL;
+  // fp32 destinations (out_mode 0: accumulate, 1: store) take every decomposition below; bf16 stores stay one item per
+  // output element
+  const bool f32_out = d->out_mode == 0 || d->out_mode == 1;
+  if (d->subpixel && (d->KH != 3 || d->KW != 3 || !f32_out || d->batched || d->subpixel > 2)) return XMC_EINVAL;
   // tap3: for 3x3 kernels on rows of >= 64 pixels whose three kw accumulators fit TMEM (Cb <= 160), a work item is a
   // filter ROW: one 66-pixel halo chunk of xa and one chunk of xb feed three taps (3x less operand traffic; these
   // narrow-channel layers are L2 -> SM bandwidth bound). XMC_WGRAD_TAP3=0 switches it off (debugging aid, read once per
   // process).
   static const int tap3_mode = [] { const char* e = getenv("XMC_WGRAD_TAP3"); return e ? atoi(e) : 1; }();
   p.tap3 = (tap3_mode && d->KH == 3 && d->KW == 3 && d->pad_h == 1 && d->pad_w == 1 && !d->subpixel && !d->batched &&
-            d->pitchWA <= 0 && d->out_mode == 0 && d->W >= 64 && p.n_tiles == 1 && 3 * (((p.BN + 31) / 32) * 32) <= 512)
+            d->pitchWA <= 0 && f32_out && d->W >= 64 && p.n_tiles == 1 && 3 * (((p.BN + 31) / 32) * 32) <= 512)
                ? 1 : 0;
   const int taps = d->subpixel ? 16 : d->KH * d->KW;
   p.subpixel = d->subpixel;
@@ -1486,7 +1496,7 @@ static int plan_wgrad(const XmcWgradDesc* d, WgradParams& p) {
   // no longer overlapped). XMC_WGRAD_TG=1 switches the grouping off (debugging aid).
   static const int tg_max = [] { const char* e = getenv("XMC_WGRAD_TG"); return e ? atoi(e) : 4; }();
   p.tg = 1;
-  if (!p.tap3 && d->out_mode == 0 && taps > 1 && p.BN <= 192) {
+  if (!p.tap3 && f32_out && taps > 1 && p.BN <= 192) {
     const int tg_minst = p.BN <= 128 ? 3 : 4;   // ring stages a grouped item must keep
     for (int tg = 4; tg >= 2; --tg) {
       if (tg > tg_max || tg > taps || tg * acc_cols > 512) continue;
@@ -1503,7 +1513,7 @@ static int plan_wgrad(const XmcWgradDesc* d, WgradParams& p) {
   const int per_item = p.tap3 ? 3 : p.tg;   // accumulators (taps) an item computes
   const int base_ctas = m_tiles * p.n_tiles * p.groups * nbatch;
   int ksplit = 1;
-  if (d->out_mode == 0) {
+  if (f32_out) {
     // Split K (pixels) across CTAs with a small cost model (microseconds): tensor time = waves x chunks per CTA x
     // (four 128 x BN x 16 MMAs = 2 BN cycles per 64-pixel chunk and tap) + one epilogue per item, plus — as soon as
     // the reduction is split — the partial tiles' round trip through the workspace and the second-stage launch.
@@ -1558,7 +1568,7 @@ static int plan_wgrad(const XmcWgradDesc* d, WgradParams& p) {
 // A workspace is needed whenever an output element has more than one producer item: K split across CTAs, or the
 // sub-pixel parity taps (each destination tap sums four of them).
 static bool wgrad_needs_ws(const XmcWgradDesc* d, const WgradParams& p) {
-  return d->out_mode == 0 && (p.ksplit > 1 || d->subpixel);
+  return (d->out_mode == 0 || d->out_mode == 1) && (p.ksplit > 1 || d->subpixel);
 }
 
 extern "C" int xmc_conv2d_wgrad_workspace_bytes(const XmcWgradDesc* d, long long* bytes) {
@@ -1653,6 +1663,7 @@ extern "C" int xmc_conv2d_wgrad(const XmcWgradDesc* d, const void* xa, const voi
     r.ksplit = p.ksplit; r.nbatch = d->batched ? d->N : 1; r.src_taps = p.ws_taps;
     r.dst_taps = d->KH * d->KW; r.Ca = d->Ca; r.Cb = d->Cb; r.ldOut = d->ldOut; r.subpixel = p.subpixel;
     r.vec_ok = p.vec_ok;
+    r.store = d->out_mode == 1 ? 1 : 0;
     r.ws_split_stride = p.ws_split_stride; r.out_tap_stride = d->out_tap_stride;
     r.out_batch_stride = d->out_batch_stride;
     const long long total = (long long)r.nbatch * r.dst_taps * r.Ca * (r.Cb / 4);

@@ -501,7 +501,7 @@ class GeneratorEngine:
 
   # ------------------------------------------------------------------------------------------------------------
   def _conv_wgrad(self, rec, x_in, dy, grads):
-    ops.wgrad(x_in, dy, rec.kh, grads[rec.w_off:], out_mode=0, ld_out=rec.cout, tap_stride=rec.cin * rec.cout)
+    ops.wgrad(x_in, dy, rec.kh, grads[rec.w_off:], out_mode=1, ld_out=rec.cout, tap_stride=rec.cin * rec.cout)
     ops.colsum(dy, grads[rec.b_off:])
 
   def backward(self, ctx, d_img, params, grads):
@@ -558,7 +558,7 @@ class GeneratorEngine:
       dc1 = ops.bn_bwd(dh2, sv["c1"], sv["mr1"], gb, dgb, sv["Hc"], g1, b1, True, False, group=grp)
       # conv1 (Conv_0, sub-pixel form): weight gradient from the low-resolution input and the 2x gradient; input
       # gradient = 4x4 / stride-2 / pad-1 convolution over the gradient, directly at the input resolution
-      ops.wgrad(sv["u"], dc1, 3, grads[r0.w_off:], out_mode=0, ld_out=bcout, tap_stride=bcin * bcout, subpixel=True)
+      ops.wgrad(sv["u"], dc1, 3, grads[r0.w_off:], out_mode=1, ld_out=bcout, tap_stride=bcin * bcout, subpixel=True)
       ops.colsum(dc1, grads[r0.b_off:])
       _, vd_off = self.subpixel[(name, self.cpre + "_0")]
       du = ops.conv_fwd(dc1, self.arena[vd_off:], 4, bcin, ldb=16 * bcout * S_, stride=2, pad=1)
@@ -850,7 +850,7 @@ class DiscriminatorEngine:
 
   def _pooled_wgrad(self, rec, x, dout, grads):
     """Weight / bias gradient of _pooled_fwd: x full resolution, dout half resolution."""
-    ops.wgrad(x, dout, 3, grads[rec.w_off:], out_mode=0, ld_out=rec.cout, tap_stride=rec.cin * rec.cout, alpha=0.25,
+    ops.wgrad(x, dout, 3, grads[rec.w_off:], out_mode=1, ld_out=rec.cout, tap_stride=rec.cin * rec.cout, alpha=0.25,
               subpixel=2)
     ops.colsum(dout, grads[rec.b_off:])   # d/db of the mean of four copies of b = column sum of the pooled gradient
 
@@ -951,7 +951,7 @@ class DiscriminatorEngine:
 
   # ------------------------------------------------------------------------------------------------------------
   def _wgrad(self, rec, x_in, dy, grads, dy_low=None):
-    ops.wgrad(x_in, dy, rec.kh, grads[rec.w_off:], out_mode=0, ld_out=rec.cout, tap_stride=rec.cin * rec.cout)
+    ops.wgrad(x_in, dy, rec.kh, grads[rec.w_off:], out_mode=1, ld_out=rec.cout, tap_stride=rec.cin * rec.cout)
     # the bias gradient of a conv whose output is average-pooled equals the column sum of the pooled gradient
     ops.colsum(dy if dy_low is None else dy_low, grads[rec.b_off:])
 
