@@ -59,3 +59,54 @@ def test_two_rank_gradient_and_metric_mean():
   assert torch.allclose(m0, (l0 + l1) / 2, rtol=1e-6, atol=1e-8)
   assert not torch.allclose(l0, l1)  # different shards -> different local gradients
   assert torch.allclose(s0, s1)
+
+
+def _sliced_worker(rank, world, port, out):
+  os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  from xmcgan_image_generation_b200 import xmc_gan
+  n = 5000 + 4 * 37                      # a multiple of 4 (xmc_adam's granularity), not of the slice size
+  g = torch.Generator().manual_seed(11 + rank)
+  flat = torch.randn(n, generator=g)
+  local = flat.clone()
+  handles = xmc_gan._all_reduce_sliced(flat, 3)
+  # consecutive, non-overlapping slices on 1024-element boundaries that cover the buffer exactly once
+  assert handles[0][0] == 0 and handles[-1][1] == n
+  for (lo, hi, _), (lo2, _, _) in zip(handles[:-1], handles[1:]):
+    assert hi == lo2 and lo % 1024 == 0 and hi % 1024 == 0
+  for lo, hi, work in handles:
+    work.wait()
+  other = torch.randn(n, generator=torch.Generator().manual_seed(11 + (1 - rank)))
+  ok = torch.allclose(flat, local + other, atol=0, rtol=0)
+  # one replica: no handles at all (the caller then applies Adam in one call)
+  out[rank] = bool(ok)
+  dist.barrier()
+  dist.destroy_process_group()
+
+
+def test_sliced_all_reduce_covers_the_buffer_once():
+  """xmc_gan._all_reduce_sliced (the generator-gradient all-reduce issued in slices so that Adam of slice i can run
+  under the all-reduce of slice i+1): on two gloo ranks every element is summed exactly once, bit-exact."""
+  world, port = 2, _free_port()
+  out = mp.Manager().dict()
+  mp.spawn(_sliced_worker, args=(world, port, out), nprocs=world, join=True)
+  assert out[0] and out[1]
+
+
+def test_sm_reservation_bookkeeping():
+  """ops.reserve_sms / release_sms (SMs left to a concurrent collective): the window closes after the announced amount
+  of executed GEMM work or at release; pure host-side state on top of xmc_set_sm_limit."""
+  from xmcgan_image_generation_b200 import ops
+  ops.release_sms()
+  assert ops._RESERVE[0] == 0.0
+  ops.reserve_sms(16, 1.0)               # 1 TFLOP of GEMM work
+  assert ops._RESERVE[0] == 1e12
+  ops._spend(0.4e12)
+  assert ops._RESERVE[0] == 0.6e12
+  ops._spend(0.7e12)                     # past the window: released
+  assert ops._RESERVE[0] == 0.0
+  ops.reserve_sms(0, 1.0)                # n <= 0: nothing reserved
+  assert ops._RESERVE[0] == 0.0
+  ops.reserve_sms(8, 2.0)
+  ops.release_sms()
+  assert ops._RESERVE[0] == 0.0
