@@ -48,6 +48,7 @@ struct FwdParams {
   int strideH, strideW;
   int parities;  // 1, or 4: sub-pixel mode (nearest-2x-upsample fused into a 3x3 conv as four 2x2 convs)
   uint32_t stage_tx_bytes;
+  int debug;   // profiling aid (XMC_FWD_DEBUG): 1 = no MMAs (fetch pipeline alone), 2 = no loads (MMA + epilogue alone)
   uint32_t idesc;
   void* out;
   int out_dtype, ldOut;
@@ -461,12 +462,14 @@ gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           int ca = 0, in_part = 0;
           for (int c = 0; c < p.cchunks; ++c) {
             mbar_wait(empty_bar(stage), phase ^ 1);
-            mbar_arrive_expect_tx(full_bar(stage), p.stage_tx_bytes);
+            mbar_arrive_expect_tx(full_bar(stage), p.debug == 2 ? 0u : p.stage_tx_bytes);
             const uint32_t sa = sbase + stage * kStageBytes;
-            tma_load_4d(sa, &tmA, full_bar(stage), ca, w0 * p.strideW + kw - pad_w,
-                        h0 * p.strideH + kh - pad_h, n0);
-            tma_load_3d(sa + kABytes, &tmB, full_bar(stage), tap * p.C + c * 64, par * p.Cout + nt * p.BN,
-                        p.batched ? n0 : 0);
+            if (p.debug != 2) {
+              tma_load_4d(sa, &tmA, full_bar(stage), ca, w0 * p.strideW + kw - pad_w,
+                          h0 * p.strideH + kh - pad_h, n0);
+              tma_load_3d(sa + kABytes, &tmB, full_bar(stage), tap * p.C + c * 64, par * p.Cout + nt * p.BN,
+                          p.batched ? n0 : 0);
+            }
             if (++stage == kStages) { stage = 0; phase ^= 1; }
             // next chunk's channel offset; two-part operand: chunks walk [hi | lo | hi] of the stored [hi | lo]
             ca += 64;
@@ -503,7 +506,8 @@ gemm_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             // advance 16 K-elements = 32 bytes inside the 128B swizzle row: +2 in the (addr>>4) field
-            if (j < nmma) umma_bf16(d_tmem, adesc + 2 * j, bdesc + 2 * j, p.idesc, (k > 0 || j > 0) ? 1u : 0u);
+            if (j < nmma && !(p.debug == 1 && k > 0))
+              umma_bf16(d_tmem, adesc + 2 * j, bdesc + 2 * j, p.idesc, (k > 0 || j > 0) ? 1u : 0u);
           }
           umma_commit(empty_bar(stage));
           if (k == kiters - 1) umma_commit(tfull_bar(acc));
@@ -1321,6 +1325,8 @@ extern "C" int xmc_conv2d_fwd(const XmcConvDesc* d, const void* x, const void* w
   p.n_tiles = ceil_div(d->Cout, p.BN);
   p.idesc = make_idesc_bf16(128, p.BN, 0, 0);
   p.stage_tx_bytes = (uint32_t)(64 * p.tw * p.th * p.tn * 2 + 64 * p.BN * 2);
+  static const int fwd_debug = [] { const char* e = getenv("XMC_FWD_DEBUG"); return e ? atoi(e) : 0; }();
+  p.debug = fwd_debug;
   p.out = y; p.out_dtype = d->out_dtype; p.ldOut = d->ldOut;
   p.bias = bias; p.residual = residual; p.mask = mask;
   // fp32 activations: residual / mask are fp32 tensors and the output must be fp32 (the A operand is the bf16
