@@ -1,0 +1,175 @@
+"""Generates tests/golden/reference_libml.npz by EXECUTING THE REFERENCE'S OWN SOURCE for the loss / attention layer of
+the path (xmcgan/libml/losses.py, xmcgan/libml/attention_lib.py) and three host helpers (utils/image_utils.make_grid,
+utils/device_utils.get_device_groups, train_utils.split_input_dict) on fixed-seed inputs.
+
+JAX is not installable in this environment, so the reference modules are imported from /root/reference with a small
+numpy-backed stand-in for the handful of `jax` entry points they use (jnp.* = numpy.*, jax.nn.softmax / log_softmax /
+relu / one_hot, jax.lax.rsqrt, jax.scipy.special.logsumexp, jax.vmap over the leading axis, jax.tree_map over a dict,
+jax.device_count). Those functions are pure array arithmetic in float32, so numpy reproduces XLA-CPU's results up to
+summation order (~1e-7); everything else — the formulas, axes, masks, constants — is the reference's code, line for
+line. This is what pins `oracle/xmc_oracle.py` for these functions (tests/test_reference_golden.py); the networks,
+their backward and the optimiser need Flax and stay pinned by known answers only.
+
+Run in the build container only (reads /root/reference):  python -m tests.golden.make_reference_golden"""
+import ast
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+
+REF = "/root/reference"
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_libml.npz")
+
+
+def _jax_stand_in(device_count=8):
+  jnp = types.ModuleType("jax.numpy")
+  jnp.__dict__.update({k: getattr(np, k) for k in dir(np) if not k.startswith("_")})
+  jnp.ndarray = np.ndarray
+
+  def softmax(x, axis=-1):
+    e = np.exp(x - np.max(x, axis=axis, keepdims=True))
+    return e / np.sum(e, axis=axis, keepdims=True)
+
+  def log_softmax(x, axis=-1):
+    s = x - np.max(x, axis=axis, keepdims=True)
+    return s - np.log(np.sum(np.exp(s), axis=axis, keepdims=True))
+
+  nn = types.ModuleType("jax.nn")
+  nn.softmax, nn.log_softmax = softmax, log_softmax
+  nn.relu = lambda x: np.maximum(x, 0)
+  nn.one_hot = lambda idx, n: (np.asarray(idx)[..., None] == np.arange(n)).astype(np.float32)
+  lax = types.ModuleType("jax.lax")
+  lax.rsqrt = lambda x: (1.0 / np.sqrt(x)).astype(np.asarray(x).dtype)
+  special = types.ModuleType("jax.scipy.special")
+
+  def logsumexp(a, axis=None, keepdims=False):
+    m = np.max(a, axis=axis, keepdims=True)
+    r = m + np.log(np.sum(np.exp(a - m), axis=axis, keepdims=True))
+    return r if keepdims else np.squeeze(r, axis=axis)
+
+  special.logsumexp = logsumexp
+  jscipy = types.ModuleType("jax.scipy")
+  jscipy.special = special
+
+  def vmap(fn):
+    return lambda *args: np.stack([fn(*[a[i] for a in args]) for i in range(len(args[0]))])
+
+  jax = types.ModuleType("jax")
+  jax.numpy, jax.nn, jax.lax, jax.scipy, jax.vmap = jnp, nn, lax, jscipy, vmap
+  jax.tree_map = lambda fn, d: {k: fn(v) for k, v in d.items()}
+  jax.device_count = lambda: device_count
+  return {"jax": jax, "jax.numpy": jnp, "jax.nn": nn, "jax.lax": lax, "jax.scipy": jscipy,
+          "jax.scipy.special": special}
+
+
+def _load(name, path):
+  spec = importlib.util.spec_from_file_location(name, path)
+  mod = importlib.util.module_from_spec(spec)
+  sys.modules[name] = mod
+  spec.loader.exec_module(mod)
+  return mod
+
+
+def load_reference(device_count=8):
+  """(losses, attention_lib, image_utils, device_utils, split_input_dict) of the reference on the stand-in."""
+  shim = _jax_stand_in(device_count)
+  sys.modules.update(shim)
+  absl = types.ModuleType("absl")
+  absl.logging = types.SimpleNamespace(info=lambda *a, **k: None)
+  sys.modules.setdefault("absl", absl)
+  for pkg in ("xmcgan", "xmcgan.libml", "xmcgan.utils"):
+    sys.modules.setdefault(pkg, types.ModuleType(pkg))
+  losses = _load("xmcgan.libml.losses", f"{REF}/xmcgan/libml/losses.py")
+  sys.modules["xmcgan.libml"].losses = losses
+  attention_lib = _load("xmcgan.libml.attention_lib", f"{REF}/xmcgan/libml/attention_lib.py")
+  image_utils = _load("xmcgan.utils.image_utils", f"{REF}/xmcgan/utils/image_utils.py")
+  device_utils = _load("xmcgan.utils.device_utils", f"{REF}/xmcgan/utils/device_utils.py")
+  # train_utils.py imports flax / clu / tensorflow at module level: take the one pure function out of its source
+  tree = ast.parse(open(f"{REF}/xmcgan/train_utils.py").read())
+  fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "split_input_dict")
+  scope = {"jax": shim["jax"], "jnp": shim["jax.numpy"], "Dict": dict}
+  exec(compile(ast.Module(body=[fn], type_ignores=[]), "train_utils.py", "exec"), scope)
+  return losses, attention_lib, image_utils, device_utils, scope["split_input_dict"]
+
+
+def load_reference_fid():
+  """calculate_fid / _calculate_frechet_distance / calculate_inception_score of xmcgan/utils/tf_inception_utils.py:
+  the module imports TensorFlow at the top, the three functions are pure numpy / scipy — they are taken out of its
+  source. scipy.linalg.sqrtm lost its `disp` argument in newer releases; the stand-in restores the old return value."""
+  import warnings
+  from scipy import linalg as sl
+  tree = ast.parse(open(f"{REF}/xmcgan/utils/tf_inception_utils.py").read())
+  names = ("_calculate_frechet_distance", "calculate_fid", "calculate_inception_score")
+  body = [n for n in tree.body if (isinstance(n, ast.FunctionDef) and n.name in names) or
+          (isinstance(n, ast.ClassDef) and n.name.endswith("Error"))]
+  linalg = types.SimpleNamespace(sqrtm=lambda a, disp=True: (sl.sqrtm(a), 0.0) if disp is False else sl.sqrtm(a))
+  scope = {"np": np, "linalg": linalg, "warnings": warnings}
+  exec(compile(ast.Module(body=body, type_ignores=[]), "tf_inception_utils.py", "exec"), scope)
+  return scope["calculate_fid"], scope["calculate_inception_score"]
+
+
+def compute():
+  losses, A, image_utils, device_utils, split_input_dict = load_reference()
+  rng = np.random.default_rng(20211017)
+  f32 = np.float32
+  B, R, L, D = 4, 16, 6, 8
+  out = {}
+  region = rng.normal(size=(B, R, D)).astype(f32)
+  words = (rng.normal(size=(B, L, D)) * 0.7).astype(f32)
+  max_len = np.array([[3.0], [6.0], [2.0], [5.0]], f32)
+  out.update(region=region, words=words, max_len=max_len)
+  # word_loss: (loss, accuracy, entropy), default gammas
+  out["word_loss"] = np.array([float(v) for v in A.word_loss(region, words, max_len)], np.float64)
+  # contrastive_loss on sentence / image features
+  img, cond = rng.normal(size=(B, D)).astype(f32), rng.normal(size=(B, D)).astype(f32)
+  out.update(img=img, cond=cond)
+  out["contrastive_loss"] = np.array([float(v) for v in A.contrastive_loss(img, cond)], np.float64)
+  out["contrastive_loss_t05_nonorm"] = np.array(
+      [float(v) for v in A.contrastive_loss(img, cond, l2_norm=False, temperature=0.5)], np.float64)
+  # attention (per-word region context) and attention_for_g (per-region word context) with padding masks
+  mask = (np.arange(L, dtype=f32)[None, :] >= max_len).astype(f32)[:, None, :].repeat(R, 1)     # [B, R, L]
+  out["mask"] = mask
+  out["attention_ctx"] = A.attention(region, words, 5.0, mask).astype(f32)
+  out["attention_ctx_nomask"] = A.attention(region, words, 5.0).astype(f32)
+  ctx, attn = A.attention_for_g(region, words, 15.0, mask)
+  out["attention_for_g_ctx"], out["attention_for_g_attn"] = ctx.astype(f32), attn.astype(f32)
+  out["l2_normalize"] = A.l2_normalize(region, -1).astype(f32)
+  out["cosine_similarity"] = A.cosine_similarity(words, out["attention_ctx"]).astype(f32)
+  logits = (rng.normal(size=(B, B)) * 3).astype(f32)
+  labels = np.eye(B, dtype=f32)
+  out["logits"] = logits
+  out["get_statistics"] = np.array([float(v) for v in A.get_statistics(logits, labels)], np.float64)
+  out["tf_cross_entropy"] = losses.tf_cross_entropy_loss_with_logits(labels=labels, logits=logits).astype(f32)
+  out["cross_entropy_int"] = losses.cross_entropy_loss_with_logits(labels=np.arange(B), logits=logits).astype(f32)
+  real_logit, fake_logit = rng.normal(size=(B, 1)).astype(f32), rng.normal(size=(B, 1)).astype(f32)
+  out.update(real_logit=real_logit, fake_logit=fake_logit)
+  out["hinge_loss"] = np.array([float(v) for v in losses.hinge_loss(real_logit, fake_logit)], np.float64)
+  out["hinge_loss_d"] = np.array([float(losses.hinge_loss_d(real_logit, fake_logit))], np.float64)
+  out["hinge_loss_g"] = np.array([float(losses.hinge_loss_g(fake_logit))], np.float64)
+  # host helpers
+  samples = rng.random(size=(10, 4, 6, 3)).astype(f32)
+  out["grid_samples"] = samples
+  out["make_grid_9"] = image_utils.make_grid(samples, 9)
+  out["make_grid_64"] = image_utils.make_grid(samples, 64)     # cut to the batch: 3 x 3 of 10
+  out["device_groups_8_16_4"] = np.array(device_utils.get_device_groups(16, 4))     # 8 devices, groups of 4
+  out["device_groups_8_8_4"] = np.array(device_utils.get_device_groups(8, 4))       # groups of 2
+  # FID / Inception score statistics (tf_inception_utils.py:123-224)
+  calculate_fid, calculate_inception_score = load_reference_fid()
+  pool1 = rng.normal(size=(300, 12))
+  pool2 = rng.normal(size=(260, 12)) * 1.5 + 0.3
+  preds = rng.random(size=(205, 7)) ** 3 + 1e-3
+  preds = preds / preds.sum(1, keepdims=True)
+  out.update(fid_pool1=pool1, fid_pool2=pool2, is_preds=preds)
+  out["fid"] = np.array([calculate_fid(pool1, pool2), calculate_fid(pool1, pool1)], np.float64)
+  out["inception_score_10"] = np.array(calculate_inception_score(preds, 10), np.float64)
+  out["inception_score_1"] = np.array(calculate_inception_score(preds, 1), np.float64)
+  parts = split_input_dict({"a": np.arange(24, dtype=f32).reshape(8, 3), "b": np.arange(8)}, 2)
+  out["split_a0"], out["split_a1"], out["split_b1"] = parts[0]["a"], parts[1]["a"], parts[1]["b"]
+  return out
+
+
+if __name__ == "__main__":
+  np.savez_compressed(OUT, **compute())
+  print("wrote", OUT)

@@ -1,0 +1,92 @@
+"""The oracle — and the product's host-side helpers — against outputs of THE REFERENCE'S OWN CODE
+(tests/golden/reference_libml.npz, made by tests/golden/make_reference_golden.py: xmcgan/libml/losses.py,
+xmcgan/libml/attention_lib.py, utils/image_utils.make_grid, utils/device_utils.get_device_groups and
+train_utils.split_input_dict executed from /root/reference on a numpy stand-in for the few `jax` entry points they
+use). This pins the loss / attention layer of oracle/xmc_oracle.py to the reference itself rather than to a reading of
+it: float32 throughout, 2e-6 relative (summation order). The fixture travels; /root/reference is not read here."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import xmc_oracle as orc
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_libml.npz"))
+T = lambda k: torch.from_numpy(G[k])
+
+
+def close(got, want, tol=2e-6):
+  got = np.asarray([float(v) for v in got]) if isinstance(got, (tuple, list)) else np.asarray(got, np.float64)
+  want = np.asarray(want, np.float64)
+  assert got.shape == want.shape, (got.shape, want.shape)
+  assert np.max(np.abs(got - want)) <= tol * max(1.0, np.max(np.abs(want))), np.max(np.abs(got - want))
+
+
+def test_word_loss_matches_the_reference_code():
+  # (loss, accuracy, entropy): attention_lib.py:130-191 incl. the region-axis softmax, the -1e9 masks, un-normalised
+  # words in the cosine, logsumexp over words, both cross-entropy directions
+  close(orc.word_loss(T("region"), T("words"), T("max_len")), G["word_loss"], 5e-6)
+
+
+def test_contrastive_loss_matches_the_reference_code():
+  close(orc.contrastive_loss(T("img"), T("cond")), G["contrastive_loss"])
+  close(orc.contrastive_loss(T("img"), T("cond"), l2_norm=False, temperature=0.5), G["contrastive_loss_t05_nonorm"])
+
+
+def test_attention_functions_match_the_reference_code():
+  close(orc.attention(T("region"), T("words"), 5.0, T("mask")), G["attention_ctx"])
+  close(orc.attention(T("region"), T("words"), 5.0), G["attention_ctx_nomask"])
+  ctx, attn = orc.attention_for_g(T("region"), T("words"), 15.0, T("mask"))
+  close(ctx, G["attention_for_g_ctx"])
+  close(attn, G["attention_for_g_attn"])
+  # padded words carry exactly zero weight in the reference too (exp(-1e9) underflows)
+  assert (G["attention_for_g_attn"][0, :, 3:] == 0).all() and (attn[0, :, 3:] == 0).all()
+  close(orc.l2_normalize(T("region"), -1), G["l2_normalize"])
+  close(orc.cosine_similarity(T("words"), T("attention_ctx")), G["cosine_similarity"])
+
+
+def test_losses_match_the_reference_code():
+  labels = torch.eye(4)
+  close(orc.tf_cross_entropy_loss_with_logits(labels, T("logits")), G["tf_cross_entropy"])
+  # the integer-label form (losses.py:38-44) is the one-hot form on the diagonal labels
+  close(orc.tf_cross_entropy_loss_with_logits(labels, T("logits"))[:, None], G["cross_entropy_int"])
+  close(orc.get_statistics(T("logits"), labels), G["get_statistics"])
+  d, g = orc.hinge_loss(T("real_logit"), T("fake_logit"))
+  close([d, g], G["hinge_loss"])
+  # hinge_loss_d / hinge_loss_g (losses.py:20-27) are the two halves of hinge_loss
+  close([d], G["hinge_loss_d"], 1e-6)
+  close([g], G["hinge_loss_g"])
+
+
+def test_host_helpers_match_the_reference_code():
+  from xmcgan_image_generation_b200 import parallel, train_utils
+  samples = T("grid_samples")
+  assert np.array_equal(train_utils.make_grid(samples, 9).numpy(), G["make_grid_9"])
+  assert np.array_equal(train_utils.make_grid(samples, 64).numpy(), G["make_grid_64"])
+  assert parallel.get_device_groups(16, 4, device_count=8) == G["device_groups_8_16_4"].tolist()
+  assert parallel.get_device_groups(8, 4, device_count=8) == G["device_groups_8_8_4"].tolist()
+  a, b = torch.arange(24, dtype=torch.float32).reshape(8, 3), torch.arange(8)
+  for split in (train_utils.split_input_dict, orc.split_input_dict):
+    parts = split({"a": a, "b": b}, 2)
+    assert np.array_equal(np.asarray(parts[0]["a"]), G["split_a0"]) and np.array_equal(np.asarray(parts[1]["a"]), G["split_a1"])
+    assert np.array_equal(np.asarray(parts[1]["b"]), G["split_b1"])
+
+
+def test_fixture_is_what_the_reference_produces_today():
+  """In the build container (where /root/reference exists) the committed fixture is regenerated and compared, so it
+  cannot drift from the reference's code; elsewhere the check is skipped."""
+  if not os.path.isdir("/root/reference/xmcgan"):
+    pytest.skip("/root/reference is not present on this machine")
+  import subprocess
+  import sys
+  code = ("import numpy as np; from tests.golden import make_reference_golden as m; d = m.compute(); "
+          f"g = np.load({m_path!r}); "
+          "assert sorted(d) == sorted(g.files); "
+          "assert all(np.array_equal(np.asarray(d[k]), g[k]) for k in g.files); print('same')")
+  out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+  assert out.returncode == 0 and "same" in out.stdout, out.stderr[-2000:]
+
+
+m_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_libml.npz")
