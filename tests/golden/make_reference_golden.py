@@ -170,6 +170,107 @@ def compute():
   return out
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# The networks: xmcgan/nets/xmc_net.py + nets/common.py + libml/layers.py executed on tests/golden/flax_stand_in.py
+# ---------------------------------------------------------------------------------------------------------------------
+OUT_NETS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_nets.npz")
+NET_CFG = dict(gf_dim=8, df_dim=8, z_dim=8, batch_size=4)   # the narrowest widths the product's layouts accept
+NET_E, NET_L, NET_B = 8, 5, 2
+
+
+def load_reference_nets():
+  """xmc_net of the reference on the numpy stand-ins for jax and flax.linen."""
+  from tests.golden import flax_stand_in
+  losses, attention_lib, image_utils, device_utils, _ = load_reference()
+  flax_stand_in.install(sys.modules["jax"], sys.modules)
+  sys.modules.setdefault("xmcgan.nets", types.ModuleType("xmcgan.nets"))
+  sys.modules["xmcgan.libml"].attention_lib = attention_lib
+  sys.modules["xmcgan.utils"].device_utils = device_utils
+  layers = _load("xmcgan.libml.layers", f"{REF}/xmcgan/libml/layers.py")
+  sys.modules["xmcgan.libml"].layers = layers
+  common = _load("xmcgan.nets.common", f"{REF}/xmcgan/nets/common.py")
+  sys.modules["xmcgan.nets"].common = common
+  return _load("xmcgan.nets.xmc_net", f"{REF}/xmcgan/nets/xmc_net.py")
+
+
+def flatten(tree, prefix=""):
+  out = {}
+  for k, v in tree.items():
+    if isinstance(v, dict):
+      out.update(flatten(v, f"{prefix}{k}/"))
+    else:
+      out[prefix + k] = np.asarray(v, np.float32)
+  return out
+
+
+def unflatten(flat):
+  tree = {}
+  for key, v in flat.items():
+    node = tree
+    parts = key.split("/")
+    for p in parts[:-1]:
+      node = node.setdefault(p, {})
+    node[parts[-1]] = v
+  return tree
+
+
+def net_inputs(**overrides):
+  """Config, variables (the product's own initialiser: same Flax tree names as the reference expects) and a batch."""
+  import torch
+  from tests import helpers
+  cfg = helpers.small_config(**dict(NET_CFG, **overrides))
+  _, _, g_vars, d_vars = helpers.cpu_variables(cfg, E=NET_E, seed=21)
+  to_np = lambda t: {k: to_np(v) if isinstance(v, dict) else v.detach().numpy().astype(np.float32) for k, v in t.items()}
+  g_vars, d_vars = to_np(g_vars), to_np(d_vars)
+  # running statistics that are not the initial (0, 1): the eval-mode pass must really use them
+  rng = np.random.default_rng(5)
+  for k, v in flatten(g_vars["batch_stats"]).items():
+    v += (rng.normal(size=v.shape) * 0.1).astype(np.float32) if k.endswith("mean") else \
+        (rng.random(size=v.shape) * 0.5).astype(np.float32)
+  batch = {k: v.numpy().astype(np.float32) for k, v in helpers.make_batch(NET_B, cfg, E=NET_E, L=NET_L, seed=4).items()}
+  return cfg, g_vars, d_vars, batch
+
+
+def compute_nets():
+  xmc_net = load_reference_nets()
+  cfg, g_vars, d_vars, batch = net_inputs()
+  # the weights are rebuilt from their seed by net_inputs() (they would make the fixture several MB): the fixture keeps
+  # one checksum pair per tree so that a change of the initialiser shows up as such, not as a parity failure
+  out = {"cfg/" + k: np.array(v) for k, v in NET_CFG.items()}
+  for name, tree in (("g_vars", g_vars), ("d_vars", d_vars), ("batch", batch)):
+    leaves = flatten(tree)
+    out["checksum/" + name] = np.array([sum(float(v.astype(np.float64).sum()) for v in leaves.values()),
+                                        sum(float(np.abs(v.astype(np.float64)).sum()) for v in leaves.values())])
+  z = batch["z"]
+  # Generator: train mode (batch statistics, new running averages) and inference mode (running averages)
+  img, g_new = xmc_net.Generator(config=cfg, train=True).apply(g_vars, (batch, z), mutable=["batch_stats"])
+  out["g_train/image"] = img
+  out.update({"g_train/new/" + k: v for k, v in flatten(g_new).items()})
+  out["g_eval/image"] = xmc_net.Generator(config=cfg, train=False).apply(g_vars, (batch, z), mutable=False)
+  # Discriminator on [real; fake] (train mode: the power-iteration vectors advance)
+  both = np.concatenate([batch["image"], img], axis=0)
+  (logit, stats), d_new = xmc_net.Discriminator(config=cfg, train=True).apply(
+      d_vars, (both, batch), mutable=["spectral_norm_stats"])
+  out["d_train/logit"] = logit
+  out.update({"d_train/stats/" + k: np.array(float(v), np.float64) for k, v in stats.items()})
+  out.update({"d_train/new/" + k: v for k, v in flatten(d_new).items()})
+  (logit_e, _) = xmc_net.Discriminator(config=cfg, train=False).apply(d_vars, (both, batch), mutable=False)
+  out["d_eval/logit"] = logit_e
+  # variant: spectrally normalised generator (every conv / dense of G through layers.SpectralConv / SpectralDense, its
+  # own spectral_norm_stats collection); the image is kept at every 4th pixel to keep the fixture small
+  cfg2, g2, _, batch2 = net_inputs(g_spectral_norm=True)
+  leaves = flatten(g2)
+  out["checksum/g_vars_sn"] = np.array([sum(float(v.astype(np.float64).sum()) for v in leaves.values()),
+                                        sum(float(np.abs(v.astype(np.float64)).sum()) for v in leaves.values())])
+  img2, new2 = xmc_net.Generator(config=cfg2, train=True).apply(g2, (batch2, batch2["z"]),
+                                                               mutable=["batch_stats", "spectral_norm_stats"])
+  out["g_sn_train/image_s4"] = img2[:, ::4, ::4]
+  out.update({"g_sn_train/new/" + k: v for k, v in flatten(new2).items()})
+  return out
+
+
 if __name__ == "__main__":
   np.savez_compressed(OUT, **compute())
   print("wrote", OUT)
+  np.savez_compressed(OUT_NETS, **compute_nets())
+  print("wrote", OUT_NETS, os.path.getsize(OUT_NETS), "bytes")

@@ -83,10 +83,90 @@ def test_fixture_is_what_the_reference_produces_today():
   code = ("import numpy as np; from tests.golden import make_reference_golden as m; d = m.compute(); "
           f"g = np.load({m_path!r}); "
           "assert sorted(d) == sorted(g.files); "
-          "assert all(np.array_equal(np.asarray(d[k]), g[k]) for k in g.files); print('same')")
+          "assert all(np.array_equal(np.asarray(d[k]), g[k]) for k in g.files); "
+          "d = m.compute_nets(); g = np.load(m.OUT_NETS); assert sorted(d) == sorted(g.files); "
+          "assert all(np.allclose(np.asarray(d[k]), g[k], rtol=1e-6, atol=1e-7) for k in g.files); print('same')")
   out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True,
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
   assert out.returncode == 0 and "same" in out.stdout, out.stderr[-2000:]
 
 
 m_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_libml.npz")
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# The networks: oracle.generator_apply / discriminator_apply against the reference's own xmc_net.py / common.py /
+# layers.py executed on the numpy stand-in for flax.linen (tests/golden/flax_stand_in.py)
+# ----------------------------------------------------------------------------------------------------------------------
+N = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_nets.npz"))
+
+
+def _net_inputs():
+  from tests.golden import make_reference_golden as m
+  cfg, g_vars, d_vars, batch = m.net_inputs()
+  for name, tree in (("g_vars", g_vars), ("d_vars", d_vars), ("batch", batch)):
+    leaves = m.flatten(tree)
+    got = [sum(float(v.astype(np.float64).sum()) for v in leaves.values()),
+           sum(float(np.abs(v.astype(np.float64)).sum()) for v in leaves.values())]
+    assert np.allclose(got, N["checksum/" + name], rtol=1e-9), f"{name}: the seeded inputs changed, regenerate the fixture"
+  to_t = lambda t: {k: to_t(v) if isinstance(v, dict) else torch.from_numpy(v) for k, v in t.items()}
+  return cfg, to_t(g_vars), to_t(d_vars), to_t(batch), m
+
+
+def test_generator_matches_the_reference_network_code():
+  """Image in train mode (batch statistics) and in inference mode (running averages), and every new running average,
+  against the reference's Generator / GenBlock / GenSpatialBlock / (Local)ConditionalBatchNorm / attention_for_g code
+  run on the stand-in. That the reference's code finds every parameter under the product's tree names is part of the
+  check (the fixture could not have been generated otherwise)."""
+  cfg, g_vars, _, batch, m = _net_inputs()
+  img, new = orc.generator_apply(g_vars, (batch, batch["z"]), cfg, True, orc.FP32)
+  close(img, N["g_train/image"], 2e-5)
+  got = m.flatten({k: v for k, v in new.items()})
+  want = {k[len("g_train/new/"):]: N[k] for k in N.files if k.startswith("g_train/new/")}
+  assert sorted(got) == sorted(want)
+  for k in want:
+    close(got[k], want[k], 2e-5)
+  img_e, _ = orc.generator_apply(g_vars, (batch, batch["z"]), cfg, False, orc.FP32)
+  close(img_e, N["g_eval/image"], 2e-5)
+  assert np.abs(N["g_eval/image"] - N["g_train/image"]).max() > 1e-3     # the two modes really differ
+
+
+def test_spectrally_normalised_generator_matches_the_reference_network_code():
+  """config.g_spectral_norm = True: every generator layer through the reference's layers.SpectralConv /
+  SpectralDense; image, new running averages and new power-iteration vectors."""
+  from tests.golden import make_reference_golden as m
+  cfg, g_vars, _, batch = m.net_inputs(g_spectral_norm=True)
+  leaves = m.flatten(g_vars)
+  got = [sum(float(v.astype(np.float64).sum()) for v in leaves.values()),
+         sum(float(np.abs(v.astype(np.float64)).sum()) for v in leaves.values())]
+  assert np.allclose(got, N["checksum/g_vars_sn"], rtol=1e-9)
+  to_t = lambda t: {k: to_t(v) if isinstance(v, dict) else torch.from_numpy(v) for k, v in t.items()}
+  g_vars, batch = to_t(g_vars), to_t(batch)
+  img, new = orc.generator_apply(g_vars, (batch, batch["z"]), cfg, True, orc.FP32)
+  close(img[:, ::4, ::4], N["g_sn_train/image_s4"], 5e-5)
+  got = m.flatten({k: v for k, v in new.items()})
+  want = {k[len("g_sn_train/new/"):]: N[k] for k in N.files if k.startswith("g_sn_train/new/")}
+  assert sorted(got) == sorted(want) and any(k.startswith("spectral_norm_stats/") for k in want)
+  for k in want:
+    close(got[k], want[k], 5e-5)
+
+
+def test_discriminator_matches_the_reference_network_code():
+  """Logits, all 15 entries of the statistics dictionary (word / sentence / image contrastive losses, accuracies,
+  entropies) and every advanced power-iteration vector, on [real; fake] with the fake half taken from the fixture."""
+  cfg, _, d_vars, batch, m = _net_inputs()
+  both = torch.cat([batch["image"], torch.from_numpy(N["g_train/image"])], 0)
+  (logit, stats), new = orc.discriminator_apply(d_vars, (both, batch), cfg, True, orc.FP32)
+  close(logit, N["d_train/logit"], 5e-5)
+  want_stats = {k[len("d_train/stats/"):]: float(N[k]) for k in N.files if k.startswith("d_train/stats/")}
+  assert len(want_stats) == 15
+  for k, v in want_stats.items():
+    assert k in stats, k
+    assert abs(float(stats[k]) - v) <= 5e-5 * max(1.0, abs(v)), (k, float(stats[k]), v)
+  got = m.flatten({k: v for k, v in new.items()})
+  want = {k[len("d_train/new/"):]: N[k] for k in N.files if k.startswith("d_train/new/")}
+  assert sorted(got) == sorted(want)
+  for k in want:
+    close(got[k], want[k], 2e-5)
+  (logit_e, _), _ = orc.discriminator_apply(d_vars, (both, batch), cfg, False, orc.FP32)
+  close(logit_e, N["d_eval/logit"], 5e-5)
