@@ -4,16 +4,17 @@ This file is a plain torch-CPU (fp32) restatement of the reference algorithm. It
 `__graft_entry__.smoke()` and the `cpu_baseline` / `--impl reference` legs of `bench.py`; nothing in the product
 package (`xmcgan_image_generation_b200/`) imports it and it must never be used as a fallback compute path.
 
-PARITY, two tiers. (a) The loss / attention layer below (losses.py and attention_lib.py: hinge losses, cross-entropies,
-l2_normalize, cosine_similarity, get_statistics, contrastive_loss, attention, attention_for_g, word_loss) and
-split_input_dict are PINNED against outputs of the reference's own code: tests/golden/make_reference_golden.py executes
-those modules from /root/reference on a numpy stand-in for the few `jax` entry points they use, the results are
-committed as tests/golden/reference_libml.npz and tests/test_reference_golden.py holds this file to them at 2e-6.
-(b) Everything that needs Flax to run — the networks, spectral norm, BatchNorm, the backward passes, Adam, the ResNet —
-is PARITY UNPINNED BY UPSTREAM: the reference (JAX/Flax, not installable here: no jax/flax/clu/ml_collections wheels,
-no network) ships no golden vectors or numeric tests for this path. That part is pinned by (1) analytic
-known-answer tests in tests/test_oracle.py, (2) gradient checks against torch autograd of the same restatement, and
-(3) line-by-line citations below. Gradients are produced by torch autograd over this restatement.
+PARITY, two tiers. (a) The FORWARD pass is PINNED against outputs of the reference's own code: tests/golden/
+make_reference_golden.py executes the reference's losses.py, attention_lib.py, nets/xmc_net.py, nets/common.py and
+libml/layers.py from /root/reference on numpy stand-ins for the `jax` entry points and the slice of `flax.linen` they
+use (tests/golden/flax_stand_in.py); the results are committed as tests/golden/reference_libml.npz /
+reference_nets.npz and tests/test_reference_golden.py holds this file to them — losses and attention at 2e-6,
+generator_apply / discriminator_apply (train and inference mode, all statistics, state updates) at 2e-5 / 5e-5.
+(b) What needs JAX itself — jax.grad through the networks, flax.optim.Adam, the Flax ResNet-50 — is PARITY UNPINNED BY
+UPSTREAM: the reference (JAX/Flax, not installable here: no jax/flax/clu/ml_collections wheels, no network) ships no
+golden vectors or numeric tests for this path (SURVEY.md §4). The backward is torch autograd over the pinned forward;
+it, Adam and the ResNet are pinned by (1) analytic known-answer tests in tests/test_oracle.py, (2) finite-difference
+gradient checks, and (3) line-by-line citations below.
 
 Every function cites the reference file:line it follows (paths relative to /root/reference).
 
