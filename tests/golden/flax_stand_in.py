@@ -1,5 +1,5 @@
 """A numpy-backed, apply-only stand-in for the slice of `flax.linen` / `jax` that the reference's network code uses
-(xmcgan/nets/xmc_net.py, xmcgan/nets/common.py, xmcgan/libml/layers.py), so that THOSE FILES can be executed from
+(xmcgan/nets/xmc_net.py, xmcgan/nets/common.py, xmcgan/libml/layers.py, xmcgan/utils/resnet_v1.py), so that THOSE FILES can be executed from
 /root/reference without JAX / Flax (neither is installable here). Test infrastructure, used only by
 tests/golden/make_reference_golden.py.
 
@@ -10,7 +10,7 @@ statistics, up / down-sampling calls, every reshape / tile / concatenate — and
 parameters (a `self.param` looks its value up under the path the call order produces: a naming mismatch is a KeyError).
 
 What is restated here (from flax 0.3.3 / jax semantics, the same statements oracle/xmc_oracle.py makes): the
-primitives nn.Conv (NHWC x HWIO, SAME, stride 1), nn.Dense, nn.BatchNorm (mean / mean-of-squares statistics, running
+primitives nn.Conv (NHWC x HWIO, XLA's SAME padding, any stride), nn.max_pool, nn.Dense, nn.BatchNorm (mean / mean-of-squares statistics, running
 averages momentum * old + (1 - momentum) * new, rsqrt(var + eps)), lax.conv_general_dilated / dot_general,
 jax.image.resize(nearest, integer factor), lax.reduce_window(add) 2x2 / stride 2, stop_gradient = identity (forward).
 All arithmetic is numpy float32."""
@@ -22,13 +22,30 @@ import numpy as np
 _STACK = []   # modules whose __call__ is executing, innermost last
 
 
-def conv2d_same(x, kernel):
-  """NHWC x HWIO -> NHWC, stride 1, SAME padding (odd kernels)."""
+def _same_pads(n, k, s):
+  """XLA 'SAME': out = ceil(n / s), total = max((out - 1) * s + k - n, 0), low = total // 2."""
+  total = max((-(-n // s) - 1) * s + k - n, 0)
+  return total // 2, total - total // 2
+
+
+def conv2d_same(x, kernel, strides=(1, 1)):
+  """NHWC x HWIO -> NHWC, SAME padding as XLA computes it, any stride."""
   kh, kw, cin, cout = kernel.shape
   x = np.asarray(x, np.float32)
-  xp = np.pad(x, ((0, 0), (kh // 2, kh // 2), (kw // 2, kw // 2), (0, 0)))
-  win = np.lib.stride_tricks.sliding_window_view(xp, (kh, kw), axis=(1, 2))   # [N, H, W, C, kh, kw]
+  xp = np.pad(x, ((0, 0), _same_pads(x.shape[1], kh, strides[0]), _same_pads(x.shape[2], kw, strides[1]), (0, 0)))
+  win = np.lib.stride_tricks.sliding_window_view(xp, (kh, kw), axis=(1, 2))[:, ::strides[0], ::strides[1]]
   return np.einsum("nhwcij,ijco->nhwo", win, np.asarray(kernel, np.float32), optimize=True).astype(np.float32)
+
+
+def max_pool(x, window_shape, strides=None, padding="VALID"):
+  """flax.linen.max_pool on NHWC: lax.reduce_window(max) with -inf padding."""
+  strides = strides or (1, 1)
+  assert padding == "SAME"
+  xp = np.pad(np.asarray(x, np.float32), ((0, 0), _same_pads(x.shape[1], window_shape[0], strides[0]),
+                                          _same_pads(x.shape[2], window_shape[1], strides[1]), (0, 0)),
+              constant_values=-np.inf)
+  win = np.lib.stride_tricks.sliding_window_view(xp, tuple(window_shape), axis=(1, 2))[:, ::strides[0], ::strides[1]]
+  return win.max(axis=(-2, -1))
 
 
 class _Ctx:
@@ -156,9 +173,9 @@ class Conv(Module):
   bias_init: object = None
 
   def __call__(self, inputs):
-    assert self.padding == "SAME" and not self.strides and self.feature_group_count == 1
+    assert self.padding == "SAME" and self.feature_group_count == 1
     kernel = self.param("kernel", None, tuple(self.kernel_size) + (inputs.shape[-1], self.features))
-    y = conv2d_same(inputs, kernel)
+    y = conv2d_same(inputs, kernel, tuple(self.strides) if self.strides else (1, 1))
     return y + self.param("bias", None, (self.features,)) if self.use_bias else y
 
 
@@ -259,6 +276,7 @@ def install(jax, sys_modules):
   linit.lecun_normal = linit.normal = lambda *a, **k: None
   linit.zeros = None
   linen.initializers = linit
+  linen.max_pool = max_pool
   flax = types.ModuleType("flax")
   flax.linen = linen
   mlc = types.ModuleType("ml_collections")

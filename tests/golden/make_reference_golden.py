@@ -269,8 +269,34 @@ def compute_nets():
   return out
 
 
+def resnet_inputs():
+  """Synthetic frozen weights (oracle.resnet50_random_variables: the reference's checkpoint is not shipped) and two
+  224 x 224 images (the bilinear resize in front of the network is jax.image.resize, not reference code)."""
+  from oracle import xmc_oracle as orc
+  variables = orc.resnet50_random_variables(seed=3)
+  to_np = lambda t: {k: to_np(v) if isinstance(v, dict) else v.numpy().astype(np.float32) for k, v in t.items()}
+  images = np.random.default_rng(9).random(size=(2, 224, 224, 3)).astype(np.float32)
+  return to_np(variables), images
+
+
+def compute_resnet():
+  """utils/resnet_v1.py (ResNet50 = ResNet + ResNetStage + BottleneckResNetBlock) in inference mode on the stand-in."""
+  load_reference_nets()
+  resnet_v1 = _load("xmcgan.utils.resnet_v1", f"{REF}/xmcgan/utils/resnet_v1.py")
+  variables, images = resnet_inputs()
+  pool, logits = resnet_v1.ResNet50(num_classes=1000).apply(variables, images, mutable=False, train=False)
+  leaves = flatten(variables)
+  return {"resnet/checksum": np.array([sum(float(v.astype(np.float64).sum()) for v in leaves.values()),
+                                       sum(float(np.abs(v.astype(np.float64)).sum()) for v in leaves.values()),
+                                       float(images.astype(np.float64).sum())]),
+          "resnet/pool_shape": np.array(pool.shape), "resnet/pool_c16": pool[..., ::16].astype(np.float32),
+          "resnet/pool_mean": pool.mean(axis=(1, 2)).astype(np.float32), "resnet/logits": logits.astype(np.float32)}
+
+
 if __name__ == "__main__":
   np.savez_compressed(OUT, **compute())
   print("wrote", OUT)
-  np.savez_compressed(OUT_NETS, **compute_nets())
+  nets = compute_nets()
+  nets.update(compute_resnet())
+  np.savez_compressed(OUT_NETS, **nets)
   print("wrote", OUT_NETS, os.path.getsize(OUT_NETS), "bytes")

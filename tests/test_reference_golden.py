@@ -84,7 +84,7 @@ def test_fixture_is_what_the_reference_produces_today():
           f"g = np.load({m_path!r}); "
           "assert sorted(d) == sorted(g.files); "
           "assert all(np.array_equal(np.asarray(d[k]), g[k]) for k in g.files); "
-          "d = m.compute_nets(); g = np.load(m.OUT_NETS); assert sorted(d) == sorted(g.files); "
+          "d = m.compute_nets(); d.update(m.compute_resnet()); g = np.load(m.OUT_NETS); assert sorted(d) == sorted(g.files); "
           "assert all(np.allclose(np.asarray(d[k]), g[k], rtol=1e-6, atol=1e-7) for k in g.files); print('same')")
   out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True,
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -170,3 +170,22 @@ def test_discriminator_matches_the_reference_network_code():
     close(got[k], want[k], 2e-5)
   (logit_e, _), _ = orc.discriminator_apply(d_vars, (both, batch), cfg, False, orc.FP32)
   close(logit_e, N["d_eval/logit"], 5e-5)
+
+
+def test_resnet50_matches_the_reference_network_code():
+  """oracle.resnet50_apply (the frozen feature branch, inference-mode BatchNorm) against the reference's
+  utils/resnet_v1.py — ResNet / ResNetStage / BottleneckResNetBlock with their explicit layer names, the stride on the
+  3x3 convolution, no ReLU after init_bn, max_pool 3x3 / 2 SAME, global mean, head — run on the stand-in with the same
+  synthetic weights and 224 x 224 images: pooled features and logits."""
+  from tests.golden import make_reference_golden as m
+  variables, images = m.resnet_inputs()
+  leaves = m.flatten(variables)
+  got = [sum(float(v.astype(np.float64).sum()) for v in leaves.values()),
+         sum(float(np.abs(v.astype(np.float64)).sum()) for v in leaves.values()), float(images.astype(np.float64).sum())]
+  assert np.allclose(got, N["resnet/checksum"], rtol=1e-9), "the seeded ResNet inputs changed, regenerate the fixture"
+  to_t = lambda t: {k: to_t(v) if isinstance(v, dict) else torch.from_numpy(v) for k, v in t.items()}
+  pool, logits = orc.resnet50_apply(to_t(variables), torch.from_numpy(images), orc.FP32)
+  assert tuple(pool.shape) == tuple(N["resnet/pool_shape"]) == (2, 7, 7, 2048)
+  close(pool[..., ::16], N["resnet/pool_c16"], 5e-5)
+  close(pool.mean(dim=(1, 2)), N["resnet/pool_mean"], 5e-5)
+  close(logits, N["resnet/logits"], 5e-5)
