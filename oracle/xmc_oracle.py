@@ -10,11 +10,13 @@ libml/layers.py and utils/resnet_v1.py from /root/reference on numpy stand-ins f
 use (tests/golden/flax_stand_in.py); the results are committed as tests/golden/reference_libml.npz /
 reference_nets.npz and tests/test_reference_golden.py holds this file to them — losses and attention at 2e-6,
 generator_apply / discriminator_apply (train and inference mode, all statistics, state updates) and resnet50_apply at
-2e-5 / 5e-5. (b) What needs JAX itself — jax.grad through the networks, flax.optim.Adam — is PARITY UNPINNED BY
-UPSTREAM: the reference (JAX/Flax, not installable here: no jax/flax/clu/ml_collections wheels, no network) ships no
-golden vectors or numeric tests for this path (SURVEY.md §4). The backward is torch autograd over the pinned forward;
-it and Adam are pinned by (1) analytic known-answer tests in tests/test_oracle.py, (2) finite-difference
-gradient checks, and (3) line-by-line citations below.
+2e-5 / 5e-5. The BACKWARD pass (torch autograd over that forward) is pinned as well: 19 directional derivatives of d_loss / g_loss
+agree to 1.4e-4 with central differences of the reference's own loss_fn (taken out of xmcgan/xmc_gan.py, executed on
+the stand-ins in float64, jax.lax.stop_gradient honoured by replaying the base run's stopped values).
+(b) PARITY UNPINNED BY UPSTREAM is what is not array code of the reference: flax.optim.Adam.apply_gradient (restated
+from flax 0.3.3), the collectives, jax.image.resize — the reference (JAX/Flax, not installable here) ships no golden
+vectors or numeric tests for this path. Those are pinned by (1) analytic known-answer tests in
+tests/test_oracle.py and (2) line-by-line citations below.
 
 Every function cites the reference file:line it follows (paths relative to /root/reference).
 

@@ -20,6 +20,22 @@ import types
 import numpy as np
 
 _STACK = []   # modules whose __call__ is executing, innermost last
+DTYPE = [np.float32]   # arithmetic type of the primitives; the finite-difference gradient run switches it to float64
+# jax.lax.stop_gradient under finite differences: the base run RECORDS every stopped value, the perturbed runs REPLAY
+# them, so that the difference quotient treats them as the constants jax.grad sees (d stop_gradient(u(w)) / dw = 0)
+SG = {"mode": None, "tape": [], "pos": 0}
+
+
+def stop_gradient(x):
+  if SG["mode"] == "record":
+    SG["tape"].append(np.array(x, copy=True))
+    return x
+  if SG["mode"] == "replay":
+    v = SG["tape"][SG["pos"]]
+    SG["pos"] += 1
+    assert v.shape == np.shape(x)
+    return v
+  return x
 
 
 def _same_pads(n, k, s):
@@ -31,17 +47,17 @@ def _same_pads(n, k, s):
 def conv2d_same(x, kernel, strides=(1, 1)):
   """NHWC x HWIO -> NHWC, SAME padding as XLA computes it, any stride."""
   kh, kw, cin, cout = kernel.shape
-  x = np.asarray(x, np.float32)
+  x = np.asarray(x, DTYPE[0])
   xp = np.pad(x, ((0, 0), _same_pads(x.shape[1], kh, strides[0]), _same_pads(x.shape[2], kw, strides[1]), (0, 0)))
   win = np.lib.stride_tricks.sliding_window_view(xp, (kh, kw), axis=(1, 2))[:, ::strides[0], ::strides[1]]
-  return np.einsum("nhwcij,ijco->nhwo", win, np.asarray(kernel, np.float32), optimize=True).astype(np.float32)
+  return np.einsum("nhwcij,ijco->nhwo", win, np.asarray(kernel, DTYPE[0]), optimize=True).astype(DTYPE[0])
 
 
 def max_pool(x, window_shape, strides=None, padding="VALID"):
   """flax.linen.max_pool on NHWC: lax.reduce_window(max) with -inf padding."""
   strides = strides or (1, 1)
   assert padding == "SAME"
-  xp = np.pad(np.asarray(x, np.float32), ((0, 0), _same_pads(x.shape[1], window_shape[0], strides[0]),
+  xp = np.pad(np.asarray(x, DTYPE[0]), ((0, 0), _same_pads(x.shape[1], window_shape[0], strides[0]),
                                           _same_pads(x.shape[2], window_shape[1], strides[1]), (0, 0)),
               constant_values=-np.inf)
   win = np.lib.stride_tricks.sliding_window_view(xp, tuple(window_shape), axis=(1, 2))[:, ::strides[0], ::strides[1]]
@@ -80,7 +96,7 @@ class _Variable:
 
   @value.setter
   def value(self, v):
-    self._ctx.put(self._col, self._path, np.asarray(v, np.float32))
+    self._ctx.put(self._col, self._path, np.asarray(v, DTYPE[0]))
 
 
 def compact(fn):
@@ -143,7 +159,7 @@ class Module:
     pass
 
   def param(self, name, init_fn, *init_args):
-    return np.asarray(self._ctx.get("params", self._path + (name,)), np.float32)
+    return np.asarray(self._ctx.get("params", self._path + (name,)), DTYPE[0])
 
   def variable(self, col, name, init_fn=None, *init_args):
     return _Variable(self._ctx, col, self._path + (name,))
@@ -188,7 +204,7 @@ class Dense(Module):
   bias_init: object = None
 
   def __call__(self, inputs):
-    y = np.matmul(np.asarray(inputs, np.float32), self.param("kernel", None, (inputs.shape[-1], self.features)))
+    y = np.matmul(np.asarray(inputs, DTYPE[0]), self.param("kernel", None, (inputs.shape[-1], self.features)))
     return y + self.param("bias", None, (self.features,)) if self.use_bias else y
 
 
@@ -209,7 +225,7 @@ class BatchNorm(Module):
   def __call__(self, x, use_running_average=None):
     use_ra = self.use_running_average if use_running_average is None else use_running_average
     assert self.axis_name is None, "cross-replica statistics are not part of the stand-in"
-    x = np.asarray(x, np.float32)
+    x = np.asarray(x, DTYPE[0])
     red = tuple(range(x.ndim - 1))
     ra_mean, ra_var = self.variable("batch_stats", "mean"), self.variable("batch_stats", "var")
     if use_ra:
@@ -217,22 +233,22 @@ class BatchNorm(Module):
     else:
       mean = np.mean(x, axis=red)
       var = np.mean(np.square(x), axis=red) - np.square(mean)
-      m = np.float32(self.momentum)
+      m = DTYPE[0](self.momentum)
       new_mean, new_var = m * ra_mean.value + (1 - m) * mean, m * ra_var.value + (1 - m) * var
       ra_mean.value, ra_var.value = new_mean, new_var
-    mul = 1.0 / np.sqrt(var + np.float32(self.epsilon))
+    mul = 1.0 / np.sqrt(var + DTYPE[0](self.epsilon))
     if self.use_scale:
       mul = mul * self.param("scale", None)
     y = (x - mean) * mul
     if self.use_bias:
       y = y + self.param("bias", None)
-    return y.astype(np.float32)
+    return y.astype(DTYPE[0])
 
 
 def install(jax, sys_modules):
   """Adds the lax / image pieces to the jax stand-in of make_reference_golden and registers flax.linen & friends."""
   lax = jax.lax
-  lax.stop_gradient = lambda x: x
+  lax.stop_gradient = stop_gradient
   lax.add = np.add
   lax.Precision = types.SimpleNamespace(HIGHEST=None, DEFAULT=None)
   lax.ConvDimensionNumbers = collections.namedtuple("ConvDimensionNumbers", "lhs_spec rhs_spec out_spec")

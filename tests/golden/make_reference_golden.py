@@ -269,6 +269,106 @@ def compute_nets():
   return out
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Gradients: central differences of the reference's own loss_fn (xmc_gan.train_g_d / train_d), stop_gradient honoured
+# ---------------------------------------------------------------------------------------------------------------------
+GRAD_EPS = 3e-8   # the loss is piecewise smooth (ReLU kinks, B = 2): at 1e-5 kink crossings cost 2 %, below 1e-7 the quotient is stable to 1e-5
+D_LEAVES = ("DiscOptimizedBlock_0/SpectralConv_0/kernel", "DiscBlock_3/SpectralConv_1/kernel",
+            "DiscBlock_1/SpectralConv_2/bias", "SpectralDense_0/kernel", "SpectralDense_1/kernel", "SpectralConv_0/kernel")
+G_LEAVES = ("Dense_0/kernel", "Dense_1/bias", "GenBlock_0/ConditionalBatchNorm_0/Dense_0/kernel",
+            "GenBlock_1/Conv_2/kernel", "GenSpatialBlock_1/LocalConditionalBatchNorm_1/Conv_1/kernel", "Conv_0/kernel",
+            "Conv_1/kernel")
+
+
+def grad_directions(g_params, d_params):
+  """[(name, which network, {leaf path: direction})]: three dense random directions per network and one direction per
+  selected leaf, from a fixed seed over the leaves in sorted order (the test rebuilds exactly these)."""
+  rng = np.random.default_rng(77)
+  out = []
+  for net, params, leaves in (("d", d_params, D_LEAVES), ("g", g_params, G_LEAVES)):
+    flat = flatten(params)
+    for i in range(3):
+      out.append((f"{net}/dense{i}", net, {k: rng.normal(size=flat[k].shape) for k in sorted(flat)}))
+    for leaf in leaves:
+      out.append((f"{net}/{leaf}", net, {leaf: rng.normal(size=flat[leaf].shape)}))
+  return out
+
+
+def reference_loss_fn(xmc_net, losses, cfg, state, batch):
+  """train_g_d's nested loss_fn(params_d, params_g) -> ((d_loss, g_loss), aux) and calculate_contrastive_loss, taken
+  out of xmcgan/xmc_gan.py by their AST nodes and executed with the closure variables of train_g_d supplied as globals
+  (train_d's loss_fn returns the same d_loss: same code up to the unused generator statistics). Float64 throughout:
+  the one `jnp.float32` cast of the logits in that code is mapped to float64 so that differences of 1e-5 survive."""
+  import functools
+  tree = ast.parse(open(f"{REF}/xmcgan/xmc_gan.py").read())
+  top = {n.name: n for n in tree.body if isinstance(n, ast.FunctionDef)}
+  nested = next(n for n in ast.walk(top["train_g_d"]) if isinstance(n, ast.FunctionDef) and n.name == "loss_fn")
+  jnp64 = types.SimpleNamespace(**vars(sys.modules["jax.numpy"]))
+  jnp64.float32 = np.float64
+  scope = {"jnp": jnp64, "jax": sys.modules["jax"], "losses": losses, "state": state, "batch": batch, "rng": None,
+           "config": cfg, "dtype": np.float64, "additional_data": {},
+           "generator": functools.partial(xmc_net.Generator, config=cfg, dtype=np.float64),
+           "discriminator": functools.partial(xmc_net.Discriminator, config=cfg, dtype=np.float64)}
+  exec(compile(ast.Module(body=[top["calculate_contrastive_loss"], nested], type_ignores=[]), "xmc_gan.py", "exec"), scope)
+  return scope["loss_fn"]
+
+
+def compute_grads():
+  """Directional derivatives of d_loss wrt the discriminator's parameters and of g_loss wrt the generator's (the two
+  pull-backs of xmc_gan.py:162-167) by central differences of the reference's loss_fn in float64."""
+  from tests.golden import flax_stand_in as F
+  xmc_net = load_reference_nets()
+  losses = sys.modules["xmcgan.libml.losses"]
+  cfg, g_vars, d_vars, batch = net_inputs()
+  to64 = lambda t: {k: to64(v) if isinstance(v, dict) else np.asarray(v, np.float64) for k, v in t.items()}
+  g_vars, d_vars, batch = to64(g_vars), to64(d_vars), to64(batch)
+  state = types.SimpleNamespace(generator_state={"batch_stats": g_vars["batch_stats"]},
+                                discriminator_state={"spectral_norm_stats": d_vars["spectral_norm_stats"]})
+  loss_fn = reference_loss_fn(xmc_net, losses, cfg, state, batch)
+  F.DTYPE[0] = np.float64
+  try:
+    F.SG.update(mode="record", tape=[], pos=0)
+    (d0, g0), _ = loss_fn(d_vars["params"], g_vars["params"])
+    out = {"grads/base": np.array([float(d0), float(g0)]), "grads/eps": np.array(GRAD_EPS),
+           "grads/stopped_values": np.array(len(F.SG["tape"]))}
+
+    def shifted(params, direction, sign):
+      flat = flatten_any(params)
+      for k, v in direction.items():
+        flat[k] = flat[k] + sign * GRAD_EPS * v
+      return unflatten(flat)
+
+    def losses_at(pd, pg):
+      F.SG.update(mode="replay", pos=0)
+      (d, g), _ = loss_fn(pd, pg)
+      assert F.SG["pos"] == len(F.SG["tape"])
+      return float(d), float(g)
+
+    for name, net, direction in grad_directions(g_vars["params"], d_vars["params"]):
+      if net == "d":
+        plus = losses_at(shifted(d_vars["params"], direction, +1), g_vars["params"])[0]
+        minus = losses_at(shifted(d_vars["params"], direction, -1), g_vars["params"])[0]
+      else:
+        plus = losses_at(d_vars["params"], shifted(g_vars["params"], direction, +1))[1]
+        minus = losses_at(d_vars["params"], shifted(g_vars["params"], direction, -1))[1]
+      out["grads/fd/" + name] = np.array((plus - minus) / (2 * GRAD_EPS))
+  finally:
+    F.DTYPE[0] = np.float32
+    F.SG.update(mode=None, tape=[], pos=0)
+  return out
+
+
+def flatten_any(tree, prefix=""):
+  """flatten() without the float32 cast."""
+  out = {}
+  for k, v in tree.items():
+    if isinstance(v, dict):
+      out.update(flatten_any(v, f"{prefix}{k}/"))
+    else:
+      out[prefix + k] = v
+  return out
+
+
 def resnet_inputs():
   """Synthetic frozen weights (oracle.resnet50_random_variables: the reference's checkpoint is not shipped) and two
   224 x 224 images (the bilinear resize in front of the network is jax.image.resize, not reference code)."""
@@ -298,5 +398,6 @@ if __name__ == "__main__":
   print("wrote", OUT)
   nets = compute_nets()
   nets.update(compute_resnet())
+  nets.update(compute_grads())
   np.savez_compressed(OUT_NETS, **nets)
   print("wrote", OUT_NETS, os.path.getsize(OUT_NETS), "bytes")

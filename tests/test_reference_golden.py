@@ -84,8 +84,8 @@ def test_fixture_is_what_the_reference_produces_today():
           f"g = np.load({m_path!r}); "
           "assert sorted(d) == sorted(g.files); "
           "assert all(np.array_equal(np.asarray(d[k]), g[k]) for k in g.files); "
-          "d = m.compute_nets(); d.update(m.compute_resnet()); g = np.load(m.OUT_NETS); assert sorted(d) == sorted(g.files); "
-          "assert all(np.allclose(np.asarray(d[k]), g[k], rtol=1e-6, atol=1e-7) for k in g.files); print('same')")
+          "d = m.compute_nets(); d.update(m.compute_resnet()); d.update(m.compute_grads()); g = np.load(m.OUT_NETS); assert sorted(d) == sorted(g.files); "
+          "assert all(np.allclose(np.asarray(d[k]), g[k], rtol=1e-4 if k.startswith('grads/fd') else 1e-6, atol=1e-7) for k in g.files); print('same')")
   out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True,
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
   assert out.returncode == 0 and "same" in out.stdout, out.stderr[-2000:]
@@ -189,3 +189,33 @@ def test_resnet50_matches_the_reference_network_code():
   close(pool[..., ::16], N["resnet/pool_c16"], 5e-5)
   close(pool.mean(dim=(1, 2)), N["resnet/pool_mean"], 5e-5)
   close(logits, N["resnet/logits"], 5e-5)
+
+
+def test_gradients_match_finite_differences_of_the_reference_loss_code():
+  """The two pull-backs of xmc_gan.train_g_d (d_loss wrt the discriminator's parameters, g_loss wrt the generator's,
+  xmc_gan.py:162-167; train_d's gradient is the first one) as the oracle's autograd computes them, against central
+  differences (float64, eps 3e-8) of the reference's OWN `loss_fn` — taken out of xmcgan/xmc_gan.py and executed with
+  the reference's networks on the stand-in, `jax.lax.stop_gradient` honoured by replaying the base run's stopped values
+  (the power-iteration vectors u0 / v0 of every spectrally normalised layer) in the perturbed runs. 19 directional
+  derivatives: three dense random directions per network and one per selected leaf (first / deep / shortcut
+  convolutions, both dense heads, the word projections, conditional-BatchNorm gamma / beta layers, the output conv).
+  This pins WHICH parameters each loss differentiates, where stop_gradient cuts, and the BatchNorm-statistics and
+  attention terms of the backward pass — everything autograd derives from the forward pinned above."""
+  from tests.golden import make_reference_golden as m
+  cfg, g_np, d_np, batch_np = m.net_inputs()
+  to_t = lambda t: {k: to_t(v) if isinstance(v, dict) else torch.from_numpy(v) for k, v in t.items()}
+  state = orc.make_state(to_t(g_np), to_t(d_np))
+  r = orc.d_losses_and_grads(state, to_t(batch_np), cfg, orc.FP32, want_g=True)
+  close([r["d_loss"], r["g_loss"]], N["grads/base"], 2e-6)
+  key = lambda p: p if isinstance(p, str) else "/".join(p)
+  grads = {"d": {key(p): g for p, g in orc.tree_leaves(r["d_grad"])},
+           "g": {key(p): g for p, g in orc.tree_leaves(r["g_grad"])}}
+  assert int(N["grads/stopped_values"]) == 40      # u0 and v0 of the discriminator's 20 spectrally normalised layers
+  worst = 0.0
+  for name, net, direction in m.grad_directions(g_np["params"], d_np["params"]):
+    got = sum(float((grads[net][k].double().numpy() * v).sum()) for k, v in direction.items())
+    want = float(N["grads/fd/" + name])
+    err = abs(got - want) / max(abs(want), 0.05)
+    worst = max(worst, err)
+    assert err < 1e-3, (name, got, want)
+  print(f"[oracle autograd vs finite differences of the reference's loss_fn] worst relative difference {worst:.1e}")
