@@ -4,15 +4,16 @@ This file is a plain torch-CPU (fp32) restatement of the reference algorithm. It
 `__graft_entry__.smoke()` and the `cpu_baseline` / `--impl reference` legs of `bench.py`; nothing in the product
 package (`xmcgan_image_generation_b200/`) imports it and it must never be used as a fallback compute path.
 
-PARITY, two tiers. (a) The FORWARD pass is PINNED against outputs of the reference's own code: tests/golden/
-make_reference_golden.py executes the reference's losses.py, attention_lib.py, nets/xmc_net.py, nets/common.py,
-libml/layers.py and utils/resnet_v1.py from /root/reference on numpy stand-ins for the `jax` entry points and the slice of `flax.linen` they
-use (tests/golden/flax_stand_in.py); the results are committed as tests/golden/reference_libml.npz /
-reference_nets.npz and tests/test_reference_golden.py holds this file to them — losses and attention at 2e-6,
-generator_apply / discriminator_apply (train and inference mode, all statistics, state updates) and resnet50_apply at
-2e-5 / 5e-5. The BACKWARD pass (torch autograd over that forward) is pinned as well: 19 directional derivatives of d_loss / g_loss
-agree to 1.4e-4 with central differences of the reference's own loss_fn (taken out of xmcgan/xmc_gan.py, executed on
-the stand-ins in float64, jax.lax.stop_gradient honoured by replaying the base run's stopped values).
+PARITY, two tiers.
+(a) PINNED against the reference's own code. Forward: tests/golden/make_reference_golden.py executes the reference's
+losses.py, attention_lib.py, nets/xmc_net.py, nets/common.py, libml/layers.py and utils/resnet_v1.py from
+/root/reference on numpy stand-ins for the `jax` entry points and the slice of `flax.linen` they use
+(tests/golden/flax_stand_in.py); the results are committed as tests/golden/reference_libml.npz / reference_nets.npz
+and tests/test_reference_golden.py holds this file to them — losses and attention at 2e-6, generator_apply /
+discriminator_apply (train and inference mode, all statistics, state updates) and resnet50_apply at 2e-5 / 5e-5.
+Backward (torch autograd over that forward): 19 directional derivatives of d_loss / g_loss agree to 1.4e-4 with
+central differences of the reference's own loss_fn (taken out of xmcgan/xmc_gan.py, executed on the stand-ins in
+float64, jax.lax.stop_gradient honoured by replaying the base run's stopped values).
 (b) PARITY UNPINNED BY UPSTREAM is what is not array code of the reference: flax.optim.Adam.apply_gradient (restated
 from flax 0.3.3), the collectives, jax.image.resize — the reference (JAX/Flax, not installable here) ships no golden
 vectors or numeric tests for this path. Those are pinned by (1) analytic known-answer tests in
