@@ -266,7 +266,28 @@ def compute_nets():
                                                                mutable=["batch_stats", "spectral_norm_stats"])
   out["g_sn_train/image_s4"] = img2[:, ::4, ::4]
   out.update({"g_sn_train/new/" + k: v for k, v in flatten(new2).items()})
+  # variant: the 256 px configuration (six blocks in both networks, xmc_net.py:81-86,202-205); image every 8th pixel
+  cfg3, g3, d3, batch3 = net_inputs(image_size=256)
+  out["checksum/vars_256"] = checksum(dict(g=g3, d=d3, b=batch3))
+  img3, _ = xmc_net.Generator(config=cfg3, train=True).apply(g3, (batch3, batch3["z"]), mutable=["batch_stats"])
+  (logit3, stats3), _ = xmc_net.Discriminator(config=cfg3, train=True).apply(
+      d3, (np.concatenate([batch3["image"], img3]), batch3), mutable=["spectral_norm_stats"])
+  out["px256/image_s8"], out["px256/image_mean"], out["px256/logit"] = img3[:, ::8, ::8], img3.mean(axis=(1, 2)), logit3
+  out.update({"px256/stats/" + k: np.array(float(v), np.float64) for k, v in stats3.items()})
+  # variants: the contrastive-loss switches of coco_xmc.py off one at a time (discriminator on the 128 px images above)
+  for switch in ("word_contrastive", "sentence_contrastive", "image_contrastive"):
+    cfg4, _, d4, batch4 = net_inputs(**{switch: False})
+    (logit4, stats4), _ = xmc_net.Discriminator(config=cfg4, train=True).apply(
+        d4, (both, batch4), mutable=["spectral_norm_stats"])
+    out[f"no_{switch}/logit"] = logit4
+    out.update({f"no_{switch}/stats/" + k: np.array(float(v), np.float64) for k, v in stats4.items()})
   return out
+
+
+def checksum(tree):
+  leaves = flatten(tree)
+  return np.array([sum(float(v.astype(np.float64).sum()) for v in leaves.values()),
+                   sum(float(np.abs(v.astype(np.float64)).sum()) for v in leaves.values())])
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -219,3 +219,45 @@ def test_gradients_match_finite_differences_of_the_reference_loss_code():
     worst = max(worst, err)
     assert err < 1e-3, (name, got, want)
   print(f"[oracle autograd vs finite differences of the reference's loss_fn] worst relative difference {worst:.1e}")
+
+
+def _stats_close(stats, prefix, tol=5e-5):
+  want = {k[len(prefix):]: float(N[k]) for k in N.files if k.startswith(prefix)}
+  assert len(want) == 15
+  for k, v in want.items():
+    assert abs(float(stats[k]) - v) <= tol * max(1.0, abs(v)), (prefix, k, float(stats[k]), v)
+
+
+def test_256px_configuration_matches_the_reference_network_code():
+  """image_size = 256 (six blocks in both networks, xmc_net.py:81-86,202-205): generated image, discriminator logits
+  and statistics."""
+  from tests.golden import make_reference_golden as m
+  cfg, g_np, d_np, batch_np = m.net_inputs(image_size=256)
+  assert np.allclose(m.checksum(dict(g=g_np, d=d_np, b=batch_np)), N["checksum/vars_256"], rtol=1e-9)
+  to_t = lambda t: {k: to_t(v) if isinstance(v, dict) else torch.from_numpy(v) for k, v in t.items()}
+  g_vars, d_vars, batch = to_t(g_np), to_t(d_np), to_t(batch_np)
+  img, _ = orc.generator_apply(g_vars, (batch, batch["z"]), cfg, True, orc.FP32)
+  assert tuple(img.shape) == (2, 256, 256, 3)
+  close(img[:, ::8, ::8], N["px256/image_s8"], 5e-5)
+  close(img.mean(dim=(1, 2)), N["px256/image_mean"], 5e-5)
+  (logit, stats), _ = orc.discriminator_apply(d_vars, (torch.cat([batch["image"], img.detach()]), batch), cfg, True,
+                                              orc.FP32)
+  close(logit, N["px256/logit"], 1e-4)
+  _stats_close(stats, "px256/stats/", 1e-4)
+
+
+@pytest.mark.parametrize("switch", ["word_contrastive", "sentence_contrastive", "image_contrastive"])
+def test_loss_switches_match_the_reference_network_code(switch):
+  """coco_xmc.py's contrastive-loss switches off one at a time: the discriminator's statistics dictionary (zeros where
+  the reference leaves its initial 0) and logits; without word_contrastive the word projection is not even created."""
+  from tests.golden import make_reference_golden as m
+  cfg, _, d_np, batch_np = m.net_inputs(**{switch: False})
+  to_t = lambda t: {k: to_t(v) if isinstance(v, dict) else torch.from_numpy(v) for k, v in t.items()}
+  d_vars, batch = to_t(d_np), to_t(batch_np)
+  both = torch.cat([batch["image"], torch.from_numpy(N["g_train/image"])], 0)
+  (logit, stats), _ = orc.discriminator_apply(d_vars, (both, batch), cfg, True, orc.FP32)
+  close(logit, N[f"no_{switch}/logit"], 5e-5)
+  _stats_close(stats, f"no_{switch}/stats/")
+  zeroed = {"word_contrastive": "real_word_loss", "sentence_contrastive": "fake_sentence_loss",
+            "image_contrastive": "image_contrastive_loss"}[switch]
+  assert float(N[f"no_{switch}/stats/{zeroed}"]) == 0.0 and float(stats[zeroed]) == 0.0
