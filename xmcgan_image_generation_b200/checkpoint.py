@@ -23,7 +23,6 @@ import re
 
 import msgpack
 import numpy as np
-import torch
 
 EXT_NDARRAY, EXT_NATIVE_COMPLEX, EXT_NPSCALAR = 1, 2, 3
 

@@ -10,7 +10,6 @@ xmcgan/libml/attention_lib.py:46-219. Differences that are exact in real arithme
     discriminator has no cross-example op, so the real half cannot reach the generator).
 """
 import collections
-import ctypes
 import math
 
 import numpy as np
