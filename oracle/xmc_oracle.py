@@ -29,6 +29,7 @@ keeps MORE precision than the reference's bf16 graph (fp32 logit head, fp32 pre-
 follows the pipeline; those spots are marked "B200 path" below.
 """
 import math
+
 import torch
 import torch.nn.functional as F
 
